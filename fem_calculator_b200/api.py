@@ -1,0 +1,170 @@
+"""Thin Python objects over the C-ABI handle.  Array in, array out; all numerics run in
+libfemb200.so on the GPU.  The reference-shaped adapters live in ``compat.py``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class Handle:
+    """Owns one femb_handle (one device, one stream)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        self._h = C.c_void_p()
+        rc = self.lib.femb_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise L.FembError(rc, "femb_create failed: no usable CUDA (sm_100) device — femb200 has no CPU fallback")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.femb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.femb_last_error(self._h)
+            raise L.FembError(rc, msg.decode() if msg else "")
+
+    # ---- shared ---------------------------------------------------------------------
+    def assemble(self):
+        self._check(self.lib.femb_assemble(self._h))
+
+    def get_csr(self, which=L.MAT_K):
+        """(indptr int32, indices int32, data float64) of K or M."""
+        nr, nz = C.c_int64(), C.c_int64()
+        self._check(self.lib.femb_get_csr_size(self._h, which, C.byref(nr), C.byref(nz)))
+        indptr = np.zeros(nr.value + 1, dtype=np.int32)
+        indices = np.zeros(nz.value, dtype=np.int32)
+        data = np.zeros(nz.value, dtype=np.float64)
+        self._check(self.lib.femb_get_csr(self._h, which, indptr, indices, data))
+        return indptr, indices, data
+
+    def set_bc(self, fixed_dofs, f, u_prescribed=None):
+        fixed = np.ascontiguousarray(fixed_dofs, dtype=np.int64)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        up = None if u_prescribed is None else np.ascontiguousarray(u_prescribed, dtype=np.float64)
+        self._check(self.lib.femb_set_bc(self._h, len(fixed), L.ptr(fixed), f, L.ptr(up)))
+        self.ndof = len(f)
+
+    def solve_static(self, method=L.SOLVER_AUTO, precond=L.PRECOND_BLOCK_JACOBI, rtol=1e-12, max_iter=200000,
+                     check_every=50, minus_f=True, want_u=True, want_reactions=True, profile=False):
+        o = L.SolveOpts(method, precond, max_iter, check_every, rtol, int(profile), 0)
+        st = L.Stats()
+        u = np.zeros(self.ndof) if want_u else None
+        r = np.zeros(self.ndof) if want_reactions else None
+        rc = self.lib.femb_solve_static(self._h, C.byref(o), int(minus_f), L.ptr(u), L.ptr(r), C.byref(st))
+        self.last_stats = st.as_dict()
+        self._check(rc)
+        return u, r, self.last_stats
+
+    def modal(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6):
+        o = L.EigOpts(k, block, max_iter, 0, rtol, lambda_min)
+        st = L.Stats()
+        lam = np.zeros(k)
+        phi = np.zeros((k, self.ndof))  # column-major (ndof,k) == row-major (k,ndof)
+        nf = C.c_int32()
+        rc = self.lib.femb_modal(self._h, C.byref(o), L.ptr(lam), L.ptr(phi), C.byref(nf), C.byref(st))
+        self.last_stats = st.as_dict()
+        self._check(rc)
+        n = nf.value
+        return lam[:n].copy(), np.ascontiguousarray(phi[:n].T), self.last_stats
+
+    def time_kernel(self, which, warm=3, reps=20):
+        ms, by = C.c_double(), C.c_double()
+        self._check(self.lib.femb_time_kernel(self._h, which, warm, reps, C.byref(ms), C.byref(by)))
+        return ms.value, by.value
+
+
+class FrameModel(Handle):
+    """3-D frame: element generation -> assembly -> BC -> solve -> stress / modal."""
+
+    def set_mesh(self, points, conn, elem_sec, sec_props, E, G, rho=7850.0):
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        self.conn = np.ascontiguousarray(conn, dtype=np.int64)
+        es = np.ascontiguousarray(elem_sec, dtype=np.int32)
+        sp = np.ascontiguousarray(sec_props, dtype=np.float64).reshape(-1, 8)
+        self.n_nodes, self.n_elem = len(self.points), len(self.conn)
+        self.ndof = 6 * self.n_nodes
+        self._check(self.lib.femb_frame_set_mesh(self._h, self.n_nodes, self.n_elem, self.points, self.conn.reshape(-1),
+                                                 es, len(sp), sp.reshape(-1), float(E), float(G), float(rho)))
+
+    def elements(self, want_k=True, want_m=True):
+        ke = np.zeros((self.n_elem, 12, 12)) if want_k else None
+        me = np.zeros((self.n_elem, 12, 12)) if want_m else None
+        self._check(self.lib.femb_frame_elements(self._h, L.ptr(ke), L.ptr(me)))
+        return ke, me
+
+    def stress(self, u=None):
+        s = np.zeros(self.n_nodes)
+        uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        self._check(self.lib.femb_frame_stress(self._h, L.ptr(uu), L.ptr(s)))
+        return s
+
+    def batch_solve(self, xyz, sec_props, E, G, fixed_mask, f, want_u=True):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        sp = np.ascontiguousarray(sec_props, dtype=np.float64).reshape(-1, 8)
+        fm = np.ascontiguousarray(fixed_mask, dtype=np.uint8)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        nm, ne = len(sp), len(xyz) - 1
+        u = np.zeros((nm, 6 * len(xyz))) if want_u else None
+        st = L.Stats()
+        rc = self.lib.femb_frame_batch_solve(self._h, nm, ne, xyz.reshape(-1), sp.reshape(-1), float(E), float(G),
+                                             fm, f.reshape(-1), L.ptr(u), C.byref(st))
+        self.last_stats = st.as_dict()
+        self._check(rc)
+        return u, self.last_stats
+
+
+class Tet10Model(Handle):
+    """Tet10 solid: element generation -> assembly -> BC -> solve -> reactions."""
+
+    def set_mesh(self, points, conn10, E, nu):
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        self.conn = np.ascontiguousarray(conn10, dtype=np.int64)
+        self.n_nodes, self.n_elem = len(self.points), len(self.conn)
+        self.ndof = 3 * self.n_nodes
+        self._check(self.lib.femb_tet10_set_mesh(self._h, self.n_nodes, self.n_elem, self.points,
+                                                 self.conn.reshape(-1), float(E), float(nu)))
+
+    def elements(self):
+        ke = np.zeros((self.n_elem, 30, 30))
+        self._check(self.lib.femb_tet10_elements(self._h, L.ptr(ke)))
+        return ke
+
+    @property
+    def negative_detj(self):
+        return int(self.lib.femb_tet10_negative_detj(self._h))
+
+
+def symbolic_pattern(n_nodes, conn):
+    """Host-only block-CSR pattern (rowptr, colidx) — needs no GPU."""
+    lib = L.load()
+    conn = np.ascontiguousarray(conn, dtype=np.int64)
+    nper = conn.shape[1]
+    nb = C.c_int64()
+    rc = lib.femb_symbolic_pattern(n_nodes, len(conn), nper, conn.reshape(-1), C.byref(nb), None, None)
+    if rc:
+        raise L.FembError(rc, "femb_symbolic_pattern")
+    rowptr = np.zeros(n_nodes + 1, dtype=np.int32)
+    colidx = np.zeros(nb.value, dtype=np.int32)
+    rc = lib.femb_symbolic_pattern(n_nodes, len(conn), nper, conn.reshape(-1), C.byref(nb), L.ptr(rowptr), L.ptr(colidx))
+    if rc:
+        raise L.FembError(rc, "femb_symbolic_pattern")
+    return rowptr, colidx

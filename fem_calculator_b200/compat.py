@@ -1,0 +1,315 @@
+"""Reference-shaped host side: the same names, inputs, outputs and error behaviour as the
+reference's Python entry points for the hot path, with every numerical step executed by
+libfemb200.so on the GPU.
+
+  BeamAnalysisWindow.run_simulation        BeamSolver.py:345-465  -> run_simulation_b200 /
+                                                                     BeamAnalysisB200
+  get_timoshenko_stiffness_matrix          BeamSolver.py:646-660  -> BeamAnalysisB200.<same>
+  get_lumped_mass_matrix                   BeamSolver.py:662-675  -> BeamAnalysisB200.<same>
+  bc_nodes_indexing                        BeamSolver.py:677-686  -> BeamAnalysisB200.<same>
+  ForceAnalysis                            ReactionSolver.py:16-232 -> ForceAnalysisB200
+
+Only the group -> node -> DOF bookkeeping (a few numpy index operations that define the
+input layout) stays on the host.  There is no CPU fallback: without a CUDA device every
+numerical call raises, which the reference's callers surface through their existing
+``except Exception`` dialogs (BeamSolver.py:464-465, FEM_main.py:378-382).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from .api import FrameModel, Tet10Model
+from .msh import Mesh, read_msh
+from .sections import calculate_section_properties as _closed_form_sections
+
+RHO_LITERAL = 7850  # BeamSolver.py:376 — the UI's density field is ignored by the reference
+
+
+def _group_nodes(mesh, element_type, name):
+    """BeamSolver.py:677-686 / ReactionSolver.py:75-85 (KeyError -> empty array)."""
+    try:
+        cells = mesh.cells_dict.get(element_type)
+        if cells is None:
+            return np.array([], dtype=int)
+        phys = mesh.cell_data_dict.get("gmsh:physical", {}).get(element_type)
+        if phys is None:
+            return np.array([], dtype=int)
+        target = mesh.field_data[name][0]
+        return np.unique(np.asarray(cells)[np.asarray(phys) == target].flatten())
+    except (KeyError, IndexError):
+        return np.array([], dtype=int)
+
+
+def frame_bc_vectors(mesh, bc_data, num_nodes):
+    """Up_node (sorted unique fixed DOFs) and the load vector f, BeamSolver.py:395-409."""
+    f = np.zeros(6 * num_nodes)
+    up = []
+    for bc in bc_data:
+        nodes = _group_nodes(mesh, "vertex", bc["group"])
+        if bc["type"] == "Fix":
+            for c, key in enumerate(("fix_x", "fix_y", "fix_z", "fix_rx", "fix_ry", "fix_rz")):
+                if bc.get(key):
+                    up.append(6 * nodes + c)
+        elif bc["type"] == "Force":
+            f[6 * nodes + 0] += bc.get("force_x", 0)
+            f[6 * nodes + 1] += bc.get("force_y", 0)
+            f[6 * nodes + 2] += bc.get("force_z", 0)
+    fixed = np.unique(np.concatenate(up)).astype(np.int64) if up else np.zeros(0, dtype=np.int64)
+    return fixed, f
+
+
+def frame_section_table(mesh, section_data, props_fn):
+    """Per-element section index + (S,8) table, BeamSolver.py:356-371.  Returns
+    (elem_sec, props, missing_group_name or None)."""
+    props_map = {s["group"]: props_fn(s["type"], s["params"], s.get("rotate", False)) for s in section_data}
+    gid2name = {int(v[0]): k for k, v in mesh.field_data.items()}
+    tags = np.asarray(mesh.cell_data_dict["gmsh:physical"]["line"])
+    names = list(props_map.keys())
+    lut = {}
+    for t in np.unique(tags):
+        name = gid2name.get(int(t))
+        if not name or name not in props_map:
+            return None, None, name
+        lut[int(t)] = names.index(name)
+    lut_arr = np.full((max(lut) + 1) if lut else 1, 0, dtype=np.int32)
+    for t, sidx in lut.items():
+        lut_arr[t] = sidx
+    elem_sec = lut_arr[tags].astype(np.int32)
+    props = np.asarray([props_map[n] for n in names], dtype=np.float64).reshape(-1, 8)
+    return elem_sec, props, None
+
+
+def run_simulation_b200(window, k_modes=20, device=0, props_fn=None, solver=L.SOLVER_AUTO, rtol=1e-12,
+                        modal_rtol=1e-8, on_error=None):
+    """Drop-in body for BeamAnalysisWindow.run_simulation (BeamSolver.py:345-455).
+
+    Reads exactly what the reference reads (window.mesh / points / conn / section_data /
+    bc_data / young_input.text() / poisson_input.text()) and writes exactly what it writes
+    (window.u, window.smoothed_stresses, window.natural_frequencies [rad/s],
+    window.mode_shapes (6N, n_modes)).  ``k_modes`` lowest modes are returned instead of
+    all n_f (the report prints 10, the plots use 5: BeamSolver.py:540-547,575).
+    ``on_error(title, message)`` stands in for QMessageBox.critical; default raises.
+    """
+    def err(title, msg):
+        if on_error is not None:
+            on_error(title, msg)
+            return None
+        raise RuntimeError(f"{title}: {msg}")
+
+    if not window.mesh:
+        return err("Error", "Please load a mesh file first.")
+    E = float(window.young_input.text())
+    nu = float(window.poisson_input.text())
+    G = E / (2 * (1 + nu))
+    num_nodes = len(window.points)
+    fn = props_fn or _closed_form_sections
+    elem_sec, props, missing = frame_section_table(window.mesh, window.section_data, fn)
+    if elem_sec is None:
+        return err("Error", f"Section properties not defined for physical group '{missing}'.")
+    fixed, f = frame_bc_vectors(window.mesh, window.bc_data, num_nodes)
+
+    model = FrameModel(device)
+    try:
+        model.set_mesh(window.points, window.conn, elem_sec, props, E, G, RHO_LITERAL)
+        model.assemble()
+        model.set_bc(fixed, f)
+        u, reactions, st = model.solve_static(method=solver, rtol=rtol)
+        window.u = u
+        window.reaction_forces = reactions          # extra: K u - f (the reference computes none)
+        window.smoothed_stresses = model.stress()
+        window.solve_stats = st
+        if k_modes:
+            lam, phi, mst = model.modal(k=int(k_modes), rtol=modal_rtol)
+            window.natural_frequencies = np.sqrt(lam)      # BeamSolver.py:451
+            window.mode_shapes = phi                        # zeros on fixed DOFs, :453-455
+            window.modal_stats = mst
+    finally:
+        model.close()
+    return window
+
+
+class _Text:
+    def __init__(self, v):
+        self._v = v
+
+    def text(self):
+        return repr(float(self._v))
+
+
+class BeamAnalysisB200:
+    """Headless stand-in for BeamAnalysisWindow (BeamSolver.py:176) exposing the hot-path
+    attributes and helper methods with the reference's names and signatures."""
+
+    def __init__(self, mesh=None, section_data=None, bc_data=None, E=2e11, nu=0.3, device=0, props_fn=None):
+        self.mesh = mesh
+        self.points = None if mesh is None else mesh.points
+        self.conn = None if mesh is None else mesh.cells_dict.get("line")
+        self.section_data = list(section_data or [])
+        self.bc_data = list(bc_data or [])
+        self.young_input, self.poisson_input = _Text(E), _Text(nu)
+        self.u = self.smoothed_stresses = self.natural_frequencies = self.mode_shapes = None
+        self.device = device
+        self.props_fn = props_fn
+
+    def mesh_load(self, mesh_path):
+        """BeamSolver.py:207-220 without the file dialog."""
+        self.mesh = read_msh(mesh_path)
+        self.points = self.mesh.points
+        self.conn = self.mesh.cells_dict.get("line")
+        if self.conn is None:
+            raise ValueError("No 'line' elements in .msh file.")
+        self.section_data.clear()
+        self.bc_data.clear()
+
+    def run_simulation(self, k_modes=20, **kw):
+        return run_simulation_b200(self, k_modes=k_modes, device=self.device, props_fn=self.props_fn, **kw)
+
+    def bc_nodes_indexing(self, element_type, bc_name):
+        return _group_nodes(self.mesh, element_type, bc_name)
+
+    def _one_element(self, L_, E, G, props, rho, want_k, want_m):
+        m = FrameModel(self.device)
+        try:
+            pts = np.array([[0.0, 0.0, 0.0], [float(L_), 0.0, 0.0]])
+            m.set_mesh(pts, np.array([[0, 1]]), np.zeros(1, dtype=np.int32), np.asarray(props, dtype=np.float64), E, G, rho)
+            ke, me = m.elements(want_k, want_m)
+        finally:
+            m.close()
+        return ke, me
+
+    def get_timoshenko_stiffness_matrix(self, L, E, G, A, I_x, I_y, J, kappa_y, kappa_z):
+        """BeamSolver.py:646 — local 12x12 stiffness, evaluated by the CUDA element kernel on
+        an x-aligned element (lambda = I, so global == local)."""
+        ke, _ = self._one_element(L, E, G, [A, I_x, I_y, J, kappa_y, kappa_z, 0.0, 0.0], 0.0, True, False)
+        return ke[0]
+
+    def get_lumped_mass_matrix(self, L, A, Ix, Iy, J, rho):
+        """BeamSolver.py:662."""
+        _, me = self._one_element(L, 1.0, 1.0, [A, Ix, Iy, J, 0.0, 0.0, 0.0, 0.0], rho, False, True)
+        return me[0]
+
+
+class ForceAnalysisB200:
+    """ForceAnalysis (ReactionSolver.py:16) with the numerical methods on the GPU.  Same
+    constructor, attributes and method names; ``msh_file`` may also be an in-memory mesh."""
+
+    def __init__(self, msh_file, force_data, fix_data, E, v, device=0):
+        self.msh_file = msh_file
+        self.force_data = force_data
+        self.fix_data = fix_data
+        self.E = E
+        self.v = v
+        self.pd = 3
+        self.points = None
+        self.tetra10_conn = None
+        self.num_nodes = 0
+        self.K = None
+        self.u = None
+        self.f = None
+        self.reaction_forces = None
+        self.fixed_nodes_info = []
+        self.negative_detJ_count = 0
+        self.applied_forces_info = []
+        self.device = device
+        self._model = None
+        self._read_mesh()
+
+    def _read_mesh(self):
+        """ReactionSolver.py:59-73."""
+        self.mesh = read_msh(self.msh_file) if isinstance(self.msh_file, str) else self.msh_file
+        self.points = self.mesh.points
+        self.num_nodes = len(self.points)
+        self.tetra10_conn = self.mesh.cells_dict.get("tetra10")
+        if self.tetra10_conn is None:
+            raise ValueError("메쉬 파일에 'tetra10' 요소가 없습니다.")  # same message as :68
+        self.diri_nodes = self._get_nodes_from_physical_group("Diri_BCs", "vertex")
+        self.neumann_nodes = self._get_nodes_from_physical_group("Neumann_BCs", "vertex")
+
+    def _get_nodes_from_physical_group(self, group_name, cell_type):
+        return _group_nodes(self.mesh, cell_type, group_name)
+
+    def _ensure_model(self):
+        if self._model is None:
+            self._model = Tet10Model(self.device)
+            self._model.set_mesh(self.points, self.tetra10_conn, self.E, self.v)
+        return self._model
+
+    def assemble_stiffness_matrix(self, export_csr=True):
+        """ReactionSolver.py:115-152.  K stays resident in HBM; ``export_csr`` also copies
+        it back as a scipy CSR matrix into ``self.K`` like the reference (structural
+        pattern: exact zeros are kept)."""
+        m = self._ensure_model()
+        m.assemble()
+        self.negative_detJ_count = m.negative_detj
+        if export_csr:
+            indptr, indices, data = m.get_csr(L.MAT_K)
+            try:
+                import scipy.sparse as sp
+                n = self.pd * self.num_nodes
+                self.K = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+            except ImportError:
+                self.K = (indptr, indices, data)
+
+    def apply_boundary_conditions(self):
+        """ReactionSolver.py:154-194 (nearest node inside the group; DOF fixed iff flag == 0)."""
+        total_dof = self.pd * self.num_nodes
+        self.f = np.zeros(total_dof)
+        fixed_dofs = []
+        self.fixed_nodes_info = []
+        self.applied_forces_info = []
+        for fix_info in self.fix_data:
+            pos = np.array([fix_info["pos_x"], fix_info["pos_y"], fix_info["pos_z"]])
+            distances = np.linalg.norm(self.points[self.diri_nodes] - pos, axis=1)
+            node_idx = self.diri_nodes[np.argmin(distances)]
+            dofs = []
+            if fix_info["fix_x"] == 0: dofs.append(3 * node_idx)
+            if fix_info["fix_y"] == 0: dofs.append(3 * node_idx + 1)
+            if fix_info["fix_z"] == 0: dofs.append(3 * node_idx + 2)
+            fixed_dofs.extend(dofs)
+            self.fixed_nodes_info.append({"node_idx": node_idx, "pos": self.points[node_idx], "dofs": dofs})
+        self.fixed_dofs = np.unique(fixed_dofs)
+        for force_item in self.force_data:
+            force_vec = np.array([force_item["force_x"], force_item["force_y"], force_item["force_z"]])
+            pos = np.array([force_item["force_x_pstn"], force_item["force_y_pstn"], force_item["force_z_pstn"]])
+            distances = np.linalg.norm(self.points[self.neumann_nodes] - pos, axis=1)
+            node_idx = self.neumann_nodes[np.argmin(distances)]
+            self.f[3 * node_idx: 3 * node_idx + 3] += force_vec
+            self.applied_forces_info.append({"node_idx": node_idx, "pos": self.points[node_idx], "force_vec": force_vec})
+        self.active_dofs = np.setdiff1d(np.arange(total_dof), self.fixed_dofs)
+        self._ensure_model().set_bc(self.fixed_dofs.astype(np.int64), self.f)
+
+    def solve(self, method=L.SOLVER_AUTO, rtol=1e-12):
+        """ReactionSolver.py:196-205: u on active DOFs, reaction_forces = K_full @ u."""
+        m = self._ensure_model()
+        self.u, self.reaction_forces, self.solve_stats = m.solve_static(method=method, rtol=rtol, minus_f=False)
+
+    def print_reactions(self):
+        """ReactionSolver.py:207-224."""
+        if self.reaction_forces is None:
+            return
+        print("\n--- Reaction Forces ---")
+        total_reaction = np.zeros(3)
+        for i, info in enumerate(self.fixed_nodes_info):
+            node_idx = info["node_idx"]
+            reactions = self.reaction_forces[3 * node_idx: 3 * node_idx + 3]
+            total_reaction += reactions
+            print(f"  Node {node_idx} (Fix Point {i+1}): Rx={reactions[0]:.4e}, Ry={reactions[1]:.4e}, Rz={reactions[2]:.4e} N")
+        print("\n--- Force Equilibrium Check ---")
+        total_applied_force = np.zeros(3)
+        for force_item in self.force_data:
+            total_applied_force += [force_item["force_x"], force_item["force_y"], force_item["force_z"]]
+        print(f"  Sum of Applied Forces (Fx, Fy, Fz): {total_applied_force}")
+        print(f"  Sum of Reaction Forces (Rx, Ry, Rz): {-total_reaction}")
+
+    def run_simulation(self):
+        """ReactionSolver.py:226-232 minus the docx report (out of scope)."""
+        self.assemble_stiffness_matrix()
+        self.apply_boundary_conditions()
+        self.solve()
+        self.print_reactions()
+
+    def close(self):
+        if self._model is not None:
+            self._model.close()
+            self._model = None

@@ -1,0 +1,291 @@
+// Fused element + assembly kernel (frame and Tet10) and the parity-export element kernels.
+//
+// One CTA owns a TILE of consecutive block rows (nodes).  The BSR values of a tile are one
+// contiguous range of HBM, so the CTA builds them in shared memory and streams them out
+// with a single bulk async copy (cp.async.bulk smem -> global, SASS UBLKCP) — or a fully
+// coalesced 16-byte store loop when the bulk path is disabled.  Each thread evaluates ONE
+// contribution (element e, local block a,b) straight from node coordinates and section
+// data in registers; contributions that land in the same block are added in ascending
+// list order, one per __syncthreads_or step, so the sum order is fixed by the symbolic
+// phase: no float atomics, bit-reproducible run to run.  Element matrices are never
+// materialised in HBM: traffic = mesh in + K (+M) out + the 12-byte/contribution map.
+#include "common.cuh"
+#include "elements.cuh"
+
+namespace femb {
+
+struct PatternDev {
+  const int32_t* rowptr;
+  const int32_t* contrib_ptr;
+  const uint32_t* contrib;
+  const int32_t* contrib_blk;
+  const int32_t* tile_ptr;
+};
+
+struct FrameEl {
+  static constexpr int BS = 6;
+  static constexpr int BS2 = 36;
+  static constexpr bool HAS_MASS = true;
+  FrameParams P;
+  struct Rec { FrameRec r; };
+  __device__ __forceinline__ void kblock(uint32_t code, Rec& rec, double* acc) const {
+    frame_record(P, code >> 2, rec.r);
+    frame_kblock<true>(rec.r, (code >> 1) & 1, code & 1, acc);
+  }
+  __device__ __forceinline__ bool has_mass(uint32_t code) const { return ((code >> 1) & 1) == (code & 1); }
+  __device__ __forceinline__ void mblock(uint32_t, const Rec& rec, double* acc) const { frame_mblock(rec.r, acc); }
+};
+
+struct Tet10El {
+  static constexpr int BS = 3;
+  static constexpr int BS2 = 9;
+  static constexpr bool HAS_MASS = false;
+  Tet10Params P;
+  struct Rec {};
+  __device__ __forceinline__ void kblock(uint32_t code, Rec&, double* acc) const {
+    const uint32_t e = code / 100u, ab = code % 100u;
+    tet10_kblock(P, e, ab / 10u, ab % 10u, ab == 0u, acc);
+  }
+  __device__ __forceinline__ bool has_mass(uint32_t) const { return false; }
+  __device__ __forceinline__ void mblock(uint32_t, const Rec&, double*) const {}
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+template <class EL, int THREADS, bool BULK>
+__global__ void __launch_bounds__(THREADS)
+assemble_tiles_kernel(const EL el, const PatternDev pat, double* __restrict__ Kvals,
+                      double* __restrict__ Mdiag) {
+  constexpr int BS2 = EL::BS2;
+  extern __shared__ __align__(128) double s_out[];  // [nblk*BS2] then mass [nnodes*BS2]
+  const int tid = threadIdx.x;
+  const int n0 = pat.tile_ptr[blockIdx.x], n1 = pat.tile_ptr[blockIdx.x + 1];
+  const int b0 = pat.rowptr[n0], b1 = pat.rowptr[n1];
+  const int c0 = pat.contrib_ptr[b0], c1 = pat.contrib_ptr[b1];
+  const int nblk = b1 - b0;
+  double* s_mass = s_out + (size_t)nblk * BS2;
+
+  // blocks nobody contributes to (isolated points) must still be written as zeros
+  for (int t = tid; t < nblk; t += THREADS) {
+    if (pat.contrib_ptr[b0 + t + 1] == pat.contrib_ptr[b0 + t]) {
+#pragma unroll
+      for (int k = 0; k < BS2; ++k) s_out[(size_t)t * BS2 + k] = 0.0;
+    }
+  }
+  if (EL::HAS_MASS) {
+    for (int t = tid; t < (n1 - n0) * BS2; t += THREADS) s_mass[t] = 0.0;
+  }
+  __syncthreads();
+
+  for (int base = c0; base < c1; base += THREADS) {  // normally a single pass
+    const int c = base + tid;
+    int myk = -1, slot = 0, mslot = -1;
+    bool first = false;
+    double acc[BS2];
+    typename EL::Rec rec;
+    uint32_t code = 0;
+    if (c < c1) {
+      code = pat.contrib[c];
+      const int blk = pat.contrib_blk[c];
+      const int cb = pat.contrib_ptr[blk];
+      first = (c == cb);
+      myk = c - max(cb, base);
+      slot = blk - b0;
+      el.kblock(code, rec, acc);
+    }
+    for (int k = 0; __syncthreads_or(myk >= k); ++k) {
+      if (myk == k) {
+        double* dst = s_out + (size_t)slot * BS2;
+        if (first) {
+#pragma unroll
+          for (int q = 0; q < BS2; ++q) dst[q] = acc[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < BS2; ++q) dst[q] += acc[q];
+        }
+      }
+    }
+    if (EL::HAS_MASS) {
+      // second ordered pass: lumped-mass diagonal blocks (diagonal contributions only);
+      // the row node of a diagonal block is found from the block's slot via rowptr.
+      if (c < c1 && el.has_mass(code)) {
+        el.mblock(code, rec, acc);
+        const int blk = slot + b0;
+        int lo = n0, hi = n1 - 1;  // largest node with rowptr[node] <= blk
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (pat.rowptr[mid] <= blk) lo = mid; else hi = mid - 1;
+        }
+        mslot = lo - n0;
+      } else {
+        myk = -1;
+      }
+      for (int k = 0; __syncthreads_or(myk >= k); ++k) {
+        if (myk == k) {
+          double* dst = s_mass + (size_t)mslot * BS2;
+#pragma unroll
+          for (int q = 0; q < BS2; ++q) dst[q] += acc[q];
+        }
+      }
+    }
+  }
+  // (the last __syncthreads_or above is the barrier that publishes s_out / s_mass)
+
+  double* gK = Kvals + (size_t)b0 * BS2;
+  const int nK = nblk * BS2;
+  if (BULK) {
+    // generic-proxy writes -> visible to the async proxy, then one thread issues the copies
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(gK), "r"(smem_u32(s_out)), "r"((uint32_t)(nK * 8)) : "memory");
+      if (EL::HAS_MASS) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(Mdiag + (size_t)n0 * BS2), "r"(smem_u32(s_mass)),
+                        "r"((uint32_t)((n1 - n0) * BS2 * 8)) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    if ((BS2 & 1) == 0) {
+      const double2* s2 = reinterpret_cast<const double2*>(s_out);
+      double2* g2 = reinterpret_cast<double2*>(gK);
+      for (int i = tid; i < nK / 2; i += THREADS) g2[i] = s2[i];
+    } else {
+      for (int i = tid; i < nK; i += THREADS) gK[i] = s_out[i];
+    }
+    if (EL::HAS_MASS) {
+      double* gM = Mdiag + (size_t)n0 * BS2;
+      for (int i = tid; i < (n1 - n0) * BS2; i += THREADS) gM[i] = s_mass[i];
+    }
+  }
+}
+
+// ---- parity export: per-element global-axis matrices ------------------------------------
+__global__ void frame_elements_kernel(FrameParams P, int64_t n_elem, double* __restrict__ ke,
+                                      double* __restrict__ me) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_elem * 4) return;
+  const uint32_t e = (uint32_t)(t >> 2);
+  const int a = (int)((t >> 1) & 1), b = (int)(t & 1);
+  FrameRec R;
+  frame_record(P, e, R);
+  double acc[36];
+  if (ke) {
+    frame_kblock<true>(R, a, b, acc);
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) ke[(size_t)e * 144 + (6 * a + r) * 12 + 6 * b + c] = acc[r * 6 + c];
+  }
+  if (me) {
+    if (a == b) frame_mblock(R, acc);
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c)
+        me[(size_t)e * 144 + (6 * a + r) * 12 + 6 * b + c] = (a == b) ? acc[r * 6 + c] : 0.0;
+  }
+}
+
+__global__ void tet10_elements_kernel(Tet10Params P, int64_t n_elem, double* __restrict__ ke) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_elem * 100) return;
+  const uint32_t e = (uint32_t)(t / 100);
+  const int a = (int)((t % 100) / 10), b = (int)(t % 10);
+  double acc[9];
+  Tet10Params Q = P;
+  tet10_kblock(Q, e, a, b, false, acc);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) ke[(size_t)e * 900 + (3 * a + r) * 30 + 3 * b + c] = acc[r * 3 + c];
+}
+
+static FrameParams frame_params(const femb_handle* h) {
+  FrameParams P;
+  P.xyz = h->xyz.p; P.conn = h->conn.p; P.elem_sec = h->elem_sec.p; P.sec_props = h->sec_props.p;
+  P.E = h->E; P.G = h->G; P.rho = h->rho;
+  return P;
+}
+
+static Tet10Params tet10_params(const femb_handle* h) {
+  Tet10Params P;
+  P.xyz = h->xyz.p; P.conn = h->conn.p;
+  const double C1 = h->E / ((1.0 + h->nu) * (1.0 - 2.0 * h->nu));  // ReactionSolver.py:89
+  const double C2 = (1.0 - 2.0 * h->nu) / 2.0;                      // :90
+  P.lam = C1 * h->nu; P.mu2 = C1 * (1.0 - h->nu); P.gsh = C1 * C2;
+  P.skipped = h->counters.p;
+  return P;
+}
+
+int launch_frame_elements(femb_handle* h, double* d_ke, double* d_me) {
+  const int64_t n = h->n_elem * 4;
+  if (n == 0) return FEMB_OK;
+  frame_elements_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(frame_params(h), h->n_elem, d_ke, d_me);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+int launch_tet10_elements(femb_handle* h, double* d_ke) {
+  const int64_t n = h->n_elem * 100;
+  if (n == 0) return FEMB_OK;
+  tet10_elements_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(tet10_params(h), h->n_elem, d_ke);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+constexpr int kAsmThreads = 128;
+
+static bool bulk_enabled() {
+  const char* s = getenv("FEMB_ASM_BULK");
+  return !(s && s[0] == '0');
+}
+
+template <class EL>
+static int launch_assemble_t(femb_handle* h, const EL& el) {
+  const femb::Symbolic& S = h->sym;
+  const int n_tiles = (int)S.tile_ptr.size() - 1;
+  if (n_tiles <= 0) return FEMB_OK;
+  // dynamic shared memory: the largest tile
+  size_t smem = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int n0 = S.tile_ptr[t], n1 = S.tile_ptr[t + 1];
+    size_t need = (size_t)(S.rowptr[n1] - S.rowptr[n0]) * EL::BS2 * 8;
+    if (EL::HAS_MASS) need += (size_t)(n1 - n0) * EL::BS2 * 8;
+    smem = need > smem ? need : smem;
+  }
+  smem = (smem + 127) & ~size_t(127);
+  if (smem > 200 * 1024) return fail(h, FEMB_ERR_ARG, "assembly tile exceeds shared memory (node degree too large)");
+  PatternDev pat{h->rowptr.p, h->contrib_ptr.p, h->contrib.p, h->contrib_blk.p, h->tile_ptr.p};
+  const bool bulk = bulk_enabled() && (EL::BS2 % 2 == 0);
+  if (bulk) {
+    auto k = assemble_tiles_kernel<EL, kAsmThreads, true>;
+    FEMB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<n_tiles, kAsmThreads, smem, h->stream>>>(el, pat, h->Kvals.p, h->Mdiag.p);
+  } else {
+    auto k = assemble_tiles_kernel<EL, kAsmThreads, false>;
+    FEMB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<n_tiles, kAsmThreads, smem, h->stream>>>(el, pat, h->Kvals.p, h->Mdiag.p);
+  }
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+int launch_assemble(femb_handle* h) {
+  if (h->kind == Kind::Frame) {
+    FrameEl el;
+    el.P = frame_params(h);
+    return launch_assemble_t(h, el);
+  }
+  if (h->kind == Kind::Tet10) {
+    FEMB_CUDA(h, cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * h->counters.n, h->stream));
+    Tet10El el;
+    el.P = tet10_params(h);
+    return launch_assemble_t(h, el);
+  }
+  return fail(h, FEMB_ERR_ARG, "no mesh set");
+}
+
+}  // namespace femb

@@ -1,0 +1,434 @@
+// extern "C" entry points of libfemb200 (see include/femb200.h for the contract).
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+using namespace femb;
+
+namespace femb {
+int bc_build_mask(femb_handle* h, const int64_t* d_fixed, int64_t n_fixed);
+int apply_prescribed(femb_handle* h);
+}
+
+static int need(femb_handle* h, bool cond, const char* msg) {
+  return cond ? FEMB_OK : fail(h, FEMB_ERR_ARG, msg);
+}
+
+extern "C" {
+
+int femb_version(void) { return 100; }
+
+int femb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int femb_create(int device, femb_handle** out) {
+  if (!out) return FEMB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return FEMB_ERR_CUDA;  // no CPU fallback by design
+  }
+  if (device < 0 || device >= n) return FEMB_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return FEMB_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FEMB_ERR_CUDA;
+  if (prop.major < 10) return FEMB_ERR_CUDA;  // sm_100a code only
+  femb_handle* h = new femb_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaMallocHost(&h->pinned, 4096) != cudaSuccess) {
+    delete h;
+    return FEMB_ERR_CUDA;
+  }
+  h->pinned_bytes = 4096;
+  *out = h;
+  return FEMB_OK;
+}
+
+void femb_destroy(femb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* femb_last_error(const femb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+static int set_mesh_common(femb_handle* h, Kind kind, int bs, int nper, int64_t n_nodes, int64_t n_elem,
+                           const double* xyz, const int64_t* conn) {
+  if (!h) return FEMB_ERR_ARG;
+  if (n_nodes <= 0 || n_elem < 0 || !xyz || (n_elem > 0 && !conn)) return fail(h, FEMB_ERR_ARG, "bad mesh arguments");
+  if (n_nodes * bs >= (int64_t)INT32_MAX || n_elem * nper * nper >= (int64_t)UINT32_MAX)
+    return fail(h, FEMB_ERR_ARG, "mesh too large for 32-bit indices on one device");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  h->h_conn.resize((size_t)(n_elem * nper));
+  for (size_t i = 0; i < h->h_conn.size(); ++i) {
+    if (conn[i] < 0 || conn[i] >= n_nodes) return fail(h, FEMB_ERR_ARG, "connectivity index out of range");
+    h->h_conn[i] = (int32_t)conn[i];
+  }
+  h->kind = kind; h->bs = bs;
+  h->n_nodes = n_nodes; h->n_elem = n_elem; h->ndof = n_nodes * bs;
+  h->have_symbolic = h->assembled = h->have_bc = h->have_solution = false;
+  FEMB_CUDA(h, upload(h->xyz, xyz, (size_t)n_nodes * 3, h->stream));
+  FEMB_CUDA(h, upload(h->conn, h->h_conn, h->stream));
+  FEMB_CUDA(h, h->counters.alloc(4));
+  FEMB_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 4 * sizeof(unsigned long long), h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));  // caller may free its buffers now
+  return FEMB_OK;
+}
+
+int femb_frame_set_mesh(femb_handle* h, int64_t n_nodes, int64_t n_elem, const double* xyz,
+                        const int64_t* conn, const int32_t* elem_sec, int32_t n_sec,
+                        const double* sec_props, double E, double G, double rho) {
+  if (!h) return FEMB_ERR_ARG;
+  if (n_sec <= 0 || !sec_props || (n_elem > 0 && !elem_sec)) return fail(h, FEMB_ERR_ARG, "bad section arguments");
+  for (int64_t e = 0; e < n_elem; ++e)
+    if (elem_sec[e] < 0 || elem_sec[e] >= n_sec) return fail(h, FEMB_ERR_ARG, "element section index out of range");
+  int rc = set_mesh_common(h, Kind::Frame, 6, 2, n_nodes, n_elem, xyz, conn);
+  if (rc) return rc;
+  h->E = E; h->G = G; h->rho = rho; h->n_sec = n_sec;
+  FEMB_CUDA(h, upload(h->elem_sec, elem_sec, (size_t)n_elem, h->stream));
+  FEMB_CUDA(h, upload(h->sec_props, sec_props, (size_t)n_sec * 8, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FEMB_OK;
+}
+
+int femb_tet10_set_mesh(femb_handle* h, int64_t n_nodes, int64_t n_elem, const double* xyz,
+                        const int64_t* conn10, double E, double nu) {
+  int rc = set_mesh_common(h, Kind::Tet10, 3, 10, n_nodes, n_elem, xyz, conn10);
+  if (rc) return rc;
+  h->E = E; h->nu = nu;
+  return FEMB_OK;
+}
+
+int femb_frame_elements(femb_handle* h, double* ke, double* me) {
+  if (!h || h->kind != Kind::Frame) return fail(h, FEMB_ERR_ARG, "frame mesh not set");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->n_elem * 144;
+  DevBuf<double> dk, dm;
+  if (ke) FEMB_CUDA(h, dk.alloc(cnt));
+  if (me) FEMB_CUDA(h, dm.alloc(cnt));
+  int rc = launch_frame_elements(h, dk.p, dm.p);
+  if (rc) return rc;
+  if (ke) FEMB_CUDA(h, cudaMemcpyAsync(ke, dk.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (me) FEMB_CUDA(h, cudaMemcpyAsync(me, dm.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FEMB_OK;
+}
+
+int femb_tet10_elements(femb_handle* h, double* ke) {
+  if (!h || h->kind != Kind::Tet10 || !ke) return fail(h, FEMB_ERR_ARG, "tet10 mesh not set");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->n_elem * 900;
+  DevBuf<double> dk;
+  FEMB_CUDA(h, dk.alloc(cnt));
+  int rc = launch_tet10_elements(h, dk.p);
+  if (rc) return rc;
+  FEMB_CUDA(h, cudaMemcpyAsync(ke, dk.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FEMB_OK;
+}
+
+int64_t femb_tet10_negative_detj(const femb_handle* h) { return h ? h->neg_detj : -1; }
+
+static int ensure_symbolic(femb_handle* h) {
+  if (h->have_symbolic) return FEMB_OK;
+  const int nper = (h->kind == Kind::Frame) ? 2 : 10;
+  // tile capacities: <= 128 contributions (one per thread of the 128-thread assembly CTA is
+  // the common case; larger rows fall back to chunking) and a shared-memory budget in blocks.
+  const int max_contrib = 128;
+  const int max_blocks = (h->bs == 6) ? 96 : 512;
+  build_symbolic(h->n_nodes, h->n_elem, nper, h->bs, h->h_conn.data(), max_blocks, max_contrib, h->sym);
+  const Symbolic& S = h->sym;
+  if (S.nnzb * (int64_t)h->bs * h->bs >= ((int64_t)1 << 40)) return fail(h, FEMB_ERR_ARG, "matrix too large");
+  FEMB_CUDA(h, upload(h->rowptr, S.rowptr, h->stream));
+  FEMB_CUDA(h, upload(h->colidx, S.colidx, h->stream));
+  FEMB_CUDA(h, upload(h->blk_row, S.blk_row, h->stream));
+  FEMB_CUDA(h, upload(h->diag_blk, S.diag_blk, h->stream));
+  FEMB_CUDA(h, upload(h->contrib_ptr, S.contrib_ptr, h->stream));
+  FEMB_CUDA(h, upload(h->contrib, S.contrib, h->stream));
+  FEMB_CUDA(h, upload(h->contrib_blk, S.contrib_blk, h->stream));
+  FEMB_CUDA(h, upload(h->tile_ptr, S.tile_ptr, h->stream));
+  FEMB_CUDA(h, h->Kvals.alloc((size_t)S.nnzb * h->bs * h->bs));
+  if (h->kind == Kind::Frame) FEMB_CUDA(h, h->Mdiag.alloc((size_t)h->n_nodes * 36));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_symbolic = true;
+  return FEMB_OK;
+}
+
+int femb_assemble(femb_handle* h) {
+  if (!h || h->kind == Kind::None) return fail(h, FEMB_ERR_ARG, "no mesh set");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_symbolic(h);
+  if (rc) return rc;
+  rc = launch_assemble(h);
+  if (rc) return rc;
+  if (h->kind == Kind::Tet10) {
+    unsigned long long* pc = reinterpret_cast<unsigned long long*>(h->pinned);
+    FEMB_CUDA(h, cudaMemcpyAsync(pc, h->counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->neg_detj = (int64_t)pc[0];
+  } else {
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->assembled = true;
+  h->have_solution = false;
+  return FEMB_OK;
+}
+
+int femb_get_csr_size(femb_handle* h, int which, int64_t* n_rows, int64_t* nnz) {
+  if (!h || !h->assembled || !n_rows || !nnz) return fail(h, FEMB_ERR_ARG, "assemble first");
+  if (which == FEMB_MAT_M && h->kind != Kind::Frame) return fail(h, FEMB_ERR_ARG, "mass matrix exists for frames only");
+  *n_rows = h->ndof;
+  *nnz = (which == FEMB_MAT_K) ? h->sym.nnzb * h->bs * h->bs : h->n_nodes * h->bs * h->bs;
+  return FEMB_OK;
+}
+
+int femb_get_csr(femb_handle* h, int which, int32_t* indptr, int32_t* indices, double* vals) {
+  if (!h || !h->assembled || !indptr || !indices || !vals) return fail(h, FEMB_ERR_ARG, "assemble first");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  const int bs = h->bs, bs2 = bs * bs;
+  const Symbolic& S = h->sym;
+  if (which == FEMB_MAT_K) {
+    if (S.nnzb * (int64_t)bs2 >= INT32_MAX) return fail(h, FEMB_ERR_ARG, "CSR export needs nnz < 2^31");
+    std::vector<double> bv((size_t)S.nnzb * bs2);
+    FEMB_CUDA(h, cudaMemcpyAsync(bv.data(), h->Kvals.p, bv.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    int64_t pos = 0;
+    for (int64_t i = 0; i < h->n_nodes; ++i) {
+      for (int r = 0; r < bs; ++r) {
+        indptr[i * bs + r] = (int32_t)pos;
+        for (int32_t b = S.rowptr[i]; b < S.rowptr[i + 1]; ++b)
+          for (int c = 0; c < bs; ++c) {
+            indices[pos] = S.colidx[b] * bs + c;
+            vals[pos] = bv[(size_t)b * bs2 + r * bs + c];
+            ++pos;
+          }
+      }
+    }
+    indptr[h->ndof] = (int32_t)pos;
+    return FEMB_OK;
+  }
+  if (which == FEMB_MAT_M && h->kind == Kind::Frame) {
+    std::vector<double> bv((size_t)h->n_nodes * bs2);
+    FEMB_CUDA(h, cudaMemcpyAsync(bv.data(), h->Mdiag.p, bv.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    int64_t pos = 0;
+    for (int64_t i = 0; i < h->n_nodes; ++i)
+      for (int r = 0; r < bs; ++r) {
+        indptr[i * bs + r] = (int32_t)pos;
+        for (int c = 0; c < bs; ++c) {
+          indices[pos] = (int32_t)(i * bs + c);
+          vals[pos] = bv[(size_t)i * bs2 + r * bs + c];
+          ++pos;
+        }
+      }
+    indptr[h->ndof] = (int32_t)pos;
+    return FEMB_OK;
+  }
+  return fail(h, FEMB_ERR_ARG, "unknown matrix selector");
+}
+
+int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, const double* f,
+                const double* u_prescribed) {
+  if (!h || h->kind == Kind::None) return fail(h, FEMB_ERR_ARG, "no mesh set");
+  if (n_fixed < 0 || (n_fixed > 0 && !fixed_dofs) || !f) return fail(h, FEMB_ERR_ARG, "bad BC arguments");
+  for (int64_t i = 0; i < n_fixed; ++i) {
+    if (fixed_dofs[i] < 0 || fixed_dofs[i] >= h->ndof) return fail(h, FEMB_ERR_ARG, "fixed DOF out of range");
+    if (i > 0 && fixed_dofs[i] <= fixed_dofs[i - 1]) return fail(h, FEMB_ERR_ARG, "fixed_dofs must be sorted and unique");
+  }
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  DevBuf<int64_t> dfix;
+  FEMB_CUDA(h, upload(dfix, fixed_dofs, (size_t)n_fixed, h->stream));
+  FEMB_CUDA(h, h->free_mask.alloc((size_t)h->ndof));
+  FEMB_CUDA(h, upload(h->f, f, (size_t)h->ndof, h->stream));
+  bool nonzero = false;
+  if (u_prescribed)
+    for (int64_t i = 0; i < n_fixed && !nonzero; ++i) nonzero = u_prescribed[fixed_dofs[i]] != 0.0;
+  if (nonzero) FEMB_CUDA(h, upload(h->u0, u_prescribed, (size_t)h->ndof, h->stream));
+  else h->u0.release();
+  int rc = bc_build_mask(h, dfix.p, n_fixed);
+  if (rc) return rc;
+  rc = setup_bc_vectors(h);
+  if (rc) return rc;
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n_fixed = n_fixed;
+  h->have_bc = true;
+  h->have_solution = false;
+  return FEMB_OK;
+}
+
+static femb_solve_opts default_solve_opts() {
+  femb_solve_opts o;
+  std::memset(&o, 0, sizeof(o));
+  o.method = FEMB_SOLVER_AUTO; o.precond = FEMB_PRECOND_BLOCK_JACOBI; o.max_iter = 200000;
+  o.check_every = 50; o.rtol = 1e-12;
+  return o;
+}
+
+int femb_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, double* u,
+                      double* reactions, femb_stats* stats) {
+  if (!h) return FEMB_ERR_ARG;
+  int rc = need(h, h->assembled && h->have_bc, "call femb_assemble and femb_set_bc first");
+  if (rc) return rc;
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  femb_solve_opts o = opts ? *opts : default_solve_opts();
+  if (o.max_iter <= 0) o.max_iter = 200000;
+  if (!(o.rtol > 0.0)) o.rtol = 1e-12;
+  femb_stats st;
+  std::memset(&st, 0, sizeof(st));
+  h->launches = 0;
+  FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  int method = o.method;
+  if (method == FEMB_SOLVER_AUTO) {
+    const int64_t nfree = h->ndof - h->n_fixed;
+    if (h->kind == Kind::Frame && h->sym.is_chain) method = FEMB_SOLVER_CHAIN;
+    else if (nfree <= 2048) method = FEMB_SOLVER_DENSE;
+    else method = FEMB_SOLVER_PCG;
+  }
+  if (method == FEMB_SOLVER_PCG) rc = run_pcg(h, o, &st);
+  else if (method == FEMB_SOLVER_CHAIN) rc = run_chain_solve(h, &st);
+  else if (method == FEMB_SOLVER_DENSE) rc = run_dense_solve(h, &st);
+  else rc = fail(h, FEMB_ERR_ARG, "unknown solver method");
+  if (rc == FEMB_OK) rc = apply_prescribed(h);
+  if (rc == FEMB_OK) {
+    h->have_solution = true;
+    if (reactions) {
+      rc = launch_reactions(h, minus_f != 0, h->q.p);
+      if (rc == FEMB_OK)
+        FEMB_CUDA(h, cudaMemcpyAsync(reactions, h->q.p, (size_t)h->ndof * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (rc == FEMB_OK && u)
+      FEMB_CUDA(h, cudaMemcpyAsync(u, h->x.p, (size_t)h->ndof * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  cudaEventRecord(h->ev1, h->stream);
+  cudaError_t se = cudaStreamSynchronize(h->stream);
+  if (rc == FEMB_OK && se != cudaSuccess) rc = fail(h, FEMB_ERR_CUDA, cudaGetErrorString(se));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  st.device_ms = ms;
+  st.kernel_launches = (int32_t)h->launches;
+  if (stats) *stats = st;
+  return rc;
+}
+
+int femb_modal(femb_handle* h, const femb_eig_opts* opts, double* lambda, double* phi,
+               int32_t* n_found, femb_stats* stats) {
+  if (!h) return FEMB_ERR_ARG;
+  int rc = need(h, h->kind == Kind::Frame && h->assembled && h->have_bc, "frame: call femb_assemble and femb_set_bc first");
+  if (rc) return rc;
+  if (!opts || opts->k <= 0 || !lambda || !n_found) return fail(h, FEMB_ERR_ARG, "bad modal arguments");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  femb_eig_opts o = *opts;
+  if (o.max_iter <= 0) o.max_iter = 5000;
+  if (!(o.rtol > 0.0)) o.rtol = 1e-8;
+  femb_stats st;
+  std::memset(&st, 0, sizeof(st));
+  h->launches = 0;
+  FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  rc = run_modal(h, o, lambda, phi, n_found, &st);
+  cudaEventRecord(h->ev1, h->stream);
+  cudaError_t se = cudaStreamSynchronize(h->stream);
+  if (rc == FEMB_OK && se != cudaSuccess) rc = fail(h, FEMB_ERR_CUDA, cudaGetErrorString(se));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  st.device_ms = ms;
+  st.kernel_launches = (int32_t)h->launches;
+  if (stats) *stats = st;
+  return rc;
+}
+
+int femb_frame_stress(femb_handle* h, const double* u, double* sigma_node) {
+  if (!h || h->kind != Kind::Frame || !sigma_node) return fail(h, FEMB_ERR_ARG, "frame mesh not set");
+  if (!u && !h->have_solution) return fail(h, FEMB_ERR_ARG, "no solution on the device; pass u");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_symbolic(h);
+  if (rc) return rc;
+  DevBuf<double> du, ds;
+  const double* d_u = h->x.p;
+  if (u) {
+    FEMB_CUDA(h, upload(du, u, (size_t)h->ndof, h->stream));
+    d_u = du.p;
+  }
+  FEMB_CUDA(h, ds.alloc((size_t)h->n_nodes));
+  rc = launch_frame_stress(h, d_u, ds.p);
+  if (rc) return rc;
+  FEMB_CUDA(h, cudaMemcpyAsync(sigma_node, ds.p, (size_t)h->n_nodes * 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FEMB_OK;
+}
+
+int femb_frame_batch_solve(femb_handle* h, int64_t n_models, int64_t n_elem, const double* xyz,
+                           const double* sec_props, double E, double G, const uint8_t* fixed_mask,
+                           const double* f, double* u, femb_stats* stats) {
+  if (!h) return FEMB_ERR_ARG;
+  if (n_models <= 0 || n_elem <= 0 || !xyz || !sec_props || !fixed_mask || !f) return fail(h, FEMB_ERR_ARG, "bad batch arguments");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  femb_stats st;
+  std::memset(&st, 0, sizeof(st));
+  h->launches = 0;
+  int rc = run_batch_chain(h, n_models, n_elem, xyz, sec_props, E, G, fixed_mask, f, u, &st);
+  st.kernel_launches = (int32_t)h->launches;
+  if (stats) *stats = st;
+  return rc;
+}
+
+int femb_time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes) {
+  if (!h || !ms || !bytes || reps <= 0) return fail(h, FEMB_ERR_ARG, "bad arguments");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  return time_kernel(h, which, warm, reps, ms, bytes);
+}
+
+}  // extern "C"
+
+namespace femb {
+
+int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes) {
+  int rc = FEMB_OK;
+  const int bs2 = h->bs * h->bs;
+  const Symbolic& S = h->sym;
+  if (which == 0) {
+    if (!h->assembled || !h->have_bc) return fail(h, FEMB_ERR_ARG, "assemble + set_bc first");
+    // BSR SpMV: 8 B/value + 4 B/block column + 4 B/row pointer + x read once + y written + mask
+    *bytes = 8.0 * S.nnzb * bs2 + 4.0 * S.nnzb + 4.0 * (h->n_nodes + 1) + 8.0 * h->ndof * 2 + 1.0 * h->ndof;
+    for (int i = 0; i < warm && !rc; ++i) rc = launch_spmv(h, h->b.p, h->q.p, true, nullptr);
+    FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps && !rc; ++i) rc = launch_spmv(h, h->b.p, h->q.p, true, nullptr);
+    FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  } else if (which == 1) {
+    if (!h->have_symbolic) return fail(h, FEMB_ERR_ARG, "assemble once first");
+    // fused element+assembly: mesh in (60 B/element frame, 10*(4+24) tet) + K (+M) out;
+    // the scatter map (12 B/contribution + 4 B/block) is counted as algorithmic input too.
+    const double mesh_in = (h->kind == Kind::Frame) ? 60.0 * h->n_elem : 280.0 * h->n_elem;
+    *bytes = mesh_in + 8.0 * S.nnzb * bs2 + (h->kind == Kind::Frame ? 8.0 * h->n_nodes * bs2 : 0.0) +
+             12.0 * S.n_contrib + 4.0 * S.nnzb;
+    for (int i = 0; i < warm && !rc; ++i) rc = launch_assemble(h);
+    FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps && !rc; ++i) rc = launch_assemble(h);
+    FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  } else {
+    return fail(h, FEMB_ERR_ARG, "unknown kernel selector");
+  }
+  if (rc) return rc;
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  float t = 0.f;
+  FEMB_CUDA(h, cudaEventElapsedTime(&t, h->ev0, h->ev1));
+  *ms = (double)t / reps;
+  return FEMB_OK;
+}
+
+}  // namespace femb

@@ -1,0 +1,162 @@
+// Shared declarations for libfemb200: handle layout, device buffers, error plumbing.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/femb200.h"
+
+namespace femb {
+
+constexpr int kNumSMsB200 = 148;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    if (count == n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// Host-side symbolic structure (block-CSR pattern + contribution lists + tiles).
+struct Symbolic {
+  int32_t bs = 0;              // block size (6 frame, 3 tet10)
+  int32_t nper = 0;            // nodes per element
+  int64_t n_nodes = 0, n_elem = 0;
+  int64_t nnzb = 0;            // number of bs x bs blocks
+  int64_t n_contrib = 0;
+  std::vector<int32_t> rowptr;       // (n_nodes+1)
+  std::vector<int32_t> colidx;       // (nnzb) sorted within each row
+  std::vector<int32_t> blk_row;      // (nnzb) row node of each block
+  std::vector<int32_t> diag_blk;     // (n_nodes) index of block (i,i)
+  std::vector<int32_t> contrib_ptr;  // (nnzb+1)
+  std::vector<uint32_t> contrib;     // (n_contrib) e*nper^2 + a*nper + b, ascending per block
+  std::vector<int32_t> contrib_blk;  // (n_contrib) owning block
+  std::vector<int32_t> tile_ptr;     // (n_tiles+1) node ranges of assembly tiles
+  int32_t tile_max_blocks = 0;       // capacity limits the tiles were packed for
+  int32_t tile_max_contrib = 0;
+  bool is_chain = false;             // path graph(s): block-tridiagonal after chain ordering
+  std::vector<int32_t> chain_order;  // (n_nodes) node visited at chain position k
+};
+
+void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int32_t* conn,
+                    int tile_max_blocks, int tile_max_contrib, Symbolic& out);
+
+enum class Kind { None, Frame, Tet10 };
+
+}  // namespace femb
+
+struct femb_handle {
+  int device = 0;
+  int num_sms = femb::kNumSMsB200;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  femb::Kind kind = femb::Kind::None;
+  int bs = 0;
+  int64_t n_nodes = 0, n_elem = 0, ndof = 0;
+  int64_t launches = 0;  // kernel launches since the counter was last reset
+
+  // mesh (device)
+  femb::DevBuf<double> xyz;        // (n_nodes,3)
+  femb::DevBuf<int32_t> conn;      // (n_elem,nper)
+  femb::DevBuf<int32_t> elem_sec;  // (n_elem)
+  femb::DevBuf<double> sec_props;  // (n_sec,8)
+  int32_t n_sec = 0;
+  double E = 0, G = 0, rho = 0, nu = 0;
+  std::vector<int32_t> h_conn;     // host copy for the symbolic phase
+
+  // pattern (device)
+  femb::Symbolic sym;
+  bool have_symbolic = false, assembled = false;
+  femb::DevBuf<int32_t> rowptr, colidx, blk_row, diag_blk, contrib_ptr, contrib_blk, tile_ptr;
+  femb::DevBuf<uint32_t> contrib;
+  femb::DevBuf<double> Kvals;      // (nnzb, bs, bs)
+  femb::DevBuf<double> Mdiag;      // (n_nodes, bs, bs) frame only
+  femb::DevBuf<unsigned long long> counters;  // device scalars: [0] skipped gauss points
+  int64_t neg_detj = 0;
+
+  // BC + vectors (device)
+  bool have_bc = false;
+  int64_t n_fixed = 0;
+  femb::DevBuf<uint8_t> free_mask;  // (ndof) 1 = free DOF
+  femb::DevBuf<double> f, u0;       // load vector, prescribed values
+  femb::DevBuf<double> b, x, r, z, p, q;
+  femb::DevBuf<double> Dinv;        // block-Jacobi inverse (n_nodes,bs,bs) or Jacobi (ndof)
+  femb::DevBuf<double> partials;    // reduction scratch
+  femb::DevBuf<double> scal;        // device scalars for PCG
+  femb::DevBuf<int32_t> flags;      // [0] done, [1] iterations, [2] ticket counters...
+  bool have_solution = false;
+
+  void* pinned = nullptr;           // small pinned staging area
+  size_t pinned_bytes = 0;
+};
+
+namespace femb {
+
+inline int fail(femb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define FEMB_CUDA(h, expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      return femb::fail((h), _e == cudaErrorMemoryAllocation ? FEMB_ERR_NOMEM : FEMB_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    }                                                                                   \
+  } while (0)
+
+template <typename T>
+inline cudaError_t upload(DevBuf<T>& d, const T* src, size_t count, cudaStream_t s) {
+  cudaError_t e = d.alloc(count);
+  if (e != cudaSuccess || count == 0) return e;
+  return cudaMemcpyAsync(d.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+template <typename T>
+inline cudaError_t upload(DevBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
+  return upload(d, v.data(), v.size(), s);
+}
+
+// ---- kernel launch wrappers implemented in the .cu files ---------------------------------
+int launch_frame_elements(femb_handle* h, double* d_ke, double* d_me);
+int launch_tet10_elements(femb_handle* h, double* d_ke);
+int launch_assemble(femb_handle* h);
+int launch_expand_csr(femb_handle* h, int which, int32_t* d_indptr, int32_t* d_indices, double* d_vals);
+int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st);
+int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials);
+int launch_reactions(femb_handle* h, bool minus_f, double* d_out);
+int setup_bc_vectors(femb_handle* h);
+int launch_frame_stress(femb_handle* h, const double* d_u, double* d_sigma);
+int run_chain_solve(femb_handle* h, femb_stats* st);
+int run_dense_solve(femb_handle* h, femb_stats* st);
+int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda, double* phi, int32_t* n_found,
+              femb_stats* st);
+int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const double* xyz,
+                    const double* sec_props, double E, double G, const uint8_t* fixed_mask,
+                    const double* f, double* u, femb_stats* st);
+int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes);
+
+}  // namespace femb

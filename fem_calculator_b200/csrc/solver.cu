@@ -1,0 +1,502 @@
+// BSR SpMV, boundary-condition masking, block-Jacobi PCG and reaction recovery.
+//
+// Operator.  BCs are eliminated by masking (free_mask): A = P K P + (I - P), P = diag(free).
+// Every Krylov vector keeps exact zeros on the fixed DOFs, so K's fixed COLUMNS multiply
+// zeros and only the fixed ROWS need overriding in the SpMV epilogue — K_ff is never
+// materialised and the un-eliminated K stays available for r = K u - f
+// (BeamSolver.py:412-418, ReactionSolver.py:199-205).
+//
+// SpMV.  BSR with bs x bs row-major blocks, one thread per scalar row: the bs threads of a
+// block row read one contiguous 8*bs*bs-byte block per step with 16-byte loads, x comes
+// through the read-only path (L2 resident: 8 B/DOF).  HBM-bound: 8 B/nnz + 4 B/block.
+//
+// Reductions are two-stage and ordered (per-CTA partial -> last CTA sums the partials in
+// index order), so dot products — and therefore the whole PCG trajectory — are
+// bit-reproducible run to run; float atomics are never used.
+#include "common.cuh"
+
+namespace femb {
+
+constexpr int kVecThreads = 256;
+
+struct Scal {  // device scalar block (doubles)
+  enum { PQ = 0, RZ0 = 1, RZ1 = 2, RR = 3, BB = 4, TOL2 = 5, COUNT = 8 };
+};
+struct Flag {  // device int block
+  enum { DONE = 0, ITERS = 1, TICKET0 = 2, TICKET1 = 3, TICKET2 = 4, COUNT = 8 };
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// CTA-wide ordered sum; result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) s_red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = (l < THREADS / 32) ? s_red[l] : 0.0;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;
+}
+
+// Last-CTA-done ordered reduction of NV interleaved partial arrays (partials[v*stride + cta]).
+// Returns true in ALL threads of the last CTA, whose thread 0 holds the totals in out[].
+template <int THREADS, int NV>
+__device__ __forceinline__ bool grid_reduce(const double (&mine)[NV], double* partials, int stride,
+                                            int* ticket, double* s_red, double (&out)[NV]) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) partials[(size_t)v * stride + blockIdx.x] = mine[v];
+    __threadfence();
+    const int t = atomicAdd(ticket, 1);
+    s_last = (t == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) a += partials[(size_t)v * stride + i];
+    out[v] = block_sum<THREADS>(a, s_red);
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+  return true;
+}
+
+// ------------------------------------------------------------------------------- SpMV
+// y = A x over block rows; MASKED: rows with free_mask==0 return x (identity rows).
+// DOT: also accumulates sum(x_i * y_i) into `dot` through the ordered grid reduction and,
+// being the PCG's first kernel of an iteration, honours the done flag.
+template <int BS, bool MASKED, bool DOT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
+                const double* __restrict__ x, double* __restrict__ y, int64_t nrows,
+                double* partials, int pstride, double* scal, int* flags) {
+  static_assert(BS == 6 || BS == 3, "block size");
+  __shared__ double s_red[THREADS / 32];
+  if (DOT && flags[Flag::DONE]) return;
+  double dot = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < nrows; g += (int64_t)gridDim.x * THREADS) {
+    const int node = (int)(g / BS);
+    const int r = (int)(g - (int64_t)node * BS);
+    const int b0 = __ldg(rowptr + node), b1 = __ldg(rowptr + node + 1);
+    double acc = 0.0;
+    if (BS == 6) {
+#pragma unroll 4
+      for (int b = b0; b < b1; ++b) {
+        const int col = __ldg(colidx + b);
+        const double2* a2 = reinterpret_cast<const double2*>(vals + (size_t)b * 36 + r * 6);
+        const double2* x2 = reinterpret_cast<const double2*>(x + (size_t)col * 6);
+        const double2 a0 = __ldcs(a2), a1 = __ldcs(a2 + 1), a2v = __ldcs(a2 + 2);
+        const double2 x0 = __ldg(x2), x1 = __ldg(x2 + 1), x2v = __ldg(x2 + 2);
+        acc += a0.x * x0.x; acc += a0.y * x0.y; acc += a1.x * x1.x;
+        acc += a1.y * x1.y; acc += a2v.x * x2v.x; acc += a2v.y * x2v.y;
+      }
+    } else {
+#pragma unroll 4
+      for (int b = b0; b < b1; ++b) {
+        const int col = __ldg(colidx + b);
+        const double* a = vals + (size_t)b * 9 + r * 3;
+        const double* xc = x + (size_t)col * 3;
+        acc += __ldcs(a) * __ldg(xc); acc += __ldcs(a + 1) * __ldg(xc + 1); acc += __ldcs(a + 2) * __ldg(xc + 2);
+      }
+    }
+    const double xg = x[g];
+    if (MASKED && !free_mask[g]) acc = xg;
+    y[g] = acc;
+    if (DOT) dot += xg * acc;
+  }
+  if (DOT) {
+    double mine[1], tot[1];
+    mine[0] = block_sum<THREADS>(dot, s_red);
+    if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET0, s_red, tot)) {
+      if (threadIdx.x == 0) scal[Scal::PQ] = tot[0];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- BC
+__global__ void fill_mask_kernel(uint8_t* mask, int64_t n, uint8_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mask[i] = v;
+}
+__global__ void clear_fixed_kernel(uint8_t* mask, const int64_t* fixed, int64_t nf) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += (int64_t)gridDim.x * blockDim.x) mask[fixed[i]] = 0;
+}
+// u0m = prescribed values on fixed DOFs, 0 elsewhere
+__global__ void mask_prescribed_kernel(const double* u0, const uint8_t* mask, double* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = mask[i] ? 0.0 : u0[i];
+}
+// b = free ? f - (K u0)_i : 0     (f_f - k_fs u_s, BeamSolver.py:416)
+__global__ void rhs_kernel(const double* f, const double* Ku0, const uint8_t* mask, double* b, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    b[i] = mask[i] ? (Ku0 ? f[i] - Ku0[i] : f[i]) : 0.0;
+}
+
+// ------------------------------------------------------------------- preconditioner
+// Block-Jacobi: invert the masked diagonal block (fixed rows/cols -> identity) by
+// Gauss-Jordan without pivoting (SPD); a non-positive pivot degrades that row to identity.
+// mode 1 (Jacobi) keeps only the reciprocal diagonal inside the same block layout.
+template <int BS>
+__global__ void precond_setup_kernel(const double* __restrict__ vals, const int32_t* __restrict__ diag_blk,
+                                     const uint8_t* __restrict__ mask, double* __restrict__ Dinv,
+                                     int64_t n_nodes, int mode) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  double A[BS][BS], B[BS][BS];
+  const double* d = vals + (size_t)diag_blk[i] * BS * BS;
+#pragma unroll
+  for (int r = 0; r < BS; ++r)
+#pragma unroll
+    for (int c = 0; c < BS; ++c) {
+      const bool fr = mask[i * BS + r] && mask[i * BS + c];
+      double v = fr ? d[r * BS + c] : (r == c ? 1.0 : 0.0);
+      if (mode != 2 && r != c) v = 0.0;
+      if (mode == 0) v = (r == c) ? 1.0 : 0.0;
+      A[r][c] = v;
+      B[r][c] = (r == c) ? 1.0 : 0.0;
+    }
+#pragma unroll
+  for (int k = 0; k < BS; ++k) {
+    double piv = A[k][k];
+    if (!(piv > 0.0)) {  // not SPD here (e.g. an unconnected point): fall back to identity row
+#pragma unroll
+      for (int c = 0; c < BS; ++c) { A[k][c] = (c == k) ? 1.0 : 0.0; A[c][k] = (c == k) ? 1.0 : 0.0; B[k][c] = (c == k) ? 1.0 : 0.0; }
+      piv = 1.0;
+    }
+    const double ip = 1.0 / piv;
+#pragma unroll
+    for (int c = 0; c < BS; ++c) { A[k][c] *= ip; B[k][c] *= ip; }
+#pragma unroll
+    for (int r = 0; r < BS; ++r) {
+      if (r == k) continue;
+      const double m = A[r][k];
+#pragma unroll
+      for (int c = 0; c < BS; ++c) { A[r][c] -= m * A[k][c]; B[r][c] -= m * B[k][c]; }
+    }
+  }
+  double* o = Dinv + (size_t)i * BS * BS;
+#pragma unroll
+  for (int r = 0; r < BS; ++r)
+#pragma unroll
+    for (int c = 0; c < BS; ++c) o[r * BS + c] = 0.5 * (B[r][c] + B[c][r]);
+}
+
+template <int BS>
+__device__ __forceinline__ double apply_dinv_row(const double* __restrict__ Dinv, int64_t g, const double* rn) {
+  const int64_t node = g / BS;
+  const int r = (int)(g - node * BS);
+  const double* d = Dinv + (size_t)node * BS * BS + r * BS;
+  double z = 0.0;
+#pragma unroll
+  for (int c = 0; c < BS; ++c) z += __ldg(d + c) * rn[c];
+  return z;
+}
+
+// -------------------------------------------------------------------------------- PCG
+// init: x = 0, r = b, z = Dinv r, p = z; rz -> RZ0, bb -> BB, tol2 = rtol^2 * bb
+template <int BS, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, double* __restrict__ x,
+                double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, int64_t n,
+                double rtol, double* partials, int pstride, double* scal, int* flags) {
+  __shared__ double s_red[THREADS / 32];
+  double rz = 0.0, bb = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const int64_t node = g / BS;
+    double rn[BS];
+#pragma unroll
+    for (int c = 0; c < BS; ++c) rn[c] = b[node * BS + c];
+    const double bg = b[g];
+    const double zg = apply_dinv_row<BS>(Dinv, g, rn);
+    x[g] = 0.0; r[g] = bg; z[g] = zg; p[g] = zg;
+    rz += bg * zg; bb += bg * bg;
+  }
+  double mine[2], tot[2];
+  mine[0] = block_sum<THREADS>(rz, s_red);
+  mine[1] = block_sum<THREADS>(bb, s_red);
+  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
+    if (threadIdx.x == 0) {
+      scal[Scal::RZ0] = tot[0]; scal[Scal::RZ1] = tot[0];
+      scal[Scal::BB] = tot[1]; scal[Scal::RR] = tot[1];
+      scal[Scal::TOL2] = rtol * rtol * tot[1];
+      flags[Flag::ITERS] = 0;
+      flags[Flag::DONE] = (tot[1] == 0.0) ? 1 : 0;  // zero load: u = 0 is the answer
+    }
+  }
+}
+
+// x += alpha p; r -= alpha q; z = Dinv r; rz_new, rr ; convergence / breakdown decision
+template <int BS, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pcg_update_xr_kernel(const double* __restrict__ Dinv, const double* __restrict__ p, const double* __restrict__ q,
+                     double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, int64_t n,
+                     int parity, int max_iter, double* partials, int pstride, double* scal, int* flags) {
+  __shared__ double s_red[THREADS / 32];
+  if (flags[Flag::DONE]) return;
+  const double pq = scal[Scal::PQ];
+  const double rz_old = scal[Scal::RZ0 + (parity ^ 1)];
+  const bool bad = !(pq > 0.0);            // K_ff not positive definite along p
+  const double alpha = bad ? 0.0 : rz_old / pq;
+  double rz = 0.0, rr = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const int64_t node = g / BS;
+    double rn[BS];
+#pragma unroll
+    for (int c = 0; c < BS; ++c) rn[c] = r[node * BS + c] - alpha * q[node * BS + c];
+    const int rloc = (int)(g - node * BS);
+    const double rg = rn[rloc];
+    const double zg = apply_dinv_row<BS>(Dinv, g, rn);
+    x[g] += alpha * p[g];
+    z[g] = zg;
+    rz += rg * zg; rr += rg * rg;
+  }
+  // r[g] is also read by the other rows of its node, so it is committed in a second pass.
+  // All rows of a node live in the same CTA and grid-stride step (THREADS % BS == 0), hence
+  // the barrier is enough; the re-read of r and q hits L1.
+  __syncthreads();
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS)
+    r[g] -= alpha * q[g];
+  double mine[2], tot[2];
+  mine[0] = block_sum<THREADS>(rz, s_red);
+  mine[1] = block_sum<THREADS>(rr, s_red);
+  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
+    if (threadIdx.x == 0) {
+      scal[Scal::RZ0 + parity] = tot[0];
+      scal[Scal::RR] = tot[1];
+      const int it = flags[Flag::ITERS] + 1;
+      flags[Flag::ITERS] = it;
+      if (bad) flags[Flag::DONE] = 2;
+      else if (tot[1] <= scal[Scal::TOL2]) flags[Flag::DONE] = 1;
+      else if (it >= max_iter) flags[Flag::DONE] = 3;
+    }
+  }
+}
+
+// p = z + beta p
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pcg_update_p_kernel(const double* __restrict__ z, double* __restrict__ p, int64_t n, int parity,
+                    const double* scal, const int* flags) {
+  if (flags[Flag::DONE]) return;
+  const double beta = scal[Scal::RZ0 + parity] / scal[Scal::RZ0 + (parity ^ 1)];
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS)
+    p[g] = z[g] + beta * p[g];
+}
+
+// out = K u - f (minus_f) or K u
+__global__ void axpy_sub_kernel(double* out, const double* f, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] -= f[i];
+}
+// x[fixed] = prescribed
+__global__ void set_prescribed_kernel(double* x, const double* u0, const uint8_t* mask, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!mask[i]) x[i] = u0[i];
+}
+
+// ---------------------------------------------------------------------------- host side
+static int vec_grid(const femb_handle* h, int64_t n, int threads) {
+  int64_t need = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)h->num_sms * 8;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+// grid for kernels whose CTAs must own whole nodes: chunk = THREADS rows must be a multiple
+// of BS in the grid-stride pattern.  THREADS=256 is not a multiple of 6, so those kernels
+// use kRowThreads = 192 (divisible by 6 and 3).
+constexpr int kRowThreads = 192;
+
+int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials) {
+  const int64_t n = h->ndof;
+  const int grid = vec_grid(h, n, kRowThreads);
+  const int pstride = h->num_sms * 8;
+#define SPMV(BS, M, D)                                                                         \
+  bsr_spmv_kernel<BS, M, D, kRowThreads><<<grid, kRowThreads, 0, h->stream>>>(                  \
+      h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, x, y, n, dot_partials, pstride,    \
+      h->scal.p, h->flags.p)
+  const bool dot = dot_partials != nullptr;
+  if (h->bs == 6) {
+    if (masked && dot) SPMV(6, true, true);
+    else if (masked) SPMV(6, true, false);
+    else SPMV(6, false, false);
+  } else {
+    if (masked && dot) SPMV(3, true, true);
+    else if (masked) SPMV(3, true, false);
+    else SPMV(3, false, false);
+  }
+#undef SPMV
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+int setup_bc_vectors(femb_handle* h) {
+  const int64_t n = h->ndof;
+  FEMB_CUDA(h, h->b.alloc(n));
+  FEMB_CUDA(h, h->x.alloc(n));
+  FEMB_CUDA(h, h->r.alloc(n));
+  FEMB_CUDA(h, h->z.alloc(n));
+  FEMB_CUDA(h, h->p.alloc(n));
+  FEMB_CUDA(h, h->q.alloc(n));
+  FEMB_CUDA(h, h->partials.alloc((size_t)h->num_sms * 8 * 4));
+  FEMB_CUDA(h, h->scal.alloc(Scal::COUNT));
+  FEMB_CUDA(h, h->flags.alloc(Flag::COUNT));
+  FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
+  FEMB_CUDA(h, cudaMemsetAsync(h->scal.p, 0, sizeof(double) * Scal::COUNT, h->stream));
+  return FEMB_OK;
+}
+
+// b = masked(f - K u0)   (u0 == nullptr -> b = masked f)
+static int build_rhs(femb_handle* h, bool have_u0) {
+  const int64_t n = h->ndof;
+  const int g = vec_grid(h, n, kVecThreads);
+  if (have_u0) {
+    mask_prescribed_kernel<<<g, kVecThreads, 0, h->stream>>>(h->u0.p, h->free_mask.p, h->p.p, n);
+    h->launches++;
+    int rc = launch_spmv(h, h->p.p, h->q.p, false, nullptr);
+    if (rc) return rc;
+    rhs_kernel<<<g, kVecThreads, 0, h->stream>>>(h->f.p, h->q.p, h->free_mask.p, h->b.p, n);
+  } else {
+    rhs_kernel<<<g, kVecThreads, 0, h->stream>>>(h->f.p, nullptr, h->free_mask.p, h->b.p, n);
+  }
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+static int setup_precond(femb_handle* h, int mode) {
+  FEMB_CUDA(h, h->Dinv.alloc((size_t)h->n_nodes * h->bs * h->bs));
+  const int grid = (int)((h->n_nodes + 127) / 128);
+  if (h->bs == 6)
+    precond_setup_kernel<6><<<grid, 128, 0, h->stream>>>(h->Kvals.p, h->diag_blk.p, h->free_mask.p, h->Dinv.p, h->n_nodes, mode);
+  else
+    precond_setup_kernel<3><<<grid, 128, 0, h->stream>>>(h->Kvals.p, h->diag_blk.p, h->free_mask.p, h->Dinv.p, h->n_nodes, mode);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+struct PcgPeek {
+  int32_t flags[Flag::COUNT];
+  double scal[Scal::COUNT];
+};
+
+int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
+  const int64_t n = h->ndof;
+  const int gridv = vec_grid(h, n, kRowThreads);
+  const int pstride = h->num_sms * 8;
+  int rc = build_rhs(h, h->u0.p != nullptr);
+  if (rc) return rc;
+  rc = setup_precond(h, o.precond);
+  if (rc) return rc;
+  FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
+#define INIT(BS) pcg_init_kernel<BS, kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->b.p, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, n, o.rtol, h->partials.p, pstride, h->scal.p, h->flags.p)
+  if (h->bs == 6) INIT(6); else INIT(3);
+#undef INIT
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+
+  PcgPeek* peek = reinterpret_cast<PcgPeek*>(h->pinned);
+  const int check = o.check_every > 0 ? o.check_every : 50;
+  const bool prof = o.profile != 0;
+  std::vector<cudaEvent_t> evs;
+  int spmv_launches = 0;
+  int it = 0;
+  int done = 0;
+  while (!done && it < o.max_iter) {
+    const int batch = (o.max_iter - it) < check ? (o.max_iter - it) : check;
+    for (int k = 0; k < batch; ++k, ++it) {
+      const int parity = (it + 1) & 1;
+      if (prof) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, h->stream);
+        rc = launch_spmv(h, h->p.p, h->q.p, true, h->partials.p);
+        cudaEventRecord(b, h->stream);
+        evs.push_back(a); evs.push_back(b);
+      } else {
+        rc = launch_spmv(h, h->p.p, h->q.p, true, h->partials.p);
+      }
+      if (rc) return rc;
+      ++spmv_launches;
+#define UPD(BS) pcg_update_xr_kernel<BS, kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
+      if (h->bs == 6) UPD(6); else UPD(3);
+#undef UPD
+      pcg_update_p_kernel<kVecThreads><<<vec_grid(h, n, kVecThreads), kVecThreads, 0, h->stream>>>(h->z.p, h->p.p, n, parity, h->scal.p, h->flags.p);
+      h->launches += 2;
+    }
+    FEMB_CUDA(h, cudaGetLastError());
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->scal, h->scal.p, sizeof(peek->scal), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    done = peek->flags[Flag::DONE];
+  }
+  FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, cudaMemcpyAsync(peek->scal, h->scal.p, sizeof(peek->scal), cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  done = peek->flags[Flag::DONE];
+  if (st) {
+    st->method_used = FEMB_SOLVER_PCG;
+    st->iterations = peek->flags[Flag::ITERS];
+    st->converged = (done == 1);
+    st->spmv_launches = spmv_launches;
+    const double bb = peek->scal[Scal::BB];
+    st->rel_residual = bb > 0.0 ? sqrt(peek->scal[Scal::RR] / bb) : 0.0;
+    st->spmv_ms = 0.0;
+    for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+      st->spmv_ms += ms;
+    }
+  }
+  for (auto e : evs) cudaEventDestroy(e);
+  if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");
+  if (done != 1) return fail(h, FEMB_ERR_NOT_CONVERGED, "PCG did not reach rtol within max_iter");
+  return FEMB_OK;
+}
+
+int setup_rhs_for_direct(femb_handle* h) { return build_rhs(h, h->u0.p != nullptr); }
+
+// x[fixed] = prescribed value (the reference always prescribes 0: BeamSolver.py:413,418)
+int apply_prescribed(femb_handle* h) {
+  if (!h->u0.p) return FEMB_OK;
+  set_prescribed_kernel<<<vec_grid(h, h->ndof, kVecThreads), kVecThreads, 0, h->stream>>>(h->x.p, h->u0.p, h->free_mask.p, h->ndof);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+int launch_reactions(femb_handle* h, bool minus_f, double* d_out) {
+  int rc = launch_spmv(h, h->x.p, d_out, false, nullptr);
+  if (rc) return rc;
+  if (minus_f) {
+    axpy_sub_kernel<<<vec_grid(h, h->ndof, kVecThreads), kVecThreads, 0, h->stream>>>(d_out, h->f.p, h->ndof);
+    h->launches++;
+    FEMB_CUDA(h, cudaGetLastError());
+  }
+  return FEMB_OK;
+}
+
+int bc_build_mask(femb_handle* h, const int64_t* d_fixed, int64_t n_fixed) {
+  const int64_t n = h->ndof;
+  fill_mask_kernel<<<vec_grid(h, n, kVecThreads), kVecThreads, 0, h->stream>>>(h->free_mask.p, n, 1);
+  if (n_fixed > 0)
+    clear_fixed_kernel<<<vec_grid(h, n_fixed, kVecThreads), kVecThreads, 0, h->stream>>>(h->free_mask.p, d_fixed, n_fixed);
+  h->launches += 2;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+}  // namespace femb

@@ -1,0 +1,197 @@
+/* femb200 — C ABI of the B200-native FEM hot path (libfemb200.so).
+ *
+ * Drop-in boundary for the numerical core of euler8511/FEM-calculator.  The reference has
+ * no FFI of its own: its "interface" for this path is a set of Python methods on two
+ * classes.  Each entry point below names the reference code it replaces (file:line into
+ * /root/reference); fem_calculator_b200/compat.py binds them with ctypes and re-creates
+ * the reference's Python signatures on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; femb_last_error(h) gives the text;
+ *   - all array arguments are caller-owned, C-contiguous HOST pointers (the library copies
+ *     to / from HBM on the handle's stream); a NULL output pointer means "leave it on the
+ *     device, do not copy back";
+ *   - indices: node / element / DOF numbers are 0-based; DOF = bs*node + c with bs = 6
+ *     (frame: ux,uy,uz,rx,ry,rz — BeamSolver.py:354,360,390-393) or bs = 3 (Tet10 —
+ *     ReactionSolver.py:148);
+ *   - a handle owns one CUDA device + one stream and is not thread-safe; different
+ *     handles are independent; there is no hidden global state and NO CPU fallback: every
+ *     compute entry point fails with FEMB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef FEMB200_H
+#define FEMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct femb_handle femb_handle;
+
+enum {
+  FEMB_OK = 0,
+  FEMB_ERR_ARG = -1,       /* bad argument / call order */
+  FEMB_ERR_CUDA = -2,      /* CUDA runtime error or no usable device */
+  FEMB_ERR_NOT_CONVERGED = -3,
+  FEMB_ERR_SINGULAR = -4,  /* non-positive pivot / breakdown: K_ff not SPD */
+  FEMB_ERR_NOMEM = -5
+};
+
+/* which matrix femb_get_csr exports */
+enum { FEMB_MAT_K = 0, FEMB_MAT_M = 1 };
+
+/* femb_solve_opts.method */
+enum {
+  FEMB_SOLVER_AUTO = 0,    /* chain -> block-tridiagonal; tiny -> dense Cholesky; else PCG */
+  FEMB_SOLVER_PCG = 1,     /* preconditioned conjugate gradients on the BSR operator */
+  FEMB_SOLVER_CHAIN = 2,   /* direct block-tridiagonal Cholesky (path graphs only) */
+  FEMB_SOLVER_DENSE = 3    /* dense FP64 Cholesky of K_ff (small systems) */
+};
+
+/* femb_solve_opts.precond */
+enum { FEMB_PRECOND_NONE = 0, FEMB_PRECOND_JACOBI = 1, FEMB_PRECOND_BLOCK_JACOBI = 2 };
+
+typedef struct {
+  int32_t method;        /* FEMB_SOLVER_*                         default AUTO            */
+  int32_t precond;       /* FEMB_PRECOND_*                        default BLOCK_JACOBI    */
+  int32_t max_iter;      /* PCG iteration cap                     default 200000          */
+  int32_t check_every;   /* host polls convergence every N its    default 50              */
+  double rtol;           /* stop at ||r||_2 <= rtol*||b||_2       default 1e-12           */
+  int32_t profile;       /* 1: time every SpMV launch with CUDA events (adds overhead)    */
+  int32_t reserved;
+} femb_solve_opts;
+
+typedef struct {
+  int32_t k;             /* number of lowest modes wanted                                  */
+  int32_t block;         /* LOBPCG block size (>= k; 0 = k + max(4, k/4))                  */
+  int32_t max_iter;      /* default 5000                                                   */
+  int32_t reserved;
+  double rtol;           /* ||K phi - lambda M phi|| <= rtol*||K phi||   default 1e-8      */
+  double lambda_min;     /* keep eigenvalues > lambda_min (BeamSolver.py:448)  default 1e-6 */
+} femb_eig_opts;
+
+typedef struct {
+  int32_t method_used;
+  int32_t iterations;
+  int32_t converged;
+  int32_t spmv_launches;      /* SpMV kernel launches in this call                         */
+  int32_t kernel_launches;    /* all kernel launches of this library in this call          */
+  int32_t reserved;
+  double rel_residual;        /* final ||r||/||b||                                         */
+  double device_ms;           /* CUDA-event time of the whole call on the handle's stream  */
+  double spmv_ms;             /* summed SpMV device time (only when opts.profile)          */
+} femb_stats;
+
+int femb_version(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int femb_device_count(void);
+
+int femb_create(int device, femb_handle** out);
+void femb_destroy(femb_handle* h);
+const char* femb_last_error(const femb_handle* h);
+
+/* ---- frame (3-D Timoshenko / Euler-Bernoulli beam) path ------------------------------
+ * Replaces the per-element loop of BeamAnalysisWindow.run_simulation, BeamSolver.py:364-393,
+ * i.e. get_timoshenko_stiffness_matrix (:646-660), get_lumped_mass_matrix (:662-675),
+ * the direction-cosine matrix (:378-384), R^T k R / R^T m R (:386-388) and the scatter
+ * (:390-393).
+ *   xyz       (n_nodes,3) float64  — mesh.points                       (:372)
+ *   conn      (n_elem,2)  int64    — mesh.cells_dict['line']           (:364)
+ *   elem_sec  (n_elem)    int32    — index into sec_props per element  (:365-371)
+ *   sec_props (n_sec,8)   float64  — rows (A, I_x, I_y, J, kappa_y, kappa_z, c_y_max,
+ *                                    c_z_max) = calculate_section_properties' record (:79)
+ *   E, G, rho                      — :350-352 and the literal 7850 at :376            */
+int femb_frame_set_mesh(femb_handle* h, int64_t n_nodes, int64_t n_elem, const double* xyz,
+                        const int64_t* conn, const int32_t* elem_sec, int32_t n_sec,
+                        const double* sec_props, double E, double G, double rho);
+
+/* Parity export of the per-element global-axis matrices R^T k R and R^T m R
+ * (BeamSolver.py:387-388): ke, me are (n_elem,12,12) float64, either may be NULL. */
+int femb_frame_elements(femb_handle* h, double* ke, double* me);
+
+/* ---- Tet10 path ----------------------------------------------------------------------
+ * Replaces ForceAnalysis._create_material_matrix / _shape_funcs_tet10 /
+ * assemble_stiffness_matrix, ReactionSolver.py:87-152.
+ *   conn10 (n_elem,10) int64 in meshio/VTK node order (:102-110).
+ * Parity constants kept: Gauss literals 0.58541020 / 0.13819660 (:120-123), w = 1/4
+ * (:124), Gauss points with detJ <= 1e-12 skipped and counted (:133-135).              */
+int femb_tet10_set_mesh(femb_handle* h, int64_t n_nodes, int64_t n_elem, const double* xyz,
+                        const int64_t* conn10, double E, double nu);
+/* ke: (n_elem,30,30) float64 parity export of Ke (ReactionSolver.py:128-146). */
+int femb_tet10_elements(femb_handle* h, double* ke);
+/* ForceAnalysis.negative_detJ_count (ReactionSolver.py:49,134) after femb_assemble. */
+int64_t femb_tet10_negative_detj(const femb_handle* h);
+
+/* ---- shared: assembly, BC, solve, modal ----------------------------------------------
+ * femb_assemble: symbolic pattern on first call (block-CSR over node adjacency, columns
+ * sorted, one diagonal block per node), then the fused element+assembly kernel:
+ * deterministic, atomic-free, bit-reproducible run to run.  Replaces the scatter at
+ * BeamSolver.py:390-393 (dense K, M) and ReactionSolver.py:148-151 (lil -> csr).        */
+int femb_assemble(femb_handle* h);
+
+/* CSR export (two calls: sizes, then data).  Scalar CSR expanded from the stored BSR:
+ * indices sorted within rows, no duplicates, structural zeros kept.  which = FEMB_MAT_K
+ * or FEMB_MAT_M (frame only; M is block-diagonal).                                      */
+int femb_get_csr_size(femb_handle* h, int which, int64_t* n_rows, int64_t* nnz);
+int femb_get_csr(femb_handle* h, int which, int32_t* indptr, int32_t* indices, double* vals);
+
+/* Boundary conditions + load vector: replaces BeamSolver.py:395-416 /
+ * ReactionSolver.py:174,194,199-200 (the group -> node -> DOF bookkeeping stays in the
+ * Python shim).  fixed_dofs: sorted unique global DOFs (Up_node / fixed_dofs); f: (ndof)
+ * nodal loads; u_prescribed: (ndof) or NULL (the reference always prescribes 0,
+ * BeamSolver.py:413).  Elimination is applied on the device as a DOF mask on the
+ * operator, which is algebraically K_ff with u[fixed] = prescribed.                    */
+int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, const double* f,
+                const double* u_prescribed);
+
+/* Static solve K u = F + reaction recovery: replaces np.linalg.solve(k_ff, f_f)
+ * (BeamSolver.py:417-418) and spsolve + K @ u (ReactionSolver.py:201-205).
+ *   u          (ndof) out, fixed DOFs carry the prescribed value
+ *   reactions  (ndof) out, K_full @ u - f   (minus_f != 0)   [frame convention]
+ *                       or K_full @ u       (minus_f == 0)   [ReactionSolver.py:205]    */
+int femb_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, double* u,
+                      double* reactions, femb_stats* stats);
+
+/* Lowest-k modes of K_ff phi = lambda M_ff phi: replaces inv(m_ff) @ k_ff + qr_algorithm
+ * (BeamSolver.py:440-455,467-481).  lambda: (k) ascending, eigenvalues <= lambda_min
+ * dropped (:448); phi: (ndof,k) column-major (phi[j*ndof + i]), M-normalised, zeros on
+ * fixed DOFs (:453-455).  n_found receives the number of modes returned.               */
+int femb_modal(femb_handle* h, const femb_eig_opts* opts, double* lambda, double* phi,
+               int32_t* n_found, femb_stats* stats);
+
+/* Node-averaged axial + bending stress: replaces BeamSolver.py:420-438.  u: (ndof) or
+ * NULL to use the last solution held on the device; sigma_node: (n_nodes).             */
+int femb_frame_stress(femb_handle* h, const double* u, double* sigma_node);
+
+/* ---- batched independent chain models (BASELINE config 4) ----------------------------
+ * n_models cantilever/chain models of n_elem elements each (nodes 0..n_elem in chain
+ * order along xyz), one section record per model, solved by a batched block-tridiagonal
+ * Cholesky (one warp per model).  Equivalent to n_models calls of run_simulation's
+ * static part (BeamSolver.py:360-418).
+ *   xyz        (n_nodes,3) shared node coordinates, n_nodes = n_elem+1
+ *   sec_props  (n_models,8)
+ *   fixed_mask (ndof) uint8, 1 = fixed DOF, shared by all models
+ *   f          (n_models, ndof) loads;  u (n_models, ndof) out                          */
+int femb_frame_batch_solve(femb_handle* h, int64_t n_models, int64_t n_elem, const double* xyz,
+                           const double* sec_props, double E, double G,
+                           const uint8_t* fixed_mask, const double* f, double* u,
+                           femb_stats* stats);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------
+ * Time `reps` back-to-back launches of one kernel with CUDA events on the handle's stream
+ * (after `warm` untimed launches); *ms receives the mean per launch, *bytes the
+ * algorithmic bytes of one launch.  which: 0 = BSR SpMV (masked
+ * K_ff operator), 1 = fused element+assembly, 2 = one full PCG iteration.               */
+int femb_time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes);
+
+/* Host-only symbolic analysis (no GPU needed; exercised by the CPU test-suite):
+ * block-CSR pattern of an element mesh.  Two calls: pass NULL outputs to get sizes.     */
+int femb_symbolic_pattern(int64_t n_nodes, int64_t n_elem, int32_t nodes_per_elem,
+                          const int64_t* conn, int64_t* n_blocks, int32_t* rowptr,
+                          int32_t* colidx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMB200_H */
