@@ -297,7 +297,7 @@ int femb_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, 
   if (method == FEMB_SOLVER_AUTO) {
     const int64_t nfree = h->ndof - h->n_fixed;
     if (h->kind == Kind::Frame && h->sym.is_chain) method = FEMB_SOLVER_CHAIN;
-    else if (nfree <= 2048) method = FEMB_SOLVER_DENSE;
+    else if (h->ndof <= 2048 && nfree > 0) method = FEMB_SOLVER_DENSE;
     else method = FEMB_SOLVER_PCG;
   }
   if (method == FEMB_SOLVER_PCG) rc = run_pcg(h, o, &st);
