@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the FEM hot path on B200 (contract in the task prompt).
+
+Metric (BASELINE.json): DOF/s of the static solve at ~1M DOF.  One "step" = one pass of the
+hot path over the synthetic BASELINE config-3 frame (56x56x54 lattice, 169,344 nodes,
+1,016,064 DOF, 498,848 elements, box/C/L sections, 5 % seeded node jitter):
+    fused element+assembly  ->  BC mask / RHS  ->  Jacobi-type PCG to ||r||/||b|| <= 1e-12
+    ->  reaction recovery K u - f.
+`value`  : free DOFs / step, device-timed (CUDA events on the library's stream), mesh and
+           loads resident in HBM.  Every step re-assembles a matrix of 359 MB (> 126 MB L2)
+           and streams it ~7k times, so inputs are larger than L2 (no flush needed).
+`e2e`    : the same metric through the reference-shaped entry point
+           (compat.BeamAnalysisB200.run_simulation: host numpy arrays in, u / reactions /
+           stresses out, symbolic analysis + all H2D/D2H inside the timed region).
+`roofline`: the dominant kernel (BSR SpMV, ~70 % of the step), CUDA-event-timed inside the
+           timed steps (every 8th launch), against MEASURED_PEAKS.json.
+N > 1 (torchrun): independent load cases of the same frame, one per GPU (weak scaling, no
+data-path collective; north_star: "independent load cases ... dealt out one batch per GPU").
+`--impl reference`: the CPU oracle port of the reference path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+LATTICE = (56, 56, 54)
+JITTER = 0.05
+RTOL = 1e-12
+SAMPLE_LATTICE = (40, 40, 38)
+SAMPLE_ITERS = 400
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_case(load_scale=1.0, lattice=LATTICE):
+    from fem_calculator_b200 import compat, meshgen
+    from fem_calculator_b200.sections import calculate_section_properties as csp
+    mesh, sec, bc = meshgen.lattice_frame_case(*lattice, jitter=JITTER,
+                                               load=(100.0 * load_scale, 0.0, -1000.0 * load_scale))
+    es, props, _ = compat.frame_section_table(mesh, sec, csp)
+    fixed, f = compat.frame_bc_vectors(mesh, bc, len(mesh.points))
+    return mesh, sec, bc, es, props, fixed, f
+
+
+def cpu_baseline_sample(full_n_elem, full_n_free, full_iterations):
+    """Oracle port on a bounded sample, scaled to the full workload (oracle/cpu_baseline.py)."""
+    from oracle import cpu_baseline as CB
+    mesh, sec, bc, es, props, fixed, f = build_case(lattice=SAMPLE_LATTICE)
+    from fem_calculator_b200 import meshgen
+    s = CB.lattice_static_sample(mesh, es, props, bc, meshgen.E_STEEL, meshgen.NU_STEEL, cg_iters=SAMPLE_ITERS)
+    dofs, t_full = CB.scaled_static_dof_per_s(s, full_n_elem, full_n_free, full_iterations)
+    return dofs, t_full, s
+
+
+def sample_text(s, iters):
+    return (f"oracle/ref_sparse port: {SAMPLE_LATTICE[0]}x{SAMPLE_LATTICE[1]}x{SAMPLE_LATTICE[2]} lattice slice "
+            f"({s['n_elem']} elements, {s['n_free']} free DOF): numpy element formation + scipy COO->CSR "
+            f"({s['t_assemble']:.2f} s) + {SAMPLE_ITERS} Jacobi-PCG iterations ({s['t_per_iter']*1e3:.2f} ms each); "
+            f"scaled linearly in elements to 498,848 elements and to the {iters} iterations the same "
+            f"Jacobi-PCG needs at full size for rtol 1e-12")
+
+
+JACOBI_ITERS_FULL = 6931  # Jacobi-PCG iterations at full size, rtol 1e-12 (profiles/r01_*, measured on B200)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_nodes = LATTICE[0] * LATTICE[1] * LATTICE[2]
+    n_free = 6 * (n_nodes - LATTICE[0] * LATTICE[1])
+    n_elem = (LATTICE[0] - 1) * LATTICE[1] * LATTICE[2] + LATTICE[0] * (LATTICE[1] - 1) * LATTICE[2] + \
+        LATTICE[0] * LATTICE[1] * (LATTICE[2] - 1)
+    vals, s = [], None
+    for i in range(args.warmup + args.steps):
+        dofs, t_full, s = cpu_baseline_sample(n_elem, n_free, JACOBI_ITERS_FULL)
+        if i >= args.warmup:
+            vals.append((dofs, t_full))
+    v = statistics.mean(x[0] for x in vals)
+    t = statistics.mean(x[1] for x in vals)
+    out = {"impl": "reference", "metric": "static_solve_dof_per_s", "value": v, "unit": "DOF/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(),
+           "cpu_baseline": {"value": v, "unit": "DOF/s", "cores": 1, "kind": "port", "sample": sample_text(s, JACOBI_ITERS_FULL)},
+           "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(parallel="1 GPU"):
+    return {"workload": "BASELINE configs[2]: synthetic gmsh-like 3D space frame, 56x56x54 lattice, 169,344 nodes / "
+                        "1,016,064 DOF (997,248 free), 498,848 Timoshenko elements, box/C/L sections, base fixed, "
+                        "loads on all top nodes; static solve K u = F (PCG rtol 1e-12) with reaction recovery",
+            "step": "fused element+assembly -> BC -> PCG -> reactions", "l2": "inputs larger than L2 (359 MB matrix)",
+            "parallelism": parallel}
+
+
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from fem_calculator_b200 import _lib as L
+    from fem_calculator_b200 import compat, meshgen
+    from fem_calculator_b200.api import FrameModel
+    from fem_calculator_b200.sections import calculate_section_properties as csp
+
+    E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+    mesh, sec, bc, es, props, fixed, f = build_case(load_scale=1.0 + 0.25 * rank)  # one load case per GPU
+    n_free = len(f) - len(fixed)
+    n_elem = len(es)
+    m = FrameModel(local)
+    m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)))
+    m.assemble()
+    m.set_bc(fixed, f)
+    solve_kw = dict(method=L.SOLVER_PCG, precond=L.PRECOND_JACOBI, rtol=RTOL, want_u=False, want_reactions=False)
+
+    def step(profile=0):
+        m.assemble()
+        _, _, st = m.solve_static(profile=profile, **solve_kw)
+        return st
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    m.timer_start()
+    stats = [step(profile=8) for _ in range(args.steps)]
+    total_ms = m.timer_stop()
+    clocks = sampler.stop()
+    barrier()
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n_free / (ms_per_step / 1e3)
+    launches = sum(s["kernel_launches"] for s in stats) + args.steps  # + one assembly launch per step
+    iters = stats[-1]["iterations"]
+    spmv_ms = sum(s["spmv_ms"] for s in stats) / max(1, sum(s["spmv_timed"] for s in stats))
+    spmv_share = spmv_ms * sum(s["spmv_launches"] for s in stats) / total_ms if world == 1 else None
+
+    # per-kernel roofline numbers (algorithmic bytes: DESIGN.md §kernels)
+    peak, peak_src = peaks()
+    _, spmv_bytes = m.time_kernel(0, 1, 1)
+    asm_ms, asm_bytes = m.time_kernel(1, 3, 20)
+    spmv_b2b_ms, _ = m.time_kernel(0, 3, 50)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_spmv_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    roofline = {"kernel": "bsr_spmv_kernel<6,masked,dot> (inside PCG)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "share_of_step": spmv_share,
+                "traffic": traffic}
+    extra = {
+        "pcg": {"iterations": iters, "ms_per_iteration": stats[-1]["device_ms"] / max(1, iters),
+                "rel_residual": stats[-1]["rel_residual"], "precond": "jacobi"},
+        "assembly": {"kernel": "assemble_tiles_kernel<FrameEl> (fused element+assembly)", "ms": asm_ms,
+                     "elements_per_s": n_elem / (asm_ms * 1e-3), "achieved_gbs": asm_bytes / (asm_ms * 1e-3) / 1e9,
+                     "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": asm_bytes},
+        "spmv_back_to_back": {"ms": spmv_b2b_ms, "achieved_gbs": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9,
+                              "frac": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9 / peak},
+    }
+    m.close()
+
+    # end-to-end through the reference-shaped entry point, host buffers in / out
+    e2e_steps = max(1, min(args.steps, 3))
+    w = compat.BeamAnalysisB200(mesh, sec, bc, E, nu, device=local)
+    w.run_simulation(k_modes=0, solver=L.SOLVER_PCG, rtol=RTOL)  # warm-up (context, allocator)
+    L.io_bytes(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        w.run_simulation(k_modes=0, solver=L.SOLVER_PCG, rtol=RTOL)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    barrier()
+    h2d, d2h = L.io_bytes()
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * n_free / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": h2d // e2e_steps,
+           "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "fem_calculator_b200.compat.BeamAnalysisB200.run_simulation (BeamSolver.py:345 signature), "
+                  "timed with the host clock around the call"}
+
+    out = {"metric": "static_solve_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict("1 GPU" if world == 1 else f"{world} independent load cases, one per GPU (no collective)"),
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+    out.update(extra)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # Jacobi-PCG iteration count at full size comes from this very run (same algorithm, same rtol)
+        dofs, t_full, s = cpu_baseline_sample(n_elem, n_free, iters)
+        out["cpu_baseline"] = {"value": dofs, "unit": "DOF/s", "cores": 1, "kind": "port",
+                               "sample": sample_text(s, iters), "est_seconds_full": t_full}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,7 +32,7 @@ class EigOpts(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("method_used", C.c_int32), ("iterations", C.c_int32), ("converged", C.c_int32),
-                ("spmv_launches", C.c_int32), ("kernel_launches", C.c_int32), ("reserved", C.c_int32),
+                ("spmv_launches", C.c_int32), ("kernel_launches", C.c_int32), ("spmv_timed", C.c_int32),
                 ("rel_residual", C.c_double), ("device_ms", C.c_double), ("spmv_ms", C.c_double)]
 
     def as_dict(self):
@@ -74,6 +74,8 @@ SIGNATURES = {
     "femb_frame_batch_solve": (C.c_int, [_P, C.c_int64, C.c_int64, _F64, _F64, C.c_double, C.c_double,
                                          _U8, _F64, _P, C.POINTER(Stats)]),
     "femb_time_kernel": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "femb_timer": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "femb_io_bytes": (None, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
     "femb_symbolic_pattern": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _I64, C.POINTER(C.c_int64), _P, _P]),
 }
 
@@ -108,3 +110,10 @@ def ptr(a):
 
 def device_count() -> int:
     return int(load().femb_device_count())
+
+
+def io_bytes(reset=False):
+    """(host->device, device->host) bytes copied through the library since the last reset."""
+    a, b = C.c_int64(), C.c_int64()
+    load().femb_io_bytes(C.byref(a), C.byref(b), int(reset))
+    return a.value, b.value

@@ -86,6 +86,14 @@ class Handle:
         n = nf.value
         return lam[:n].copy(), np.ascontiguousarray(phi[:n].T), self.last_stats
 
+    def timer_start(self):
+        self._check(self.lib.femb_timer(self._h, 0, None))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.femb_timer(self._h, 1, C.byref(ms)))
+        return ms.value
+
     def time_kernel(self, which, warm=3, reps=20):
         ms, by = C.c_double(), C.c_double()
         self._check(self.lib.femb_time_kernel(self._h, which, warm, reps, C.byref(ms), C.byref(by)))

@@ -15,9 +15,19 @@ static int need(femb_handle* h, bool cond, const char* msg) {
   return cond ? FEMB_OK : fail(h, FEMB_ERR_ARG, msg);
 }
 
+namespace femb {
+long long g_h2d_bytes = 0, g_d2h_bytes = 0;
+}
+
 extern "C" {
 
 int femb_version(void) { return 100; }
+
+void femb_io_bytes(int64_t* h2d, int64_t* d2h, int reset) {
+  if (h2d) *h2d = femb::g_h2d_bytes;
+  if (d2h) *d2h = femb::g_d2h_bytes;
+  if (reset) femb::g_h2d_bytes = femb::g_d2h_bytes = 0;
+}
 
 int femb_device_count(void) {
   int n = 0;
@@ -62,6 +72,8 @@ void femb_destroy(femb_handle* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -124,8 +136,8 @@ int femb_frame_elements(femb_handle* h, double* ke, double* me) {
   if (me) FEMB_CUDA(h, dm.alloc(cnt));
   int rc = launch_frame_elements(h, dk.p, dm.p);
   if (rc) return rc;
-  if (ke) FEMB_CUDA(h, cudaMemcpyAsync(ke, dk.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
-  if (me) FEMB_CUDA(h, cudaMemcpyAsync(me, dm.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (ke) FEMB_CUDA(h, download(ke, dk.p, cnt * 8, h->stream));
+  if (me) FEMB_CUDA(h, download(me, dm.p, cnt * 8, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   return FEMB_OK;
 }
@@ -138,7 +150,7 @@ int femb_tet10_elements(femb_handle* h, double* ke) {
   FEMB_CUDA(h, dk.alloc(cnt));
   int rc = launch_tet10_elements(h, dk.p);
   if (rc) return rc;
-  FEMB_CUDA(h, cudaMemcpyAsync(ke, dk.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, download(ke, dk.p, cnt * 8, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   return FEMB_OK;
 }
@@ -179,7 +191,7 @@ int femb_assemble(femb_handle* h) {
   if (rc) return rc;
   if (h->kind == Kind::Tet10) {
     unsigned long long* pc = reinterpret_cast<unsigned long long*>(h->pinned);
-    FEMB_CUDA(h, cudaMemcpyAsync(pc, h->counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, download(pc, h->counters.p, sizeof(unsigned long long), h->stream));
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->neg_detj = (int64_t)pc[0];
   } else {
@@ -206,7 +218,7 @@ int femb_get_csr(femb_handle* h, int which, int32_t* indptr, int32_t* indices, d
   if (which == FEMB_MAT_K) {
     if (S.nnzb * (int64_t)bs2 >= INT32_MAX) return fail(h, FEMB_ERR_ARG, "CSR export needs nnz < 2^31");
     std::vector<double> bv((size_t)S.nnzb * bs2);
-    FEMB_CUDA(h, cudaMemcpyAsync(bv.data(), h->Kvals.p, bv.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, download(bv.data(), h->Kvals.p, bv.size() * 8, h->stream));
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
     int64_t pos = 0;
     for (int64_t i = 0; i < h->n_nodes; ++i) {
@@ -225,7 +237,7 @@ int femb_get_csr(femb_handle* h, int which, int32_t* indptr, int32_t* indices, d
   }
   if (which == FEMB_MAT_M && h->kind == Kind::Frame) {
     std::vector<double> bv((size_t)h->n_nodes * bs2);
-    FEMB_CUDA(h, cudaMemcpyAsync(bv.data(), h->Mdiag.p, bv.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, download(bv.data(), h->Mdiag.p, bv.size() * 8, h->stream));
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
     int64_t pos = 0;
     for (int64_t i = 0; i < h->n_nodes; ++i)
@@ -307,13 +319,12 @@ int femb_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, 
   if (rc == FEMB_OK) rc = apply_prescribed(h);
   if (rc == FEMB_OK) {
     h->have_solution = true;
-    if (reactions) {
-      rc = launch_reactions(h, minus_f != 0, h->q.p);
-      if (rc == FEMB_OK)
-        FEMB_CUDA(h, cudaMemcpyAsync(reactions, h->q.p, (size_t)h->ndof * 8, cudaMemcpyDeviceToHost, h->stream));
-    }
+    // reaction recovery always runs on the device (it is part of the path); the copy is optional
+    rc = launch_reactions(h, minus_f != 0, h->q.p);
+    if (rc == FEMB_OK && reactions)
+      FEMB_CUDA(h, download(reactions, h->q.p, (size_t)h->ndof * 8, h->stream));
     if (rc == FEMB_OK && u)
-      FEMB_CUDA(h, cudaMemcpyAsync(u, h->x.p, (size_t)h->ndof * 8, cudaMemcpyDeviceToHost, h->stream));
+      FEMB_CUDA(h, download(u, h->x.p, (size_t)h->ndof * 8, h->stream));
   }
   cudaEventRecord(h->ev1, h->stream);
   cudaError_t se = cudaStreamSynchronize(h->stream);
@@ -367,7 +378,7 @@ int femb_frame_stress(femb_handle* h, const double* u, double* sigma_node) {
   FEMB_CUDA(h, ds.alloc((size_t)h->n_nodes));
   rc = launch_frame_stress(h, d_u, ds.p);
   if (rc) return rc;
-  FEMB_CUDA(h, cudaMemcpyAsync(sigma_node, ds.p, (size_t)h->n_nodes * 8, cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, download(sigma_node, ds.p, (size_t)h->n_nodes * 8, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   return FEMB_OK;
 }
@@ -385,6 +396,24 @@ int femb_frame_batch_solve(femb_handle* h, int64_t n_models, int64_t n_elem, con
   st.kernel_launches = (int32_t)h->launches;
   if (stats) *stats = st;
   return rc;
+}
+
+int femb_timer(femb_handle* h, int stop, double* ms) {
+  if (!h) return FEMB_ERR_ARG;
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  if (!h->ev_t0) { FEMB_CUDA(h, cudaEventCreate(&h->ev_t0)); FEMB_CUDA(h, cudaEventCreate(&h->ev_t1)); }
+  if (!stop) {
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FEMB_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
+    return FEMB_OK;
+  }
+  if (!ms) return fail(h, FEMB_ERR_ARG, "ms is NULL");
+  FEMB_CUDA(h, cudaEventRecord(h->ev_t1, h->stream));
+  FEMB_CUDA(h, cudaEventSynchronize(h->ev_t1));
+  float t = 0.f;
+  FEMB_CUDA(h, cudaEventElapsedTime(&t, h->ev_t0, h->ev_t1));
+  *ms = t;
+  return FEMB_OK;
 }
 
 int femb_time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes) {

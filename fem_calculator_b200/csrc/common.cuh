@@ -71,6 +71,7 @@ struct femb_handle {
   int num_sms = femb::kNumSMsB200;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // femb_timer
   std::string err;
   femb::Kind kind = femb::Kind::None;
   int bs = 0;
@@ -128,11 +129,20 @@ inline int fail(femb_handle* h, int code, const std::string& msg) {
     }                                                                                   \
   } while (0)
 
+// process-wide host<->device traffic counters (bench.py reports them per step)
+extern long long g_h2d_bytes, g_d2h_bytes;
+
 template <typename T>
 inline cudaError_t upload(DevBuf<T>& d, const T* src, size_t count, cudaStream_t s) {
   cudaError_t e = d.alloc(count);
   if (e != cudaSuccess || count == 0) return e;
+  g_h2d_bytes += (long long)(count * sizeof(T));
   return cudaMemcpyAsync(d.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+inline cudaError_t download(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  g_d2h_bytes += (long long)bytes;
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
 }
 
 template <typename T>

@@ -308,7 +308,7 @@ int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const doub
   FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   int* hs = reinterpret_cast<int*>(h->pinned);
   FEMB_CUDA(h, cudaMemcpyAsync(hs, status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  if (u) FEMB_CUDA(h, cudaMemcpyAsync(u, du.p, (size_t)n_models * ndof * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (u) FEMB_CUDA(h, download(u, du.p, (size_t)n_models * ndof * 8, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);

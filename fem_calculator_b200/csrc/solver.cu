@@ -194,6 +194,19 @@ __global__ void precond_setup_kernel(const double* __restrict__ vals, const int3
     for (int c = 0; c < BS; ++c) o[r * BS + c] = 0.5 * (B[r][c] + B[c][r]);
 }
 
+// scalar Jacobi: reciprocal of the masked diagonal (identity on fixed DOFs / non-positive pivots)
+template <int BS>
+__global__ void jacobi_setup_kernel(const double* __restrict__ vals, const int32_t* __restrict__ diag_blk,
+                                    const uint8_t* __restrict__ mask, double* __restrict__ dinv, int64_t n,
+                                    int identity) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const int64_t node = g / BS;
+  const int r = (int)(g - node * BS);
+  const double d = vals[(size_t)diag_blk[node] * BS * BS + r * BS + r];
+  dinv[g] = (!identity && mask[g] && d > 0.0) ? 1.0 / d : 1.0;
+}
+
 template <int BS>
 __device__ __forceinline__ double apply_dinv_row(const double* __restrict__ Dinv, int64_t g, const double* rn) {
   const int64_t node = g / BS;
@@ -207,7 +220,7 @@ __device__ __forceinline__ double apply_dinv_row(const double* __restrict__ Dinv
 
 // -------------------------------------------------------------------------------- PCG
 // init: x = 0, r = b, z = Dinv r, p = z; rz -> RZ0, bb -> BB, tol2 = rtol^2 * bb
-template <int BS, int THREADS>
+template <int BS, int THREADS, bool BLOCKJ>
 __global__ void __launch_bounds__(THREADS)
 pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, double* __restrict__ x,
                 double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, int64_t n,
@@ -215,12 +228,17 @@ pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, d
   __shared__ double s_red[THREADS / 32];
   double rz = 0.0, bb = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
-    const int64_t node = g / BS;
-    double rn[BS];
-#pragma unroll
-    for (int c = 0; c < BS; ++c) rn[c] = b[node * BS + c];
     const double bg = b[g];
-    const double zg = apply_dinv_row<BS>(Dinv, g, rn);
+    double zg;
+    if (BLOCKJ) {
+      const int64_t node = g / BS;
+      double rn[BS];
+#pragma unroll
+      for (int c = 0; c < BS; ++c) rn[c] = b[node * BS + c];
+      zg = apply_dinv_row<BS>(Dinv, g, rn);
+    } else {
+      zg = Dinv[g] * bg;
+    }
     x[g] = 0.0; r[g] = bg; z[g] = zg; p[g] = zg;
     rz += bg * zg; bb += bg * bg;
   }
@@ -239,7 +257,7 @@ pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, d
 }
 
 // x += alpha p; r -= alpha q; z = Dinv r; rz_new, rr ; convergence / breakdown decision
-template <int BS, int THREADS>
+template <int BS, int THREADS, bool BLOCKJ>
 __global__ void __launch_bounds__(THREADS)
 pcg_update_xr_kernel(const double* __restrict__ Dinv, const double* __restrict__ p, const double* __restrict__ q,
                      double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, int64_t n,
@@ -251,24 +269,36 @@ pcg_update_xr_kernel(const double* __restrict__ Dinv, const double* __restrict__
   const bool bad = !(pq > 0.0);            // K_ff not positive definite along p
   const double alpha = bad ? 0.0 : rz_old / pq;
   double rz = 0.0, rr = 0.0;
-  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
-    const int64_t node = g / BS;
-    double rn[BS];
+  if (BLOCKJ) {
+    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+      const int64_t node = g / BS;
+      double rn[BS];
 #pragma unroll
-    for (int c = 0; c < BS; ++c) rn[c] = r[node * BS + c] - alpha * q[node * BS + c];
-    const int rloc = (int)(g - node * BS);
-    const double rg = rn[rloc];
-    const double zg = apply_dinv_row<BS>(Dinv, g, rn);
-    x[g] += alpha * p[g];
-    z[g] = zg;
-    rz += rg * zg; rr += rg * rg;
+      for (int c = 0; c < BS; ++c) rn[c] = r[node * BS + c] - alpha * q[node * BS + c];
+      const int rloc = (int)(g - node * BS);
+      const double rg = rn[rloc];
+      const double zg = apply_dinv_row<BS>(Dinv, g, rn);
+      x[g] += alpha * p[g];
+      z[g] = zg;
+      rz += rg * zg; rr += rg * rg;
+    }
+    // r[g] is also read by the other rows of its node, so it is committed in a second pass.
+    // All rows of a node live in the same CTA and grid-stride step (THREADS % BS == 0), hence
+    // the barrier is enough; the re-read of r and q hits L1.
+    __syncthreads();
+    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS)
+      r[g] -= alpha * q[g];
+  } else {
+    // scalar Jacobi: purely element-wise, one pass
+    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+      const double rg = r[g] - alpha * q[g];
+      const double zg = __ldg(Dinv + g) * rg;
+      x[g] += alpha * p[g];
+      r[g] = rg;
+      z[g] = zg;
+      rz += rg * zg; rr += rg * rg;
+    }
   }
-  // r[g] is also read by the other rows of its node, so it is committed in a second pass.
-  // All rows of a node live in the same CTA and grid-stride step (THREADS % BS == 0), hence
-  // the barrier is enough; the re-read of r and q hits L1.
-  __syncthreads();
-  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS)
-    r[g] -= alpha * q[g];
   double mine[2], tot[2];
   mine[0] = block_sum<THREADS>(rz, s_red);
   mine[1] = block_sum<THREADS>(rr, s_red);
@@ -377,6 +407,16 @@ static int build_rhs(femb_handle* h, bool have_u0) {
 }
 
 static int setup_precond(femb_handle* h, int mode) {
+  if (mode != FEMB_PRECOND_BLOCK_JACOBI) {
+    FEMB_CUDA(h, h->Dinv.alloc((size_t)h->ndof));
+    const int g = (int)((h->ndof + 255) / 256);
+    const int ident = (mode == FEMB_PRECOND_NONE);
+    if (h->bs == 6) jacobi_setup_kernel<6><<<g, 256, 0, h->stream>>>(h->Kvals.p, h->diag_blk.p, h->free_mask.p, h->Dinv.p, h->ndof, ident);
+    else jacobi_setup_kernel<3><<<g, 256, 0, h->stream>>>(h->Kvals.p, h->diag_blk.p, h->free_mask.p, h->Dinv.p, h->ndof, ident);
+    h->launches++;
+    FEMB_CUDA(h, cudaGetLastError());
+    return FEMB_OK;
+  }
   FEMB_CUDA(h, h->Dinv.alloc((size_t)h->n_nodes * h->bs * h->bs));
   const int grid = (int)((h->n_nodes + 127) / 128);
   if (h->bs == 6)
@@ -402,8 +442,10 @@ int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
   rc = setup_precond(h, o.precond);
   if (rc) return rc;
   FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
-#define INIT(BS) pcg_init_kernel<BS, kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->b.p, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, n, o.rtol, h->partials.p, pstride, h->scal.p, h->flags.p)
-  if (h->bs == 6) INIT(6); else INIT(3);
+  const bool blockj = (o.precond == FEMB_PRECOND_BLOCK_JACOBI);
+#define INIT(BS, BJ) pcg_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->b.p, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, n, o.rtol, h->partials.p, pstride, h->scal.p, h->flags.p)
+  if (h->bs == 6) { if (blockj) INIT(6, true); else INIT(6, false); }
+  else { if (blockj) INIT(3, true); else INIT(3, false); }
 #undef INIT
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
@@ -419,7 +461,7 @@ int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
     const int batch = (o.max_iter - it) < check ? (o.max_iter - it) : check;
     for (int k = 0; k < batch; ++k, ++it) {
       const int parity = (it + 1) & 1;
-      if (prof) {
+      if (prof && (it % o.profile) == 0) {
         cudaEvent_t a, b;
         cudaEventCreate(&a); cudaEventCreate(&b);
         cudaEventRecord(a, h->stream);
@@ -431,8 +473,9 @@ int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
       }
       if (rc) return rc;
       ++spmv_launches;
-#define UPD(BS) pcg_update_xr_kernel<BS, kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
-      if (h->bs == 6) UPD(6); else UPD(3);
+#define UPD(BS, BJ) pcg_update_xr_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
+      if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
+      else { if (blockj) UPD(3, true); else UPD(3, false); }
 #undef UPD
       pcg_update_p_kernel<kVecThreads><<<vec_grid(h, n, kVecThreads), kVecThreads, 0, h->stream>>>(h->z.p, h->p.p, n, parity, h->scal.p, h->flags.p);
       h->launches += 2;
@@ -460,6 +503,7 @@ int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
       cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
       st->spmv_ms += ms;
     }
+    st->spmv_timed = (int32_t)(evs.size() / 2);  // number of SpMV launches that were timed
   }
   for (auto e : evs) cudaEventDestroy(e);
   if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");

@@ -58,7 +58,7 @@ typedef struct {
   int32_t max_iter;      /* PCG iteration cap                     default 200000          */
   int32_t check_every;   /* host polls convergence every N its    default 50              */
   double rtol;           /* stop at ||r||_2 <= rtol*||b||_2       default 1e-12           */
-  int32_t profile;       /* 1: time every SpMV launch with CUDA events (adds overhead)    */
+  int32_t profile;       /* P>0: time every P-th SpMV launch with CUDA events              */
   int32_t reserved;
 } femb_solve_opts;
 
@@ -77,10 +77,10 @@ typedef struct {
   int32_t converged;
   int32_t spmv_launches;      /* SpMV kernel launches in this call                         */
   int32_t kernel_launches;    /* all kernel launches of this library in this call          */
-  int32_t reserved;
+  int32_t spmv_timed;         /* SpMV launches bracketed by events (opts.profile)          */
   double rel_residual;        /* final ||r||/||b||                                         */
   double device_ms;           /* CUDA-event time of the whole call on the handle's stream  */
-  double spmv_ms;             /* summed SpMV device time (only when opts.profile)          */
+  double spmv_ms;             /* summed device time of the timed SpMV launches              */
 } femb_stats;
 
 int femb_version(void);
@@ -184,6 +184,14 @@ int femb_frame_batch_solve(femb_handle* h, int64_t n_models, int64_t n_elem, con
  * algorithmic bytes of one launch.  which: 0 = BSR SpMV (masked
  * K_ff operator), 1 = fused element+assembly, 2 = one full PCG iteration.               */
 int femb_time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes);
+
+/* CUDA-event stopwatch on the handle's stream: stop = 0 records the start (after draining the
+ * stream), stop = 1 records the end and returns the elapsed device time in *ms. */
+int femb_timer(femb_handle* h, int stop, double* ms);
+
+/* Bytes this process has copied host->device / device->host through the library since the
+ * last reset (bench.py's e2e accounting). */
+void femb_io_bytes(int64_t* h2d, int64_t* d2h, int reset);
 
 /* Host-only symbolic analysis (no GPU needed; exercised by the CPU test-suite):
  * block-CSR pattern of an element mesh.  Two calls: pass NULL outputs to get sizes.     */
