@@ -165,6 +165,124 @@ assemble_tiles_kernel(const EL el, const PatternDev pat, double* __restrict__ Kv
   }
 }
 
+// ---- frame fast path: one thread per (node, incident element end) ------------------------
+// The thread evaluates the element record ONCE and produces both the off-diagonal block
+// (node, other end) — stored straight into the tile's staging area — and its share of the
+// node's diagonal block, kept as the 21-value upper triangle (+7 compact mass values) and
+// added in element-ascending order, one rank per __syncthreads_or step.  Compared with the
+// generic one-thread-per-contribution kernel this halves the record evaluations and cuts
+// the shared-memory accumulate traffic from 72 to 28 values per element end.
+struct PairDev {
+  const int32_t* rowptr;
+  const int32_t* diag_blk;
+  const int32_t* pair_ptr;
+  const uint32_t* pair_code;
+  const int32_t* pair_blk;
+  const uint8_t* pair_rank;
+  const int32_t* tile_ptr;
+};
+
+template <int THREADS, bool BULK>
+__global__ void __launch_bounds__(THREADS)
+frame_assemble_pairs_kernel(const FrameParams P, const PairDev pat, double* __restrict__ Kvals,
+                            double* __restrict__ Mdiag) {
+  extern __shared__ __align__(128) double s_out[];  // K blocks [nblk*36] | mass [nn*36] | diag acc [nn*28]
+  const int tid = threadIdx.x;
+  const int n0 = pat.tile_ptr[blockIdx.x], n1 = pat.tile_ptr[blockIdx.x + 1];
+  const int nn = n1 - n0;
+  const int b0 = pat.rowptr[n0], b1 = pat.rowptr[n1];
+  const int p0 = pat.pair_ptr[n0], p1 = pat.pair_ptr[n1];
+  const int nblk = b1 - b0;
+  double* s_mass = s_out + (size_t)nblk * 36;
+  double* s_diag = s_mass + (size_t)nn * 36;
+  for (int t = tid; t < nn * 28; t += THREADS) s_diag[t] = 0.0;
+  __syncthreads();
+
+  for (int base = p0; base < p1; base += THREADS) {  // normally a single pass
+    const int p = base + tid;
+    int myk = -1, rank = -1, slot = 0, nslot = 0;
+    double acc[36];
+    FrameRec R;
+    int a = 0;
+    if (p < p1) {
+      const uint32_t code = pat.pair_code[p];
+      a = (int)(code & 1u);
+      slot = pat.pair_blk[p] - b0;
+      rank = (int)pat.pair_rank[p];
+      int lo = n0, hi = n1 - 1;  // node owning pair p: largest node with pair_ptr[node] <= p
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (pat.pair_ptr[mid] <= p) lo = mid; else hi = mid - 1;
+      }
+      nslot = lo - n0;
+      myk = p - max(pat.pair_ptr[lo], base);
+      frame_record(P, code >> 1, R);
+      frame_kblock<true>(R, a, 1 - a, acc);
+      if (rank == 0) {
+        double2* dst = reinterpret_cast<double2*>(s_out + (size_t)slot * 36);
+#pragma unroll
+        for (int q = 0; q < 18; ++q) dst[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
+      }
+    }
+    // duplicate members between the same two nodes (rare): ordered adds after the rank-0 store
+    for (int k = 1; __syncthreads_or(rank >= k); ++k) {
+      if (rank == k) {
+        double* dst = s_out + (size_t)slot * 36;
+#pragma unroll
+        for (int q = 0; q < 36; ++q) dst[q] += acc[q];
+      }
+    }
+    // diagonal share: 21 symmetric stiffness values + 7 compact mass values, ordered by rank
+    if (p < p1) frame_diag_sym(R, a, acc, acc + 21);
+    for (int k = 0; __syncthreads_or(myk >= k); ++k) {
+      if (myk == k) {
+        double* dst = s_diag + (size_t)nslot * 28;
+#pragma unroll
+        for (int q = 0; q < 28; ++q) dst[q] += acc[q];
+      }
+    }
+  }
+
+  // expand the symmetric accumulators into the diagonal K blocks and the dense mass blocks
+  for (int t = tid; t < nn * 36; t += THREADS) {
+    const int ns = t / 36, rc = t - ns * 36;
+    const int r = rc / 6, c = rc - r * 6;
+    const double* d = s_diag + (size_t)ns * 28;
+    s_out[(size_t)(pat.diag_blk[n0 + ns] - b0) * 36 + rc] = d[sym6_index(r, c)];
+    double mv = 0.0;
+    if (r < 3 && c < 3) mv = (r == c) ? d[21] : 0.0;
+    else if (r >= 3 && c >= 3) {
+      const int rr = r - 3, cc = c - 3;
+      const int lo = rr < cc ? rr : cc, hi = rr < cc ? cc : rr;
+      mv = d[22 + lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo)];
+    }
+    s_mass[t] = mv;
+  }
+
+  double* gK = Kvals + (size_t)b0 * 36;
+  double* gM = Mdiag + (size_t)n0 * 36;
+  if (BULK) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(gK), "r"(smem_u32(s_out)), "r"((uint32_t)(nblk * 288)) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(gM), "r"(smem_u32(s_mass)), "r"((uint32_t)(nn * 288)) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    __syncthreads();
+    const double2* s2 = reinterpret_cast<const double2*>(s_out);
+    double2* g2 = reinterpret_cast<double2*>(gK);
+    for (int i = tid; i < nblk * 18; i += THREADS) g2[i] = s2[i];
+    const double2* m2 = reinterpret_cast<const double2*>(s_mass);
+    double2* gm2 = reinterpret_cast<double2*>(gM);
+    for (int i = tid; i < nn * 18; i += THREADS) gm2[i] = m2[i];
+  }
+}
+
 // ---- parity export: per-element global-axis matrices ------------------------------------
 __global__ void frame_elements_kernel(FrameParams P, int64_t n_elem, double* __restrict__ ke,
                                       double* __restrict__ me) {
@@ -273,7 +391,40 @@ static int launch_assemble_t(femb_handle* h, const EL& el) {
   return FEMB_OK;
 }
 
+static int launch_assemble_pairs(femb_handle* h) {
+  const femb::Symbolic& S = h->sym;
+  const int n_tiles = (int)S.pair_tile_ptr.size() - 1;
+  if (n_tiles <= 0) return FEMB_OK;
+  size_t smem = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int n0 = S.pair_tile_ptr[t], n1 = S.pair_tile_ptr[t + 1];
+    const size_t need = (size_t)(S.rowptr[n1] - S.rowptr[n0]) * 288 + (size_t)(n1 - n0) * (288 + 224);
+    smem = need > smem ? need : smem;
+  }
+  smem = (smem + 127) & ~size_t(127);
+  if (smem > 200 * 1024) return fail(h, FEMB_ERR_ARG, "assembly tile exceeds shared memory (node degree too large)");
+  PairDev pat{h->rowptr.p, h->diag_blk.p, h->pair_ptr.p, h->pair_code.p, h->pair_blk.p, h->pair_rank.p, h->pair_tile_ptr.p};
+  if (bulk_enabled()) {
+    auto k = frame_assemble_pairs_kernel<kAsmThreads, true>;
+    FEMB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<n_tiles, kAsmThreads, smem, h->stream>>>(frame_params(h), pat, h->Kvals.p, h->Mdiag.p);
+  } else {
+    auto k = frame_assemble_pairs_kernel<kAsmThreads, false>;
+    FEMB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<n_tiles, kAsmThreads, smem, h->stream>>>(frame_params(h), pat, h->Kvals.p, h->Mdiag.p);
+  }
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+static bool generic_forced() {
+  const char* s = getenv("FEMB_ASM_GENERIC");
+  return s && s[0] == '1';
+}
+
 int launch_assemble(femb_handle* h) {
+  if (h->kind == Kind::Frame && h->sym.pairs_ok && !generic_forced()) return launch_assemble_pairs(h);
   if (h->kind == Kind::Frame) {
     FrameEl el;
     el.P = frame_params(h);

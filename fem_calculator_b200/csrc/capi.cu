@@ -163,7 +163,7 @@ static int ensure_symbolic(femb_handle* h) {
   // tile capacities: <= 128 contributions (one per thread of the 128-thread assembly CTA is
   // the common case; larger rows fall back to chunking) and a shared-memory budget in blocks.
   const int max_contrib = 128;
-  const int max_blocks = (h->bs == 6) ? 96 : 512;
+  const int max_blocks = (h->bs == 6) ? 160 : 512;
   build_symbolic(h->n_nodes, h->n_elem, nper, h->bs, h->h_conn.data(), max_blocks, max_contrib, h->sym);
   const Symbolic& S = h->sym;
   if (S.nnzb * (int64_t)h->bs * h->bs >= ((int64_t)1 << 40)) return fail(h, FEMB_ERR_ARG, "matrix too large");
@@ -175,6 +175,13 @@ static int ensure_symbolic(femb_handle* h) {
   FEMB_CUDA(h, upload(h->contrib, S.contrib, h->stream));
   FEMB_CUDA(h, upload(h->contrib_blk, S.contrib_blk, h->stream));
   FEMB_CUDA(h, upload(h->tile_ptr, S.tile_ptr, h->stream));
+  if (S.pairs_ok) {
+    FEMB_CUDA(h, upload(h->pair_ptr, S.pair_ptr, h->stream));
+    FEMB_CUDA(h, upload(h->pair_code, S.pair_code, h->stream));
+    FEMB_CUDA(h, upload(h->pair_blk, S.pair_blk, h->stream));
+    FEMB_CUDA(h, upload(h->pair_rank, S.pair_rank, h->stream));
+    FEMB_CUDA(h, upload(h->pair_tile_ptr, S.pair_tile_ptr, h->stream));
+  }
   FEMB_CUDA(h, h->Kvals.alloc((size_t)S.nnzb * h->bs * h->bs));
   if (h->kind == Kind::Frame) FEMB_CUDA(h, h->Mdiag.alloc((size_t)h->n_nodes * 36));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -443,8 +450,10 @@ int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, doubl
     // fused element+assembly: mesh in (60 B/element frame, 10*(4+24) tet) + K (+M) out;
     // the scatter map (12 B/contribution + 4 B/block) is counted as algorithmic input too.
     const double mesh_in = (h->kind == Kind::Frame) ? 60.0 * h->n_elem : 280.0 * h->n_elem;
-    *bytes = mesh_in + 8.0 * S.nnzb * bs2 + (h->kind == Kind::Frame ? 8.0 * h->n_nodes * bs2 : 0.0) +
-             12.0 * S.n_contrib + 4.0 * S.nnzb;
+    const bool pairs = (h->kind == Kind::Frame) && S.pairs_ok;
+    const double map_bytes = pairs ? 9.0 * (double)S.pair_code.size() + 8.0 * h->n_nodes
+                                   : 12.0 * S.n_contrib + 4.0 * S.nnzb;
+    *bytes = mesh_in + 8.0 * S.nnzb * bs2 + (h->kind == Kind::Frame ? 8.0 * h->n_nodes * bs2 : 0.0) + map_bytes;
     for (int i = 0; i < warm && !rc; ++i) rc = launch_assemble(h);
     FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < reps && !rc; ++i) rc = launch_assemble(h);

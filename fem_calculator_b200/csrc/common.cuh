@@ -55,6 +55,13 @@ struct Symbolic {
   std::vector<int32_t> tile_ptr;     // (n_tiles+1) node ranges of assembly tiles
   int32_t tile_max_blocks = 0;       // capacity limits the tiles were packed for
   int32_t tile_max_contrib = 0;
+  // frame "pair" view: one entry per (node, incident element end), element-ascending per node
+  std::vector<int32_t> pair_ptr;     // (n_nodes+1)
+  std::vector<uint32_t> pair_code;   // (n_pairs) e*2 + a
+  std::vector<int32_t> pair_blk;     // (n_pairs) block (node, other end)
+  std::vector<uint8_t> pair_rank;    // (n_pairs) rank inside that block's contribution list
+  std::vector<int32_t> pair_tile_ptr;  // (n_pair_tiles+1) node ranges of the pair-kernel tiles
+  bool pairs_ok = false;             // false: self-loop element or >255 duplicates -> generic kernel
   bool is_chain = false;             // path graph(s): block-tridiagonal after chain ordering
   std::vector<int32_t> chain_order;  // (n_nodes) node visited at chain position k
 };
@@ -92,6 +99,9 @@ struct femb_handle {
   bool have_symbolic = false, assembled = false;
   femb::DevBuf<int32_t> rowptr, colidx, blk_row, diag_blk, contrib_ptr, contrib_blk, tile_ptr;
   femb::DevBuf<uint32_t> contrib;
+  femb::DevBuf<int32_t> pair_ptr, pair_blk, pair_tile_ptr;
+  femb::DevBuf<uint32_t> pair_code;
+  femb::DevBuf<uint8_t> pair_rank;
   femb::DevBuf<double> Kvals;      // (nnzb, bs, bs)
   femb::DevBuf<double> Mdiag;      // (n_nodes, bs, bs) frame only
   femb::DevBuf<unsigned long long> counters;  // device scalars: [0] skipped gauss points

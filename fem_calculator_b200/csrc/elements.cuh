@@ -39,8 +39,10 @@ __device__ __forceinline__ void frame_record(const FrameParams& P, uint32_t e, F
   const double A = __ldg(sp), Ix = __ldg(sp + 1), Iy = __ldg(sp + 2), J = __ldg(sp + 3),
                ky = __ldg(sp + 4), kz = __ldg(sp + 5);
   const double L2 = dx * dx + dy * dy + dz * dz;
-  const double L = sqrt(L2);                       // BeamSolver.py:373
-  const double iL = 1.0 / L;
+  // 1/L through rsqrt (one MUFU + Newton) instead of sqrt followed by a division; the few-ulp
+  // difference to numpy's norm/divide is far inside the 1e-14 parity band.
+  const double iL = rsqrt(L2);
+  const double L = L2 * iL;                        // BeamSolver.py:373
   const double cx = dx * iL, cy = dy * iL, cz = dz * iL;  // :378-379
   const double h2 = cx * cx + cy * cy;
   if (h2 < 1e-12) {                                // vertical member, :380-381 (eps = 1e-6)
@@ -50,30 +52,41 @@ __device__ __forceinline__ void frame_record(const FrameParams& P, uint32_t e, F
     r.n2[0] = -s; r.n2[1] = 0.0; r.n2[2] = 0.0;
   } else {                                         // :383-384 (a zero-length element lands here
                                                    // with NaN direction cosines, as in numpy)
-    const double D = sqrt(h2);
-    const double iD = 1.0 / D;
+    const double iD = rsqrt(h2);
+    const double D = h2 * iD;
     r.t[0] = cx; r.t[1] = cy; r.t[2] = cz;
     r.n1[0] = -cy * iD; r.n1[1] = cx * iD; r.n1[2] = 0.0;
     r.n2[0] = -cx * cz * iD; r.n2[1] = -cy * cz * iD; r.n2[2] = D;
   }
   const double E = P.E, G = P.G;
   const bool ok = L > 0.0;                         // every term is guarded by L > 0 (:649-653)
-  const double den_z = G * ky * A * L2;            // :647
-  const double den_y = G * kz * A * L2;            // :648
-  const double phi_z = den_z > 0.0 ? (12.0 * E * Iy) / den_z : 0.0;
-  const double phi_y = den_y > 0.0 ? (12.0 * E * Ix) / den_y : 0.0;
   const double iL1 = ok ? iL : 0.0;
   const double iL2 = iL1 * iL1, iL3 = iL2 * iL1;
-  const double oz = 1.0 / (1.0 + phi_z), oy = 1.0 / (1.0 + phi_y);
+  // Timoshenko factors with ONE reciprocal per bending plane: with q = 12 E I and
+  // den = G kappa A L^2 (:647-648), phi = q/den and
+  //   1/(1+phi) = den/(den+q), (4+phi)/(1+phi) = (4 den+q)/(den+q), (2-phi)/(1+phi) = (2 den-q)/(den+q);
+  // den <= 0 selects the Euler-Bernoulli fallback phi = 0.
   const double EIz = E * Iy, EIy = E * Ix;         // local x-y bending uses I_y, x-z uses I_x
-  r.k11z = 12.0 * EIz * iL3 * oz;
-  r.k12z = 6.0 * EIz * iL2 * oz;
-  r.k22z = (4.0 + phi_z) * EIz * iL1 * oz;
-  r.k23z = (2.0 - phi_z) * EIz * iL1 * oz;
-  r.k11y = 12.0 * EIy * iL3 * oy;
-  r.k12y = 6.0 * EIy * iL2 * oy;
-  r.k22y = (4.0 + phi_y) * EIy * iL1 * oy;
-  r.k23y = (2.0 - phi_y) * EIy * iL1 * oy;
+  const double qz = 12.0 * EIz, qy = 12.0 * EIy;
+  const double den_z = G * ky * A * L2;
+  const double den_y = G * kz * A * L2;
+  double oz = 1.0, f22z = 4.0, f23z = 2.0, oy = 1.0, f22y = 4.0, f23y = 2.0;
+  if (den_z > 0.0) {
+    const double rq = 1.0 / (den_z + qz);
+    oz = den_z * rq; f22z = (4.0 * den_z + qz) * rq; f23z = (2.0 * den_z - qz) * rq;
+  }
+  if (den_y > 0.0) {
+    const double rq = 1.0 / (den_y + qy);
+    oy = den_y * rq; f22y = (4.0 * den_y + qy) * rq; f23y = (2.0 * den_y - qy) * rq;
+  }
+  r.k11z = qz * iL3 * oz;
+  r.k12z = 0.5 * qz * iL2 * oz;
+  r.k22z = f22z * EIz * iL1;
+  r.k23z = f23z * EIz * iL1;
+  r.k11y = qy * iL3 * oy;
+  r.k12y = 0.5 * qy * iL2 * oy;
+  r.k22y = f22y * EIy * iL1;
+  r.k23y = f23y * EIy * iL1;
   r.tor = G * J * iL1;                             // :653
   r.ax = A * E * iL1;                              // :655
   const double hl = 0.5 * P.rho * L;               // BeamSolver.py:667-670
@@ -118,6 +131,40 @@ __device__ __forceinline__ void frame_kblock(const FrameRec& R, int a, int b, do
   }
 }
 
+// Upper triangle (21 values, row-major r<=c) of the diagonal block [a][a] of R^T k R, which is
+// exactly symmetric in floating point (every entry is the same sum of commuting products),
+// plus the compact lumped mass of that end: m[0] = rho A L/2 (translational, times I) and
+// m[1..6] = upper triangle of the rotational 3x3 block (BeamSolver.py:662-675, :388).
+__device__ __forceinline__ void frame_diag_sym(const FrameRec& R, int a, double* d, double* m) {
+  const double sa = (a == 0) ? 1.0 : -1.0;
+  const double az = sa * R.k12z, ay = sa * R.k12y;
+  int q = 0, qm = 1;
+  m[0] = R.mt;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {  // rows 0..2: uu(r, c>=r) then u-theta(r, 0..2)
+#pragma unroll
+    for (int c = r; c < 3; ++c)
+      d[q++] = R.ax * (R.t[r] * R.t[c]) + R.k11z * (R.n1[r] * R.n1[c]) + R.k11y * (R.n2[r] * R.n2[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[q++] = az * (R.n1[r] * R.n2[c]) - ay * (R.n2[r] * R.n1[c]);
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {  // rows 3..5: theta-theta(r, c>=r)
+#pragma unroll
+    for (int c = r; c < 3; ++c) {
+      const double tt = R.t[r] * R.t[c], n11 = R.n1[r] * R.n1[c], n22 = R.n2[r] * R.n2[c];
+      d[q++] = R.tor * tt + R.k22y * n11 + R.k22z * n22;
+      m[qm++] = R.mrx * tt + R.mry * n11 + R.mrz * n22;
+    }
+  }
+}
+
+// index into the 21-value upper triangle of a symmetric 6x6
+__device__ __forceinline__ int sym6_index(int r, int c) {
+  const int lo = r < c ? r : c, hi = r < c ? c : r;
+  return lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);
+}
+
 // acc (6x6) = diagonal block [a][a] of R^T m R (lumped mass, BeamSolver.py:662-675, :388).
 __device__ __forceinline__ void frame_mblock(const FrameRec& R, double* acc) {
 #pragma unroll
@@ -127,7 +174,7 @@ __device__ __forceinline__ void frame_mblock(const FrameRec& R, double* acc) {
       const double tt = R.t[r] * R.t[c];
       const double n11 = R.n1[r] * R.n1[c];
       const double n22 = R.n2[r] * R.n2[c];
-      acc[r * 6 + c] = R.mt * tt + R.mt * n11 + R.mt * n22;
+      acc[r * 6 + c] = (r == c) ? R.mt : 0.0;  // lambda^T (m_t I) lambda = m_t I
       acc[r * 6 + 3 + c] = 0.0;
       acc[(3 + r) * 6 + c] = 0.0;
       acc[(3 + r) * 6 + 3 + c] = R.mrx * tt + R.mry * n11 + R.mrz * n22;

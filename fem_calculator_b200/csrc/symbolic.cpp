@@ -131,6 +131,60 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
   }
   S.tile_ptr.push_back((int32_t)N);
 
+  // 4b. frame pair view (one thread of the pair kernel per (node, incident element end)):
+  //     the diagonal block's list (codes e*4 + a*3, element-ascending) enumerates the pairs;
+  //     each pair also owns the off-diagonal contribution (e, a, 1-a) to block (node, other).
+  S.pairs_ok = false;
+  if (nper == 2) {
+    bool ok = true;
+    S.pair_ptr.assign(N + 1, 0);
+    for (int64_t i = 0; i < N; ++i) {
+      const int32_t d = S.diag_blk[i];
+      S.pair_ptr[i + 1] = S.pair_ptr[i] + (S.contrib_ptr[d + 1] - S.contrib_ptr[d]);
+    }
+    const int64_t np = S.pair_ptr[N];
+    S.pair_code.resize(np); S.pair_blk.resize(np); S.pair_rank.resize(np);
+    for (int64_t i = 0; i < N && ok; ++i) {
+      const int32_t d = S.diag_blk[i];
+      int64_t p = S.pair_ptr[i];
+      for (int32_t cc = S.contrib_ptr[d]; cc < S.contrib_ptr[d + 1] && ok; ++cc, ++p) {
+        const uint32_t code = S.contrib[cc];
+        const uint32_t e = code >> 2, a = (code >> 1) & 1u, b = code & 1u;
+        if (a != b) { ok = false; break; }                       // self-loop element
+        const int32_t other = conn[e * 2 + (1 - a)];
+        if (other == (int32_t)i) { ok = false; break; }
+        const int32_t* cb = S.colidx.data() + S.rowptr[i];
+        const int32_t* ce = S.colidx.data() + S.rowptr[i + 1];
+        const int32_t blk = (int32_t)(std::lower_bound(cb, ce, other) - S.colidx.data());
+        const uint32_t ocode = e * 4u + a * 2u + (1u - a);
+        const uint32_t* ob = S.contrib.data() + S.contrib_ptr[blk];
+        const uint32_t* oe = S.contrib.data() + S.contrib_ptr[blk + 1];
+        const int64_t rank = std::lower_bound(ob, oe, ocode) - ob;
+        if (rank > 255) { ok = false; break; }
+        S.pair_code[p] = e * 2u + a;
+        S.pair_blk[p] = blk;
+        S.pair_rank[p] = (uint8_t)rank;
+      }
+    }
+    S.pairs_ok = ok;
+    if (ok) {
+      S.pair_tile_ptr.clear();
+      S.pair_tile_ptr.push_back(0);
+      int64_t tb = 0, tp = 0;
+      for (int64_t i = 0; i < N; ++i) {
+        const int64_t rb = S.rowptr[i + 1] - S.rowptr[i];
+        const int64_t rp = S.pair_ptr[i + 1] - S.pair_ptr[i];
+        if (i > S.pair_tile_ptr.back() && (tb + rb > tile_max_blocks || tp + rp > tile_max_contrib)) {
+          S.pair_tile_ptr.push_back((int32_t)i);
+          tb = tp = 0;
+        }
+        tb += rb;
+        tp += rp;
+      }
+      S.pair_tile_ptr.push_back((int32_t)N);
+    }
+  }
+
   // 5. chain detection (frames): every node has <= 2 distinct neighbours, no cycles.
   //    chain_order lists nodes path by path from an end point; isolated nodes last-in-place.
   S.is_chain = false;

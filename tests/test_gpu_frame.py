@@ -91,6 +91,46 @@ def test_bulk_and_plain_store_paths_agree():
     assert np.array_equal(vals[0], vals[2]) and np.array_equal(vals[1], vals[3])
 
 
+def test_pair_kernel_agrees_with_generic_contribution_kernel():
+    """The frame fast path (one thread per element end) and the generic one-thread-per-
+    contribution kernel build the same K and M (same closed forms; only the association of the
+    diagonal sums differs by design: both add in element-ascending order)."""
+    mesh, sec, bc = meshgen.lattice_frame_case(7, 6, 5, jitter=0.05)
+    es, props, _ = compat.frame_section_table(mesh, sec, csp)
+    out = {}
+    for flag in ("0", "1"):
+        os.environ["FEMB_ASM_GENERIC"] = flag
+        m = FrameModel(0)
+        m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, 2e11, 2e11 / 2.6)
+        m.assemble()
+        out[flag] = (m.get_csr(L.MAT_K)[2], m.get_csr(L.MAT_M)[2])
+        m.close()
+    os.environ.pop("FEMB_ASM_GENERIC")
+    for a, b in zip(out["0"], out["1"]):
+        assert np.abs(a - b).max() <= 4e-16 * np.abs(b).max()
+
+
+def test_duplicate_members_and_isolated_points():
+    """Two members between the same nodes (ordered accumulation in one block) and a mesh
+    point no element touches (all-zero rows, BeamSolver.py:354,360)."""
+    pts = np.array([[0, 0, 0], [1.0, 0.2, 0.1], [2.0, 0.5, -0.3], [5.0, 5.0, 5.0]])
+    conn = np.array([[0, 1], [1, 2], [1, 0], [0, 1]])
+    props = np.array([[5e-3, 4e-6, 1e-6, 2.8e-6, 0.83, 0.83, 0.02, 0.05], [2e-3, 1e-6, 2e-6, 1e-6, 0.5, 0.6, 0.02, 0.05]])
+    es = np.array([0, 1, 1, 0], dtype=np.int32)
+    m = FrameModel(0)
+    m.set_mesh(pts, conn, es, props, 2e11, 2e11 / 2.6)
+    m.assemble()
+    indptr, indices, data = m.get_csr(L.MAT_K)
+    mp, mi, md = m.get_csr(L.MAT_M)
+    m.close()
+    Ko, Mo = S.frame_assemble(pts, conn, es, props, 2e11, 0.3)
+    assert np.array_equal(indptr, Ko.indptr) and np.array_equal(indices, Ko.indices)
+    assert np.abs(data - Ko.data).max() <= 1e-14 * np.abs(Ko.data).max()
+    M = sp.csr_matrix((md, mi, mp), shape=Ko.shape).toarray()
+    assert np.abs(M - Mo.toarray()).max() <= 1e-14 * np.abs(Mo.toarray()).max()
+    assert np.all(data[indptr[18]:indptr[24]] == 0.0)
+
+
 def _methods_for(name):
     if name.startswith("c3"):
         return [L.SOLVER_AUTO, L.SOLVER_PCG, L.SOLVER_DENSE]
