@@ -206,6 +206,7 @@ int femb_assemble(femb_handle* h) {
   }
   h->assembled = true;
   h->have_solution = false;
+  h->chain_factored = h->dense_factored = false;
   return FEMB_OK;
 }
 
@@ -288,6 +289,7 @@ int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, cons
   h->n_fixed = n_fixed;
   h->have_bc = true;
   h->have_solution = false;
+  h->chain_factored = h->dense_factored = false;
   return FEMB_OK;
 }
 

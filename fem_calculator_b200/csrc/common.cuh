@@ -35,6 +35,8 @@ struct DevBuf {
     if (e == cudaSuccess) n = count;
     return e;
   }
+  // grow-only variant: keeps a larger existing allocation
+  cudaError_t ensure(size_t count) { return (p && count <= n) ? cudaSuccess : alloc(count); }
   size_t bytes() const { return n * sizeof(T); }
 };
 
@@ -119,6 +121,12 @@ struct femb_handle {
   femb::DevBuf<int32_t> flags;      // [0] done, [1] iterations, [2] ticket counters...
   bool have_solution = false;
 
+  // persistent direct-solver factors (invalidated by femb_assemble / femb_set_bc)
+  bool chain_factored = false, dense_factored = false;
+  femb::DevBuf<int32_t> chain_order;
+  femb::DevBuf<double> chainG, chainW;   // (n_nodes,36) each, chain positions
+  femb::DevBuf<double> denseL;           // (ndof,ndof) Cholesky factor of the masked operator
+
   void* pinned = nullptr;           // small pinned staging area
   size_t pinned_bytes = 0;
 };
@@ -172,6 +180,11 @@ int setup_bc_vectors(femb_handle* h);
 int launch_frame_stress(femb_handle* h, const double* d_u, double* d_sigma);
 int run_chain_solve(femb_handle* h, femb_stats* st);
 int run_dense_solve(femb_handle* h, femb_stats* st);
+int chain_factor(femb_handle* h);
+int chain_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_t ld);
+int dense_factor(femb_handle* h);
+int dense_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_t ld);
+int pcg_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda, double* phi, int32_t* n_found,
               femb_stats* st);
 int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const double* xyz,

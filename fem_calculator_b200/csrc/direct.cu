@@ -62,16 +62,17 @@ __device__ __forceinline__ unsigned node_mask(const uint8_t* free_mask, int64_t 
   return m;
 }
 
-// ---- single-model chain solve on the assembled BSR matrix -------------------------------
-// scratch: W (n,36) and z (n,6) in chain positions.  One warp; lane 0 walks the recurrence
-// (sequential by nature), the warp only exists so the launch is a legal shape.
-__global__ void chain_solve_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ rowptr,
-                                   const int32_t* __restrict__ colidx, const int32_t* __restrict__ diag_blk,
-                                   const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
-                                   const double* __restrict__ b, double* __restrict__ x,
-                                   double* __restrict__ W, double* __restrict__ z, int64_t n, int* status) {
+// ---- single-model chain solver on the assembled BSR matrix -------------------------------
+// factor: G_k = S_k^-1 and W_k = O_k G_k for every chain position (sequential recurrence, one
+// thread); apply: one thread per right-hand side walks forward (y) and backward (x), reading
+// the shared factors as warp-broadcast loads.  The factors persist in the handle so the modal
+// solver's shift-invert steps only pay for the sweeps.
+__global__ void chain_factor_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ rowptr,
+                                    const int32_t* __restrict__ colidx, const int32_t* __restrict__ diag_blk,
+                                    const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
+                                    double* __restrict__ Gs, double* __restrict__ W, int64_t n, int* status) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double S[36], G[36], O[36], Wk[36], y[6];
+  double S[36], G[36], O[36], Wk[36];
   bool ok = true;
   {
     const int64_t i0 = order[0];
@@ -79,21 +80,14 @@ __global__ void chain_solve_kernel(const int32_t* __restrict__ order, const int3
     const double* d = vals + (size_t)diag_blk[i0] * 36;
     for (int q = 0; q < 36; ++q) S[q] = d[q];
     mask_block(S, m0, m0, true);
-    for (int c = 0; c < 6; ++c) y[c] = b[i0 * 6 + c];
   }
   for (int64_t k = 0; k < n; ++k) {
     const int64_t i = order[k];
     ok = inv6_spd(S, G) && ok;
-    // z_k = G y
-    for (int r = 0; r < 6; ++r) {
-      double s = 0.0;
-      for (int c = 0; c < 6; ++c) s += G[r * 6 + c] * y[c];
-      z[k * 6 + r] = s;
-    }
+    for (int q = 0; q < 36; ++q) Gs[k * 36 + q] = G[q];
     if (k + 1 == n) break;
     const int64_t j = order[k + 1];
-    // O = K[j][i] (zero if j is not a neighbour: start of another path)
-    int blk = -1;
+    int blk = -1;  // O = K[j][i] (zero if j is not a neighbour: start of another path)
     for (int bb = rowptr[j]; bb < rowptr[j + 1]; ++bb)
       if (colidx[bb] == (int32_t)i) blk = bb;
     const unsigned mi = node_mask(free_mask, i), mj = node_mask(free_mask, j);
@@ -104,69 +98,113 @@ __global__ void chain_solve_kernel(const int32_t* __restrict__ order, const int3
     } else {
       for (int q = 0; q < 36; ++q) O[q] = 0.0;
     }
-    // W = O G ; S_next = D_j - W O^T ; y_next = b_j - W y
     for (int r = 0; r < 6; ++r)
       for (int c = 0; c < 6; ++c) {
-        double s = 0.0;
-        for (int t = 0; t < 6; ++t) s += O[r * 6 + t] * G[t * 6 + c];
-        Wk[r * 6 + c] = s;
+        double sacc = 0.0;
+        for (int t = 0; t < 6; ++t) sacc += O[r * 6 + t] * G[t * 6 + c];
+        Wk[r * 6 + c] = sacc;
       }
     for (int q = 0; q < 36; ++q) W[k * 36 + q] = Wk[q];
     const double* d = vals + (size_t)diag_blk[j] * 36;
     for (int q = 0; q < 36; ++q) S[q] = d[q];
     mask_block(S, mj, mj, true);
-    double yn[6];
-    for (int r = 0; r < 6; ++r) {
-      double s = b[j * 6 + r];
+    for (int r = 0; r < 6; ++r)
       for (int c = 0; c < 6; ++c) {
-        s -= Wk[r * 6 + c] * y[c];
         double t = 0.0;
         for (int q = 0; q < 6; ++q) t += Wk[r * 6 + q] * O[c * 6 + q];
         S[r * 6 + c] -= t;
       }
-      yn[r] = s;
+  }
+  *status = ok ? 0 : 1;
+}
+
+// b, x: nrhs vectors with leading dimension ld (x may alias nothing; z is staged in x)
+__global__ void chain_apply_kernel(const int32_t* __restrict__ order, const double* __restrict__ Gs,
+                                   const double* __restrict__ W, const double* __restrict__ b,
+                                   double* __restrict__ x, int64_t n, int nrhs, int64_t ld) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nrhs) return;
+  const double* bq = b + (size_t)q * ld;
+  double* xq = x + (size_t)q * ld;
+  double y[6], z[6];
+  {
+    const int64_t i0 = order[0];
+    for (int c = 0; c < 6; ++c) y[c] = bq[i0 * 6 + c];
+  }
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t i = order[k];
+    const double* G = Gs + k * 36;
+    for (int r = 0; r < 6; ++r) {
+      double sacc = 0.0;
+      for (int c = 0; c < 6; ++c) sacc += G[r * 6 + c] * y[c];
+      z[r] = sacc;
+    }
+    for (int c = 0; c < 6; ++c) xq[i * 6 + c] = z[c];   // z_k staged in x
+    if (k + 1 == n) break;
+    const int64_t j = order[k + 1];
+    const double* Wk = W + k * 36;
+    double yn[6];
+    for (int r = 0; r < 6; ++r) {
+      double sacc = bq[j * 6 + r];
+      for (int c = 0; c < 6; ++c) sacc -= Wk[r * 6 + c] * y[c];
+      yn[r] = sacc;
     }
     for (int c = 0; c < 6; ++c) y[c] = yn[c];
   }
-  // back substitution: x_k = z_k - W_k^T x_{k+1}
   double xn[6];
-  for (int c = 0; c < 6; ++c) { xn[c] = z[(n - 1) * 6 + c]; x[(int64_t)order[n - 1] * 6 + c] = xn[c]; }
+  for (int c = 0; c < 6; ++c) xn[c] = z[c];              // x_{n-1} = z_{n-1}
   for (int64_t k = n - 2; k >= 0; --k) {
+    const int64_t i = order[k];
+    const double* Wk = W + k * 36;
     double xk[6];
     for (int r = 0; r < 6; ++r) {
-      double s = z[k * 6 + r];
-      for (int c = 0; c < 6; ++c) s -= W[k * 36 + c * 6 + r] * xn[c];
-      xk[r] = s;
+      double sacc = xq[i * 6 + r];
+      for (int c = 0; c < 6; ++c) sacc -= Wk[c * 6 + r] * xn[c];
+      xk[r] = sacc;
     }
-    const int64_t i = order[k];
-    for (int c = 0; c < 6; ++c) { xn[c] = xk[c]; x[i * 6 + c] = xk[c]; }
+    for (int c = 0; c < 6; ++c) { xn[c] = xk[c]; xq[i * 6 + c] = xk[c]; }
   }
-  *status = ok ? 0 : 1;
 }
 
 // defined in solver.cu
 int setup_rhs_for_direct(femb_handle* h);
 
-int run_chain_solve(femb_handle* h, femb_stats* st) {
+int chain_factor(femb_handle* h) {
   if (h->kind != Kind::Frame || !h->sym.is_chain) return fail(h, FEMB_ERR_ARG, "mesh is not a chain (path graph)");
-  int rc = setup_rhs_for_direct(h);
-  if (rc) return rc;
-  DevBuf<int32_t> order;
-  DevBuf<double> W, z;
+  if (h->chain_factored) return FEMB_OK;
   DevBuf<int> status;
-  FEMB_CUDA(h, upload(order, h->sym.chain_order, h->stream));
-  FEMB_CUDA(h, W.alloc((size_t)h->n_nodes * 36));
-  FEMB_CUDA(h, z.alloc((size_t)h->n_nodes * 6));
+  FEMB_CUDA(h, upload(h->chain_order, h->sym.chain_order, h->stream));
+  FEMB_CUDA(h, h->chainW.alloc((size_t)h->n_nodes * 36));
+  FEMB_CUDA(h, h->chainG.alloc((size_t)h->n_nodes * 36));
   FEMB_CUDA(h, status.alloc(1));
-  chain_solve_kernel<<<1, 32, 0, h->stream>>>(order.p, h->rowptr.p, h->colidx.p, h->diag_blk.p, h->Kvals.p,
-                                              h->free_mask.p, h->b.p, h->x.p, W.p, z.p, h->n_nodes, status.p);
+  chain_factor_kernel<<<1, 32, 0, h->stream>>>(h->chain_order.p, h->rowptr.p, h->colidx.p, h->diag_blk.p, h->Kvals.p,
+                                               h->free_mask.p, h->chainG.p, h->chainW.p, h->n_nodes, status.p);
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   int* hs = reinterpret_cast<int*>(h->pinned);
   FEMB_CUDA(h, cudaMemcpyAsync(hs, status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (st) { st->method_used = FEMB_SOLVER_CHAIN; st->iterations = 1; st->converged = (*hs == 0); st->rel_residual = 0.0; }
   if (*hs != 0) return fail(h, FEMB_ERR_SINGULAR, "chain factorisation hit a non-positive pivot (K_ff not positive definite)");
+  h->chain_factored = true;
+  return FEMB_OK;
+}
+
+int chain_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_t ld) {
+  chain_apply_kernel<<<(nrhs + 31) / 32, 32, 0, h->stream>>>(h->chain_order.p, h->chainG.p, h->chainW.p, d_b, d_x,
+                                                             h->n_nodes, nrhs, ld);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+int run_chain_solve(femb_handle* h, femb_stats* st) {
+  int rc = setup_rhs_for_direct(h);
+  if (rc) return rc;
+  rc = chain_factor(h);
+  if (rc) return rc;
+  rc = chain_apply(h, h->b.p, h->x.p, 1, h->ndof);
+  if (rc) return rc;
+  if (st) { st->method_used = FEMB_SOLVER_CHAIN; st->iterations = 1; st->converged = 1; st->rel_residual = 0.0; }
   return FEMB_OK;
 }
 
@@ -337,11 +375,9 @@ __global__ void dense_fill_kernel(const int32_t* __restrict__ rowptr, const int3
   }
 }
 
-// right-looking Cholesky, one CTA, A row-major lower triangle overwritten by L; then
-// forward / backward substitution for one right-hand side.
+// right-looking Cholesky, one CTA, A row-major lower triangle overwritten by L.
 __global__ void __launch_bounds__(1024)
-dense_chol_solve_kernel(double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
-                        int n, int* status) {
+dense_chol_kernel(double* __restrict__ A, int n, int* status) {
   __shared__ double s_col[2048];
   __shared__ int s_bad;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -366,46 +402,70 @@ dense_chol_solve_kernel(double* __restrict__ A, const double* __restrict__ b, do
     }
     __syncthreads();
   }
-  // forward: L y = b   (column sweep)
-  for (int i = tid; i < n; i += nt) s_col[i] = b[i];
+  if (tid == 0) *status = s_bad;
+}
+
+// forward / backward substitution with the Cholesky factor; one CTA per right-hand side.
+__global__ void __launch_bounds__(1024)
+dense_apply_kernel(const double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
+                   int n, int64_t ld) {
+  __shared__ double s_col[2048];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double* bq = b + (size_t)blockIdx.x * ld;
+  double* xq = x + (size_t)blockIdx.x * ld;
+  for (int i = tid; i < n; i += nt) s_col[i] = bq[i];
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
+  for (int j = 0; j < n; ++j) {            // L y = b (column sweep)
     if (tid == 0) s_col[j] = s_col[j] / A[(size_t)j * n + j];
     __syncthreads();
     const double yj = s_col[j];
     for (int i = j + 1 + tid; i < n; i += nt) s_col[i] -= A[(size_t)i * n + j] * yj;
     __syncthreads();
   }
-  // backward: L^T x = y
-  for (int j = n - 1; j >= 0; --j) {
+  for (int j = n - 1; j >= 0; --j) {       // L^T x = y
     if (tid == 0) s_col[j] = s_col[j] / A[(size_t)j * n + j];
     __syncthreads();
     const double xj = s_col[j];
     for (int i = tid; i < j; i += nt) s_col[i] -= A[(size_t)j * n + i] * xj;
     __syncthreads();
   }
-  for (int i = tid; i < n; i += nt) x[i] = s_col[i];
-  if (tid == 0) *status = s_bad;
+  for (int i = tid; i < n; i += nt) xq[i] = s_col[i];
 }
 
-int run_dense_solve(femb_handle* h, femb_stats* st) {
+int dense_factor(femb_handle* h) {
   const int64_t n = h->ndof;
   if (n > 2048) return fail(h, FEMB_ERR_ARG, "dense solver is limited to 2048 DOFs");
-  int rc = setup_rhs_for_direct(h);
-  if (rc) return rc;
-  DevBuf<double> A;
+  if (h->dense_factored) return FEMB_OK;
   DevBuf<int> status;
-  FEMB_CUDA(h, A.alloc((size_t)n * n));
+  FEMB_CUDA(h, h->denseL.alloc((size_t)n * n));
   FEMB_CUDA(h, status.alloc(1));
-  dense_fill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, A.p, n, h->bs);
-  dense_chol_solve_kernel<<<1, 1024, 0, h->stream>>>(A.p, h->b.p, h->x.p, (int)n, status.p);
+  dense_fill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, h->denseL.p, n, h->bs);
+  dense_chol_kernel<<<1, 1024, 0, h->stream>>>(h->denseL.p, (int)n, status.p);
   h->launches += 2;
   FEMB_CUDA(h, cudaGetLastError());
   int* hs = reinterpret_cast<int*>(h->pinned);
   FEMB_CUDA(h, cudaMemcpyAsync(hs, status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (st) { st->method_used = FEMB_SOLVER_DENSE; st->iterations = 1; st->converged = (*hs == 0); st->rel_residual = 0.0; }
   if (*hs != 0) return fail(h, FEMB_ERR_SINGULAR, "dense Cholesky hit a non-positive pivot (K_ff not positive definite)");
+  h->dense_factored = true;
+  return FEMB_OK;
+}
+
+int dense_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_t ld) {
+  dense_apply_kernel<<<nrhs, 1024, 0, h->stream>>>(h->denseL.p, d_b, d_x, (int)h->ndof, ld);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+int run_dense_solve(femb_handle* h, femb_stats* st) {
+  int rc = setup_rhs_for_direct(h);
+  if (rc) return rc;
+  rc = dense_factor(h);
+  if (rc) return rc;
+  rc = dense_apply(h, h->b.p, h->x.p, 1, h->ndof);
+  if (rc) return rc;
+  if (st) { st->method_used = FEMB_SOLVER_DENSE; st->iterations = 1; st->converged = 1; st->rel_residual = 0.0; }
   return FEMB_OK;
 }
 

@@ -433,17 +433,28 @@ struct PcgPeek {
   double scal[Scal::COUNT];
 };
 
+static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
+
 int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
+  int rc = build_rhs(h, h->u0.p != nullptr);
+  if (rc) return rc;
+  return pcg_core(h, o, h->b.p, st);
+}
+
+// K_ff x = b for an arbitrary (already masked) device right-hand side; solution in h->x
+int pcg_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
+  return pcg_core(h, o, d_b, st);
+}
+
+static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
   const int64_t n = h->ndof;
   const int gridv = vec_grid(h, n, kRowThreads);
   const int pstride = h->num_sms * 8;
-  int rc = build_rhs(h, h->u0.p != nullptr);
-  if (rc) return rc;
-  rc = setup_precond(h, o.precond);
+  int rc = setup_precond(h, o.precond);
   if (rc) return rc;
   FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
   const bool blockj = (o.precond == FEMB_PRECOND_BLOCK_JACOBI);
-#define INIT(BS, BJ) pcg_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->b.p, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, n, o.rtol, h->partials.p, pstride, h->scal.p, h->flags.p)
+#define INIT(BS, BJ) pcg_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(d_b, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, n, o.rtol, h->partials.p, pstride, h->scal.p, h->flags.p)
   if (h->bs == 6) { if (blockj) INIT(6, true); else INIT(6, false); }
   else { if (blockj) INIT(3, true); else INIT(3, false); }
 #undef INIT

@@ -64,7 +64,7 @@ typedef struct {
 
 typedef struct {
   int32_t k;             /* number of lowest modes wanted                                  */
-  int32_t block;         /* LOBPCG block size (>= k; 0 = k + max(4, k/4))                  */
+  int32_t block;         /* Krylov block size 1..4 (0 = 4); >= multiplicity of eigenvalues  */
   int32_t max_iter;      /* default 5000                                                   */
   int32_t reserved;
   double rtol;           /* ||K phi - lambda M phi|| <= rtol*||K phi||   default 1e-8      */
@@ -77,7 +77,7 @@ typedef struct {
   int32_t converged;
   int32_t spmv_launches;      /* SpMV kernel launches in this call                         */
   int32_t kernel_launches;    /* all kernel launches of this library in this call          */
-  int32_t spmv_timed;         /* SpMV launches bracketed by events (opts.profile)          */
+  int32_t spmv_timed;         /* SpMV launches bracketed by events (opts.profile); modal: restarts */
   double rel_residual;        /* final ||r||/||b||                                         */
   double device_ms;           /* CUDA-event time of the whole call on the handle's stream  */
   double spmv_ms;             /* summed device time of the timed SpMV launches              */
