@@ -9,6 +9,8 @@
 // list order, one per __syncthreads_or step, so the sum order is fixed by the symbolic
 // phase: no float atomics, bit-reproducible run to run.  Element matrices are never
 // materialised in HBM: traffic = mesh in + K (+M) out + the 12-byte/contribution map.
+#include <algorithm>
+
 #include "common.cuh"
 #include "elements.cuh"
 
@@ -166,120 +168,282 @@ assemble_tiles_kernel(const EL el, const PatternDev pat, double* __restrict__ Kv
 }
 
 // ---- frame fast path: one thread per (node, incident element end) ------------------------
-// The thread evaluates the element record ONCE and produces both the off-diagonal block
-// (node, other end) — stored straight into the tile's staging area — and its share of the
-// node's diagonal block, kept as the 21-value upper triangle (+7 compact mass values) and
-// added in element-ascending order, one rank per __syncthreads_or step.  Compared with the
-// generic one-thread-per-contribution kernel this halves the record evaluations and cuts
-// the shared-memory accumulate traffic from 72 to 28 values per element end.
+// Each thread reads ONE 16-byte pair record (own node, other node, target block, section /
+// end flag / position in the node's list — everything the symbolic phase can resolve, so the
+// only dependent loads left are the two coordinate triples and the section row), evaluates the
+// element record once, and
+//   * streams the off-diagonal block (node, other end) straight from registers to HBM with
+//     nine 32-byte stores (STG.256; a block is 288 contiguous bytes, 32-byte aligned);
+//   * parks its share of the node's diagonal block — the 21-value upper triangle plus 7 compact
+//     lumped-mass values — in shared memory, transposed so that lanes hit distinct banks.
+// After one barrier the CTA sums every node's shares in list (= element-ascending) order and
+// writes the expanded diagonal and mass blocks with coalesced stores.  No float atomics, no
+// rank loop: the summation order is fixed by the symbolic phase, so K and M are
+// bit-reproducible run to run.  Only ~29 KB of shared memory per 128-thread CTA.
 struct PairDev {
-  const int32_t* rowptr;
-  const int32_t* diag_blk;
-  const int32_t* pair_ptr;
-  const uint32_t* pair_code;
-  const int32_t* pair_blk;
-  const uint8_t* pair_rank;
-  const int32_t* tile_ptr;
+  const int4* rec;           // (n_pairs) {node, other, blk, sec | a<<24 | pos<<25}
+  const int32_t* pair_ptr;   // (n_nodes+1)
+  const int32_t* diag_blk;   // (n_nodes)
+  const int32_t* tile_ptr;   // (n_tiles+1) node ranges, <= THREADS pairs and <= THREADS nodes each
 };
 
-template <int THREADS, bool BULK>
-__global__ void __launch_bounds__(THREADS)
+__device__ __forceinline__ void st_global_256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+constexpr int kShareStride = 29;  // odd stride (in doubles): conflict-free 64-bit shared accesses
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 4)
 frame_assemble_pairs_kernel(const FrameParams P, const PairDev pat, double* __restrict__ Kvals,
                             double* __restrict__ Mdiag) {
+  __shared__ double s_c[THREADS * kShareStride];
+  __shared__ uint8_t s_rc[28];  // share index -> r*6+c inside the 6x6 block (K: q<21, M: q>=21)
+  const int tid = threadIdx.x;
+  const int n0 = pat.tile_ptr[blockIdx.x], n1 = pat.tile_ptr[blockIdx.x + 1];
+  const int p0 = pat.pair_ptr[n0], p1 = pat.pair_ptr[n1];
+  const int p = p0 + tid;
+  if (tid < 28) {
+    int r = 0, c = 0;
+    if (tid < 21) {        // upper triangle of the 6x6, row-major
+      int q = tid;
+      while (q >= 6 - r) { q -= 6 - r; ++r; }
+      c = r + q;
+    } else if (tid == 21) {  // translational mass (scalar on the diagonal)
+      r = c = 0;
+    } else {               // upper triangle of the rotational 3x3
+      int q = tid - 22;
+      while (q >= 3 - r) { q -= 3 - r; ++r; }
+      c = 3 + r + q; r += 3;
+    }
+    s_rc[tid] = (uint8_t)(r * 6 + c);
+  }
+  if (p < p1) {
+    const int4 rec = __ldg(pat.rec + p);
+    const int a = (rec.w >> 24) & 1;
+    FrameRec R;
+    // the record is oriented from element end 0 to end 1 (BeamSolver.py:372-373)
+    frame_record_nodes(P, a ? rec.y : rec.x, a ? rec.x : rec.y, rec.w & 0xFFFFFF, R);
+    double* g = Kvals + (size_t)rec.z * 36;
+    double row[12];
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      frame_offdiag_row(R, a, 2 * h, row);
+      frame_offdiag_row(R, a, 2 * h + 1, row + 6);
+      st_global_256(g + 12 * h, row[0], row[1], row[2], row[3]);
+      st_global_256(g + 12 * h + 4, row[4], row[5], row[6], row[7]);
+      st_global_256(g + 12 * h + 8, row[8], row[9], row[10], row[11]);
+    }
+    double d[28];
+    frame_diag_sym(R, a, d, d + 21);
+    double* mine = s_c + tid * kShareStride;
+#pragma unroll
+    for (int q = 0; q < 28; ++q) mine[q] = d[q];
+  }
+  __syncthreads();
+  // one (node, share index) item per thread: ordered sum over the node's pairs, then the one
+  // to three entries of the diagonal K block / lumped-mass block that value fills.  The
+  // structurally zero entries of the mass block are zeroed once at allocation.
+  const int nn = n1 - n0;
+  for (int o = tid; o < nn * 28; o += THREADS) {
+    const int ns = o / 28, q = o - ns * 28;
+    const int node = n0 + ns;
+    const int j0 = pat.pair_ptr[node] - p0, j1 = pat.pair_ptr[node + 1] - p0;
+    double v = 0.0;
+    for (int j = j0; j < j1; ++j) v += s_c[j * kShareStride + q];
+    const int rc = s_rc[q];
+    if (q < 21) {
+      double* kd = Kvals + (size_t)pat.diag_blk[node] * 36;
+      kd[rc] = v;
+      const int r = rc / 6, c = rc - r * 6;
+      if (r != c) kd[c * 6 + r] = v;
+    } else if (q == 21) {
+      double* md = Mdiag + (size_t)node * 36;
+      md[0] = v; md[7] = v; md[14] = v;
+    } else {
+      double* md = Mdiag + (size_t)node * 36;
+      md[rc] = v;
+      const int r = rc / 6, c = rc - r * 6;
+      if (r != c) md[c * 6 + r] = v;
+    }
+  }
+}
+
+// Persistent form of the pair kernel: one CTA per resident slot walks tiles t, t+G, t+2G, ...
+// and software-pipelines the input side — the tile descriptor two tiles ahead, the pair records
+// one tile ahead, and (after the first barrier, when the element record's registers are dead)
+// the coordinates and section row of the next tile — so a tile's arithmetic never waits on a
+// dependent chain of global loads.
+struct PairDevP {
+  const int4* rec;        // (n_pairs) {node, other, blk, sec | a<<24 | pos<<25}
+  const int4* node_rec;   // (n_nodes) {first pair, pair count, diagonal block, 0}
+  const int4* tiles;      // (n_tiles) {first node, node count, first pair, pair count}
+  int n_tiles;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 4)
+frame_assemble_pairs_persistent_kernel(const FrameParams P, const PairDevP pat, double* __restrict__ Kvals,
+                                       double* __restrict__ Mdiag) {
+  __shared__ double s_c[THREADS * kShareStride];
+  __shared__ int4 s_node[THREADS];
+  __shared__ uint8_t s_rc[28];
+  const int tid = threadIdx.x;
+  const int G = gridDim.x;
+  int t = blockIdx.x;
+  if (t >= pat.n_tiles) return;
+  if (tid < 28) {
+    int r = 0, c = 0;
+    if (tid < 21) {
+      int q = tid;
+      while (q >= 6 - r) { q -= 6 - r; ++r; }
+      c = r + q;
+    } else if (tid > 21) {
+      int q = tid - 22;
+      while (q >= 3 - r) { q -= 3 - r; ++r; }
+      c = 3 + r + q; r += 3;
+    }
+    s_rc[tid] = (uint8_t)(r * 6 + c);
+  }
+  const int4 zero4 = make_int4(0, 0, 0, 0);
+  int4 td = __ldg(pat.tiles + t);
+  int4 td1 = (t + G < pat.n_tiles) ? __ldg(pat.tiles + t + G) : zero4;
+  int4 rec = (tid < td.w) ? __ldg(pat.rec + td.z + tid) : zero4;
+  FrameIn in;
+  {
+    const int a = (rec.w >> 24) & 1;
+    frame_load(P, a ? rec.y : rec.x, a ? rec.x : rec.y, rec.w & 0xFFFFFF, in);  // inactive lanes read node 0 / row 0
+  }
+  for (; t < pat.n_tiles; t += G) {
+    // ---- issue the loads of the tiles ahead
+    const int4 td2 = (t + 2 * G < pat.n_tiles) ? __ldg(pat.tiles + t + 2 * G) : zero4;
+    const int4 rec1 = (tid < td1.w) ? __ldg(pat.rec + td1.z + tid) : zero4;
+    const int4 nrec = (tid < td.y) ? __ldg(pat.node_rec + td.x + tid) : zero4;
+    // ---- phase 1: element record, off-diagonal block to HBM, diagonal shares to shared memory
+    if (tid < td.w) {
+      const int a = (rec.w >> 24) & 1;
+      FrameRec R;
+      frame_record_from(P, in, R);
+      double* g = Kvals + (size_t)rec.z * 36;
+      double row[12];
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        frame_offdiag_row(R, a, 2 * h, row);
+        frame_offdiag_row(R, a, 2 * h + 1, row + 6);
+        st_global_256(g + 12 * h, row[0], row[1], row[2], row[3]);
+        st_global_256(g + 12 * h + 4, row[4], row[5], row[6], row[7]);
+        st_global_256(g + 12 * h + 8, row[8], row[9], row[10], row[11]);
+      }
+      double d[28];
+      frame_diag_sym(R, a, d, d + 21);
+      double* mine = s_c + tid * kShareStride;
+#pragma unroll
+      for (int q = 0; q < 28; ++q) mine[q] = d[q];
+    }
+    s_node[tid] = nrec;
+    __syncthreads();
+    // ---- the next tile's coordinates / section rows travel while phase 2 runs
+    {
+      const int a = (rec1.w >> 24) & 1;
+      frame_load(P, a ? rec1.y : rec1.x, a ? rec1.x : rec1.y, rec1.w & 0xFFFFFF, in);
+    }
+    // ---- phase 2: ordered per-node sums -> diagonal K block and lumped-mass entries
+    for (int o = tid; o < td.y * 28; o += THREADS) {
+      const int ns = o / 28, q = o - ns * 28;
+      const int4 nr = s_node[ns];
+      const int j0 = nr.x - td.z, j1 = j0 + nr.y;
+      double v = 0.0;
+      for (int j = j0; j < j1; ++j) v += s_c[j * kShareStride + q];
+      const int rc = s_rc[q];
+      const int r = rc / 6, c = rc - r * 6;
+      if (q < 21) {
+        double* kd = Kvals + (size_t)nr.z * 36;
+        kd[rc] = v;
+        if (r != c) kd[c * 6 + r] = v;
+      } else {
+        double* md = Mdiag + (size_t)(td.x + ns) * 36;
+        if (q == 21) { md[0] = v; md[7] = v; md[14] = v; }
+        else {
+          md[rc] = v;
+          if (r != c) md[c * 6 + r] = v;
+        }
+      }
+    }
+    __syncthreads();  // s_c / s_node are rewritten by the next tile
+    td = td1; td1 = td2; rec = rec1;
+  }
+}
+
+// Variant with the whole tile staged in shared memory in its HBM layout and written by one
+// bulk async copy (cp.async.bulk shared -> global): stores are perfectly coalesced at the
+// price of ~420 B of shared memory per thread.  Diagonal shares are added into a 28-value
+// accumulator per node in list order, one position per __syncthreads_or step.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 4)
+frame_assemble_pairs_staged_kernel(const FrameParams P, const PairDev pat, const int32_t* __restrict__ rowptr,
+                                   double* __restrict__ Kvals, double* __restrict__ Mdiag) {
   extern __shared__ __align__(128) double s_out[];  // K blocks [nblk*36] | mass [nn*36] | diag acc [nn*28]
   const int tid = threadIdx.x;
   const int n0 = pat.tile_ptr[blockIdx.x], n1 = pat.tile_ptr[blockIdx.x + 1];
   const int nn = n1 - n0;
-  const int b0 = pat.rowptr[n0], b1 = pat.rowptr[n1];
+  const int b0 = rowptr[n0], b1 = rowptr[n1];
   const int p0 = pat.pair_ptr[n0], p1 = pat.pair_ptr[n1];
   const int nblk = b1 - b0;
   double* s_mass = s_out + (size_t)nblk * 36;
   double* s_diag = s_mass + (size_t)nn * 36;
   for (int t = tid; t < nn * 28; t += THREADS) s_diag[t] = 0.0;
-  __syncthreads();
-
-  for (int base = p0; base < p1; base += THREADS) {  // normally a single pass
-    const int p = base + tid;
-    int myk = -1, rank = -1, slot = 0, nslot = 0;
-    double acc[36];
+  const int p = p0 + tid;
+  int pos = -1, nslot = 0;
+  double d[28];
+  if (p < p1) {
+    const int4 rec = __ldg(pat.rec + p);
+    const int a = (rec.w >> 24) & 1;
+    pos = (int)((uint32_t)rec.w >> 25);
+    nslot = rec.x - n0;
     FrameRec R;
-    int a = 0;
-    if (p < p1) {
-      const uint32_t code = pat.pair_code[p];
-      a = (int)(code & 1u);
-      slot = pat.pair_blk[p] - b0;
-      rank = (int)pat.pair_rank[p];
-      int lo = n0, hi = n1 - 1;  // node owning pair p: largest node with pair_ptr[node] <= p
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (pat.pair_ptr[mid] <= p) lo = mid; else hi = mid - 1;
-      }
-      nslot = lo - n0;
-      myk = p - max(pat.pair_ptr[lo], base);
-      frame_record(P, code >> 1, R);
-      frame_kblock<true>(R, a, 1 - a, acc);
-      if (rank == 0) {
-        double2* dst = reinterpret_cast<double2*>(s_out + (size_t)slot * 36);
+    frame_record_nodes(P, a ? rec.y : rec.x, a ? rec.x : rec.y, rec.w & 0xFFFFFF, R);
+    double2* dst = reinterpret_cast<double2*>(s_out + (size_t)(rec.z - b0) * 36);
+    double row[12];
 #pragma unroll
-        for (int q = 0; q < 18; ++q) dst[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
-      }
+    for (int h = 0; h < 3; ++h) {
+      frame_offdiag_row(R, a, 2 * h, row);
+      frame_offdiag_row(R, a, 2 * h + 1, row + 6);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) dst[6 * h + q] = make_double2(row[2 * q], row[2 * q + 1]);
     }
-    // duplicate members between the same two nodes (rare): ordered adds after the rank-0 store
-    for (int k = 1; __syncthreads_or(rank >= k); ++k) {
-      if (rank == k) {
-        double* dst = s_out + (size_t)slot * 36;
+    frame_diag_sym(R, a, d, d + 21);
+  }
+  __syncthreads();
+  for (int k = 0; __syncthreads_or(pos >= k); ++k) {
+    if (pos == k) {
+      double* acc = s_diag + (size_t)nslot * 28;
 #pragma unroll
-        for (int q = 0; q < 36; ++q) dst[q] += acc[q];
-      }
-    }
-    // diagonal share: 21 symmetric stiffness values + 7 compact mass values, ordered by rank
-    if (p < p1) frame_diag_sym(R, a, acc, acc + 21);
-    for (int k = 0; __syncthreads_or(myk >= k); ++k) {
-      if (myk == k) {
-        double* dst = s_diag + (size_t)nslot * 28;
-#pragma unroll
-        for (int q = 0; q < 28; ++q) dst[q] += acc[q];
-      }
+      for (int q = 0; q < 28; ++q) acc[q] += d[q];
     }
   }
-
-  // expand the symmetric accumulators into the diagonal K blocks and the dense mass blocks
   for (int t = tid; t < nn * 36; t += THREADS) {
     const int ns = t / 36, rc = t - ns * 36;
     const int r = rc / 6, c = rc - r * 6;
-    const double* d = s_diag + (size_t)ns * 28;
-    s_out[(size_t)(pat.diag_blk[n0 + ns] - b0) * 36 + rc] = d[sym6_index(r, c)];
+    const double* dd = s_diag + (size_t)ns * 28;
+    s_out[(size_t)(pat.diag_blk[n0 + ns] - b0) * 36 + rc] = dd[sym6_index(r, c)];
     double mv = 0.0;
-    if (r < 3 && c < 3) mv = (r == c) ? d[21] : 0.0;
+    if (r < 3 && c < 3) mv = (r == c) ? dd[21] : 0.0;
     else if (r >= 3 && c >= 3) {
       const int rr = r - 3, cc = c - 3;
       const int lo = rr < cc ? rr : cc, hi = rr < cc ? cc : rr;
-      mv = d[22 + lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo)];
+      mv = dd[22 + lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo)];
     }
     s_mass[t] = mv;
   }
-
-  double* gK = Kvals + (size_t)b0 * 36;
-  double* gM = Mdiag + (size_t)n0 * 36;
-  if (BULK) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                   :: "l"(gK), "r"(smem_u32(s_out)), "r"((uint32_t)(nblk * 288)) : "memory");
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                   :: "l"(gM), "r"(smem_u32(s_mass)), "r"((uint32_t)(nn * 288)) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-  } else {
-    __syncthreads();
-    const double2* s2 = reinterpret_cast<const double2*>(s_out);
-    double2* g2 = reinterpret_cast<double2*>(gK);
-    for (int i = tid; i < nblk * 18; i += THREADS) g2[i] = s2[i];
-    const double2* m2 = reinterpret_cast<const double2*>(s_mass);
-    double2* gm2 = reinterpret_cast<double2*>(gM);
-    for (int i = tid; i < nn * 18; i += THREADS) gm2[i] = m2[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(Kvals + (size_t)b0 * 36), "r"(smem_u32(s_out)), "r"((uint32_t)(nblk * 288)) : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(Mdiag + (size_t)n0 * 36), "r"(smem_u32(s_mass)), "r"((uint32_t)(nn * 288)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 
@@ -395,23 +559,27 @@ static int launch_assemble_pairs(femb_handle* h) {
   const femb::Symbolic& S = h->sym;
   const int n_tiles = (int)S.pair_tile_ptr.size() - 1;
   if (n_tiles <= 0) return FEMB_OK;
-  size_t smem = 0;
-  for (int t = 0; t < n_tiles; ++t) {
-    const int n0 = S.pair_tile_ptr[t], n1 = S.pair_tile_ptr[t + 1];
-    const size_t need = (size_t)(S.rowptr[n1] - S.rowptr[n0]) * 288 + (size_t)(n1 - n0) * (288 + 224);
-    smem = need > smem ? need : smem;
-  }
-  smem = (smem + 127) & ~size_t(127);
-  if (smem > 200 * 1024) return fail(h, FEMB_ERR_ARG, "assembly tile exceeds shared memory (node degree too large)");
-  PairDev pat{h->rowptr.p, h->diag_blk.p, h->pair_ptr.p, h->pair_code.p, h->pair_blk.p, h->pair_rank.p, h->pair_tile_ptr.p};
-  if (bulk_enabled()) {
-    auto k = frame_assemble_pairs_kernel<kAsmThreads, true>;
-    FEMB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<n_tiles, kAsmThreads, smem, h->stream>>>(frame_params(h), pat, h->Kvals.p, h->Mdiag.p);
+  PairDev pat{reinterpret_cast<const int4*>(h->pair_rec.p), h->pair_ptr.p, h->diag_blk.p, h->pair_tile_ptr.p};
+  const char* v = getenv("FEMB_ASM_PAIRS");
+  if (!v || v[0] == '4') {
+    PairDevP pp{reinterpret_cast<const int4*>(h->pair_rec.p), reinterpret_cast<const int4*>(h->pair_node_rec.p),
+                reinterpret_cast<const int4*>(h->pair_tiles.p), n_tiles};
+    const int grid = std::min(n_tiles, h->num_sms * 4);
+    frame_assemble_pairs_persistent_kernel<kAsmThreads><<<grid, kAsmThreads, 0, h->stream>>>(frame_params(h), pp, h->Kvals.p, h->Mdiag.p);
+  } else if (v[0] == '2') {
+    frame_assemble_pairs_kernel<kAsmThreads><<<n_tiles, kAsmThreads, 0, h->stream>>>(frame_params(h), pat, h->Kvals.p, h->Mdiag.p);
   } else {
-    auto k = frame_assemble_pairs_kernel<kAsmThreads, false>;
+    size_t smem = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int n0 = S.pair_tile_ptr[t], n1 = S.pair_tile_ptr[t + 1];
+      const size_t need = (size_t)(S.rowptr[n1] - S.rowptr[n0]) * 288 + (size_t)(n1 - n0) * (288 + 224);
+      smem = need > smem ? need : smem;
+    }
+    smem = (smem + 127) & ~size_t(127);
+    if (smem > 200 * 1024) return fail(h, FEMB_ERR_ARG, "assembly tile exceeds shared memory");
+    auto k = frame_assemble_pairs_staged_kernel<kAsmThreads>;
     FEMB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<n_tiles, kAsmThreads, smem, h->stream>>>(frame_params(h), pat, h->Kvals.p, h->Mdiag.p);
+    k<<<n_tiles, kAsmThreads, smem, h->stream>>>(frame_params(h), pat, h->rowptr.p, h->Kvals.p, h->Mdiag.p);
   }
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
@@ -424,7 +592,7 @@ static bool generic_forced() {
 }
 
 int launch_assemble(femb_handle* h) {
-  if (h->kind == Kind::Frame && h->sym.pairs_ok && !generic_forced()) return launch_assemble_pairs(h);
+  if (h->kind == Kind::Frame && h->pairs_dev_ok && !generic_forced()) return launch_assemble_pairs(h);
   if (h->kind == Kind::Frame) {
     FrameEl el;
     el.P = frame_params(h);

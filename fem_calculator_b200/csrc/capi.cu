@@ -113,6 +113,7 @@ int femb_frame_set_mesh(femb_handle* h, int64_t n_nodes, int64_t n_elem, const d
   int rc = set_mesh_common(h, Kind::Frame, 6, 2, n_nodes, n_elem, xyz, conn);
   if (rc) return rc;
   h->E = E; h->G = G; h->rho = rho; h->n_sec = n_sec;
+  h->h_elem_sec.assign(elem_sec, elem_sec + n_elem);
   FEMB_CUDA(h, upload(h->elem_sec, elem_sec, (size_t)n_elem, h->stream));
   FEMB_CUDA(h, upload(h->sec_props, sec_props, (size_t)n_sec * 8, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -175,15 +176,50 @@ static int ensure_symbolic(femb_handle* h) {
   FEMB_CUDA(h, upload(h->contrib, S.contrib, h->stream));
   FEMB_CUDA(h, upload(h->contrib_blk, S.contrib_blk, h->stream));
   FEMB_CUDA(h, upload(h->tile_ptr, S.tile_ptr, h->stream));
-  if (S.pairs_ok) {
+  h->pairs_dev_ok = false;
+  if (S.pairs_ok && h->kind == Kind::Frame && h->n_sec < (1 << 24)) {
+    // 16-byte pair records: everything the pair kernel would otherwise chase through
+    // pair_code -> conn -> elem_sec is resolved here once
+    const size_t np = S.pair_code.size();
+    std::vector<int32_t> rec(np * 4);
+    for (int64_t i = 0; i < h->n_nodes; ++i)
+      for (int32_t p = S.pair_ptr[i]; p < S.pair_ptr[i + 1]; ++p) {
+        const uint32_t code = S.pair_code[p];
+        const uint32_t e = code >> 1, a = code & 1u;
+        rec[4 * (size_t)p + 0] = (int32_t)i;
+        rec[4 * (size_t)p + 1] = h->h_conn[2 * (size_t)e + (1 - a)];
+        rec[4 * (size_t)p + 2] = S.pair_blk[p];
+        rec[4 * (size_t)p + 3] = (int32_t)((uint32_t)h->h_elem_sec[e] | (a << 24) | ((uint32_t)(p - S.pair_ptr[i]) << 25));
+      }
+    std::vector<int32_t> nrec((size_t)h->n_nodes * 4, 0);
+    for (int64_t i = 0; i < h->n_nodes; ++i) {
+      nrec[4 * i + 0] = S.pair_ptr[i];
+      nrec[4 * i + 1] = S.pair_ptr[i + 1] - S.pair_ptr[i];
+      nrec[4 * i + 2] = S.diag_blk[i];
+    }
+    const size_t nt = S.pair_tile_ptr.size() - 1;
+    std::vector<int32_t> tiles(nt * 4);
+    for (size_t t = 0; t < nt; ++t) {
+      const int32_t n0 = S.pair_tile_ptr[t], n1 = S.pair_tile_ptr[t + 1];
+      tiles[4 * t + 0] = n0;
+      tiles[4 * t + 1] = n1 - n0;
+      tiles[4 * t + 2] = S.pair_ptr[n0];
+      tiles[4 * t + 3] = S.pair_ptr[n1] - S.pair_ptr[n0];
+    }
+    FEMB_CUDA(h, upload(h->pair_node_rec, nrec, h->stream));
+    FEMB_CUDA(h, upload(h->pair_tiles, tiles, h->stream));
     FEMB_CUDA(h, upload(h->pair_ptr, S.pair_ptr, h->stream));
-    FEMB_CUDA(h, upload(h->pair_code, S.pair_code, h->stream));
-    FEMB_CUDA(h, upload(h->pair_blk, S.pair_blk, h->stream));
-    FEMB_CUDA(h, upload(h->pair_rank, S.pair_rank, h->stream));
+    FEMB_CUDA(h, upload(h->pair_rec, rec, h->stream));
     FEMB_CUDA(h, upload(h->pair_tile_ptr, S.pair_tile_ptr, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));  // rec is a local
+    h->pairs_dev_ok = true;
   }
   FEMB_CUDA(h, h->Kvals.alloc((size_t)S.nnzb * h->bs * h->bs));
-  if (h->kind == Kind::Frame) FEMB_CUDA(h, h->Mdiag.alloc((size_t)h->n_nodes * 36));
+  if (h->kind == Kind::Frame) {
+    FEMB_CUDA(h, h->Mdiag.alloc((size_t)h->n_nodes * 36));
+    // the pair kernel only writes the 12 structurally non-zero entries of each lumped-mass block
+    FEMB_CUDA(h, cudaMemsetAsync(h->Mdiag.p, 0, h->Mdiag.bytes(), h->stream));
+  }
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_symbolic = true;
   return FEMB_OK;
@@ -452,10 +488,13 @@ int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, doubl
     // fused element+assembly: mesh in (60 B/element frame, 10*(4+24) tet) + K (+M) out;
     // the scatter map (12 B/contribution + 4 B/block) is counted as algorithmic input too.
     const double mesh_in = (h->kind == Kind::Frame) ? 60.0 * h->n_elem : 280.0 * h->n_elem;
-    const bool pairs = (h->kind == Kind::Frame) && S.pairs_ok;
-    const double map_bytes = pairs ? 9.0 * (double)S.pair_code.size() + 8.0 * h->n_nodes
+    const bool pairs = (h->kind == Kind::Frame) && h->pairs_dev_ok;
+    // pair kernel: 16 B/pair record + 16 B/node record; it writes only the 12 non-zero entries of
+    // each lumped-mass block (96 B/node); the generic kernel writes all 36 (288 B/node)
+    const double map_bytes = pairs ? 16.0 * (double)S.pair_code.size() + 16.0 * h->n_nodes
                                    : 12.0 * S.n_contrib + 4.0 * S.nnzb;
-    *bytes = mesh_in + 8.0 * S.nnzb * bs2 + (h->kind == Kind::Frame ? 8.0 * h->n_nodes * bs2 : 0.0) + map_bytes;
+    const double mass_out = (h->kind == Kind::Frame) ? (pairs ? 96.0 : 288.0) * h->n_nodes : 0.0;
+    *bytes = mesh_in + 8.0 * S.nnzb * bs2 + mass_out + map_bytes;
     for (int i = 0; i < warm && !rc; ++i) rc = launch_assemble(h);
     FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < reps && !rc; ++i) rc = launch_assemble(h);

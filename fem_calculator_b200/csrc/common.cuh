@@ -61,9 +61,8 @@ struct Symbolic {
   std::vector<int32_t> pair_ptr;     // (n_nodes+1)
   std::vector<uint32_t> pair_code;   // (n_pairs) e*2 + a
   std::vector<int32_t> pair_blk;     // (n_pairs) block (node, other end)
-  std::vector<uint8_t> pair_rank;    // (n_pairs) rank inside that block's contribution list
   std::vector<int32_t> pair_tile_ptr;  // (n_pair_tiles+1) node ranges of the pair-kernel tiles
-  bool pairs_ok = false;             // false: self-loop element or >255 duplicates -> generic kernel
+  bool pairs_ok = false;             // false: self-loop / duplicate members / hub node -> generic kernel
   bool is_chain = false;             // path graph(s): block-tridiagonal after chain ordering
   std::vector<int32_t> chain_order;  // (n_nodes) node visited at chain position k
 };
@@ -95,15 +94,18 @@ struct femb_handle {
   int32_t n_sec = 0;
   double E = 0, G = 0, rho = 0, nu = 0;
   std::vector<int32_t> h_conn;     // host copy for the symbolic phase
+  std::vector<int32_t> h_elem_sec; // host copy (frame): baked into the pair records
 
   // pattern (device)
   femb::Symbolic sym;
   bool have_symbolic = false, assembled = false;
   femb::DevBuf<int32_t> rowptr, colidx, blk_row, diag_blk, contrib_ptr, contrib_blk, tile_ptr;
   femb::DevBuf<uint32_t> contrib;
-  femb::DevBuf<int32_t> pair_ptr, pair_blk, pair_tile_ptr;
-  femb::DevBuf<uint32_t> pair_code;
-  femb::DevBuf<uint8_t> pair_rank;
+  femb::DevBuf<int32_t> pair_ptr, pair_tile_ptr;
+  femb::DevBuf<int32_t> pair_rec;   // (n_pairs,4) {node, other node, block, sec | end<<24 | pos<<25}
+  femb::DevBuf<int32_t> pair_node_rec;  // (n_nodes,4) {first pair, pair count, diagonal block, 0}
+  femb::DevBuf<int32_t> pair_tiles;     // (n_tiles,4) {first node, node count, first pair, pair count}
+  bool pairs_dev_ok = false;        // pair records uploaded (frame fast path usable)
   femb::DevBuf<double> Kvals;      // (nnzb, bs, bs)
   femb::DevBuf<double> Mdiag;      // (n_nodes, bs, bs) frame only
   femb::DevBuf<unsigned long long> counters;  // device scalars: [0] skipped gauss points

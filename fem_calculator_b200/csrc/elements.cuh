@@ -29,15 +29,38 @@ struct FrameRec {
   double L;
 };
 
-__device__ __forceinline__ void frame_record(const FrameParams& P, uint32_t e, FrameRec& r) {
-  const int32_t na = P.conn[2 * e], nb = P.conn[2 * e + 1];
+// raw inputs of one element record: end-to-end vector and the section row
+struct FrameIn {
+  double dx, dy, dz;
+  double A, Ix, Iy, J, ky, kz;
+};
+
+__device__ __forceinline__ void frame_load(const FrameParams& P, int32_t na, int32_t nb, int32_t sec, FrameIn& in) {
   const double* pa = P.xyz + 3 * (size_t)na;
   const double* pb = P.xyz + 3 * (size_t)nb;
-  const double dx = __ldg(pb) - __ldg(pa), dy = __ldg(pb + 1) - __ldg(pa + 1),
-               dz = __ldg(pb + 2) - __ldg(pa + 2);
-  const double* sp = P.sec_props + 8 * (size_t)P.elem_sec[e];
-  const double A = __ldg(sp), Ix = __ldg(sp + 1), Iy = __ldg(sp + 2), J = __ldg(sp + 3),
-               ky = __ldg(sp + 4), kz = __ldg(sp + 5);
+  in.dx = __ldg(pb) - __ldg(pa); in.dy = __ldg(pb + 1) - __ldg(pa + 1); in.dz = __ldg(pb + 2) - __ldg(pa + 2);
+  const double* sp = P.sec_props + 8 * (size_t)sec;
+  in.A = __ldg(sp); in.Ix = __ldg(sp + 1); in.Iy = __ldg(sp + 2); in.J = __ldg(sp + 3);
+  in.ky = __ldg(sp + 4); in.kz = __ldg(sp + 5);
+}
+
+__device__ __forceinline__ void frame_record_from(const FrameParams& P, const FrameIn& in, FrameRec& r);
+
+// element record from its two end nodes (na -> nb) and section row
+__device__ __forceinline__ void frame_record_nodes(const FrameParams& P, int32_t na, int32_t nb, int32_t sec,
+                                                   FrameRec& r) {
+  FrameIn in;
+  frame_load(P, na, nb, sec, in);
+  frame_record_from(P, in, r);
+}
+
+__device__ __forceinline__ void frame_record(const FrameParams& P, uint32_t e, FrameRec& r) {
+  frame_record_nodes(P, P.conn[2 * e], P.conn[2 * e + 1], P.elem_sec[e], r);
+}
+
+__device__ __forceinline__ void frame_record_from(const FrameParams& P, const FrameIn& in, FrameRec& r) {
+  const double dx = in.dx, dy = in.dy, dz = in.dz;
+  const double A = in.A, Ix = in.Ix, Iy = in.Iy, J = in.J, ky = in.ky, kz = in.kz;
   const double L2 = dx * dx + dy * dy + dz * dz;
   // 1/L through rsqrt (one MUFU + Newton) instead of sqrt followed by a division; the few-ulp
   // difference to numpy's norm/divide is far inside the 1e-14 parity band.
@@ -127,6 +150,28 @@ __device__ __forceinline__ void frame_kblock(const FrameRec& R, int a, int b, do
         acc[r * 6 + c] += uu; acc[r * 6 + 3 + c] += ut;
         acc[(3 + r) * 6 + c] += tu; acc[(3 + r) * 6 + 3 + c] += th;
       }
+    }
+  }
+}
+
+// row6 = row `row` (0..5) of the off-diagonal block [a][1-a] of R^T k R — the same expressions
+// as frame_kblock, one row at a time so the pair kernel can stream rows out of registers.
+__device__ __forceinline__ void frame_offdiag_row(const FrameRec& R, int a, int row, double* row6) {
+  const double sa = (a == 0) ? 1.0 : -1.0;
+  const int r = row < 3 ? row : row - 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double tt = R.t[r] * R.t[c];
+    const double n11 = R.n1[r] * R.n1[c];
+    const double n22 = R.n2[r] * R.n2[c];
+    const double n12 = R.n1[r] * R.n2[c];
+    const double n21 = R.n2[r] * R.n1[c];
+    if (row < 3) {
+      row6[c] = (-R.ax) * tt + (-R.k11z) * n11 + (-R.k11y) * n22;
+      row6[3 + c] = (sa * R.k12z) * n12 - (sa * R.k12y) * n21;
+    } else {
+      row6[c] = (-sa * R.k12z) * n21 - (-sa * R.k12y) * n12;
+      row6[3 + c] = (-R.tor) * tt + R.k23y * n11 + R.k23z * n22;
     }
   }
 }

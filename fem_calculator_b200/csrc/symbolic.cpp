@@ -143,7 +143,7 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
       S.pair_ptr[i + 1] = S.pair_ptr[i] + (S.contrib_ptr[d + 1] - S.contrib_ptr[d]);
     }
     const int64_t np = S.pair_ptr[N];
-    S.pair_code.resize(np); S.pair_blk.resize(np); S.pair_rank.resize(np);
+    S.pair_code.resize(np); S.pair_blk.resize(np);
     for (int64_t i = 0; i < N && ok; ++i) {
       const int32_t d = S.diag_blk[i];
       int64_t p = S.pair_ptr[i];
@@ -160,10 +160,11 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
         const uint32_t* ob = S.contrib.data() + S.contrib_ptr[blk];
         const uint32_t* oe = S.contrib.data() + S.contrib_ptr[blk + 1];
         const int64_t rank = std::lower_bound(ob, oe, ocode) - ob;
-        if (rank > 255) { ok = false; break; }
+        // duplicate members between the same two nodes (several contributions to one
+        // off-diagonal block) and hubs with more than 127 members use the generic kernel
+        if (rank != 0 || (oe - ob) != 1 || p - S.pair_ptr[i] > 127) { ok = false; break; }
         S.pair_code[p] = e * 2u + a;
         S.pair_blk[p] = blk;
-        S.pair_rank[p] = (uint8_t)rank;
       }
     }
     S.pairs_ok = ok;
@@ -172,13 +173,13 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
       S.pair_tile_ptr.push_back(0);
       int64_t tb = 0, tp = 0;
       for (int64_t i = 0; i < N; ++i) {
-        const int64_t rb = S.rowptr[i + 1] - S.rowptr[i];
         const int64_t rp = S.pair_ptr[i + 1] - S.pair_ptr[i];
-        if (i > S.pair_tile_ptr.back() && (tb + rb > tile_max_blocks || tp + rp > tile_max_contrib)) {
+        // pair-kernel tiles: <= 128 pairs (one per thread) and <= 128 nodes
+        if (i > S.pair_tile_ptr.back() && (tb + 1 > 128 || tp + rp > 128)) {
           S.pair_tile_ptr.push_back((int32_t)i);
           tb = tp = 0;
         }
-        tb += rb;
+        tb += 1;
         tp += rp;
       }
       S.pair_tile_ptr.push_back((int32_t)N);
