@@ -116,7 +116,7 @@ struct femb_handle {
   int64_t n_fixed = 0;
   femb::DevBuf<uint8_t> free_mask;  // (ndof) 1 = free DOF
   femb::DevBuf<double> f, u0;       // load vector, prescribed values
-  femb::DevBuf<double> b, x, r, z, p, q;
+  femb::DevBuf<double> b, x, r, z, p, q, s;
   femb::DevBuf<double> Dinv;        // block-Jacobi inverse (n_nodes,bs,bs) or Jacobi (ndof)
   femb::DevBuf<double> partials;    // reduction scratch
   femb::DevBuf<double> scal;        // device scalars for PCG

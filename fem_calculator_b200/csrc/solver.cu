@@ -13,6 +13,8 @@
 // Reductions are two-stage and ordered (per-CTA partial -> last CTA sums the partials in
 // index order), so dot products — and therefore the whole PCG trajectory — are
 // bit-reproducible run to run; float atomics are never used.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace femb {
@@ -20,7 +22,7 @@ namespace femb {
 constexpr int kVecThreads = 256;
 
 struct Scal {  // device scalar block (doubles)
-  enum { PQ = 0, RZ0 = 1, RZ1 = 2, RR = 3, BB = 4, TOL2 = 5, COUNT = 8 };
+  enum { PQ = 0, RZ0 = 1, RZ1 = 2, RR = 3, BB = 4, TOL2 = 5, ALPHA = 6, COUNT = 8 };
 };
 struct Flag {  // device int block
   enum { DONE = 0, ITERS = 1, TICKET0 = 2, TICKET1 = 3, TICKET2 = 4, COUNT = 8 };
@@ -94,6 +96,9 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     const int b0 = __ldg(rowptr + node), b1 = __ldg(rowptr + node + 1);
     double acc = 0.0;
     if (BS == 6) {
+      // three 16-byte loads per 48-byte row.  (A sector-exact split — 32 B + 16 B per row, so
+      // that no 32-byte sector is requested by two instructions — measured 10 % SLOWER on
+      // B200: 76 vs 69 us at 1M DOF, gpurun_out/r1_spmv_ab.log.)
 #pragma unroll 4
       for (int b = b0; b < b1; ++b) {
         const int col = __ldg(colidx + b);
@@ -219,12 +224,19 @@ __device__ __forceinline__ double apply_dinv_row(const double* __restrict__ Dinv
 }
 
 // -------------------------------------------------------------------------------- PCG
-// init: x = 0, r = b, z = Dinv r, p = z; rz -> RZ0, bb -> BB, tol2 = rtol^2 * bb
+// Chronopoulos-Gear form of preconditioned CG: two kernels per iteration,
+//   (1) s = A z with delta = (z, s)                      [bsr_spmv_kernel<.., DOT>]
+//   (2) beta = gamma/gamma_prev, alpha = gamma / (delta - beta*gamma/alpha_prev),
+//       p = z + beta p, q = s + beta q (= A p), x += alpha p, r -= alpha q, z = Dinv r,
+//       gamma_new = (r, z), rr = (r, r), convergence / breakdown decision  [pcg_update_kernel]
+// Every vector is read and written once per iteration by one fused kernel; all dot products go
+// through the ordered two-stage reduction (bit-reproducible).
+// init: x = 0, r = b, z = Dinv r, p = q = 0; gamma -> RZ1 (the slot iteration 0 reads), bb
 template <int BS, int THREADS, bool BLOCKJ>
 __global__ void __launch_bounds__(THREADS)
 pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, double* __restrict__ x,
-                double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, int64_t n,
-                double rtol, double* partials, int pstride, double* scal, int* flags) {
+                double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ q,
+                int64_t n, double rtol, double* partials, int pstride, double* scal, int* flags) {
   __shared__ double s_red[THREADS / 32];
   double rz = 0.0, bb = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
@@ -239,7 +251,7 @@ pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, d
     } else {
       zg = Dinv[g] * bg;
     }
-    x[g] = 0.0; r[g] = bg; z[g] = zg; p[g] = zg;
+    x[g] = 0.0; r[g] = bg; z[g] = zg; p[g] = 0.0; q[g] = 0.0;
     rz += bg * zg; bb += bg * bg;
   }
   double mine[2], tot[2];
@@ -250,50 +262,64 @@ pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, d
       scal[Scal::RZ0] = tot[0]; scal[Scal::RZ1] = tot[0];
       scal[Scal::BB] = tot[1]; scal[Scal::RR] = tot[1];
       scal[Scal::TOL2] = rtol * rtol * tot[1];
+      scal[Scal::ALPHA] = 1.0;
       flags[Flag::ITERS] = 0;
       flags[Flag::DONE] = (tot[1] == 0.0) ? 1 : 0;  // zero load: u = 0 is the answer
     }
   }
 }
 
-// x += alpha p; r -= alpha q; z = Dinv r; rz_new, rr ; convergence / breakdown decision
+// iteration `it` (parity = it & 1): gamma_it lives in RZ0 + (parity ^ 1), gamma_{it+1} goes to RZ0 + parity
 template <int BS, int THREADS, bool BLOCKJ>
 __global__ void __launch_bounds__(THREADS)
-pcg_update_xr_kernel(const double* __restrict__ Dinv, const double* __restrict__ p, const double* __restrict__ q,
-                     double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, int64_t n,
-                     int parity, int max_iter, double* partials, int pstride, double* scal, int* flags) {
+pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s, double* __restrict__ p,
+                  double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                  int64_t n, int parity, int first, int max_iter, double* partials, int pstride, double* scal,
+                  int* flags) {
   __shared__ double s_red[THREADS / 32];
   if (flags[Flag::DONE]) return;
-  const double pq = scal[Scal::PQ];
-  const double rz_old = scal[Scal::RZ0 + (parity ^ 1)];
-  const bool bad = !(pq > 0.0);            // K_ff not positive definite along p
-  const double alpha = bad ? 0.0 : rz_old / pq;
+  const double delta = scal[Scal::PQ];
+  const double gamma = scal[Scal::RZ0 + (parity ^ 1)];
+  const double beta = first ? 0.0 : gamma / scal[Scal::RZ0 + parity];
+  const double den = first ? delta : delta - beta * gamma / scal[Scal::ALPHA];
+  const bool bad = !(den > 0.0);           // K_ff not positive definite along p
+  const double alpha = bad ? 0.0 : gamma / den;
   double rz = 0.0, rr = 0.0;
   if (BLOCKJ) {
     for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
-      const int64_t node = g / BS;
+      const int64_t nb = (g / BS) * BS;
       double rn[BS];
 #pragma unroll
-      for (int c = 0; c < BS; ++c) rn[c] = r[node * BS + c] - alpha * q[node * BS + c];
-      const int rloc = (int)(g - node * BS);
-      const double rg = rn[rloc];
+      for (int c = 0; c < BS; ++c) rn[c] = r[nb + c] - alpha * (s[nb + c] + beta * q[nb + c]);
+      const int rloc = (int)(g - nb);
+      double rg = rn[0];
+#pragma unroll
+      for (int c = 1; c < BS; ++c) rg = (rloc == c) ? rn[c] : rg;
       const double zg = apply_dinv_row<BS>(Dinv, g, rn);
-      x[g] += alpha * p[g];
+      const double pg = z[g] + beta * p[g];
+      p[g] = pg;
+      x[g] += alpha * pg;
       z[g] = zg;
       rz += rg * zg; rr += rg * rg;
     }
-    // r[g] is also read by the other rows of its node, so it is committed in a second pass.
-    // All rows of a node live in the same CTA and grid-stride step (THREADS % BS == 0), hence
-    // the barrier is enough; the re-read of r and q hits L1.
+    // q[g] and r[g] are also read by the other rows of their node, so they are committed in a
+    // second pass.  All rows of a node live in the same CTA and grid-stride step
+    // (THREADS % BS == 0), hence the barrier is enough; the re-reads hit L1.
     __syncthreads();
-    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS)
-      r[g] -= alpha * q[g];
+    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+      const double qg = s[g] + beta * q[g];
+      q[g] = qg;
+      r[g] -= alpha * qg;
+    }
   } else {
     // scalar Jacobi: purely element-wise, one pass
     for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
-      const double rg = r[g] - alpha * q[g];
+      const double pg = z[g] + beta * p[g];
+      const double qg = s[g] + beta * q[g];
+      const double rg = r[g] - alpha * qg;
       const double zg = __ldg(Dinv + g) * rg;
-      x[g] += alpha * p[g];
+      p[g] = pg; q[g] = qg;
+      x[g] += alpha * pg;
       r[g] = rg;
       z[g] = zg;
       rz += rg * zg; rr += rg * rg;
@@ -306,6 +332,7 @@ pcg_update_xr_kernel(const double* __restrict__ Dinv, const double* __restrict__
     if (threadIdx.x == 0) {
       scal[Scal::RZ0 + parity] = tot[0];
       scal[Scal::RR] = tot[1];
+      scal[Scal::ALPHA] = alpha;
       const int it = flags[Flag::ITERS] + 1;
       flags[Flag::ITERS] = it;
       if (bad) flags[Flag::DONE] = 2;
@@ -313,17 +340,6 @@ pcg_update_xr_kernel(const double* __restrict__ Dinv, const double* __restrict__
       else if (it >= max_iter) flags[Flag::DONE] = 3;
     }
   }
-}
-
-// p = z + beta p
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-pcg_update_p_kernel(const double* __restrict__ z, double* __restrict__ p, int64_t n, int parity,
-                    const double* scal, const int* flags) {
-  if (flags[Flag::DONE]) return;
-  const double beta = scal[Scal::RZ0 + parity] / scal[Scal::RZ0 + (parity ^ 1)];
-  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS)
-    p[g] = z[g] + beta * p[g];
 }
 
 // out = K u - f (minus_f) or K u
@@ -367,6 +383,7 @@ int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double*
     else SPMV(3, false, false);
   }
 #undef SPMV
+#undef SPMV
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   return FEMB_OK;
@@ -380,6 +397,7 @@ int setup_bc_vectors(femb_handle* h) {
   FEMB_CUDA(h, h->z.alloc(n));
   FEMB_CUDA(h, h->p.alloc(n));
   FEMB_CUDA(h, h->q.alloc(n));
+  FEMB_CUDA(h, h->s.alloc(n));
   FEMB_CUDA(h, h->partials.alloc((size_t)h->num_sms * 8 * 4));
   FEMB_CUDA(h, h->scal.alloc(Scal::COUNT));
   FEMB_CUDA(h, h->flags.alloc(Flag::COUNT));
@@ -454,7 +472,7 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   if (rc) return rc;
   FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
   const bool blockj = (o.precond == FEMB_PRECOND_BLOCK_JACOBI);
-#define INIT(BS, BJ) pcg_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(d_b, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, n, o.rtol, h->partials.p, pstride, h->scal.p, h->flags.p)
+#define INIT(BS, BJ) pcg_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(d_b, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, n, o.rtol, h->partials.p, pstride, h->scal.p, h->flags.p)
   if (h->bs == 6) { if (blockj) INIT(6, true); else INIT(6, false); }
   else { if (blockj) INIT(3, true); else INIT(3, false); }
 #undef INIT
@@ -471,25 +489,24 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   while (!done && it < o.max_iter) {
     const int batch = (o.max_iter - it) < check ? (o.max_iter - it) : check;
     for (int k = 0; k < batch; ++k, ++it) {
-      const int parity = (it + 1) & 1;
+      const int parity = it & 1;
       if (prof && (it % o.profile) == 0) {
         cudaEvent_t a, b;
         cudaEventCreate(&a); cudaEventCreate(&b);
         cudaEventRecord(a, h->stream);
-        rc = launch_spmv(h, h->p.p, h->q.p, true, h->partials.p);
+        rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
         cudaEventRecord(b, h->stream);
         evs.push_back(a); evs.push_back(b);
       } else {
-        rc = launch_spmv(h, h->p.p, h->q.p, true, h->partials.p);
+        rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
       }
       if (rc) return rc;
       ++spmv_launches;
-#define UPD(BS, BJ) pcg_update_xr_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
+#define UPD(BS, BJ) pcg_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, it == 0 ? 1 : 0, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
       if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
       else { if (blockj) UPD(3, true); else UPD(3, false); }
 #undef UPD
-      pcg_update_p_kernel<kVecThreads><<<vec_grid(h, n, kVecThreads), kVecThreads, 0, h->stream>>>(h->z.p, h->p.p, n, parity, h->scal.p, h->flags.p);
-      h->launches += 2;
+      h->launches += 1;
     }
     FEMB_CUDA(h, cudaGetLastError());
     FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
