@@ -73,6 +73,11 @@ SIGNATURES = {
     "femb_frame_stress": (C.c_int, [_P, _P, _P]),
     "femb_frame_batch_solve": (C.c_int, [_P, C.c_int64, C.c_int64, _F64, _F64, C.c_double, C.c_double,
                                          _U8, _F64, _P, C.POINTER(Stats)]),
+    "femb_dist_unique_id": (C.c_int, [_P]),
+    "femb_dist_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "femb_dist_finalize": (None, [_P]),
+    "femb_dist_set_halo": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
+    "femb_dist_solve_static": (C.c_int, [_P, C.POINTER(SolveOpts), C.c_int, _P, _P, C.POINTER(Stats)]),
     "femb_time_kernel": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "femb_timer": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "femb_io_bytes": (None, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),

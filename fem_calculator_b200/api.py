@@ -140,6 +140,59 @@ class FrameModel(Handle):
         return u, self.last_stats
 
 
+class DistFrameModel(FrameModel):
+    """One rank of a row-block partitioned frame (one process per GPU; csrc/dist.cu).
+
+    Every rank passes the same GLOBAL arrays (what the reference holds in memory) plus its rank;
+    the local mesh and halo lists come from ``partition.partition_mesh``.  ``unique_id`` is the
+    128-byte NCCL id made by rank 0 (``DistFrameModel.unique_id()``) and broadcast by the caller
+    (torch.distributed / MPI / a file); world == 1 needs none."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = L.load().femb_dist_unique_id(buf)
+        if rc != 0:
+            raise L.FembError(rc, "femb_dist_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def setup(self, points, conn, elem_sec, sec_props, E, G, fixed_dofs, f, rank, world, unique_id=None, rho=7850.0):
+        from . import partition as P
+        points = np.asarray(points, dtype=np.float64)
+        conn = np.asarray(conn, dtype=np.int64)
+        n_nodes = len(points)
+        self.part = part = P.partition_mesh(conn, n_nodes, world, rank)
+        if world > 1:
+            idbuf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+            self._check(self.lib.femb_dist_init(self._h, int(rank), int(world), idbuf))
+        self.set_mesh(points[part.local_nodes], part.conn_local, np.asarray(elem_sec, dtype=np.int32)[part.elem_ids],
+                      sec_props, E, G, rho)
+        self.assemble()
+        fixed_l, f_l = P.localize_bc(part, 6, fixed_dofs, f, n_nodes)
+        self.set_bc(fixed_l, f_l)
+        self.n_owned_dof = 6 * part.n_owned
+        nbr = np.ascontiguousarray(part.nbr, dtype=np.int32)
+        sp = np.ascontiguousarray(part.send_ptr, dtype=np.int64)
+        sn = np.ascontiguousarray(part.send_nodes, dtype=np.int32)
+        rs = np.ascontiguousarray(part.recv_start, dtype=np.int64)
+        rcnt = np.ascontiguousarray(part.recv_count, dtype=np.int64)
+        self._check(self.lib.femb_dist_set_halo(self._h, part.n_owned, len(nbr), L.ptr(nbr), L.ptr(sp), L.ptr(sn),
+                                                L.ptr(rs), L.ptr(rcnt)))
+        return part
+
+    def solve_static_dist(self, precond=L.PRECOND_BLOCK_JACOBI, rtol=1e-12, max_iter=200000, check_every=50,
+                          minus_f=True, want_u=True, want_reactions=True):
+        """(u_owned, reactions_owned, stats) — owned DOFs only, global order within the slab."""
+        o = L.SolveOpts(L.SOLVER_PCG, precond, max_iter, check_every, rtol, 0, 0)
+        st = L.Stats()
+        u = np.zeros(self.n_owned_dof) if want_u else None
+        r = np.zeros(self.n_owned_dof) if want_reactions else None
+        rc = self.lib.femb_dist_solve_static(self._h, C.byref(o), int(minus_f), L.ptr(u), L.ptr(r), C.byref(st))
+        self.last_stats = st.as_dict()
+        self._check(rc)
+        return u, r, self.last_stats
+
+
 class Tet10Model(Handle):
     """Tet10 solid: element generation -> assembly -> BC -> solve -> reactions."""
 

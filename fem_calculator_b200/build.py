@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfemb200.so")
-SOURCES = ["capi.cu", "assemble.cu", "solver.cu", "direct.cu", "post.cu", "modal.cu", "symbolic.cpp"]
+SOURCES = ["capi.cu", "assemble.cu", "solver.cu", "direct.cu", "post.cu", "modal.cu", "dist.cu", "symbolic.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-O3,-pthread", "--use_fast_math=false"]
 
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libfemb200.so")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-Xcompiler", "-pthread", "-cudart", "shared"]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-Xcompiler", "-pthread", "-cudart", "shared", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout)

@@ -68,6 +68,7 @@ int femb_create(int device, femb_handle** out) {
 void femb_destroy(femb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  femb_dist_finalize(h);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -95,6 +96,7 @@ static int set_mesh_common(femb_handle* h, Kind kind, int bs, int nper, int64_t 
   h->kind = kind; h->bs = bs;
   h->n_nodes = n_nodes; h->n_elem = n_elem; h->ndof = n_nodes * bs;
   h->have_symbolic = h->assembled = h->have_bc = h->have_solution = false;
+  h->n_owned_nodes = 0;
   FEMB_CUDA(h, upload(h->xyz, xyz, (size_t)n_nodes * 3, h->stream));
   FEMB_CUDA(h, upload(h->conn, h->h_conn, h->stream));
   FEMB_CUDA(h, h->counters.alloc(4));

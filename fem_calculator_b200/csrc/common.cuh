@@ -129,6 +129,15 @@ struct femb_handle {
   femb::DevBuf<double> chainG, chainW;   // (n_nodes,36) each, chain positions
   femb::DevBuf<double> denseL;           // (ndof,ndof) Cholesky factor of the masked operator
 
+  // row-block distributed solve (dist.cu): this rank owns the first n_owned_nodes local nodes
+  void* nccl_comm = nullptr;
+  int dist_rank = 0, dist_world = 1;
+  int64_t n_owned_nodes = 0;
+  std::vector<int32_t> dist_nbr;                       // neighbour ranks
+  std::vector<int64_t> dist_send_ptr, dist_recv_start, dist_recv_count;   // per neighbour, in nodes
+  femb::DevBuf<int32_t> dist_send_nodes;               // local ids of the owned nodes each neighbour needs
+  femb::DevBuf<double> dist_send_buf, dist_red;
+
   void* pinned = nullptr;           // small pinned staging area
   size_t pinned_bytes = 0;
 };
@@ -177,6 +186,8 @@ int launch_assemble(femb_handle* h);
 int launch_expand_csr(femb_handle* h, int which, int32_t* d_indptr, int32_t* d_indices, double* d_vals);
 int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st);
 int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials);
+int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
+                     double* scal_out);
 int launch_reactions(femb_handle* h, bool minus_f, double* d_out);
 int setup_bc_vectors(femb_handle* h);
 int launch_frame_stress(femb_handle* h, const double* d_u, double* d_sigma);

@@ -1,0 +1,400 @@
+// Row-block (node-slab) distributed PCG for one large frame / Tet10 mesh across GPUs
+// (BASELINE configs 3/5): one process per GPU, each owning a contiguous range of
+// the mesh's nodes.  A rank's LOCAL mesh = its owned nodes (numbered first, in global order)
+// + the ghost nodes its elements touch (numbered after, sorted by global id, hence grouped by
+// owner) + every element touching an owned node ("owner computes": cut elements are duplicated,
+// so assembly needs no communication and the owned rows of K are bit-identical to the
+// single-GPU matrix).  Only the owned prefix of rows is ever computed.
+//
+// Per CG iteration (Chronopoulos-Gear form, one reduction):
+//   pack boundary entries of z -> ncclSend/ncclRecv with the neighbour ranks (ghost entries land
+//   directly in the tail of z) -> s = A z on owned rows with the local (z, s) -> ONE ncclAllReduce
+//   of {delta, gamma, ||r||^2} (3 doubles) -> fused vector update with the local partials of the
+//   next {gamma, ||r||^2}.
+// Everything is enqueued on the handle's stream; the host polls the device flag every
+// `check_every` iterations.  NCCL is loaded with dlopen at femb_dist_init, so single-GPU users
+// need no NCCL at all.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "pcg_common.cuh"
+
+namespace femb {
+
+int bc_build_mask(femb_handle* h, const int64_t* d_fixed, int64_t n_fixed);
+int setup_rhs_for_direct(femb_handle* h);
+int setup_precond_public(femb_handle* h, int mode);
+
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+
+NcclApi g_nccl;
+
+const char* load_nccl() {
+  if (g_nccl.lib) return nullptr;
+  // libnccl.so.2 resolves to the copy already loaded in the process (e.g. PyTorch's) or the system one
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return "libnccl.so.2 not found (needed only for multi-GPU row-block solves)";
+#define SYM(name)                                                           \
+  g_nccl.name = reinterpret_cast<decltype(g_nccl.name)>(dlsym(lib, "nccl" #name)); \
+  if (!g_nccl.name) return "libnccl.so.2 lacks nccl" #name
+  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Send); SYM(Recv);
+  SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString); SYM(GetVersion);
+#undef SYM
+  g_nccl.lib = lib;
+  return nullptr;
+}
+
+#define FEMB_NCCL(h, expr)                                                                   \
+  do {                                                                                       \
+    ncclResult_t _r = (expr);                                                                \
+    if (_r != ncclSuccess)                                                                   \
+      return femb::fail((h), FEMB_ERR_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
+  } while (0)
+
+// red[] slots of the distributed solver (doubles): the first three are all-reduced each iteration
+struct Red {
+  enum { DELTA = 0, GAMMA = 1, RR = 2, NRED = 3, GPREV = 4, ALPHA = 5, TOL2 = 6, BB = 7, RRFINAL = 8, COUNT = 12 };
+};
+
+__global__ void pack_nodes_kernel(const double* __restrict__ v, const int32_t* __restrict__ nodes, int64_t n_send,
+                                  int bs, double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_send * bs) return;
+  const int64_t i = t / bs;
+  const int c = (int)(t - i * bs);
+  out[t] = v[(size_t)nodes[i] * bs + c];
+}
+
+// owned rows: x = 0, r = b, z = Dinv r, p = q = 0; local gamma -> red[GAMMA], local ||b||^2 -> red[RR]
+template <int BS, int THREADS, bool BLOCKJ>
+__global__ void __launch_bounds__(THREADS)
+dist_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, double* __restrict__ x,
+                 double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ q,
+                 int64_t n, double* partials, int pstride, double* red, int* flags) {
+  __shared__ double s_red[THREADS / 32];
+  double rz = 0.0, bb = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const double bg = b[g];
+    double zg;
+    if (BLOCKJ) {
+      const int64_t node = g / BS;
+      double rn[BS];
+#pragma unroll
+      for (int c = 0; c < BS; ++c) rn[c] = b[node * BS + c];
+      zg = apply_dinv_row<BS>(Dinv, g, rn);
+    } else {
+      zg = Dinv[g] * bg;
+    }
+    x[g] = 0.0; r[g] = bg; z[g] = zg; p[g] = 0.0; q[g] = 0.0;
+    rz += bg * zg; bb += bg * bg;
+  }
+  double mine[2], tot[2];
+  mine[0] = block_sum<THREADS>(rz, s_red);
+  mine[1] = block_sum<THREADS>(bb, s_red);
+  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
+    if (threadIdx.x == 0) {
+      red[Red::GAMMA] = tot[0];
+      red[Red::RR] = tot[1];
+      red[Red::ALPHA] = 1.0; red[Red::GPREV] = 1.0;
+      flags[Flag::ITERS] = 0;
+      flags[Flag::DONE] = 0;
+    }
+  }
+}
+
+// red[DELTA..RR] hold GLOBAL sums when this kernel starts (all-reduced on the stream before it)
+template <int BS, int THREADS, bool BLOCKJ>
+__global__ void __launch_bounds__(THREADS)
+dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s, double* __restrict__ p,
+                   double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                   int64_t n, int first, double rtol, double* partials, int pstride, double* red, int* flags) {
+  __shared__ double s_red[THREADS / 32];
+  if (flags[Flag::DONE]) return;
+  const double delta = red[Red::DELTA], gamma = red[Red::GAMMA], rr = red[Red::RR];
+  const double tol2 = first ? rtol * rtol * rr : red[Red::TOL2];
+  if (first ? (rr == 0.0) : (rr <= tol2)) {       // uniform across the grid: every CTA leaves
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      red[Red::RRFINAL] = rr;
+      if (first) red[Red::BB] = rr;
+      flags[Flag::DONE] = 1;
+    }
+    return;
+  }
+  const double beta = first ? 0.0 : gamma / red[Red::GPREV];
+  const double den = first ? delta : delta - beta * gamma / red[Red::ALPHA];
+  const bool bad = !(den > 0.0);
+  const double alpha = bad ? 0.0 : gamma / den;
+  double rz = 0.0, rr_new = 0.0;
+  if (BLOCKJ) {
+    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+      const int64_t nb = (g / BS) * BS;
+      double rn[BS];
+#pragma unroll
+      for (int c = 0; c < BS; ++c) rn[c] = r[nb + c] - alpha * (s[nb + c] + beta * q[nb + c]);
+      const int rloc = (int)(g - nb);
+      double rg = rn[0];
+#pragma unroll
+      for (int c = 1; c < BS; ++c) rg = (rloc == c) ? rn[c] : rg;
+      const double zg = apply_dinv_row<BS>(Dinv, g, rn);
+      const double pg = z[g] + beta * p[g];
+      p[g] = pg;
+      x[g] += alpha * pg;
+      z[g] = zg;
+      rz += rg * zg; rr_new += rg * rg;
+    }
+    __syncthreads();  // q / r are read by the other rows of their node (same CTA, same step)
+    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+      const double qg = s[g] + beta * q[g];
+      q[g] = qg;
+      r[g] -= alpha * qg;
+    }
+  } else {
+    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+      const double pg = z[g] + beta * p[g];
+      const double qg = s[g] + beta * q[g];
+      const double rg = r[g] - alpha * qg;
+      const double zg = __ldg(Dinv + g) * rg;
+      p[g] = pg; q[g] = qg;
+      x[g] += alpha * pg;
+      r[g] = rg;
+      z[g] = zg;
+      rz += rg * zg; rr_new += rg * rg;
+    }
+  }
+  double mine[2], tot[2];
+  mine[0] = block_sum<THREADS>(rz, s_red);
+  mine[1] = block_sum<THREADS>(rr_new, s_red);
+  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
+    if (threadIdx.x == 0) {
+      red[Red::GPREV] = gamma;
+      red[Red::ALPHA] = alpha;
+      if (first) { red[Red::TOL2] = tol2; red[Red::BB] = rr; }
+      red[Red::RRFINAL] = rr;
+      red[Red::GAMMA] = tot[0];     // local partials: all-reduced before the next update
+      red[Red::RR] = tot[1];
+      flags[Flag::ITERS] = flags[Flag::ITERS] + 1;
+      if (bad) flags[Flag::DONE] = 2;
+    }
+  }
+}
+
+__global__ void sub_owned_kernel(double* out, const double* f, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] -= f[i];
+}
+
+}  // namespace
+
+int dist_halo_exchange(femb_handle* h, double* v) {
+  if (h->dist_world <= 1 || h->dist_nbr.empty()) return FEMB_OK;
+  const int bs = h->bs;
+  const int64_t n_send = h->dist_send_ptr.back();
+  if (n_send > 0) {
+    const int64_t tot = n_send * bs;
+    pack_nodes_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(v, h->dist_send_nodes.p, n_send, bs, h->dist_send_buf.p);
+    h->launches++;
+    FEMB_CUDA(h, cudaGetLastError());
+  }
+  ncclComm_t comm = reinterpret_cast<ncclComm_t>(h->nccl_comm);
+  FEMB_NCCL(h, g_nccl.GroupStart());
+  for (size_t k = 0; k < h->dist_nbr.size(); ++k) {
+    const int64_t ns = h->dist_send_ptr[k + 1] - h->dist_send_ptr[k];
+    if (ns > 0)
+      FEMB_NCCL(h, g_nccl.Send(h->dist_send_buf.p + h->dist_send_ptr[k] * bs, (size_t)(ns * bs), ncclDouble, h->dist_nbr[k], comm, h->stream));
+    if (h->dist_recv_count[k] > 0)
+      FEMB_NCCL(h, g_nccl.Recv(v + h->dist_recv_start[k] * bs, (size_t)(h->dist_recv_count[k] * bs), ncclDouble, h->dist_nbr[k], comm, h->stream));
+  }
+  FEMB_NCCL(h, g_nccl.GroupEnd());
+  return FEMB_OK;
+}
+
+int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
+  const int64_t n_all = h->ndof;
+  const int64_t n = h->n_owned_nodes * h->bs;
+  const int gridv = vec_grid(h, n, kRowThreads);
+  const int pstride = h->num_sms * 8;
+  int rc = setup_rhs_for_direct(h);           // b = masked(f - K u0) on every local row
+  if (rc) return rc;
+  rc = setup_precond_public(h, o.precond);
+  if (rc) return rc;
+  FEMB_CUDA(h, h->dist_red.alloc(Red::COUNT));
+  FEMB_CUDA(h, cudaMemsetAsync(h->dist_red.p, 0, sizeof(double) * Red::COUNT, h->stream));
+  FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
+  // ghost tails start from zero (z's is overwritten by the first halo exchange)
+  for (double* v : {h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, h->s.p})
+    FEMB_CUDA(h, cudaMemsetAsync(v, 0, sizeof(double) * n_all, h->stream));
+  const bool blockj = (o.precond == FEMB_PRECOND_BLOCK_JACOBI);
+  double* red = h->dist_red.p;
+#define INIT(BS, BJ) dist_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->b.p, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, n, h->partials.p + pstride, pstride, red, h->flags.p)
+  if (h->bs == 6) { if (blockj) INIT(6, true); else INIT(6, false); }
+  else { if (blockj) INIT(3, true); else INIT(3, false); }
+#undef INIT
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+
+  ncclComm_t comm = reinterpret_cast<ncclComm_t>(h->nccl_comm);
+  struct Peek { int32_t flags[Flag::COUNT]; double red[Red::COUNT]; };
+  Peek* peek = reinterpret_cast<Peek*>(h->pinned);
+  const int check = o.check_every > 0 ? o.check_every : 50;
+  int it = 0, done = 0, spmv_launches = 0;
+  while (!done && it <= o.max_iter) {
+    const int batch = std::min(check, o.max_iter + 1 - it);
+    for (int k = 0; k < batch; ++k, ++it) {
+      rc = dist_halo_exchange(h, h->z.p);
+      if (rc) return rc;
+      rc = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red);   // red[DELTA] = local (z, s)
+      if (rc) return rc;
+      ++spmv_launches;
+      if (h->dist_world > 1) FEMB_NCCL(h, g_nccl.AllReduce(red, red, Red::NRED, ncclDouble, ncclSum, comm, h->stream));
+#define UPD(BS, BJ) dist_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, it == 0 ? 1 : 0, o.rtol, h->partials.p + pstride, pstride, red, h->flags.p)
+      if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
+      else { if (blockj) UPD(3, true); else UPD(3, false); }
+#undef UPD
+      h->launches++;
+    }
+    FEMB_CUDA(h, cudaGetLastError());
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->red, red, sizeof(peek->red), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    done = peek->flags[Flag::DONE];
+  }
+  if (st) {
+    st->method_used = FEMB_SOLVER_PCG;
+    st->iterations = peek->flags[Flag::ITERS];
+    st->converged = (done == 1);
+    st->spmv_launches = spmv_launches;
+    const double bb = peek->red[Red::BB];
+    st->rel_residual = bb > 0.0 ? std::sqrt(peek->red[Red::RRFINAL] / bb) : 0.0;
+  }
+  if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "distributed PCG breakdown: p^T K p <= 0 (K_ff is not positive definite)");
+  if (done != 1) return fail(h, FEMB_ERR_NOT_CONVERGED, "distributed PCG did not reach rtol within max_iter");
+  return FEMB_OK;
+}
+
+}  // namespace femb
+
+using namespace femb;
+
+extern "C" {
+
+int femb_dist_unique_id(uint8_t* id128) {
+  if (!id128) return FEMB_ERR_ARG;
+  if (load_nccl()) return FEMB_ERR_CUDA;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return FEMB_ERR_CUDA;
+  std::memcpy(id128, &id, 128);
+  return FEMB_OK;
+}
+
+int femb_dist_init(femb_handle* h, int rank, int world, const uint8_t* id128) {
+  if (!h || world < 1 || rank < 0 || rank >= world || !id128) return fail(h, FEMB_ERR_ARG, "bad femb_dist_init arguments");
+  if (const char* e = load_nccl()) return fail(h, FEMB_ERR_CUDA, e);
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  if (h->nccl_comm) { g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(h->nccl_comm)); h->nccl_comm = nullptr; }
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclComm_t comm = nullptr;
+  FEMB_NCCL(h, g_nccl.CommInitRank(&comm, world, id, rank));
+  h->nccl_comm = comm;
+  h->dist_rank = rank;
+  h->dist_world = world;
+  return FEMB_OK;
+}
+
+void femb_dist_finalize(femb_handle* h) {
+  if (h && h->nccl_comm && g_nccl.CommDestroy) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(h->nccl_comm));
+    h->nccl_comm = nullptr;
+  }
+}
+
+int femb_dist_set_halo(femb_handle* h, int64_t n_owned_nodes, int32_t n_nbr, const int32_t* nbr_rank,
+                       const int64_t* send_ptr, const int32_t* send_nodes, const int64_t* recv_start,
+                       const int64_t* recv_count) {
+  if (!h || h->kind == Kind::None) return fail(h, FEMB_ERR_ARG, "set the local mesh first");
+  if (n_owned_nodes < 0 || n_owned_nodes > h->n_nodes || n_nbr < 0) return fail(h, FEMB_ERR_ARG, "bad halo arguments");
+  if (n_nbr > 0 && (!nbr_rank || !send_ptr || !recv_start || !recv_count)) return fail(h, FEMB_ERR_ARG, "bad halo arguments");
+  if (n_nbr > 0 && !h->nccl_comm) return fail(h, FEMB_ERR_ARG, "call femb_dist_init before femb_dist_set_halo");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  h->n_owned_nodes = n_owned_nodes;
+  h->dist_nbr.assign(nbr_rank, nbr_rank + n_nbr);
+  h->dist_send_ptr.assign(1, 0);
+  if (n_nbr > 0) h->dist_send_ptr.assign(send_ptr, send_ptr + n_nbr + 1);
+  h->dist_recv_start.assign(recv_start, recv_start + n_nbr);
+  h->dist_recv_count.assign(recv_count, recv_count + n_nbr);
+  const int64_t n_send = h->dist_send_ptr.back();
+  for (int k = 0; k < n_nbr; ++k) {
+    if (nbr_rank[k] < 0 || nbr_rank[k] >= h->dist_world || nbr_rank[k] == h->dist_rank) return fail(h, FEMB_ERR_ARG, "bad neighbour rank");
+    if (recv_start[k] < n_owned_nodes || recv_start[k] + recv_count[k] > h->n_nodes) return fail(h, FEMB_ERR_ARG, "ghost range outside the local tail");
+  }
+  for (int64_t i = 0; i < n_send; ++i)
+    if (send_nodes[i] < 0 || send_nodes[i] >= n_owned_nodes) return fail(h, FEMB_ERR_ARG, "send node is not owned");
+  FEMB_CUDA(h, upload(h->dist_send_nodes, send_nodes, (size_t)n_send, h->stream));
+  FEMB_CUDA(h, h->dist_send_buf.alloc((size_t)std::max<int64_t>(1, n_send * h->bs)));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FEMB_OK;
+}
+
+int femb_dist_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, double* u_owned,
+                           double* reactions_owned, femb_stats* stats) {
+  if (!h) return FEMB_ERR_ARG;
+  if (!h->assembled || !h->have_bc) return fail(h, FEMB_ERR_ARG, "call femb_assemble and femb_set_bc first");
+  if (h->n_owned_nodes <= 0) return fail(h, FEMB_ERR_ARG, "call femb_dist_set_halo first");
+  if (h->dist_world > 1 && !h->nccl_comm) return fail(h, FEMB_ERR_ARG, "call femb_dist_init first");
+  if (h->dist_world > 1) { if (const char* e = load_nccl()) return fail(h, FEMB_ERR_CUDA, e); }
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  femb_solve_opts o;
+  if (opts) o = *opts;
+  else { std::memset(&o, 0, sizeof(o)); o.precond = FEMB_PRECOND_BLOCK_JACOBI; o.check_every = 50; }
+  if (o.max_iter <= 0) o.max_iter = 200000;
+  if (!(o.rtol > 0.0)) o.rtol = 1e-12;
+  femb_stats st;
+  std::memset(&st, 0, sizeof(st));
+  h->launches = 0;
+  FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  int rc = run_dist_pcg(h, o, &st);
+  const int64_t n = h->n_owned_nodes * h->bs;
+  if (rc == FEMB_OK) {
+    h->have_solution = true;
+    rc = dist_halo_exchange(h, h->x.p);                       // ghosts of u for K_full u (and stress)
+    if (rc == FEMB_OK) rc = launch_spmv_rows(h, h->x.p, h->q.p, n, false, nullptr, h->scal.p);
+    if (rc == FEMB_OK && minus_f) {
+      sub_owned_kernel<<<vec_grid(h, n, 256), 256, 0, h->stream>>>(h->q.p, h->f.p, n);
+      h->launches++;
+    }
+    if (rc == FEMB_OK && reactions_owned) FEMB_CUDA(h, download(reactions_owned, h->q.p, (size_t)n * 8, h->stream));
+    if (rc == FEMB_OK && u_owned) FEMB_CUDA(h, download(u_owned, h->x.p, (size_t)n * 8, h->stream));
+  }
+  cudaEventRecord(h->ev1, h->stream);
+  cudaError_t se = cudaStreamSynchronize(h->stream);
+  if (rc == FEMB_OK && se != cudaSuccess) rc = fail(h, FEMB_ERR_CUDA, cudaGetErrorString(se));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  st.device_ms = ms;
+  st.kernel_launches = (int32_t)h->launches;
+  if (stats) *stats = st;
+  return rc;
+}
+
+}  // extern "C"

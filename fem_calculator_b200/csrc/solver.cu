@@ -16,65 +16,9 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "pcg_common.cuh"
 
 namespace femb {
-
-constexpr int kVecThreads = 256;
-
-struct Scal {  // device scalar block (doubles)
-  enum { PQ = 0, RZ0 = 1, RZ1 = 2, RR = 3, BB = 4, TOL2 = 5, ALPHA = 6, COUNT = 8 };
-};
-struct Flag {  // device int block
-  enum { DONE = 0, ITERS = 1, TICKET0 = 2, TICKET1 = 3, TICKET2 = 4, COUNT = 8 };
-};
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// CTA-wide ordered sum; result valid in thread 0.
-template <int THREADS>
-__device__ __forceinline__ double block_sum(double v, double* s_red) {
-  v = warp_sum(v);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) s_red[w] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (w == 0) {
-    t = (l < THREADS / 32) ? s_red[l] : 0.0;
-    t = warp_sum(t);
-  }
-  __syncthreads();
-  return t;
-}
-
-// Last-CTA-done ordered reduction of NV interleaved partial arrays (partials[v*stride + cta]).
-// Returns true in ALL threads of the last CTA, whose thread 0 holds the totals in out[].
-template <int THREADS, int NV>
-__device__ __forceinline__ bool grid_reduce(const double (&mine)[NV], double* partials, int stride,
-                                            int* ticket, double* s_red, double (&out)[NV]) {
-  __shared__ int s_last;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) partials[(size_t)v * stride + blockIdx.x] = mine[v];
-    __threadfence();
-    const int t = atomicAdd(ticket, 1);
-    s_last = (t == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return false;
-  __threadfence();
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    double a = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) a += partials[(size_t)v * stride + i];
-    out[v] = block_sum<THREADS>(a, s_red);
-  }
-  if (threadIdx.x == 0) *ticket = 0;
-  return true;
-}
 
 // ------------------------------------------------------------------------------- SpMV
 // y = A x over block rows; MASKED: rows with free_mask==0 return x (identity rows).
@@ -212,17 +156,6 @@ __global__ void jacobi_setup_kernel(const double* __restrict__ vals, const int32
   dinv[g] = (!identity && mask[g] && d > 0.0) ? 1.0 / d : 1.0;
 }
 
-template <int BS>
-__device__ __forceinline__ double apply_dinv_row(const double* __restrict__ Dinv, int64_t g, const double* rn) {
-  const int64_t node = g / BS;
-  const int r = (int)(g - node * BS);
-  const double* d = Dinv + (size_t)node * BS * BS + r * BS;
-  double z = 0.0;
-#pragma unroll
-  for (int c = 0; c < BS; ++c) z += __ldg(d + c) * rn[c];
-  return z;
-}
-
 // -------------------------------------------------------------------------------- PCG
 // Chronopoulos-Gear form of preconditioned CG: two kernels per iteration,
 //   (1) s = A z with delta = (z, s)                      [bsr_spmv_kernel<.., DOT>]
@@ -353,25 +286,20 @@ __global__ void set_prescribed_kernel(double* x, const double* u0, const uint8_t
 }
 
 // ---------------------------------------------------------------------------- host side
-static int vec_grid(const femb_handle* h, int64_t n, int threads) {
-  int64_t need = (n + threads - 1) / threads;
-  int64_t cap = (int64_t)h->num_sms * 8;
-  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials) {
+  return launch_spmv_rows(h, x, y, h->ndof, masked, dot_partials, h->scal.p);
 }
 
-// grid for kernels whose CTAs must own whole nodes: chunk = THREADS rows must be a multiple
-// of BS in the grid-stride pattern.  THREADS=256 is not a multiple of 6, so those kernels
-// use kRowThreads = 192 (divisible by 6 and 3).
-constexpr int kRowThreads = 192;
-
-int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials) {
-  const int64_t n = h->ndof;
+// rows [0, n) only (the distributed solver owns a prefix of the local rows); the fused dot goes
+// to scal_out[Scal::PQ]
+int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
+                     double* scal_out) {
   const int grid = vec_grid(h, n, kRowThreads);
   const int pstride = h->num_sms * 8;
 #define SPMV(BS, M, D)                                                                         \
   bsr_spmv_kernel<BS, M, D, kRowThreads><<<grid, kRowThreads, 0, h->stream>>>(                  \
       h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, x, y, n, dot_partials, pstride,    \
-      h->scal.p, h->flags.p)
+      scal_out, h->flags.p)
   const bool dot = dot_partials != nullptr;
   if (h->bs == 6) {
     if (masked && dot) SPMV(6, true, true);
@@ -540,6 +468,7 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
 }
 
 int setup_rhs_for_direct(femb_handle* h) { return build_rhs(h, h->u0.p != nullptr); }
+int setup_precond_public(femb_handle* h, int mode) { return setup_precond(h, mode); }
 
 // x[fixed] = prescribed value (the reference always prescribes 0: BeamSolver.py:413,418)
 int apply_prescribed(femb_handle* h) {

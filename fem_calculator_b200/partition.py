@@ -1,0 +1,112 @@
+"""Row-block (node-slab) partition of one large mesh across GPUs (BASELINE configs 3/5).
+
+Pure host logic (numpy): every rank derives its own local mesh and halo lists from the GLOBAL
+arrays the reference already holds (mesh.points, connectivity — BeamSolver.py:364-372,
+ReactionSolver.py:62-66), deterministically and without communication:
+
+* rank r owns the contiguous global node range [bounds[r], bounds[r+1]) in the mesh's own node
+  order (DOF numbering is never changed: BeamSolver.py:354,360);
+* local nodes = owned nodes (global order) followed by ghost nodes (ascending global id, hence
+  grouped by owner rank);
+* local elements = every element touching an owned node, in ascending global element order, so
+  the owned rows of the locally assembled K receive exactly the contributions, in exactly the
+  order, of the single-GPU assembly ("owner computes", cut elements duplicated);
+* for each neighbour rank: which owned nodes it needs (send list) and which contiguous range of
+  ghosts it provides (recv range).
+
+The numerics (assembly, halo exchange, PCG) run in libfemb200.so — see csrc/dist.cu.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def node_bounds(n_nodes: int, world: int) -> np.ndarray:
+    """Equal-count contiguous node ranges: bounds[r] = n_nodes*r // world."""
+    return np.array([n_nodes * r // world for r in range(world + 1)], dtype=np.int64)
+
+
+@dataclass
+class Partition:
+    rank: int
+    world: int
+    bounds: np.ndarray            # (world+1) global node range boundaries
+    local_nodes: np.ndarray       # (n_local) global ids: owned first, then ghosts (ascending)
+    n_owned: int
+    elem_ids: np.ndarray          # (n_local_elem) global element ids, ascending
+    conn_local: np.ndarray        # (n_local_elem, nper) int64 in local node ids
+    nbr: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))        # neighbour ranks, ascending
+    send_ptr: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int64))   # (n_nbr+1)
+    send_nodes: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))  # local ids of owned nodes
+    recv_start: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # first local ghost id per nbr
+    recv_count: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))
+
+    @property
+    def node_lo(self) -> int:
+        return int(self.bounds[self.rank])
+
+    @property
+    def node_hi(self) -> int:
+        return int(self.bounds[self.rank + 1])
+
+    def local_dofs(self, bs: int) -> np.ndarray:
+        """Global DOF index of every local DOF (owned + ghost), local order."""
+        return (self.local_nodes[:, None] * bs + np.arange(bs)[None, :]).reshape(-1)
+
+    def global_to_local_nodes(self, n_nodes: int) -> np.ndarray:
+        g2l = np.full(n_nodes, -1, dtype=np.int64)
+        g2l[self.local_nodes] = np.arange(len(self.local_nodes))
+        return g2l
+
+
+def partition_mesh(conn: np.ndarray, n_nodes: int, world: int, rank: int, bounds: np.ndarray | None = None) -> Partition:
+    conn = np.asarray(conn, dtype=np.int64)
+    bounds = node_bounds(n_nodes, world) if bounds is None else np.asarray(bounds, dtype=np.int64)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    owner_of = lambda nodes: np.searchsorted(bounds[1:], nodes, side="right")  # noqa: E731
+    elem_owner = owner_of(conn)                                   # (E, nper)
+    mine = (elem_owner == rank).any(axis=1)
+    elem_ids = np.nonzero(mine)[0]
+    le, lo_owner = conn[mine], elem_owner[mine]
+    touched = np.unique(le) if len(le) else np.zeros(0, np.int64)
+    ghosts = touched[(touched < lo) | (touched >= hi)]
+    local_nodes = np.concatenate([np.arange(lo, hi, dtype=np.int64), ghosts])
+    g2l = np.full(n_nodes, -1, dtype=np.int64)
+    g2l[local_nodes] = np.arange(len(local_nodes))
+    conn_local = g2l[le] if len(le) else np.zeros((0, conn.shape[1]), np.int64)
+    part = Partition(rank, world, bounds, local_nodes, hi - lo, elem_ids, conn_local)
+    if world == 1 or len(ghosts) == 0:
+        return part
+    ghost_owner = owner_of(ghosts)
+    nbrs = np.unique(ghost_owner)
+    send_ptr, send_nodes, recv_start, recv_count = [0], [], [], []
+    for s in nbrs:
+        # ghosts owned by s: one contiguous run of the (sorted) ghost list
+        idx = np.nonzero(ghost_owner == s)[0]
+        recv_start.append(part.n_owned + int(idx[0]))
+        recv_count.append(len(idx))
+        # my owned nodes that share an element with a node owned by s
+        with_s = (lo_owner == s).any(axis=1)
+        sub, subo = le[with_s], lo_owner[with_s]
+        mine_nodes = np.unique(sub[subo == rank])
+        send_nodes.append(mine_nodes - lo)
+        send_ptr.append(send_ptr[-1] + len(mine_nodes))
+    part.nbr = nbrs.astype(np.int32)
+    part.send_ptr = np.asarray(send_ptr, dtype=np.int64)
+    part.send_nodes = np.concatenate(send_nodes).astype(np.int32) if send_nodes else np.zeros(0, np.int32)
+    part.recv_start = np.asarray(recv_start, dtype=np.int64)
+    part.recv_count = np.asarray(recv_count, dtype=np.int64)
+    return part
+
+
+def localize_bc(part: Partition, bs: int, fixed_dofs_global: np.ndarray, f_global: np.ndarray, n_nodes: int):
+    """Local (owned + ghost) fixed-DOF list (sorted, local numbering) and load vector."""
+    g2l = part.global_to_local_nodes(n_nodes)
+    fixed = np.asarray(fixed_dofs_global, dtype=np.int64)
+    ln = g2l[fixed // bs]
+    keep = ln >= 0
+    fixed_local = np.sort(ln[keep] * bs + fixed[keep] % bs)
+    f_local = np.asarray(f_global, dtype=np.float64)[part.local_dofs(bs)]
+    return fixed_local.astype(np.int64), np.ascontiguousarray(f_local)

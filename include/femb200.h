@@ -178,6 +178,33 @@ int femb_frame_batch_solve(femb_handle* h, int64_t n_models, int64_t n_elem, con
                            const uint8_t* fixed_mask, const double* f, double* u,
                            femb_stats* stats);
 
+/* ---- one large mesh across GPUs: row-block (node-slab) partition ----------------------------
+ * One process (and one handle) per GPU.  Each rank passes femb_*_set_mesh its LOCAL mesh: the
+ * owned nodes first (a contiguous range of the global node order), then the ghost nodes its
+ * elements touch (sorted by global id, hence grouped by owner rank), and every element that
+ * touches an owned node; femb_assemble / femb_set_bc work on that local mesh unchanged ("owner
+ * computes": no assembly communication; owned rows equal the single-GPU rows bit for bit).
+ * fem_calculator_b200/partition.py builds these inputs from the global arrays the reference
+ * holds.  The solve exchanges the halo of the CG direction with ncclSend/ncclRecv and
+ * all-reduces the three CG scalars once per iteration (NCCL, loaded with dlopen on first use).
+ * Scales the static solve of BeamSolver.py:417 / ReactionSolver.py:201 beyond one GPU.
+ *
+ * femb_dist_unique_id: rank 0 creates the 128-byte NCCL id; the host broadcasts it by any
+ *   means (torch.distributed, MPI, a file) and every rank calls femb_dist_init.
+ * femb_dist_set_halo: n_owned_nodes = size of the owned prefix; for neighbour k (rank
+ *   nbr_rank[k]) send_nodes[send_ptr[k]..send_ptr[k+1]) are the LOCAL ids of owned nodes it
+ *   needs (ascending global id), and [recv_start[k], recv_start[k]+recv_count[k]) is the range
+ *   of local ghost nodes it owns.
+ * femb_dist_solve_static: u_owned / reactions_owned are (bs*n_owned_nodes) or NULL.          */
+int femb_dist_unique_id(uint8_t* id128);
+int femb_dist_init(femb_handle* h, int rank, int world, const uint8_t* id128);
+void femb_dist_finalize(femb_handle* h);
+int femb_dist_set_halo(femb_handle* h, int64_t n_owned_nodes, int32_t n_nbr, const int32_t* nbr_rank,
+                       const int64_t* send_ptr, const int32_t* send_nodes, const int64_t* recv_start,
+                       const int64_t* recv_count);
+int femb_dist_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, double* u_owned,
+                           double* reactions_owned, femb_stats* stats);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------
  * Time `reps` back-to-back launches of one kernel with CUDA events on the handle's stream
  * (after `warm` untimed launches); *ms receives the mean per launch, *bytes the

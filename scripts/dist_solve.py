@@ -1,0 +1,68 @@
+"""Row-block distributed static solve under torchrun (one process per GPU; NCCL halo + all-reduce in
+csrc/dist.cu).  `torchrun --nproc-per-node N scripts/dist_solve.py nx ny nz [--check]`.
+--check compares the gathered u with the CPU oracle (small lattices only)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from fem_calculator_b200 import _lib as L, meshgen, compat
+from fem_calculator_b200.api import DistFrameModel
+from fem_calculator_b200.sections import calculate_section_properties as csp
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+nx, ny, nz = [int(v) for v in args[:3]] if len(args) >= 3 else (56, 56, 54)
+check = "--check" in sys.argv
+precond = L.PRECOND_BLOCK_JACOBI if "--blockj" in sys.argv else L.PRECOND_JACOBI
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+mesh, sec, bc = meshgen.lattice_frame_case(nx, ny, nz, jitter=0.05)
+es, props, _ = compat.frame_section_table(mesh, sec, csp)
+fixed, f = compat.frame_bc_vectors(mesh, bc, len(mesh.points))
+E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+uid = None
+if world > 1:
+    t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        t = torch.tensor(list(DistFrameModel.unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    uid = bytes(t.cpu().numpy().tolist())
+m = DistFrameModel(local)
+t0 = time.time()
+part = m.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world, uid)
+t_setup = time.time() - t0
+u, r, st = m.solve_static_dist(precond=precond)            # warm-up (NCCL connections, allocator)
+if world > 1:
+    dist.barrier(); torch.cuda.synchronize()
+u, r, st = m.solve_static_dist(precond=precond)
+ms = torch.tensor([st["device_ms"]], device="cuda", dtype=torch.float64)
+if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+n_free = len(f) - len(fixed)
+if rank == 0:
+    print(json.dumps({"lattice": [nx, ny, nz], "ndof": len(f), "n_free": n_free, "world": world,
+                      "iterations": st["iterations"], "rel_residual": st["rel_residual"], "device_ms_max": float(ms.item()),
+                      "us_per_iteration": float(ms.item()) / max(1, st["iterations"]) * 1e3,
+                      "dof_per_s": n_free / (float(ms.item()) * 1e-3), "owned_nodes_rank0": int(part.n_owned),
+                      "ghost_nodes_rank0": int(len(part.local_nodes) - part.n_owned), "setup_s": t_setup,
+                      "precond": "block-jacobi" if precond == L.PRECOND_BLOCK_JACOBI else "jacobi"}), flush=True)
+if check:
+    from oracle import ref_sparse as S
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, u)
+        ug = np.concatenate(parts)
+    else:
+        ug = u
+    if rank == 0:
+        K, _ = S.frame_assemble(mesh.points, mesh.cells_dict["line"], es, props, E, nu)
+        free = np.setdiff1d(np.arange(len(f)), fixed)
+        uo, _ = S.solve_static(K, f, fixed, free, method="direct")
+        err = np.linalg.norm(ug - uo) / np.linalg.norm(uo)
+        print(f"check: ||u - u_oracle|| / ||u_oracle|| = {err:.3e}", flush=True)
+        assert err <= 1e-10
+m.close()
+if world > 1:
+    dist.destroy_process_group()
