@@ -137,6 +137,12 @@ struct femb_handle {
   std::vector<int64_t> dist_send_ptr, dist_recv_start, dist_recv_count;   // per neighbour, in nodes
   femb::DevBuf<int32_t> dist_send_nodes;               // local ids of the owned nodes each neighbour needs
   femb::DevBuf<double> dist_send_buf, dist_red;
+  femb::DevBuf<uint8_t> dist_bnd_flag;                 // (n_nodes) 1 = owned block row that reads a ghost column
+  femb::DevBuf<int32_t> dist_bnd_nodes;                // those rows, ascending
+  int64_t dist_n_bnd = 0;
+  void* nccl_comm_halo = nullptr;                      // second communicator: halo traffic on its own stream
+  cudaStream_t halo_stream = nullptr;
+  cudaEvent_t ev_vec = nullptr, ev_halo = nullptr;
 
   void* pinned = nullptr;           // small pinned staging area
   size_t pinned_bytes = 0;
@@ -187,7 +193,7 @@ int launch_expand_csr(femb_handle* h, int which, int32_t* d_indptr, int32_t* d_i
 int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st);
 int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials);
 int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
-                     double* scal_out);
+                     double* scal_out, const uint8_t* skip_node = nullptr, const int32_t* node_list = nullptr);
 int launch_reactions(femb_handle* h, bool minus_f, double* d_out);
 int setup_bc_vectors(femb_handle* h);
 int launch_frame_stress(femb_handle* h, const double* d_u, double* d_sigma);

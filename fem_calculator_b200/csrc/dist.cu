@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "pcg_common.cuh"
@@ -36,6 +37,7 @@ struct NcclApi {
   decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclCommSplit) CommSplit = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclSend) Send = nullptr;
   decltype(&ncclRecv) Recv = nullptr;
@@ -56,7 +58,7 @@ const char* load_nccl() {
 #define SYM(name)                                                           \
   g_nccl.name = reinterpret_cast<decltype(g_nccl.name)>(dlsym(lib, "nccl" #name)); \
   if (!g_nccl.name) return "libnccl.so.2 lacks nccl" #name
-  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Send); SYM(Recv);
+  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(CommSplit); SYM(AllReduce); SYM(Send); SYM(Recv);
   SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString); SYM(GetVersion);
 #undef SYM
   g_nccl.lib = lib;
@@ -72,7 +74,7 @@ const char* load_nccl() {
 
 // red[] slots of the distributed solver (doubles): the first three are all-reduced each iteration
 struct Red {
-  enum { DELTA = 0, GAMMA = 1, RR = 2, NRED = 3, GPREV = 4, ALPHA = 5, TOL2 = 6, BB = 7, RRFINAL = 8, COUNT = 12 };
+  enum { DELTA = 0, GAMMA = 1, RR = 2, DELTA2 = 3, NRED = 4, GPREV = 5, ALPHA = 6, TOL2 = 7, BB = 8, RRFINAL = 9, COUNT = 12 };
 };
 
 __global__ void pack_nodes_kernel(const double* __restrict__ v, const int32_t* __restrict__ nodes, int64_t n_send,
@@ -129,7 +131,8 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
                    int64_t n, int first, double rtol, double* partials, int pstride, double* red, int* flags) {
   __shared__ double s_red[THREADS / 32];
   if (flags[Flag::DONE]) return;
-  const double delta = red[Red::DELTA], gamma = red[Red::GAMMA], rr = red[Red::RR];
+  // (z, s) arrives in two parts: rows that read no ghost column, and the boundary rows
+  const double delta = red[Red::DELTA] + red[Red::DELTA2], gamma = red[Red::GAMMA], rr = red[Red::RR];
   const double tol2 = first ? rtol * rtol * rr : red[Red::TOL2];
   if (first ? (rr == 0.0) : (rr <= tol2)) {       // uniform across the grid: every CTA leaves
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -203,24 +206,24 @@ __global__ void sub_owned_kernel(double* out, const double* f, int64_t n) {
 
 }  // namespace
 
-int dist_halo_exchange(femb_handle* h, double* v) {
+int dist_halo_exchange(femb_handle* h, double* v, cudaStream_t stream, void* comm_v) {
   if (h->dist_world <= 1 || h->dist_nbr.empty()) return FEMB_OK;
   const int bs = h->bs;
   const int64_t n_send = h->dist_send_ptr.back();
   if (n_send > 0) {
     const int64_t tot = n_send * bs;
-    pack_nodes_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(v, h->dist_send_nodes.p, n_send, bs, h->dist_send_buf.p);
+    pack_nodes_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(v, h->dist_send_nodes.p, n_send, bs, h->dist_send_buf.p);
     h->launches++;
     FEMB_CUDA(h, cudaGetLastError());
   }
-  ncclComm_t comm = reinterpret_cast<ncclComm_t>(h->nccl_comm);
+  ncclComm_t comm = reinterpret_cast<ncclComm_t>(comm_v);
   FEMB_NCCL(h, g_nccl.GroupStart());
   for (size_t k = 0; k < h->dist_nbr.size(); ++k) {
     const int64_t ns = h->dist_send_ptr[k + 1] - h->dist_send_ptr[k];
     if (ns > 0)
-      FEMB_NCCL(h, g_nccl.Send(h->dist_send_buf.p + h->dist_send_ptr[k] * bs, (size_t)(ns * bs), ncclDouble, h->dist_nbr[k], comm, h->stream));
+      FEMB_NCCL(h, g_nccl.Send(h->dist_send_buf.p + h->dist_send_ptr[k] * bs, (size_t)(ns * bs), ncclDouble, h->dist_nbr[k], comm, stream));
     if (h->dist_recv_count[k] > 0)
-      FEMB_NCCL(h, g_nccl.Recv(v + h->dist_recv_start[k] * bs, (size_t)(h->dist_recv_count[k] * bs), ncclDouble, h->dist_nbr[k], comm, h->stream));
+      FEMB_NCCL(h, g_nccl.Recv(v + h->dist_recv_start[k] * bs, (size_t)(h->dist_recv_count[k] * bs), ncclDouble, h->dist_nbr[k], comm, stream));
   }
   FEMB_NCCL(h, g_nccl.GroupEnd());
   return FEMB_OK;
@@ -255,27 +258,88 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
   Peek* peek = reinterpret_cast<Peek*>(h->pinned);
   const int check = o.check_every > 0 ? o.check_every : 50;
   int it = 0, done = 0, spmv_launches = 0;
-  while (!done && it <= o.max_iter) {
-    const int batch = std::min(check, o.max_iter + 1 - it);
-    for (int k = 0; k < batch; ++k, ++it) {
-      rc = dist_halo_exchange(h, h->z.p);
-      if (rc) return rc;
-      rc = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red);   // red[DELTA] = local (z, s)
-      if (rc) return rc;
+  // Overlapping the halo with the interior rows is opt-in: at 1M DOF over 2 GPUs it measured SLOWER
+  // (87.8 vs 83.0 us/iteration — the extra launches and the NCCL kernel competing for SMs cost more
+  // than the ~12 us exchange they hide), at 8M DOF 3 % faster (profiles/r01_dist_2gpu.log).
+  const bool overlap = h->dist_world > 1 && h->dist_n_bnd > 0 && h->nccl_comm_halo && getenv("FEMB_DIST_OVERLAP");
+  // one CG iteration, enqueued on the handle's stream (and the halo stream when overlapping)
+  auto enqueue_iteration = [&](int first) -> int {
+    int rc2;
+    if (overlap) {
+      // halo of z on its own stream / communicator while the rows that read no ghost column run
+      FEMB_CUDA(h, cudaEventRecord(h->ev_vec, h->stream));
+      FEMB_CUDA(h, cudaStreamWaitEvent(h->halo_stream, h->ev_vec, 0));
+      rc2 = dist_halo_exchange(h, h->z.p, h->halo_stream, h->nccl_comm_halo);
+      if (rc2) return rc2;
+      FEMB_CUDA(h, cudaEventRecord(h->ev_halo, h->halo_stream));
+      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red + Red::DELTA, h->dist_bnd_flag.p, nullptr);
+      if (rc2) return rc2;
+      FEMB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, h->dist_n_bnd * h->bs, true, h->partials.p, red + Red::DELTA2, nullptr,
+                             h->dist_bnd_nodes.p);
+      if (rc2) return rc2;
       ++spmv_launches;
-      if (h->dist_world > 1) FEMB_NCCL(h, g_nccl.AllReduce(red, red, Red::NRED, ncclDouble, ncclSum, comm, h->stream));
-#define UPD(BS, BJ) dist_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, it == 0 ? 1 : 0, o.rtol, h->partials.p + pstride, pstride, red, h->flags.p)
-      if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
-      else { if (blockj) UPD(3, true); else UPD(3, false); }
-#undef UPD
-      h->launches++;
+    } else {
+      rc2 = dist_halo_exchange(h, h->z.p, h->stream, h->nccl_comm);
+      if (rc2) return rc2;
+      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red + Red::DELTA);   // local (z, s)
+      if (rc2) return rc2;
     }
+    ++spmv_launches;
+    if (h->dist_world > 1) FEMB_NCCL(h, g_nccl.AllReduce(red, red, Red::NRED, ncclDouble, ncclSum, comm, h->stream));
+#define UPD(BS, BJ) dist_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, first, o.rtol, h->partials.p + pstride, pstride, red, h->flags.p)
+    if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
+    else { if (blockj) UPD(3, true); else UPD(3, false); }
+#undef UPD
+    h->launches++;
+    return FEMB_OK;
+  };
+  auto poll = [&]() -> int {
     FEMB_CUDA(h, cudaGetLastError());
     FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
     FEMB_CUDA(h, cudaMemcpyAsync(peek->red, red, sizeof(peek->red), cudaMemcpyDeviceToHost, h->stream));
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
     done = peek->flags[Flag::DONE];
+    return FEMB_OK;
+  };
+  // iteration 0 runs eagerly (NCCL connects lazily on first use; `first` differs) ...
+  rc = enqueue_iteration(1);
+  if (rc) return rc;
+  it = 1;
+  // ... the rest as a CUDA graph of `check` iterations — NCCL calls included — launched once per
+  // poll: with 6-8 enqueues per iteration (two of them NCCL) the host, not the GPU, would
+  // otherwise set the pace of a 1M-DOF/GPU iteration.
+  const bool use_graph = h->dist_world > 1 && !getenv("FEMB_DIST_NO_GRAPH");
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  if (use_graph) {
+    FEMB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    for (int k = 0; k < check && !rc; ++k) rc = enqueue_iteration(0);
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    FEMB_CUDA(h, ce);
+    FEMB_CUDA(h, cudaGraphInstantiate(&gexec, graph, 0));
+    spmv_launches = overlap ? 2 : 1;
   }
+  while (!done && it <= o.max_iter) {
+    if (use_graph) {
+      FEMB_CUDA(h, cudaGraphLaunch(gexec, h->stream));
+      it += check;
+      spmv_launches += (overlap ? 2 : 1) * check;
+      h->launches += (overlap ? 4 : 3) * check;
+    } else {
+      const int batch = std::min(check, o.max_iter + 1 - it);
+      for (int k = 0; k < batch; ++k, ++it) {
+        rc = enqueue_iteration(0);
+        if (rc) return rc;
+      }
+    }
+    rc = poll();
+    if (rc) break;
+  }
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  if (rc) return rc;
   if (st) {
     st->method_used = FEMB_SOLVER_PCG;
     st->iterations = peek->flags[Flag::ITERS];
@@ -309,7 +373,7 @@ int femb_dist_init(femb_handle* h, int rank, int world, const uint8_t* id128) {
   if (!h || world < 1 || rank < 0 || rank >= world || !id128) return fail(h, FEMB_ERR_ARG, "bad femb_dist_init arguments");
   if (const char* e = load_nccl()) return fail(h, FEMB_ERR_CUDA, e);
   FEMB_CUDA(h, cudaSetDevice(h->device));
-  if (h->nccl_comm) { g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(h->nccl_comm)); h->nccl_comm = nullptr; }
+  femb_dist_finalize(h);
   ncclUniqueId id;
   std::memcpy(&id, id128, 128);
   ncclComm_t comm = nullptr;
@@ -317,6 +381,14 @@ int femb_dist_init(femb_handle* h, int rank, int world, const uint8_t* id128) {
   h->nccl_comm = comm;
   h->dist_rank = rank;
   h->dist_world = world;
+  if (world > 1) {
+    ncclComm_t comm2 = nullptr;
+    FEMB_NCCL(h, g_nccl.CommSplit(comm, 0, rank, &comm2, nullptr));
+    h->nccl_comm_halo = comm2;
+    if (!h->halo_stream) FEMB_CUDA(h, cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+    if (!h->ev_vec) FEMB_CUDA(h, cudaEventCreateWithFlags(&h->ev_vec, cudaEventDisableTiming));
+    if (!h->ev_halo) FEMB_CUDA(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  }
   return FEMB_OK;
 }
 
@@ -324,9 +396,13 @@ void femb_dist_finalize(femb_handle* h) {
   if (h && h->nccl_comm && g_nccl.CommDestroy) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->halo_stream) cudaStreamSynchronize(h->halo_stream);
+    if (h->nccl_comm_halo) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(h->nccl_comm_halo));
     g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(h->nccl_comm));
-    h->nccl_comm = nullptr;
+    h->nccl_comm = h->nccl_comm_halo = nullptr;
   }
+  if (h && h->halo_stream) { cudaStreamDestroy(h->halo_stream); h->halo_stream = nullptr; }
+  if (h && h->ev_vec) { cudaEventDestroy(h->ev_vec); cudaEventDestroy(h->ev_halo); h->ev_vec = h->ev_halo = nullptr; }
 }
 
 int femb_dist_set_halo(femb_handle* h, int64_t n_owned_nodes, int32_t n_nbr, const int32_t* nbr_rank,
@@ -350,6 +426,21 @@ int femb_dist_set_halo(femb_handle* h, int64_t n_owned_nodes, int32_t n_nbr, con
   }
   for (int64_t i = 0; i < n_send; ++i)
     if (send_nodes[i] < 0 || send_nodes[i] >= n_owned_nodes) return fail(h, FEMB_ERR_ARG, "send node is not owned");
+  // owned block rows that read a ghost column wait for the halo; all the others overlap with it
+  h->dist_n_bnd = 0;
+  if (n_nbr > 0) {
+    if (!h->have_symbolic) return fail(h, FEMB_ERR_ARG, "call femb_assemble before femb_dist_set_halo");
+    const Symbolic& S = h->sym;
+    std::vector<uint8_t> flag((size_t)h->n_nodes, 0);
+    std::vector<int32_t> list;
+    for (int64_t i = 0; i < n_owned_nodes; ++i)
+      for (int32_t b = S.rowptr[i]; b < S.rowptr[i + 1]; ++b)
+        if (S.colidx[b] >= n_owned_nodes) { flag[i] = 1; list.push_back((int32_t)i); break; }
+    h->dist_n_bnd = (int64_t)list.size();
+    FEMB_CUDA(h, upload(h->dist_bnd_flag, flag, h->stream));
+    FEMB_CUDA(h, upload(h->dist_bnd_nodes, list, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   FEMB_CUDA(h, upload(h->dist_send_nodes, send_nodes, (size_t)n_send, h->stream));
   FEMB_CUDA(h, h->dist_send_buf.alloc((size_t)std::max<int64_t>(1, n_send * h->bs)));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -377,7 +468,7 @@ int femb_dist_solve_static(femb_handle* h, const femb_solve_opts* opts, int minu
   const int64_t n = h->n_owned_nodes * h->bs;
   if (rc == FEMB_OK) {
     h->have_solution = true;
-    rc = dist_halo_exchange(h, h->x.p);                       // ghosts of u for K_full u (and stress)
+    rc = dist_halo_exchange(h, h->x.p, h->stream, h->nccl_comm);   // ghosts of u for K_full u (and stress)
     if (rc == FEMB_OK) rc = launch_spmv_rows(h, h->x.p, h->q.p, n, false, nullptr, h->scal.p);
     if (rc == FEMB_OK && minus_f) {
       sub_owned_kernel<<<vec_grid(h, n, 256), 256, 0, h->stream>>>(h->q.p, h->f.p, n);

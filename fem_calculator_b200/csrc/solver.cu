@@ -29,14 +29,20 @@ __global__ void __launch_bounds__(THREADS)
 bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                 const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
                 const double* __restrict__ x, double* __restrict__ y, int64_t nrows,
-                double* partials, int pstride, double* scal, int* flags) {
+                double* partials, int pstride, double* scal, int* flags,
+                const uint8_t* __restrict__ skip_node, const int32_t* __restrict__ node_list) {
+  // skip_node != nullptr: block rows flagged there are left to a later launch (rows that read
+  // ghost columns wait for the halo); node_list != nullptr: row g belongs to node_list[g / BS].
   static_assert(BS == 6 || BS == 3, "block size");
   __shared__ double s_red[THREADS / 32];
   if (DOT && flags[Flag::DONE]) return;
   double dot = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < nrows; g += (int64_t)gridDim.x * THREADS) {
-    const int node = (int)(g / BS);
+    int node = (int)(g / BS);
     const int r = (int)(g - (int64_t)node * BS);
+    if (node_list) node = __ldg(node_list + node);
+    if (skip_node && skip_node[node]) continue;
+    const int64_t go = (int64_t)node * BS + r;   // == g unless list-driven
     const int b0 = __ldg(rowptr + node), b1 = __ldg(rowptr + node + 1);
     double acc = 0.0;
     if (BS == 6) {
@@ -62,9 +68,9 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
         acc += __ldcs(a) * __ldg(xc); acc += __ldcs(a + 1) * __ldg(xc + 1); acc += __ldcs(a + 2) * __ldg(xc + 2);
       }
     }
-    const double xg = x[g];
-    if (MASKED && !free_mask[g]) acc = xg;
-    y[g] = acc;
+    const double xg = x[go];
+    if (MASKED && !free_mask[go]) acc = xg;
+    y[go] = acc;
     if (DOT) dot += xg * acc;
   }
   if (DOT) {
@@ -287,19 +293,19 @@ __global__ void set_prescribed_kernel(double* x, const double* u0, const uint8_t
 
 // ---------------------------------------------------------------------------- host side
 int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials) {
-  return launch_spmv_rows(h, x, y, h->ndof, masked, dot_partials, h->scal.p);
+  return launch_spmv_rows(h, x, y, h->ndof, masked, dot_partials, h->scal.p, nullptr, nullptr);
 }
 
 // rows [0, n) only (the distributed solver owns a prefix of the local rows); the fused dot goes
 // to scal_out[Scal::PQ]
 int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
-                     double* scal_out) {
+                     double* scal_out, const uint8_t* skip_node, const int32_t* node_list) {
   const int grid = vec_grid(h, n, kRowThreads);
   const int pstride = h->num_sms * 8;
 #define SPMV(BS, M, D)                                                                         \
   bsr_spmv_kernel<BS, M, D, kRowThreads><<<grid, kRowThreads, 0, h->stream>>>(                  \
       h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, x, y, n, dot_partials, pstride,    \
-      scal_out, h->flags.p)
+      scal_out, h->flags.p, skip_node, node_list)
   const bool dot = dot_partials != nullptr;
   if (h->bs == 6) {
     if (masked && dot) SPMV(6, true, true);
