@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfemb200.so")
+LIB_PATH = os.environ.get("FEMB_LIB") or os.path.join(HERE, "libfemb200.so")   # FEMB_LIB: A/B another build
 
 FEMB_OK, FEMB_ERR_ARG, FEMB_ERR_CUDA, FEMB_ERR_NOT_CONVERGED, FEMB_ERR_SINGULAR, FEMB_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MAT_K, MAT_M = 0, 1
@@ -33,7 +33,8 @@ class EigOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("method_used", C.c_int32), ("iterations", C.c_int32), ("converged", C.c_int32),
                 ("spmv_launches", C.c_int32), ("kernel_launches", C.c_int32), ("spmv_timed", C.c_int32),
-                ("rel_residual", C.c_double), ("device_ms", C.c_double), ("spmv_ms", C.c_double)]
+                ("rel_residual", C.c_double), ("device_ms", C.c_double), ("spmv_ms", C.c_double),
+                ("update_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -118,6 +118,8 @@ struct femb_handle {
   femb::DevBuf<double> f, u0;       // load vector, prescribed values
   femb::DevBuf<double> b, x, r, z, p, q, s;
   femb::DevBuf<double> Dinv;        // block-Jacobi inverse (n_nodes,bs,bs) or Jacobi (ndof)
+  femb::DevBuf<double> mx, mr, mp, mq, mpartials, mscal;   // multi-RHS PCG (interleaved by right-hand side)
+  femb::DevBuf<int32_t> mflags;
   femb::DevBuf<double> partials;    // reduction scratch
   femb::DevBuf<double> scal;        // device scalars for PCG
   femb::DevBuf<int32_t> flags;      // [0] done, [1] iterations, [2] ticket counters...
@@ -204,6 +206,8 @@ int chain_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_
 int dense_factor(femb_handle* h);
 int dense_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_t ld);
 int pcg_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
+int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
+                    int64_t ldx, femb_stats* st);
 int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda, double* phi, int32_t* n_found,
               femb_stats* st);
 int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const double* xyz,

@@ -110,8 +110,8 @@ dist_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, 
     rz += bg * zg; bb += bg * bg;
   }
   double mine[2], tot[2];
-  mine[0] = block_sum<THREADS>(rz, s_red);
-  mine[1] = block_sum<THREADS>(bb, s_red);
+  mine[0] = rz;
+  mine[1] = bb;
   if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
     if (threadIdx.x == 0) {
       red[Red::GAMMA] = tot[0];
@@ -184,8 +184,8 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
     }
   }
   double mine[2], tot[2];
-  mine[0] = block_sum<THREADS>(rz, s_red);
-  mine[1] = block_sum<THREADS>(rr_new, s_red);
+  mine[0] = rz;
+  mine[1] = rr_new;
   if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
     if (threadIdx.x == 0) {
       red[Red::GPREV] = gamma;

@@ -10,6 +10,7 @@
 // double eigenvalues of symmetric sections (circular, square) in the basis.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -218,6 +219,15 @@ static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const
   femb_handle* h = ws.h;
   if (method == FEMB_SOLVER_CHAIN) return chain_apply(h, B, X, nb, ws.n);
   if (method == FEMB_SOLVER_DENSE) return dense_apply(h, B, X, nb, ws.n);
+  if (h->bs == 6 && !getenv("FEMB_MODAL_SINGLE_RHS")) {
+    // all right-hand sides of the block advance in lockstep and share one matrix pass per iteration
+    femb_stats s1;
+    std::memset(&s1, 0, sizeof(s1));
+    int rc = pcg_solve_multi(h, so, B, ws.n, nb, X, ws.n, &s1);
+    st->iterations += s1.iterations;
+    st->spmv_launches += s1.spmv_launches;
+    return rc;
+  }
   for (int q = 0; q < nb; ++q) {
     femb_stats s1;
     std::memset(&s1, 0, sizeof(s1));

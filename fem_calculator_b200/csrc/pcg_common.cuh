@@ -37,28 +37,52 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
   return t;
 }
 
-// Last-CTA-done ordered reduction of NV interleaved partial arrays (partials[v*stride + cta]).
-// Returns true in ALL threads of the last CTA, whose thread 0 holds the totals in out[].
+// Ordered grid-wide sum of NV per-thread values (partials[v*stride + cta]) in two stages:
+//   1. one CTA-wide pass: warp shuffles, one barrier, thread v adds the warp sums of value v in
+//      warp order and publishes the CTA's partial;
+//   2. the last CTA to take a ticket sums the partial arrays, warp w handling values w, w+NW, ..
+//      (lanes stride the CTAs, then a shuffle tree) — all NV values in parallel, no float atomics.
+// The association is fixed by the launch geometry, so results are bit-reproducible run to run.
+// Returns true in ALL threads of the last CTA, with the totals in out[] (every thread).
 template <int THREADS, int NV>
 __device__ __forceinline__ bool grid_reduce(const double (&mine)[NV], double* partials, int stride,
-                                            int* ticket, double* s_red, double (&out)[NV]) {
+                                            int* ticket, double* /*unused*/, double (&out)[NV]) {
+  constexpr int NW = THREADS / 32;
+  static_assert(NV <= THREADS, "one thread per value");
+  __shared__ double s_part[NV * NW];
+  __shared__ double s_tot[NV];
   __shared__ int s_last;
-  if (threadIdx.x == 0) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) partials[(size_t)v * stride + blockIdx.x] = mine[v];
+  for (int v = 0; v < NV; ++v) {
+    const double t = warp_sum(mine[v]);
+    if (l == 0) s_part[v * NW + w] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) t += s_part[threadIdx.x * NW + k];
+    partials[(size_t)threadIdx.x * stride + blockIdx.x] = t;
     __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     const int t = atomicAdd(ticket, 1);
     s_last = (t == (int)gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
+  for (int v = w; v < NV; v += NW) {
     double a = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) a += partials[(size_t)v * stride + i];
-    out[v] = block_sum<THREADS>(a, s_red);
+    for (int i = l; i < (int)gridDim.x; i += 32) a += __ldcg(partials + (size_t)v * stride + i);
+    a = warp_sum(a);
+    if (l == 0) s_tot[v] = a;
   }
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) out[v] = s_tot[v];
   if (threadIdx.x == 0) *ticket = 0;
   return true;
 }

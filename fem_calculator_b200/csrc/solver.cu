@@ -13,6 +13,8 @@
 // Reductions are two-stage and ordered (per-CTA partial -> last CTA sums the partials in
 // index order), so dot products — and therefore the whole PCG trajectory — are
 // bit-reproducible run to run; float atomics are never used.
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -75,7 +77,7 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   }
   if (DOT) {
     double mine[1], tot[1];
-    mine[0] = block_sum<THREADS>(dot, s_red);
+    mine[0] = dot;
     if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET0, s_red, tot)) {
       if (threadIdx.x == 0) scal[Scal::PQ] = tot[0];
     }
@@ -194,8 +196,8 @@ pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, d
     rz += bg * zg; bb += bg * bg;
   }
   double mine[2], tot[2];
-  mine[0] = block_sum<THREADS>(rz, s_red);
-  mine[1] = block_sum<THREADS>(bb, s_red);
+  mine[0] = rz;
+  mine[1] = bb;
   if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
     if (threadIdx.x == 0) {
       scal[Scal::RZ0] = tot[0]; scal[Scal::RZ1] = tot[0];
@@ -251,22 +253,42 @@ pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s,
       r[g] -= alpha * qg;
     }
   } else {
-    // scalar Jacobi: purely element-wise, one pass
-    for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    // scalar Jacobi: purely element-wise, one pass, two rows per thread and step (16-byte accesses)
+    const int64_t n2 = n >> 1;
+    const double2* z2 = reinterpret_cast<const double2*>(z);
+    const double2* s2 = reinterpret_cast<const double2*>(s);
+    const double2* d2 = reinterpret_cast<const double2*>(Dinv);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    double2* q2 = reinterpret_cast<double2*>(q);
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    double2* zo = reinterpret_cast<double2*>(z);
+#pragma unroll 2
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n2; i += (int64_t)gridDim.x * THREADS) {
+      const double2 zv = z2[i], sv = s2[i], dv = __ldg(d2 + i);
+      double2 pv = p2[i], qv = q2[i], xv = x2[i], rv = r2[i];
+      pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
+      qv.x = sv.x + beta * qv.x; qv.y = sv.y + beta * qv.y;
+      xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+      rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
+      const double2 zn = make_double2(dv.x * rv.x, dv.y * rv.y);
+      p2[i] = pv; q2[i] = qv; x2[i] = xv; r2[i] = rv; zo[i] = zn;
+      rz += rv.x * zn.x; rz += rv.y * zn.y;
+      rr += rv.x * rv.x; rr += rv.y * rv.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // odd tail (3-DOF meshes with an odd node count)
+      const int64_t g = n - 1;
       const double pg = z[g] + beta * p[g];
       const double qg = s[g] + beta * q[g];
       const double rg = r[g] - alpha * qg;
-      const double zg = __ldg(Dinv + g) * rg;
-      p[g] = pg; q[g] = qg;
-      x[g] += alpha * pg;
-      r[g] = rg;
-      z[g] = zg;
+      const double zg = Dinv[g] * rg;
+      p[g] = pg; q[g] = qg; x[g] += alpha * pg; r[g] = rg; z[g] = zg;
       rz += rg * zg; rr += rg * rg;
     }
   }
   double mine[2], tot[2];
-  mine[0] = block_sum<THREADS>(rz, s_red);
-  mine[1] = block_sum<THREADS>(rr, s_red);
+  mine[0] = rz;
+  mine[1] = rr;
   if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
     if (threadIdx.x == 0) {
       scal[Scal::RZ0 + parity] = tot[0];
@@ -424,22 +446,21 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
     const int batch = (o.max_iter - it) < check ? (o.max_iter - it) : check;
     for (int k = 0; k < batch; ++k, ++it) {
       const int parity = it & 1;
-      if (prof && (it % o.profile) == 0) {
-        cudaEvent_t a, b;
-        cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, h->stream);
-        rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
-        cudaEventRecord(b, h->stream);
-        evs.push_back(a); evs.push_back(b);
-      } else {
-        rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
+      const bool timed = prof && (it % o.profile) == 0;
+      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+      if (timed) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        cudaEventRecord(e0, h->stream);
       }
+      rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
+      if (timed) cudaEventRecord(e1, h->stream);
       if (rc) return rc;
       ++spmv_launches;
 #define UPD(BS, BJ) pcg_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, it == 0 ? 1 : 0, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
       if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
       else { if (blockj) UPD(3, true); else UPD(3, false); }
 #undef UPD
+      if (timed) { cudaEventRecord(e2, h->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); }
       h->launches += 1;
     }
     FEMB_CUDA(h, cudaGetLastError());
@@ -460,12 +481,15 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
     const double bb = peek->scal[Scal::BB];
     st->rel_residual = bb > 0.0 ? sqrt(peek->scal[Scal::RR] / bb) : 0.0;
     st->spmv_ms = 0.0;
-    for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+    st->update_ms = 0.0;
+    for (size_t i = 0; i + 2 < evs.size(); i += 3) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
       st->spmv_ms += ms;
+      cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]);
+      st->update_ms += ms;
     }
-    st->spmv_timed = (int32_t)(evs.size() / 2);  // number of SpMV launches that were timed
+    st->spmv_timed = (int32_t)(evs.size() / 3);  // number of iterations whose two kernels were timed
   }
   for (auto e : evs) cudaEventDestroy(e);
   if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");
@@ -503,6 +527,265 @@ int bc_build_mask(femb_handle* h, const int64_t* d_fixed, int64_t n_fixed) {
     clear_fixed_kernel<<<vec_grid(h, n_fixed, kVecThreads), kVecThreads, 0, h->stream>>>(h->free_mask.p, d_fixed, n_fixed);
   h->launches += 2;
   FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
+}  // namespace femb
+
+// ------------------------------------------------------------------ multi-RHS PCG (NB = 4)
+// Four right-hand sides advance in lockstep through independent CG recurrences that share ONE
+// pass over the matrix per iteration (SpMM): the 359 MB of K are read once for four vectors.
+// Work vectors are interleaved by right-hand side, v[g*4 + q], so the gather of a block column
+// is one contiguous 192-byte read and every vector kernel is a plain double4 stream.  z = Dinv r
+// is formed on the fly (scalar Jacobi), which keeps the vector traffic at ~9.3 passes per
+// iteration.  Used by the modal solver's shift-invert steps (block Krylov, block size 4).
+namespace femb {
+
+constexpr int kNB = 4;
+struct MScal {  // doubles, each [kNB]
+  enum { PQ = 0, RZ = 4, RR = 8, BB = 12, TOL2 = 16, BETA = 20, COUNT = 24 };
+};
+struct MFlag {  // ints
+  enum { DONEQ = 0, ALLDONE = 4, ITERS = 5, BAD = 6, TICKET0 = 7, TICKET1 = 8, COUNT = 12 };
+};
+
+__device__ __forceinline__ double4 ld4(const double* p) { return *reinterpret_cast<const double4*>(p); }
+__device__ __forceinline__ void st4(double* p, double4 v) { *reinterpret_cast<double4*>(p) = v; }
+__device__ __forceinline__ double4 ldg4(const double* p) {   // 256-bit read-only load (LDG.256.CONSTANT)
+  double4 v;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+
+// x = 0, r = b (interleaved from the nb column vectors; missing columns are zero), p = Dinv r
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mpcg_init_kernel(const double* __restrict__ B, int64_t ldb, int nb, const double* __restrict__ dinv,
+                 double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, int64_t n, double rtol,
+                 double* partials, int pstride, double* scal, int* flags) {
+  __shared__ double s_red[THREADS / 32];
+  double rz[kNB] = {0, 0, 0, 0}, bb[kNB] = {0, 0, 0, 0};
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const double d = dinv[g];
+    double b[kNB];
+#pragma unroll
+    for (int q = 0; q < kNB; ++q) b[q] = q < nb ? B[(size_t)q * ldb + g] : 0.0;
+    st4(x + g * kNB, make_double4(0, 0, 0, 0));
+    st4(r + g * kNB, make_double4(b[0], b[1], b[2], b[3]));
+    st4(p + g * kNB, make_double4(d * b[0], d * b[1], d * b[2], d * b[3]));
+#pragma unroll
+    for (int q = 0; q < kNB; ++q) { rz[q] += b[q] * d * b[q]; bb[q] += b[q] * b[q]; }
+  }
+  double mine[2 * kNB], tot[2 * kNB];
+#pragma unroll
+  for (int q = 0; q < kNB; ++q) { mine[q] = rz[q]; mine[kNB + q] = bb[q]; }
+  if (grid_reduce<THREADS, 2 * kNB>(mine, partials, pstride, flags + MFlag::TICKET1, s_red, tot)) {
+    if (threadIdx.x == 0) {
+      int all = 1;
+      for (int q = 0; q < kNB; ++q) {
+        scal[MScal::RZ + q] = tot[q];
+        scal[MScal::BB + q] = tot[kNB + q];
+        scal[MScal::RR + q] = tot[kNB + q];
+        scal[MScal::TOL2 + q] = rtol * rtol * tot[kNB + q];
+        scal[MScal::BETA + q] = 0.0;
+        const int dq = (tot[kNB + q] == 0.0) ? 1 : 0;
+        flags[MFlag::DONEQ + q] = dq;
+        all &= dq;
+      }
+      flags[MFlag::ALLDONE] = all;
+      flags[MFlag::ITERS] = 0;
+      flags[MFlag::BAD] = 0;
+    }
+  }
+}
+
+// q = A p for the four interleaved vectors (masked operator), pq_j = (p_j, q_j)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mpcg_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                 const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
+                 const double* __restrict__ p, double* __restrict__ qv, int64_t n,
+                 double* partials, int pstride, double* scal, int* flags) {
+  __shared__ double s_red[THREADS / 32];
+  if (flags[MFlag::ALLDONE]) return;
+  double dot[kNB] = {0, 0, 0, 0};
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const int node = (int)(g / 6);
+    const int r = (int)(g - (int64_t)node * 6);
+    const int b0 = __ldg(rowptr + node), b1 = __ldg(rowptr + node + 1);
+    double acc[kNB] = {0, 0, 0, 0};
+#pragma unroll 2
+    for (int b = b0; b < b1; ++b) {
+      const int col = __ldg(colidx + b);
+      const double2* a2 = reinterpret_cast<const double2*>(vals + (size_t)b * 36 + r * 6);
+      const double2 a01 = __ldcs(a2), a23 = __ldcs(a2 + 1), a45 = __ldcs(a2 + 2);
+      const double a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+      const double* pc = p + (size_t)col * 6 * kNB;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double4 v = ldg4(pc + c * kNB);
+        acc[0] += a[c] * v.x; acc[1] += a[c] * v.y; acc[2] += a[c] * v.z; acc[3] += a[c] * v.w;
+      }
+    }
+    const double4 pg = ld4(p + g * kNB);
+    if (!free_mask[g]) { acc[0] = pg.x; acc[1] = pg.y; acc[2] = pg.z; acc[3] = pg.w; }
+    st4(qv + g * kNB, make_double4(acc[0], acc[1], acc[2], acc[3]));
+    dot[0] += pg.x * acc[0]; dot[1] += pg.y * acc[1]; dot[2] += pg.z * acc[2]; dot[3] += pg.w * acc[3];
+  }
+  double mine[kNB], tot[kNB];
+#pragma unroll
+  for (int q = 0; q < kNB; ++q) mine[q] = dot[q];
+  if (grid_reduce<THREADS, kNB>(mine, partials, pstride, flags + MFlag::TICKET0, s_red, tot)) {
+    if (threadIdx.x == 0)
+      for (int q = 0; q < kNB; ++q) scal[MScal::PQ + q] = tot[q];
+  }
+}
+
+// x += alpha p, r -= alpha q; rz_new = (r, Dinv r), rr = (r, r); per-vector convergence, beta
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict__ p, const double* __restrict__ qv,
+                      double* __restrict__ x, double* __restrict__ r, int64_t n, int max_iter,
+                      double* partials, int pstride, double* scal, int* flags) {
+  __shared__ double s_red[THREADS / 32];
+  if (flags[MFlag::ALLDONE]) return;
+  double alpha[kNB];
+  bool bad = false;
+#pragma unroll
+  for (int q = 0; q < kNB; ++q) {
+    const double pq = scal[MScal::PQ + q];
+    const bool dq = flags[MFlag::DONEQ + q] != 0;
+    if (!dq && !(pq > 0.0)) bad = true;
+    alpha[q] = (dq || !(pq > 0.0)) ? 0.0 : scal[MScal::RZ + q] / pq;
+  }
+  double rz[kNB] = {0, 0, 0, 0}, rr[kNB] = {0, 0, 0, 0};
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const double d = __ldg(dinv + g);
+    const double4 pv = ld4(p + g * kNB), qq = ld4(qv + g * kNB);
+    double4 xv = ld4(x + g * kNB), rv = ld4(r + g * kNB);
+    xv.x += alpha[0] * pv.x; xv.y += alpha[1] * pv.y; xv.z += alpha[2] * pv.z; xv.w += alpha[3] * pv.w;
+    rv.x -= alpha[0] * qq.x; rv.y -= alpha[1] * qq.y; rv.z -= alpha[2] * qq.z; rv.w -= alpha[3] * qq.w;
+    st4(x + g * kNB, xv);
+    st4(r + g * kNB, rv);
+    rz[0] += rv.x * d * rv.x; rz[1] += rv.y * d * rv.y; rz[2] += rv.z * d * rv.z; rz[3] += rv.w * d * rv.w;
+    rr[0] += rv.x * rv.x; rr[1] += rv.y * rv.y; rr[2] += rv.z * rv.z; rr[3] += rv.w * rv.w;
+  }
+  double mine[2 * kNB], tot[2 * kNB];
+#pragma unroll
+  for (int q = 0; q < kNB; ++q) { mine[q] = rz[q]; mine[kNB + q] = rr[q]; }
+  if (grid_reduce<THREADS, 2 * kNB>(mine, partials, pstride, flags + MFlag::TICKET1, s_red, tot)) {
+    if (threadIdx.x == 0) {
+      const int it = flags[MFlag::ITERS] + 1;
+      flags[MFlag::ITERS] = it;
+      int all = 1;
+      for (int q = 0; q < kNB; ++q) {
+        if (flags[MFlag::DONEQ + q]) continue;     // frozen: its scalars keep the converged values
+        const double rz_old = scal[MScal::RZ + q];
+        scal[MScal::RZ + q] = tot[q];
+        scal[MScal::RR + q] = tot[kNB + q];
+        scal[MScal::BETA + q] = rz_old > 0.0 ? tot[q] / rz_old : 0.0;
+        if (tot[kNB + q] <= scal[MScal::TOL2 + q]) flags[MFlag::DONEQ + q] = 1;
+        else all = 0;
+      }
+      if (bad) { flags[MFlag::BAD] = 1; all = 1; }
+      if (it >= max_iter) all = 1;
+      flags[MFlag::ALLDONE] = all;
+    }
+  }
+}
+
+// p = Dinv r + beta p (vectors that are done keep their p: it is never used again)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mpcg_update_p_kernel(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ p, int64_t n,
+                     const double* scal, const int* flags) {
+  if (flags[MFlag::ALLDONE]) return;
+  double beta[kNB];
+#pragma unroll
+  for (int q = 0; q < kNB; ++q) beta[q] = scal[MScal::BETA + q];
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const double d = __ldg(dinv + g);
+    const double4 rv = ld4(r + g * kNB);
+    double4 pv = ld4(p + g * kNB);
+    pv.x = d * rv.x + beta[0] * pv.x; pv.y = d * rv.y + beta[1] * pv.y;
+    pv.z = d * rv.z + beta[2] * pv.z; pv.w = d * rv.w + beta[3] * pv.w;
+    st4(p + g * kNB, pv);
+  }
+}
+
+__global__ void mpcg_extract_kernel(const double* __restrict__ x, double* __restrict__ X, int64_t ldx, int nb, int64_t n) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const double4 v = ld4(x + g * kNB);
+  const double e[4] = {v.x, v.y, v.z, v.w};
+  for (int q = 0; q < nb; ++q) X[(size_t)q * ldx + g] = e[q];
+}
+
+// K_ff X = B for nb <= 4 (already masked) right-hand sides, scalar-Jacobi PCG in lockstep.
+// st->iterations receives the lockstep iteration count, st->spmv_launches the SpMM launches.
+int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
+                    int64_t ldx, femb_stats* st) {
+  if (h->bs != 6 || nb < 1 || nb > kNB) return fail(h, FEMB_ERR_ARG, "multi-RHS PCG: frame operator, 1..4 right-hand sides");
+  const int64_t n = h->ndof;
+  const int gridv = vec_grid(h, n, kRowThreads);
+  const int pstride = h->num_sms * 8;
+  int rc = setup_precond(h, FEMB_PRECOND_JACOBI);
+  if (rc) return rc;
+  FEMB_CUDA(h, h->mx.ensure((size_t)n * kNB));
+  FEMB_CUDA(h, h->mr.ensure((size_t)n * kNB));
+  FEMB_CUDA(h, h->mp.ensure((size_t)n * kNB));
+  FEMB_CUDA(h, h->mq.ensure((size_t)n * kNB));
+  FEMB_CUDA(h, h->mpartials.ensure((size_t)pstride * 3 * kNB));
+  FEMB_CUDA(h, h->mscal.ensure(MScal::COUNT));
+  FEMB_CUDA(h, h->mflags.ensure(MFlag::COUNT));
+  FEMB_CUDA(h, cudaMemsetAsync(h->mflags.p, 0, sizeof(int32_t) * MFlag::COUNT, h->stream));
+  double* part0 = h->mpartials.p;                 // SpMM: kNB arrays
+  double* part1 = h->mpartials.p + (size_t)pstride * kNB;   // init / update: 2*kNB arrays
+  const int max_iter = o.max_iter > 0 ? o.max_iter : 200000;
+  mpcg_init_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(d_B, ldb, nb, h->Dinv.p, h->mx.p, h->mr.p, h->mp.p, n,
+                                                                       o.rtol, part1, pstride, h->mscal.p, h->mflags.p);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  struct Peek { int32_t flags[MFlag::COUNT]; double scal[MScal::COUNT]; };
+  Peek* peek = reinterpret_cast<Peek*>(h->pinned);
+  const int check = o.check_every > 0 ? o.check_every : 50;
+  int it = 0, all = 0, spmm = 0;
+  while (!all && it < max_iter) {
+    const int batch = std::min(check, max_iter - it);
+    for (int k = 0; k < batch; ++k, ++it) {
+      mpcg_spmm_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p,
+                                                                           h->mp.p, h->mq.p, n, part0, pstride, h->mscal.p, h->mflags.p);
+      mpcg_update_xr_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n,
+                                                                                max_iter, part1, pstride, h->mscal.p, h->mflags.p);
+      mpcg_update_p_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->mr.p, h->mp.p, n, h->mscal.p, h->mflags.p);
+      h->launches += 3;
+      ++spmm;
+    }
+    FEMB_CUDA(h, cudaGetLastError());
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->mflags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->scal, h->mscal.p, sizeof(peek->scal), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    all = peek->flags[MFlag::ALLDONE];
+  }
+  mpcg_extract_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->mx.p, d_X, ldx, nb, n);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  bool conv = true;
+  double worst = 0.0;
+  for (int q = 0; q < nb; ++q) {
+    conv = conv && peek->flags[MFlag::DONEQ + q] != 0;
+    const double bb = peek->scal[MScal::BB + q];
+    if (bb > 0.0) worst = std::max(worst, std::sqrt(peek->scal[MScal::RR + q] / bb));
+  }
+  if (st) {
+    st->method_used = FEMB_SOLVER_PCG;
+    st->iterations = peek->flags[MFlag::ITERS];
+    st->spmv_launches = spmm;
+    st->converged = conv ? 1 : 0;
+    st->rel_residual = worst;
+  }
+  if (peek->flags[MFlag::BAD]) return fail(h, FEMB_ERR_SINGULAR, "multi-RHS PCG breakdown: p^T K p <= 0 (K_ff is not positive definite)");
+  if (!conv) return fail(h, FEMB_ERR_NOT_CONVERGED, "multi-RHS PCG did not reach rtol within max_iter");
   return FEMB_OK;
 }
 

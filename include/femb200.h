@@ -81,6 +81,7 @@ typedef struct {
   double rel_residual;        /* final ||r||/||b||                                         */
   double device_ms;           /* CUDA-event time of the whole call on the handle's stream  */
   double spmv_ms;             /* summed device time of the timed SpMV launches              */
+  double update_ms;           /* summed device time of the vector-update launches that followed them */
 } femb_stats;
 
 int femb_version(void);
