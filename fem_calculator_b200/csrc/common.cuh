@@ -124,6 +124,9 @@ struct femb_handle {
   femb::DevBuf<double> scal;        // device scalars for PCG
   femb::DevBuf<int32_t> flags;      // [0] done, [1] iterations, [2] ticket counters...
   bool have_solution = false;
+  // TMA-streamed SpMV (spmv_tma.cu): node tiles whose block values fit one shared-memory stage
+  femb::DevBuf<int32_t> spmv_tiles;
+  int spmv_tile_nodes = 0, spmv_stage_bytes = 0, spmv_n_tiles = 0;
 
   // persistent direct-solver factors (invalidated by femb_assemble / femb_set_bc)
   bool chain_factored = false, dense_factored = false;
@@ -196,6 +199,8 @@ int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st);
 int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials);
 int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
                      double* scal_out, const uint8_t* skip_node = nullptr, const int32_t* node_list = nullptr);
+int launch_spmv_tma(femb_handle* h, int variant, const double* x, double* y, bool masked, double* dot_partials,
+                    double* scal_out);
 int launch_reactions(femb_handle* h, bool minus_f, double* d_out);
 int setup_bc_vectors(femb_handle* h);
 int launch_frame_stress(femb_handle* h, const double* d_u, double* d_sigma);

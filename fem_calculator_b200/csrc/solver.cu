@@ -26,7 +26,7 @@ namespace femb {
 // y = A x over block rows; MASKED: rows with free_mask==0 return x (identity rows).
 // DOT: also accumulates sum(x_i * y_i) into `dot` through the ordered grid reduction and,
 // being the PCG's first kernel of an iteration, honours the done flag.
-template <int BS, bool MASKED, bool DOT, int THREADS>
+template <int BS, bool MASKED, bool DOT, int THREADS, int UNR = 2>
 __global__ void __launch_bounds__(THREADS)
 bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                 const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
@@ -48,10 +48,11 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     const int b0 = __ldg(rowptr + node), b1 = __ldg(rowptr + node + 1);
     double acc = 0.0;
     if (BS == 6) {
-      // three 16-byte loads per 48-byte row.  (A sector-exact split — 32 B + 16 B per row, so
-      // that no 32-byte sector is requested by two instructions — measured 10 % SLOWER on
-      // B200: 76 vs 69 us at 1M DOF, gpurun_out/r1_spmv_ab.log.)
-#pragma unroll 4
+      // three 16-byte loads per 48-byte row, two blocks in flight per thread.  Measured inside
+      // PCG at 1M DOF on one B200 (profiles/r01_spmv_variants.log): unroll 2 -> 73 us, unroll 4 -> 85,
+      // unroll 8 -> 78, unroll 1 -> 83; a sector-exact 32 B + 16 B split per row 10 % slower; two rows
+      // per thread with 256-bit loads 78-85 us; TMA-staged tiles (spmv_tma.cu) 99-133 us.
+#pragma unroll UNR
       for (int b = b0; b < b1; ++b) {
         const int col = __ldg(colidx + b);
         const double2* a2 = reinterpret_cast<const double2*>(vals + (size_t)b * 36 + r * 6);
@@ -322,12 +323,21 @@ int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double*
 // to scal_out[Scal::PQ]
 int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
                      double* scal_out, const uint8_t* skip_node, const int32_t* node_list) {
-  const int grid = vec_grid(h, n, kRowThreads);
+  static int tma_variant = -1;
+  if (tma_variant < 0) { const char* e = getenv("FEMB_SPMV_TMA"); tma_variant = e ? atoi(e) : 0; }
+  if (tma_variant > 0 && h->bs == 6 && n == h->ndof && !skip_node && !node_list)
+    return launch_spmv_tma(h, tma_variant, x, y, masked, dot_partials, scal_out);
   const int pstride = h->num_sms * 8;
-#define SPMV(BS, M, D)                                                                         \
-  bsr_spmv_kernel<BS, M, D, kRowThreads><<<grid, kRowThreads, 0, h->stream>>>(                  \
+  const int grid = vec_grid(h, n, kRowThreads);
+  static int unr = -1;
+  if (unr < 0) { const char* e = getenv("FEMB_SPMV_UNROLL"); unr = e ? atoi(e) : 2; }
+#define SPMV_U(BS, M, D, U)                                                                    \
+  bsr_spmv_kernel<BS, M, D, kRowThreads, U><<<grid, kRowThreads, 0, h->stream>>>(               \
       h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, x, y, n, dot_partials, pstride,    \
       scal_out, h->flags.p, skip_node, node_list)
+#define SPMV(BS, M, D)                                                                         \
+  do { if (BS == 6 && unr == 8) SPMV_U(BS, M, D, 8); else if (BS == 6 && unr == 2) SPMV_U(BS, M, D, 2); \
+       else if (BS == 6 && unr == 4) SPMV_U(BS, M, D, 4); else SPMV_U(BS, M, D, 2); } while (0)
   const bool dot = dot_partials != nullptr;
   if (h->bs == 6) {
     if (masked && dot) SPMV(6, true, true);
@@ -340,6 +350,7 @@ int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool
   }
 #undef SPMV
 #undef SPMV
+#undef SPMV_U
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   return FEMB_OK;

@@ -11,6 +11,11 @@ m = FrameModel(0)
 m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, 2e11, 2e11 / 2.6)
 m.assemble(); m.set_bc(fixed, f)
 ms, by = m.time_kernel(0, 5, 100)
+try:
+    ms9, by9 = m.time_kernel(9, 5, 100)
+    print(f"stream-read ceiling (K values, {by9/1e6:.0f} MB): {ms9*1e3:.1f} us = {by9/ms9/1e6:.0f} GB/s")
+except Exception as e:
+    print("no stream-read hook", e)
 out = [f"lib={os.environ.get('FEMB_LIB','in-tree')} spmv b2b {ms*1e3:.1f} us"]
 for pc, name in ((L.PRECOND_JACOBI, "jacobi"), (L.PRECOND_BLOCK_JACOBI, "blockj")):
     for rep in range(2):
