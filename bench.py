@@ -12,8 +12,10 @@ hot path over the synthetic BASELINE config-3 frame (56x56x54 lattice, 169,344 n
 `e2e`    : the same metric through the reference-shaped entry point
            (compat.BeamAnalysisB200.run_simulation: host numpy arrays in, u / reactions /
            stresses out, symbolic analysis + all H2D/D2H inside the timed region).
-`roofline`: the dominant kernel (BSR SpMV, ~70 % of the step), CUDA-event-timed inside the
-           timed steps (every 8th launch), against MEASURED_PEAKS.json.
+`roofline`: the dominant kernel (BSR SpMV, ~78 % of the step), CUDA-event-timed inside the
+           timed steps (every 8th launch, events from a pre-created pool), against
+           MEASURED_PEAKS.json.  `modal` (N=1): device ms of the 20-mode modal solve of the same
+           frame; `assembly`: the fused element+assembly kernel (elements/s).
 N > 1 (torchrun): independent load cases of the same frame, one per GPU (weak scaling, no
 data-path collective; north_star: "independent load cases ... dealt out one batch per GPU").
 `--impl reference`: the CPU oracle port of the reference path on the host cores.
@@ -199,7 +201,7 @@ def run_gpu(args):
         return st
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        step(profile=8)                       # same code path as the timed steps (fills the event pool)
 
     def barrier():
         if dist is not None:
@@ -224,7 +226,9 @@ def run_gpu(args):
     value = world * n_free / (ms_per_step / 1e3)
     launches = sum(s["kernel_launches"] for s in stats) + args.steps  # + one assembly launch per step
     iters = stats[-1]["iterations"]
-    spmv_ms = sum(s["spmv_ms"] for s in stats) / max(1, sum(s["spmv_timed"] for s in stats))
+    n_timed = max(1, sum(s["spmv_timed"] for s in stats))
+    spmv_ms = sum(s["spmv_ms"] for s in stats) / n_timed
+    update_ms = sum(s["update_ms"] for s in stats) / n_timed
     spmv_share = spmv_ms * sum(s["spmv_launches"] for s in stats) / total_ms if world == 1 else None
 
     # per-kernel roofline numbers (algorithmic bytes: DESIGN.md §kernels)
@@ -240,19 +244,28 @@ def run_gpu(args):
         except Exception:
             traffic = None
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
-    roofline = {"kernel": "bsr_spmv_kernel<6,masked,dot> (inside PCG)", "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "bsr_spmv_kernel<6,masked,dot,192,2> (inside PCG, every 8th launch timed)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "share_of_step": spmv_share,
                 "traffic": traffic}
     extra = {
         "pcg": {"iterations": iters, "ms_per_iteration": stats[-1]["device_ms"] / max(1, iters),
-                "rel_residual": stats[-1]["rel_residual"], "precond": "jacobi"},
-        "assembly": {"kernel": "assemble_tiles_kernel<FrameEl> (fused element+assembly)", "ms": asm_ms,
+                "rel_residual": stats[-1]["rel_residual"], "precond": "jacobi", "form": "Chronopoulos-Gear, 2 kernels/iteration",
+                "update_kernel_ms": update_ms, "update_kernel_gbs": 12 * 8 * len(f) / (update_ms * 1e-3) / 1e9 if update_ms else None},
+        "assembly": {"kernel": "frame_assemble_pairs_persistent_kernel (fused element+assembly)", "ms": asm_ms,
                      "elements_per_s": n_elem / (asm_ms * 1e-3), "achieved_gbs": asm_bytes / (asm_ms * 1e-3) / 1e9,
                      "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": asm_bytes},
         "spmv_back_to_back": {"ms": spmv_b2b_ms, "achieved_gbs": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9,
                               "frac": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9 / peak},
     }
+    if world == 1 and not args.no_modal:
+        # second headline metric: ms per 20-mode modal solve at 1M DOF (device time of femb_modal)
+        lam, _, mst = m.modal(k=20, rtol=1e-8)
+        extra["modal"] = {"metric": "ms_per_20_mode_modal", "ms": mst["device_ms"], "modes": int(len(lam)),
+                          "lockstep_pcg_iterations": mst["iterations"], "matrix_passes": mst["spmv_launches"],
+                          "rel_residual": mst["rel_residual"], "omega_min_rad_s": float(np.sqrt(lam[0])),
+                          "omega_max_rad_s": float(np.sqrt(lam[-1])),
+                          "method": "block shift-invert Krylov (block 4), 4-RHS lockstep Jacobi-PCG as K^-1"}
     m.close()
 
     # end-to-end through the reference-shaped entry point, host buffers in / out
@@ -301,6 +314,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-modal", action="store_true", help="skip the 20-mode modal measurement (N=1 only, ~45 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

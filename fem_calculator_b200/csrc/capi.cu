@@ -75,6 +75,7 @@ void femb_destroy(femb_handle* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

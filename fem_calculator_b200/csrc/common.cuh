@@ -80,6 +80,7 @@ struct femb_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // femb_timer
+  std::vector<cudaEvent_t> ev_pool;               // opts.profile timing events (persist across solves)
   std::string err;
   femb::Kind kind = femb::Kind::None;
   int bs = 0;

@@ -460,7 +460,14 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
       const bool timed = prof && (it % o.profile) == 0;
       cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
       if (timed) {
-        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        // events come from a pool that persists in the handle: after the warm-up solves no event
+        // is created inside a timed step
+        if (h->ev_pool.size() < evs.size() + 3) {
+          const size_t old = h->ev_pool.size();
+          h->ev_pool.resize(old + 768);
+          for (size_t k = old; k < h->ev_pool.size(); ++k) cudaEventCreate(&h->ev_pool[k]);
+        }
+        e0 = h->ev_pool[evs.size()]; e1 = h->ev_pool[evs.size() + 1]; e2 = h->ev_pool[evs.size() + 2];
         cudaEventRecord(e0, h->stream);
       }
       rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
@@ -502,7 +509,6 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
     }
     st->spmv_timed = (int32_t)(evs.size() / 3);  // number of iterations whose two kernels were timed
   }
-  for (auto e : evs) cudaEventDestroy(e);
   if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");
   if (done != 1) return fail(h, FEMB_ERR_NOT_CONVERGED, "PCG did not reach rtol within max_iter");
   return FEMB_OK;
