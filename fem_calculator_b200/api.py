@@ -63,7 +63,7 @@ class Handle:
         self._check(self.lib.femb_set_bc(self._h, len(fixed), L.ptr(fixed), f, L.ptr(up)))
         self.ndof = len(f)
 
-    def solve_static(self, method=L.SOLVER_AUTO, precond=L.PRECOND_BLOCK_JACOBI, rtol=1e-12, max_iter=200000,
+    def solve_static(self, method=L.SOLVER_AUTO, precond=L.PRECOND_JACOBI, rtol=1e-12, max_iter=200000,
                      check_every=50, minus_f=True, want_u=True, want_reactions=True, profile=False):
         o = L.SolveOpts(method, precond, max_iter, check_every, rtol, int(profile), 0)
         st = L.Stats()
@@ -180,7 +180,7 @@ class DistFrameModel(FrameModel):
                                                 L.ptr(rs), L.ptr(rcnt)))
         return part
 
-    def solve_static_dist(self, precond=L.PRECOND_BLOCK_JACOBI, rtol=1e-12, max_iter=200000, check_every=50,
+    def solve_static_dist(self, precond=L.PRECOND_JACOBI, rtol=1e-12, max_iter=200000, check_every=50,
                           minus_f=True, want_u=True, want_reactions=True):
         """(u_owned, reactions_owned, stats) — owned DOFs only, global order within the slab."""
         o = L.SolveOpts(L.SOLVER_PCG, precond, max_iter, check_every, rtol, 0, 0)

@@ -336,7 +336,7 @@ int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, cons
 static femb_solve_opts default_solve_opts() {
   femb_solve_opts o;
   std::memset(&o, 0, sizeof(o));
-  o.method = FEMB_SOLVER_AUTO; o.precond = FEMB_PRECOND_BLOCK_JACOBI; o.max_iter = 200000;
+  o.method = FEMB_SOLVER_AUTO; o.precond = FEMB_PRECOND_JACOBI; o.max_iter = 200000;
   o.check_every = 50; o.rtol = 1e-12;
   return o;
 }
@@ -418,16 +418,15 @@ int femb_frame_stress(femb_handle* h, const double* u, double* sigma_node) {
   FEMB_CUDA(h, cudaSetDevice(h->device));
   int rc = ensure_symbolic(h);
   if (rc) return rc;
-  DevBuf<double> du, ds;
   const double* d_u = h->x.p;
   if (u) {
-    FEMB_CUDA(h, upload(du, u, (size_t)h->ndof, h->stream));
-    d_u = du.p;
+    FEMB_CUDA(h, upload(h->stress_u, u, (size_t)h->ndof, h->stream));
+    d_u = h->stress_u.p;
   }
-  FEMB_CUDA(h, ds.alloc((size_t)h->n_nodes));
-  rc = launch_frame_stress(h, d_u, ds.p);
+  FEMB_CUDA(h, h->stress_sigma.alloc((size_t)h->n_nodes));   // persistent: no malloc/free per call
+  rc = launch_frame_stress(h, d_u, h->stress_sigma.p);
   if (rc) return rc;
-  FEMB_CUDA(h, download(sigma_node, ds.p, (size_t)h->n_nodes * 8, h->stream));
+  FEMB_CUDA(h, download(sigma_node, h->stress_sigma.p, (size_t)h->n_nodes * 8, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   return FEMB_OK;
 }

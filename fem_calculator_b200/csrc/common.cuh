@@ -125,6 +125,7 @@ struct femb_handle {
   femb::DevBuf<double> scal;        // device scalars for PCG
   femb::DevBuf<int32_t> flags;      // [0] done, [1] iterations, [2] ticket counters...
   bool have_solution = false;
+  femb::DevBuf<double> stress_u, stress_sigma;   // femb_frame_stress staging
   // TMA-streamed SpMV (spmv_tma.cu): node tiles whose block values fit one shared-memory stage
   femb::DevBuf<int32_t> spmv_tiles;
   int spmv_tile_nodes = 0, spmv_stage_bytes = 0, spmv_n_tiles = 0;

@@ -457,7 +457,7 @@ int femb_dist_solve_static(femb_handle* h, const femb_solve_opts* opts, int minu
   FEMB_CUDA(h, cudaSetDevice(h->device));
   femb_solve_opts o;
   if (opts) o = *opts;
-  else { std::memset(&o, 0, sizeof(o)); o.precond = FEMB_PRECOND_BLOCK_JACOBI; o.check_every = 50; }
+  else { std::memset(&o, 0, sizeof(o)); o.precond = FEMB_PRECOND_JACOBI; o.check_every = 50; }
   if (o.max_iter <= 0) o.max_iter = 200000;
   if (!(o.rtol > 0.0)) o.rtol = 1e-12;
   femb_stats st;

@@ -4,7 +4,9 @@
 // assembly kernel walks.  Sparse replacement for the implicit pattern of the reference's
 // dense scatter (BeamSolver.py:390-393) and of scipy's lil -> csr (ReactionSolver.py:148-151).
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -25,6 +27,14 @@ constexpr uint32_t kNoCode = 0xFFFFFFFFu;
 
 void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int32_t* conn,
                     int tile_max_blocks, int tile_max_contrib, Symbolic& S) {
+  const bool trace = getenv("FEMB_TRACE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[femb trace]   symbolic %s: %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   S = Symbolic();
   S.bs = bs;
   S.nper = nper;
@@ -52,6 +62,7 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
     }
   }
 
+  lap("1 bucket entries by row");
   // 2. sort each row's entries by (col, code) — rows are independent, so split across threads
   unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   if (N < 4096) nt = 1;
@@ -79,6 +90,7 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
     for (auto& t : th) t.join();
   }
 
+  lap("2 sort rows");
   // 3. block rows, columns, contribution lists
   S.rowptr.assign(N + 1, 0);
   for (int64_t i = 0; i < N; ++i) S.rowptr[i + 1] = S.rowptr[i] + nblk_row[i];
@@ -113,6 +125,7 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
   }
   S.contrib_ptr[S.nnzb] = (int32_t)c;
 
+  lap("3 blocks + contribution lists");
   // 4. assembly tiles: greedy runs of consecutive block rows within the kernel's capacities
   S.tile_max_blocks = tile_max_blocks;
   S.tile_max_contrib = tile_max_contrib;
@@ -131,6 +144,7 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
   }
   S.tile_ptr.push_back((int32_t)N);
 
+  lap("4 tiles");
   // 4b. frame pair view (one thread of the pair kernel per (node, incident element end)):
   //     the diagonal block's list (codes e*4 + a*3, element-ascending) enumerates the pairs;
   //     each pair also owns the off-diagonal contribution (e, a, 1-a) to block (node, other).
@@ -186,6 +200,7 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
     }
   }
 
+  lap("4b pair view");
   // 5. chain detection (frames): every node has <= 2 distinct neighbours, no cycles.
   //    chain_order lists nodes path by path from an end point; isolated nodes last-in-place.
   S.is_chain = false;
@@ -223,6 +238,7 @@ void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int
       if (!S.is_chain) S.chain_order.clear();
     }
   }
+  lap("5 chain detection");
 }
 
 }  // namespace femb

@@ -54,7 +54,7 @@ enum { FEMB_PRECOND_NONE = 0, FEMB_PRECOND_JACOBI = 1, FEMB_PRECOND_BLOCK_JACOBI
 
 typedef struct {
   int32_t method;        /* FEMB_SOLVER_*                         default AUTO            */
-  int32_t precond;       /* FEMB_PRECOND_*                        default BLOCK_JACOBI    */
+  int32_t precond;       /* FEMB_PRECOND_*                        default JACOBI          */
   int32_t max_iter;      /* PCG iteration cap                     default 200000          */
   int32_t check_every;   /* host polls convergence every N its    default 50              */
   double rtol;           /* stop at ||r||_2 <= rtol*||b||_2       default 1e-12           */
