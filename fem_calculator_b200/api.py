@@ -180,6 +180,19 @@ class DistFrameModel(FrameModel):
                                                 L.ptr(rs), L.ptr(rcnt)))
         return part
 
+    def modal_dist(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6):
+        """(lambda (k,), phi_owned (n_owned_dof, k), stats) — collective: every rank calls it."""
+        o = L.EigOpts(k, block, max_iter, 0, rtol, lambda_min)
+        st = L.Stats()
+        lam = np.zeros(k)
+        phi = np.zeros((k, self.n_owned_dof))
+        nf = C.c_int32()
+        rc = self.lib.femb_modal(self._h, C.byref(o), L.ptr(lam), L.ptr(phi), C.byref(nf), C.byref(st))
+        self.last_stats = st.as_dict()
+        self._check(rc)
+        n = nf.value
+        return lam[:n].copy(), np.ascontiguousarray(phi[:n].T), self.last_stats
+
     def solve_static_dist(self, precond=L.PRECOND_JACOBI, rtol=1e-12, max_iter=200000, check_every=50,
                           minus_f=True, want_u=True, want_reactions=True):
         """(u_owned, reactions_owned, stats) — owned DOFs only, global order within the slab."""

@@ -327,6 +327,7 @@ int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, cons
   if (rc) return rc;
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   h->n_fixed = n_fixed;
+  h->h_fixed.assign(fixed_dofs, fixed_dofs + n_fixed);
   h->have_bc = true;
   h->have_solution = false;
   h->chain_factored = h->dense_factored = false;

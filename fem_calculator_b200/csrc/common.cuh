@@ -115,6 +115,7 @@ struct femb_handle {
   // BC + vectors (device)
   bool have_bc = false;
   int64_t n_fixed = 0;
+  std::vector<int64_t> h_fixed;      // host copy of the fixed DOF list (owned-count for the distributed modal solve)
   femb::DevBuf<uint8_t> free_mask;  // (ndof) 1 = free DOF
   femb::DevBuf<double> f, u0;       // load vector, prescribed values
   femb::DevBuf<double> b, x, r, z, p, q, s;
@@ -221,5 +222,9 @@ int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const doub
                     const double* sec_props, double E, double G, const uint8_t* fixed_mask,
                     const double* f, double* u, femb_stats* st);
 int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes);
+bool dist_active(const femb_handle* h);
+int dist_allreduce(femb_handle* h, double* d_buf, int count);
+int dist_spmv_masked(femb_handle* h, double* x, double* y);
+int dist_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 
 }  // namespace femb

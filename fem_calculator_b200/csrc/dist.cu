@@ -229,13 +229,17 @@ int dist_halo_exchange(femb_handle* h, double* v, cudaStream_t stream, void* com
   return FEMB_OK;
 }
 
-int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
+int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, femb_stats* st) {
   const int64_t n_all = h->ndof;
   const int64_t n = h->n_owned_nodes * h->bs;
   const int gridv = vec_grid(h, n, kRowThreads);
   const int pstride = h->num_sms * 8;
-  int rc = setup_rhs_for_direct(h);           // b = masked(f - K u0) on every local row
-  if (rc) return rc;
+  int rc = FEMB_OK;
+  if (!d_rhs) {
+    rc = setup_rhs_for_direct(h);             // b = masked(f - K u0) on every local row
+    if (rc) return rc;
+    d_rhs = h->b.p;
+  }
   rc = setup_precond_public(h, o.precond);
   if (rc) return rc;
   FEMB_CUDA(h, h->dist_red.alloc(Red::COUNT));
@@ -246,7 +250,7 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
     FEMB_CUDA(h, cudaMemsetAsync(v, 0, sizeof(double) * n_all, h->stream));
   const bool blockj = (o.precond == FEMB_PRECOND_BLOCK_JACOBI);
   double* red = h->dist_red.p;
-#define INIT(BS, BJ) dist_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->b.p, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, n, h->partials.p + pstride, pstride, red, h->flags.p)
+#define INIT(BS, BJ) dist_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(d_rhs, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, n, h->partials.p + pstride, pstride, red, h->flags.p)
   if (h->bs == 6) { if (blockj) INIT(6, true); else INIT(6, false); }
   else { if (blockj) INIT(3, true); else INIT(3, false); }
 #undef INIT
@@ -351,6 +355,29 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
   if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "distributed PCG breakdown: p^T K p <= 0 (K_ff is not positive definite)");
   if (done != 1) return fail(h, FEMB_ERR_NOT_CONVERGED, "distributed PCG did not reach rtol within max_iter");
   return FEMB_OK;
+}
+
+// ---- helpers for the distributed modal solve (modal.cu) ----------------------------------
+bool dist_active(const femb_handle* h) { return h->dist_world > 1 && h->n_owned_nodes > 0 && h->nccl_comm; }
+
+// in-place sum over ranks of `count` doubles on the device
+int dist_allreduce(femb_handle* h, double* d_buf, int count) {
+  if (!dist_active(h)) return FEMB_OK;
+  FEMB_NCCL(h, g_nccl.AllReduce(d_buf, d_buf, (size_t)count, ncclDouble, ncclSum,
+                                reinterpret_cast<ncclComm_t>(h->nccl_comm), h->stream));
+  return FEMB_OK;
+}
+
+// y(owned rows) = K_ff x after refreshing the ghost tail of x (x is overwritten there)
+int dist_spmv_masked(femb_handle* h, double* x, double* y) {
+  int rc = dist_halo_exchange(h, x, h->stream, h->nccl_comm);
+  if (rc) return rc;
+  return launch_spmv_rows(h, x, y, h->n_owned_nodes * h->bs, true, nullptr, h->scal.p);
+}
+
+// K_ff x = b on the owned rows (solution in h->x, owned prefix)
+int dist_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
+  return run_dist_pcg(h, o, d_b, st);
 }
 
 }  // namespace femb
@@ -464,7 +491,7 @@ int femb_dist_solve_static(femb_handle* h, const femb_solve_opts* opts, int minu
   std::memset(&st, 0, sizeof(st));
   h->launches = 0;
   FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  int rc = run_dist_pcg(h, o, &st);
+  int rc = run_dist_pcg(h, o, nullptr, &st);
   const int64_t n = h->n_owned_nodes * h->bs;
   if (rc == FEMB_OK) {
     h->have_solution = true;

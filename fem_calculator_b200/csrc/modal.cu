@@ -162,6 +162,8 @@ static void jacobi_eigh(std::vector<double>& A, int n, std::vector<double>& w, s
 struct ModalWs {
   femb_handle* h;
   int64_t n;
+  const uint8_t* mask;   // free-DOF mask; in a row-block partition the ghost tail is cleared
+  int64_t n_own;         // rows this rank owns (== n on one GPU)
   int nchunk;
   DevBuf<double> partial, dots;
   std::vector<double> hdots;
@@ -178,6 +180,8 @@ static int dots(ModalWs& ws, const double* A, int64_t lda, int m, const double* 
   dot_finish_kernel<<<(m * nb + 127) / 128, 128, 0, h->stream>>>(ws.partial.p, ws.nchunk, m * nb, ws.dots.p);
   h->launches += 2;
   FEMB_CUDA(h, cudaGetLastError());
+  int rcd = dist_allreduce(h, ws.dots.p, m * nb);   // row-block partition: ghost tails are zero, ranks sum
+  if (rcd) return rcd;
   FEMB_CUDA(h, cudaMemcpyAsync(out, ws.dots.p, sizeof(double) * m * nb, cudaMemcpyDeviceToHost, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   return FEMB_OK;
@@ -207,7 +211,7 @@ static int axpy_block(ModalWs& ws, const double* A, int64_t lda, int m, const st
 static int mass_apply(ModalWs& ws, const double* x, double* y, int nv) {
   femb_handle* h = ws.h;
   dim3 grid((unsigned)((ws.n + kMT - 1) / kMT), nv);
-  mass_apply_kernel<<<grid, kMT, 0, h->stream>>>(h->Mdiag.p, h->free_mask.p, x, y, ws.n, ws.n, nv);
+  mass_apply_kernel<<<grid, kMT, 0, h->stream>>>(h->Mdiag.p, ws.mask, x, y, ws.n, ws.n, nv);
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   return FEMB_OK;
@@ -217,6 +221,20 @@ static int mass_apply(ModalWs& ws, const double* x, double* y, int nv) {
 static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const double* B, double* X, int nb,
                        femb_stats* st) {
   femb_handle* h = ws.h;
+  if (dist_active(h)) {
+    // one distributed PCG per right-hand side; only the owned rows are meaningful, tails stay zero
+    for (int q = 0; q < nb; ++q) {
+      femb_stats s1;
+      std::memset(&s1, 0, sizeof(s1));
+      int rc = dist_solve_rhs(h, so, B + (size_t)q * ws.n, &s1);
+      if (rc) return rc;
+      st->iterations += s1.iterations;
+      st->spmv_launches += s1.spmv_launches;
+      FEMB_CUDA(h, cudaMemsetAsync(X + (size_t)q * ws.n, 0, ws.n * 8, h->stream));
+      FEMB_CUDA(h, cudaMemcpyAsync(X + (size_t)q * ws.n, h->x.p, ws.n_own * 8, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return FEMB_OK;
+  }
   if (method == FEMB_SOLVER_CHAIN) return chain_apply(h, B, X, nb, ws.n);
   if (method == FEMB_SOLVER_DENSE) return dense_apply(h, B, X, nb, ws.n);
   if (h->bs == 6 && !getenv("FEMB_MODAL_SINGLE_RHS")) {
@@ -282,13 +300,36 @@ static int compress_basis(ModalWs& ws, double* X, int m, const double* dS, int q
 int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double* phi_out, int32_t* n_found,
               femb_stats* st) {
   const int64_t n = h->ndof;
-  const int64_t nfree = n - h->n_fixed;
+  const bool dist = dist_active(h);
+  const int64_t n_own = dist ? h->n_owned_nodes * h->bs : n;
+  int64_t nfree = n - h->n_fixed;
+  DevBuf<uint8_t> own_mask;
+  DevBuf<double> cnt;
+  if (dist) {
+    // global number of free DOFs = sum over ranks of the owned free DOFs
+    int64_t own_fixed = 0;
+    for (int64_t d : h->h_fixed) own_fixed += (d < n_own) ? 1 : 0;
+    double* hc = reinterpret_cast<double*>(h->pinned);
+    hc[0] = (double)(n_own - own_fixed);
+    FEMB_CUDA(h, cnt.alloc(1));
+    FEMB_CUDA(h, cudaMemcpyAsync(cnt.p, hc, 8, cudaMemcpyHostToDevice, h->stream));
+    int rcc = dist_allreduce(h, cnt.p, 1);
+    if (rcc) return rcc;
+    FEMB_CUDA(h, cudaMemcpyAsync(hc, cnt.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    nfree = (int64_t)(hc[0] + 0.5);
+    // modal vectors keep exact zeros on the ghost tail: their local dot products are the owned parts
+    FEMB_CUDA(h, own_mask.alloc((size_t)n));
+    FEMB_CUDA(h, cudaMemsetAsync(own_mask.p, 0, (size_t)n, h->stream));
+    FEMB_CUDA(h, cudaMemcpyAsync(own_mask.p, h->free_mask.p, (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
+  }
   *n_found = 0;
   if (nfree <= 0) return FEMB_OK;
   const int k = (int)std::min<int64_t>(o.k, nfree);
   const int nb = (int)std::min<int64_t>(4, std::max<int64_t>(1, std::min<int64_t>(o.block > 0 ? o.block : 4, nfree)));
   int method = FEMB_SOLVER_PCG;           // static solver behind the shift-invert operator
-  if (h->sym.is_chain) method = FEMB_SOLVER_CHAIN;
+  if (dist) method = FEMB_SOLVER_PCG;      // row-block partition: distributed PCG
+  else if (h->sym.is_chain) method = FEMB_SOLVER_CHAIN;
   else if (n <= 2048) method = FEMB_SOLVER_DENSE;
   int rc = FEMB_OK;
   if (method == FEMB_SOLVER_CHAIN) rc = chain_factor(h);
@@ -302,7 +343,7 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
   const int mmax = (int)std::min<int64_t>(nfree, std::max(3 * k + 12, 40) + nb);   // basis capacity
   const int keep = (int)std::min<int64_t>(nfree, k + 2 * nb);                      // thick-restart size
   ModalWs ws;
-  ws.h = h; ws.n = n; ws.nchunk = std::max(1, std::min(h->num_sms * 2, (int)((n + kMT - 1) / kMT)));
+  ws.h = h; ws.n = n; ws.n_own = n_own; ws.mask = dist ? own_mask.p : h->free_mask.p; ws.nchunk = std::max(1, std::min(h->num_sms * 2, (int)((n + kMT - 1) / kMT)));
   DevBuf<double> V, MV, OPV, W, MW, dC, dS, Tmp;
   FEMB_CUDA(h, V.alloc((size_t)mmax * n));
   FEMB_CUDA(h, MV.alloc((size_t)mmax * n));
@@ -318,7 +359,7 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
   int m = 0, steps = 0, restarts = 0;
   uint32_t seed = 1;
   for (int q = 0; q < nb; ++q) {
-    random_fill_kernel<<<gridn, kMT, 0, h->stream>>>(W.p + (size_t)q * n, h->free_mask.p, n, seed++);
+    random_fill_kernel<<<gridn, kMT, 0, h->stream>>>(W.p + (size_t)q * n, ws.mask, n, seed++);
     h->launches++;
   }
   int ncand = nb;              // candidate vectors currently in W
@@ -342,7 +383,7 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
       if (rc) return rc;
       if (!(nrm2 > 1e-20 * std::max(nrm0, 1e-300)) || !(nrm2 > 0.0)) {
         // collapsed (invariant subspace): try one fresh random direction
-        random_fill_kernel<<<gridn, kMT, 0, h->stream>>>(wa, h->free_mask.p, n, seed++);
+        random_fill_kernel<<<gridn, kMT, 0, h->stream>>>(wa, ws.mask, n, seed++);
         h->launches++;
         rc = orth_candidate(ws, V.p, MV.p, m, W.p, MW.p, na, wa, mwa, dC, coef, &nrm2);
         if (rc) return rc;
@@ -449,7 +490,12 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
           FEMB_CUDA(h, cudaMemsetAsync(my, 0, n * 8, h->stream));
           rc = axpy_block(ws, MV.p, n, m, s1, my, n, 1, dC);    // my = M V s
           if (rc) return rc;
-          rc = launch_spmv(h, y, ky, true, nullptr);            // ky = K_ff y (fixed rows: y = 0)
+          if (dist_active(h)) {
+            FEMB_CUDA(h, cudaMemsetAsync(ky, 0, n * 8, h->stream));
+            rc = dist_spmv_masked(h, y, ky);                    // fills y's ghost tail; y is rebuilt per pair
+          } else {
+            rc = launch_spmv(h, y, ky, true, nullptr);          // ky = K_ff y (fixed rows: y = 0)
+          }
           if (rc) return rc;
           st->spmv_launches++;
           double nk = 0.0, nr = 0.0;
@@ -472,7 +518,7 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
     }
     if (finished) break;
     for (int q = ncand; q < nb; ++q) {   // pad the candidate block with random directions
-      random_fill_kernel<<<gridn, kMT, 0, h->stream>>>(W.p + (size_t)q * n, h->free_mask.p, n, seed++);
+      random_fill_kernel<<<gridn, kMT, 0, h->stream>>>(W.p + (size_t)q * n, ws.mask, n, seed++);
       h->launches++;
     }
     ncand = nb;
@@ -498,7 +544,7 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
   for (int c = 0; c < kk; ++c) {
     if (!(lam[c] > o.lambda_min) || !std::isfinite(lam[c])) continue;
     lambda_out[nout] = lam[c];
-    if (phi_out) FEMB_CUDA(h, download(phi_out + (size_t)nout * n, Tmp.p + (size_t)c * n, n * 8, h->stream));
+    if (phi_out) FEMB_CUDA(h, download(phi_out + (size_t)nout * n_own, Tmp.p + (size_t)c * n, n_own * 8, h->stream));
     ++nout;
   }
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));

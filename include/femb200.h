@@ -157,7 +157,9 @@ int femb_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, 
 /* Lowest-k modes of K_ff phi = lambda M_ff phi: replaces inv(m_ff) @ k_ff + qr_algorithm
  * (BeamSolver.py:440-455,467-481).  lambda: (k) ascending, eigenvalues <= lambda_min
  * dropped (:448); phi: (ndof,k) column-major (phi[j*ndof + i]), M-normalised, zeros on
- * fixed DOFs (:453-455).  n_found receives the number of modes returned.               */
+ * fixed DOFs (:453-455).  n_found receives the number of modes returned.  On a handle set up
+ * with femb_dist_init / femb_dist_set_halo (row-block partition) every rank calls it, lambda is
+ * identical on all ranks and phi holds the rank's OWNED rows only: (bs*n_owned_nodes, k).      */
 int femb_modal(femb_handle* h, const femb_eig_opts* opts, double* lambda, double* phi,
                int32_t* n_found, femb_stats* stats);
 
