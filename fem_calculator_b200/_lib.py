@@ -79,6 +79,8 @@ SIGNATURES = {
     "femb_dist_finalize": (None, [_P]),
     "femb_dist_set_halo": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
     "femb_dist_solve_static": (C.c_int, [_P, C.POINTER(SolveOpts), C.c_int, _P, _P, C.POINTER(Stats)]),
+    "femb_dist_p2p_export": (C.c_int, [_P, _P]),
+    "femb_dist_p2p_import": (C.c_int, [_P, _P, _P]),
     "femb_time_kernel": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "femb_timer": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "femb_io_bytes": (None, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),

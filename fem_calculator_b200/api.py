@@ -156,7 +156,11 @@ class DistFrameModel(FrameModel):
             raise L.FembError(rc, "femb_dist_unique_id failed (libnccl.so.2 not loadable?)")
         return bytes(buf)
 
-    def setup(self, points, conn, elem_sec, sec_props, E, G, fixed_dofs, f, rank, world, unique_id=None, rho=7850.0):
+    def setup(self, points, conn, elem_sec, sec_props, E, G, fixed_dofs, f, rank, world, unique_id=None, rho=7850.0,
+              all_gather=None):
+        """``all_gather(obj) -> [obj of rank 0, ..., obj of rank world-1]`` (e.g. a wrapper of
+        torch.distributed.all_gather_object) switches the iteration's exchanges from NCCL to the
+        peer-memory kernels (CUDA IPC over NVLink); without it NCCL is used."""
         from . import partition as P
         points = np.asarray(points, dtype=np.float64)
         conn = np.asarray(conn, dtype=np.int64)
@@ -178,6 +182,18 @@ class DistFrameModel(FrameModel):
         rcnt = np.ascontiguousarray(part.recv_count, dtype=np.int64)
         self._check(self.lib.femb_dist_set_halo(self._h, part.n_owned, len(nbr), L.ptr(nbr), L.ptr(sp), L.ptr(sn),
                                                 L.ptr(rs), L.ptr(rcnt)))
+        self.p2p = False
+        if world > 1 and all_gather is not None and world <= 8:
+            buf = (C.c_uint8 * 128)()
+            self._check(self.lib.femb_dist_p2p_export(self._h, buf))
+            mine = (bytes(buf), {int(s): int(r) for s, r in zip(part.nbr, part.recv_start)})
+            everyone = all_gather(mine)
+            blob = b"".join(e[0] for e in everyone)
+            # where MY nodes start in neighbour k's ghost numbering = its recv_start for source rank `rank`
+            pgs = np.array([everyone[int(s)][1][int(rank)] for s in part.nbr], dtype=np.int64)
+            hb = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+            self._check(self.lib.femb_dist_p2p_import(self._h, hb, L.ptr(pgs)))
+            self.p2p = True
         return part
 
     def modal_dist(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6):

@@ -152,6 +152,15 @@ struct femb_handle {
   cudaStream_t halo_stream = nullptr;
   cudaEvent_t ev_vec = nullptr, ev_halo = nullptr;
 
+  // peer-memory exchange (CUDA IPC over NVLink): mapped peers, mailboxes, sequence base
+  femb::DevBuf<char> p2p_comm;
+  void* p2p_dev = nullptr;                 // host copy of the P2PDev kernel argument
+  const double* p2p_z_exported = nullptr;  // the z vector whose IPC handle the peers hold
+  long long* p2p_base_dev = nullptr;
+  int* p2p_ticket = nullptr;
+  long long p2p_seq_base = 0;
+  std::vector<void*> p2p_mapped;
+
   void* pinned = nullptr;           // small pinned staging area
   size_t pinned_bytes = 0;
 };

@@ -200,6 +200,114 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
   }
 }
 
+// ---- peer-memory (NVLink) exchange: no NCCL call inside the iteration ----------------------
+// Every rank maps its peers' z vectors and mailboxes through CUDA IPC.  Two small kernels per
+// iteration replace the ncclSend/ncclRecv group and the ncclAllReduce:
+//   p2p_halo_kernel      stores my boundary entries of z straight into each neighbour's ghost
+//                        tail (remote stores over NVLink), then the last CTA releases a
+//                        sequence flag at every neighbour and waits for theirs;
+//   p2p_allreduce_kernel one warp: lane p stores my four partial sums + sequence number into
+//                        peer p's mailbox, waits for peer p's entry in mine, and lane 0 adds the
+//                        entries in rank order (deterministic) into red[0..3].
+// Sequence numbers come from a per-solve base plus the device-side iteration counter, so the
+// kernels have fixed arguments and replay inside a CUDA graph.  Waits are bounded: a lost peer
+// sets DONE = 4 instead of hanging the GPU.
+struct MailSlot { double v[4]; long long seq; long long pad[3]; };   // 64 bytes
+constexpr int kMaxRanks = 8;
+
+struct P2PDev {
+  double* peer_z[kMaxRanks];          // per neighbour k: its z vector (mapped)
+  long long peer_ghost_start[kMaxRanks];   // per neighbour k: first local node of MY data in its numbering
+  long long* peer_halo_flag[kMaxRanks];    // per neighbour k: its halo flag array (mapped), indexed by source rank
+  MailSlot* peer_mail[kMaxRanks];     // per RANK p: its mailbox array [world][2]
+  MailSlot* my_mail;
+  long long* my_halo_flag;            // [world]
+  const long long* base;              // device copy of the per-solve sequence base
+  int nbr[kMaxRanks];
+  long long send_ptr[kMaxRanks + 1];
+  int n_nbr, world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr long long kSpinLimit = 1ll << 26;
+
+__global__ void __launch_bounds__(256)
+p2p_halo_kernel(const double* __restrict__ z, const int32_t* __restrict__ send_nodes, const P2PDev pd, int bs,
+                int* flags, int* ticket) {
+  if (flags[Flag::DONE]) return;
+  const long long seq = pd.base[0] + flags[Flag::ITERS] + 1;
+  const long long total = pd.send_ptr[pd.n_nbr] * bs;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / bs;
+    const int c = (int)(t - i * bs);
+    int k = 0;
+    while (k + 1 < pd.n_nbr && i >= pd.send_ptr[k + 1]) ++k;
+    double* dst = pd.peer_z[k] + (pd.peer_ghost_start[k] + (i - pd.send_ptr[k])) * bs + c;
+    *dst = z[(size_t)send_nodes[i] * bs + c];
+  }
+  __threadfence_system();
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(ticket, 1);
+    s_last = (t == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *ticket = 0;
+  if ((int)threadIdx.x < pd.n_nbr) {
+    const int k = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(pd.peer_halo_flag[k] + pd.rank, seq);           // my entries of z have landed at neighbour k
+    long long spins = 0;
+    while (ld_acquire_sys(pd.my_halo_flag + pd.nbr[k]) < seq) {     // neighbour k's entries have landed here
+      if (++spins > kSpinLimit) { flags[Flag::DONE] = 4; break; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32)
+p2p_allreduce_kernel(double* red, const P2PDev pd, int* flags) {
+  if (flags[Flag::DONE]) return;
+  const long long seq = pd.base[0] + flags[Flag::ITERS] + 1;
+  const int par = (int)(seq & 1);
+  const int lane = threadIdx.x;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  bool lost = false;
+  if (lane < pd.world) {
+    MailSlot* dst = pd.peer_mail[lane] + (pd.rank * 2 + par);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst->v[q] = red[q];
+    __threadfence_system();
+    st_release_sys(&dst->seq, seq);
+    const MailSlot* src = pd.my_mail + (lane * 2 + par);
+    long long spins = 0;
+    while (ld_acquire_sys(&src->seq) != seq) {
+      if (++spins > kSpinLimit) { lost = true; break; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const volatile double*>(&src->v[q]);
+  }
+  lost = __any_sync(0xffffffffu, lost);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int p = 0; p < pd.world; ++p) {        // rank order: identical association on every rank
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] += __shfl_sync(0xffffffffu, v[q], p);
+  }
+  if (lane == 0) {
+    if (lost) flags[Flag::DONE] = 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) red[q] = acc[q];
+  }
+}
+
 __global__ void sub_owned_kernel(double* out, const double* f, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] -= f[i];
 }
@@ -267,6 +375,14 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
   // than the ~12 us exchange they hide), at 8M DOF 3 % faster (profiles/r01_dist_2gpu.log).
   const bool overlap = h->dist_world > 1 && h->dist_n_bnd > 0 && h->nccl_comm_halo && getenv("FEMB_DIST_OVERLAP");
   // one CG iteration, enqueued on the handle's stream (and the halo stream when overlapping)
+  // peer-memory path (femb_dist_p2p_import done and the exported z vector still the live one)
+  const bool p2p = h->dist_world > 1 && h->p2p_dev && h->p2p_z_exported == h->z.p && !overlap && !getenv("FEMB_DIST_NO_P2P");
+  const P2PDev* pd = reinterpret_cast<const P2PDev*>(h->p2p_dev);
+  if (p2p) {
+    long long* hb = reinterpret_cast<long long*>(reinterpret_cast<char*>(h->pinned) + 2048);
+    *hb = h->p2p_seq_base;
+    FEMB_CUDA(h, cudaMemcpyAsync(h->p2p_base_dev, hb, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  }
   auto enqueue_iteration = [&](int first) -> int {
     int rc2;
     if (overlap) {
@@ -283,6 +399,13 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
                              h->dist_bnd_nodes.p);
       if (rc2) return rc2;
       ++spmv_launches;
+    } else if (p2p) {
+      const long long tot = h->dist_send_ptr.back() * h->bs;
+      const int gridh = (int)std::max<long long>(1, std::min<long long>((tot + 255) / 256, h->num_sms));
+      p2p_halo_kernel<<<gridh, 256, 0, h->stream>>>(h->z.p, h->dist_send_nodes.p, *pd, h->bs, h->flags.p, h->p2p_ticket);
+      h->launches++;
+      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red + Red::DELTA);
+      if (rc2) return rc2;
     } else {
       rc2 = dist_halo_exchange(h, h->z.p, h->stream, h->nccl_comm);
       if (rc2) return rc2;
@@ -290,7 +413,12 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
       if (rc2) return rc2;
     }
     ++spmv_launches;
-    if (h->dist_world > 1) FEMB_NCCL(h, g_nccl.AllReduce(red, red, Red::NRED, ncclDouble, ncclSum, comm, h->stream));
+    if (p2p) {
+      p2p_allreduce_kernel<<<1, 32, 0, h->stream>>>(red, *pd, h->flags.p);
+      h->launches++;
+    } else if (h->dist_world > 1) {
+      FEMB_NCCL(h, g_nccl.AllReduce(red, red, Red::NRED, ncclDouble, ncclSum, comm, h->stream));
+    }
 #define UPD(BS, BJ) dist_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, first, o.rtol, h->partials.p + pstride, pstride, red, h->flags.p)
     if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
     else { if (blockj) UPD(3, true); else UPD(3, false); }
@@ -314,6 +442,7 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
   // poll: with 6-8 enqueues per iteration (two of them NCCL) the host, not the GPU, would
   // otherwise set the pace of a 1M-DOF/GPU iteration.
   const bool use_graph = h->dist_world > 1 && !getenv("FEMB_DIST_NO_GRAPH");
+  (void)comm;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   if (use_graph) {
@@ -343,7 +472,9 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
   }
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
+  if (p2p) h->p2p_seq_base += (long long)peek->flags[Flag::ITERS] + 2;   // identical on every rank
   if (rc) return rc;
+  if (done == 4) return fail(h, FEMB_ERR_CUDA, "peer-memory exchange timed out waiting for another rank");
   if (st) {
     st->method_used = FEMB_SOLVER_PCG;
     st->iterations = peek->flags[Flag::ITERS];
@@ -428,6 +559,11 @@ void femb_dist_finalize(femb_handle* h) {
     g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(h->nccl_comm));
     h->nccl_comm = h->nccl_comm_halo = nullptr;
   }
+  if (h) {
+    for (void* p : h->p2p_mapped) cudaIpcCloseMemHandle(p);
+    h->p2p_mapped.clear();
+    if (h->p2p_dev) { delete reinterpret_cast<P2PDev*>(h->p2p_dev); h->p2p_dev = nullptr; }
+  }
   if (h && h->halo_stream) { cudaStreamDestroy(h->halo_stream); h->halo_stream = nullptr; }
   if (h && h->ev_vec) { cudaEventDestroy(h->ev_vec); cudaEventDestroy(h->ev_halo); h->ev_vec = h->ev_halo = nullptr; }
 }
@@ -471,6 +607,75 @@ int femb_dist_set_halo(femb_handle* h, int64_t n_owned_nodes, int32_t n_nbr, con
   FEMB_CUDA(h, upload(h->dist_send_nodes, send_nodes, (size_t)n_send, h->stream));
   FEMB_CUDA(h, h->dist_send_buf.alloc((size_t)std::max<int64_t>(1, n_send * h->bs)));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FEMB_OK;
+}
+
+int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128) {
+  if (!h || !handles128) return FEMB_ERR_ARG;
+  if (!h->have_bc || !h->z.p) return fail(h, FEMB_ERR_ARG, "call femb_set_bc before femb_dist_p2p_export");
+  if (h->dist_world > kMaxRanks) return fail(h, FEMB_ERR_ARG, "peer-memory path supports up to 8 ranks");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  const size_t bytes = sizeof(MailSlot) * h->dist_world * 2 + sizeof(long long) * (h->dist_world + 2) + 64;
+  FEMB_CUDA(h, h->p2p_comm.alloc(bytes));
+  FEMB_CUDA(h, cudaMemset(h->p2p_comm.p, 0, bytes));
+  cudaIpcMemHandle_t hz, hc;
+  FEMB_CUDA(h, cudaIpcGetMemHandle(&hz, h->z.p));
+  FEMB_CUDA(h, cudaIpcGetMemHandle(&hc, h->p2p_comm.p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::memcpy(handles128, &hz, 64);
+  std::memcpy(handles128 + 64, &hc, 64);
+  h->p2p_z_exported = h->z.p;
+  return FEMB_OK;
+}
+
+int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64_t* peer_ghost_start) {
+  if (!h || !all_handles) return FEMB_ERR_ARG;
+  if (!h->p2p_comm.p || h->p2p_z_exported != h->z.p) return fail(h, FEMB_ERR_ARG, "call femb_dist_p2p_export first");
+  if (h->dist_nbr.size() > 0 && !peer_ghost_start) return fail(h, FEMB_ERR_ARG, "peer_ghost_start missing");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  const int world = h->dist_world, rank = h->dist_rank;
+  P2PDev* pd = new P2PDev();
+  std::memset(pd, 0, sizeof(P2PDev));
+  char* cb = reinterpret_cast<char*>(h->p2p_comm.p);
+  auto mail_of = [&](char* base) { return reinterpret_cast<MailSlot*>(base); };
+  auto flag_of = [&](char* base) { return reinterpret_cast<long long*>(base + sizeof(MailSlot) * world * 2); };
+  pd->my_mail = mail_of(cb);
+  pd->my_halo_flag = flag_of(cb);
+  h->p2p_base_dev = flag_of(cb) + world;
+  h->p2p_ticket = reinterpret_cast<int*>(flag_of(cb) + world + 1);
+  pd->base = h->p2p_base_dev;
+  pd->world = world; pd->rank = rank;
+  std::vector<char*> peer_comm(world, nullptr);
+  std::vector<double*> peer_z(world, nullptr);
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) { peer_comm[p] = cb; peer_z[p] = h->z.p; continue; }
+    cudaIpcMemHandle_t hc;
+    std::memcpy(&hc, all_handles + (size_t)p * 128 + 64, 64);
+    void* ptr = nullptr;
+    FEMB_CUDA(h, cudaIpcOpenMemHandle(&ptr, hc, cudaIpcMemLazyEnablePeerAccess));
+    peer_comm[p] = reinterpret_cast<char*>(ptr);
+    h->p2p_mapped.push_back(ptr);
+  }
+  for (int p = 0; p < world; ++p) pd->peer_mail[p] = mail_of(peer_comm[p]);
+  pd->n_nbr = (int)h->dist_nbr.size();
+  if (pd->n_nbr > kMaxRanks) { delete pd; return fail(h, FEMB_ERR_ARG, "too many neighbour ranks"); }
+  for (int k = 0; k < pd->n_nbr; ++k) {
+    const int p = h->dist_nbr[k];
+    cudaIpcMemHandle_t hz;
+    std::memcpy(&hz, all_handles + (size_t)p * 128, 64);
+    void* ptr = nullptr;
+    FEMB_CUDA(h, cudaIpcOpenMemHandle(&ptr, hz, cudaIpcMemLazyEnablePeerAccess));
+    h->p2p_mapped.push_back(ptr);
+    pd->peer_z[k] = reinterpret_cast<double*>(ptr);
+    pd->peer_ghost_start[k] = peer_ghost_start[k];
+    pd->peer_halo_flag[k] = flag_of(peer_comm[p]);
+    pd->nbr[k] = p;
+    pd->send_ptr[k] = h->dist_send_ptr[k];
+  }
+  pd->send_ptr[pd->n_nbr] = h->dist_send_ptr.back();
+  if (h->p2p_dev) delete reinterpret_cast<P2PDev*>(h->p2p_dev);
+  h->p2p_dev = pd;
+  h->p2p_seq_base = 0;
   return FEMB_OK;
 }
 

@@ -207,6 +207,14 @@ int femb_dist_set_halo(femb_handle* h, int64_t n_owned_nodes, int32_t n_nbr, con
                        const int64_t* recv_count);
 int femb_dist_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, double* u_owned,
                            double* reactions_owned, femb_stats* stats);
+/* Optional peer-memory (NVLink) exchange for the iteration: after femb_set_bc + femb_dist_set_halo
+ * every rank exports two CUDA-IPC handles (128 bytes: its CG direction vector and its mailbox), the
+ * host gathers the world*128 bytes and every rank imports them together with, per neighbour k, the
+ * first local node index of THIS rank's nodes in neighbour k's ghost numbering.  The distributed
+ * PCG then replaces ncclSend/ncclRecv + ncclAllReduce by two small kernels that store straight into
+ * the peers' memory (see csrc/dist.cu); without the import it uses NCCL.  Up to 8 ranks.        */
+int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128);
+int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64_t* peer_ghost_start);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------
  * Time `reps` back-to-back launches of one kernel with CUDA events on the handle's stream

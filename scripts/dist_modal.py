@@ -27,8 +27,15 @@ if world > 1:
         t = torch.tensor(list(DistFrameModel.unique_id()), dtype=torch.uint8, device="cuda")
     dist.broadcast(t, 0)
     uid = bytes(t.cpu().numpy().tolist())
+def _gather(obj):
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+use_p2p = world > 1 and not os.environ.get("FEMB_DIST_NO_P2P")
 m = DistFrameModel(local)
-part = m.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world, uid)
+part = m.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world, uid, all_gather=_gather if use_p2p else None)
 t0 = time.time()
 lam, phi, st = m.modal_dist(k=k) if world > 1 else m.modal(k=k)
 wall = time.time() - t0

@@ -29,9 +29,16 @@ if world > 1:
         t = torch.tensor(list(DistFrameModel.unique_id()), dtype=torch.uint8, device="cuda")
     dist.broadcast(t, 0)
     uid = bytes(t.cpu().numpy().tolist())
+def _gather(obj):
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+use_p2p = world > 1 and not os.environ.get("FEMB_DIST_NO_P2P")
 m = DistFrameModel(local)
 t0 = time.time()
-part = m.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world, uid)
+part = m.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world, uid, all_gather=_gather if use_p2p else None)
 t_setup = time.time() - t0
 u, r, st = m.solve_static_dist(precond=precond)            # warm-up (NCCL connections, allocator)
 if world > 1:
@@ -47,7 +54,7 @@ if rank == 0:
                       "us_per_iteration": float(ms.item()) / max(1, st["iterations"]) * 1e3,
                       "dof_per_s": n_free / (float(ms.item()) * 1e-3), "owned_nodes_rank0": int(part.n_owned),
                       "ghost_nodes_rank0": int(len(part.local_nodes) - part.n_owned), "setup_s": t_setup,
-                      "precond": "block-jacobi" if precond == L.PRECOND_BLOCK_JACOBI else "jacobi"}), flush=True)
+                      "precond": "block-jacobi" if precond == L.PRECOND_BLOCK_JACOBI else "jacobi", "exchange": "p2p" if getattr(m, "p2p", False) else "nccl"}), flush=True)
 if check:
     from oracle import ref_sparse as S
     if world > 1:
