@@ -160,6 +160,8 @@ struct femb_handle {
   int* p2p_ticket = nullptr;
   long long p2p_seq_base = 0;
   std::vector<void*> p2p_mapped;
+  femb::DevBuf<char> p2p_dev_copy;         // device-resident P2PDev for the fused kernels
+  femb::DevBuf<int32_t> p2p_send_slot, p2p_extra;
 
   void* pinned = nullptr;           // small pinned staging area
   size_t pinned_bytes = 0;
@@ -210,7 +212,8 @@ int launch_expand_csr(femb_handle* h, int which, int32_t* d_indptr, int32_t* d_i
 int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st);
 int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials);
 int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
-                     double* scal_out, const uint8_t* skip_node = nullptr, const int32_t* node_list = nullptr);
+                     double* scal_out, const uint8_t* skip_node = nullptr, const int32_t* node_list = nullptr,
+                     const void* p2p_dev = nullptr);
 int launch_spmv_tma(femb_handle* h, int variant, const double* x, double* y, bool masked, double* dot_partials,
                     double* scal_out);
 int launch_reactions(femb_handle* h, bool minus_f, double* d_out);

@@ -128,11 +128,43 @@ template <int BS, int THREADS, bool BLOCKJ>
 __global__ void __launch_bounds__(THREADS)
 dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s, double* __restrict__ p,
                    double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
-                   int64_t n, int first, double rtol, double* partials, int pstride, double* red, int* flags) {
+                   int64_t n, int first, double rtol, double* partials, int pstride, double* red, int* flags,
+                   const P2PDev* __restrict__ p2p) {
   __shared__ double s_red[THREADS / 32];
+  __shared__ double s_glob[3];
   if (flags[Flag::DONE]) return;
-  // (z, s) arrives in two parts: rows that read no ghost column, and the boundary rows
-  const double delta = red[Red::DELTA] + red[Red::DELTA2], gamma = red[Red::GAMMA], rr = red[Red::RR];
+  double delta, gamma, rr;
+  if (p2p) {
+    // fused peer-memory mode: every rank's SpMV posted {delta, gamma, ||r||^2} in this rank's mailbox;
+    // one warp per CTA waits for all of them and adds them in rank order (identical on every rank)
+    if (threadIdx.x < 32) {
+      const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;
+      const int lane = threadIdx.x;
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      bool lost = false;
+      if (lane < p2p->world) {
+        const MailSlot* src = p2p->my_mail + (lane * 2 + (int)(seq & 1));
+        long long spins = 0;
+        while (ld_acquire_sys(&src->seq) != seq) {
+          if (++spins > kSpinLimit) { lost = true; break; }
+        }
+        v0 = *reinterpret_cast<const volatile double*>(&src->v[0]);
+        v1 = *reinterpret_cast<const volatile double*>(&src->v[1]);
+        v2 = *reinterpret_cast<const volatile double*>(&src->v[2]);
+      }
+      lost = __any_sync(0xffffffffu, lost);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int p = 0; p < p2p->world; ++p) {
+        a0 += __shfl_sync(0xffffffffu, v0, p); a1 += __shfl_sync(0xffffffffu, v1, p); a2 += __shfl_sync(0xffffffffu, v2, p);
+      }
+      if (lane == 0) { s_glob[0] = a0; s_glob[1] = a1; s_glob[2] = a2; if (lost) flags[Flag::DONE] = 4; }
+    }
+    __syncthreads();
+    delta = s_glob[0]; gamma = s_glob[1]; rr = s_glob[2];
+  } else {
+    // (z, s) arrives in two parts: rows that read no ghost column, and the boundary rows
+    delta = red[Red::DELTA] + red[Red::DELTA2]; gamma = red[Red::GAMMA]; rr = red[Red::RR];
+  }
   const double tol2 = first ? rtol * rtol * rr : red[Red::TOL2];
   if (first ? (rr == 0.0) : (rr <= tol2)) {       // uniform across the grid: every CTA leaves
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -147,6 +179,7 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
   const bool bad = !(den > 0.0);
   const double alpha = bad ? 0.0 : gamma / den;
   double rz = 0.0, rr_new = 0.0;
+  bool pushed = false;
   if (BLOCKJ) {
     for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
       const int64_t nb = (g / BS) * BS;
@@ -162,6 +195,10 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
       p[g] = pg;
       x[g] += alpha * pg;
       z[g] = zg;
+      if (p2p) {
+        const int sl = __ldg(p2p->send_slot + (int)(g / BS));
+        if (sl >= 0) { p2p->peer_z[sl >> 28][(size_t)(sl & 0xFFFFFFF) * BS + rloc] = zg; pushed = true; }
+      }
       rz += rg * zg; rr_new += rg * rg;
     }
     __syncthreads();  // q / r are read by the other rows of their node (same CTA, same step)
@@ -180,9 +217,15 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
       x[g] += alpha * pg;
       r[g] = rg;
       z[g] = zg;
+      if (p2p) {
+        const int node = (int)(g / BS);
+        const int sl = __ldg(p2p->send_slot + node);
+        if (sl >= 0) { p2p->peer_z[sl >> 28][(size_t)(sl & 0xFFFFFFF) * BS + (int)(g - (int64_t)node * BS)] = zg; pushed = true; }
+      }
       rz += rg * zg; rr_new += rg * rg;
     }
   }
+  if (pushed) __threadfence_system();     // this thread's remote stores are ordered before the CTA's ticket
   double mine[2], tot[2];
   mine[0] = rz;
   mine[1] = rr_new;
@@ -196,6 +239,21 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
       red[Red::RR] = tot[1];
       flags[Flag::ITERS] = flags[Flag::ITERS] + 1;
       if (bad) flags[Flag::DONE] = 2;
+    }
+    if (p2p) {
+      // last CTA: every CTA's remote stores are done.  Nodes with several destinations, then the
+      // sequence flag of the NEXT SpMV's halo at every neighbour.
+      for (int e = threadIdx.x; e < p2p->n_extra * BS; e += THREADS) {
+        const int i = e / BS, c = e - i * BS;
+        const int node = p2p->extra[2 * i], sl = p2p->extra[2 * i + 1];
+        p2p->peer_z[sl >> 28][(size_t)(sl & 0xFFFFFFF) * BS + c] = z[(size_t)node * BS + c];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if ((int)threadIdx.x < p2p->n_nbr) {
+        const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;   // ITERS was just advanced
+        st_release_sys(p2p->peer_halo_flag[threadIdx.x] + p2p->rank, seq);
+      }
     }
   }
 }
@@ -212,32 +270,6 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
 // Sequence numbers come from a per-solve base plus the device-side iteration counter, so the
 // kernels have fixed arguments and replay inside a CUDA graph.  Waits are bounded: a lost peer
 // sets DONE = 4 instead of hanging the GPU.
-struct MailSlot { double v[4]; long long seq; long long pad[3]; };   // 64 bytes
-constexpr int kMaxRanks = 8;
-
-struct P2PDev {
-  double* peer_z[kMaxRanks];          // per neighbour k: its z vector (mapped)
-  long long peer_ghost_start[kMaxRanks];   // per neighbour k: first local node of MY data in its numbering
-  long long* peer_halo_flag[kMaxRanks];    // per neighbour k: its halo flag array (mapped), indexed by source rank
-  MailSlot* peer_mail[kMaxRanks];     // per RANK p: its mailbox array [world][2]
-  MailSlot* my_mail;
-  long long* my_halo_flag;            // [world]
-  const long long* base;              // device copy of the per-solve sequence base
-  int nbr[kMaxRanks];
-  long long send_ptr[kMaxRanks + 1];
-  int n_nbr, world, rank;
-};
-
-__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
-  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
-  long long v;
-  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-constexpr long long kSpinLimit = 1ll << 26;
-
 __global__ void __launch_bounds__(256)
 p2p_halo_kernel(const double* __restrict__ z, const int32_t* __restrict__ send_nodes, const P2PDev pd, int bs,
                 int* flags, int* ticket) {
@@ -378,6 +410,9 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
   // peer-memory path (femb_dist_p2p_import done and the exported z vector still the live one)
   const bool p2p = h->dist_world > 1 && h->p2p_dev && h->p2p_z_exported == h->z.p && !overlap && !getenv("FEMB_DIST_NO_P2P");
   const P2PDev* pd = reinterpret_cast<const P2PDev*>(h->p2p_dev);
+  // fused: the exchanges live inside the SpMV and update kernels (two launches per iteration);
+  // FEMB_DIST_P2P_KERNELS=1 keeps the two stand-alone exchange kernels instead
+  const bool fused = p2p && h->p2p_dev_copy.p && !getenv("FEMB_DIST_P2P_KERNELS");
   if (p2p) {
     long long* hb = reinterpret_cast<long long*>(reinterpret_cast<char*>(h->pinned) + 2048);
     *hb = h->p2p_seq_base;
@@ -399,12 +434,16 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
                              h->dist_bnd_nodes.p);
       if (rc2) return rc2;
       ++spmv_launches;
+    } else if (p2p && fused && !first) {
+      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red + Red::DELTA, nullptr, nullptr, h->p2p_dev_copy.p);
+      if (rc2) return rc2;
     } else if (p2p) {
       const long long tot = h->dist_send_ptr.back() * h->bs;
       const int gridh = (int)std::max<long long>(1, std::min<long long>((tot + 255) / 256, h->num_sms));
       p2p_halo_kernel<<<gridh, 256, 0, h->stream>>>(h->z.p, h->dist_send_nodes.p, *pd, h->bs, h->flags.p, h->p2p_ticket);
       h->launches++;
-      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red + Red::DELTA);
+      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red + Red::DELTA, nullptr, nullptr,
+                             fused ? h->p2p_dev_copy.p : nullptr);
       if (rc2) return rc2;
     } else {
       rc2 = dist_halo_exchange(h, h->z.p, h->stream, h->nccl_comm);
@@ -413,13 +452,15 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
       if (rc2) return rc2;
     }
     ++spmv_launches;
-    if (p2p) {
+    if (p2p && fused) {
+      // nothing to launch: the SpMV's last CTA posted the partial sums, the update kernel collects them
+    } else if (p2p) {
       p2p_allreduce_kernel<<<1, 32, 0, h->stream>>>(red, *pd, h->flags.p);
       h->launches++;
     } else if (h->dist_world > 1) {
       FEMB_NCCL(h, g_nccl.AllReduce(red, red, Red::NRED, ncclDouble, ncclSum, comm, h->stream));
     }
-#define UPD(BS, BJ) dist_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, first, o.rtol, h->partials.p + pstride, pstride, red, h->flags.p)
+#define UPD(BS, BJ) dist_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, first, o.rtol, h->partials.p + pstride, pstride, red, h->flags.p, (p2p && fused) ? reinterpret_cast<const P2PDev*>(h->p2p_dev_copy.p) : nullptr)
     if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
     else { if (blockj) UPD(3, true); else UPD(3, false); }
 #undef UPD
@@ -673,6 +714,33 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
     pd->send_ptr[k] = h->dist_send_ptr[k];
   }
   pd->send_ptr[pd->n_nbr] = h->dist_send_ptr.back();
+  // fused mode tables: destination of every owned node's entries
+  {
+    std::vector<int32_t> slot((size_t)h->n_owned_nodes, -1), extra;
+    std::vector<int32_t> snodes((size_t)h->dist_send_ptr.back());
+    FEMB_CUDA(h, cudaMemcpy(snodes.data(), h->dist_send_nodes.p, snodes.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    bool ok = true;
+    for (int k = 0; k < pd->n_nbr && ok; ++k)
+      for (int64_t i = h->dist_send_ptr[k]; i < h->dist_send_ptr[k + 1]; ++i) {
+        const int64_t idx = peer_ghost_start[k] + (i - h->dist_send_ptr[k]);
+        if (idx >= (1 << 28)) { ok = false; break; }
+        const int32_t sl = (int32_t)((k << 28) | (int32_t)idx);
+        const int32_t node = snodes[i];
+        if (slot[node] < 0) slot[node] = sl;
+        else { extra.push_back(node); extra.push_back(sl); }
+      }
+    if (ok) {
+      FEMB_CUDA(h, upload(h->p2p_send_slot, slot, h->stream));
+      if (extra.empty()) { extra.push_back(0); extra.push_back(0); pd->n_extra = 0; }
+      else pd->n_extra = (int)(extra.size() / 2);
+      FEMB_CUDA(h, upload(h->p2p_extra, extra, h->stream));
+      pd->send_slot = h->p2p_send_slot.p;
+      pd->extra = h->p2p_extra.p;
+      FEMB_CUDA(h, h->p2p_dev_copy.alloc(sizeof(P2PDev)));
+      FEMB_CUDA(h, cudaMemcpyAsync(h->p2p_dev_copy.p, pd, sizeof(P2PDev), cudaMemcpyHostToDevice, h->stream));
+      FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+  }
   if (h->p2p_dev) delete reinterpret_cast<P2PDev*>(h->p2p_dev);
   h->p2p_dev = pd;
   h->p2p_seq_base = 0;

@@ -98,6 +98,41 @@ __device__ __forceinline__ double apply_dinv_row(const double* __restrict__ Dinv
   return z;
 }
 
+
+// ---- peer-memory exchange (dist.cu; hooks in the SpMV and the distributed update kernel) -----
+struct MailSlot { double v[4]; long long seq; long long pad[3]; };   // 64 bytes
+constexpr int kMaxRanks = 8;
+
+struct P2PDev {
+  double* peer_z[kMaxRanks];          // per neighbour k: its z vector (mapped)
+  long long peer_ghost_start[kMaxRanks];   // per neighbour k: first local node of MY data in its numbering
+  long long* peer_halo_flag[kMaxRanks];    // per neighbour k: its halo flag array (mapped), indexed by source rank
+  MailSlot* peer_mail[kMaxRanks];     // per RANK p: its mailbox array [world][2]
+  MailSlot* my_mail;
+  long long* my_halo_flag;            // [world]
+  const long long* base;              // device copy of the per-solve sequence base
+  int nbr[kMaxRanks];
+  long long send_ptr[kMaxRanks + 1];
+  int n_nbr, world, rank;
+  // fused mode (no separate exchange kernels): per owned node, destination of its z entries
+  // (k << 28 | ghost node index at neighbour k, -1 = interior) and the few nodes with several
+  // destinations as (node, slot) pairs handled by the update kernel's last CTA
+  const int32_t* send_slot;
+  const int32_t* extra;      // (n_extra, 2)
+  int n_extra;
+};
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr long long kSpinLimit = 1ll << 22;   // ~seconds of polling, then DONE = 4
+
+
 inline int vec_grid(const femb_handle* h, int64_t n, int threads) {
   int64_t need = (n + threads - 1) / threads;
   int64_t cap = (int64_t)h->num_sms * 8;

@@ -32,13 +32,27 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
                 const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
                 const double* __restrict__ x, double* __restrict__ y, int64_t nrows,
                 double* partials, int pstride, double* scal, int* flags,
-                const uint8_t* __restrict__ skip_node, const int32_t* __restrict__ node_list) {
+                const uint8_t* __restrict__ skip_node, const int32_t* __restrict__ node_list,
+                const P2PDev* __restrict__ p2p) {
   // skip_node != nullptr: block rows flagged there are left to a later launch (rows that read
   // ghost columns wait for the halo); node_list != nullptr: row g belongs to node_list[g / BS].
   static_assert(BS == 6 || BS == 3, "block size");
   __shared__ double s_red[THREADS / 32];
   if (DOT && flags[Flag::DONE]) return;
+  if (DOT && p2p) {
+    // fused peer-memory mode: the neighbours' update kernels stored the ghost entries of x straight
+    // into this rank's vector and released a sequence flag — wait for it before gathering
+    if ((int)threadIdx.x < p2p->n_nbr) {
+      const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;
+      long long spins = 0;
+      while (ld_acquire_sys(p2p->my_halo_flag + p2p->nbr[threadIdx.x]) < seq) {
+        if (++spins > kSpinLimit) { flags[Flag::DONE] = 4; break; }
+      }
+    }
+    __syncthreads();
+  }
   double dot = 0.0;
+  const int n_owned_p2p = (DOT && p2p) ? (int)(nrows / BS) : 0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < nrows; g += (int64_t)gridDim.x * THREADS) {
     int node = (int)(g / BS);
     const int r = (int)(g - (int64_t)node * BS);
@@ -58,7 +72,15 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
         const double2* a2 = reinterpret_cast<const double2*>(vals + (size_t)b * 36 + r * 6);
         const double2* x2 = reinterpret_cast<const double2*>(x + (size_t)col * 6);
         const double2 a0 = __ldcs(a2), a1 = __ldcs(a2 + 1), a2v = __ldcs(a2 + 2);
-        const double2 x0 = __ldg(x2), x1 = __ldg(x2 + 1), x2v = __ldg(x2 + 2);
+        double2 x0, x1, x2v;
+        if (p2p && col >= n_owned_p2p) {
+          // ghost entries are stored by peer GPUs, possibly while CTAs of this kernel are already
+          // resident: read them L2-coherently (the non-coherent path served stale L1 lines — measured
+          // as 15,319 instead of 6,931 iterations at 1M DOF on 2 GPUs)
+          x0 = __ldcg(x2); x1 = __ldcg(x2 + 1); x2v = __ldcg(x2 + 2);
+        } else {
+          x0 = __ldg(x2); x1 = __ldg(x2 + 1); x2v = __ldg(x2 + 2);
+        }
         acc += a0.x * x0.x; acc += a0.y * x0.y; acc += a1.x * x1.x;
         acc += a1.y * x1.y; acc += a2v.x * x2v.x; acc += a2v.y * x2v.y;
       }
@@ -81,6 +103,14 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     mine[0] = dot;
     if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET0, s_red, tot)) {
       if (threadIdx.x == 0) scal[Scal::PQ] = tot[0];
+      if (p2p && (int)threadIdx.x < p2p->world) {
+        // post {delta, gamma, ||r||^2} of this rank in every peer's mailbox (scal = the solver's red[])
+        const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;
+        MailSlot* dst = p2p->peer_mail[threadIdx.x] + (p2p->rank * 2 + (int)(seq & 1));
+        dst->v[0] = tot[0]; dst->v[1] = scal[1]; dst->v[2] = scal[2]; dst->v[3] = 0.0;
+        __threadfence_system();
+        st_release_sys(&dst->seq, seq);
+      }
     }
   }
 }
@@ -316,16 +346,16 @@ __global__ void set_prescribed_kernel(double* x, const double* u0, const uint8_t
 
 // ---------------------------------------------------------------------------- host side
 int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double* dot_partials) {
-  return launch_spmv_rows(h, x, y, h->ndof, masked, dot_partials, h->scal.p, nullptr, nullptr);
+  return launch_spmv_rows(h, x, y, h->ndof, masked, dot_partials, h->scal.p, nullptr, nullptr, nullptr);
 }
 
 // rows [0, n) only (the distributed solver owns a prefix of the local rows); the fused dot goes
 // to scal_out[Scal::PQ]
 int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
-                     double* scal_out, const uint8_t* skip_node, const int32_t* node_list) {
+                     double* scal_out, const uint8_t* skip_node, const int32_t* node_list, const void* p2p_dev) {
   static int tma_variant = -1;
   if (tma_variant < 0) { const char* e = getenv("FEMB_SPMV_TMA"); tma_variant = e ? atoi(e) : 0; }
-  if (tma_variant > 0 && h->bs == 6 && n == h->ndof && !skip_node && !node_list)
+  if (tma_variant > 0 && h->bs == 6 && n == h->ndof && !skip_node && !node_list && !p2p_dev)
     return launch_spmv_tma(h, tma_variant, x, y, masked, dot_partials, scal_out);
   const int pstride = h->num_sms * 8;
   const int grid = vec_grid(h, n, kRowThreads);
@@ -334,7 +364,7 @@ int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool
 #define SPMV_U(BS, M, D, U)                                                                    \
   bsr_spmv_kernel<BS, M, D, kRowThreads, U><<<grid, kRowThreads, 0, h->stream>>>(               \
       h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, x, y, n, dot_partials, pstride,    \
-      scal_out, h->flags.p, skip_node, node_list)
+      scal_out, h->flags.p, skip_node, node_list, reinterpret_cast<const P2PDev*>(p2p_dev))
 #define SPMV(BS, M, D)                                                                         \
   do { if (BS == 6 && unr == 8) SPMV_U(BS, M, D, 8); else if (BS == 6 && unr == 2) SPMV_U(BS, M, D, 2); \
        else if (BS == 6 && unr == 4) SPMV_U(BS, M, D, 4); else SPMV_U(BS, M, D, 2); } while (0)
