@@ -18,14 +18,23 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool owned = true;   // false: p points into another allocation (adopt)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     n = 0;
+    owned = true;
+  }
+  // view of `count` elements inside memory owned by someone else
+  void adopt(T* ptr, size_t count) {
+    release();
+    p = ptr;
+    n = count;
+    owned = false;
   }
   cudaError_t alloc(size_t count) {
     if (count == n && p) return cudaSuccess;

@@ -157,10 +157,11 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
       for (int p = 0; p < p2p->world; ++p) {
         a0 += __shfl_sync(0xffffffffu, v0, p); a1 += __shfl_sync(0xffffffffu, v1, p); a2 += __shfl_sync(0xffffffffu, v2, p);
       }
-      if (lane == 0) { s_glob[0] = a0; s_glob[1] = a1; s_glob[2] = a2; if (lost) flags[Flag::DONE] = 4; }
+      if (lane == 0) { s_glob[0] = a0; s_glob[1] = a1; s_glob[2] = lost ? -1.0 : a2; if (lost) flags[Flag::DONE] = 4; }
     }
     __syncthreads();
     delta = s_glob[0]; gamma = s_glob[1]; rr = s_glob[2];
+    if (rr < 0.0) return;                 // a peer never answered: DONE = 4 is reported by the host
   } else {
     // (z, s) arrives in two parts: rows that read no ghost column, and the boundary rows
     delta = red[Red::DELTA] + red[Red::DELTA2]; gamma = red[Red::GAMMA]; rr = red[Red::RR];
@@ -414,6 +415,9 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
   // FEMB_DIST_P2P_KERNELS=1 keeps the two stand-alone exchange kernels instead
   const bool fused = p2p && h->p2p_dev_copy.p && !getenv("FEMB_DIST_P2P_KERNELS");
   if (p2p) {
+    // line the ranks up once per solve (they arrive from host-side setup of different length): the
+    // bounded waits of the peer-memory kernels are sized for iteration-scale skew, NCCL's is unbounded
+    FEMB_NCCL(h, g_nccl.AllReduce(red + Red::DELTA2, red + Red::DELTA2, 1, ncclDouble, ncclSum, comm, h->stream));
     long long* hb = reinterpret_cast<long long*>(reinterpret_cast<char*>(h->pinned) + 2048);
     *hb = h->p2p_seq_base;
     FEMB_CUDA(h, cudaMemcpyAsync(h->p2p_base_dev, hb, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
@@ -656,15 +660,20 @@ int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128) {
   if (!h->have_bc || !h->z.p) return fail(h, FEMB_ERR_ARG, "call femb_set_bc before femb_dist_p2p_export");
   if (h->dist_world > kMaxRanks) return fail(h, FEMB_ERR_ARG, "peer-memory path supports up to 8 ranks");
   FEMB_CUDA(h, cudaSetDevice(h->device));
-  const size_t bytes = sizeof(MailSlot) * h->dist_world * 2 + sizeof(long long) * (h->dist_world + 2) + 64;
+  // ONE dedicated allocation per rank — mailboxes, flags and the z vector itself — of at least
+  // 2 MB, so that it is never a sub-allocation of a block shared with other buffers: the IPC
+  // handle then maps exactly this memory at offset 0 in every peer.
+  const size_t zbytes = (size_t)h->ndof * sizeof(double);
+  const size_t bytes = std::max<size_t>(kP2PZOffset + zbytes, (size_t)4 << 20);
+  h->z.release();                       // z moves into the exported allocation
   FEMB_CUDA(h, h->p2p_comm.alloc(bytes));
   FEMB_CUDA(h, cudaMemset(h->p2p_comm.p, 0, bytes));
-  cudaIpcMemHandle_t hz, hc;
-  FEMB_CUDA(h, cudaIpcGetMemHandle(&hz, h->z.p));
+  h->z.adopt(reinterpret_cast<double*>(h->p2p_comm.p + kP2PZOffset), (size_t)h->ndof);
+  cudaIpcMemHandle_t hc;
   FEMB_CUDA(h, cudaIpcGetMemHandle(&hc, h->p2p_comm.p));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  std::memcpy(handles128, &hz, 64);
-  std::memcpy(handles128 + 64, &hc, 64);
+  std::memset(handles128, 0, 128);
+  std::memcpy(handles128, &hc, 64);
   h->p2p_z_exported = h->z.p;
   return FEMB_OK;
 }
@@ -687,11 +696,10 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
   pd->base = h->p2p_base_dev;
   pd->world = world; pd->rank = rank;
   std::vector<char*> peer_comm(world, nullptr);
-  std::vector<double*> peer_z(world, nullptr);
   for (int p = 0; p < world; ++p) {
-    if (p == rank) { peer_comm[p] = cb; peer_z[p] = h->z.p; continue; }
+    if (p == rank) { peer_comm[p] = cb; continue; }
     cudaIpcMemHandle_t hc;
-    std::memcpy(&hc, all_handles + (size_t)p * 128 + 64, 64);
+    std::memcpy(&hc, all_handles + (size_t)p * 128, 64);
     void* ptr = nullptr;
     FEMB_CUDA(h, cudaIpcOpenMemHandle(&ptr, hc, cudaIpcMemLazyEnablePeerAccess));
     peer_comm[p] = reinterpret_cast<char*>(ptr);
@@ -702,12 +710,7 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
   if (pd->n_nbr > kMaxRanks) { delete pd; return fail(h, FEMB_ERR_ARG, "too many neighbour ranks"); }
   for (int k = 0; k < pd->n_nbr; ++k) {
     const int p = h->dist_nbr[k];
-    cudaIpcMemHandle_t hz;
-    std::memcpy(&hz, all_handles + (size_t)p * 128, 64);
-    void* ptr = nullptr;
-    FEMB_CUDA(h, cudaIpcOpenMemHandle(&ptr, hz, cudaIpcMemLazyEnablePeerAccess));
-    h->p2p_mapped.push_back(ptr);
-    pd->peer_z[k] = reinterpret_cast<double*>(ptr);
+    pd->peer_z[k] = reinterpret_cast<double*>(peer_comm[p] + kP2PZOffset);
     pd->peer_ghost_start[k] = peer_ghost_start[k];
     pd->peer_halo_flag[k] = flag_of(peer_comm[p]);
     pd->nbr[k] = p;

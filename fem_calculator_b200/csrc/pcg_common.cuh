@@ -102,6 +102,7 @@ __device__ __forceinline__ double apply_dinv_row(const double* __restrict__ Dinv
 // ---- peer-memory exchange (dist.cu; hooks in the SpMV and the distributed update kernel) -----
 struct MailSlot { double v[4]; long long seq; long long pad[3]; };   // 64 bytes
 constexpr int kMaxRanks = 8;
+constexpr size_t kP2PZOffset = 8192;   // mailboxes + flags live below, the z vector above (same layout on every rank)
 
 struct P2PDev {
   double* peer_z[kMaxRanks];          // per neighbour k: its z vector (mapped)
@@ -130,7 +131,7 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
   asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-constexpr long long kSpinLimit = 1ll << 22;   // ~seconds of polling, then DONE = 4
+constexpr long long kSpinLimit = 1ll << 24;   // several seconds of polling, then DONE = 4
 
 
 inline int vec_grid(const femb_handle* h, int64_t n, int threads) {
