@@ -175,99 +175,18 @@ assemble_tiles_kernel(const EL el, const PatternDev pat, double* __restrict__ Kv
 //   * streams the off-diagonal block (node, other end) straight from registers to HBM with
 //     nine 32-byte stores (STG.256; a block is 288 contiguous bytes, 32-byte aligned);
 //   * parks its share of the node's diagonal block — the 21-value upper triangle plus 7 compact
-//     lumped-mass values — in shared memory, transposed so that lanes hit distinct banks.
+//     lumped-mass values — in shared memory (odd row stride: conflict-free).
 // After one barrier the CTA sums every node's shares in list (= element-ascending) order and
-// writes the expanded diagonal and mass blocks with coalesced stores.  No float atomics, no
-// rank loop: the summation order is fixed by the symbolic phase, so K and M are
-// bit-reproducible run to run.  Only ~29 KB of shared memory per 128-thread CTA.
-struct PairDev {
-  const int4* rec;           // (n_pairs) {node, other, blk, sec | a<<24 | pos<<25}
-  const int32_t* pair_ptr;   // (n_nodes+1)
-  const int32_t* diag_blk;   // (n_nodes)
-  const int32_t* tile_ptr;   // (n_tiles+1) node ranges, <= THREADS pairs and <= THREADS nodes each
-};
-
+// writes the diagonal block and the 12 non-zero lumped-mass entries.  No float atomics, no rank
+// loop: the summation order is fixed by the symbolic phase, so K and M are bit-reproducible.
+// History (1M-DOF frame, one B200): generic tile kernel 330 us -> first pair kernel (tile staged
+// in shared memory + bulk copy, rank loop) 209 us -> register-streamed stores + share table 127 us
+// -> persistent CTAs with software-pipelined inputs 101 us (profiles/r01_ncu_full_assembly_*.txt).
 __device__ __forceinline__ void st_global_256(double* p, double a, double b, double c, double d) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
 constexpr int kShareStride = 29;  // odd stride (in doubles): conflict-free 64-bit shared accesses
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 4)
-frame_assemble_pairs_kernel(const FrameParams P, const PairDev pat, double* __restrict__ Kvals,
-                            double* __restrict__ Mdiag) {
-  __shared__ double s_c[THREADS * kShareStride];
-  __shared__ uint8_t s_rc[28];  // share index -> r*6+c inside the 6x6 block (K: q<21, M: q>=21)
-  const int tid = threadIdx.x;
-  const int n0 = pat.tile_ptr[blockIdx.x], n1 = pat.tile_ptr[blockIdx.x + 1];
-  const int p0 = pat.pair_ptr[n0], p1 = pat.pair_ptr[n1];
-  const int p = p0 + tid;
-  if (tid < 28) {
-    int r = 0, c = 0;
-    if (tid < 21) {        // upper triangle of the 6x6, row-major
-      int q = tid;
-      while (q >= 6 - r) { q -= 6 - r; ++r; }
-      c = r + q;
-    } else if (tid == 21) {  // translational mass (scalar on the diagonal)
-      r = c = 0;
-    } else {               // upper triangle of the rotational 3x3
-      int q = tid - 22;
-      while (q >= 3 - r) { q -= 3 - r; ++r; }
-      c = 3 + r + q; r += 3;
-    }
-    s_rc[tid] = (uint8_t)(r * 6 + c);
-  }
-  if (p < p1) {
-    const int4 rec = __ldg(pat.rec + p);
-    const int a = (rec.w >> 24) & 1;
-    FrameRec R;
-    // the record is oriented from element end 0 to end 1 (BeamSolver.py:372-373)
-    frame_record_nodes(P, a ? rec.y : rec.x, a ? rec.x : rec.y, rec.w & 0xFFFFFF, R);
-    double* g = Kvals + (size_t)rec.z * 36;
-    double row[12];
-#pragma unroll
-    for (int h = 0; h < 3; ++h) {
-      frame_offdiag_row(R, a, 2 * h, row);
-      frame_offdiag_row(R, a, 2 * h + 1, row + 6);
-      st_global_256(g + 12 * h, row[0], row[1], row[2], row[3]);
-      st_global_256(g + 12 * h + 4, row[4], row[5], row[6], row[7]);
-      st_global_256(g + 12 * h + 8, row[8], row[9], row[10], row[11]);
-    }
-    double d[28];
-    frame_diag_sym(R, a, d, d + 21);
-    double* mine = s_c + tid * kShareStride;
-#pragma unroll
-    for (int q = 0; q < 28; ++q) mine[q] = d[q];
-  }
-  __syncthreads();
-  // one (node, share index) item per thread: ordered sum over the node's pairs, then the one
-  // to three entries of the diagonal K block / lumped-mass block that value fills.  The
-  // structurally zero entries of the mass block are zeroed once at allocation.
-  const int nn = n1 - n0;
-  for (int o = tid; o < nn * 28; o += THREADS) {
-    const int ns = o / 28, q = o - ns * 28;
-    const int node = n0 + ns;
-    const int j0 = pat.pair_ptr[node] - p0, j1 = pat.pair_ptr[node + 1] - p0;
-    double v = 0.0;
-    for (int j = j0; j < j1; ++j) v += s_c[j * kShareStride + q];
-    const int rc = s_rc[q];
-    if (q < 21) {
-      double* kd = Kvals + (size_t)pat.diag_blk[node] * 36;
-      kd[rc] = v;
-      const int r = rc / 6, c = rc - r * 6;
-      if (r != c) kd[c * 6 + r] = v;
-    } else if (q == 21) {
-      double* md = Mdiag + (size_t)node * 36;
-      md[0] = v; md[7] = v; md[14] = v;
-    } else {
-      double* md = Mdiag + (size_t)node * 36;
-      md[rc] = v;
-      const int r = rc / 6, c = rc - r * 6;
-      if (r != c) md[c * 6 + r] = v;
-    }
-  }
-}
 
 // Persistent form of the pair kernel: one CTA per resident slot walks tiles t, t+G, t+2G, ...
 // and software-pipelines the input side — the tile descriptor two tiles ahead, the pair records
@@ -371,79 +290,6 @@ frame_assemble_pairs_persistent_kernel(const FrameParams P, const PairDevP pat, 
     }
     __syncthreads();  // s_c / s_node are rewritten by the next tile
     td = td1; td1 = td2; rec = rec1;
-  }
-}
-
-// Variant with the whole tile staged in shared memory in its HBM layout and written by one
-// bulk async copy (cp.async.bulk shared -> global): stores are perfectly coalesced at the
-// price of ~420 B of shared memory per thread.  Diagonal shares are added into a 28-value
-// accumulator per node in list order, one position per __syncthreads_or step.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 4)
-frame_assemble_pairs_staged_kernel(const FrameParams P, const PairDev pat, const int32_t* __restrict__ rowptr,
-                                   double* __restrict__ Kvals, double* __restrict__ Mdiag) {
-  extern __shared__ __align__(128) double s_out[];  // K blocks [nblk*36] | mass [nn*36] | diag acc [nn*28]
-  const int tid = threadIdx.x;
-  const int n0 = pat.tile_ptr[blockIdx.x], n1 = pat.tile_ptr[blockIdx.x + 1];
-  const int nn = n1 - n0;
-  const int b0 = rowptr[n0], b1 = rowptr[n1];
-  const int p0 = pat.pair_ptr[n0], p1 = pat.pair_ptr[n1];
-  const int nblk = b1 - b0;
-  double* s_mass = s_out + (size_t)nblk * 36;
-  double* s_diag = s_mass + (size_t)nn * 36;
-  for (int t = tid; t < nn * 28; t += THREADS) s_diag[t] = 0.0;
-  const int p = p0 + tid;
-  int pos = -1, nslot = 0;
-  double d[28];
-  if (p < p1) {
-    const int4 rec = __ldg(pat.rec + p);
-    const int a = (rec.w >> 24) & 1;
-    pos = (int)((uint32_t)rec.w >> 25);
-    nslot = rec.x - n0;
-    FrameRec R;
-    frame_record_nodes(P, a ? rec.y : rec.x, a ? rec.x : rec.y, rec.w & 0xFFFFFF, R);
-    double2* dst = reinterpret_cast<double2*>(s_out + (size_t)(rec.z - b0) * 36);
-    double row[12];
-#pragma unroll
-    for (int h = 0; h < 3; ++h) {
-      frame_offdiag_row(R, a, 2 * h, row);
-      frame_offdiag_row(R, a, 2 * h + 1, row + 6);
-#pragma unroll
-      for (int q = 0; q < 6; ++q) dst[6 * h + q] = make_double2(row[2 * q], row[2 * q + 1]);
-    }
-    frame_diag_sym(R, a, d, d + 21);
-  }
-  __syncthreads();
-  for (int k = 0; __syncthreads_or(pos >= k); ++k) {
-    if (pos == k) {
-      double* acc = s_diag + (size_t)nslot * 28;
-#pragma unroll
-      for (int q = 0; q < 28; ++q) acc[q] += d[q];
-    }
-  }
-  for (int t = tid; t < nn * 36; t += THREADS) {
-    const int ns = t / 36, rc = t - ns * 36;
-    const int r = rc / 6, c = rc - r * 6;
-    const double* dd = s_diag + (size_t)ns * 28;
-    s_out[(size_t)(pat.diag_blk[n0 + ns] - b0) * 36 + rc] = dd[sym6_index(r, c)];
-    double mv = 0.0;
-    if (r < 3 && c < 3) mv = (r == c) ? dd[21] : 0.0;
-    else if (r >= 3 && c >= 3) {
-      const int rr = r - 3, cc = c - 3;
-      const int lo = rr < cc ? rr : cc, hi = rr < cc ? cc : rr;
-      mv = dd[22 + lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo)];
-    }
-    s_mass[t] = mv;
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  if (tid == 0) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(Kvals + (size_t)b0 * 36), "r"(smem_u32(s_out)), "r"((uint32_t)(nblk * 288)) : "memory");
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(Mdiag + (size_t)n0 * 36), "r"(smem_u32(s_mass)), "r"((uint32_t)(nn * 288)) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 
@@ -559,28 +405,10 @@ static int launch_assemble_pairs(femb_handle* h) {
   const femb::Symbolic& S = h->sym;
   const int n_tiles = (int)S.pair_tile_ptr.size() - 1;
   if (n_tiles <= 0) return FEMB_OK;
-  PairDev pat{reinterpret_cast<const int4*>(h->pair_rec.p), h->pair_ptr.p, h->diag_blk.p, h->pair_tile_ptr.p};
-  const char* v = getenv("FEMB_ASM_PAIRS");
-  if (!v || v[0] == '4') {
-    PairDevP pp{reinterpret_cast<const int4*>(h->pair_rec.p), reinterpret_cast<const int4*>(h->pair_node_rec.p),
-                reinterpret_cast<const int4*>(h->pair_tiles.p), n_tiles};
-    const int grid = std::min(n_tiles, h->num_sms * 4);
-    frame_assemble_pairs_persistent_kernel<kAsmThreads><<<grid, kAsmThreads, 0, h->stream>>>(frame_params(h), pp, h->Kvals.p, h->Mdiag.p);
-  } else if (v[0] == '2') {
-    frame_assemble_pairs_kernel<kAsmThreads><<<n_tiles, kAsmThreads, 0, h->stream>>>(frame_params(h), pat, h->Kvals.p, h->Mdiag.p);
-  } else {
-    size_t smem = 0;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int n0 = S.pair_tile_ptr[t], n1 = S.pair_tile_ptr[t + 1];
-      const size_t need = (size_t)(S.rowptr[n1] - S.rowptr[n0]) * 288 + (size_t)(n1 - n0) * (288 + 224);
-      smem = need > smem ? need : smem;
-    }
-    smem = (smem + 127) & ~size_t(127);
-    if (smem > 200 * 1024) return fail(h, FEMB_ERR_ARG, "assembly tile exceeds shared memory");
-    auto k = frame_assemble_pairs_staged_kernel<kAsmThreads>;
-    FEMB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<n_tiles, kAsmThreads, smem, h->stream>>>(frame_params(h), pat, h->rowptr.p, h->Kvals.p, h->Mdiag.p);
-  }
+  PairDevP pp{reinterpret_cast<const int4*>(h->pair_rec.p), reinterpret_cast<const int4*>(h->pair_node_rec.p),
+              reinterpret_cast<const int4*>(h->pair_tiles.p), n_tiles};
+  const int grid = std::min(n_tiles, h->num_sms * 4);   // 4 resident CTAs per SM (128 registers, 32 KB shared)
+  frame_assemble_pairs_persistent_kernel<kAsmThreads><<<grid, kAsmThreads, 0, h->stream>>>(frame_params(h), pp, h->Kvals.p, h->Mdiag.p);
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   return FEMB_OK;

@@ -212,9 +212,7 @@ static int ensure_symbolic(femb_handle* h) {
     }
     FEMB_CUDA(h, upload(h->pair_node_rec, nrec, h->stream));
     FEMB_CUDA(h, upload(h->pair_tiles, tiles, h->stream));
-    FEMB_CUDA(h, upload(h->pair_ptr, S.pair_ptr, h->stream));
     FEMB_CUDA(h, upload(h->pair_rec, rec, h->stream));
-    FEMB_CUDA(h, upload(h->pair_tile_ptr, S.pair_tile_ptr, h->stream));
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));  // rec is a local
     h->pairs_dev_ok = true;
   }

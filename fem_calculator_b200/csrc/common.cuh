@@ -111,7 +111,6 @@ struct femb_handle {
   bool have_symbolic = false, assembled = false;
   femb::DevBuf<int32_t> rowptr, colidx, blk_row, diag_blk, contrib_ptr, contrib_blk, tile_ptr;
   femb::DevBuf<uint32_t> contrib;
-  femb::DevBuf<int32_t> pair_ptr, pair_tile_ptr;
   femb::DevBuf<int32_t> pair_rec;   // (n_pairs,4) {node, other node, block, sec | end<<24 | pos<<25}
   femb::DevBuf<int32_t> pair_node_rec;  // (n_nodes,4) {first pair, pair count, diagonal block, 0}
   femb::DevBuf<int32_t> pair_tiles;     // (n_tiles,4) {first node, node count, first pair, pair count}

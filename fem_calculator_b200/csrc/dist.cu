@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(THREADS)
 dist_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, double* __restrict__ x,
                  double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ q,
                  int64_t n, double* partials, int pstride, double* red, int* flags) {
-  __shared__ double s_red[THREADS / 32];
   double rz = 0.0, bb = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
     const double bg = b[g];
@@ -112,7 +111,7 @@ dist_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, 
   double mine[2], tot[2];
   mine[0] = rz;
   mine[1] = bb;
-  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
+  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
       red[Red::GAMMA] = tot[0];
       red[Red::RR] = tot[1];
@@ -130,7 +129,6 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
                    double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
                    int64_t n, int first, double rtol, double* partials, int pstride, double* red, int* flags,
                    const P2PDev* __restrict__ p2p) {
-  __shared__ double s_red[THREADS / 32];
   __shared__ double s_glob[3];
   if (flags[Flag::DONE]) return;
   double delta, gamma, rr;
@@ -230,7 +228,7 @@ dist_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s
   double mine[2], tot[2];
   mine[0] = rz;
   mine[1] = rr_new;
-  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
+  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
       red[Red::GPREV] = gamma;
       red[Red::ALPHA] = alpha;

@@ -46,7 +46,7 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
 // Returns true in ALL threads of the last CTA, with the totals in out[] (every thread).
 template <int THREADS, int NV>
 __device__ __forceinline__ bool grid_reduce(const double (&mine)[NV], double* partials, int stride,
-                                            int* ticket, double* /*unused*/, double (&out)[NV]) {
+                                            int* ticket, double (&out)[NV]) {
   constexpr int NW = THREADS / 32;
   static_assert(NV <= THREADS, "one thread per value");
   __shared__ double s_part[NV * NW];

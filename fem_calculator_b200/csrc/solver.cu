@@ -37,7 +37,6 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   // skip_node != nullptr: block rows flagged there are left to a later launch (rows that read
   // ghost columns wait for the halo); node_list != nullptr: row g belongs to node_list[g / BS].
   static_assert(BS == 6 || BS == 3, "block size");
-  __shared__ double s_red[THREADS / 32];
   if (DOT && flags[Flag::DONE]) return;
   if (DOT && p2p) {
     // fused peer-memory mode: the neighbours' update kernels stored the ghost entries of x straight
@@ -101,7 +100,7 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   if (DOT) {
     double mine[1], tot[1];
     mine[0] = dot;
-    if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET0, s_red, tot)) {
+    if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET0, tot)) {
       if (threadIdx.x == 0) scal[Scal::PQ] = tot[0];
       if (p2p && (int)threadIdx.x < p2p->world) {
         // post {delta, gamma, ||r||^2} of this rank in every peer's mailbox (scal = the solver's red[])
@@ -209,7 +208,6 @@ __global__ void __launch_bounds__(THREADS)
 pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, double* __restrict__ x,
                 double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ q,
                 int64_t n, double rtol, double* partials, int pstride, double* scal, int* flags) {
-  __shared__ double s_red[THREADS / 32];
   double rz = 0.0, bb = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
     const double bg = b[g];
@@ -229,7 +227,7 @@ pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ Dinv, d
   double mine[2], tot[2];
   mine[0] = rz;
   mine[1] = bb;
-  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
+  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
       scal[Scal::RZ0] = tot[0]; scal[Scal::RZ1] = tot[0];
       scal[Scal::BB] = tot[1]; scal[Scal::RR] = tot[1];
@@ -248,7 +246,6 @@ pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s,
                   double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
                   int64_t n, int parity, int first, int max_iter, double* partials, int pstride, double* scal,
                   int* flags) {
-  __shared__ double s_red[THREADS / 32];
   if (flags[Flag::DONE]) return;
   const double delta = scal[Scal::PQ];
   const double gamma = scal[Scal::RZ0 + (parity ^ 1)];
@@ -320,7 +317,7 @@ pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s,
   double mine[2], tot[2];
   mine[0] = rz;
   mine[1] = rr;
-  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, s_red, tot)) {
+  if (grid_reduce<THREADS, 2>(mine, partials, pstride, flags + Flag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
       scal[Scal::RZ0 + parity] = tot[0];
       scal[Scal::RR] = tot[1];
@@ -610,7 +607,6 @@ __global__ void __launch_bounds__(THREADS)
 mpcg_init_kernel(const double* __restrict__ B, int64_t ldb, int nb, const double* __restrict__ dinv,
                  double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, int64_t n, double rtol,
                  double* partials, int pstride, double* scal, int* flags) {
-  __shared__ double s_red[THREADS / 32];
   double rz[kNB] = {0, 0, 0, 0}, bb[kNB] = {0, 0, 0, 0};
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
     const double d = dinv[g];
@@ -626,7 +622,7 @@ mpcg_init_kernel(const double* __restrict__ B, int64_t ldb, int nb, const double
   double mine[2 * kNB], tot[2 * kNB];
 #pragma unroll
   for (int q = 0; q < kNB; ++q) { mine[q] = rz[q]; mine[kNB + q] = bb[q]; }
-  if (grid_reduce<THREADS, 2 * kNB>(mine, partials, pstride, flags + MFlag::TICKET1, s_red, tot)) {
+  if (grid_reduce<THREADS, 2 * kNB>(mine, partials, pstride, flags + MFlag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
       int all = 1;
       for (int q = 0; q < kNB; ++q) {
@@ -653,7 +649,6 @@ mpcg_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
                  const double* __restrict__ p, double* __restrict__ qv, int64_t n,
                  double* partials, int pstride, double* scal, int* flags) {
-  __shared__ double s_red[THREADS / 32];
   if (flags[MFlag::ALLDONE]) return;
   double dot[kNB] = {0, 0, 0, 0};
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
@@ -682,7 +677,7 @@ mpcg_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   double mine[kNB], tot[kNB];
 #pragma unroll
   for (int q = 0; q < kNB; ++q) mine[q] = dot[q];
-  if (grid_reduce<THREADS, kNB>(mine, partials, pstride, flags + MFlag::TICKET0, s_red, tot)) {
+  if (grid_reduce<THREADS, kNB>(mine, partials, pstride, flags + MFlag::TICKET0, tot)) {
     if (threadIdx.x == 0)
       for (int q = 0; q < kNB; ++q) scal[MScal::PQ + q] = tot[q];
   }
@@ -694,7 +689,6 @@ __global__ void __launch_bounds__(THREADS)
 mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict__ p, const double* __restrict__ qv,
                       double* __restrict__ x, double* __restrict__ r, int64_t n, int max_iter,
                       double* partials, int pstride, double* scal, int* flags) {
-  __shared__ double s_red[THREADS / 32];
   if (flags[MFlag::ALLDONE]) return;
   double alpha[kNB];
   bool bad = false;
@@ -720,7 +714,7 @@ mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict_
   double mine[2 * kNB], tot[2 * kNB];
 #pragma unroll
   for (int q = 0; q < kNB; ++q) { mine[q] = rz[q]; mine[kNB + q] = rr[q]; }
-  if (grid_reduce<THREADS, 2 * kNB>(mine, partials, pstride, flags + MFlag::TICKET1, s_red, tot)) {
+  if (grid_reduce<THREADS, 2 * kNB>(mine, partials, pstride, flags + MFlag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
       const int it = flags[MFlag::ITERS] + 1;
       flags[MFlag::ITERS] = it;

@@ -112,7 +112,7 @@ bsr6_spmv_tma_kernel(const int32_t* __restrict__ tile_ptr, int n_tiles, const in
   if (DOT) {
     double mine[1], tot[1];
     mine[0] = dot;
-    if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET0, nullptr, tot)) {
+    if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET0, tot)) {
       if (threadIdx.x == 0) scal[Scal::PQ] = tot[0];
     }
   }
