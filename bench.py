@@ -268,6 +268,37 @@ def run_gpu(args):
                           "method": "block shift-invert Krylov (block 4), 4-RHS lockstep Jacobi-PCG as K^-1"}
     m.close()
 
+    if world > 1 and not args.no_rowblock:
+        # strong-scaling companion (not the headline): the SAME frame split by node slabs across the N
+        # GPUs, distributed PCG with peer-memory (NVLink) halo + scalar exchange fused into its kernels
+        import torch
+        from fem_calculator_b200.api import DistFrameModel
+        mesh0, sec0, bc0, es0, props0, fixed0, f0 = build_case(load_scale=1.0)
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t = torch.tensor(list(DistFrameModel.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+
+        def _gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+        d = DistFrameModel(local)
+        d.setup(mesh0.points, mesh0.cells_dict["line"], es0, props0, E, E / (2 * (1 + nu)), fixed0, f0, rank, world,
+                bytes(t.cpu().numpy().tolist()), all_gather=_gather)
+        d.solve_static_dist(precond=L.PRECOND_JACOBI, rtol=RTOL, want_u=False, want_reactions=False)   # warm-up
+        barrier()
+        _, _, dst = d.solve_static_dist(precond=L.PRECOND_JACOBI, rtol=RTOL, want_u=False, want_reactions=False)
+        tt = torch.tensor([dst["device_ms"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        extra["rowblock"] = {"what": "one 1,016,064-DOF frame, node-slab partition over the N GPUs (strong scaling), PCG solve only",
+                             "iterations": dst["iterations"], "ms": float(tt.item()),
+                             "us_per_iteration": float(tt.item()) / max(1, dst["iterations"]) * 1e3,
+                             "dof_per_s": (len(f0) - len(fixed0)) / (float(tt.item()) * 1e-3),
+                             "exchange": "peer memory (CUDA IPC over NVLink), fused into SpMV/update" if d.p2p else "NCCL"}
+        d.close()
+
     # end-to-end through the reference-shaped entry point, host buffers in / out
     e2e_steps = max(1, min(args.steps, 3))
     w = compat.BeamAnalysisB200(mesh, sec, bc, E, nu, device=local)
@@ -314,6 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rowblock", action="store_true", help="N>1: skip the row-block (strong-scaling) companion solve")
     ap.add_argument("--no-modal", action="store_true", help="skip the 20-mode modal measurement (N=1 only, ~45 s)")
     args = ap.parse_args()
     if args.impl == "reference":
