@@ -64,7 +64,10 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
       // three 16-byte loads per 48-byte row, two blocks in flight per thread.  Measured inside
       // PCG at 1M DOF on one B200 (profiles/r01_spmv_variants.log): unroll 2 -> 73 us, unroll 4 -> 85,
       // unroll 8 -> 78, unroll 1 -> 83; a sector-exact 32 B + 16 B split per row 10 % slower; two rows
-      // per thread with 256-bit loads 78-85 us; TMA-staged tiles (spmv_tma.cu) 99-133 us.
+      // per thread with 256-bit loads 78-85 us; TMA-staged tiles (spmv_tma.cu) 99-133 us.  Reading
+      // only the diagonal + upper blocks from HBM and the lower ones as L2-resident transposes cut
+      // DRAM traffic to 237 MB (ncu) but not the time (81.5 vs 82.3 us): the kernel is bound by the
+      // dependent colidx -> x gather steps per row, not by bandwidth.
 #pragma unroll UNR
       for (int b = b0; b < b1; ++b) {
         const int col = __ldg(colidx + b);
@@ -356,15 +359,10 @@ int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool
     return launch_spmv_tma(h, tma_variant, x, y, masked, dot_partials, scal_out);
   const int pstride = h->num_sms * 8;
   const int grid = vec_grid(h, n, kRowThreads);
-  static int unr = -1;
-  if (unr < 0) { const char* e = getenv("FEMB_SPMV_UNROLL"); unr = e ? atoi(e) : 2; }
-#define SPMV_U(BS, M, D, U)                                                                    \
-  bsr_spmv_kernel<BS, M, D, kRowThreads, U><<<grid, kRowThreads, 0, h->stream>>>(               \
+#define SPMV(BS, M, D)                                                                         \
+  bsr_spmv_kernel<BS, M, D, kRowThreads><<<grid, kRowThreads, 0, h->stream>>>(                  \
       h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, x, y, n, dot_partials, pstride,    \
       scal_out, h->flags.p, skip_node, node_list, reinterpret_cast<const P2PDev*>(p2p_dev))
-#define SPMV(BS, M, D)                                                                         \
-  do { if (BS == 6 && unr == 8) SPMV_U(BS, M, D, 8); else if (BS == 6 && unr == 2) SPMV_U(BS, M, D, 2); \
-       else if (BS == 6 && unr == 4) SPMV_U(BS, M, D, 4); else SPMV_U(BS, M, D, 2); } while (0)
   const bool dot = dot_partials != nullptr;
   if (h->bs == 6) {
     if (masked && dot) SPMV(6, true, true);
@@ -377,7 +375,6 @@ int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool
   }
 #undef SPMV
 #undef SPMV
-#undef SPMV_U
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   return FEMB_OK;
