@@ -17,22 +17,24 @@ FEMB_OK, FEMB_ERR_ARG, FEMB_ERR_CUDA, FEMB_ERR_NOT_CONVERGED, FEMB_ERR_SINGULAR,
 MAT_K, MAT_M = 0, 1
 SOLVER_AUTO, SOLVER_PCG, SOLVER_CHAIN, SOLVER_DENSE = 0, 1, 2, 3
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = 0, 1, 2
+OP_AUTO, OP_BSR, OP_EBE = 0, 1, 2
 
 
 class SolveOpts(C.Structure):
     _fields_ = [("method", C.c_int32), ("precond", C.c_int32), ("max_iter", C.c_int32),
                 ("check_every", C.c_int32), ("rtol", C.c_double), ("profile", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("op", C.c_int32)]
 
 
 class EigOpts(C.Structure):
-    _fields_ = [("k", C.c_int32), ("block", C.c_int32), ("max_iter", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("k", C.c_int32), ("block", C.c_int32), ("max_iter", C.c_int32), ("op", C.c_int32),
                 ("rtol", C.c_double), ("lambda_min", C.c_double)]
 
 
 class Stats(C.Structure):
     _fields_ = [("method_used", C.c_int32), ("iterations", C.c_int32), ("converged", C.c_int32),
                 ("spmv_launches", C.c_int32), ("kernel_launches", C.c_int32), ("spmv_timed", C.c_int32),
+                ("op_used", C.c_int32), ("reserved", C.c_int32),
                 ("rel_residual", C.c_double), ("device_ms", C.c_double), ("spmv_ms", C.c_double),
                 ("update_ms", C.c_double)]
 
@@ -70,6 +72,7 @@ SIGNATURES = {
     "femb_get_csr": (C.c_int, [_P, C.c_int, _I32, _I32, _F64]),
     "femb_set_bc": (C.c_int, [_P, C.c_int64, _P, _F64, _P]),
     "femb_solve_static": (C.c_int, [_P, C.POINTER(SolveOpts), C.c_int, _P, _P, C.POINTER(Stats)]),
+    "femb_apply_k": (C.c_int, [_P, C.c_int, C.c_int, _F64, _F64, C.POINTER(C.c_int32)]),
     "femb_modal": (C.c_int, [_P, C.POINTER(EigOpts), _P, _P, C.POINTER(C.c_int32), C.POINTER(Stats)]),
     "femb_frame_stress": (C.c_int, [_P, _P, _P]),
     "femb_frame_batch_solve": (C.c_int, [_P, C.c_int64, C.c_int64, _F64, _F64, C.c_double, C.c_double,

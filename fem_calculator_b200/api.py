@@ -64,8 +64,8 @@ class Handle:
         self.ndof = len(f)
 
     def solve_static(self, method=L.SOLVER_AUTO, precond=L.PRECOND_JACOBI, rtol=1e-12, max_iter=200000,
-                     check_every=50, minus_f=True, want_u=True, want_reactions=True, profile=False):
-        o = L.SolveOpts(method, precond, max_iter, check_every, rtol, int(profile), 0)
+                     check_every=50, minus_f=True, want_u=True, want_reactions=True, profile=False, op=L.OP_AUTO):
+        o = L.SolveOpts(method, precond, max_iter, check_every, rtol, int(profile), int(op))
         st = L.Stats()
         u = np.zeros(self.ndof) if want_u else None
         r = np.zeros(self.ndof) if want_reactions else None
@@ -74,8 +74,16 @@ class Handle:
         self._check(rc)
         return u, r, self.last_stats
 
-    def modal(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6):
-        o = L.EigOpts(k, block, max_iter, 0, rtol, lambda_min)
+    def apply_k(self, x, op=L.OP_AUTO, masked=False):
+        """(K x or K_ff x, operator used) — the product the Krylov loops are built on."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        used = C.c_int32()
+        self._check(self.lib.femb_apply_k(self._h, int(op), int(masked), x, y, C.byref(used)))
+        return y, used.value
+
+    def modal(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6, op=L.OP_AUTO):
+        o = L.EigOpts(k, block, max_iter, int(op), rtol, lambda_min)
         st = L.Stats()
         lam = np.zeros(k)
         phi = np.zeros((k, self.ndof))  # column-major (ndof,k) == row-major (k,ndof)

@@ -385,6 +385,26 @@ int femb_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, 
   return rc;
 }
 
+int femb_apply_k(femb_handle* h, int op, int masked, const double* x, double* y, int32_t* op_used) {
+  if (!h) return FEMB_ERR_ARG;
+  int rc = need(h, h->assembled && h->have_bc, "call femb_assemble and femb_set_bc first");
+  if (rc) return rc;
+  if (!x || !y) return fail(h, FEMB_ERR_ARG, "x / y is NULL");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  DevBuf<double> dx, dy;
+  FEMB_CUDA(h, upload(dx, x, (size_t)h->ndof, h->stream));
+  FEMB_CUDA(h, dy.alloc((size_t)h->ndof));
+  const bool ebe = ebe_selected(h, op);
+  if (op == FEMB_OP_EBE && !ebe) return fail(h, FEMB_ERR_ARG, "matrix-free operator not available for this mesh");
+  if (ebe) rc = launch_ebe(h, dx.p, dy.p, 1, masked != 0, nullptr, nullptr, nullptr, nullptr);
+  else rc = launch_spmv(h, dx.p, dy.p, masked != 0, nullptr);
+  if (rc) return rc;
+  FEMB_CUDA(h, download(y, dy.p, (size_t)h->ndof * 8, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (op_used) *op_used = ebe ? FEMB_OP_EBE : FEMB_OP_BSR;
+  return FEMB_OK;
+}
+
 int femb_modal(femb_handle* h, const femb_eig_opts* opts, double* lambda, double* phi,
                int32_t* n_found, femb_stats* stats) {
   if (!h) return FEMB_ERR_ARG;
@@ -515,6 +535,26 @@ int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, doubl
     FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < reps && !rc; ++i) rc = launch_assemble(h);
     FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  } else if (which == 3 || which == 4) {
+    if (!h->assembled || !h->have_bc) return fail(h, FEMB_ERR_ARG, "assemble + set_bc first");
+    if (!ebe_available(h)) return fail(h, FEMB_ERR_ARG, "matrix-free operator not available for this mesh");
+    const int nb = which == 3 ? 1 : 4;
+    *bytes = ebe_bytes(h, nb);
+    DevBuf<double> xin, yout;
+    FEMB_CUDA(h, xin.alloc((size_t)h->ndof * nb));
+    FEMB_CUDA(h, yout.alloc((size_t)h->ndof * nb));
+    FEMB_CUDA(h, cudaMemsetAsync(xin.p, 0, xin.bytes(), h->stream));
+    FEMB_CUDA(h, cudaMemcpyAsync(xin.p, h->b.p, (size_t)h->ndof * 8, cudaMemcpyDeviceToDevice, h->stream));
+    for (int i = 0; i < warm && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, nullptr, nullptr, nullptr, nullptr);
+    FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, nullptr, nullptr, nullptr, nullptr);
+    FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (rc) return rc;
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    float t3 = 0.f;
+    FEMB_CUDA(h, cudaEventElapsedTime(&t3, h->ev0, h->ev1));
+    *ms = (double)t3 / reps;
+    return FEMB_OK;
   } else if (which == 9) {
     if (!h->assembled) return fail(h, FEMB_ERR_ARG, "assemble first");
     // read-streaming ceiling: sum the K values (same bytes as one SpMV matrix pass) with 16-byte loads

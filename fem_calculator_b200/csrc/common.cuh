@@ -224,6 +224,12 @@ int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool
                      const void* p2p_dev = nullptr);
 int launch_spmv_tma(femb_handle* h, int variant, const double* x, double* y, bool masked, double* dot_partials,
                     double* scal_out);
+// matrix-free frame operator (ebe.cu)
+bool ebe_available(const femb_handle* h);
+bool ebe_selected(const femb_handle* h, int op);
+double ebe_bytes(const femb_handle* h, int nb);
+int launch_ebe(femb_handle* h, const double* x, double* y, int nb, bool masked, double* dot_partials,
+               double* scal_out, int* ticket, const int* done);
 int launch_reactions(femb_handle* h, bool minus_f, double* d_out);
 int setup_bc_vectors(femb_handle* h);
 int launch_frame_stress(femb_handle* h, const double* d_u, double* d_sigma);

@@ -242,6 +242,7 @@ static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const
     femb_stats s1;
     std::memset(&s1, 0, sizeof(s1));
     int rc = pcg_solve_multi(h, so, B, ws.n, nb, X, ws.n, &s1);
+    st->op_used = s1.op_used;
     st->iterations += s1.iterations;
     st->spmv_launches += s1.spmv_launches;
     return rc;
@@ -251,6 +252,7 @@ static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const
     std::memset(&s1, 0, sizeof(s1));
     int rc = pcg_solve_rhs(h, so, B + (size_t)q * ws.n, &s1);
     if (rc) return rc;
+    st->op_used = s1.op_used;
     st->iterations += s1.iterations;
     st->spmv_launches += s1.spmv_launches;
     FEMB_CUDA(h, cudaMemcpyAsync(X + (size_t)q * ws.n, h->x.p, ws.n * 8, cudaMemcpyDeviceToDevice, h->stream));
@@ -339,6 +341,7 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
   std::memset(&so, 0, sizeof(so));
   so.method = FEMB_SOLVER_PCG; so.precond = FEMB_PRECOND_JACOBI; so.max_iter = 200000; so.check_every = 50;
   so.rtol = std::min(1e-11, o.rtol * 1e-3);
+  so.op = o.op;
 
   const int mmax = (int)std::min<int64_t>(nfree, std::max(3 * k + 12, 40) + nb);   // basis capacity
   const int keep = (int)std::min<int64_t>(nfree, k + 2 * nb);                      // thick-restart size

@@ -473,6 +473,7 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   PcgPeek* peek = reinterpret_cast<PcgPeek*>(h->pinned);
   const int check = o.check_every > 0 ? o.check_every : 50;
   const bool prof = o.profile != 0;
+  const bool ebe = ebe_selected(h, o.op);   // matrix-free frame operator (ebe.cu) instead of the BSR SpMV
   std::vector<cudaEvent_t> evs;
   int spmv_launches = 0;
   int it = 0;
@@ -494,7 +495,9 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
         e0 = h->ev_pool[evs.size()]; e1 = h->ev_pool[evs.size() + 1]; e2 = h->ev_pool[evs.size() + 2];
         cudaEventRecord(e0, h->stream);
       }
-      rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
+      if (ebe) rc = launch_ebe(h, h->z.p, h->s.p, 1, true, h->partials.p, h->scal.p + Scal::PQ, h->flags.p + Flag::TICKET0,
+                               h->flags.p + Flag::DONE);
+      else rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
       if (timed) cudaEventRecord(e1, h->stream);
       if (rc) return rc;
       ++spmv_launches;
@@ -517,6 +520,7 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   done = peek->flags[Flag::DONE];
   if (st) {
     st->method_used = FEMB_SOLVER_PCG;
+    st->op_used = ebe ? FEMB_OP_EBE : FEMB_OP_BSR;
     st->iterations = peek->flags[Flag::ITERS];
     st->converged = (done == 1);
     st->spmv_launches = spmv_launches;
@@ -787,12 +791,20 @@ int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B,
   struct Peek { int32_t flags[MFlag::COUNT]; double scal[MScal::COUNT]; };
   Peek* peek = reinterpret_cast<Peek*>(h->pinned);
   const int check = o.check_every > 0 ? o.check_every : 50;
+  const bool ebe = ebe_selected(h, o.op);
   int it = 0, all = 0, spmm = 0;
   while (!all && it < max_iter) {
     const int batch = std::min(check, max_iter - it);
     for (int k = 0; k < batch; ++k, ++it) {
-      mpcg_spmm_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p,
-                                                                           h->mp.p, h->mq.p, n, part0, pstride, h->mscal.p, h->mflags.p);
+      if (ebe) {
+        rc = launch_ebe(h, h->mp.p, h->mq.p, kNB, true, part0, h->mscal.p + MScal::PQ, h->mflags.p + MFlag::TICKET0,
+                        h->mflags.p + MFlag::ALLDONE);
+        if (rc) return rc;
+        h->launches--;   // counted with the two update kernels below
+      } else {
+        mpcg_spmm_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p,
+                                                                             h->mp.p, h->mq.p, n, part0, pstride, h->mscal.p, h->mflags.p);
+      }
       mpcg_update_xr_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n,
                                                                                 max_iter, part1, pstride, h->mscal.p, h->mflags.p);
       mpcg_update_p_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->mr.p, h->mp.p, n, h->mscal.p, h->mflags.p);
@@ -817,6 +829,7 @@ int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B,
   }
   if (st) {
     st->method_used = FEMB_SOLVER_PCG;
+    st->op_used = ebe ? FEMB_OP_EBE : FEMB_OP_BSR;
     st->iterations = peek->flags[MFlag::ITERS];
     st->spmv_launches = spmm;
     st->converged = conv ? 1 : 0;

@@ -52,6 +52,16 @@ enum {
 /* femb_solve_opts.precond */
 enum { FEMB_PRECOND_NONE = 0, FEMB_PRECOND_JACOBI = 1, FEMB_PRECOND_BLOCK_JACOBI = 2 };
 
+/* femb_solve_opts.op / femb_eig_opts.op: how the Krylov loops apply K_ff.
+ *   BSR  the assembled block-CSR matrix (HBM-bound: 8 B per stored value and product);
+ *   EBE  matrix-free: every (node, element end) pair rebuilds its element record from the node
+ *        coordinates and the section row and applies the closed form of R^T k R
+ *        (BeamSolver.py:386-387) to the two end displacement vectors — frames whose members are
+ *        unique (no duplicate members, node degree <= 127), single GPU;
+ *   AUTO EBE where it applies, else BSR.
+ * K is assembled either way (Jacobi diagonal, reactions K u - f, CSR export).               */
+enum { FEMB_OP_AUTO = 0, FEMB_OP_BSR = 1, FEMB_OP_EBE = 2 };
+
 typedef struct {
   int32_t method;        /* FEMB_SOLVER_*                         default AUTO            */
   int32_t precond;       /* FEMB_PRECOND_*                        default JACOBI          */
@@ -59,14 +69,14 @@ typedef struct {
   int32_t check_every;   /* host polls convergence every N its    default 50              */
   double rtol;           /* stop at ||r||_2 <= rtol*||b||_2       default 1e-12           */
   int32_t profile;       /* P>0: time every P-th SpMV launch with CUDA events              */
-  int32_t reserved;
+  int32_t op;            /* FEMB_OP_*                             default AUTO            */
 } femb_solve_opts;
 
 typedef struct {
   int32_t k;             /* number of lowest modes wanted                                  */
   int32_t block;         /* Krylov block size 1..4 (0 = 4); >= multiplicity of eigenvalues  */
   int32_t max_iter;      /* default 5000                                                   */
-  int32_t reserved;
+  int32_t op;            /* FEMB_OP_* of the inner shift-invert solves   default AUTO             */
   double rtol;           /* ||K phi - lambda M phi|| <= rtol*||K phi||   default 1e-8      */
   double lambda_min;     /* keep eigenvalues > lambda_min (BeamSolver.py:448)  default 1e-6 */
 } femb_eig_opts;
@@ -78,6 +88,8 @@ typedef struct {
   int32_t spmv_launches;      /* SpMV kernel launches in this call                         */
   int32_t kernel_launches;    /* all kernel launches of this library in this call          */
   int32_t spmv_timed;         /* SpMV launches bracketed by events (opts.profile); modal: restarts */
+  int32_t op_used;            /* FEMB_OP_BSR or FEMB_OP_EBE for the Krylov loops of this call (0: none) */
+  int32_t reserved;
   double rel_residual;        /* final ||r||/||b||                                         */
   double device_ms;           /* CUDA-event time of the whole call on the handle's stream  */
   double spmv_ms;             /* summed device time of the timed SpMV launches              */
@@ -154,6 +166,12 @@ int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, cons
 int femb_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, double* u,
                       double* reactions, femb_stats* stats);
 
+/* y = K x (masked == 0: the un-eliminated matrix, the product behind K @ u at ReactionSolver.py:205)
+ * or y = K_ff x with identity rows on the fixed DOFs (masked != 0; x must be zero there), applied by
+ * the operator the Krylov loops would use for `op` (FEMB_OP_*).  x, y: (ndof) host arrays.
+ * Returns the operator actually used in *op_used (may be NULL).                                 */
+int femb_apply_k(femb_handle* h, int op, int masked, const double* x, double* y, int32_t* op_used);
+
 /* Lowest-k modes of K_ff phi = lambda M_ff phi: replaces inv(m_ff) @ k_ff + qr_algorithm
  * (BeamSolver.py:440-455,467-481).  lambda: (k) ascending, eigenvalues <= lambda_min
  * dropped (:448); phi: (ndof,k) column-major (phi[j*ndof + i]), M-normalised, zeros on
@@ -220,7 +238,8 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
  * Time `reps` back-to-back launches of one kernel with CUDA events on the handle's stream
  * (after `warm` untimed launches); *ms receives the mean per launch, *bytes the
  * algorithmic bytes of one launch.  which: 0 = BSR SpMV (masked
- * K_ff operator), 1 = fused element+assembly, 2 = one full PCG iteration.               */
+ * K_ff operator), 1 = fused element+assembly, 3 = matrix-free (EBE) operator, 4 = its 4-vector
+ * form, 9 = plain 16-byte read of the K values (streaming ceiling).                      */
 int femb_time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes);
 
 /* CUDA-event stopwatch on the handle's stream: stop = 0 records the start (after draining the
