@@ -213,7 +213,13 @@ static int ensure_symbolic(femb_handle* h) {
     FEMB_CUDA(h, upload(h->pair_node_rec, nrec, h->stream));
     FEMB_CUDA(h, upload(h->pair_tiles, tiles, h->stream));
     FEMB_CUDA(h, upload(h->pair_rec, rec, h->stream));
-    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));  // rec is a local
+    std::vector<int32_t> epair(np * 2);   // matrix-free operator: {other node, element << 1 | end}
+    for (size_t p = 0; p < np; ++p) {
+      epair[2 * p] = rec[4 * p + 1];
+      epair[2 * p + 1] = (int32_t)S.pair_code[p];
+    }
+    FEMB_CUDA(h, upload(h->ebe_pair, epair, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));  // rec / epair are locals
     h->pairs_dev_ok = true;
   }
   FEMB_CUDA(h, h->Kvals.alloc((size_t)S.nnzb * h->bs * h->bs));
@@ -243,6 +249,7 @@ int femb_assemble(femb_handle* h) {
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   h->assembled = true;
+  h->ebe_rec_valid = false;
   h->have_solution = false;
   h->chain_factored = h->dense_factored = false;
   return FEMB_OK;

@@ -115,6 +115,11 @@ struct femb_handle {
   femb::DevBuf<int32_t> pair_node_rec;  // (n_nodes,4) {first pair, pair count, diagonal block, 0}
   femb::DevBuf<int32_t> pair_tiles;     // (n_tiles,4) {first node, node count, first pair, pair count}
   bool pairs_dev_ok = false;        // pair records uploaded (frame fast path usable)
+  // matrix-free operator (ebe.cu): 8-byte pair list {other node, element << 1 | end} and the
+  // 128-byte element records (direction cosines + stiffness magnitudes), rebuilt after each assembly
+  femb::DevBuf<int32_t> ebe_pair;   // (n_pairs,2)
+  femb::DevBuf<double> ebe_rec;     // (n_elem,16)
+  bool ebe_rec_valid = false;
   femb::DevBuf<double> Kvals;      // (nnzb, bs, bs)
   femb::DevBuf<double> Mdiag;      // (n_nodes, bs, bs) frame only
   femb::DevBuf<unsigned long long> counters;  // device scalars: [0] skipped gauss points

@@ -37,6 +37,7 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   // skip_node != nullptr: block rows flagged there are left to a later launch (rows that read
   // ghost columns wait for the halo); node_list != nullptr: row g belongs to node_list[g / BS].
   static_assert(BS == 6 || BS == 3, "block size");
+  pdl_wait();
   if (DOT && flags[Flag::DONE]) return;
   if (DOT && p2p) {
     // fused peer-memory mode: the neighbours' update kernels stored the ghost entries of x straight
@@ -249,6 +250,7 @@ pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s,
                   double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
                   int64_t n, int parity, int first, int max_iter, double* partials, int pstride, double* scal,
                   int* flags) {
+  pdl_wait();
   if (flags[Flag::DONE]) return;
   const double delta = scal[Scal::PQ];
   const double gamma = scal[Scal::RZ0 + (parity ^ 1)];
@@ -317,6 +319,7 @@ pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s,
       rz += rg * zg; rr += rg * rg;
     }
   }
+  pdl_trigger();
   double mine[2], tot[2];
   mine[0] = rz;
   mine[1] = rr;
@@ -501,7 +504,7 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
       if (timed) cudaEventRecord(e1, h->stream);
       if (rc) return rc;
       ++spmv_launches;
-#define UPD(BS, BJ) pcg_update_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, it == 0 ? 1 : 0, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
+#define UPD(BS, BJ) launch_pdl(pcg_update_kernel<BS, kRowThreads, BJ>, occ_grid(h, pcg_update_kernel<BS, kRowThreads, BJ>, BJ ? n : (n + 1) / 2, kRowThreads), kRowThreads, h->stream, h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, it == 0 ? 1 : 0, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
       if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
       else { if (blockj) UPD(3, true); else UPD(3, false); }
 #undef UPD
@@ -650,6 +653,7 @@ mpcg_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
                  const double* __restrict__ p, double* __restrict__ qv, int64_t n,
                  double* partials, int pstride, double* scal, int* flags) {
+  pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
   double dot[kNB] = {0, 0, 0, 0};
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
@@ -690,6 +694,7 @@ __global__ void __launch_bounds__(THREADS)
 mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict__ p, const double* __restrict__ qv,
                       double* __restrict__ x, double* __restrict__ r, int64_t n, int max_iter,
                       double* partials, int pstride, double* scal, int* flags) {
+  pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
   double alpha[kNB];
   bool bad = false;
@@ -712,6 +717,7 @@ mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict_
     rz[0] += rv.x * d * rv.x; rz[1] += rv.y * d * rv.y; rz[2] += rv.z * d * rv.z; rz[3] += rv.w * d * rv.w;
     rr[0] += rv.x * rv.x; rr[1] += rv.y * rv.y; rr[2] += rv.z * rv.z; rr[3] += rv.w * rv.w;
   }
+  pdl_trigger();
   double mine[2 * kNB], tot[2 * kNB];
 #pragma unroll
   for (int q = 0; q < kNB; ++q) { mine[q] = rz[q]; mine[kNB + q] = rr[q]; }
@@ -741,6 +747,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 mpcg_update_p_kernel(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ p, int64_t n,
                      const double* scal, const int* flags) {
+  pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
   double beta[kNB];
 #pragma unroll
@@ -792,6 +799,8 @@ int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B,
   Peek* peek = reinterpret_cast<Peek*>(h->pinned);
   const int check = o.check_every > 0 ? o.check_every : 50;
   const bool ebe = ebe_selected(h, o.op);
+  const int grid_xr = occ_grid(h, mpcg_update_xr_kernel<kRowThreads>, n, kRowThreads);
+  const int grid_mm = occ_grid(h, mpcg_spmm_kernel<kRowThreads>, n, kRowThreads);
   int it = 0, all = 0, spmm = 0;
   while (!all && it < max_iter) {
     const int batch = std::min(check, max_iter - it);
@@ -802,12 +811,12 @@ int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B,
         if (rc) return rc;
         h->launches--;   // counted with the two update kernels below
       } else {
-        mpcg_spmm_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p,
+        mpcg_spmm_kernel<kRowThreads><<<grid_mm, kRowThreads, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p,
                                                                              h->mp.p, h->mq.p, n, part0, pstride, h->mscal.p, h->mflags.p);
       }
-      mpcg_update_xr_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n,
-                                                                                max_iter, part1, pstride, h->mscal.p, h->mflags.p);
-      mpcg_update_p_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->mr.p, h->mp.p, n, h->mscal.p, h->mflags.p);
+      launch_pdl(mpcg_update_xr_kernel<kRowThreads>, grid_xr, kRowThreads, h->stream, h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n,
+                 max_iter, part1, pstride, h->mscal.p, h->mflags.p);
+      launch_pdl(mpcg_update_p_kernel<kRowThreads>, gridv, kRowThreads, h->stream, h->Dinv.p, h->mr.p, h->mp.p, n, h->mscal.p, h->mflags.p);
       h->launches += 3;
       ++spmm;
     }
