@@ -4,18 +4,20 @@
 Metric (BASELINE.json): DOF/s of the static solve at ~1M DOF.  One "step" = one pass of the
 hot path over the synthetic BASELINE config-3 frame (56x56x54 lattice, 169,344 nodes,
 1,016,064 DOF, 498,848 elements, box/C/L sections, 5 % seeded node jitter):
-    fused element+assembly  ->  BC mask / RHS  ->  Jacobi-type PCG to ||r||/||b|| <= 1e-12
-    ->  reaction recovery K u - f.
+    fused element+assembly  ->  BC mask / RHS  ->  Jacobi-PCG to ||r||/||b|| <= 1e-12 with the
+    matrix-free (element-by-element) frame operator  ->  reaction recovery K u - f (assembled K).
 `value`  : free DOFs / step, device-timed (CUDA events on the library's stream), mesh and
-           loads resident in HBM.  Every step re-assembles a matrix of 359 MB (> 126 MB L2)
-           and streams it ~7k times, so inputs are larger than L2 (no flush needed).
+           loads resident in HBM.  Every step re-assembles the 359 MB matrix (> 126 MB L2), which
+           evicts the solver's working set between steps (no extra flush needed).
 `e2e`    : the same metric through the reference-shaped entry point
            (compat.BeamAnalysisB200.run_simulation: host numpy arrays in, u / reactions /
            stresses out, symbolic analysis + all H2D/D2H inside the timed region).
-`roofline`: the dominant kernel (BSR SpMV, ~78 % of the step), CUDA-event-timed inside the
+`roofline`: the dominant kernel (the operator kernel of the PCG), CUDA-event-timed inside the
            timed steps (every 8th launch, events from a pre-created pool), against
-           MEASURED_PEAKS.json.  `modal` (N=1): device ms of the 20-mode modal solve of the same
-           frame; `assembly`: the fused element+assembly kernel (elements/s).
+           MEASURED_PEAKS.json; `roofline_bsr_spmv`: the assembled-matrix SpMV the same solve would
+           use without the matrix-free operator (one extra solve after the timed region);
+           `modal` (N=1): device ms of the 20-mode modal solve of the same frame; `assembly`: the
+           fused element+assembly kernel (elements/s).
 N > 1 (torchrun): independent load cases of the same frame, one per GPU (weak scaling, no
 data-path collective; north_star: "independent load cases ... dealt out one batch per GPU").
 `--impl reference`: the CPU oracle port of the reference path on the host cores.
@@ -166,7 +168,8 @@ def config_dict(parallel="1 GPU"):
     return {"workload": "BASELINE configs[2]: synthetic gmsh-like 3D space frame, 56x56x54 lattice, 169,344 nodes / "
                         "1,016,064 DOF (997,248 free), 498,848 Timoshenko elements, box/C/L sections, base fixed, "
                         "loads on all top nodes; static solve K u = F (PCG rtol 1e-12) with reaction recovery",
-            "step": "fused element+assembly -> BC -> PCG -> reactions", "l2": "inputs larger than L2 (359 MB matrix)",
+            "step": "fused element+assembly -> BC -> PCG (matrix-free operator) -> reactions",
+            "l2": "every step re-assembles the 359 MB K (> 126 MB L2), evicting the CG working set (~80 MB) between steps",
             "parallelism": parallel}
 
 
@@ -233,21 +236,41 @@ def run_gpu(args):
 
     # per-kernel roofline numbers (algorithmic bytes: DESIGN.md §kernels)
     peak, peak_src = peaks()
+    ebe = stats[-1].get("op_used") == L.OP_EBE
     _, spmv_bytes = m.time_kernel(0, 1, 1)
     asm_ms, asm_bytes = m.time_kernel(1, 3, 20)
     spmv_b2b_ms, _ = m.time_kernel(0, 3, 50)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_spmv_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
-    roofline = {"kernel": "bsr_spmv_kernel<6,masked,dot,192,2> (inside PCG, every 8th launch timed)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "share_of_step": spmv_share,
-                "traffic": traffic}
+    op_bytes = spmv_bytes
+    op_b2b_ms = spmv_b2b_ms
+    if ebe:
+        op_b2b_ms, op_bytes = m.time_kernel(3, 3, 50)
+
+    def _traffic(name):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            try:
+                return json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                return None
+        return None
+
+    achieved = op_bytes / (spmv_ms * 1e-3) / 1e9
+    if ebe:
+        roofline = {"kernel": "frame_ebe_node_kernel<1,1,2,masked,dot,128,4> — matrix-free frame operator y = K_ff x "
+                              "(inside PCG, every 8th launch timed)",
+                    "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": achieved / peak, "bytes_per_launch": op_bytes, "ms_per_launch": spmv_ms,
+                    "share_of_step": spmv_share, "traffic": _traffic("ncu_ebe_traffic.json"),
+                    "note": "algorithmic bytes are the kernel's own compulsory traffic (16 B/pair + node records + "
+                            "coordinates + x + y + mask = 40 MB), 9x fewer than the 359 MB the assembled SpMV streams for "
+                            "the same product; the kernel is FP64-issue / gather-latency bound, not HBM bound (ncu: FP64 "
+                            "pipe 41 %, DRAM 13 % of peak) — see roofline_bsr_spmv for the HBM-bound form of the product",
+                    "equivalent_bsr_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9}
+    else:
+        roofline = {"kernel": "bsr_spmv_kernel<6,masked,dot,192,2> (inside PCG, every 8th launch timed)", "bound": "hbm",
+                    "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                    "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "share_of_step": spmv_share,
+                    "traffic": _traffic("ncu_spmv_traffic.json")}
     extra = {
         "pcg": {"iterations": iters, "ms_per_iteration": stats[-1]["device_ms"] / max(1, iters),
                 "rel_residual": stats[-1]["rel_residual"], "precond": "jacobi", "form": "Chronopoulos-Gear, 2 kernels/iteration",
@@ -257,7 +280,22 @@ def run_gpu(args):
                      "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": asm_bytes},
         "spmv_back_to_back": {"ms": spmv_b2b_ms, "achieved_gbs": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9,
                               "frac": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9 / peak},
+        "operator_back_to_back_ms": op_b2b_ms,
     }
+    extra["pcg"]["operator"] = "matrix-free (EBE)" if ebe else "assembled BSR"
+    extra["pcg"]["update_kernel_frac"] = (extra["pcg"]["update_kernel_gbs"] / peak) if extra["pcg"]["update_kernel_gbs"] else None
+    if ebe and world == 1:
+        # the HBM-bound form of the same product: one solve with the assembled BSR operator, outside the timed region
+        _, _, bst = m.solve_static(profile=8, op=L.OP_BSR, **solve_kw)
+        nb_t = max(1, bst["spmv_timed"])
+        b_ms = bst["spmv_ms"] / nb_t
+        b_ach = spmv_bytes / (b_ms * 1e-3) / 1e9
+        extra["roofline_bsr_spmv"] = {"kernel": "bsr_spmv_kernel<6,masked,dot,192,2> (inside a PCG with op = BSR, every 8th launch timed)",
+                                      "bound": "hbm", "achieved": b_ach, "peak": peak, "unit": "GB/s", "frac": b_ach / peak,
+                                      "bytes_per_launch": spmv_bytes, "ms_per_launch": b_ms,
+                                      "traffic": _traffic("ncu_spmv_traffic.json"),
+                                      "pcg_ms": bst["device_ms"], "pcg_iterations": bst["iterations"],
+                                      "dof_per_s_pcg_only": n_free / (bst["device_ms"] * 1e-3)}
     if world == 1 and not args.no_modal:
         # second headline metric: ms per 20-mode modal solve at 1M DOF (device time of femb_modal)
         lam, _, mst = m.modal(k=20, rtol=1e-8)
@@ -265,6 +303,7 @@ def run_gpu(args):
                           "lockstep_pcg_iterations": mst["iterations"], "matrix_passes": mst["spmv_launches"],
                           "rel_residual": mst["rel_residual"], "omega_min_rad_s": float(np.sqrt(lam[0])),
                           "omega_max_rad_s": float(np.sqrt(lam[-1])),
+                          "operator": "matrix-free (EBE), 4 vectors per pass" if mst.get("op_used") == L.OP_EBE else "assembled BSR SpMM",
                           "method": "block shift-invert Krylov (block 4), 4-RHS lockstep Jacobi-PCG as K^-1"}
     m.close()
 

@@ -542,19 +542,23 @@ int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, doubl
     FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < reps && !rc; ++i) rc = launch_assemble(h);
     FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-  } else if (which == 3 || which == 4) {
+  } else if (which == 3 || which == 4 || which == 5) {
+    // 3 / 4: matrix-free operator on 1 / 4 vectors; 5: on 1 vector with the fused (x, y) reduction
     if (!h->assembled || !h->have_bc) return fail(h, FEMB_ERR_ARG, "assemble + set_bc first");
     if (!ebe_available(h)) return fail(h, FEMB_ERR_ARG, "matrix-free operator not available for this mesh");
-    const int nb = which == 3 ? 1 : 4;
+    const int nb = which == 4 ? 4 : 1;
+    double* part = which == 5 ? h->partials.p : nullptr;
+    double* sc = which == 5 ? h->scal.p + 7 : nullptr;
+    int* tick = which == 5 ? h->flags.p + 4 : nullptr;   // Flag::TICKET2
     *bytes = ebe_bytes(h, nb);
     DevBuf<double> xin, yout;
     FEMB_CUDA(h, xin.alloc((size_t)h->ndof * nb));
     FEMB_CUDA(h, yout.alloc((size_t)h->ndof * nb));
     FEMB_CUDA(h, cudaMemsetAsync(xin.p, 0, xin.bytes(), h->stream));
     FEMB_CUDA(h, cudaMemcpyAsync(xin.p, h->b.p, (size_t)h->ndof * 8, cudaMemcpyDeviceToDevice, h->stream));
-    for (int i = 0; i < warm && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, nullptr, nullptr, nullptr, nullptr);
+    for (int i = 0; i < warm && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, part, sc, tick, nullptr);
     FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    for (int i = 0; i < reps && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, nullptr, nullptr, nullptr, nullptr);
+    for (int i = 0; i < reps && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, part, sc, tick, nullptr);
     FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     if (rc) return rc;
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));

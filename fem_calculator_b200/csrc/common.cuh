@@ -133,6 +133,7 @@ struct femb_handle {
   femb::DevBuf<double> f, u0;       // load vector, prescribed values
   femb::DevBuf<double> b, x, r, z, p, q, s;
   femb::DevBuf<double> Dinv;        // block-Jacobi inverse (n_nodes,bs,bs) or Jacobi (ndof)
+  femb::DevBuf<double> r2, q2, fpartials;   // fused one-kernel-per-iteration PCG (fused_pcg.cu): ping-pong r / q, partial sums
   femb::DevBuf<double> mx, mr, mp, mq, mpartials, mscal;   // multi-RHS PCG (interleaved by right-hand side)
   femb::DevBuf<int32_t> mflags;
   femb::DevBuf<double> partials;    // reduction scratch
@@ -235,6 +236,9 @@ bool ebe_selected(const femb_handle* h, int op);
 double ebe_bytes(const femb_handle* h, int nb);
 int launch_ebe(femb_handle* h, const double* x, double* y, int nb, bool masked, double* dot_partials,
                double* scal_out, int* ticket, const int* done);
+bool fused_pcg_applicable(const femb_handle* h, const femb_solve_opts& o);
+int pcg_fused(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
+int setup_precond_public(femb_handle* h, int mode);
 int launch_reactions(femb_handle* h, bool minus_f, double* d_out);
 int setup_bc_vectors(femb_handle* h);
 int launch_frame_stress(femb_handle* h, const double* d_u, double* d_sigma);

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "ebe.cuh"
 #include "elements.cuh"
 #include "pcg_common.cuh"
 
@@ -32,61 +33,6 @@ struct EbeDev {
   const int4* tiles;      // (n_tiles) {first node, node count, first pair, pair count}
   int n_tiles;
 };
-
-// stiffness part of the element record (the lumped-mass terms of FrameRec are dead code here)
-struct KRec {
-  double t[3], n1[3], n2[3];
-  double ax, tor, k11z, k11y, c12z, c12y, k23z, k23y, d22z, d22y;   // c12 = s_a*k12, d22 = k22 - k23
-};
-
-__device__ __forceinline__ void krec_from(const FrameParams& P, const FrameIn& in, int a, KRec& k) {
-  FrameRec R;
-  frame_record_from(P, in, R);
-  const double sa = a ? -1.0 : 1.0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { k.t[i] = R.t[i]; k.n1[i] = R.n1[i]; k.n2[i] = R.n2[i]; }
-  k.ax = R.ax; k.tor = R.tor; k.k11z = R.k11z; k.k11y = R.k11y;
-  k.c12z = sa * R.k12z; k.c12y = sa * R.k12y;
-  k.k23z = R.k23z; k.k23y = R.k23y;
-  k.d22z = R.k22z - R.k23z; k.d22y = R.k22y - R.k23y;
-}
-
-__device__ __forceinline__ double dot3(const double* a, double x, double y, double z) {
-  return a[0] * x + a[1] * y + a[2] * z;
-}
-
-// out[0..5] = K_e[a][a] ua + K_e[a][1-a] uo in global axes.  With d = translations, th = rotations
-// and the projections on (t, n1, n2) the two block rows of elements.cuh collapse to
-//   force : ax (t.dd) t + [k11z (n1.dd) + c12z (n2.ts)] n1 + [k11y (n2.dd) - c12y (n1.ts)] n2
-//   moment: tor (t.td) t + [-c12y (n2.dd) + k23y (n1.ts) + d22y (n1.ta)] n1
-//                        + [ c12z (n1.dd) + k23z (n2.ts) + d22z (n2.ta)] n2
-// where dd = d_a - d_o, td = th_a - th_o, ts = th_a + th_o, ta = th_a.
-__device__ __forceinline__ void ebe_apply(const KRec& k, const double* ua, const double* uo, double* out) {
-  const double ddx = ua[0] - uo[0], ddy = ua[1] - uo[1], ddz = ua[2] - uo[2];
-  const double tdx = ua[3] - uo[3], tdy = ua[4] - uo[4], tdz = ua[5] - uo[5];
-  const double tsx = ua[3] + uo[3], tsy = ua[4] + uo[4], tsz = ua[5] + uo[5];
-  const double dt = dot3(k.t, ddx, ddy, ddz), d1 = dot3(k.n1, ddx, ddy, ddz), d2 = dot3(k.n2, ddx, ddy, ddz);
-  const double tt = dot3(k.t, tdx, tdy, tdz);
-  const double s1 = dot3(k.n1, tsx, tsy, tsz), s2 = dot3(k.n2, tsx, tsy, tsz);
-  const double a1 = dot3(k.n1, ua[3], ua[4], ua[5]), a2 = dot3(k.n2, ua[3], ua[4], ua[5]);
-  const double ft = k.ax * dt;
-  const double f1 = k.k11z * d1 + k.c12z * s2;
-  const double f2 = k.k11y * d2 - k.c12y * s1;
-  const double mt = k.tor * tt;
-  const double m1 = k.k23y * s1 + k.d22y * a1 - k.c12y * d2;
-  const double m2 = k.k23z * s2 + k.d22z * a2 + k.c12z * d1;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    out[i] = ft * k.t[i] + f1 * k.n1[i] + f2 * k.n2[i];
-    out[3 + i] = mt * k.t[i] + m1 * k.n1[i] + m2 * k.n2[i];
-  }
-}
-
-__device__ __forceinline__ void load6(const double* __restrict__ x, int node, double* u) {
-  const double2* p = reinterpret_cast<const double2*>(x + (size_t)node * 6);
-  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
-}
 
 // NB = 1: plain vectors x[g], y[g].  NB = 4: four vectors interleaved by right-hand side,
 // x[g*4 + q] (the multi-RHS PCG layout of solver.cu).
@@ -640,7 +586,7 @@ bool ebe_selected(const femb_handle* h, int op) {
     if (e && (e[0] == 'b' || e[0] == 'B')) env = FEMB_OP_BSR;
     if (e && (e[0] == 'e' || e[0] == 'E')) env = FEMB_OP_EBE;
   }
-  if (env) op = env;
+  if (env && op != FEMB_OP_EBE_FUSED) op = env;
   if (op == FEMB_OP_BSR) return false;
   return ebe_available(h);
 }

@@ -1,0 +1,105 @@
+// Device pieces of the matrix-free frame operator shared by ebe.cu (operator kernels) and
+// fused_pcg.cu (one-kernel-per-iteration PCG): the stiffness part of the element record and the
+// closed form of K_e[a][a] ua + K_e[a][1-a] uo (BeamSolver.py:386-387, 646-660).
+#pragma once
+
+#include "common.cuh"
+#include "elements.cuh"
+
+namespace femb {
+
+// stiffness part of the element record (the lumped-mass terms of FrameRec are dead code here)
+struct KRec {
+  double t[3], n1[3], n2[3];
+  double ax, tor, k11z, k11y, c12z, c12y, k23z, k23y, d22z, d22y;   // c12 = s_a*k12, d22 = k22 - k23
+};
+
+// Lean form of frame_record_from (elements.cuh) for the operator: only the stiffness magnitudes
+// that ebe_apply needs, with the Timoshenko algebra reduced per bending plane to
+//   psi = 1/(1+phi) = den/(den + 12 EI)   (den = G kappa A L^2; den <= 0 -> psi = 1, BeamSolver.py:647-648)
+//   e = EI/L,  w = psi e:   k23 = (2-phi)/(1+phi) e = 3w - e,   k22 - k23 = 2e,
+//   k12 = 6 w / L,  k11 = 2 k12 / L                                         (BeamSolver.py:649-652)
+// and n2 = t x n1 (n1.z = 0 in both branches of BeamSolver.py:380-384).  ~75 FP64 instructions
+// instead of ~100; values agree with the assembled K to a few ulp (tests/test_gpu_operator.py).
+__device__ __forceinline__ void krec_from(const FrameParams& P, const FrameIn& in, int a, KRec& k) {
+  const double dx = in.dx, dy = in.dy, dz = in.dz;
+  const double L2 = dx * dx + dy * dy + dz * dz;
+  const double iL = rsqrt(L2);
+  const double cx = dx * iL, cy = dy * iL, cz = dz * iL;
+  const double h2 = cx * cx + cy * cy;
+  if (h2 < 1e-12) {                                  // vertical member (eps = 1e-6)
+    const double s = cz > 0.0 ? 1.0 : -1.0;
+    k.t[0] = 0.0; k.t[1] = 0.0; k.t[2] = s;
+    k.n1[0] = 0.0; k.n1[1] = 1.0; k.n1[2] = 0.0;
+    k.n2[0] = -s; k.n2[1] = 0.0; k.n2[2] = 0.0;
+  } else {
+    const double iD = rsqrt(h2);
+    k.t[0] = cx; k.t[1] = cy; k.t[2] = cz;
+    k.n1[0] = -cy * iD; k.n1[1] = cx * iD; k.n1[2] = 0.0;
+    k.n2[0] = -cz * k.n1[1]; k.n2[1] = cz * k.n1[0]; k.n2[2] = cx * k.n1[1] - cy * k.n1[0];
+  }
+  const double iL1 = (L2 > 0.0) ? iL : 0.0;          // every term is guarded by L > 0 (BeamSolver.py:649-655)
+  const double sa = a ? -1.0 : 1.0;
+  const double E = P.E, G = P.G;
+  k.ax = in.A * E * iL1;
+  k.tor = G * in.J * iL1;
+  {
+    const double EI = E * in.Iy;                     // local x-y bending uses I_y
+    const double den = G * in.ky * in.A * L2;
+    const double e = EI * iL1;
+    double w = e;
+    if (den > 0.0) w = e * (den / (den + 12.0 * EI));
+    const double k12 = 6.0 * w * iL1;
+    k.k23z = 3.0 * w - e; k.d22z = 2.0 * e; k.c12z = sa * k12; k.k11z = 2.0 * k12 * iL1;
+  }
+  {
+    const double EI = E * in.Ix;                     // local x-z bending uses I_x
+    const double den = G * in.kz * in.A * L2;
+    const double e = EI * iL1;
+    double w = e;
+    if (den > 0.0) w = e * (den / (den + 12.0 * EI));
+    const double k12 = 6.0 * w * iL1;
+    k.k23y = 3.0 * w - e; k.d22y = 2.0 * e; k.c12y = sa * k12; k.k11y = 2.0 * k12 * iL1;
+  }
+}
+
+__device__ __forceinline__ double dot3(const double* a, double x, double y, double z) {
+  return a[0] * x + a[1] * y + a[2] * z;
+}
+
+// out[0..5] = K_e[a][a] ua + K_e[a][1-a] uo in global axes.  With d = translations, th = rotations
+// and the projections on (t, n1, n2) the two block rows of elements.cuh collapse to
+//   force : ax (t.dd) t + [k11z (n1.dd) + c12z (n2.ts)] n1 + [k11y (n2.dd) - c12y (n1.ts)] n2
+//   moment: tor (t.td) t + [-c12y (n2.dd) + k23y (n1.ts) + d22y (n1.ta)] n1
+//                        + [ c12z (n1.dd) + k23z (n2.ts) + d22z (n2.ta)] n2
+// where dd = d_a - d_o, td = th_a - th_o, ts = th_a + th_o, ta = th_a.
+__device__ __forceinline__ void ebe_apply(const KRec& k, const double* ua, const double* uo, double* out) {
+  const double ddx = ua[0] - uo[0], ddy = ua[1] - uo[1], ddz = ua[2] - uo[2];
+  const double tdx = ua[3] - uo[3], tdy = ua[4] - uo[4], tdz = ua[5] - uo[5];
+  const double tsx = ua[3] + uo[3], tsy = ua[4] + uo[4], tsz = ua[5] + uo[5];
+  // n1.z == 0 in both branches of the direction-cosine matrix: its products are left out
+  const double dt = dot3(k.t, ddx, ddy, ddz), d1 = k.n1[0] * ddx + k.n1[1] * ddy, d2 = dot3(k.n2, ddx, ddy, ddz);
+  const double tt = dot3(k.t, tdx, tdy, tdz);
+  const double s1 = k.n1[0] * tsx + k.n1[1] * tsy, s2 = dot3(k.n2, tsx, tsy, tsz);
+  const double a1 = k.n1[0] * ua[3] + k.n1[1] * ua[4], a2 = dot3(k.n2, ua[3], ua[4], ua[5]);
+  const double ft = k.ax * dt;
+  const double f1 = k.k11z * d1 + k.c12z * s2;
+  const double f2 = k.k11y * d2 - k.c12y * s1;
+  const double mt = k.tor * tt;
+  const double m1 = k.k23y * s1 + k.d22y * a1 - k.c12y * d2;
+  const double m2 = k.k23z * s2 + k.d22z * a2 + k.c12z * d1;
+  out[0] = ft * k.t[0] + f1 * k.n1[0] + f2 * k.n2[0];
+  out[1] = ft * k.t[1] + f1 * k.n1[1] + f2 * k.n2[1];
+  out[2] = ft * k.t[2] + f2 * k.n2[2];
+  out[3] = mt * k.t[0] + m1 * k.n1[0] + m2 * k.n2[0];
+  out[4] = mt * k.t[1] + m1 * k.n1[1] + m2 * k.n2[1];
+  out[5] = mt * k.t[2] + m2 * k.n2[2];
+}
+
+__device__ __forceinline__ void load6(const double* __restrict__ x, int node, double* u) {
+  const double2* p = reinterpret_cast<const double2*>(x + (size_t)node * 6);
+  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
+}
+
+}  // namespace femb

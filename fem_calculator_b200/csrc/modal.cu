@@ -245,6 +245,11 @@ static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const
     st->op_used = s1.op_used;
     st->iterations += s1.iterations;
     st->spmv_launches += s1.spmv_launches;
+    // (Tried: a Galerkin start X0 = OPV (OPV^T MV)^-1 OPV^T B from the solves already done, to take the
+    // lowest modes out of the residual.  At 1M DOF the 2-norm of the projected right-hand side GROWS
+    // 3-100x and every block still needs ~7,300 lockstep iterations (gpurun_out/r1_gal_modal2.log):
+    // CG on this operator is not held back by the few lowest modes but by the wide axial / bending
+    // stiffness spread, so the idea was dropped.)
     return rc;
   }
   for (int q = 0; q < nb; ++q) {

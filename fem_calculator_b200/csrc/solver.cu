@@ -459,6 +459,7 @@ int pcg_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, f
 }
 
 static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
+  if (fused_pcg_applicable(h, o)) return pcg_fused(h, o, d_b, st);
   const int64_t n = h->ndof;
   const int gridv = vec_grid(h, n, kRowThreads);
   const int pstride = h->num_sms * 8;

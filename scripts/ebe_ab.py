@@ -17,7 +17,7 @@ for which, name in ((0, "bsr spmv"), (3, "ebe x1"), (4, "ebe x4")):
     ms, by = m.time_kernel(which, 5, 100)
     print(f"{name}: b2b {ms*1e3:.1f} us, {by/1e6:.1f} MB algorithmic -> {by/ms/1e6:.0f} GB/s")
 us = {}
-for op, name in ((L.OP_BSR, "bsr"), (L.OP_EBE, "ebe")):
+for op, name in ((L.OP_BSR, "bsr"), (L.OP_EBE_FUSED, "ebe-fused"), (L.OP_EBE, "ebe")):
     for rep in range(2):
         u, r, st = m.solve_static(method=L.SOLVER_PCG, rtol=1e-12, want_reactions=False, op=op)
     us[name] = u
@@ -25,7 +25,7 @@ for op, name in ((L.OP_BSR, "bsr"), (L.OP_EBE, "ebe")):
           f"res {st['rel_residual']:.2e} DOF/s {(len(f)-len(fixed))/(st['device_ms']/1e3):.3e}")
     u, r, st = m.solve_static(method=L.SOLVER_PCG, rtol=1e-12, want_u=False, want_reactions=False, op=op, profile=8)
     k = max(1, st["spmv_timed"])
-    print(f"   in-loop ({k} timed): operator {st['spmv_ms']/k*1e3:.1f} us, update {st['update_ms']/k*1e3:.1f} us")
+    print(f"   in-loop ({k} timed): operator {st['spmv_ms']/k*1e3:.1f} us, update {st['update_ms']/k*1e3:.1f} us, {st['device_ms']/st['iterations']*1e3:.2f} us/it")
 print("||u_ebe - u_bsr|| / ||u_bsr|| =", np.linalg.norm(us["ebe"] - us["bsr"]) / np.linalg.norm(us["bsr"]))
 if os.environ.get("MODAL", "1") == "1":
     for op, name in ((L.OP_EBE, "ebe"),) + (((L.OP_BSR, "bsr"),) if os.environ.get("MODAL_BSR") else ()):
