@@ -213,13 +213,7 @@ static int ensure_symbolic(femb_handle* h) {
     FEMB_CUDA(h, upload(h->pair_node_rec, nrec, h->stream));
     FEMB_CUDA(h, upload(h->pair_tiles, tiles, h->stream));
     FEMB_CUDA(h, upload(h->pair_rec, rec, h->stream));
-    std::vector<int32_t> epair(np * 2);   // matrix-free operator: {other node, element << 1 | end}
-    for (size_t p = 0; p < np; ++p) {
-      epair[2 * p] = rec[4 * p + 1];
-      epair[2 * p + 1] = (int32_t)S.pair_code[p];
-    }
-    FEMB_CUDA(h, upload(h->ebe_pair, epair, h->stream));
-    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));  // rec / epair are locals
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));  // rec is a local
     h->pairs_dev_ok = true;
   }
   FEMB_CUDA(h, h->Kvals.alloc((size_t)S.nnzb * h->bs * h->bs));
@@ -249,7 +243,6 @@ int femb_assemble(femb_handle* h) {
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   h->assembled = true;
-  h->ebe_rec_valid = false;
   h->have_solution = false;
   h->chain_factored = h->dense_factored = false;
   return FEMB_OK;
@@ -403,7 +396,7 @@ int femb_apply_k(femb_handle* h, int op, int masked, const double* x, double* y,
   FEMB_CUDA(h, dy.alloc((size_t)h->ndof));
   const bool ebe = ebe_selected(h, op);
   if (op == FEMB_OP_EBE && !ebe) return fail(h, FEMB_ERR_ARG, "matrix-free operator not available for this mesh");
-  if (ebe) rc = launch_ebe(h, dx.p, dy.p, 1, masked != 0, nullptr, nullptr, nullptr, nullptr);
+  if (ebe) rc = launch_ebe(h, dx.p, dy.p, 1, masked != 0, nullptr, nullptr, nullptr, nullptr, nullptr);
   else rc = launch_spmv(h, dx.p, dy.p, masked != 0, nullptr);
   if (rc) return rc;
   FEMB_CUDA(h, download(y, dy.p, (size_t)h->ndof * 8, h->stream));
@@ -556,9 +549,9 @@ int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, doubl
     FEMB_CUDA(h, yout.alloc((size_t)h->ndof * nb));
     FEMB_CUDA(h, cudaMemsetAsync(xin.p, 0, xin.bytes(), h->stream));
     FEMB_CUDA(h, cudaMemcpyAsync(xin.p, h->b.p, (size_t)h->ndof * 8, cudaMemcpyDeviceToDevice, h->stream));
-    for (int i = 0; i < warm && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, part, sc, tick, nullptr);
+    for (int i = 0; i < warm && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, part, sc, tick, nullptr, nullptr);
     FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    for (int i = 0; i < reps && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, part, sc, tick, nullptr);
+    for (int i = 0; i < reps && !rc; ++i) rc = launch_ebe(h, xin.p, yout.p, nb, true, part, sc, tick, nullptr, nullptr);
     FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     if (rc) return rc;
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));

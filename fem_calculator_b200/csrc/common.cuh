@@ -115,11 +115,6 @@ struct femb_handle {
   femb::DevBuf<int32_t> pair_node_rec;  // (n_nodes,4) {first pair, pair count, diagonal block, 0}
   femb::DevBuf<int32_t> pair_tiles;     // (n_tiles,4) {first node, node count, first pair, pair count}
   bool pairs_dev_ok = false;        // pair records uploaded (frame fast path usable)
-  // matrix-free operator (ebe.cu): 8-byte pair list {other node, element << 1 | end} and the
-  // 128-byte element records (direction cosines + stiffness magnitudes), rebuilt after each assembly
-  femb::DevBuf<int32_t> ebe_pair;   // (n_pairs,2)
-  femb::DevBuf<double> ebe_rec;     // (n_elem,16)
-  bool ebe_rec_valid = false;
   femb::DevBuf<double> Kvals;      // (nnzb, bs, bs)
   femb::DevBuf<double> Mdiag;      // (n_nodes, bs, bs) frame only
   femb::DevBuf<unsigned long long> counters;  // device scalars: [0] skipped gauss points
@@ -234,8 +229,10 @@ int launch_spmv_tma(femb_handle* h, int variant, const double* x, double* y, boo
 bool ebe_available(const femb_handle* h);
 bool ebe_selected(const femb_handle* h, int op);
 double ebe_bytes(const femb_handle* h, int nb);
+struct PcgLink;
 int launch_ebe(femb_handle* h, const double* x, double* y, int nb, bool masked, double* dot_partials,
-               double* scal_out, int* ticket, const int* done);
+               double* scal_out, int* ticket, const int* done, const PcgLink* link);
+int ebe_grid(const femb_handle* h, int nb);
 bool fused_pcg_applicable(const femb_handle* h, const femb_solve_opts& o);
 int pcg_fused(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 int setup_precond_public(femb_handle* h, int mode);

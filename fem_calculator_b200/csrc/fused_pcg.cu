@@ -65,27 +65,6 @@ __device__ __forceinline__ void store6(double* __restrict__ v, int node, const d
   p[0] = make_double2(u[0], u[1]); p[1] = make_double2(u[2], u[3]); p[2] = make_double2(u[4], u[5]);
 }
 
-// CTA-wide ordered sum of NV values; result in every thread
-template <int THREADS, int NV>
-__device__ __forceinline__ void block_sum_all(double (&v)[NV], double* s_part /* NV*THREADS/32 */) {
-  constexpr int NW = THREADS / 32;
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const double t = warp_sum(v[k]);
-    if (l == 0) s_part[k * NW + w] = t;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) t += s_part[k * NW + i];
-    v[k] = t;
-  }
-  __syncthreads();
-}
-
 // it = -1: INIT (x = 0, r = b, p = q = 0, z = D b, s = A z); it >= 0: update(it) + operator(it+1).
 // T lanes share a node (pairs part, part+T, ...).  partials: [2 buffers][3 values][pstride].
 template <int T, int THREADS, int MINB>

@@ -90,6 +90,77 @@ __device__ __forceinline__ bool grid_reduce(const double (&mine)[NV], double* pa
   return true;
 }
 
+// CTA-wide ordered sum of NV per-thread values; the result is returned in every thread.
+template <int THREADS, int NV>
+__device__ __forceinline__ void block_sum_all(double (&v)[NV], double* s_part /* NV * THREADS / 32 */) {
+  constexpr int NW = THREADS / 32;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double t = warp_sum(v[k]);
+    if (l == 0) s_part[k * NW + w] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) t += s_part[k * NW + i];
+    v[k] = t;
+  }
+  __syncthreads();
+}
+
+// ---- linked reductions of the single-vector PCG ---------------------------------------------
+// grid_reduce finishes a dot product with a serial tail — ticket atomic, last CTA re-reads all
+// partials, writes the scalar, the next kernel reads it — measured at 3.7 us per kernel on a 21 us
+// operator launch.  In the linked form a kernel only PUBLISHES its per-CTA partial sums; every CTA
+// of the NEXT kernel adds all published partials itself, in the same fixed order (bit-identical in
+// all CTAs, still no float atomics), and derives alpha / beta / the convergence decision locally.
+//   operator(it): consumes {gamma, rr} of update(it-1) [buffer it & 1] -> convergence / iteration cap,
+//                 publishes delta = (z, s)
+//   update(it)  : consumes delta and {gamma, rr} [buffer it & 1] -> beta, alpha; publishes the new
+//                 {gamma, rr} into buffer (it+1) & 1
+// CTA 0 mirrors the scalars into scal / flags for the host; gamma and alpha of the previous iteration
+// travel through parity-indexed slots so no kernel reads a slot another CTA of the same launch writes.
+struct PcgLink {
+  double* upd_partials;   // [2 buffers][2 values][pstride]   {gamma = (r, z), rr = (r, r)}
+  double* op_partials;    // [pstride]                         {delta = (z, A z)}
+  double* scal;
+  int* flags;
+  int n_upd, n_op;        // CTAs that publish into upd_partials / op_partials
+  int pstride;
+  int it, max_iter;
+  double rtol;
+};
+
+// operator-side prologue: true (in all threads of all CTAs alike) when the solve is over
+template <int THREADS>
+__device__ __forceinline__ bool pcg_link_decide(const PcgLink& L, double* s_part /* 2 * THREADS / 32 */) {
+  const double* pb = L.upd_partials + (size_t)(L.it & 1) * 2 * L.pstride;
+  double tot[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < L.n_upd; i += THREADS) { tot[0] += __ldcg(pb + i); tot[1] += __ldcg(pb + L.pstride + i); }
+  block_sum_all<THREADS, 2>(tot, s_part);
+  const double rr = tot[1];
+  int done = 0;
+  double tol2;
+  if (L.it == 0) {
+    tol2 = L.rtol * L.rtol * rr;             // the init kernel publishes {gamma_0, ||b||^2}
+    if (rr == 0.0) done = 1;                 // zero load: u = 0 is the answer
+  } else {
+    tol2 = L.scal[Scal::TOL2];
+    if (rr <= tol2) done = 1;
+    else if (L.it >= L.max_iter) done = 3;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    L.scal[Scal::RR] = rr;
+    if (L.it == 0) { L.scal[Scal::BB] = rr; L.scal[Scal::TOL2] = tol2; }
+    L.flags[Flag::ITERS] = L.it;             // updates completed so far
+    if (done) L.flags[Flag::DONE] = done;
+  }
+  return done != 0;
+}
+
 template <int BS>
 __device__ __forceinline__ double apply_dinv_row(const double* __restrict__ Dinv, int64_t g, const double* rn) {
   const int64_t node = g / BS;

@@ -337,6 +337,104 @@ pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s,
   }
 }
 
+// ---- linked single-vector PCG (matrix-free operator, scalar Jacobi): see PcgLink -------------
+// init: x = 0, r = b, z = Dinv r, p = q = 0; publishes {gamma_0, ||b||^2} into buffer 0
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pcg_init_linked_kernel(const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
+                       double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ q,
+                       int64_t n, const PcgLink L) {
+  __shared__ double s_part[2 * THREADS / 32];
+  double v[2] = {0.0, 0.0};
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const double bg = b[g];
+    const double zg = dinv[g] * bg;
+    x[g] = 0.0; r[g] = bg; z[g] = zg; p[g] = 0.0; q[g] = 0.0;
+    v[0] += bg * zg; v[1] += bg * bg;
+  }
+  block_sum_all<THREADS, 2>(v, s_part);
+  if (threadIdx.x == 0) { L.upd_partials[blockIdx.x] = v[0]; L.upd_partials[L.pstride + blockIdx.x] = v[1]; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { L.flags[Flag::DONE] = 0; L.flags[Flag::ITERS] = 0; }
+}
+
+// update(it): consumes delta (operator) and {gamma, rr} (previous update / init), then the same
+// element-wise pass as pcg_update_kernel's scalar-Jacobi branch; publishes the new {gamma, rr}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pcg_update_linked_kernel(const double* __restrict__ dinv, const double* __restrict__ s, double* __restrict__ p,
+                         double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                         int64_t n, const PcgLink L) {
+  __shared__ double s_part[2 * THREADS / 32];
+  if (L.flags[Flag::DONE]) return;
+  const int rd = L.it & 1, wr = rd ^ 1;
+  double tot[2] = {0.0, 0.0};
+  {
+    const double* pu = L.upd_partials + (size_t)rd * 2 * L.pstride;
+    for (int i = threadIdx.x; i < L.n_op; i += THREADS) tot[0] += __ldcg(L.op_partials + i);
+    for (int i = threadIdx.x; i < L.n_upd; i += THREADS) tot[1] += __ldcg(pu + i);
+  }
+  block_sum_all<THREADS, 2>(tot, s_part);
+  const double delta = tot[0], gamma = tot[1];
+  const bool first = (L.it == 0);
+  const double beta = first ? 0.0 : gamma / L.scal[Scal::RZ0 + rd];
+  const double den = first ? delta : delta - beta * gamma / L.scal[Scal::ALPHA + rd];
+  const bool bad = !(den > 0.0);           // K_ff not positive definite along p
+  const double alpha = bad ? 0.0 : gamma / den;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    L.scal[Scal::RZ0 + wr] = gamma;
+    L.scal[Scal::ALPHA + wr] = alpha;
+    L.scal[Scal::PQ] = delta;
+    if (bad) L.flags[Flag::DONE] = 2;
+  }
+  if (bad) return;
+  double v[2] = {0.0, 0.0};
+  const int64_t n2 = n >> 1;
+  const double2* z2 = reinterpret_cast<const double2*>(z);
+  const double2* s2 = reinterpret_cast<const double2*>(s);
+  const double2* d2 = reinterpret_cast<const double2*>(dinv);
+  double2* p2 = reinterpret_cast<double2*>(p);
+  double2* q2 = reinterpret_cast<double2*>(q);
+  double2* x2 = reinterpret_cast<double2*>(x);
+  double2* r2 = reinterpret_cast<double2*>(r);
+  double2* zo = reinterpret_cast<double2*>(z);
+#pragma unroll 2
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n2; i += (int64_t)gridDim.x * THREADS) {
+    const double2 zv = z2[i], sv = s2[i], dv = __ldg(d2 + i);
+    double2 pv = p2[i], qv = q2[i], xv = x2[i], rv = r2[i];
+    pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
+    qv.x = sv.x + beta * qv.x; qv.y = sv.y + beta * qv.y;
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
+    const double2 zn = make_double2(dv.x * rv.x, dv.y * rv.y);
+    p2[i] = pv; q2[i] = qv; x2[i] = xv; r2[i] = rv; zo[i] = zn;
+    v[0] += rv.x * zn.x; v[0] += rv.y * zn.y;
+    v[1] += rv.x * rv.x; v[1] += rv.y * rv.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // odd tail
+    const int64_t g = n - 1;
+    const double pg = z[g] + beta * p[g];
+    const double qg = s[g] + beta * q[g];
+    const double rg = r[g] - alpha * qg;
+    const double zg = dinv[g] * rg;
+    p[g] = pg; q[g] = qg; x[g] += alpha * pg; r[g] = rg; z[g] = zg;
+    v[0] += rg * zg; v[1] += rg * rg;
+  }
+  block_sum_all<THREADS, 2>(v, s_part);
+  if (threadIdx.x == 0) {
+    double* po = L.upd_partials + (size_t)wr * 2 * L.pstride;
+    po[blockIdx.x] = v[0]; po[L.pstride + blockIdx.x] = v[1];
+  }
+}
+
+// one CTA: the operator-side decision alone, so the host's poll sees the state after the last update
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pcg_decide_linked_kernel(const PcgLink L) {
+  __shared__ double s_part[2 * THREADS / 32];
+  if (L.flags[Flag::DONE]) return;
+  pcg_link_decide<THREADS>(L, s_part);
+}
+
 // out = K u - f (minus_f) or K u
 __global__ void axpy_sub_kernel(double* out, const double* f, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] -= f[i];
@@ -440,11 +538,6 @@ static int setup_precond(femb_handle* h, int mode) {
   return FEMB_OK;
 }
 
-struct PcgPeek {
-  int32_t flags[Flag::COUNT];
-  double scal[Scal::COUNT];
-};
-
 static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 
 int run_pcg(femb_handle* h, const femb_solve_opts& o, femb_stats* st) {
@@ -458,8 +551,101 @@ int pcg_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, f
   return pcg_core(h, o, d_b, st);
 }
 
+struct PcgPeek {
+  int32_t flags[Flag::COUNT];
+  double scal[Scal::COUNT];
+};
+
+// Matrix-free operator + scalar Jacobi: two kernels per iteration with linked reductions (PcgLink).
+static int pcg_core_linked(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
+  const int64_t n = h->ndof;
+  const int pstride = h->num_sms * 8;
+  int rc = setup_precond(h, o.precond);
+  if (rc) return rc;
+  FEMB_CUDA(h, h->fpartials.ensure((size_t)pstride * 6));
+  FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
+  FEMB_CUDA(h, cudaMemsetAsync(h->scal.p, 0, sizeof(double) * Scal::COUNT, h->stream));
+  constexpr int UT = 256;
+  const int grid_u = occ_grid(h, pcg_update_linked_kernel<UT>, (n + 1) / 2, UT);
+  PcgLink L;
+  L.upd_partials = h->fpartials.p; L.op_partials = h->fpartials.p + (size_t)4 * pstride;
+  L.scal = h->scal.p; L.flags = h->flags.p;
+  L.n_upd = grid_u; L.n_op = ebe_grid(h, 1); L.pstride = pstride;
+  L.it = 0; L.max_iter = o.max_iter; L.rtol = o.rtol;
+  pcg_init_linked_kernel<UT><<<grid_u, UT, 0, h->stream>>>(d_b, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, n, L);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  PcgPeek* peek = reinterpret_cast<PcgPeek*>(h->pinned);
+  const int check = o.check_every > 0 ? o.check_every : 50;
+  const bool prof = o.profile != 0;
+  std::vector<cudaEvent_t> evs;
+  int spmv_launches = 0, it = 0, done = 0;
+  while (!done && it < o.max_iter) {
+    const int batch = std::min(check, o.max_iter - it);
+    for (int k = 0; k < batch; ++k, ++it) {
+      const bool timed = prof && (it % o.profile) == 0;
+      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+      if (timed) {
+        if (h->ev_pool.size() < evs.size() + 3) {
+          const size_t old = h->ev_pool.size();
+          h->ev_pool.resize(old + 768);
+          for (size_t e = old; e < h->ev_pool.size(); ++e) cudaEventCreate(&h->ev_pool[e]);
+        }
+        e0 = h->ev_pool[evs.size()]; e1 = h->ev_pool[evs.size() + 1]; e2 = h->ev_pool[evs.size() + 2];
+        cudaEventRecord(e0, h->stream);
+      }
+      L.it = it;
+      rc = launch_ebe(h, h->z.p, h->s.p, 1, true, nullptr, nullptr, nullptr, nullptr, &L);
+      if (timed) cudaEventRecord(e1, h->stream);
+      if (rc) return rc;
+      ++spmv_launches;
+      pcg_update_linked_kernel<UT><<<grid_u, UT, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, L);
+      if (timed) { cudaEventRecord(e2, h->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); }
+      h->launches++;
+    }
+    L.it = it;
+    pcg_decide_linked_kernel<128><<<1, 128, 0, h->stream>>>(L);
+    h->launches++;
+    FEMB_CUDA(h, cudaGetLastError());
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->scal, h->scal.p, sizeof(peek->scal), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    done = peek->flags[Flag::DONE];
+  }
+  if (st) {
+    st->method_used = FEMB_SOLVER_PCG;
+    st->op_used = FEMB_OP_EBE;
+    st->iterations = peek->flags[Flag::ITERS];
+    st->converged = (done == 1);
+    st->spmv_launches = spmv_launches;
+    const double bb = peek->scal[Scal::BB];
+    st->rel_residual = bb > 0.0 ? sqrt(peek->scal[Scal::RR] / bb) : 0.0;
+    st->spmv_ms = 0.0;
+    st->update_ms = 0.0;
+    for (size_t i = 0; i + 2 < evs.size(); i += 3) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+      st->spmv_ms += ms;
+      cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]);
+      st->update_ms += ms;
+    }
+    st->spmv_timed = (int32_t)(evs.size() / 3);
+  }
+  if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");
+  if (done != 1) return fail(h, FEMB_ERR_NOT_CONVERGED, "PCG did not reach rtol within max_iter");
+  return FEMB_OK;
+}
+
+static bool linked_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FEMB_PCG_LINKED"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
 static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
   if (fused_pcg_applicable(h, o)) return pcg_fused(h, o, d_b, st);
+  if (h->bs == 6 && o.precond != FEMB_PRECOND_BLOCK_JACOBI && ebe_selected(h, o.op) && linked_enabled())
+    return pcg_core_linked(h, o, d_b, st);
   const int64_t n = h->ndof;
   const int gridv = vec_grid(h, n, kRowThreads);
   const int pstride = h->num_sms * 8;
@@ -500,7 +686,7 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
         cudaEventRecord(e0, h->stream);
       }
       if (ebe) rc = launch_ebe(h, h->z.p, h->s.p, 1, true, h->partials.p, h->scal.p + Scal::PQ, h->flags.p + Flag::TICKET0,
-                               h->flags.p + Flag::DONE);
+                               h->flags.p + Flag::DONE, nullptr);
       else rc = launch_spmv(h, h->z.p, h->s.p, true, h->partials.p);
       if (timed) cudaEventRecord(e1, h->stream);
       if (rc) return rc;
@@ -808,7 +994,7 @@ int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B,
     for (int k = 0; k < batch; ++k, ++it) {
       if (ebe) {
         rc = launch_ebe(h, h->mp.p, h->mq.p, kNB, true, part0, h->mscal.p + MScal::PQ, h->mflags.p + MFlag::TICKET0,
-                        h->mflags.p + MFlag::ALLDONE);
+                        h->mflags.p + MFlag::ALLDONE, nullptr);
         if (rc) return rc;
         h->launches--;   // counted with the two update kernels below
       } else {

@@ -12,7 +12,7 @@ fixed, f = compat.frame_bc_vectors(mesh, bc, len(mesh.points))
 m = FrameModel(0)
 m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, 2e11, 2e11 / 2.6)
 m.assemble(); m.set_bc(fixed, f)
-tag = f"v1={os.environ.get('FEMB_EBE_VARIANT','-')} v4={os.environ.get('FEMB_EBE_VARIANT4','-')} ctas={os.environ.get('FEMB_EBE_CTAS','-')}"
+tag = f"linked={os.environ.get('FEMB_PCG_LINKED','1')}"
 ms1, _ = m.time_kernel(3, 5, 100)
 ms4, _ = m.time_kernel(4, 5, 100)
 ms5, _ = m.time_kernel(5, 5, 100)
