@@ -559,6 +559,16 @@ int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, doubl
     FEMB_CUDA(h, cudaEventElapsedTime(&t3, h->ev0, h->ev1));
     *ms = (double)t3 / reps;
     return FEMB_OK;
+  } else if (which == 7) {
+    // dense blocked Cholesky of the masked operator (fill + factor + mirror); *bytes receives the
+    // FLOP count n^3/3 of the factorisation instead of bytes
+    if (!h->assembled || !h->have_bc) return fail(h, FEMB_ERR_ARG, "assemble + set_bc first");
+    const double nn = (double)h->ndof;
+    *bytes = nn * nn * nn / 3.0;
+    for (int i = 0; i < warm && !rc; ++i) { h->dense_factored = false; rc = dense_factor(h); }
+    FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps && !rc; ++i) { h->dense_factored = false; rc = dense_factor(h); }
+    FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   } else if (which == 9) {
     if (!h->assembled) return fail(h, FEMB_ERR_ARG, "assemble first");
     // read-streaming ceiling: sum the K values (same bytes as one SpMV matrix pass) with 16-byte loads

@@ -6,6 +6,8 @@
 //     one thread per model, model-interleaved scratch so every access is coalesced;
 //   * small systems: dense FP64 Cholesky of the masked operator.
 // All replace np.linalg.solve(k_ff, f_f) (BeamSolver.py:417) / spsolve (ReactionSolver.py:201).
+#include <algorithm>
+
 #include "common.cuh"
 #include "elements.cuh"
 
@@ -355,93 +357,220 @@ int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const doub
   return FEMB_OK;
 }
 
-// ---- small dense Cholesky of the masked operator ----------------------------------------
+// ---- dense FP64 Cholesky of the masked operator: blocked, trailing update on DMMA -----------------
+// For reduced systems small enough to be a real dense contraction (north_star (4); robust where
+// cond(K_ff) defeats CG).  A = P K P + (I - P) is expanded to a dense row-major matrix padded to a
+// multiple of 64 (identity on the padding) and factored right-looking in 64-column panels:
+//   1. chol_potrf_block_kernel   64x64 diagonal block, one CTA, shared memory
+//   2. chol_trsm_kernel          panel rows x L_kk^-T, one thread per row (row in registers)
+//   3. chol_syrk_dmma_kernel     trailing A_ij -= P_i P_j^T on the FP64 tensor cores:
+//                                mma.sync.m8n8k4.f64 (SASS DMMA), 64x64 tile per CTA, both panel
+//                                tiles staged once in shared memory (K = 64 fits), n^3/3 flops
+// After the factorisation L^T is mirrored into the upper triangle so both substitution sweeps read
+// contiguous rows.  Non-positive pivots are reported, never patched silently.
+constexpr int kCB = 64;           // panel width / tile edge
+constexpr int kCBLd = kCB + 4;    // shared row stride (doubles): conflict-free DMMA fragment loads
+constexpr int64_t kDenseMax = 16384;
+
 __global__ void dense_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                   const double* __restrict__ vals, const uint8_t* __restrict__ mask,
-                                  double* __restrict__ A, int64_t n, int bs) {
-  // one thread per scalar row: writes the row of A = P K P + (I - P), column-major is the
-  // same as row-major here (symmetric); we store row-major A[r*n + c].
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n) return;
+                                  double* __restrict__ A, int64_t n, int64_t ld, int bs) {
+  // one CTA per row of the padded matrix: zero the row, then scatter the row of P K P + (I - P)
+  const int64_t g = blockIdx.x;
+  double* row = A + (size_t)g * ld;
+  for (int64_t c = threadIdx.x; c < ld; c += blockDim.x) row[c] = 0.0;
+  __syncthreads();
+  if (g >= n || !mask[g]) { if (threadIdx.x == 0) row[g] = 1.0; return; }
   const int64_t node = g / bs;
   const int r = (int)(g - node * bs);
-  double* row = A + (size_t)g * n;
-  for (int64_t c = 0; c < n; ++c) row[c] = 0.0;
-  if (!mask[g]) { row[g] = 1.0; return; }
-  for (int b = rowptr[node]; b < rowptr[node + 1]; ++b) {
-    const int64_t cn = colidx[b];
-    for (int c = 0; c < bs; ++c)
-      if (mask[cn * bs + c]) row[cn * bs + c] = vals[(size_t)b * bs * bs + r * bs + c];
+  const int b0 = rowptr[node], b1 = rowptr[node + 1];
+  for (int t = threadIdx.x; t < (b1 - b0) * bs; t += blockDim.x) {
+    const int b = b0 + t / bs, c = t % bs;
+    const int64_t col = (int64_t)colidx[b] * bs + c;
+    if (mask[col]) row[col] = vals[(size_t)b * bs * bs + r * bs + c];
   }
 }
 
-// right-looking Cholesky, one CTA, A row-major lower triangle overwritten by L.
-__global__ void __launch_bounds__(1024)
-dense_chol_kernel(double* __restrict__ A, int n, int* status) {
-  __shared__ double s_col[2048];
-  __shared__ int s_bad;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) s_bad = 0;
+__global__ void __launch_bounds__(256)
+chol_potrf_block_kernel(double* __restrict__ A, int64_t ld, int k0, int* status) {
+  __shared__ double s[kCB][kCB + 1];
+  __shared__ double s_inv;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < kCB * kCB; t += 256) s[t / kCB][t % kCB] = A[(size_t)(k0 + t / kCB) * ld + k0 + t % kCB];
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    const double ajj = A[(size_t)j * n + j];
-    if (!(ajj > 0.0)) { if (tid == 0) s_bad = 1; }
-    const double d = sqrt(ajj > 0.0 ? ajj : 1.0);
-    const double id = 1.0 / d;
-    for (int i = j + tid; i < n; i += nt) {
-      const double v = (i == j) ? d : A[(size_t)i * n + j] * id;
-      A[(size_t)i * n + j] = v;
-      s_col[i] = v;
+  for (int j = 0; j < kCB; ++j) {
+    if (tid == 0) {
+      double d = s[j][j];
+      if (!(d > 0.0)) { *status = 1; d = 1.0; }
+      d = sqrt(d);
+      s[j][j] = d;
+      s_inv = 1.0 / d;
     }
     __syncthreads();
-    // trailing update: A[i][c] -= L[i][j] L[c][j], j < c <= i ; rows distributed by warps
-    const int w = tid >> 5, l = tid & 31, nw = nt >> 5;
-    for (int i = j + 1 + w; i < n; i += nw) {
-      const double lij = s_col[i];
-      for (int c = j + 1 + l; c <= i; c += 32) A[(size_t)i * n + c] -= lij * s_col[c];
+    if (tid > j && tid < kCB) s[tid][j] *= s_inv;
+    __syncthreads();
+    const int m = kCB - 1 - j;                       // trailing (m x m) lower update
+    for (int t = tid; t < m * m; t += 256) {
+      const int i = j + 1 + t / m, c = j + 1 + t % m;
+      if (c <= i) s[i][c] -= s[i][j] * s[c][j];
     }
     __syncthreads();
   }
-  if (tid == 0) *status = s_bad;
+  for (int t = tid; t < kCB * kCB; t += 256) {
+    const int i = t / kCB, c = t % kCB;
+    if (c <= i) A[(size_t)(k0 + i) * ld + k0 + c] = s[i][c];
+  }
 }
 
-// forward / backward substitution with the Cholesky factor; one CTA per right-hand side.
+// rows below the diagonal block: X L_kk^T = A_panel, one thread per row
+__global__ void __launch_bounds__(128)
+chol_trsm_kernel(double* __restrict__ A, int64_t ld, int k0, int n_pad) {
+  __shared__ double L[kCB][kCB + 1];
+  __shared__ double invd[kCB];
+  for (int t = threadIdx.x; t < kCB * kCB; t += 128) L[t / kCB][t % kCB] = A[(size_t)(k0 + t / kCB) * ld + k0 + t % kCB];
+  __syncthreads();
+  if (threadIdx.x < kCB) invd[threadIdx.x] = 1.0 / L[threadIdx.x][threadIdx.x];
+  __syncthreads();
+  const int row = k0 + kCB + blockIdx.x * 128 + threadIdx.x;
+  if (row >= n_pad) return;
+  double* a = A + (size_t)row * ld + k0;
+  double x[kCB];
+#pragma unroll
+  for (int c = 0; c < kCB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(a + c); x[c] = v.x; x[c + 1] = v.y; }
+#pragma unroll
+  for (int c = 0; c < kCB; ++c) {
+    double v = x[c];
+#pragma unroll
+    for (int j = 0; j < c; ++j) v -= x[j] * L[c][j];
+    x[c] = v * invd[c];
+  }
+#pragma unroll
+  for (int c = 0; c < kCB; c += 2) *reinterpret_cast<double2*>(a + c) = make_double2(x[c], x[c + 1]);
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// trailing update of the lower tiles (ti >= tj): A[ti][tj] -= P_ti P_tj^T, P = the panel just solved
+__global__ void __launch_bounds__(128)
+chol_syrk_dmma_kernel(double* __restrict__ A, int64_t ld, int k0) {
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti) return;
+  extern __shared__ __align__(16) double smem[];
+  double* Pa = smem;                       // [64][kCBLd]
+  double* Pb = smem + kCB * kCBLd;
+  const int r0 = k0 + kCB + ti * kCB, c0 = k0 + kCB + tj * kCB;
+  for (int t = threadIdx.x; t < kCB * kCB / 2; t += 128) {
+    const int i = t / (kCB / 2), c = (t % (kCB / 2)) * 2;
+    const double2 va = *reinterpret_cast<const double2*>(A + (size_t)(r0 + i) * ld + k0 + c);
+    const double2 vb = *reinterpret_cast<const double2*>(A + (size_t)(c0 + i) * ld + k0 + c);
+    Pa[i * kCBLd + c] = va.x; Pa[i * kCBLd + c + 1] = va.y;
+    Pb[i * kCBLd + c] = vb.x; Pb[i * kCBLd + c + 1] = vb.y;
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = (w >> 1) * 32, wc = (w & 1) * 32;      // this warp's 32x32 quadrant
+  const int fr = lane >> 2, fk = lane & 3;               // fragment row / k index of this lane
+  double acc[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#pragma unroll 4
+  for (int kk = 0; kk < kCB; kk += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = Pa[(wr + mi * 8 + fr) * kCBLd + kk + fk];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) b[ni] = Pb[(wc + ni * 8 + fr) * kCBLd + kk + fk];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      double2* c = reinterpret_cast<double2*>(A + (size_t)(r0 + wr + mi * 8 + fr) * ld + c0 + wc + ni * 8 + 2 * fk);
+      double2 v = *c;
+      v.x -= acc[mi][ni][0]; v.y -= acc[mi][ni][1];
+      *c = v;
+    }
+}
+
+// upper triangle <- transpose of the lower one (so that column sweeps read contiguous rows)
+__global__ void chol_mirror_kernel(double* __restrict__ A, int64_t ld, int n_pad) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int i = bi * 32 + threadIdx.y, j = bj * 32 + threadIdx.x;
+  t[threadIdx.y][threadIdx.x] = A[(size_t)i * ld + j];
+  __syncthreads();
+  const int ui = bj * 32 + threadIdx.y, uj = bi * 32 + threadIdx.x;   // element (ui, uj) = L[uj][ui]
+  if (uj > ui) A[(size_t)ui * ld + uj] = t[threadIdx.x][threadIdx.y];
+}
+
+// L y = b, L^T x = y with one CTA per right-hand side; the working vector lives in shared memory and
+// both sweeps stream contiguous rows (row j of the mirrored upper triangle = column j of L).
 __global__ void __launch_bounds__(1024)
 dense_apply_kernel(const double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
-                   int n, int64_t ld) {
-  __shared__ double s_col[2048];
+                   int n, int64_t lda, int64_t ld) {
+  extern __shared__ double s_col[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const double* bq = b + (size_t)blockIdx.x * ld;
   double* xq = x + (size_t)blockIdx.x * ld;
   for (int i = tid; i < n; i += nt) s_col[i] = bq[i];
   __syncthreads();
-  for (int j = 0; j < n; ++j) {            // L y = b (column sweep)
-    if (tid == 0) s_col[j] = s_col[j] / A[(size_t)j * n + j];
+  for (int j = 0; j < n; ++j) {            // forward: y_j, then s[i] -= L[i][j] y_j (i > j)
+    const double* row = A + (size_t)j * lda;
+    const double yj = s_col[j] / row[j];
     __syncthreads();
-    const double yj = s_col[j];
-    for (int i = j + 1 + tid; i < n; i += nt) s_col[i] -= A[(size_t)i * n + j] * yj;
+    if (tid == 0) s_col[j] = yj;
+    for (int i = j + 1 + tid; i < n; i += nt) s_col[i] -= row[i] * yj;
     __syncthreads();
   }
-  for (int j = n - 1; j >= 0; --j) {       // L^T x = y
-    if (tid == 0) s_col[j] = s_col[j] / A[(size_t)j * n + j];
+  for (int j = n - 1; j >= 0; --j) {       // backward: x_j, then s[i] -= L[j][i] x_j (i < j)
+    const double* row = A + (size_t)j * lda;
+    const double xj = s_col[j] / row[j];
     __syncthreads();
-    const double xj = s_col[j];
-    for (int i = tid; i < j; i += nt) s_col[i] -= A[(size_t)j * n + i] * xj;
+    if (tid == 0) s_col[j] = xj;
+    for (int i = tid; i < j; i += nt) s_col[i] -= row[i] * xj;
     __syncthreads();
   }
   for (int i = tid; i < n; i += nt) xq[i] = s_col[i];
 }
 
+int64_t dense_max_dof() { return kDenseMax; }
+
 int dense_factor(femb_handle* h) {
   const int64_t n = h->ndof;
-  if (n > 2048) return fail(h, FEMB_ERR_ARG, "dense solver is limited to 2048 DOFs");
+  if (n > kDenseMax) return fail(h, FEMB_ERR_ARG, "dense solver is limited to 16384 DOFs");
   if (h->dense_factored) return FEMB_OK;
+  const int64_t n_pad = (n + kCB - 1) / kCB * kCB;
   DevBuf<int> status;
-  FEMB_CUDA(h, h->denseL.alloc((size_t)n * n));
+  FEMB_CUDA(h, h->denseL.alloc((size_t)n_pad * n_pad));
   FEMB_CUDA(h, status.alloc(1));
-  dense_fill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, h->denseL.p, n, h->bs);
-  dense_chol_kernel<<<1, 1024, 0, h->stream>>>(h->denseL.p, (int)n, status.p);
-  h->launches += 2;
+  FEMB_CUDA(h, cudaMemsetAsync(status.p, 0, sizeof(int), h->stream));
+  dense_fill_kernel<<<(unsigned)n_pad, 256, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p, h->denseL.p, n, n_pad, h->bs);
+  h->launches++;
+  const size_t smem = (size_t)2 * kCB * kCBLd * sizeof(double);
+  FEMB_CUDA(h, cudaFuncSetAttribute(chol_syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int64_t k0 = 0; k0 < n_pad; k0 += kCB) {
+    chol_potrf_block_kernel<<<1, 256, 0, h->stream>>>(h->denseL.p, n_pad, (int)k0, status.p);
+    h->launches++;
+    const int64_t rem = n_pad - k0 - kCB;
+    if (rem > 0) {
+      chol_trsm_kernel<<<(unsigned)((rem + 127) / 128), 128, 0, h->stream>>>(h->denseL.p, n_pad, (int)k0, (int)n_pad);
+      const unsigned nt = (unsigned)(rem / kCB);
+      chol_syrk_dmma_kernel<<<dim3(nt, nt), 128, smem, h->stream>>>(h->denseL.p, n_pad, (int)k0);
+      h->launches += 2;
+    }
+  }
+  chol_mirror_kernel<<<dim3((unsigned)(n_pad / 32), (unsigned)(n_pad / 32)), dim3(32, 32), 0, h->stream>>>(h->denseL.p, n_pad, (int)n_pad);
+  h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   int* hs = reinterpret_cast<int*>(h->pinned);
   FEMB_CUDA(h, cudaMemcpyAsync(hs, status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -452,7 +581,11 @@ int dense_factor(femb_handle* h) {
 }
 
 int dense_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_t ld) {
-  dense_apply_kernel<<<nrhs, 1024, 0, h->stream>>>(h->denseL.p, d_b, d_x, (int)h->ndof, ld);
+  const int64_t n = h->ndof;
+  const int64_t n_pad = (n + kCB - 1) / kCB * kCB;
+  const size_t smem = (size_t)n * sizeof(double);
+  FEMB_CUDA(h, cudaFuncSetAttribute(dense_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+  dense_apply_kernel<<<nrhs, 1024, smem, h->stream>>>(h->denseL.p, d_b, d_x, (int)n, n_pad, ld);
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   return FEMB_OK;

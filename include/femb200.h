@@ -46,7 +46,8 @@ enum {
   FEMB_SOLVER_AUTO = 0,    /* chain -> block-tridiagonal; tiny -> dense Cholesky; else PCG */
   FEMB_SOLVER_PCG = 1,     /* preconditioned conjugate gradients on the BSR operator */
   FEMB_SOLVER_CHAIN = 2,   /* direct block-tridiagonal Cholesky (path graphs only) */
-  FEMB_SOLVER_DENSE = 3    /* dense FP64 Cholesky of K_ff (small systems) */
+  FEMB_SOLVER_DENSE = 3    /* dense FP64 blocked Cholesky of K_ff, trailing update on DMMA (<= 16384 DOF;
+                              AUTO picks it up to 2048 DOF) */
 };
 
 /* femb_solve_opts.precond */
@@ -242,7 +243,8 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
  * (after `warm` untimed launches); *ms receives the mean per launch, *bytes the
  * algorithmic bytes of one launch.  which: 0 = BSR SpMV (masked
  * K_ff operator), 1 = fused element+assembly, 3 = matrix-free (EBE) operator, 4 = its 4-vector
- * form, 9 = plain 16-byte read of the K values (streaming ceiling).                      */
+ * form, 5 = EBE with the fused (x, y) reduction, 7 = dense blocked Cholesky (fill + factor; *bytes
+ * then receives the FLOP count n^3/3), 9 = plain 16-byte read of the K values (streaming ceiling). */
 int femb_time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes);
 
 /* CUDA-event stopwatch on the handle's stream: stop = 0 records the start (after draining the
