@@ -231,8 +231,10 @@ bool ebe_selected(const femb_handle* h, int op);
 double ebe_bytes(const femb_handle* h, int nb);
 struct PcgLink;
 int launch_ebe(femb_handle* h, const double* x, double* y, int nb, bool masked, double* dot_partials,
-               double* scal_out, int* ticket, const int* done, const PcgLink* link);
-int ebe_grid(const femb_handle* h, int nb);
+               double* scal_out, int* ticket, const int* done, const PcgLink* link, const void* p2p_dev = nullptr,
+               int64_t n_rows_nodes = -1);
+int ebe_grid(const femb_handle* h, int nb, int64_t n_nodes);
+bool ebe_available_dist(const femb_handle* h);
 bool fused_pcg_applicable(const femb_handle* h, const femb_solve_opts& o);
 int pcg_fused(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 int setup_precond_public(femb_handle* h, int mode);

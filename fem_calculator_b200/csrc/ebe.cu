@@ -64,6 +64,14 @@ __device__ __forceinline__ void load_u(const double* __restrict__ x, int node, i
   }
 }
 
+// L2-coherent gather of a ghost node's entries (single vector): peer GPUs store them while CTAs of this
+// kernel may already be resident, so the non-coherent path could serve stale L1 lines (solver.cu)
+__device__ __forceinline__ void load6_cg(const double* __restrict__ x, int node, double* u) {
+  const double2* p = reinterpret_cast<const double2*>(x + (size_t)node * 6);
+  const double2 a = __ldcg(p), b = __ldcg(p + 1), c = __ldcg(p + 2);
+  u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
+}
+
 template <int NBT, int NB>
 __device__ __forceinline__ void store_u(double* __restrict__ y, int node, int qg, const double (&u)[NB][6]) {
   if constexpr (NBT == 1) {
@@ -83,6 +91,10 @@ __device__ __forceinline__ void store_u(double* __restrict__ y, int node, int qg
   }
 }
 
+// p2p (DOT, single vector, row-block distributed PCG — dist.cu): the first n_nodes local nodes are
+// the rank's owned rows; before gathering, the kernel waits for the neighbours' halo flags, ghost
+// entries (node id >= n_nodes) are read L2-coherently, and the last CTA of the (x, y) reduction posts
+// the rank's partial sums into every peer's mailbox — the same three hooks as bsr_spmv_kernel.
 // LINK: the launch belongs to the linked single-vector PCG (pcg_common.cuh): the kernel first
 // finishes the update kernel's reductions (convergence decision) and publishes its own (x, y)
 // partial instead of running a last-CTA reduction.  Otherwise DOT adds (x_q, y_q) through the ordered
@@ -92,7 +104,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 frame_ebe_node_kernel(const FrameParams P, const int4* __restrict__ pair_rec, const int4* __restrict__ node_rec,
                       int n_nodes, const uint8_t* __restrict__ free_mask, const double* __restrict__ x,
                       double* __restrict__ y, double* partials, int pstride, double* scal, int* ticket,
-                      const int* done, const PcgLink link) {
+                      const int* done, const PcgLink link, const P2PDev* __restrict__ p2p) {
   constexpr int QS = NBT / NB;
   constexpr int LPN = QS * T;
   constexpr int NPC = THREADS / LPN;   // nodes per CTA and step
@@ -104,6 +116,17 @@ frame_ebe_node_kernel(const FrameParams P, const int4* __restrict__ pair_rec, co
     if (pcg_link_decide<THREADS>(link, s_link)) return;
   } else if (DOT && done && *done) {
     return;
+  }
+  if (DOT && !LINK && NBT == 1 && p2p) {
+    // done points at flags[Flag::DONE] (= flags[0]); the iteration counter sits next to it
+    if ((int)threadIdx.x < p2p->n_nbr) {
+      const long long seq = p2p->base[0] + done[Flag::ITERS] + 1;
+      long long spins = 0;
+      while (ld_acquire_sys(p2p->my_halo_flag + p2p->nbr[threadIdx.x]) < seq) {
+        if (++spins > kSpinLimit) { const_cast<int*>(done)[Flag::DONE] = 4; break; }
+      }
+    }
+    __syncthreads();
   }
   const int lin = threadIdx.x % LPN;
   const int qg = lin / T, part = lin % T;
@@ -148,7 +171,8 @@ frame_ebe_node_kernel(const FrameParams P, const int4* __restrict__ pair_rec, co
       in.A = __ldg(sp); in.Ix = __ldg(sp + 1); in.Iy = __ldg(sp + 2); in.J = __ldg(sp + 3);
       in.ky = __ldg(sp + 4); in.kz = __ldg(sp + 5);
       double uo[NB][6];
-      load_u<NBT, NB>(x, rec.y, qg, uo);
+      if (NBT == 1 && DOT && !LINK && p2p && rec.y >= n_nodes) load6_cg(x, rec.y, uo[0]);
+      else load_u<NBT, NB>(x, rec.y, qg, uo);
       KRec k;
       krec_from(P, in, a, k);
 #pragma unroll
@@ -204,6 +228,14 @@ frame_ebe_node_kernel(const FrameParams P, const int4* __restrict__ pair_rec, co
     if (grid_reduce<THREADS, NBT>(mine, partials, pstride, ticket, tot)) {
       if (threadIdx.x == 0)
         for (int q = 0; q < NBT; ++q) scal[q] = tot[q];
+      if (NBT == 1 && p2p && (int)threadIdx.x < p2p->world) {
+        // post {delta, gamma, ||r||^2} of this rank in every peer's mailbox (scal = the solver's red[])
+        const long long seq = p2p->base[0] + done[Flag::ITERS] + 1;
+        MailSlot* dst = p2p->peer_mail[threadIdx.x] + (p2p->rank * 2 + (int)(seq & 1));
+        dst->v[0] = tot[0]; dst->v[1] = scal[1]; dst->v[2] = scal[2]; dst->v[3] = 0.0;
+        __threadfence_system();
+        st_release_sys(&dst->seq, seq);
+      }
     }
   }
 }
@@ -218,6 +250,14 @@ static FrameParams ebe_params(const femb_handle* h) {
 // operator choice of a Krylov solve: opts.op (FEMB_OP_*), overridable with FEMB_OPERATOR=bsr|ebe
 bool ebe_available(const femb_handle* h) {
   return h->kind == Kind::Frame && h->pairs_dev_ok && !dist_active(h);
+}
+
+// row-block partition: the pair lists of the owned nodes are complete on every rank ("owner computes":
+// the local mesh holds every element that touches an owned node), ghost nodes are only gathered from
+bool ebe_available_dist(const femb_handle* h) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("FEMB_OPERATOR"); off = (e && (e[0] == 'b' || e[0] == 'B')) ? 1 : 0; }
+  return !off && h->kind == Kind::Frame && h->pairs_dev_ok && dist_active(h);
 }
 
 bool ebe_selected(const femb_handle* h, int op) {
@@ -244,29 +284,34 @@ double ebe_bytes(const femb_handle* h, int nb) {
          1.0 * h->ndof;
 }
 
-int ebe_grid(const femb_handle* h, int nb) {
+int ebe_grid(const femb_handle* h, int nb, int64_t n_nodes) {
   const int lanes_per_node = 2;   // nb = 1: T = 2;  nb = 4: two lanes with two vectors each
   const int npc = kEbeThreads / lanes_per_node;
-  const int need = ((int)h->n_nodes + npc - 1) / npc;
+  const int need = ((int)n_nodes + npc - 1) / npc;
   return std::max(1, std::min(need, h->num_sms * (nb == 1 ? kEbe1CtasPerSm : kEbe4CtasPerSm)));
 }
 
 // y = K_ff x (masked) or K x; nb = 1 (plain) or 4 (interleaved by right-hand side, x[g*4 + q]).
 // dot_partials != null: (x_q, y_q) -> scal_out[q] through the ordered grid reduction (ticket = its
 // ticket slot, done = early-exit flag, may be null).  link != null (nb = 1): linked PCG launch.
+// p2p_dev / n_rows_nodes: row-block distributed launch over the first n_rows_nodes (owned) nodes.
 int launch_ebe(femb_handle* h, const double* x, double* y, int nb, bool masked, double* dot_partials,
-               double* scal_out, int* ticket, const int* done, const PcgLink* link) {
+               double* scal_out, int* ticket, const int* done, const PcgLink* link, const void* p2p_dev,
+               int64_t n_rows_nodes) {
   if (h->n_nodes <= 0) return FEMB_OK;
   const FrameParams P = ebe_params(h);
   const int pstride = h->num_sms * 8;
   const int4* pr = reinterpret_cast<const int4*>(h->pair_rec.p);
   const int4* nr = reinterpret_cast<const int4*>(h->pair_node_rec.p);
-  const int n_nodes = (int)h->n_nodes;
-  const int grid = ebe_grid(h, nb);
+  const int n_nodes = (int)(n_rows_nodes >= 0 ? n_rows_nodes : h->n_nodes);
+  if (n_nodes == 0) return FEMB_OK;
+  const int grid = ebe_grid(h, nb, n_nodes);
   const PcgLink nolink = {};
+  const P2PDev* p2p = reinterpret_cast<const P2PDev*>(p2p_dev);
+  if (p2p && !(nb == 1 && masked && dot_partials && done && !link)) return fail(h, FEMB_ERR_ARG, "peer-memory operator launch: masked single vector with reduction");
 #define EBE(NBT, NB, T, M, D, LK, MINB)                                                                      \
   frame_ebe_node_kernel<NBT, NB, T, M, D, LK, kEbeThreads, MINB><<<grid, kEbeThreads, 0, h->stream>>>(        \
-      P, pr, nr, n_nodes, h->free_mask.p, x, y, dot_partials, pstride, scal_out, ticket, done, LK ? *link : nolink)
+      P, pr, nr, n_nodes, h->free_mask.p, x, y, dot_partials, pstride, scal_out, ticket, done, LK ? *link : nolink, p2p)
   if (nb == 1) {
     if (link) {
       if (!masked) return fail(h, FEMB_ERR_ARG, "linked operator launch is masked");

@@ -458,6 +458,12 @@ int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool
   if (tma_variant < 0) { const char* e = getenv("FEMB_SPMV_TMA"); tma_variant = e ? atoi(e) : 0; }
   if (tma_variant > 0 && h->bs == 6 && n == h->ndof && !skip_node && !node_list && !p2p_dev)
     return launch_spmv_tma(h, tma_variant, x, y, masked, dot_partials, scal_out);
+  // row-block distributed PCG on a frame: the matrix-free operator over the owned nodes (dist.cu passes
+  // scal_out = red + DELTA, whose neighbours red[1], red[2] the peer-memory epilogue posts, and the
+  // reduction's flags block)
+  if (masked && dot_partials && !skip_node && !node_list && h->bs == 6 && n == h->n_owned_nodes * 6 && ebe_available_dist(h))
+    return launch_ebe(h, x, y, 1, true, dot_partials, scal_out, h->flags.p + Flag::TICKET0, h->flags.p + Flag::DONE, nullptr,
+                      p2p_dev, h->n_owned_nodes);
   const int pstride = h->num_sms * 8;
   const int grid = vec_grid(h, n, kRowThreads);
 #define SPMV(BS, M, D)                                                                         \
@@ -570,7 +576,7 @@ static int pcg_core_linked(femb_handle* h, const femb_solve_opts& o, const doubl
   PcgLink L;
   L.upd_partials = h->fpartials.p; L.op_partials = h->fpartials.p + (size_t)4 * pstride;
   L.scal = h->scal.p; L.flags = h->flags.p;
-  L.n_upd = grid_u; L.n_op = ebe_grid(h, 1); L.pstride = pstride;
+  L.n_upd = grid_u; L.n_op = ebe_grid(h, 1, h->n_nodes); L.pstride = pstride;
   L.it = 0; L.max_iter = o.max_iter; L.rtol = o.rtol;
   pcg_init_linked_kernel<UT><<<grid_u, UT, 0, h->stream>>>(d_b, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, n, L);
   h->launches++;
