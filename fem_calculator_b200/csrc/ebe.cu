@@ -288,7 +288,7 @@ int ebe_grid(const femb_handle* h, int nb, int64_t n_nodes) {
   const int lanes_per_node = 2;   // nb = 1: T = 2;  nb = 4: two lanes with two vectors each
   const int npc = kEbeThreads / lanes_per_node;
   const int need = ((int)n_nodes + npc - 1) / npc;
-  return std::max(1, std::min(need, h->num_sms * (nb == 1 ? kEbe1CtasPerSm : kEbe4CtasPerSm)));
+  return std::max(1, std::min(need, h->num_sms * (nb == 1 ? kEbe1CtasPerSm : kEbe4CtasPerSm)));   // nb = 2, 4: 168 registers
 }
 
 // y = K_ff x (masked) or K x; nb = 1 (plain) or 4 (interleaved by right-hand side, x[g*4 + q]).
@@ -323,8 +323,12 @@ int launch_ebe(femb_handle* h, const double* x, double* y, int nb, bool masked, 
     if (masked && dot_partials) EBE(4, 2, 1, true, true, false, kEbe4CtasPerSm);
     else if (masked) EBE(4, 2, 1, true, false, false, kEbe4CtasPerSm);
     else EBE(4, 2, 1, false, false, false, kEbe4CtasPerSm);
+  } else if (nb == 2 && !link) {      // two interleaved vectors: both on one lane, two lanes split the pairs
+    if (masked && dot_partials) EBE(2, 2, 2, true, true, false, kEbe4CtasPerSm);
+    else if (masked) EBE(2, 2, 2, true, false, false, kEbe4CtasPerSm);
+    else EBE(2, 2, 2, false, false, false, kEbe4CtasPerSm);
   } else {
-    return fail(h, FEMB_ERR_ARG, "matrix-free operator: 1 or 4 vectors");
+    return fail(h, FEMB_ERR_ARG, "matrix-free operator: 1, 2 or 4 vectors");
   }
 #undef EBE
   h->launches++;

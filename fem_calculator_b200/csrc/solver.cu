@@ -773,62 +773,78 @@ int bc_build_mask(femb_handle* h, const int64_t* d_fixed, int64_t n_fixed) {
 
 }  // namespace femb
 
-// ------------------------------------------------------------------ multi-RHS PCG (NB = 4)
-// Four right-hand sides advance in lockstep through independent CG recurrences that share ONE
-// pass over the matrix per iteration (SpMM): the 359 MB of K are read once for four vectors.
-// Work vectors are interleaved by right-hand side, v[g*4 + q], so the gather of a block column
-// is one contiguous 192-byte read and every vector kernel is a plain double4 stream.  z = Dinv r
-// is formed on the fly (scalar Jacobi), which keeps the vector traffic at ~9.3 passes per
-// iteration.  Used by the modal solver's shift-invert steps (block Krylov, block size 4).
+// ------------------------------------------------------------- multi-RHS PCG (NB = 2 or 4)
+// NB right-hand sides advance in lockstep through independent CG recurrences that share ONE
+// operator pass per iteration: the matrix-free kernel rebuilds each element record once for NB
+// vectors (or, with the assembled operator, the 359 MB of K are read once: SpMM).  Work vectors are
+// interleaved by right-hand side, v[g*NB + q], so the gather of a block column is one contiguous read
+// and every vector kernel is a plain 16- / 32-byte stream.  z = Dinv r is formed on the fly (scalar
+// Jacobi).  Used by the modal solver's shift-invert steps (block Krylov, block size 2 or 4).
 namespace femb {
 
-constexpr int kNB = 4;
-struct MScal {  // doubles, each [kNB]
+struct MScal {  // doubles, each [4] (NB = 2 uses the first two slots)
   enum { PQ = 0, RZ = 4, RR = 8, BB = 12, TOL2 = 16, BETA = 20, COUNT = 24 };
 };
 struct MFlag {  // ints
   enum { DONEQ = 0, ALLDONE = 4, ITERS = 5, BAD = 6, TICKET0 = 7, TICKET1 = 8, COUNT = 12 };
 };
 
-__device__ __forceinline__ double4 ld4(const double* p) { return *reinterpret_cast<const double4*>(p); }
-__device__ __forceinline__ void st4(double* p, double4 v) { *reinterpret_cast<double4*>(p) = v; }
-__device__ __forceinline__ double4 ldg4(const double* p) {   // 256-bit read-only load (LDG.256.CONSTANT)
-  double4 v;
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
-  return v;
+template <int NB>
+__device__ __forceinline__ void ldv(const double* p, double (&v)[NB]) {
+  if constexpr (NB == 4) {
+    const double4 t = *reinterpret_cast<const double4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+}
+template <int NB>
+__device__ __forceinline__ void stv(double* p, const double (&v)[NB]) {
+  if constexpr (NB == 4) *reinterpret_cast<double4*>(p) = make_double4(v[0], v[1], v[2], v[3]);
+  else *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+template <int NB>
+__device__ __forceinline__ void ldgv(const double* p, double (&v)[NB]) {   // read-only path (LDG.CONSTANT)
+  if constexpr (NB == 4) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+  } else {
+    asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+  }
 }
 
 // x = 0, r = b (interleaved from the nb column vectors; missing columns are zero), p = Dinv r
-template <int THREADS>
+template <int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 mpcg_init_kernel(const double* __restrict__ B, int64_t ldb, int nb, const double* __restrict__ dinv,
                  double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, int64_t n, double rtol,
                  double* partials, int pstride, double* scal, int* flags) {
-  double rz[kNB] = {0, 0, 0, 0}, bb[kNB] = {0, 0, 0, 0};
+  double mine[2 * NB];
+#pragma unroll
+  for (int q = 0; q < 2 * NB; ++q) mine[q] = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
     const double d = dinv[g];
-    double b[kNB];
+    double b[NB], z0[NB], pz[NB];
 #pragma unroll
-    for (int q = 0; q < kNB; ++q) b[q] = q < nb ? B[(size_t)q * ldb + g] : 0.0;
-    st4(x + g * kNB, make_double4(0, 0, 0, 0));
-    st4(r + g * kNB, make_double4(b[0], b[1], b[2], b[3]));
-    st4(p + g * kNB, make_double4(d * b[0], d * b[1], d * b[2], d * b[3]));
+    for (int q = 0; q < NB; ++q) { b[q] = q < nb ? B[(size_t)q * ldb + g] : 0.0; z0[q] = 0.0; pz[q] = d * b[q]; }
+    stv<NB>(x + g * NB, z0);
+    stv<NB>(r + g * NB, b);
+    stv<NB>(p + g * NB, pz);
 #pragma unroll
-    for (int q = 0; q < kNB; ++q) { rz[q] += b[q] * d * b[q]; bb[q] += b[q] * b[q]; }
+    for (int q = 0; q < NB; ++q) { mine[q] += b[q] * d * b[q]; mine[NB + q] += b[q] * b[q]; }
   }
-  double mine[2 * kNB], tot[2 * kNB];
-#pragma unroll
-  for (int q = 0; q < kNB; ++q) { mine[q] = rz[q]; mine[kNB + q] = bb[q]; }
-  if (grid_reduce<THREADS, 2 * kNB>(mine, partials, pstride, flags + MFlag::TICKET1, tot)) {
+  double tot[2 * NB];
+  if (grid_reduce<THREADS, 2 * NB>(mine, partials, pstride, flags + MFlag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
       int all = 1;
-      for (int q = 0; q < kNB; ++q) {
+      for (int q = 0; q < 4; ++q) flags[MFlag::DONEQ + q] = 1;   // slots beyond NB stay "done"
+      for (int q = 0; q < NB; ++q) {
         scal[MScal::RZ + q] = tot[q];
-        scal[MScal::BB + q] = tot[kNB + q];
-        scal[MScal::RR + q] = tot[kNB + q];
-        scal[MScal::TOL2 + q] = rtol * rtol * tot[kNB + q];
+        scal[MScal::BB + q] = tot[NB + q];
+        scal[MScal::RR + q] = tot[NB + q];
+        scal[MScal::TOL2 + q] = rtol * rtol * tot[NB + q];
         scal[MScal::BETA + q] = 0.0;
-        const int dq = (tot[kNB + q] == 0.0) ? 1 : 0;
+        const int dq = (tot[NB + q] == 0.0) ? 1 : 0;
         flags[MFlag::DONEQ + q] = dq;
         all &= dq;
       }
@@ -839,8 +855,8 @@ mpcg_init_kernel(const double* __restrict__ B, int64_t ldb, int nb, const double
   }
 }
 
-// q = A p for the four interleaved vectors (masked operator), pq_j = (p_j, q_j)
-template <int THREADS>
+// q = A p for the NB interleaved vectors (masked assembled operator), pq_j = (p_j, q_j)
+template <int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 mpcg_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                  const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
@@ -848,84 +864,93 @@ mpcg_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  double* partials, int pstride, double* scal, int* flags) {
   pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
-  double dot[kNB] = {0, 0, 0, 0};
+  double dot[NB];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) dot[q] = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
     const int node = (int)(g / 6);
     const int r = (int)(g - (int64_t)node * 6);
     const int b0 = __ldg(rowptr + node), b1 = __ldg(rowptr + node + 1);
-    double acc[kNB] = {0, 0, 0, 0};
+    double acc[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) acc[q] = 0.0;
 #pragma unroll 2
     for (int b = b0; b < b1; ++b) {
       const int col = __ldg(colidx + b);
       const double2* a2 = reinterpret_cast<const double2*>(vals + (size_t)b * 36 + r * 6);
       const double2 a01 = __ldcs(a2), a23 = __ldcs(a2 + 1), a45 = __ldcs(a2 + 2);
       const double a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
-      const double* pc = p + (size_t)col * 6 * kNB;
+      const double* pc = p + (size_t)col * 6 * NB;
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        const double4 v = ldg4(pc + c * kNB);
-        acc[0] += a[c] * v.x; acc[1] += a[c] * v.y; acc[2] += a[c] * v.z; acc[3] += a[c] * v.w;
+        double v[NB];
+        ldgv<NB>(pc + c * NB, v);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) acc[q] += a[c] * v[q];
       }
     }
-    const double4 pg = ld4(p + g * kNB);
-    if (!free_mask[g]) { acc[0] = pg.x; acc[1] = pg.y; acc[2] = pg.z; acc[3] = pg.w; }
-    st4(qv + g * kNB, make_double4(acc[0], acc[1], acc[2], acc[3]));
-    dot[0] += pg.x * acc[0]; dot[1] += pg.y * acc[1]; dot[2] += pg.z * acc[2]; dot[3] += pg.w * acc[3];
-  }
-  double mine[kNB], tot[kNB];
+    double pg[NB];
+    ldv<NB>(p + g * NB, pg);
+    if (!free_mask[g]) {
 #pragma unroll
-  for (int q = 0; q < kNB; ++q) mine[q] = dot[q];
-  if (grid_reduce<THREADS, kNB>(mine, partials, pstride, flags + MFlag::TICKET0, tot)) {
+      for (int q = 0; q < NB; ++q) acc[q] = pg[q];
+    }
+    stv<NB>(qv + g * NB, acc);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) dot[q] += pg[q] * acc[q];
+  }
+  double tot[NB];
+  if (grid_reduce<THREADS, NB>(dot, partials, pstride, flags + MFlag::TICKET0, tot)) {
     if (threadIdx.x == 0)
-      for (int q = 0; q < kNB; ++q) scal[MScal::PQ + q] = tot[q];
+      for (int q = 0; q < NB; ++q) scal[MScal::PQ + q] = tot[q];
   }
 }
 
 // x += alpha p, r -= alpha q; rz_new = (r, Dinv r), rr = (r, r); per-vector convergence, beta
-template <int THREADS>
+template <int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict__ p, const double* __restrict__ qv,
                       double* __restrict__ x, double* __restrict__ r, int64_t n, int max_iter,
                       double* partials, int pstride, double* scal, int* flags) {
   pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
-  double alpha[kNB];
+  double alpha[NB];
   bool bad = false;
 #pragma unroll
-  for (int q = 0; q < kNB; ++q) {
+  for (int q = 0; q < NB; ++q) {
     const double pq = scal[MScal::PQ + q];
     const bool dq = flags[MFlag::DONEQ + q] != 0;
     if (!dq && !(pq > 0.0)) bad = true;
     alpha[q] = (dq || !(pq > 0.0)) ? 0.0 : scal[MScal::RZ + q] / pq;
   }
-  double rz[kNB] = {0, 0, 0, 0}, rr[kNB] = {0, 0, 0, 0};
+  double mine[2 * NB];
+#pragma unroll
+  for (int q = 0; q < 2 * NB; ++q) mine[q] = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
     const double d = __ldg(dinv + g);
-    const double4 pv = ld4(p + g * kNB), qq = ld4(qv + g * kNB);
-    double4 xv = ld4(x + g * kNB), rv = ld4(r + g * kNB);
-    xv.x += alpha[0] * pv.x; xv.y += alpha[1] * pv.y; xv.z += alpha[2] * pv.z; xv.w += alpha[3] * pv.w;
-    rv.x -= alpha[0] * qq.x; rv.y -= alpha[1] * qq.y; rv.z -= alpha[2] * qq.z; rv.w -= alpha[3] * qq.w;
-    st4(x + g * kNB, xv);
-    st4(r + g * kNB, rv);
-    rz[0] += rv.x * d * rv.x; rz[1] += rv.y * d * rv.y; rz[2] += rv.z * d * rv.z; rz[3] += rv.w * d * rv.w;
-    rr[0] += rv.x * rv.x; rr[1] += rv.y * rv.y; rr[2] += rv.z * rv.z; rr[3] += rv.w * rv.w;
+    double pv[NB], qq[NB], xv[NB], rv[NB];
+    ldv<NB>(p + g * NB, pv); ldv<NB>(qv + g * NB, qq); ldv<NB>(x + g * NB, xv); ldv<NB>(r + g * NB, rv);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { xv[q] += alpha[q] * pv[q]; rv[q] -= alpha[q] * qq[q]; }
+    stv<NB>(x + g * NB, xv);
+    stv<NB>(r + g * NB, rv);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { mine[q] += rv[q] * d * rv[q]; mine[NB + q] += rv[q] * rv[q]; }
   }
   pdl_trigger();
-  double mine[2 * kNB], tot[2 * kNB];
-#pragma unroll
-  for (int q = 0; q < kNB; ++q) { mine[q] = rz[q]; mine[kNB + q] = rr[q]; }
-  if (grid_reduce<THREADS, 2 * kNB>(mine, partials, pstride, flags + MFlag::TICKET1, tot)) {
+  double tot[2 * NB];
+  if (grid_reduce<THREADS, 2 * NB>(mine, partials, pstride, flags + MFlag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
       const int it = flags[MFlag::ITERS] + 1;
       flags[MFlag::ITERS] = it;
       int all = 1;
-      for (int q = 0; q < kNB; ++q) {
+      for (int q = 0; q < NB; ++q) {
         if (flags[MFlag::DONEQ + q]) continue;     // frozen: its scalars keep the converged values
         const double rz_old = scal[MScal::RZ + q];
         scal[MScal::RZ + q] = tot[q];
-        scal[MScal::RR + q] = tot[kNB + q];
+        scal[MScal::RR + q] = tot[NB + q];
         scal[MScal::BETA + q] = rz_old > 0.0 ? tot[q] / rz_old : 0.0;
-        if (tot[kNB + q] <= scal[MScal::TOL2 + q]) flags[MFlag::DONEQ + q] = 1;
+        if (tot[NB + q] <= scal[MScal::TOL2 + q]) flags[MFlag::DONEQ + q] = 1;
         else all = 0;
       }
       if (bad) { flags[MFlag::BAD] = 1; all = 1; }
@@ -936,80 +961,81 @@ mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict_
 }
 
 // p = Dinv r + beta p (vectors that are done keep their p: it is never used again)
-template <int THREADS>
+template <int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 mpcg_update_p_kernel(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ p, int64_t n,
                      const double* scal, const int* flags) {
   pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
-  double beta[kNB];
+  double beta[NB];
 #pragma unroll
-  for (int q = 0; q < kNB; ++q) beta[q] = scal[MScal::BETA + q];
+  for (int q = 0; q < NB; ++q) beta[q] = scal[MScal::BETA + q];
   for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
     const double d = __ldg(dinv + g);
-    const double4 rv = ld4(r + g * kNB);
-    double4 pv = ld4(p + g * kNB);
-    pv.x = d * rv.x + beta[0] * pv.x; pv.y = d * rv.y + beta[1] * pv.y;
-    pv.z = d * rv.z + beta[2] * pv.z; pv.w = d * rv.w + beta[3] * pv.w;
-    st4(p + g * kNB, pv);
+    double rv[NB], pv[NB];
+    ldv<NB>(r + g * NB, rv); ldv<NB>(p + g * NB, pv);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) pv[q] = d * rv[q] + beta[q] * pv[q];
+    stv<NB>(p + g * NB, pv);
   }
 }
 
+template <int NB>
 __global__ void mpcg_extract_kernel(const double* __restrict__ x, double* __restrict__ X, int64_t ldx, int nb, int64_t n) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
-  const double4 v = ld4(x + g * kNB);
-  const double e[4] = {v.x, v.y, v.z, v.w};
-  for (int q = 0; q < nb; ++q) X[(size_t)q * ldx + g] = e[q];
+  double e[NB];
+  ldv<NB>(x + g * NB, e);
+  for (int q = 0; q < nb && q < NB; ++q) X[(size_t)q * ldx + g] = e[q];
 }
 
-// K_ff X = B for nb <= 4 (already masked) right-hand sides, scalar-Jacobi PCG in lockstep.
-// st->iterations receives the lockstep iteration count, st->spmv_launches the SpMM launches.
-int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
-                    int64_t ldx, femb_stats* st) {
-  if (h->bs != 6 || nb < 1 || nb > kNB) return fail(h, FEMB_ERR_ARG, "multi-RHS PCG: frame operator, 1..4 right-hand sides");
+// K_ff X = B for nb <= NB (already masked) right-hand sides, scalar-Jacobi PCG in lockstep.
+// st->iterations receives the lockstep iteration count, st->spmv_launches the operator launches.
+template <int NB>
+static int pcg_solve_multi_t(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
+                             int64_t ldx, femb_stats* st) {
   const int64_t n = h->ndof;
   const int gridv = vec_grid(h, n, kRowThreads);
   const int pstride = h->num_sms * 8;
   int rc = setup_precond(h, FEMB_PRECOND_JACOBI);
   if (rc) return rc;
-  FEMB_CUDA(h, h->mx.ensure((size_t)n * kNB));
-  FEMB_CUDA(h, h->mr.ensure((size_t)n * kNB));
-  FEMB_CUDA(h, h->mp.ensure((size_t)n * kNB));
-  FEMB_CUDA(h, h->mq.ensure((size_t)n * kNB));
-  FEMB_CUDA(h, h->mpartials.ensure((size_t)pstride * 3 * kNB));
+  FEMB_CUDA(h, h->mx.ensure((size_t)n * NB));
+  FEMB_CUDA(h, h->mr.ensure((size_t)n * NB));
+  FEMB_CUDA(h, h->mp.ensure((size_t)n * NB));
+  FEMB_CUDA(h, h->mq.ensure((size_t)n * NB));
+  FEMB_CUDA(h, h->mpartials.ensure((size_t)pstride * 3 * 4));
   FEMB_CUDA(h, h->mscal.ensure(MScal::COUNT));
   FEMB_CUDA(h, h->mflags.ensure(MFlag::COUNT));
   FEMB_CUDA(h, cudaMemsetAsync(h->mflags.p, 0, sizeof(int32_t) * MFlag::COUNT, h->stream));
-  double* part0 = h->mpartials.p;                 // SpMM: kNB arrays
-  double* part1 = h->mpartials.p + (size_t)pstride * kNB;   // init / update: 2*kNB arrays
+  double* part0 = h->mpartials.p;                          // operator: NB arrays
+  double* part1 = h->mpartials.p + (size_t)pstride * 4;    // init / update: 2*NB arrays
   const int max_iter = o.max_iter > 0 ? o.max_iter : 200000;
-  mpcg_init_kernel<kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(d_B, ldb, nb, h->Dinv.p, h->mx.p, h->mr.p, h->mp.p, n,
-                                                                       o.rtol, part1, pstride, h->mscal.p, h->mflags.p);
+  mpcg_init_kernel<NB, kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(d_B, ldb, nb, h->Dinv.p, h->mx.p, h->mr.p, h->mp.p, n,
+                                                                           o.rtol, part1, pstride, h->mscal.p, h->mflags.p);
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   struct Peek { int32_t flags[MFlag::COUNT]; double scal[MScal::COUNT]; };
   Peek* peek = reinterpret_cast<Peek*>(h->pinned);
   const int check = o.check_every > 0 ? o.check_every : 50;
   const bool ebe = ebe_selected(h, o.op);
-  const int grid_xr = occ_grid(h, mpcg_update_xr_kernel<kRowThreads>, n, kRowThreads);
-  const int grid_mm = occ_grid(h, mpcg_spmm_kernel<kRowThreads>, n, kRowThreads);
+  const int grid_xr = occ_grid(h, mpcg_update_xr_kernel<NB, kRowThreads>, n, kRowThreads);
+  const int grid_mm = occ_grid(h, mpcg_spmm_kernel<NB, kRowThreads>, n, kRowThreads);
   int it = 0, all = 0, spmm = 0;
   while (!all && it < max_iter) {
     const int batch = std::min(check, max_iter - it);
     for (int k = 0; k < batch; ++k, ++it) {
       if (ebe) {
-        rc = launch_ebe(h, h->mp.p, h->mq.p, kNB, true, part0, h->mscal.p + MScal::PQ, h->mflags.p + MFlag::TICKET0,
+        rc = launch_ebe(h, h->mp.p, h->mq.p, NB, true, part0, h->mscal.p + MScal::PQ, h->mflags.p + MFlag::TICKET0,
                         h->mflags.p + MFlag::ALLDONE, nullptr);
         if (rc) return rc;
         h->launches--;   // counted with the two update kernels below
       } else {
-        mpcg_spmm_kernel<kRowThreads><<<grid_mm, kRowThreads, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p,
-                                                                             h->mp.p, h->mq.p, n, part0, pstride, h->mscal.p, h->mflags.p);
+        mpcg_spmm_kernel<NB, kRowThreads><<<grid_mm, kRowThreads, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p,
+                                                                                   h->mp.p, h->mq.p, n, part0, pstride, h->mscal.p, h->mflags.p);
       }
-      launch_pdl(mpcg_update_xr_kernel<kRowThreads>, grid_xr, kRowThreads, h->stream, h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n,
+      launch_pdl(mpcg_update_xr_kernel<NB, kRowThreads>, grid_xr, kRowThreads, h->stream, h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n,
                  max_iter, part1, pstride, h->mscal.p, h->mflags.p);
-      launch_pdl(mpcg_update_p_kernel<kRowThreads>, gridv, kRowThreads, h->stream, h->Dinv.p, h->mr.p, h->mp.p, n, h->mscal.p, h->mflags.p);
+      launch_pdl(mpcg_update_p_kernel<NB, kRowThreads>, gridv, kRowThreads, h->stream, h->Dinv.p, h->mr.p, h->mp.p, n, h->mscal.p, h->mflags.p);
       h->launches += 3;
       ++spmm;
     }
@@ -1019,7 +1045,7 @@ int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B,
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
     all = peek->flags[MFlag::ALLDONE];
   }
-  mpcg_extract_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->mx.p, d_X, ldx, nb, n);
+  mpcg_extract_kernel<NB><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->mx.p, d_X, ldx, nb, n);
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   bool conv = true;
@@ -1040,6 +1066,13 @@ int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B,
   if (peek->flags[MFlag::BAD]) return fail(h, FEMB_ERR_SINGULAR, "multi-RHS PCG breakdown: p^T K p <= 0 (K_ff is not positive definite)");
   if (!conv) return fail(h, FEMB_ERR_NOT_CONVERGED, "multi-RHS PCG did not reach rtol within max_iter");
   return FEMB_OK;
+}
+
+int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
+                    int64_t ldx, femb_stats* st) {
+  if (h->bs != 6 || nb < 1 || nb > 4) return fail(h, FEMB_ERR_ARG, "multi-RHS PCG: frame operator, 1..4 right-hand sides");
+  if (nb <= 2) return pcg_solve_multi_t<2>(h, o, d_B, ldb, nb, d_X, ldx, st);
+  return pcg_solve_multi_t<4>(h, o, d_B, ldb, nb, d_X, ldx, st);
 }
 
 }  // namespace femb

@@ -78,7 +78,9 @@ typedef struct {
 
 typedef struct {
   int32_t k;             /* number of lowest modes wanted                                  */
-  int32_t block;         /* Krylov block size 1..4 (0 = 4); >= multiplicity of eigenvalues  */
+  int32_t block;         /* Krylov block size 1..4; 0 = 4 behind a factorisation (chain / dense), 2 behind
+                            PCG (every solve costs thousands of iterations); use >= the multiplicity
+                            of the wanted eigenvalues                                              */
   int32_t max_iter;      /* default 5000                                                   */
   int32_t op;            /* FEMB_OP_* of the inner shift-invert solves   default AUTO             */
   double rtol;           /* ||K phi - lambda M phi|| <= rtol*||K phi||   default 1e-8      */
