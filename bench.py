@@ -134,7 +134,8 @@ def sample_text(s, iters):
             f"({s['n_elem']} elements, {s['n_free']} free DOF): numpy element formation + scipy COO->CSR "
             f"({s['t_assemble']:.2f} s) + {SAMPLE_ITERS} Jacobi-PCG iterations ({s['t_per_iter']*1e3:.2f} ms each); "
             f"scaled linearly in elements to 498,848 elements and to the {iters} iterations the same "
-            f"Jacobi-PCG needs at full size for rtol 1e-12")
+            f"Jacobi-PCG needs at full size for rtol 1e-12; scipy's sparse mat-vec and the numpy vector updates that "
+            f"make up >97 % of this time are single-threaded (cores = 1)")
 
 
 JACOBI_ITERS_FULL = 6931  # Jacobi-PCG iterations at full size, rtol 1e-12 (profiles/r01_*, measured on B200)
@@ -264,7 +265,7 @@ def run_gpu(args):
                     "note": "algorithmic bytes are the kernel's own compulsory traffic (16 B/pair + node records + "
                             "coordinates + x + y + mask = 40 MB), 9x fewer than the 359 MB the assembled SpMV streams for "
                             "the same product; the kernel is FP64-issue / gather-latency bound, not HBM bound (ncu: FP64 "
-                            "pipe 41 %, DRAM 13 % of peak) — see roofline_bsr_spmv for the HBM-bound form of the product",
+                            "pipe 34-41 %, DRAM 13 % of peak) — see roofline_bsr_spmv for the HBM-bound form of the product",
                     "equivalent_bsr_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9}
     else:
         roofline = {"kernel": "bsr_spmv_kernel<6,masked,dot,192,2> (inside PCG, every 8th launch timed)", "bound": "hbm",
