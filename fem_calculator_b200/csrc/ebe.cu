@@ -24,7 +24,8 @@
 // a three-stage software pipeline over the pair loop (record two ahead, operands one ahead) 21.7 us;
 // per-element records stored after assembly (128 B: t, n1, magnitudes) and read back per pair
 // 28.5-31 us — the gathers, not the FP64 work, set the time (ncu: FP64 pipe 41 %, DRAM 13 %), which
-// is also why trimming the record from ~100 to ~75 FP64 instructions did not move it.  Four vectors:
+// is also why trimming the record from ~100 to ~75 FP64 instructions did not move it, nor did padded
+// coordinates with one 32-byte gather per node and 32-byte section-row loads (21.7 us).  Four vectors:
 // 2 vectors per lane / 2 lanes per node 53 us against 96 us for the shared-memory form and 123 us for
 // the assembled SpMM.
 //
