@@ -46,7 +46,8 @@ struct Tet10El {
   struct Rec {};
   __device__ __forceinline__ void kblock(uint32_t code, Rec&, double* acc) const {
     const uint32_t e = code / 100u, ab = code % 100u;
-    tet10_kblock(P, e, ab / 10u, ab % 10u, ab == 0u, acc);
+    if (P.grad) tet10_kblock_stored(P, e, ab / 10u, ab % 10u, acc);   // two-stage: point records from the pre-pass
+    else tet10_kblock(P, e, ab / 10u, ab % 10u, ab == 0u, acc);
   }
   __device__ __forceinline__ bool has_mass(uint32_t) const { return false; }
   __device__ __forceinline__ void mblock(uint32_t, const Rec&, double*) const {}
@@ -316,6 +317,39 @@ __global__ void frame_elements_kernel(FrameParams P, int64_t n_elem, double* __r
   }
 }
 
+// pre-pass of the two-stage Tet10 assembly: one thread per (element, Gauss point)
+__global__ void tet10_point_records_kernel(Tet10Params P, int64_t n_elem, double* __restrict__ grad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_elem * 4) return;
+  tet10_point_record(P, (uint32_t)(t >> 2), (int)(t & 3), grad + (size_t)t * kTetGradStride);
+}
+
+// second stage: one thread per 3x3 block of K walks the block's contribution list (element-ascending,
+// fixed by the symbolic phase) and adds the contributions in registers — no barriers, no atomics, one
+// 72-byte store per block.  (The generic tile kernel spends its time in the rank loop: a Tet10 block
+// collects up to ~24 contributions, one CTA barrier each.)
+__global__ void __launch_bounds__(128)
+tet10_block_gather_kernel(const Tet10Params P, const int32_t* __restrict__ contrib_ptr, const uint32_t* __restrict__ contrib,
+                          int64_t nnzb, double* __restrict__ Kvals) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  const int c0 = __ldg(contrib_ptr + b), c1 = __ldg(contrib_ptr + b + 1);
+  for (int c = c0; c < c1; ++c) {
+    const uint32_t code = __ldg(contrib + c);
+    const uint32_t e = code / 100u, ab = code % 100u;
+    double t[9];
+    tet10_kblock_stored(P, e, (int)(ab / 10u), (int)(ab % 10u), t);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] += t[k];
+  }
+  double* o = Kvals + (size_t)b * 9;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) o[k] = acc[k];
+}
+
 __global__ void tet10_elements_kernel(Tet10Params P, int64_t n_elem, double* __restrict__ ke) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_elem * 100) return;
@@ -342,6 +376,7 @@ static Tet10Params tet10_params(const femb_handle* h) {
   const double C2 = (1.0 - 2.0 * h->nu) / 2.0;                      // :90
   P.lam = C1 * h->nu; P.mu2 = C1 * (1.0 - h->nu); P.gsh = C1 * C2;
   P.skipped = h->counters.p;
+  P.grad = nullptr;
   return P;
 }
 
@@ -430,6 +465,21 @@ int launch_assemble(femb_handle* h) {
     FEMB_CUDA(h, cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * h->counters.n, h->stream));
     Tet10El el;
     el.P = tet10_params(h);
+    static int one_stage = -1;   // FEMB_TET10_ONE_STAGE=1: every contribution thread evaluates the Jacobians itself
+    if (one_stage < 0) { const char* e = getenv("FEMB_TET10_ONE_STAGE"); one_stage = (e && e[0] == '1') ? 1 : 0; }
+    if (!one_stage && h->n_elem > 0) {
+      FEMB_CUDA(h, h->tet_grad.ensure((size_t)h->n_elem * 4 * kTetGradStride));
+      const int64_t nt = h->n_elem * 4;
+      tet10_point_records_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, h->stream>>>(el.P, h->n_elem, h->tet_grad.p);
+      h->launches++;
+      FEMB_CUDA(h, cudaGetLastError());
+      el.P.grad = h->tet_grad.p;
+      const int64_t nnzb = h->sym.nnzb;
+      tet10_block_gather_kernel<<<(unsigned)((nnzb + 127) / 128), 128, 0, h->stream>>>(el.P, h->contrib_ptr.p, h->contrib.p, nnzb, h->Kvals.p);
+      h->launches++;
+      FEMB_CUDA(h, cudaGetLastError());
+      return FEMB_OK;
+    }
     return launch_assemble_t(h, el);
   }
   return fail(h, FEMB_ERR_ARG, "no mesh set");

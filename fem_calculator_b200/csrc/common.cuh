@@ -117,6 +117,7 @@ struct femb_handle {
   bool pairs_dev_ok = false;        // pair records uploaded (frame fast path usable)
   femb::DevBuf<double> Kvals;      // (nnzb, bs, bs)
   femb::DevBuf<double> Mdiag;      // (n_nodes, bs, bs) frame only
+  femb::DevBuf<double> tet_grad;   // (n_elem,4,32) Tet10 Gauss-point records of the two-stage assembly
   femb::DevBuf<unsigned long long> counters;  // device scalars: [0] skipped gauss points
   int64_t neg_detj = 0;
 
