@@ -342,7 +342,9 @@ def run_gpu(args):
     # end-to-end through the reference-shaped entry point, host buffers in / out
     e2e_steps = max(1, min(args.steps, 3))
     w = compat.BeamAnalysisB200(mesh, sec, bc, E, nu, device=local)
-    w.run_simulation(k_modes=0, solver=L.SOLVER_PCG, rtol=RTOL)  # warm-up (context, allocator)
+    tc = time.perf_counter()
+    w.run_simulation(k_modes=0, solver=L.SOLVER_PCG, rtol=RTOL)  # warm-up (context, allocator, symbolic analysis)
+    e2e_first_call_s = time.perf_counter() - tc
     L.io_bytes(reset=True)
     barrier()
     t0 = time.perf_counter()
@@ -358,8 +360,13 @@ def run_gpu(args):
         e2e_s = float(t.item())
     e2e = {"value": world * n_free / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": h2d // e2e_steps,
            "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "first_call_ms": e2e_first_call_s * 1e3,
            "api": "fem_calculator_b200.compat.BeamAnalysisB200.run_simulation (BeamSolver.py:345 signature), "
-                  "timed with the host clock around the call"}
+                  "timed with the host clock around the call; every call takes coordinates, connectivity, sections, "
+                  "BCs and loads as host numpy arrays, copies coordinates / section data / loads / BCs to the device and "
+                  "returns u / reactions / stresses to the host; the connectivity is compared with the previous call's and "
+                  "the symbolic analysis (block pattern, pair records, 62 MB of device tables) is rebuilt and re-uploaded only "
+                  "when it changed — first_call_ms is a call that builds it"}
 
     out = {"metric": "static_solve_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

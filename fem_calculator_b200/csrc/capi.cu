@@ -89,18 +89,27 @@ static int set_mesh_common(femb_handle* h, Kind kind, int bs, int nper, int64_t 
   if (n_nodes * bs >= (int64_t)INT32_MAX || n_elem * nper * nper >= (int64_t)UINT32_MAX)
     return fail(h, FEMB_ERR_ARG, "mesh too large for 32-bit indices on one device");
   FEMB_CUDA(h, cudaSetDevice(h->device));
-  h->h_conn.resize((size_t)(n_elem * nper));
-  for (size_t i = 0; i < h->h_conn.size(); ++i) {
+  // Same connectivity as the mesh already held (the usual re-run: new loads, sections or coordinates on
+  // the same topology)?  Then the symbolic analysis — block pattern, contribution lists, pair records,
+  // all functions of the connectivity alone — and its device copies stay valid.
+  bool same_topology = h->have_symbolic && h->kind == kind && h->bs == bs && h->n_nodes == n_nodes &&
+                       h->n_elem == n_elem && h->h_conn.size() == (size_t)(n_elem * nper);
+  for (size_t i = 0; i < (size_t)(n_elem * nper); ++i) {
     if (conn[i] < 0 || conn[i] >= n_nodes) return fail(h, FEMB_ERR_ARG, "connectivity index out of range");
-    h->h_conn[i] = (int32_t)conn[i];
+    if (same_topology && h->h_conn[i] != (int32_t)conn[i]) same_topology = false;
+  }
+  if (!same_topology) {
+    h->h_conn.resize((size_t)(n_elem * nper));
+    for (size_t i = 0; i < h->h_conn.size(); ++i) h->h_conn[i] = (int32_t)conn[i];
   }
   h->kind = kind; h->bs = bs;
   h->n_nodes = n_nodes; h->n_elem = n_elem; h->ndof = n_nodes * bs;
-  h->have_symbolic = h->assembled = h->have_bc = h->have_solution = false;
+  h->have_symbolic = same_topology;
+  h->assembled = h->have_bc = h->have_solution = false;
   h->n_owned_nodes = 0;
   h->spmv_tile_nodes = 0;
   FEMB_CUDA(h, upload(h->xyz, xyz, (size_t)n_nodes * 3, h->stream));
-  FEMB_CUDA(h, upload(h->conn, h->h_conn, h->stream));
+  if (!same_topology) FEMB_CUDA(h, upload(h->conn, h->h_conn, h->stream));
   FEMB_CUDA(h, h->counters.alloc(4));
   FEMB_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 4 * sizeof(unsigned long long), h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));  // caller may free its buffers now
@@ -116,8 +125,12 @@ int femb_frame_set_mesh(femb_handle* h, int64_t n_nodes, int64_t n_elem, const d
     if (elem_sec[e] < 0 || elem_sec[e] >= n_sec) return fail(h, FEMB_ERR_ARG, "element section index out of range");
   int rc = set_mesh_common(h, Kind::Frame, 6, 2, n_nodes, n_elem, xyz, conn);
   if (rc) return rc;
+  // the pair records carry each element's section index: a changed assignment invalidates them
+  const bool same_sections = h->have_symbolic && h->n_sec == n_sec && h->h_elem_sec.size() == (size_t)n_elem &&
+                             std::equal(elem_sec, elem_sec + n_elem, h->h_elem_sec.begin());
+  if (!same_sections) h->have_symbolic = false;
   h->E = E; h->G = G; h->rho = rho; h->n_sec = n_sec;
-  h->h_elem_sec.assign(elem_sec, elem_sec + n_elem);
+  if (!same_sections) h->h_elem_sec.assign(elem_sec, elem_sec + n_elem);
   FEMB_CUDA(h, upload(h->elem_sec, elem_sec, (size_t)n_elem, h->stream));
   FEMB_CUDA(h, upload(h->sec_props, sec_props, (size_t)n_sec * 8, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));

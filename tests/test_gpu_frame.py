@@ -259,3 +259,33 @@ def test_full_size_c3_properties():
     F = f.reshape(-1, 6)[:, :3].sum(axis=0)
     assert np.abs(R + F).max() <= 1e-7 * np.abs(F).max()                 # sum of reactions = -sum of loads
     assert np.all(u[fixed] == 0.0) and np.isfinite(u).all()
+
+
+def test_same_topology_reuses_symbolic_analysis_correctly():
+    """Re-running on the same connectivity keeps the symbolic analysis (pattern, pair records): new
+    coordinates, new section assignment and a new topology must each give the oracle's K."""
+    E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+    m = FrameModel(0)
+    variants = []
+    mesh, sec, bc = meshgen.lattice_frame_case(5, 4, 4, jitter=0.0)
+    es, props, _ = compat.frame_section_table(mesh, sec, csp)
+    conn = mesh.cells_dict["line"]
+    variants.append((mesh.points, conn, es))
+    mesh2, _, _ = meshgen.lattice_frame_case(5, 4, 4, jitter=0.08)
+    variants.append((mesh2.points, conn, es))                       # same topology, new coordinates
+    variants.append((mesh2.points, conn, (es + 1) % len(props)))    # new section assignment
+    variants.append((mesh2.points, conn[::-1].copy(), es[::-1].copy()))   # new element order -> new topology
+    for pts, cn, sec_ids in variants:
+        m.set_mesh(pts, cn, sec_ids, props, E, E / (2 * (1 + nu)))
+        m.assemble()
+        indptr, indices, data = m.get_csr(L.MAT_K)
+        Ko, _ = S.frame_assemble(pts, cn, sec_ids, props, E, nu)
+        assert np.array_equal(indptr, Ko.indptr) and np.array_equal(indices, Ko.indices)
+        assert np.abs(data - Ko.data).max() <= 1e-14 * np.abs(Ko.data).max()
+        fixed, f = compat.frame_bc_vectors(mesh, bc, len(pts))
+        m.set_bc(fixed, f)
+        u, _, st = m.solve_static(method=L.SOLVER_PCG)
+        _, free, _ = S.frame_bc(mesh, bc)
+        uo, _ = S.solve_static(Ko, f, fixed, free, method="direct")
+        assert np.linalg.norm(u - uo) <= 1e-10 * np.linalg.norm(uo)
+    m.close()
