@@ -110,12 +110,12 @@ frame_ebe_node_kernel(const FrameParams P, const int4* __restrict__ pair_rec, co
   constexpr int LPN = QS * T;
   constexpr int NPC = THREADS / LPN;   // nodes per CTA and step
   static_assert(32 % LPN == 0 && THREADS % 32 == 0, "a node's lanes share a warp");
-  static_assert(!LINK || (DOT && NBT == 1), "linked reductions: single-vector PCG");
-  if (LINK) {
+  static_assert(!LINK || DOT, "linked reductions publish the (x, y) partials");
+  if (LINK && NBT == 1) {
     __shared__ double s_link[2 * THREADS / 32];
     if (link.flags[Flag::DONE]) return;
     if (pcg_link_decide<THREADS>(link, s_link)) return;
-  } else if (DOT && done && *done) {
+  } else if (DOT && done && *done) {   // lockstep PCG (NBT > 1), linked or not: early-exit flag of the caller
     return;
   }
   if (DOT && !LINK && NBT == 1 && p2p) {
@@ -212,10 +212,22 @@ frame_ebe_node_kernel(const FrameParams P, const int4* __restrict__ pair_rec, co
     }
   }
   if (LINK) {
-    __shared__ double s_pub[THREADS / 32];
-    double v[1] = {dot[0]};
-    block_sum_all<THREADS, 1>(v, s_pub);
-    if (threadIdx.x == 0) link.op_partials[blockIdx.x] = v[0];
+    // publish this CTA's partial sums, one array per vector: op_partials[q * pstride + cta]
+    __shared__ double s_pub[NBT * THREADS / 32];
+    double mine[NBT];
+#pragma unroll
+    for (int q = 0; q < NBT; ++q) mine[q] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+#pragma unroll
+      for (int g = 0; g < QS; ++g)
+        if (g == qg) mine[g * NB + q] = dot[q];
+    }
+    block_sum_all<THREADS, NBT>(mine, s_pub);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int q = 0; q < NBT; ++q) link.op_partials[(size_t)q * link.pstride + blockIdx.x] = mine[q];
+    }
   } else if (DOT) {
     double mine[NBT], tot[NBT];
 #pragma unroll
@@ -313,13 +325,17 @@ int launch_ebe(femb_handle* h, const double* x, double* y, int nb, bool masked, 
 #define EBE(NBT, NB, T, M, D, LK, MINB)                                                                      \
   frame_ebe_node_kernel<NBT, NB, T, M, D, LK, kEbeThreads, MINB><<<grid, kEbeThreads, 0, h->stream>>>(        \
       P, pr, nr, n_nodes, h->free_mask.p, x, y, dot_partials, pstride, scal_out, ticket, done, LK ? *link : nolink, p2p)
+  if (link && !masked) return fail(h, FEMB_ERR_ARG, "linked operator launch is masked");
   if (nb == 1) {
     if (link) {
-      if (!masked) return fail(h, FEMB_ERR_ARG, "linked operator launch is masked");
       EBE(1, 1, 2, true, true, true, kEbe1CtasPerSm);
     } else if (masked && dot_partials) EBE(1, 1, 2, true, true, false, kEbe1CtasPerSm);
     else if (masked) EBE(1, 1, 2, true, false, false, kEbe1CtasPerSm);
     else EBE(1, 1, 2, false, false, false, kEbe1CtasPerSm);
+  } else if (nb == 4 && link) {
+    EBE(4, 2, 1, true, true, true, kEbe4CtasPerSm);
+  } else if (nb == 2 && link) {
+    EBE(2, 2, 2, true, true, true, kEbe4CtasPerSm);
   } else if (nb == 4 && !link) {
     if (masked && dot_partials) EBE(4, 2, 1, true, true, false, kEbe4CtasPerSm);
     else if (masked) EBE(4, 2, 1, true, false, false, kEbe4CtasPerSm);

@@ -980,6 +980,156 @@ mpcg_update_p_kernel(const double* __restrict__ dinv, const double* __restrict__
   }
 }
 
+// ---- linked lockstep iteration (matrix-free operator): the operator publishes its (p_q, A p_q)
+// partials, the x/r kernel consumes them and publishes {rz_q, rr_q}, the p kernel consumes those,
+// decides per-vector convergence and beta.  No ticket / last-CTA tails; rz and the per-vector done
+// flags travel through parity-indexed slots (slot it & 1 is read in iteration it, (it+1) & 1 written).
+struct MLink {
+  double* op_partials;    // [NB][pstride]
+  double* xr_partials;    // [2 buffers][2 NB][pstride]
+  double* scal;           // MScal layout; RZ lives in two parity slots: RZ + 4 * parity ... see MLScal
+  int* flags;
+  int n_op, n_xr, pstride;
+  int it, max_iter;
+};
+struct MLScal { enum { RZ0 = 0, RZ1 = 4, RR = 8, BB = 12, TOL2 = 16, COUNT = 24 }; };
+struct MLFlag { enum { DONEQ0 = 0, DONEQ1 = 4, ALLDONE = 8, ITERS = 9, BAD = 10, COUNT = 12 }; };
+
+template <int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mpcg_init_linked_kernel(const double* __restrict__ B, int64_t ldb, int nb, const double* __restrict__ dinv,
+                        double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, int64_t n, double rtol,
+                        double* partials, int pstride, int* ticket, double* scal, int* flags) {
+  double mine[2 * NB];
+#pragma unroll
+  for (int q = 0; q < 2 * NB; ++q) mine[q] = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const double d = dinv[g];
+    double b[NB], z0[NB], pz[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { b[q] = q < nb ? B[(size_t)q * ldb + g] : 0.0; z0[q] = 0.0; pz[q] = d * b[q]; }
+    stv<NB>(x + g * NB, z0);
+    stv<NB>(r + g * NB, b);
+    stv<NB>(p + g * NB, pz);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { mine[q] += b[q] * d * b[q]; mine[NB + q] += b[q] * b[q]; }
+  }
+  double tot[2 * NB];
+  if (grid_reduce<THREADS, 2 * NB>(mine, partials, pstride, ticket, tot)) {   // once per solve
+    if (threadIdx.x == 0) {
+      int all = 1;
+      for (int q = 0; q < 4; ++q) { flags[MLFlag::DONEQ0 + q] = 1; flags[MLFlag::DONEQ1 + q] = 1; }
+      for (int q = 0; q < NB; ++q) {
+        scal[MLScal::RZ0 + q] = tot[q];
+        scal[MLScal::BB + q] = tot[NB + q];
+        scal[MLScal::RR + q] = tot[NB + q];
+        scal[MLScal::TOL2 + q] = rtol * rtol * tot[NB + q];
+        const int dq = (tot[NB + q] == 0.0) ? 1 : 0;
+        flags[MLFlag::DONEQ0 + q] = dq;
+        all &= dq;
+      }
+      flags[MLFlag::ALLDONE] = all;
+      flags[MLFlag::ITERS] = 0;
+      flags[MLFlag::BAD] = 0;
+    }
+  }
+}
+
+template <int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mpcg_update_xr_linked_kernel(const double* __restrict__ dinv, const double* __restrict__ p, const double* __restrict__ qv,
+                             double* __restrict__ x, double* __restrict__ r, int64_t n, const MLink L) {
+  __shared__ double s_part[2 * NB * THREADS / 32];
+  if (L.flags[MLFlag::ALLDONE]) return;
+  const int par = L.it & 1;
+  double pq[NB];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) pq[q] = 0.0;
+  for (int i = threadIdx.x; i < L.n_op; i += THREADS) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) pq[q] += __ldcg(L.op_partials + (size_t)q * L.pstride + i);
+  }
+  block_sum_all<THREADS, NB>(pq, s_part);
+  double alpha[NB];
+  bool bad = false;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const bool dq = L.flags[MLFlag::DONEQ0 + 4 * par + q] != 0;
+    if (!dq && !(pq[q] > 0.0)) bad = true;
+    alpha[q] = (dq || !(pq[q] > 0.0)) ? 0.0 : L.scal[MLScal::RZ0 + 4 * par + q] / pq[q];
+  }
+  if (bad) {                                  // K_ff not positive definite along some p_q
+    if (blockIdx.x == 0 && threadIdx.x == 0) { L.flags[MLFlag::BAD] = 1; L.flags[MLFlag::ALLDONE] = 1; }
+    return;
+  }
+  double mine[2 * NB];
+#pragma unroll
+  for (int q = 0; q < 2 * NB; ++q) mine[q] = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const double d = __ldg(dinv + g);
+    double pv[NB], qq[NB], xv[NB], rv[NB];
+    ldv<NB>(p + g * NB, pv); ldv<NB>(qv + g * NB, qq); ldv<NB>(x + g * NB, xv); ldv<NB>(r + g * NB, rv);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { xv[q] += alpha[q] * pv[q]; rv[q] -= alpha[q] * qq[q]; }
+    stv<NB>(x + g * NB, xv);
+    stv<NB>(r + g * NB, rv);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { mine[q] += rv[q] * d * rv[q]; mine[NB + q] += rv[q] * rv[q]; }
+  }
+  block_sum_all<THREADS, 2 * NB>(mine, s_part);
+  if (threadIdx.x == 0) {
+    double* po = L.xr_partials + (size_t)par * 2 * NB * L.pstride;
+#pragma unroll
+    for (int v = 0; v < 2 * NB; ++v) po[(size_t)v * L.pstride + blockIdx.x] = mine[v];
+  }
+}
+
+template <int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mpcg_update_p_linked_kernel(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ p, int64_t n,
+                            const MLink L) {
+  __shared__ double s_part[2 * NB * THREADS / 32];
+  if (L.flags[MLFlag::ALLDONE]) return;
+  const int par = L.it & 1;
+  double tot[2 * NB];
+#pragma unroll
+  for (int v = 0; v < 2 * NB; ++v) tot[v] = 0.0;
+  {
+    const double* pi = L.xr_partials + (size_t)par * 2 * NB * L.pstride;
+    for (int i = threadIdx.x; i < L.n_xr; i += THREADS) {
+#pragma unroll
+      for (int v = 0; v < 2 * NB; ++v) tot[v] += __ldcg(pi + (size_t)v * L.pstride + i);
+    }
+  }
+  block_sum_all<THREADS, 2 * NB>(tot, s_part);
+  double beta[NB];
+  int all = 1;
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const bool dq = L.flags[MLFlag::DONEQ0 + 4 * par + q] != 0;
+    const double rz_old = L.scal[MLScal::RZ0 + 4 * par + q];
+    beta[q] = (!dq && rz_old > 0.0) ? tot[q] / rz_old : 0.0;
+    const int ndq = (dq || tot[NB + q] <= L.scal[MLScal::TOL2 + q]) ? 1 : 0;
+    all &= ndq;
+    if (lead) {   // frozen vectors keep their converged scalars
+      L.scal[MLScal::RZ0 + 4 * (par ^ 1) + q] = dq ? rz_old : tot[q];
+      if (!dq) L.scal[MLScal::RR + q] = tot[NB + q];
+      L.flags[MLFlag::DONEQ0 + 4 * (par ^ 1) + q] = ndq;
+    }
+  }
+  if (L.it + 1 >= L.max_iter) all = 1;
+  if (lead) { L.flags[MLFlag::ITERS] = L.it + 1; if (all) L.flags[MLFlag::ALLDONE] = 1; }
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
+    const double d = __ldg(dinv + g);
+    double rv[NB], pv[NB];
+    ldv<NB>(r + g * NB, rv); ldv<NB>(p + g * NB, pv);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) pv[q] = d * rv[q] + beta[q] * pv[q];
+    stv<NB>(p + g * NB, pv);
+  }
+}
+
 template <int NB>
 __global__ void mpcg_extract_kernel(const double* __restrict__ x, double* __restrict__ X, int64_t ldx, int nb, int64_t n) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -991,6 +1141,82 @@ __global__ void mpcg_extract_kernel(const double* __restrict__ x, double* __rest
 
 // K_ff X = B for nb <= NB (already masked) right-hand sides, scalar-Jacobi PCG in lockstep.
 // st->iterations receives the lockstep iteration count, st->spmv_launches the operator launches.
+template <int NB>
+static int pcg_solve_multi_linked(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
+                                  int64_t ldx, femb_stats* st) {
+  const int64_t n = h->ndof;
+  const int gridv = vec_grid(h, n, kRowThreads);
+  const int pstride = h->num_sms * 8;
+  int rc = setup_precond(h, FEMB_PRECOND_JACOBI);
+  if (rc) return rc;
+  FEMB_CUDA(h, h->mx.ensure((size_t)n * NB));
+  FEMB_CUDA(h, h->mr.ensure((size_t)n * NB));
+  FEMB_CUDA(h, h->mp.ensure((size_t)n * NB));
+  FEMB_CUDA(h, h->mq.ensure((size_t)n * NB));
+  FEMB_CUDA(h, h->mpartials.ensure((size_t)pstride * (4 + 16 + 8)));   // operator [4], x/r [2][8], init [8]
+  FEMB_CUDA(h, h->mscal.ensure(MLScal::COUNT));
+  FEMB_CUDA(h, h->mflags.ensure(MLFlag::COUNT + 1));
+  FEMB_CUDA(h, cudaMemsetAsync(h->mflags.p, 0, sizeof(int32_t) * (MLFlag::COUNT + 1), h->stream));
+  constexpr int UT = 256;
+  const int grid_xr = occ_grid(h, mpcg_update_xr_linked_kernel<NB, UT>, n, UT);
+  const int grid_p = occ_grid(h, mpcg_update_p_linked_kernel<NB, UT>, n, UT);
+  const int max_iter = o.max_iter > 0 ? o.max_iter : 200000;
+  MLink L;
+  L.op_partials = h->mpartials.p; L.xr_partials = h->mpartials.p + (size_t)4 * pstride;
+  L.scal = h->mscal.p; L.flags = h->mflags.p;
+  L.n_op = ebe_grid(h, NB, h->n_nodes); L.n_xr = grid_xr; L.pstride = pstride; L.it = 0; L.max_iter = max_iter;
+  mpcg_init_linked_kernel<NB, kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(
+      d_B, ldb, nb, h->Dinv.p, h->mx.p, h->mr.p, h->mp.p, n, o.rtol, h->mpartials.p + (size_t)20 * pstride, pstride,
+      h->mflags.p + MLFlag::COUNT, h->mscal.p, h->mflags.p);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  struct Peek { int32_t flags[MLFlag::COUNT]; double scal[MLScal::COUNT]; };
+  Peek* peek = reinterpret_cast<Peek*>(h->pinned);
+  const int check = o.check_every > 0 ? o.check_every : 50;
+  PcgLink opl = {};                 // the operator kernel only needs where to publish
+  opl.op_partials = L.op_partials; opl.pstride = pstride; opl.flags = h->mflags.p;
+  int it = 0, all = 0, spmm = 0;
+  while (!all && it < max_iter) {
+    const int batch = std::min(check, max_iter - it);
+    for (int k = 0; k < batch; ++k, ++it) {
+      L.it = it;
+      rc = launch_ebe(h, h->mp.p, h->mq.p, NB, true, nullptr, nullptr, nullptr, h->mflags.p + MLFlag::ALLDONE, &opl);
+      if (rc) return rc;
+      mpcg_update_xr_linked_kernel<NB, UT><<<grid_xr, UT, 0, h->stream>>>(h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n, L);
+      mpcg_update_p_linked_kernel<NB, UT><<<grid_p, UT, 0, h->stream>>>(h->Dinv.p, h->mr.p, h->mp.p, n, L);
+      h->launches += 2;
+      ++spmm;
+    }
+    FEMB_CUDA(h, cudaGetLastError());
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->mflags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->scal, h->mscal.p, sizeof(peek->scal), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    all = peek->flags[MLFlag::ALLDONE];
+  }
+  mpcg_extract_kernel<NB><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->mx.p, d_X, ldx, nb, n);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  const int fin = peek->flags[MLFlag::ITERS] & 1;   // the done flags the last p kernel wrote
+  bool conv = true;
+  double worst = 0.0;
+  for (int q = 0; q < nb; ++q) {
+    conv = conv && peek->flags[MLFlag::DONEQ0 + 4 * fin + q] != 0;
+    const double bb = peek->scal[MLScal::BB + q];
+    if (bb > 0.0) worst = std::max(worst, std::sqrt(peek->scal[MLScal::RR + q] / bb));
+  }
+  if (st) {
+    st->method_used = FEMB_SOLVER_PCG;
+    st->op_used = FEMB_OP_EBE;
+    st->iterations = peek->flags[MLFlag::ITERS];
+    st->spmv_launches = spmm;
+    st->converged = conv ? 1 : 0;
+    st->rel_residual = worst;
+  }
+  if (peek->flags[MLFlag::BAD]) return fail(h, FEMB_ERR_SINGULAR, "multi-RHS PCG breakdown: p^T K p <= 0 (K_ff is not positive definite)");
+  if (!conv) return fail(h, FEMB_ERR_NOT_CONVERGED, "multi-RHS PCG did not reach rtol within max_iter");
+  return FEMB_OK;
+}
+
 template <int NB>
 static int pcg_solve_multi_t(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
                              int64_t ldx, femb_stats* st) {
@@ -1071,6 +1297,10 @@ static int pcg_solve_multi_t(femb_handle* h, const femb_solve_opts& o, const dou
 int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
                     int64_t ldx, femb_stats* st) {
   if (h->bs != 6 || nb < 1 || nb > 4) return fail(h, FEMB_ERR_ARG, "multi-RHS PCG: frame operator, 1..4 right-hand sides");
+  if (ebe_selected(h, o.op) && linked_enabled()) {
+    if (nb <= 2) return pcg_solve_multi_linked<2>(h, o, d_B, ldb, nb, d_X, ldx, st);
+    return pcg_solve_multi_linked<4>(h, o, d_B, ldb, nb, d_X, ldx, st);
+  }
   if (nb <= 2) return pcg_solve_multi_t<2>(h, o, d_B, ldb, nb, d_X, ldx, st);
   return pcg_solve_multi_t<4>(h, o, d_B, ldb, nb, d_X, ldx, st);
 }
