@@ -18,7 +18,7 @@
 // part 0 masks, stores and accumulates (x, y).  No shared memory, no barriers, no float atomics:
 // bit-reproducible run to run.  The node's own coordinates and x entries are loaded once per node.
 //
-// Measured alternatives at 1M DOF on one B200 (gpurun_out/r1_ebe_variants*.log), single vector,
+// Measured alternatives at 1M DOF on one B200 (profiles/r01_ebe_operator_variants.log), single vector,
 // back to back: one thread per pair with the per-node sum in shared memory (two phases, one barrier
 // per 128-pair tile) 29.0 us; this kernel with T = 1 / 2 / 4 lanes per node 22.3 / 20.5 / 36.9 us;
 // a three-stage software pipeline over the pair loop (record two ahead, operands one ahead) 21.7 us;

@@ -22,7 +22,7 @@
 // Vectors per iteration: 6 read + 5 written (own node) — the gathers hit L1/L2.
 // Reproducible run to run; preconditioner: scalar Jacobi (or none).
 //
-// MEASURED (1M-DOF frame, one B200, gpurun_out/r1_fused_ab.log): 52.0 us per iteration against 45.1 us
+// MEASURED (1M-DOF frame, one B200, profiles/r01_pcg_iteration_experiments.log): 52.0 us per iteration against 45.1 us
 // for operator + update as two kernels — same iteration count, same answer.  The four-fold gather
 // volume per neighbour (D, r, q, s instead of z) costs more than the saved launch gap and reduction
 // tail, so this path is opt-in (FEMB_OP_EBE_FUSED / FEMB_FUSED_PCG=1) and the two-kernel iteration

@@ -247,7 +247,7 @@ static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const
     st->spmv_launches += s1.spmv_launches;
     // (Tried: a Galerkin start X0 = OPV (OPV^T MV)^-1 OPV^T B from the solves already done, to take the
     // lowest modes out of the residual.  At 1M DOF the 2-norm of the projected right-hand side GROWS
-    // 3-100x and every block still needs ~7,300 lockstep iterations (gpurun_out/r1_gal_modal2.log):
+    // 3-100x and every block still needs ~7,300 lockstep iterations (profiles/r01_modal_galerkin_start_negative.log):
     // CG on this operator is not held back by the few lowest modes but by the wide axial / bending
     // stiffness spread, so the idea was dropped.)
     return rc;

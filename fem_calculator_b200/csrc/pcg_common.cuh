@@ -220,7 +220,7 @@ inline int vec_grid(const femb_handle* h, int64_t n, int threads) {
 // scheduled while the previous kernel drains; pdl_wait() (griddepcontrol.wait) at the top of every
 // kernel blocks until the previous grid has completed and flushed its memory, so the data flow is
 // unchanged.  pdl_trigger() is called once a CTA's main loop is done.  Measured at 1M DOF
-// (gpurun_out/r1_pdl.log): single-vector PCG 45.9 -> 44.7 us/iteration, but the three-kernel
+// (profiles/r01_pcg_iteration_experiments.log): single-vector PCG 45.9 -> 44.7 us/iteration, but the three-kernel
 // lockstep iteration of the modal solve got 60 % SLOWER (early-resident CTAs of the next kernels
 // take SM slots from the running one), so it is opt-in: FEMB_PDL=1.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
