@@ -351,6 +351,8 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
   femb_solve_opts so;
   std::memset(&so, 0, sizeof(so));
   so.method = FEMB_SOLVER_PCG; so.precond = FEMB_PRECOND_JACOBI; so.max_iter = 200000; so.check_every = 50;
+  // inner solves 1000x tighter than the wanted pencil residual: measured at 1M DOF, 20 modes, rtol 1e-8 —
+  // inner 1e-10 stalls at a pencil residual of 7.7e-8, inner 1e-9 at 3.2e-6 (and both take longer)
   so.rtol = std::min(1e-11, o.rtol * 1e-3);
   so.op = o.op;
 
