@@ -462,22 +462,28 @@ chol_syrk_dmma_kernel(double* __restrict__ A, int64_t ld, int k0) {
   double* Pa = smem;                       // [64][kCBLd]
   double* Pb = smem + kCB * kCBLd;
   const int r0 = k0 + kCB + ti * kCB, c0 = k0 + kCB + tj * kCB;
-  for (int t = threadIdx.x; t < kCB * kCB / 2; t += 128) {
-    const int i = t / (kCB / 2), c = (t % (kCB / 2)) * 2;
-    const double2 va = *reinterpret_cast<const double2*>(A + (size_t)(r0 + i) * ld + k0 + c);
-    const double2 vb = *reinterpret_cast<const double2*>(A + (size_t)(c0 + i) * ld + k0 + c);
-    Pa[i * kCBLd + c] = va.x; Pa[i * kCBLd + c + 1] = va.y;
-    Pb[i * kCBLd + c] = vb.x; Pb[i * kCBLd + c + 1] = vb.y;
-  }
-  __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wr = (w >> 1) * 32, wc = (w & 1) * 32;      // this warp's 32x32 quadrant
   const int fr = lane >> 2, fk = lane & 3;               // fragment row / k index of this lane
+  // D = (-P_i) P_j^T + C: the accumulators start from the C tile, whose loads are issued before the
+  // panel tiles are staged, so their latency hides behind the staging and no read-modify-write waits
+  // at the end of the kernel
   double acc[4][4][2];
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    for (int ni = 0; ni < 4; ++ni) {
+      const double2 v = *reinterpret_cast<const double2*>(A + (size_t)(r0 + wr + mi * 8 + fr) * ld + c0 + wc + ni * 8 + 2 * fk);
+      acc[mi][ni][0] = v.x; acc[mi][ni][1] = v.y;
+    }
+  for (int t = threadIdx.x; t < kCB * kCB / 2; t += 128) {
+    const int i = t / (kCB / 2), c = (t % (kCB / 2)) * 2;
+    const double2 va = *reinterpret_cast<const double2*>(A + (size_t)(r0 + i) * ld + k0 + c);
+    const double2 vb = *reinterpret_cast<const double2*>(A + (size_t)(c0 + i) * ld + k0 + c);
+    Pa[i * kCBLd + c] = -va.x; Pa[i * kCBLd + c + 1] = -va.y;
+    Pb[i * kCBLd + c] = vb.x; Pb[i * kCBLd + c + 1] = vb.y;
+  }
+  __syncthreads();
 #pragma unroll 4
   for (int kk = 0; kk < kCB; kk += 4) {
     double a[4], b[4];
@@ -493,12 +499,9 @@ chol_syrk_dmma_kernel(double* __restrict__ A, int64_t ld, int k0) {
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      double2* c = reinterpret_cast<double2*>(A + (size_t)(r0 + wr + mi * 8 + fr) * ld + c0 + wc + ni * 8 + 2 * fk);
-      double2 v = *c;
-      v.x -= acc[mi][ni][0]; v.y -= acc[mi][ni][1];
-      *c = v;
-    }
+    for (int ni = 0; ni < 4; ++ni)
+      *reinterpret_cast<double2*>(A + (size_t)(r0 + wr + mi * 8 + fr) * ld + c0 + wc + ni * 8 + 2 * fk) =
+          make_double2(acc[mi][ni][0], acc[mi][ni][1]);
 }
 
 // upper triangle <- transpose of the lower one (so that column sweeps read contiguous rows)
