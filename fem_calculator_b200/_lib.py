@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("FEMB_LIB") or os.path.join(HERE, "libfemb200.so")   #
 FEMB_OK, FEMB_ERR_ARG, FEMB_ERR_CUDA, FEMB_ERR_NOT_CONVERGED, FEMB_ERR_SINGULAR, FEMB_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MAT_K, MAT_M = 0, 1
 SOLVER_AUTO, SOLVER_PCG, SOLVER_CHAIN, SOLVER_DENSE = 0, 1, 2, 3
-PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = 0, 1, 2
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_TWO_LEVEL = 0, 1, 2, 3
 OP_AUTO, OP_BSR, OP_EBE, OP_EBE_FUSED = 0, 1, 2, 3
 
 
@@ -34,12 +34,12 @@ class EigOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("method_used", C.c_int32), ("iterations", C.c_int32), ("converged", C.c_int32),
                 ("spmv_launches", C.c_int32), ("kernel_launches", C.c_int32), ("spmv_timed", C.c_int32),
-                ("op_used", C.c_int32), ("reserved", C.c_int32),
+                ("op_used", C.c_int32), ("coarse_dim", C.c_int32),
                 ("rel_residual", C.c_double), ("device_ms", C.c_double), ("spmv_ms", C.c_double),
                 ("update_ms", C.c_double)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ }
 
 
 class FembError(RuntimeError):
@@ -88,6 +88,7 @@ SIGNATURES = {
     "femb_timer": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "femb_io_bytes": (None, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
     "femb_symbolic_pattern": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _I64, C.POINTER(C.c_int64), _P, _P]),
+    "femb_symbolic_aggregates": (C.c_int, [C.c_int64, _P, C.c_int32, _P]),
 }
 
 _lib = None

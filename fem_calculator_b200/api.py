@@ -266,3 +266,15 @@ def symbolic_pattern(n_nodes, conn):
     if rc:
         raise L.FembError(rc, "femb_symbolic_pattern")
     return rowptr, colidx
+
+
+def symbolic_aggregates(points, n_parts):
+    """Host-only: the node aggregates of the two-level preconditioner (proportional recursive
+    coordinate bisection, csrc/coarse.cpp) — aggregate id per node, needs no GPU."""
+    lib = L.load()
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    agg = np.zeros(len(pts), dtype=np.int32)
+    rc = lib.femb_symbolic_aggregates(len(pts), L.ptr(pts), int(n_parts), L.ptr(agg))
+    if rc:
+        raise L.FembError(rc, "femb_symbolic_aggregates")
+    return agg

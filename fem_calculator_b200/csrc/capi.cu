@@ -194,6 +194,7 @@ static int ensure_symbolic(femb_handle* h) {
   FEMB_CUDA(h, upload(h->contrib_blk, S.contrib_blk, h->stream));
   FEMB_CUDA(h, upload(h->tile_ptr, S.tile_ptr, h->stream));
   h->pairs_dev_ok = false;
+  h->coarse_sym_ok = h->coarse_num_ok = false;
   if (S.pairs_ok && h->kind == Kind::Frame && h->n_sec < (1 << 24)) {
     // 16-byte pair records: everything the pair kernel would otherwise chase through
     // pair_code -> conn -> elem_sec is resolved here once
@@ -258,6 +259,7 @@ int femb_assemble(femb_handle* h) {
   h->assembled = true;
   h->have_solution = false;
   h->chain_factored = h->dense_factored = false;
+  h->coarse_num_ok = h->coarse_failed = false;
   return FEMB_OK;
 }
 
@@ -342,6 +344,7 @@ int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, cons
   h->have_bc = true;
   h->have_solution = false;
   h->chain_factored = h->dense_factored = false;
+  h->coarse_num_ok = h->coarse_failed = false;
   return FEMB_OK;
 }
 

@@ -76,6 +76,19 @@ struct Symbolic {
   std::vector<int32_t> chain_order;  // (n_nodes) node visited at chain position k
 };
 
+// Host-side symbolic part of the two-level preconditioner (coarse.cpp)
+struct CoarseSym {
+  int32_t n_agg = 0, max_nbr = 0;
+  std::vector<int32_t> node_agg;   // (n_nodes) aggregate of each node
+  std::vector<int32_t> agg_ptr;    // (n_agg+1)
+  std::vector<int32_t> agg_nodes;  // (n_nodes) node lists, ascending node id per aggregate
+  std::vector<int32_t> nbr_ptr;    // (n_agg+1)
+  std::vector<int32_t> nbr;        // neighbour aggregates (self included), ascending per aggregate
+  std::vector<int32_t> blk_slot;   // (nnzb) slot of block (i, j) in the neighbour list of agg(i)
+};
+void build_aggregates(int64_t n_nodes, const double* xyz, int n_parts, std::vector<int32_t>& agg);
+void build_coarse_symbolic(const Symbolic& S, const std::vector<int32_t>& agg, int n_agg, CoarseSym& C);
+
 void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int32_t* conn,
                     int tile_max_blocks, int tile_max_contrib, Symbolic& out);
 
@@ -146,6 +159,18 @@ struct femb_handle {
   femb::DevBuf<int32_t> chain_order;
   femb::DevBuf<double> chainG, chainW;   // (n_nodes,36) each, chain positions
   femb::DevBuf<double> denseL;           // (ndof,ndof) Cholesky factor of the masked operator
+
+  // two-level preconditioner (twolevel.cu): aggregates + rigid-body coarse space
+  bool coarse_sym_ok = false;     // aggregate tables on the device match the current topology
+  bool coarse_num_ok = false;     // coarse_inv matches the current K and BC mask
+  bool coarse_failed = false;     // the Galerkin matrix of the current K / BC could not be factored
+  int32_t coarse_n_agg = 0, coarse_max_nbr = 0;
+  int64_t coarse_n = 0, coarse_n_pad = 0;   // 6 * n_agg and its multiple-of-64 padding
+  femb::DevBuf<int32_t> agg_ptr, agg_nodes, agg_nbr_ptr, agg_nbr, blk_slot;
+  femb::DevBuf<double> agg_centroid;        // (n_agg,3)
+  femb::DevBuf<double> coarse_aug;          // (2 n_pad)^2 work matrix of the inversion
+  femb::DevBuf<double> coarse_inv;          // (n_pad, n_pad) inverse of the Galerkin matrix
+  femb::DevBuf<double> coarse_r;            // (4 * n_pad) restricted residual(s)
 
   // row-block distributed solve (dist.cu): this rank owns the first n_owned_nodes local nodes
   void* nccl_comm = nullptr;
@@ -249,6 +274,10 @@ int chain_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_
 int dense_factor(femb_handle* h);
 int dense_apply(femb_handle* h, const double* d_b, double* d_x, int nrhs, int64_t ld);
 int pcg_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
+// two-level preconditioner (twolevel.cu, direct.cu)
+bool twolevel_applicable(const femb_handle* h, const femb_solve_opts& o);
+int pcg_twolevel(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
+int coarse_invert(femb_handle* h, double* aug, int64_t n_pad, double* inv, bool* ok);
 int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
                     int64_t ldx, femb_stats* st);
 int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda, double* phi, int32_t* n_found,

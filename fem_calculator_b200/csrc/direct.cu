@@ -605,4 +605,47 @@ int run_dense_solve(femb_handle* h, femb_stats* st) {
   return FEMB_OK;
 }
 
+// ---- explicit inverse of the coarse Galerkin matrix (two-level preconditioner, twolevel.cu) --------
+// The coarse solve runs once per CG iteration between two 20-us kernels; two triangular sweeps
+// (n sequential steps) would cost more than the whole iteration, a product with the explicit inverse
+// is one bandwidth-bound pass over n^2 numbers that stay in L2.  The inverse comes out of the SAME
+// three kernels as the factorisation: eliminate the first n columns of the augmented matrix
+//     [ Kc  . ]        after panel k0 the identity rows n+i with i >= k0+64 are still zero in
+//     [ I   0 ]        every eliminated column, so each step works on the n rows [k0+64, n+k0+64)
+// and the Schur complement left in the lower right block is 0 - I Kc^-1 I = -Kc^-1
+// (chol_trsm turns the identity rows into L^-T, chol_syrk_dmma subtracts their Gram matrix).
+// n^3 DMMA flops in n/64 steps of equal size.  `aug` is (2 n_pad)^2, zero except Kc and the identity.
+__global__ void coarse_extract_kernel(const double* __restrict__ aug, int64_t ld, int64_t n_pad,
+                                      double* __restrict__ inv) {
+  const int64_t i = blockIdx.y, j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pad) return;
+  const int64_t r = i > j ? i : j, c = i > j ? j : i;      // the lower tiles hold the result
+  inv[i * n_pad + j] = -aug[(n_pad + r) * ld + n_pad + c];
+}
+
+int coarse_invert(femb_handle* h, double* aug, int64_t n_pad, double* inv, bool* ok) {
+  const int64_t m = 2 * n_pad;
+  DevBuf<int> status;
+  FEMB_CUDA(h, status.alloc(1));
+  FEMB_CUDA(h, cudaMemsetAsync(status.p, 0, sizeof(int), h->stream));
+  const size_t smem = (size_t)2 * kCB * kCBLd * sizeof(double);
+  FEMB_CUDA(h, cudaFuncSetAttribute(chol_syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned nt = (unsigned)(n_pad / kCB);
+  for (int64_t k0 = 0; k0 < n_pad; k0 += kCB) {
+    chol_potrf_block_kernel<<<1, 256, 0, h->stream>>>(aug, m, (int)k0, status.p);
+    const int64_t row_end = n_pad + k0 + kCB;                 // <= m; rows beyond are still zero in this panel
+    chol_trsm_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, h->stream>>>(aug, m, (int)k0, (int)row_end);
+    chol_syrk_dmma_kernel<<<dim3(nt, nt), 128, smem, h->stream>>>(aug, m, (int)k0);
+    h->launches += 3;
+  }
+  coarse_extract_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)n_pad), 256, 0, h->stream>>>(aug, m, n_pad, inv);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  int* hs = reinterpret_cast<int*>(h->pinned);
+  FEMB_CUDA(h, cudaMemcpyAsync(hs, status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  *ok = (*hs == 0);
+  return FEMB_OK;
+}
+
 }  // namespace femb

@@ -649,6 +649,7 @@ static bool linked_enabled() {
 }
 
 static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
+  if (twolevel_applicable(h, o)) return pcg_twolevel(h, o, d_b, st);
   if (fused_pcg_applicable(h, o)) return pcg_fused(h, o, d_b, st);
   if (h->bs == 6 && o.precond != FEMB_PRECOND_BLOCK_JACOBI && ebe_selected(h, o.op) && linked_enabled())
     return pcg_core_linked(h, o, d_b, st);

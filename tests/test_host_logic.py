@@ -174,3 +174,22 @@ def test_mesh_generators_sizes():
     assert 56 * 56 * 54 == 169344 and 55 * 56 * 54 * 2 + 56 * 56 * 53 == 498848
     tm, fd, xd = meshgen.tet10_box_case(2, 1, 2)
     assert len(tm.cells_dict["tetra10"]) == 24 and len(tm.points) == 75
+
+
+def test_aggregates_are_a_balanced_partition():
+    """Two-level preconditioner, host side (csrc/coarse.cpp): recursive coordinate bisection gives
+    every aggregate floor/ceil(n/parts) nodes, is deterministic, and cuts a lattice into boxes."""
+    mesh, _, _ = meshgen.lattice_frame_case(12, 10, 9, jitter=0.05)
+    for parts in (1, 2, 7, 40, 444):
+        agg = api.symbolic_aggregates(mesh.points, parts)
+        cnt = np.bincount(agg, minlength=parts)
+        n = len(mesh.points)
+        assert agg.min() >= 0 and agg.max() < parts and cnt.sum() == n
+        assert cnt.max() - cnt.min() <= 1 or parts > n // 2, (parts, cnt.min(), cnt.max())
+        assert np.array_equal(agg, api.symbolic_aggregates(mesh.points, parts))
+    agg = api.symbolic_aggregates(mesh.points, 8)
+    for a in range(8):                      # 8 parts of a box: every part is itself a box of ~1/8 the volume
+        p = mesh.points[agg == a]
+        ext = p.max(0) - p.min(0)
+        assert (ext <= np.array([12, 10, 9]) * 0.5 + 0.2).all(), (a, ext)
+    assert api.symbolic_aggregates(np.zeros((0, 3)), 4).size == 0
