@@ -85,29 +85,40 @@ __device__ __forceinline__ void rbm_column(int m, double rx, double ry, double r
 }
 
 // Kc(I, J) = sum over stored blocks (i in I, j in J) of T_i^T D_i K_ij D_j T_j, written into the top
-// left corner of the augmented work matrix (row-major, leading dimension ld).  Thread (g, e): entry
-// e = (r, c) of the coarse blocks of slots g, g + 28, ...; every thread scans the aggregate's block
-// rows in storage order and adds the blocks of its slot — a fixed order, no atomics.  Blocks between
-// free interior nodes cancel to round-off (rigid motions are in the kernel of their elements); they
-// are summed like the others so that no topology / BC case needs a special path.
+// left corner of the augmented work matrix (row-major, leading dimension ld).  One CTA per coarse
+// block row I, 28 groups of 36 threads (one thread per entry (r, c) of a coarse 6x6 block).  A work
+// item is (slot s of I's neighbour list, chunk of kTlAsmChunk nodes of I): its group walks the block
+// rows of the chunk in storage order, adds the blocks of slot s and parks the partial sum in `scratch`;
+// after a barrier thread (s, e) adds the chunk partials of its entry in chunk order — fixed order, no
+// atomics.  Blocks between free interior nodes cancel to round-off (rigid motions are in the kernel
+// of their elements); they are summed like the others so no topology / BC case needs a special path.
+// (First version: every thread scanned ALL block rows of the aggregate for its slot — the 36 threads
+// of the self slot walked ~2,600 blocks one after the other; 20 ms of the 24 ms setup at 1M DOF.)
+constexpr int kTlAsmChunk = 16;
+
 __global__ void __launch_bounds__(kTlAsmGroups * 36)
 tl_coarse_assemble_kernel(const int32_t* __restrict__ agg_ptr, const int32_t* __restrict__ agg_nodes,
                           const int32_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr,
                           const int32_t* __restrict__ blk_slot, const int32_t* __restrict__ rowptr,
                           const int32_t* __restrict__ colidx, const double* __restrict__ Kvals,
                           const double* __restrict__ xyz, const double* __restrict__ centroid,
-                          const uint8_t* __restrict__ free_mask, double* __restrict__ aug, int64_t ld) {
+                          const uint8_t* __restrict__ free_mask, double* __restrict__ aug, int64_t ld,
+                          double* __restrict__ scratch, int64_t scratch_per_agg) {
   const int I = blockIdx.x;
   const int e = threadIdx.x % 36, g = threadIdx.x / 36;
   const int r = e / 6, c = e % 6;
   const int first = agg_ptr[I], cnt = agg_ptr[I + 1] - first;
   const int s0 = nbr_ptr[I], ns = nbr_ptr[I + 1] - s0;
+  const int nchunk = (cnt + kTlAsmChunk - 1) / kTlAsmChunk;
   const double cIx = centroid[3 * (size_t)I], cIy = centroid[3 * (size_t)I + 1], cIz = centroid[3 * (size_t)I + 2];
-  for (int s = g; s < ns; s += kTlAsmGroups) {
+  double* part = scratch + (size_t)I * scratch_per_agg;       // [slot][chunk][36]
+  for (int item = g; item < ns * nchunk; item += kTlAsmGroups) {
+    const int s = item % ns, ch = item / ns;
     const int J = nbr[s0 + s];
     const double cJx = centroid[3 * (size_t)J], cJy = centroid[3 * (size_t)J + 1], cJz = centroid[3 * (size_t)J + 2];
     double acc = 0.0;
-    for (int k = 0; k < cnt; ++k) {
+    const int k1 = min(cnt, (ch + 1) * kTlAsmChunk);
+    for (int k = ch * kTlAsmChunk; k < k1; ++k) {
       const int i = agg_nodes[first + k];
       const int b0 = rowptr[i], b1 = rowptr[i + 1];
       bool have_ti = false;
@@ -135,6 +146,13 @@ tl_coarse_assemble_kernel(const int32_t* __restrict__ agg_ptr, const int32_t* __
         acc += sum;
       }
     }
+    part[((size_t)s * nchunk + ch) * 36 + e] = acc;
+  }
+  __syncthreads();
+  for (int s = g; s < ns; s += kTlAsmGroups) {
+    const int J = nbr[s0 + s];
+    double acc = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch) acc += part[((size_t)s * nchunk + ch) * 36 + e];
     if (J == I && r == c) acc = (acc > 0.0) ? acc * (1.0 + kTlRidge) : 1.0;   // fully fixed / empty aggregate: identity
     aug[(size_t)(6 * I + r) * ld + 6 * J + c] = acc;
   }
@@ -345,6 +363,10 @@ static int ensure_coarse_symbolic(femb_handle* h) {
   FEMB_CUDA(h, h->agg_centroid.alloc((size_t)n_agg * 3));
   FEMB_CUDA(h, h->coarse_inv.alloc((size_t)h->coarse_n_pad * h->coarse_n_pad));
   FEMB_CUDA(h, h->coarse_r.alloc((size_t)h->coarse_n_pad * 4));
+  int max_cnt = 0;
+  for (int a = 0; a < n_agg; ++a) max_cnt = std::max(max_cnt, C.agg_ptr[a + 1] - C.agg_ptr[a]);
+  h->coarse_scratch_per_agg = (int64_t)std::max(1, C.max_nbr) * ((max_cnt + kTlAsmChunk - 1) / kTlAsmChunk) * 36;
+  FEMB_CUDA(h, h->coarse_scratch.alloc((size_t)h->coarse_scratch_per_agg * n_agg));
   h->coarse_sym_ok = true;
   h->coarse_num_ok = false;
   return FEMB_OK;
@@ -358,18 +380,36 @@ static int ensure_coarse_numeric(femb_handle* h) {
   const int n_agg = h->coarse_n_agg;
   const int64_t n = h->coarse_n, n_pad = h->coarse_n_pad, m = 2 * n_pad;
   FEMB_CUDA(h, h->coarse_aug.ensure((size_t)m * m));
+  const bool trace = getenv("FEMB_TRACE") != nullptr;
+  cudaEvent_t te[3] = {nullptr, nullptr, nullptr};
+  if (trace) {
+    for (auto& e : te) cudaEventCreate(&e);
+    cudaEventRecord(te[0], h->stream);
+  }
   FEMB_CUDA(h, cudaMemsetAsync(h->coarse_aug.p, 0, (size_t)m * m * sizeof(double), h->stream));
   FEMB_CUDA(h, cudaMemsetAsync(h->coarse_r.p, 0, h->coarse_r.bytes(), h->stream));
   tl_centroid_kernel<<<n_agg, kTlThreads, 0, h->stream>>>(h->agg_ptr.p, h->agg_nodes.p, h->xyz.p, h->agg_centroid.p, n_agg);
   tl_aug_identity_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, h->stream>>>(h->coarse_aug.p, n, n_pad);
   tl_coarse_assemble_kernel<<<n_agg, kTlAsmGroups * 36, 0, h->stream>>>(
       h->agg_ptr.p, h->agg_nodes.p, h->agg_nbr_ptr.p, h->agg_nbr.p, h->blk_slot.p, h->rowptr.p, h->colidx.p,
-      h->Kvals.p, h->xyz.p, h->agg_centroid.p, h->free_mask.p, h->coarse_aug.p, m);
+      h->Kvals.p, h->xyz.p, h->agg_centroid.p, h->free_mask.p, h->coarse_aug.p, m, h->coarse_scratch.p,
+      h->coarse_scratch_per_agg);
   h->launches += 3;
   FEMB_CUDA(h, cudaGetLastError());
+  if (trace) cudaEventRecord(te[1], h->stream);
   bool ok = false;
   rc = coarse_invert(h, h->coarse_aug.p, n_pad, h->coarse_inv.p, &ok);
   if (rc) return rc;
+  if (trace) {
+    cudaEventRecord(te[2], h->stream);
+    cudaEventSynchronize(te[2]);
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, te[0], te[1]);
+    cudaEventElapsedTime(&b, te[1], te[2]);
+    for (auto& e : te) cudaEventDestroy(e);
+    fprintf(stderr, "[femb trace] two-level numeric setup: coarse dim %lld, Galerkin assembly %.3f ms, inversion %.3f ms\n",
+            (long long)n, a, b);
+  }
   h->coarse_num_ok = ok;
   h->coarse_failed = !ok;
   return FEMB_OK;

@@ -93,6 +93,9 @@ typedef struct {
   int32_t op;            /* FEMB_OP_* of the inner shift-invert solves   default AUTO             */
   double rtol;           /* ||K phi - lambda M phi|| <= rtol*||K phi||   default 1e-8      */
   double lambda_min;     /* keep eigenvalues > lambda_min (BeamSolver.py:448)  default 1e-6 */
+  int32_t precond;       /* preconditioner of the inner PCG solves: FEMB_PRECOND_TWO_LEVEL, anything else =
+                            JACOBI (4-/2-vector lockstep PCG); ignored behind a factorisation            */
+  int32_t reserved;
 } femb_eig_opts;
 
 typedef struct {
