@@ -169,7 +169,8 @@ def config_dict(parallel="1 GPU"):
     return {"workload": "BASELINE configs[2]: synthetic gmsh-like 3D space frame, 56x56x54 lattice, 169,344 nodes / "
                         "1,016,064 DOF (997,248 free), 498,848 Timoshenko elements, box/C/L sections, base fixed, "
                         "loads on all top nodes; static solve K u = F (PCG rtol 1e-12) with reaction recovery",
-            "step": "fused element+assembly -> BC -> PCG (matrix-free operator) -> reactions",
+            "step": "fused element+assembly -> BC -> two-level PCG (matrix-free operator; Jacobi + rigid-body coarse space, "
+                    "Galerkin matrix and its inverse rebuilt every step) -> reactions",
             "l2": "every step re-assembles the 359 MB K (> 126 MB L2), evicting the CG working set (~80 MB) between steps",
             "parallelism": parallel}
 
@@ -197,7 +198,9 @@ def run_gpu(args):
     m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)))
     m.assemble()
     m.set_bc(fixed, f)
-    solve_kw = dict(method=L.SOLVER_PCG, precond=L.PRECOND_JACOBI, rtol=RTOL, want_u=False, want_reactions=False)
+    # FEMB_PRECOND_AUTO: at this size the two-level preconditioner (Jacobi + rigid-body coarse space, csrc/twolevel.cu);
+    # its numeric setup (Galerkin matrix + explicit inverse) is rebuilt inside every timed step, after the assembly
+    solve_kw = dict(method=L.SOLVER_PCG, precond=L.PRECOND_AUTO, rtol=RTOL, want_u=False, want_reactions=False)
 
     def step(profile=0):
         m.assemble()
@@ -235,6 +238,12 @@ def run_gpu(args):
     update_ms = sum(s["update_ms"] for s in stats) / n_timed
     spmv_share = spmv_ms * sum(s["spmv_launches"] for s in stats) / total_ms if world == 1 else None
 
+    coarse_dim = int(stats[-1].get("coarse_dim", 0))
+    if coarse_dim:
+        n_pad = (coarse_dim + 63) // 64 * 64
+        upd_bytes = 13 * 8 * len(f) + 8 * n_pad * n_pad + 2 * (24 + 4) * len(mesh.points)
+    else:
+        upd_bytes = 12 * 8 * len(f)
     # per-kernel roofline numbers (algorithmic bytes: DESIGN.md §kernels)
     peak, peak_src = peaks()
     ebe = stats[-1].get("op_used") == L.OP_EBE
@@ -274,8 +283,12 @@ def run_gpu(args):
                     "traffic": _traffic("ncu_spmv_traffic.json")}
     extra = {
         "pcg": {"iterations": iters, "ms_per_iteration": stats[-1]["device_ms"] / max(1, iters),
-                "rel_residual": stats[-1]["rel_residual"], "precond": "jacobi", "form": "Chronopoulos-Gear, 2 kernels/iteration",
-                "update_kernel_ms": update_ms, "update_kernel_gbs": 12 * 8 * len(f) / (update_ms * 1e-3) / 1e9 if update_ms else None},
+                "rel_residual": stats[-1]["rel_residual"],
+                "precond": "two-level (Jacobi + 6 rigid-body modes per aggregate)" if coarse_dim else "jacobi",
+                "coarse_dim": coarse_dim,
+                "form": "Chronopoulos-Gear, 3 kernels/iteration (operator, update + restriction, coarse solve + prolongation)"
+                        if coarse_dim else "Chronopoulos-Gear, 2 kernels/iteration",
+                "update_kernel_ms": update_ms, "update_kernel_gbs": upd_bytes / (update_ms * 1e-3) / 1e9 if update_ms else None},
         "assembly": {"kernel": "frame_assemble_pairs_persistent_kernel (fused element+assembly)", "ms": asm_ms,
                      "elements_per_s": n_elem / (asm_ms * 1e-3), "achieved_gbs": asm_bytes / (asm_ms * 1e-3) / 1e9,
                      "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": asm_bytes},
@@ -283,11 +296,27 @@ def run_gpu(args):
                               "frac": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9 / peak},
         "operator_back_to_back_ms": op_b2b_ms,
     }
+    if coarse_dim:
+        extra["pcg"]["update_kernel_note"] = ("tl_update_kernel + tl_coarse_z_kernel together (two launches): 10 + 3 vector "
+                                              "passes, the n_pad^2 coarse inverse, coordinates and node lists")
     extra["pcg"]["operator"] = "matrix-free (EBE)" if ebe else "assembled BSR"
     extra["pcg"]["update_kernel_frac"] = (extra["pcg"]["update_kernel_gbs"] / peak) if extra["pcg"]["update_kernel_gbs"] else None
+    if coarse_dim and world == 1:
+        # the same step with the plain Jacobi preconditioner, outside the timed region (what the coarse space buys)
+        jkw = dict(solve_kw, precond=L.PRECOND_JACOBI)
+        m.solve_static(**jkw)
+        _, _, jst = m.solve_static(profile=8, **jkw)
+        extra["jacobi_pcg"] = {"iterations": jst["iterations"], "pcg_ms": jst["device_ms"],
+                               "ms_per_iteration": jst["device_ms"] / max(1, jst["iterations"]),
+                               "operator_ms": jst["spmv_ms"] / max(1, jst["spmv_timed"]),
+                               "update_ms": jst["update_ms"] / max(1, jst["spmv_timed"]),
+                               "dof_per_s_pcg_only": n_free / (jst["device_ms"] * 1e-3)}
+        _, _, tst = m.solve_static(**solve_kw)      # coarse inverse kept: the solve alone
+        extra["pcg"]["solve_only_ms"] = tst["device_ms"]
+        extra["pcg"]["coarse_setup_ms"] = stats[-1]["device_ms"] - tst["device_ms"]
     if ebe and world == 1:
         # the HBM-bound form of the same product: one solve with the assembled BSR operator, outside the timed region
-        _, _, bst = m.solve_static(profile=8, op=L.OP_BSR, **solve_kw)
+        _, _, bst = m.solve_static(profile=8, op=L.OP_BSR, **dict(solve_kw, precond=L.PRECOND_JACOBI))
         nb_t = max(1, bst["spmv_timed"])
         b_ms = bst["spmv_ms"] / nb_t
         b_ach = spmv_bytes / (b_ms * 1e-3) / 1e9
@@ -299,13 +328,17 @@ def run_gpu(args):
                                       "dof_per_s_pcg_only": n_free / (bst["device_ms"] * 1e-3)}
     if world == 1 and not args.no_modal:
         # second headline metric: ms per 20-mode modal solve at 1M DOF (device time of femb_modal)
-        lam, _, mst = m.modal(k=20, rtol=1e-8)
+        two_level_modal = os.environ.get("FEMB_BENCH_MODAL_PRECOND", "two_level") != "jacobi"
+        lam, _, mst = m.modal(k=20, rtol=1e-8, precond=L.PRECOND_TWO_LEVEL if two_level_modal else L.PRECOND_JACOBI)
         extra["modal"] = {"metric": "ms_per_20_mode_modal", "ms": mst["device_ms"], "modes": int(len(lam)),
                           "lockstep_pcg_iterations": mst["iterations"], "matrix_passes": mst["spmv_launches"],
                           "rel_residual": mst["rel_residual"], "omega_min_rad_s": float(np.sqrt(lam[0])),
                           "omega_max_rad_s": float(np.sqrt(lam[-1])),
-                          "operator": "matrix-free (EBE), 4 vectors per pass" if mst.get("op_used") == L.OP_EBE else "assembled BSR SpMM",
-                          "method": "block shift-invert Krylov (block 4), 4-RHS lockstep Jacobi-PCG as K^-1"}
+                          "operator": "matrix-free (EBE)" if mst.get("op_used") == L.OP_EBE else "assembled BSR SpMM",
+                          "coarse_dim": int(mst.get("coarse_dim", 0)),
+                          "method": ("block shift-invert Krylov (block 2), two-level PCG as K^-1, one right-hand side at a time"
+                                     if mst.get("coarse_dim") else
+                                     "block shift-invert Krylov (block 2), 2-RHS lockstep Jacobi-PCG as K^-1")}
     m.close()
 
     if world > 1 and not args.no_rowblock:

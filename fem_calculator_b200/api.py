@@ -63,7 +63,7 @@ class Handle:
         self._check(self.lib.femb_set_bc(self._h, len(fixed), L.ptr(fixed), f, L.ptr(up)))
         self.ndof = len(f)
 
-    def solve_static(self, method=L.SOLVER_AUTO, precond=L.PRECOND_JACOBI, rtol=1e-12, max_iter=200000,
+    def solve_static(self, method=L.SOLVER_AUTO, precond=L.PRECOND_AUTO, rtol=1e-12, max_iter=200000,
                      check_every=50, minus_f=True, want_u=True, want_reactions=True, profile=False, op=L.OP_AUTO):
         o = L.SolveOpts(method, precond, max_iter, check_every, rtol, int(profile), int(op))
         st = L.Stats()

@@ -351,7 +351,7 @@ int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, cons
 static femb_solve_opts default_solve_opts() {
   femb_solve_opts o;
   std::memset(&o, 0, sizeof(o));
-  o.method = FEMB_SOLVER_AUTO; o.precond = FEMB_PRECOND_JACOBI; o.max_iter = 200000;
+  o.method = FEMB_SOLVER_AUTO; o.precond = FEMB_PRECOND_AUTO; o.max_iter = 200000;
   o.check_every = 50; o.rtol = 1e-12;
   return o;
 }

@@ -113,7 +113,7 @@ tl_coarse_assemble_kernel(const int32_t* __restrict__ agg_ptr, const int32_t* __
   const double cIx = centroid[3 * (size_t)I], cIy = centroid[3 * (size_t)I + 1], cIz = centroid[3 * (size_t)I + 2];
   double* part = scratch + (size_t)I * scratch_per_agg;       // [slot][chunk][36]
   for (int item = g; item < ns * nchunk; item += kTlAsmGroups) {
-    const int s = item % ns, ch = item / ns;
+    const int ch = item % nchunk, s = item / nchunk;   // consecutive groups take consecutive chunks of one slot
     const int J = nbr[s0 + s];
     const double cJx = centroid[3 * (size_t)J], cJy = centroid[3 * (size_t)J + 1], cJz = centroid[3 * (size_t)J + 2];
     double acc = 0.0;
@@ -415,8 +415,12 @@ static int ensure_coarse_numeric(femb_handle* h) {
   return FEMB_OK;
 }
 
+constexpr int64_t kTlAutoNodes = 50000;   // FEMB_PRECOND_AUTO: below this the coarse setup costs more than it saves
+
 bool twolevel_applicable(const femb_handle* h, const femb_solve_opts& o) {
-  return o.precond == FEMB_PRECOND_TWO_LEVEL && h->bs == 6 && ebe_selected(h, o.op == FEMB_OP_EBE_FUSED ? FEMB_OP_AUTO : o.op);
+  const bool want = o.precond == FEMB_PRECOND_TWO_LEVEL ||
+                    (o.precond == FEMB_PRECOND_AUTO && o.op != FEMB_OP_EBE_FUSED && h->n_nodes >= kTlAutoNodes);
+  return want && h->bs == 6 && ebe_selected(h, o.op == FEMB_OP_EBE_FUSED ? FEMB_OP_AUTO : o.op);
 }
 
 int pcg_twolevel(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {

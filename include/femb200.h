@@ -59,7 +59,9 @@ enum { FEMB_PRECOND_NONE = 0, FEMB_PRECOND_JACOBI = 1, FEMB_PRECOND_BLOCK_JACOBI
                                      GPU with the matrix-free operator (csrc/twolevel.cu): 5x fewer iterations
                                      than Jacobi at 1M DOF.  Where it does not apply (Tet10, BSR operator, the
                                      row-block distributed solve) the solve runs with JACOBI;
-                                     femb_stats.coarse_dim tells which one ran.                              */ };
+                                     femb_stats.coarse_dim tells which one ran.                              */,
+       FEMB_PRECOND_AUTO = 4      /* TWO_LEVEL where it applies and the mesh has >= 50,000 nodes (below that the
+                                     coarse setup costs more than it saves), else JACOBI                       */ };
 
 /* femb_solve_opts.op / femb_eig_opts.op: how the Krylov loops apply K_ff.
  *   BSR  the assembled block-CSR matrix (HBM-bound: 8 B per stored value and product);
@@ -76,7 +78,7 @@ enum { FEMB_OP_AUTO = 0, FEMB_OP_BSR = 1, FEMB_OP_EBE = 2,
 
 typedef struct {
   int32_t method;        /* FEMB_SOLVER_*                         default AUTO            */
-  int32_t precond;       /* FEMB_PRECOND_*                        default JACOBI          */
+  int32_t precond;       /* FEMB_PRECOND_*                        default AUTO            */
   int32_t max_iter;      /* PCG iteration cap                     default 200000          */
   int32_t check_every;   /* host polls convergence every N its    default 50              */
   double rtol;           /* stop at ||r||_2 <= rtol*||b||_2       default 1e-12           */
@@ -93,8 +95,9 @@ typedef struct {
   int32_t op;            /* FEMB_OP_* of the inner shift-invert solves   default AUTO             */
   double rtol;           /* ||K phi - lambda M phi|| <= rtol*||K phi||   default 1e-8      */
   double lambda_min;     /* keep eigenvalues > lambda_min (BeamSolver.py:448)  default 1e-6 */
-  int32_t precond;       /* preconditioner of the inner PCG solves: FEMB_PRECOND_TWO_LEVEL, anything else =
-                            JACOBI (4-/2-vector lockstep PCG); ignored behind a factorisation            */
+  int32_t precond;       /* preconditioner of the inner PCG solves: FEMB_PRECOND_TWO_LEVEL (one right-hand side
+                            at a time), FEMB_PRECOND_AUTO (as for the static solve), anything else = JACOBI
+                            (4-/2-vector lockstep PCG); ignored behind a factorisation                   */
   int32_t reserved;
 } femb_eig_opts;
 

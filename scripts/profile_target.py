@@ -16,7 +16,7 @@ for _ in range(3):
     m.assemble()
 m.set_bc(fixed, f)
 try:
-    m.solve_static(method=L.SOLVER_PCG, precond=L.PRECOND_JACOBI, max_iter=iters, want_u=False, want_reactions=False)
+    m.solve_static(method=L.SOLVER_PCG, precond=getattr(L, "PRECOND_" + os.environ.get("PCG_PRECOND", "JACOBI")), max_iter=iters, want_u=False, want_reactions=False)
 except L.FembError as e:
     assert e.code == L.FEMB_ERR_NOT_CONVERGED, e
 m.close()
