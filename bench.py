@@ -409,9 +409,11 @@ def run_gpu(args):
     out.update(extra)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # Jacobi-PCG iteration count at full size comes from this very run (same algorithm, same rtol)
-        dofs, t_full, s = cpu_baseline_sample(n_elem, n_free, iters)
+        # the CPU port runs the Jacobi-PCG (oracle/cpu_baseline.py): scale with ITS iteration count at full size
+        cpu_iters = extra.get("jacobi_pcg", {}).get("iterations", iters if not coarse_dim else JACOBI_ITERS_FULL)
+        dofs, t_full, s = cpu_baseline_sample(n_elem, n_free, cpu_iters)
         out["cpu_baseline"] = {"value": dofs, "unit": "DOF/s", "cores": 1, "kind": "port",
-                               "sample": sample_text(s, iters), "est_seconds_full": t_full}
+                               "sample": sample_text(s, cpu_iters), "est_seconds_full": t_full}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if dist is not None:

@@ -6,9 +6,10 @@
 // frame those are locally rigid-body motions (every unconstrained element of BeamSolver.py:646-660
 // has the six rigid motions in its kernel).  So the nodes are grouped into aggregates (coarse.cpp)
 // and the additive two-level preconditioner
-//        M^-1 r = D^-1 r + P (P^T A P)^-1 P^T r,      A = the masked operator K_ff + I_fixed,
+//        M^-1 r = omega D^-1 r + P (P^T A P)^-1 P^T r,      A = the masked operator K_ff + I_fixed,
 // is used, P = six rigid-body modes per aggregate (translations, rotations about the centroid) with
-// the rows of fixed DOFs zeroed.  1,372 instead of 6,931 iterations at 1M DOF with 444 aggregates.
+// the rows of fixed DOFs zeroed (the Jacobi term carries a weight omega = 2).  1,324 instead of 6,931
+// iterations at 1M DOF with 444 aggregates.
 //
 // Pieces (all deterministic — fixed-order sums, no float atomics):
 //   tl_centroid_kernel        centroid of every aggregate (per assembled K: coordinates may change)
@@ -29,9 +30,11 @@
 
 namespace femb {
 
-constexpr int kTlThreads = 128;       // update / coarse-z CTAs (one per aggregate)
+constexpr int kTlThreads = 384;       // update / coarse-z CTAs (one per aggregate); one thread per (node, DOF pair)
 constexpr int kTlAsmGroups = 28;      // coarse-assembly CTA: 28 slot groups x 36 entries = 1008 threads
 constexpr int kTlMaxAgg = 1024;       // one published partial per aggregate (partials arrays hold num_sms * 8)
+constexpr double kTlOmega = 2.0;      // weight of the Jacobi term in the additive preconditioner (FEMB_TL_OMEGA):
+                                      // 1M DOF, 444 aggregates: omega 1 / 2 / 3 -> 1372 / 1324 / 1342 iterations
 constexpr double kTlRidge = 1e-8;     // relative ridge on diag(Kc): keeps the factorisation positive when the
                                       // free DOFs of an aggregate do not carry all six rigid-body modes
 
@@ -44,6 +47,7 @@ struct TlDev {
   const double* inv;        // (n_pad, n_pad)
   double* rc;               // (n_pad)
   int n_agg, n_pad;
+  double omega;             // weight of the Jacobi term: z = omega D^-1 r + P Kc^-1 P^T r
 };
 
 __global__ void tl_centroid_kernel(const int32_t* __restrict__ agg_ptr, const int32_t* __restrict__ agg_nodes,
@@ -177,6 +181,21 @@ __device__ __forceinline__ void st6(double* __restrict__ v, int node, const doub
   p[0] = make_double2(u[0], u[1]); p[1] = make_double2(u[2], u[3]); p[2] = make_double2(u[4], u[5]);
 }
 
+// a thread of the per-aggregate kernels owns one 16-byte DOF pair (2 * part, 2 * part + 1) of a node:
+// consecutive lanes touch consecutive 16-byte chunks, and a thread carries 2 instead of 6 values per
+// vector (the thread-per-node form needed 96 registers and ran at 18 % warp occupancy, 24 us per launch)
+__device__ __forceinline__ double2 ld2(const double* __restrict__ v, int node, int part) {
+  return *(reinterpret_cast<const double2*>(v + (size_t)node * 6) + part);
+}
+__device__ __forceinline__ void st2(double* __restrict__ v, int node, int part, double2 a) {
+  *(reinterpret_cast<double2*>(v + (size_t)node * 6) + part) = a;
+}
+// the pair as a 6-vector with zeros elsewhere (adding zeros is exact, so restrict_add stays the one formula)
+__device__ __forceinline__ void expand_pair(int part, double2 a, double* u) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { u[2 * c] = (c == part) ? a.x : 0.0; u[2 * c + 1] = (c == part) ? a.y : 0.0; }
+}
+
 // P^T r contribution of one node: translations take the force, rotations take rho x force + moment
 __device__ __forceinline__ void restrict_add(const double* r, double rx, double ry, double rz, double* acc) {
   acc[0] += r[0]; acc[1] += r[1]; acc[2] += r[2];
@@ -187,7 +206,7 @@ __device__ __forceinline__ void restrict_add(const double* r, double rx, double 
 
 // init: x = 0, r = b, p = q = 0 on the aggregate's nodes; rc = P^T b; publishes ||b||^2 into buffer 0
 // (gamma_0 follows from tl_coarse_z_kernel with wr = 0)
-__global__ void __launch_bounds__(kTlThreads)
+__global__ void __launch_bounds__(kTlThreads, 3)
 tl_init_kernel(const TlDev T, const double* __restrict__ b, double* __restrict__ x, double* __restrict__ r,
                double* __restrict__ p, double* __restrict__ q, const PcgLink L) {
   __shared__ double s_part[7 * kTlThreads / 32];
@@ -195,16 +214,16 @@ tl_init_kernel(const TlDev T, const double* __restrict__ b, double* __restrict__
   const int first = T.agg_ptr[I], cnt = T.agg_ptr[I + 1] - first;
   const double cx = T.centroid[3 * (size_t)I], cy = T.centroid[3 * (size_t)I + 1], cz = T.centroid[3 * (size_t)I + 2];
   double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  const double zero[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int k = threadIdx.x; k < cnt; k += kTlThreads) {
-    const int node = T.agg_nodes[first + k];
-    double bv[6];
-    ld6(b, node, bv);
-    st6(r, node, bv); st6(x, node, zero); st6(p, node, zero); st6(q, node, zero);
+  for (int w = threadIdx.x; w < 3 * cnt; w += kTlThreads) {
+    const int node = T.agg_nodes[first + w / 3], part = w % 3;
+    const double2 bv = ld2(b, node, part);
+    const double2 zz = make_double2(0.0, 0.0);
+    st2(r, node, part, bv); st2(x, node, part, zz); st2(p, node, part, zz); st2(q, node, part, zz);
     const double* pp = T.xyz + 3 * (size_t)node;
-    restrict_add(bv, pp[0] - cx, pp[1] - cy, pp[2] - cz, v);
-#pragma unroll
-    for (int a = 0; a < 6; ++a) v[6] += bv[a] * bv[a];
+    double b6[6];
+    expand_pair(part, bv, b6);
+    restrict_add(b6, pp[0] - cx, pp[1] - cy, pp[2] - cz, v);
+    v[6] += bv.x * bv.x + bv.y * bv.y;
   }
   block_sum_all<kTlThreads, 7>(v, s_part);
   if (threadIdx.x == 0) {
@@ -218,7 +237,7 @@ tl_init_kernel(const TlDev T, const double* __restrict__ b, double* __restrict__
 // update(it): consumes delta (operator) and gamma (coarse-z of the previous iteration / init) like
 // pcg_update_linked_kernel, then p = z + beta p, q = s + beta q, x += alpha p, r -= alpha q on the
 // aggregate's nodes, rc = P^T r, and publishes ||r||^2 into buffer (it + 1) & 1
-__global__ void __launch_bounds__(kTlThreads)
+__global__ void __launch_bounds__(kTlThreads, 3)
 tl_update_kernel(const TlDev T, const double* __restrict__ z, const double* __restrict__ s, double* __restrict__ p,
                  double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, const PcgLink L) {
   __shared__ double s_part[7 * kTlThreads / 32];
@@ -248,22 +267,22 @@ tl_update_kernel(const TlDev T, const double* __restrict__ z, const double* __re
   const int first = T.agg_ptr[I], cnt = T.agg_ptr[I + 1] - first;
   const double cx = T.centroid[3 * (size_t)I], cy = T.centroid[3 * (size_t)I + 1], cz = T.centroid[3 * (size_t)I + 2];
   double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int k = threadIdx.x; k < cnt; k += kTlThreads) {
-    const int node = T.agg_nodes[first + k];
-    double zv[6], sv[6], pv[6], qv[6], xv[6], rv[6];
-    ld6(z, node, zv); ld6(s, node, sv); ld6(p, node, pv); ld6(q, node, qv); ld6(x, node, xv); ld6(r, node, rv);
+#pragma unroll 1
+  for (int w = threadIdx.x; w < 3 * cnt; w += kTlThreads) {
+    const int node = T.agg_nodes[first + w / 3], part = w % 3;
+    const double2 zv = ld2(z, node, part), sv = ld2(s, node, part);
+    double2 pv = ld2(p, node, part), qv = ld2(q, node, part), xv = ld2(x, node, part), rv = ld2(r, node, part);
     const double* pp = T.xyz + 3 * (size_t)node;
     const double rx = pp[0] - cx, ry = pp[1] - cy, rz = pp[2] - cz;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      pv[a] = zv[a] + beta * pv[a];
-      qv[a] = sv[a] + beta * qv[a];
-      xv[a] += alpha * pv[a];
-      rv[a] -= alpha * qv[a];
-      v[6] += rv[a] * rv[a];
-    }
-    st6(p, node, pv); st6(q, node, qv); st6(x, node, xv); st6(r, node, rv);
-    restrict_add(rv, rx, ry, rz, v);
+    pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
+    qv.x = sv.x + beta * qv.x; qv.y = sv.y + beta * qv.y;
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
+    st2(p, node, part, pv); st2(q, node, part, qv); st2(x, node, part, xv); st2(r, node, part, rv);
+    v[6] += rv.x * rv.x + rv.y * rv.y;
+    double r6[6];
+    expand_pair(part, rv, r6);
+    restrict_add(r6, rx, ry, rz, v);
   }
   block_sum_all<kTlThreads, 7>(v, s_part);
   if (threadIdx.x == 0) {
@@ -275,7 +294,7 @@ tl_update_kernel(const TlDev T, const double* __restrict__ z, const double* __re
 
 // y_I = (Kc^-1 rc)[6I .. 6I+6), then z = D^-1 r + P y on the aggregate's nodes; publishes the (r, z)
 // partial into buffer wr.  The inverse is symmetric: rows are read, contiguously.
-__global__ void __launch_bounds__(kTlThreads)
+__global__ void __launch_bounds__(kTlThreads, 3)
 tl_coarse_z_kernel(const TlDev T, const double* __restrict__ dinv, const double* __restrict__ r,
                    double* __restrict__ z, int wr, const PcgLink L) {
   __shared__ double s_part[6 * kTlThreads / 32];
@@ -300,24 +319,25 @@ tl_coarse_z_kernel(const TlDev T, const double* __restrict__ dinv, const double*
   const int first = T.agg_ptr[I], cnt = T.agg_ptr[I + 1] - first;
   const double cx = T.centroid[3 * (size_t)I], cy = T.centroid[3 * (size_t)I + 1], cz = T.centroid[3 * (size_t)I + 2];
   double g[1] = {0.0};
-  for (int k = threadIdx.x; k < cnt; k += kTlThreads) {
-    const int node = T.agg_nodes[first + k];
-    double rv[6], dv[6], zv[6];
-    ld6(r, node, rv); ld6(dinv, node, dv);
+  for (int w = threadIdx.x; w < 3 * cnt; w += kTlThreads) {
+    const int node = T.agg_nodes[first + w / 3], part = w % 3;
+    const double2 rv = ld2(r, node, part), dv = ld2(dinv, node, part);
     const double* pp = T.xyz + 3 * (size_t)node;
     const double rx = pp[0] - cx, ry = pp[1] - cy, rz = pp[2] - cz;
-    const uint8_t* fm = T.free_mask + 6 * (size_t)node;
+    const uint8_t* fm = T.free_mask + 6 * (size_t)node + 2 * part;
     double c[6];                                   // (P y)_node = (y_t + y_w x rho, y_w)
     c[0] = y[0] + y[4] * rz - y[5] * ry;
     c[1] = y[1] + y[5] * rx - y[3] * rz;
     c[2] = y[2] + y[3] * ry - y[4] * rx;
     c[3] = y[3]; c[4] = y[4]; c[5] = y[5];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      zv[a] = dv[a] * rv[a] + (fm[a] ? c[a] : 0.0);
-      g[0] += rv[a] * zv[a];
-    }
-    st6(z, node, zv);
+    double ca = c[0], cb = c[1];
+    if (part == 1) { ca = c[2]; cb = c[3]; }
+    if (part == 2) { ca = c[4]; cb = c[5]; }
+    double2 zv;
+    zv.x = T.omega * dv.x * rv.x + (fm[0] ? ca : 0.0);
+    zv.y = T.omega * dv.y * rv.y + (fm[1] ? cb : 0.0);
+    g[0] += rv.x * zv.x + rv.y * zv.y;
+    st2(z, node, part, zv);
   }
   block_sum_all<kTlThreads, 1>(g, s_part);
   if (threadIdx.x == 0) L.upd_partials[(size_t)wr * 2 * L.pstride + I] = g[0];
@@ -442,6 +462,8 @@ int pcg_twolevel(femb_handle* h, const femb_solve_opts& o, const double* d_b, fe
   TlDev T;
   T.agg_ptr = h->agg_ptr.p; T.agg_nodes = h->agg_nodes.p; T.centroid = h->agg_centroid.p; T.xyz = h->xyz.p;
   T.free_mask = h->free_mask.p; T.inv = h->coarse_inv.p; T.rc = h->coarse_r.p; T.n_agg = n_agg; T.n_pad = (int)h->coarse_n_pad;
+  T.omega = kTlOmega;
+  if (const char* e = getenv("FEMB_TL_OMEGA")) { const double v = atof(e); if (v > 0.0) T.omega = v; }
   PcgLink L;
   L.upd_partials = h->fpartials.p; L.op_partials = h->fpartials.p + (size_t)4 * pstride;
   L.scal = h->scal.p; L.flags = h->flags.p;

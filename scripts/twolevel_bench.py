@@ -21,7 +21,9 @@ uj, _, st = m.solve_static(method=L.SOLVER_PCG, precond=L.PRECOND_JACOBI, want_r
 uj, _, st = m.solve_static(method=L.SOLVER_PCG, precond=L.PRECOND_JACOBI, want_reactions=False)
 print(f"jacobi     : {st['iterations']} its, {st['device_ms']:.1f} ms, {nfree / st['device_ms'] / 1e3:.2f} M DOF/s", flush=True)
 for a in aggs:
-    if a:
+    if a.startswith("w"):        # "w2.0": Jacobi weight omega, aggregates as before
+        os.environ["FEMB_TL_OMEGA"] = a[1:]
+    elif a:
         os.environ["FEMB_COARSE_AGGS"] = a
     m.set_mesh(mesh.points, mesh.cells_dict["line"], es[::-1].copy(), props, E, E / (2 * (1 + nu)))   # force a new symbolic phase
     m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)))
