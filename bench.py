@@ -331,7 +331,7 @@ def run_gpu(args):
         two_level_modal = os.environ.get("FEMB_BENCH_MODAL_PRECOND", "two_level") != "jacobi"
         lam, _, mst = m.modal(k=20, rtol=1e-8, precond=L.PRECOND_TWO_LEVEL if two_level_modal else L.PRECOND_JACOBI)
         extra["modal"] = {"metric": "ms_per_20_mode_modal", "ms": mst["device_ms"], "modes": int(len(lam)),
-                          "lockstep_pcg_iterations": mst["iterations"], "matrix_passes": mst["spmv_launches"],
+                          "pcg_iterations": mst["iterations"], "matrix_passes": mst["spmv_launches"],
                           "rel_residual": mst["rel_residual"], "omega_min_rad_s": float(np.sqrt(lam[0])),
                           "omega_max_rad_s": float(np.sqrt(lam[-1])),
                           "operator": "matrix-free (EBE)" if mst.get("op_used") == L.OP_EBE else "assembled BSR SpMM",

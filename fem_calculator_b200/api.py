@@ -82,7 +82,7 @@ class Handle:
         self._check(self.lib.femb_apply_k(self._h, int(op), int(masked), x, y, C.byref(used)))
         return y, used.value
 
-    def modal(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6, op=L.OP_AUTO, precond=L.PRECOND_JACOBI):
+    def modal(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6, op=L.OP_AUTO, precond=L.PRECOND_AUTO):
         o = L.EigOpts(k, block, max_iter, int(op), rtol, lambda_min, int(precond), 0)
         st = L.Stats()
         lam = np.zeros(k)
