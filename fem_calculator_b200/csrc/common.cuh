@@ -170,6 +170,7 @@ struct femb_handle {
   femb::DevBuf<double> agg_centroid;        // (n_agg,3)
   femb::DevBuf<double> coarse_aug;          // (2 n_pad)^2 work matrix of the inversion
   femb::DevBuf<double> coarse_inv;          // (n_pad, n_pad) inverse of the Galerkin matrix
+  femb::DevBuf<double> coarse_invp;         // its lower 6x6 blocks, packed (FEMB_TL_PACKED)
   femb::DevBuf<double> coarse_r;            // (4 * n_pad) restricted residual(s)
   femb::DevBuf<double> coarse_scratch;      // chunk partial sums of the Galerkin assembly
   int64_t coarse_scratch_per_agg = 0;
