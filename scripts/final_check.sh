@@ -10,6 +10,7 @@ OFF=$(us gpurun_out/r1_pf_off.log); ON=$(us gpurun_out/r1_pf_on.log)
 PF=$(python -c "print(1 if float('${ON:-999}') < 0.99 * float('${OFF:-1}') else 0)")
 echo "prefetch off ${OFF} us/it, on ${ON} us/it -> FEMB_TL_PREFETCH=${PF}" | tee gpurun_out/r1_pf_choice.log
 export FEMB_TL_PREFETCH=$PF
+timeout 60 python __graft_entry__.py --smoke 2>&1 | tail -1
 timeout 150 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/r1_tests_final3.log
 timeout 200 python bench.py > gpurun_out/r1_bench_final3.json 2> gpurun_out/r1_bench_final3.err
 python -c "
