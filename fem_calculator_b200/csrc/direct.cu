@@ -462,13 +462,54 @@ chol_potrf_block_reg_kernel(double* __restrict__ A, int64_t ld, int k0, int* sta
     if (c <= i) row[c] = a[c];
 }
 
-static bool potrf_reg_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("FEMB_POTRF_REG"); on = (e && e[0] == '0') ? 0 : 1; }   // default on; 0 = shared-memory version
-  return on != 0;
+// Leaner form of the register-resident kernel (the default; FEMB_POTRF_REG=1 / 0 select the older ones): the ncu capture of the version above
+// shows it instruction-fetch bound (stall no_instruction 5.6 per issue, 11k instructions per warp).  Here
+// the update of row i runs unpredicated over k = j+1..63 (entries right of the diagonal are never
+// published nor stored, so updating them is harmless), the column is read with 16-byte shared loads,
+// and 1/d, 1/sqrt(d), sqrt(d) all come from one rsqrt — about a third of the instructions.
+__global__ void __launch_bounds__(kCB)
+chol_potrf_block_lean_kernel(double* __restrict__ A, int64_t ld, int k0, int* status) {
+  __shared__ __align__(16) double col[2][kCB];
+  const int i = threadIdx.x;
+  double a[kCB];
+  {
+    const double* row = A + (size_t)(k0 + i) * ld + k0;
+#pragma unroll
+    for (int c = 0; c < kCB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(row + c); a[c] = v.x; a[c + 1] = v.y; }
+  }
+#pragma unroll
+  for (int j = 0; j < kCB; ++j) {
+    double* cj = col[j & 1];
+    if (i >= j) cj[i] = a[j];
+    __syncthreads();
+    double d = cj[j];
+    if (!(d > 0.0)) { if (i == j) *status = 1; d = 1.0; }
+    const double rs = rsqrt(d);               // 1/sqrt(d); d * rs = sqrt(d); rs * rs = 1/d
+    const double t = a[j] * (rs * rs);
+    if (((j + 1) & 1) && j + 1 < kCB) a[j + 1] -= t * cj[j + 1];          // odd first column: scalar, then pairs
+#pragma unroll
+    for (int k = (j + 2) & ~1; k < kCB; k += 2) {
+      const double2 c2 = *reinterpret_cast<const double2*>(cj + k);
+      a[k] -= t * c2.x;
+      a[k + 1] -= t * c2.y;
+    }
+    a[j] = (i == j) ? d * rs : a[j] * rs;
+  }
+  double* row = A + (size_t)(k0 + i) * ld + k0;
+#pragma unroll
+  for (int c = 0; c < kCB; ++c)
+    if (c <= i) row[c] = a[c];
+}
+
+static int potrf_variant() {      // FEMB_POTRF_REG: 0 = shared-memory version, 1 = register rows, 2 = lean register rows (default)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FEMB_POTRF_REG"); v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+  return v;
 }
 static void launch_potrf_block(femb_handle* h, double* A, int64_t ld, int k0, int* status) {
-  if (potrf_reg_enabled()) chol_potrf_block_reg_kernel<<<1, kCB, 0, h->stream>>>(A, ld, k0, status);
+  const int v = potrf_variant();
+  if (v == 2) chol_potrf_block_lean_kernel<<<1, kCB, 0, h->stream>>>(A, ld, k0, status);
+  else if (v == 1) chol_potrf_block_reg_kernel<<<1, kCB, 0, h->stream>>>(A, ld, k0, status);
   else chol_potrf_block_kernel<<<1, 256, 0, h->stream>>>(A, ld, k0, status);
 }
 
