@@ -278,3 +278,26 @@ def symbolic_aggregates(points, n_parts):
     if rc:
         raise L.FembError(rc, "femb_symbolic_aggregates")
     return agg
+
+
+def symbolic_coarse(points, conn, n_parts):
+    """Host-only: (agg_of_node, nbr_ptr, nbr, blk_slot) of the two-level preconditioner's symbolic
+    phase for a frame mesh (csrc/coarse.cpp) — needs no GPU."""
+    lib = L.load()
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    cn = np.ascontiguousarray(conn, dtype=np.int64).reshape(-1, 2)
+    n = len(pts)
+    agg = np.zeros(n, dtype=np.int32)
+    nbr_ptr = np.zeros(int(n_parts) + 1, dtype=np.int32)
+    nn = C.c_int64()
+    rc = lib.femb_symbolic_coarse(n, len(cn), L.ptr(cn), L.ptr(pts), int(n_parts), L.ptr(agg), L.ptr(nbr_ptr), C.byref(nn), None, None)
+    if rc:
+        raise L.FembError(rc, "femb_symbolic_coarse")
+    rowptr, colidx = symbolic_pattern(n, cn)
+    nbr = np.zeros(nn.value, dtype=np.int32)
+    slot = np.zeros(len(colidx), dtype=np.int32)
+    rc = lib.femb_symbolic_coarse(n, len(cn), L.ptr(cn), L.ptr(pts), int(n_parts), L.ptr(agg), L.ptr(nbr_ptr), C.byref(nn),
+                                  L.ptr(nbr), L.ptr(slot))
+    if rc:
+        raise L.FembError(rc, "femb_symbolic_coarse")
+    return agg, nbr_ptr, nbr, slot

@@ -107,3 +107,29 @@ extern "C" int femb_symbolic_aggregates(int64_t n_nodes, const double* xyz, int3
   if (n_nodes) std::memcpy(agg_of_node, agg.data(), (size_t)n_nodes * sizeof(int32_t));
   return FEMB_OK;
 }
+
+// Host-only view of the whole coarse symbolic phase for the CPU test-suite: aggregates, aggregate
+// adjacency and per-block slots of a frame mesh (2 nodes per element).  Two calls: with nbr == NULL
+// and blk_slot == NULL only agg_of_node, nbr_ptr and *n_nbr are filled.
+extern "C" int femb_symbolic_coarse(int64_t n_nodes, int64_t n_elem, const int64_t* conn, const double* xyz,
+                                    int32_t n_parts, int32_t* agg_of_node, int32_t* nbr_ptr, int64_t* n_nbr,
+                                    int32_t* nbr, int32_t* blk_slot) {
+  if (n_nodes < 0 || n_elem < 0 || n_parts < 1 || (!conn && n_elem > 0) || (!xyz && n_nodes > 0) || !n_nbr) return FEMB_ERR_ARG;
+  std::vector<int32_t> c32((size_t)n_elem * 2);
+  for (size_t i = 0; i < c32.size(); ++i) {
+    if (conn[i] < 0 || conn[i] >= n_nodes) return FEMB_ERR_ARG;
+    c32[i] = (int32_t)conn[i];
+  }
+  femb::Symbolic S;
+  femb::build_symbolic(n_nodes, n_elem, 2, 6, c32.data(), 1 << 30, 1 << 30, S);
+  std::vector<int32_t> agg;
+  femb::build_aggregates(n_nodes, xyz, n_parts, agg);
+  femb::CoarseSym C;
+  femb::build_coarse_symbolic(S, agg, n_parts, C);
+  if (agg_of_node && n_nodes) std::memcpy(agg_of_node, agg.data(), (size_t)n_nodes * sizeof(int32_t));
+  if (nbr_ptr) std::memcpy(nbr_ptr, C.nbr_ptr.data(), C.nbr_ptr.size() * sizeof(int32_t));
+  *n_nbr = (int64_t)C.nbr.size();
+  if (nbr && !C.nbr.empty()) std::memcpy(nbr, C.nbr.data(), C.nbr.size() * sizeof(int32_t));
+  if (blk_slot && !C.blk_slot.empty()) std::memcpy(blk_slot, C.blk_slot.data(), C.blk_slot.size() * sizeof(int32_t));
+  return FEMB_OK;
+}

@@ -282,6 +282,14 @@ int femb_symbolic_pattern(int64_t n_nodes, int64_t n_elem, int32_t nodes_per_ele
  * agg_of_node: (n_nodes) out, values in [0, n_parts).                                      */
 int femb_symbolic_aggregates(int64_t n_nodes, const double* xyz, int32_t n_parts, int32_t* agg_of_node);
 
+/* Host-only: the whole symbolic phase of the two-level preconditioner for a frame mesh (conn: (n_elem,2)) —
+ * aggregates, aggregate adjacency induced by the block pattern (nbr_ptr (n_parts+1), nbr: ascending, self
+ * included) and, per stored block b = (i, j) of femb_symbolic_pattern, blk_slot[b] with
+ * nbr[nbr_ptr[agg(i)] + blk_slot[b]] == agg(j).  Two calls: nbr == blk_slot == NULL returns *n_nbr.      */
+int femb_symbolic_coarse(int64_t n_nodes, int64_t n_elem, const int64_t* conn, const double* xyz,
+                         int32_t n_parts, int32_t* agg_of_node, int32_t* nbr_ptr, int64_t* n_nbr,
+                         int32_t* nbr, int32_t* blk_slot);
+
 #ifdef __cplusplus
 }
 #endif

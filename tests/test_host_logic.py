@@ -193,3 +193,25 @@ def test_aggregates_are_a_balanced_partition():
         ext = p.max(0) - p.min(0)
         assert (ext <= np.array([12, 10, 9]) * 0.5 + 0.2).all(), (a, ext)
     assert api.symbolic_aggregates(np.zeros((0, 3)), 4).size == 0
+
+
+@pytest.mark.parametrize("parts", [1, 5, 37])
+def test_coarse_symbolic_slots_and_adjacency(parts):
+    """Aggregate adjacency and per-block slots (csrc/coarse.cpp) against a numpy restatement from the
+    block pattern: neighbour lists sorted, unique, self included, symmetric; every block's slot points
+    at the aggregate of its column node."""
+    mesh, _, _ = meshgen.lattice_frame_case(9, 7, 6, jitter=0.05)
+    conn = mesh.cells_dict["line"]
+    n = len(mesh.points)
+    agg, nbr_ptr, nbr, slot = api.symbolic_coarse(mesh.points, conn, parts)
+    assert np.array_equal(agg, api.symbolic_aggregates(mesh.points, parts))
+    rowptr, colidx = api.symbolic_pattern(n, conn)
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    pairs = set(zip(agg[rows].tolist(), agg[colidx].tolist()))
+    for a in range(parts):
+        lst = nbr[nbr_ptr[a]:nbr_ptr[a + 1]]
+        assert np.all(np.diff(lst) > 0) and a in lst
+        assert set(lst.tolist()) == {j for (i, j) in pairs if i == a}
+        for j in lst:
+            assert a in nbr[nbr_ptr[j]:nbr_ptr[j + 1]]
+    assert np.array_equal(nbr[nbr_ptr[agg[rows]] + slot], agg[colidx])
