@@ -89,6 +89,8 @@ SIGNATURES = {
     "femb_io_bytes": (None, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
     "femb_symbolic_pattern": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _I64, C.POINTER(C.c_int64), _P, _P]),
     "femb_symbolic_aggregates": (C.c_int, [C.c_int64, _P, C.c_int32, _P]),
+    "femb_symbolic_lines": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_double, C.c_int32, C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int64), _P, _P, _P, _P]),
     "femb_symbolic_coarse": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, _P, C.POINTER(C.c_int64), _P, _P]),
 }
 

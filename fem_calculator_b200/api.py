@@ -301,3 +301,24 @@ def symbolic_coarse(points, conn, n_parts):
     if rc:
         raise L.FembError(rc, "femb_symbolic_coarse")
     return agg, nbr_ptr, nbr, slot
+
+
+def symbolic_lines(points, conn, cos_tol=0.94, min_nodes=3):
+    """Host-only: member lines (maximal chains of nearly collinear members, csrc/coarse.cpp) as
+    (line_ptr, line_nodes, line_dir (n_lines,3), line_family) — needs no GPU."""
+    lib = L.load()
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    cn = np.ascontiguousarray(conn, dtype=np.int64).reshape(-1, 2)
+    nl, nn = C.c_int64(), C.c_int64()
+    args = (len(pts), len(cn), L.ptr(cn), L.ptr(pts), float(cos_tol), int(min_nodes), C.byref(nl), C.byref(nn))
+    rc = lib.femb_symbolic_lines(*args, None, None, None, None)
+    if rc:
+        raise L.FembError(rc, "femb_symbolic_lines")
+    line_ptr = np.zeros(nl.value + 1, dtype=np.int32)
+    line_nodes = np.zeros(max(nn.value, 1), dtype=np.int32)
+    line_dir = np.zeros((max(nl.value, 1), 3))
+    fam = np.zeros(max(nl.value, 1), dtype=np.int32)
+    rc = lib.femb_symbolic_lines(*args, L.ptr(line_ptr), L.ptr(line_nodes), L.ptr(line_dir), L.ptr(fam))
+    if rc:
+        raise L.FembError(rc, "femb_symbolic_lines")
+    return line_ptr, line_nodes[:nn.value], line_dir[:nl.value], fam[:nl.value]

@@ -88,6 +88,9 @@ struct CoarseSym {
 };
 void build_aggregates(int64_t n_nodes, const double* xyz, int n_parts, std::vector<int32_t>& agg);
 void build_coarse_symbolic(const Symbolic& S, const std::vector<int32_t>& agg, int n_agg, CoarseSym& C);
+void build_member_lines(int64_t n_nodes, int64_t n_elem, const int32_t* conn, const double* xyz, double cos_tol,
+                        int min_nodes, std::vector<int32_t>& line_ptr, std::vector<int32_t>& line_nodes,
+                        std::vector<double>& line_dir, std::vector<int32_t>& line_family);
 
 void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int32_t* conn,
                     int tile_max_blocks, int tile_max_contrib, Symbolic& out);

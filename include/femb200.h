@@ -290,6 +290,15 @@ int femb_symbolic_coarse(int64_t n_nodes, int64_t n_elem, const int64_t* conn, c
                          int32_t n_parts, int32_t* agg_of_node, int32_t* nbr_ptr, int64_t* n_nbr,
                          int32_t* nbr, int32_t* blk_slot);
 
+/* Host-only: member lines of a frame mesh — maximal chains of members whose consecutive directions differ by
+ * less than acos(cos_tol) (groundwork for the line coarse space).  Every element belongs
+ * to exactly one chain; chains with fewer than min_nodes nodes are dropped.  line_nodes: node ids ordered
+ * along each line (line_ptr: (n_lines+1)); line_dir: (n_lines,3) unit end-to-end direction; line_family:
+ * index of its dominant component.  Two calls: line_nodes == NULL returns *n_lines and *n_line_nodes.     */
+int femb_symbolic_lines(int64_t n_nodes, int64_t n_elem, const int64_t* conn, const double* xyz,
+                        double cos_tol, int32_t min_nodes, int64_t* n_lines, int64_t* n_line_nodes,
+                        int32_t* line_ptr, int32_t* line_nodes, double* line_dir, int32_t* line_family);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,3 +215,92 @@ def test_coarse_symbolic_slots_and_adjacency(parts):
         for j in lst:
             assert a in nbr[nbr_ptr[j]:nbr_ptr[j + 1]]
     assert np.array_equal(nbr[nbr_ptr[agg[rows]] + slot], agg[colidx])
+
+
+def _check_lines_cover(conn, line_ptr, line_nodes):
+    """consecutive nodes of a line are joined by an element; no element is used twice"""
+    key = {tuple(sorted(e)): k for k, e in enumerate(conn.tolist())}
+    used = set()
+    for a, b in zip(line_ptr[:-1], line_ptr[1:]):
+        nodes = line_nodes[a:b].tolist()
+        for u, v in zip(nodes[:-1], nodes[1:]):
+            k = key[tuple(sorted((u, v)))]
+            assert k not in used
+            used.add(k)
+    return used
+
+
+@pytest.mark.parametrize("jitter", [0.0, 0.05])
+def test_member_lines_of_a_lattice(jitter):
+    """Member-line detection (csrc/coarse.cpp): a 6x5x4 lattice has 20 + 24 + 30 lines of 6 / 5 / 4
+    nodes, grouped by direction, and together they use every member exactly once."""
+    mesh, _, _ = meshgen.lattice_frame_case(6, 5, 4, jitter=jitter)
+    conn = mesh.cells_dict["line"]
+    lp, ln, ld, lf = api.symbolic_lines(mesh.points, conn)
+    assert len(lf) == 74 and np.array_equal(np.bincount(lf), [20, 24, 30])
+    for fam, length in ((0, 6), (1, 5), (2, 4)):
+        assert np.all(np.diff(lp)[lf == fam] == length)
+        assert np.all(ld[lf == fam][:, fam] > 0.98)
+    assert len(_check_lines_cover(conn, lp, ln)) == len(conn)
+    again = api.symbolic_lines(mesh.points, conn)
+    assert all(np.array_equal(x, y) for x, y in zip((lp, ln, ld, lf), again))
+
+
+def test_member_lines_corners_rings_and_short_members():
+    # an L: 4 members along x, then 3 along y -> two lines meeting at the corner node
+    pts = np.array([[i, 0, 0] for i in range(5)] + [[4, j, 0] for j in range(1, 4)], dtype=float)
+    conn = np.array([[i, i + 1] for i in range(7)])
+    lp, ln, ld, lf = api.symbolic_lines(pts, conn)
+    assert len(lf) == 2 and sorted(np.diff(lp).tolist()) == [4, 5] and sorted(lf.tolist()) == [0, 1]
+    # a square ring with subdivided sides -> four lines; a regular 60-gon (6 degrees per corner) -> one closed line
+    side = [[i, 0, 0] for i in range(4)] + [[4, i, 0] for i in range(4)] + [[4 - i, 4, 0] for i in range(4)] + [[0, 4 - i, 0] for i in range(4)]
+    ring = np.array([[i, (i + 1) % 16] for i in range(16)])
+    lp, ln, ld, lf = api.symbolic_lines(np.array(side, dtype=float), ring)
+    assert len(lf) == 4 and np.all(np.diff(lp) == 5)
+    t = 2 * np.pi * np.arange(60) / 60
+    lp, ln, ld, lf = api.symbolic_lines(np.stack([np.cos(t), np.sin(t), 0 * t], 1), np.array([[i, (i + 1) % 60] for i in range(60)]))
+    assert len(lf) == 1 and lp[1] == 61 and ln[0] == ln[-1]
+    # isolated single members are dropped at min_nodes = 3 and kept at 2; empty meshes are fine
+    pts = np.array([[0, 0, 0], [1, 0, 0], [0, 5, 0], [0, 5, 1]], dtype=float)
+    two = np.array([[0, 1], [2, 3]])
+    assert len(api.symbolic_lines(pts, two)[3]) == 0
+    assert len(api.symbolic_lines(pts, two, min_nodes=2)[3]) == 2
+    assert len(api.symbolic_lines(np.zeros((0, 3)), np.zeros((0, 2), dtype=np.int64))[3]) == 0
+
+
+def test_member_line_modes_cut_the_iteration_count():
+    """Why the lines matter: with one axial translation mode per detected line next
+    to the rigid-body modes of the aggregates, the additive two-level PCG of csrc/twolevel.cu (restated in
+    numpy on the oracle's K) needs several times fewer iterations."""
+    import scipy.sparse as sp
+    from prototypes.coarse_space_study import pcg, rigid_body_modes
+    mesh, sec, bc = meshgen.lattice_frame_case(10, 9, 8, jitter=0.05)
+    es, props = meshgen.section_table(mesh, sec)
+    K, _ = S.frame_assemble(mesh.points, mesh.cells_dict["line"], es, props, meshgen.E_STEEL, meshgen.NU_STEEL)
+    fixed, free, f = S.frame_bc(mesh, bc)
+    n = K.shape[0]
+    mask = np.zeros(n, bool); mask[free] = True
+    Dm = sp.diags(mask.astype(float))
+    A = (Dm @ K @ Dm + sp.diags((~mask).astype(float))).tocsr()
+    b, d = f * mask, A.diagonal()
+    agg = api.symbolic_aggregates(mesh.points, 4).astype(np.int64)
+    P = rigid_body_modes(mesh.points, agg, 4, mask)
+    lp, ln, ld, lf = api.symbolic_lines(mesh.points, mesh.cells_dict["line"])
+    rows, cols, vals = [], [], []
+    for k in range(len(lf)):
+        nodes = ln[lp[k]:lp[k + 1]]
+        for c in range(3):
+            rows.append(6 * nodes + c); cols.append(np.full(len(nodes), k)); vals.append(np.full(len(nodes), ld[k, c]))
+    Pl = Dm @ sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, len(lf)))
+
+    def iterations(Pc):
+        Kc = (Pc.T @ A @ Pc).toarray()
+        zero = np.diag(Kc) <= 0
+        Kc[zero, zero] = 1.0
+        Kci = np.linalg.inv(Kc)
+        x, it = pcg(A, b, lambda r: 2 * r / d + Pc @ (Kci @ (Pc.T @ r)))
+        assert np.linalg.norm(A @ x - b) <= 1e-11 * np.linalg.norm(b)
+        return it
+
+    it_rbm, it_lines = iterations(P.tocsr()), iterations(sp.hstack([P, Pl]).tocsr())
+    assert it_lines < 0.3 * it_rbm, (it_rbm, it_lines)
