@@ -14,12 +14,13 @@
 // Pieces (all deterministic — fixed-order sums, no float atomics):
 //   tl_centroid_kernel        centroid of every aggregate (per assembled K: coordinates may change)
 //   tl_coarse_assemble_kernel Kc = P^T A P from the assembled BSR K: one CTA per coarse block row, one
-//                             thread per entry of a coarse 6x6 block, blocks of K visited in storage order
+//                             thread per entry of a coarse 6x6 block, work items = (neighbour slot, node
+//                             chunk), chunk partials added in chunk order
 //   coarse_invert (direct.cu) Kc^-1 explicitly, on the DMMA Cholesky kernels
 //   tl_update_kernel          one CTA per aggregate: the Chronopoulos-Gear vector update of its nodes
 //                             fused with the restriction rc = P^T r of the new residual
 //   tl_coarse_z_kernel        one CTA per aggregate: its six rows of y = Kc^-1 rc, then
-//                             z = D^-1 r + P y for its nodes and the (r, z) partial
+//                             z = omega D^-1 r + P y for its nodes and the (r, z) partial
 // The iteration is  operator (ebe.cu, linked reductions) -> tl_update -> tl_coarse_z : three kernels,
 // the reductions travel as published partial sums exactly as in the linked Jacobi-PCG (pcg_common.cuh).
 #include <algorithm>
