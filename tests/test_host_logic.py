@@ -304,3 +304,57 @@ def test_member_line_modes_cut_the_iteration_count():
 
     it_rbm, it_lines = iterations(P.tocsr()), iterations(sp.hstack([P, Pl]).tocsr())
     assert it_lines < 0.3 * it_rbm, (it_rbm, it_lines)
+
+
+def test_line_precond_spec_matches_matrix_form():
+    """tests/prototypes/line_precond_spec.py (the loop-level specification the round-2 kernels will be
+    transcribed from) against plain sparse algebra: per-direction Galerkin blocks, segment diagonal and
+    one application of the preconditioner."""
+    import scipy.sparse as sp
+    from prototypes import line_precond_spec as LS
+    mesh, sec, bc = meshgen.lattice_frame_case(7, 6, 5, jitter=0.05)
+    es, props = meshgen.section_table(mesh, sec)
+    conn = mesh.cells_dict["line"]
+    K, _ = S.frame_assemble(mesh.points, conn, es, props, meshgen.E_STEEL, meshgen.NU_STEEL)
+    fixed, free, f = S.frame_bc(mesh, bc)
+    n = K.shape[0]
+    mask = np.zeros(n, bool); mask[free] = True
+    Dm = sp.diags(mask.astype(float))
+    A = (Dm @ K @ Dm + sp.diags((~mask).astype(float))).tocsr()
+    lp, ln, ld, lf = api.symbolic_lines(mesh.points, conn)
+    Kb = K.tobsr((6, 6))
+    Kb.sort_indices()
+    rowptr, colidx = api.symbolic_pattern(len(mesh.points), conn)
+    assert np.array_equal(rowptr, Kb.indptr) and np.array_equal(colidx, Kb.indices)
+    Kf, row_in_family, Dseg = LS.galerkin(rowptr, colidx, Kb.data, mask, lp, ln, ld, lf)
+    # matrix form
+    rows, cols, vals, srows, scols = [], [], [], [], []
+    seg_first, n_seg = LS.segments(lp)
+    for k in range(len(lf)):
+        nodes = ln[lp[k]:lp[k + 1]]
+        for c in range(3):
+            rows.append(6 * nodes + c); cols.append(np.full(len(nodes), k)); vals.append(np.full(len(nodes), ld[k, c]))
+            scols.append(seg_first[k] + np.arange(len(nodes)) // LS.SEG)
+    Pl = (Dm @ sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, len(lf)))).tocsr()
+    Ps = (Dm @ sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(scols))), shape=(n, n_seg))).tocsr()
+    G = (Pl.T @ A @ Pl).toarray()
+    dead = np.diag(G) <= 0.0                 # lines inside the fixed base: identity rows, as in the spec
+    G[dead, dead] = 1.0
+    for fam in range(3):
+        idx = np.flatnonzero(lf == fam)
+        idx = idx[np.argsort(row_in_family[idx])]
+        ref = G[np.ix_(idx, idx)]
+        assert np.abs(Kf[fam] - ref).max() <= 1e-12 * np.abs(ref).max()
+    dref = (Ps.T @ A @ Ps).diagonal()
+    assert np.abs(Dseg - dref).max() <= 1e-12 * np.abs(dref).max()
+    Kf_inv = [np.linalg.inv(m) for m in Kf]
+    rng = np.random.default_rng(7)
+    r = rng.standard_normal(n) * mask
+    d = A.diagonal()
+    z = LS.apply(r, 1.0 / d, 2.0, mask, lp, ln, ld, lf, Kf_inv, row_in_family, Dseg)
+    Gbd = np.zeros_like(G)
+    for fam in range(3):
+        idx = np.flatnonzero(lf == fam)
+        Gbd[np.ix_(idx, idx)] = G[np.ix_(idx, idx)]
+    zref = 2.0 * r / d + Pl @ np.linalg.solve(Gbd, Pl.T @ r) + Ps @ ((Ps.T @ r) / np.where(dref > 0, dref, 1.0))
+    assert np.abs(z - zref).max() <= 1e-10 * np.abs(zref).max()
