@@ -201,6 +201,17 @@ class BeamAnalysisB200:
     def bc_nodes_indexing(self, element_type, bc_name):
         return _group_nodes(self.mesh, element_type, bc_name)
 
+    def qr_algorithm(self, A, max_iter=1000, tol=1e-9):
+        """BeamSolver.py:467 — the unshifted dense QR iteration on inv(M_ff) K_ff.  Deliberately not
+        re-created: it is the O(n^3)-per-sweep step this library replaces (femb_modal solves the
+        symmetric pencil K_ff phi = lambda M_ff phi for the lowest modes on the GPU), and a numpy
+        restatement here would be a CPU path inside the product.  The reference's own method keeps
+        working on ITS class (INTEGRATION.md patches run_simulation only); on this class it points
+        the caller at the supported route."""
+        raise NotImplementedError(
+            "qr_algorithm (BeamSolver.py:467) is superseded by the GPU modal solve: call run_simulation(k_modes=...) "
+            "or fem_calculator_b200.api.FrameModel.modal(); the dense QR iteration is not part of femb200")
+
     def _one_element(self, L_, E, G, props, rho, want_k, want_m):
         m = FrameModel(self.device)
         try:

@@ -358,3 +358,10 @@ def test_line_precond_spec_matches_matrix_form():
         Gbd[np.ix_(idx, idx)] = G[np.ix_(idx, idx)]
     zref = 2.0 * r / d + Pl @ np.linalg.solve(Gbd, Pl.T @ r) + Ps @ ((Ps.T @ r) / np.where(dref > 0, dref, 1.0))
     assert np.abs(z - zref).max() <= 1e-10 * np.abs(zref).max()
+
+
+def test_qr_algorithm_helper_points_at_the_modal_solve():
+    """BeamSolver.py:467 is deliberately not restated on the CPU: the mirror class says so."""
+    w = compat.BeamAnalysisB200.__new__(compat.BeamAnalysisB200)
+    with pytest.raises(NotImplementedError, match="modal"):
+        w.qr_algorithm(np.eye(3))
