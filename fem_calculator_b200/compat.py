@@ -201,6 +201,43 @@ class BeamAnalysisB200:
     def bc_nodes_indexing(self, element_type, bc_name):
         return _group_nodes(self.mesh, element_type, bc_name)
 
+    # ---- result consumers (the step after the path): the two tables of the reference's report as arrays / CSV
+    def nodal_result_table(self):
+        """Rows of the 'Nodal displacement and stress results' table (BeamSolver.py:530-538) as an
+        (N, 8) float array: node id, x, y, z [m], u_x, u_y, u_z [m], smoothed stress [MPa]."""
+        if self.u is None or self.smoothed_stresses is None:
+            raise RuntimeError("run_simulation first")
+        pts = np.asarray(self.points, dtype=np.float64)
+        disp = np.asarray(self.u, dtype=np.float64).reshape(-1, 6)[:, :3]
+        return np.column_stack([np.arange(len(pts)), pts, disp, np.asarray(self.smoothed_stresses) / 1e6])
+
+    def modal_result_table(self, n_modes=10):
+        """Rows of the 'Modal Analysis Results' table (BeamSolver.py:540-547): mode number, frequency in
+        rad/s and in Hz for the first ``n_modes`` (the report prints 10) — (m, 3) float array."""
+        if self.natural_frequencies is None:
+            return np.zeros((0, 3))
+        w = np.asarray(self.natural_frequencies, dtype=np.float64)[:n_modes]
+        return np.column_stack([np.arange(1, len(w) + 1), w, w / (2 * np.pi)])
+
+    def write_result_tables(self, prefix):
+        """The two tables as CSV with the reference's column titles and number formats
+        (``<prefix>_nodes.csv``, ``<prefix>_modes.csv``); returns the paths written."""
+        paths = []
+        nodal = self.nodal_result_table()
+        with open(f"{prefix}_nodes.csv", "w") as fh:
+            fh.write("Node ID,X (m),Y (m),Z (m),Disp X (m),Disp Y (m),Disp Z (m),Stress (MPa)\n")
+            for r in nodal:
+                fh.write(f"{int(r[0])},{r[1]:.4f},{r[2]:.4f},{r[3]:.4f},{r[4]:.4e},{r[5]:.4e},{r[6]:.4e},{r[7]:.4f}\n")
+        paths.append(f"{prefix}_nodes.csv")
+        modal = self.modal_result_table()
+        if len(modal):
+            with open(f"{prefix}_modes.csv", "w") as fh:
+                fh.write("Mode,Frequency (rad/s),Frequency (Hz)\n")
+                for r in modal:
+                    fh.write(f"{int(r[0])},{r[1]:.4f},{r[2]:.4f}\n")
+            paths.append(f"{prefix}_modes.csv")
+        return paths
+
     def qr_algorithm(self, A, max_iter=1000, tol=1e-9):
         """BeamSolver.py:467 — the unshifted dense QR iteration on inv(M_ff) K_ff.  Deliberately not
         re-created: it is the O(n^3)-per-sweep step this library replaces (femb_modal solves the

@@ -365,3 +365,24 @@ def test_qr_algorithm_helper_points_at_the_modal_solve():
     w = compat.BeamAnalysisB200.__new__(compat.BeamAnalysisB200)
     with pytest.raises(NotImplementedError, match="modal"):
         w.qr_algorithm(np.eye(3))
+
+
+def test_result_tables_follow_the_reference_report(tmp_path):
+    """BeamSolver.py:530-547: nodal table (node, x, y, z, u_x, u_y, u_z, stress in MPa) and the
+    first-10 frequency table (mode, rad/s, Hz), as arrays and CSV with the report's formats."""
+    w = compat.BeamAnalysisB200.__new__(compat.BeamAnalysisB200)
+    w.points = np.array([[0.0, 0.0, 0.0], [1.0, 0.5, 0.25]])
+    w.u = np.arange(12, dtype=float) * 1e-3
+    w.smoothed_stresses = np.array([2.5e6, 48e6])
+    w.natural_frequencies = np.linspace(10.0, 130.0, 13)
+    t = w.nodal_result_table()
+    assert t.shape == (2, 8) and np.allclose(t[1], [1, 1.0, 0.5, 0.25, 6e-3, 7e-3, 8e-3, 48.0])
+    m = w.modal_result_table()
+    assert m.shape == (10, 3) and np.allclose(m[0], [1, 10.0, 10.0 / (2 * np.pi)])
+    paths = w.write_result_tables(str(tmp_path / "run"))
+    nodes = open(paths[0]).read().splitlines()
+    assert nodes[0].startswith("Node ID,X (m)") and nodes[2] == "1,1.0000,0.5000,0.2500,6.0000e-03,7.0000e-03,8.0000e-03,48.0000"
+    modes = open(paths[1]).read().splitlines()
+    assert len(modes) == 11 and modes[1] == "1,10.0000,1.5915"
+    w.natural_frequencies = None
+    assert w.modal_result_table().shape == (0, 3) and len(w.write_result_tables(str(tmp_path / "static"))) == 1
