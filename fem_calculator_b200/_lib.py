@@ -17,7 +17,7 @@ FEMB_OK, FEMB_ERR_ARG, FEMB_ERR_CUDA, FEMB_ERR_NOT_CONVERGED, FEMB_ERR_SINGULAR,
 MAT_K, MAT_M = 0, 1
 SOLVER_AUTO, SOLVER_PCG, SOLVER_CHAIN, SOLVER_DENSE = 0, 1, 2, 3
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_TWO_LEVEL, PRECOND_AUTO = 0, 1, 2, 3, 4
-OP_AUTO, OP_BSR, OP_EBE, OP_EBE_FUSED = 0, 1, 2, 3
+OP_AUTO, OP_BSR, OP_EBE = 0, 1, 2
 
 
 class SolveOpts(C.Structure):

@@ -107,7 +107,6 @@ static int set_mesh_common(femb_handle* h, Kind kind, int bs, int nper, int64_t 
   h->have_symbolic = same_topology;
   h->assembled = h->have_bc = h->have_solution = false;
   h->n_owned_nodes = 0;
-  h->spmv_tile_nodes = 0;
   FEMB_CUDA(h, upload(h->xyz, xyz, (size_t)n_nodes * 3, h->stream));
   if (!same_topology) FEMB_CUDA(h, upload(h->conn, h->h_conn, h->stream));
   FEMB_CUDA(h, h->counters.alloc(4));

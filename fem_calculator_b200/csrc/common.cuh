@@ -145,7 +145,7 @@ struct femb_handle {
   femb::DevBuf<double> f, u0;       // load vector, prescribed values
   femb::DevBuf<double> b, x, r, z, p, q, s;
   femb::DevBuf<double> Dinv;        // block-Jacobi inverse (n_nodes,bs,bs) or Jacobi (ndof)
-  femb::DevBuf<double> r2, q2, fpartials;   // fused one-kernel-per-iteration PCG (fused_pcg.cu): ping-pong r / q, partial sums
+  femb::DevBuf<double> fpartials;   // published partial sums of the linked reductions (pcg_common.cuh: PcgLink)
   femb::DevBuf<double> mx, mr, mp, mq, mpartials, mscal;   // multi-RHS PCG (interleaved by right-hand side)
   femb::DevBuf<int32_t> mflags;
   femb::DevBuf<double> partials;    // reduction scratch
@@ -153,9 +153,6 @@ struct femb_handle {
   femb::DevBuf<int32_t> flags;      // [0] done, [1] iterations, [2] ticket counters...
   bool have_solution = false;
   femb::DevBuf<double> stress_u, stress_sigma;   // femb_frame_stress staging
-  // TMA-streamed SpMV (spmv_tma.cu): node tiles whose block values fit one shared-memory stage
-  femb::DevBuf<int32_t> spmv_tiles;
-  int spmv_tile_nodes = 0, spmv_stage_bytes = 0, spmv_n_tiles = 0;
 
   // persistent direct-solver factors (invalidated by femb_assemble / femb_set_bc)
   bool chain_factored = false, dense_factored = false;
@@ -173,7 +170,6 @@ struct femb_handle {
   femb::DevBuf<double> agg_centroid;        // (n_agg,3)
   femb::DevBuf<double> coarse_aug;          // (2 n_pad)^2 work matrix of the inversion
   femb::DevBuf<double> coarse_inv;          // (n_pad, n_pad) inverse of the Galerkin matrix
-  femb::DevBuf<double> coarse_invp;         // its lower 6x6 blocks, packed (FEMB_TL_PACKED)
   femb::DevBuf<double> coarse_r;            // (4 * n_pad) restricted residual(s)
   femb::DevBuf<double> coarse_scratch;      // chunk partial sums of the Galerkin assembly
   int64_t coarse_scratch_per_agg = 0;
@@ -255,8 +251,6 @@ int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double*
 int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
                      double* scal_out, const uint8_t* skip_node = nullptr, const int32_t* node_list = nullptr,
                      const void* p2p_dev = nullptr);
-int launch_spmv_tma(femb_handle* h, int variant, const double* x, double* y, bool masked, double* dot_partials,
-                    double* scal_out);
 // matrix-free frame operator (ebe.cu)
 bool ebe_available(const femb_handle* h);
 bool ebe_selected(const femb_handle* h, int op);
@@ -267,8 +261,6 @@ int launch_ebe(femb_handle* h, const double* x, double* y, int nb, bool masked, 
                int64_t n_rows_nodes = -1);
 int ebe_grid(const femb_handle* h, int nb, int64_t n_nodes);
 bool ebe_available_dist(const femb_handle* h);
-bool fused_pcg_applicable(const femb_handle* h, const femb_solve_opts& o);
-int pcg_fused(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 int setup_precond_public(femb_handle* h, int mode);
 int launch_reactions(femb_handle* h, bool minus_f, double* d_out);
 int setup_bc_vectors(femb_handle* h);

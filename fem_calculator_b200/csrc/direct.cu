@@ -363,7 +363,7 @@ int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const doub
 // For reduced systems small enough to be a real dense contraction (north_star (4); robust where
 // cond(K_ff) defeats CG).  A = P K P + (I - P) is expanded to a dense row-major matrix padded to a
 // multiple of 64 (identity on the padding) and factored right-looking in 64-column panels:
-//   1. chol_potrf_block_kernel   64x64 diagonal block, one CTA, shared memory
+//   1. chol_potrf_block_lean_kernel  64x64 diagonal block, one CTA, one row per thread in registers
 //   2. chol_trsm_kernel          panel rows x L_kk^-T, one thread per row (row in registers)
 //   3. chol_syrk_dmma_kernel     trailing A_ij -= P_i P_j^T on the FP64 tensor cores:
 //                                mma.sync.m8n8k4.f64 (SASS DMMA), 64x64 tile per CTA, both panel
@@ -393,80 +393,14 @@ __global__ void dense_fill_kernel(const int32_t* __restrict__ rowptr, const int3
   }
 }
 
-__global__ void __launch_bounds__(256)
-chol_potrf_block_kernel(double* __restrict__ A, int64_t ld, int k0, int* status) {
-  __shared__ double s[kCB][kCB + 1];
-  __shared__ double s_inv;
-  const int tid = threadIdx.x;
-  for (int t = tid; t < kCB * kCB; t += 256) s[t / kCB][t % kCB] = A[(size_t)(k0 + t / kCB) * ld + k0 + t % kCB];
-  __syncthreads();
-  for (int j = 0; j < kCB; ++j) {
-    if (tid == 0) {
-      double d = s[j][j];
-      if (!(d > 0.0)) { *status = 1; d = 1.0; }
-      d = sqrt(d);
-      s[j][j] = d;
-      s_inv = 1.0 / d;
-    }
-    __syncthreads();
-    if (tid > j && tid < kCB) s[tid][j] *= s_inv;
-    __syncthreads();
-    const int m = kCB - 1 - j;                       // trailing (m x m) lower update
-    for (int t = tid; t < m * m; t += 256) {
-      const int i = j + 1 + t / m, c = j + 1 + t % m;
-      if (c <= i) s[i][c] -= s[i][j] * s[c][j];
-    }
-    __syncthreads();
-  }
-  for (int t = tid; t < kCB * kCB; t += 256) {
-    const int i = t / kCB, c = t % kCB;
-    if (c <= i) A[(size_t)(k0 + i) * ld + k0 + c] = s[i][c];
-  }
-}
-
-// The same 64x64 factorisation with one thread per ROW, the row in registers (fully unrolled, static
-// indexing) and one barrier per column: at step j every thread i >= j publishes its a_ij, all read the
-// pivot d = a_jj and the column, and update a_ik -= (a_ij / d) a_kj for j < k <= i — the scaling by
-// 1/sqrt(d) is applied to the stored column only, so no thread waits for the pivot's square root.
-// Two warps instead of eight and 64 barriers instead of 192: the ncu launch list of the coarse
-// inversion showed the shared-memory version at 64 us per panel, more than the trsm (19 us) and the
-// DMMA update (37 us) of the same panel together.
-__global__ void __launch_bounds__(kCB)
-chol_potrf_block_reg_kernel(double* __restrict__ A, int64_t ld, int k0, int* status) {
-  __shared__ double col[2][kCB];
-  const int i = threadIdx.x;
-  double a[kCB];
-  {
-    const double* row = A + (size_t)(k0 + i) * ld + k0;
-#pragma unroll
-    for (int c = 0; c < kCB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(row + c); a[c] = v.x; a[c + 1] = v.y; }
-  }
-#pragma unroll
-  for (int j = 0; j < kCB; ++j) {
-    double* cj = col[j & 1];
-    if (i >= j) cj[i] = a[j];
-    __syncthreads();
-    double d = cj[j];
-    if (!(d > 0.0)) { if (i == j) *status = 1; d = 1.0; }
-    const double inv2 = 1.0 / d;
-    const double sd = sqrt(d);
-    const double t = a[j] * inv2;
-#pragma unroll
-    for (int k = j + 1; k < kCB; ++k)
-      if (k <= i) a[k] -= t * cj[k];
-    a[j] = (i == j) ? sd : a[j] / sd;
-  }
-  double* row = A + (size_t)(k0 + i) * ld + k0;
-#pragma unroll
-  for (int c = 0; c < kCB; ++c)
-    if (c <= i) row[c] = a[c];
-}
-
-// Leaner form of the register-resident kernel (the default; FEMB_POTRF_REG=1 / 0 select the older ones): the ncu capture of the version above
-// shows it instruction-fetch bound (stall no_instruction 5.6 per issue, 11k instructions per warp).  Here
-// the update of row i runs unpredicated over k = j+1..63 (entries right of the diagonal are never
-// published nor stored, so updating them is harmless), the column is read with 16-byte shared loads,
-// and 1/d, 1/sqrt(d), sqrt(d) all come from one rsqrt — about a third of the instructions.
+// 64x64 diagonal block, one thread per ROW with the row in registers (fully unrolled, static indexing),
+// one barrier per column: at step j every thread i >= j publishes its a_ij, all read the pivot d = a_jj
+// and the column, and update a_ik -= (a_ij / d) a_kj.  The update of row i runs unpredicated over
+// k = j+1..63 (entries right of the diagonal are never published nor stored), the column is read with
+// 16-byte shared loads, and 1/d, 1/sqrt(d), sqrt(d) all come from one rsqrt.  History (ncu launch list of
+// the coarse inversion, profiles/r01_ncu_full_two_level_setup.txt): a shared-memory version with eight
+// warps and three barriers per column 64 us per panel; a predicated register version 9.5k SASS
+// instructions, instruction-fetch bound (stall no_instruction 5.6 per issue); this one 5.8k, no spills.
 __global__ void __launch_bounds__(kCB)
 chol_potrf_block_lean_kernel(double* __restrict__ A, int64_t ld, int k0, int* status) {
   __shared__ __align__(16) double col[2][kCB];
@@ -501,16 +435,8 @@ chol_potrf_block_lean_kernel(double* __restrict__ A, int64_t ld, int k0, int* st
     if (c <= i) row[c] = a[c];
 }
 
-static int potrf_variant() {      // FEMB_POTRF_REG: 0 = shared-memory version, 1 = register rows, 2 = lean register rows (default)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FEMB_POTRF_REG"); v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
-  return v;
-}
 static void launch_potrf_block(femb_handle* h, double* A, int64_t ld, int k0, int* status) {
-  const int v = potrf_variant();
-  if (v == 2) chol_potrf_block_lean_kernel<<<1, kCB, 0, h->stream>>>(A, ld, k0, status);
-  else if (v == 1) chol_potrf_block_reg_kernel<<<1, kCB, 0, h->stream>>>(A, ld, k0, status);
-  else chol_potrf_block_kernel<<<1, 256, 0, h->stream>>>(A, ld, k0, status);
+  chol_potrf_block_lean_kernel<<<1, kCB, 0, h->stream>>>(A, ld, k0, status);
 }
 
 // rows below the diagonal block: X L_kk^T = A_panel, one thread per row

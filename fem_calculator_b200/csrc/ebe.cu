@@ -281,7 +281,7 @@ bool ebe_selected(const femb_handle* h, int op) {
     if (e && (e[0] == 'b' || e[0] == 'B')) env = FEMB_OP_BSR;
     if (e && (e[0] == 'e' || e[0] == 'E')) env = FEMB_OP_EBE;
   }
-  if (env && op != FEMB_OP_EBE_FUSED) op = env;
+  if (env) op = env;
   if (op == FEMB_OP_BSR) return false;
   return ebe_available(h);
 }

@@ -1,5 +1,4 @@
-// Device pieces of the matrix-free frame operator shared by ebe.cu (operator kernels) and
-// fused_pcg.cu (one-kernel-per-iteration PCG): the stiffness part of the element record and the
+// Device pieces of the matrix-free frame operator (ebe.cu): the stiffness part of the element record and the
 // closed form of K_e[a][a] ua + K_e[a][1-a] uo (BeamSolver.py:386-387, 646-660).
 #pragma once
 

@@ -214,35 +214,6 @@ inline int vec_grid(const femb_handle* h, int64_t n, int threads) {
   return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
-// ---- programmatic dependent launch (PDL) -------------------------------------------------------
-// The Krylov loops are chains of short kernels (20-30 us) that each end in a grid-reduction tail.
-// Launched with the programmatic-stream-serialization attribute, the next kernel's CTAs are
-// scheduled while the previous kernel drains; pdl_wait() (griddepcontrol.wait) at the top of every
-// kernel blocks until the previous grid has completed and flushed its memory, so the data flow is
-// unchanged.  pdl_trigger() is called once a CTA's main loop is done.  Measured at 1M DOF
-// (profiles/r01_pcg_iteration_experiments.log): single-vector PCG 45.9 -> 44.7 us/iteration, but the three-kernel
-// lockstep iteration of the modal solve got 60 % SLOWER (early-resident CTAs of the next kernels
-// take SM slots from the running one), so it is opt-in: FEMB_PDL=1.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-inline bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("FEMB_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on != 0;
-}
-
-template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
 // Grid of a grid-stride kernel sized to what is actually co-resident: a kernel that needs more
 // registers than 65536 / (8 CTAs x threads) would otherwise run its "8 CTAs per SM" in two waves,
 // the second one mostly empty (measured: pcg_update_kernel, 56 registers -> 6 resident CTAs of 192

@@ -37,7 +37,6 @@ bsr_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   // skip_node != nullptr: block rows flagged there are left to a later launch (rows that read
   // ghost columns wait for the halo); node_list != nullptr: row g belongs to node_list[g / BS].
   static_assert(BS == 6 || BS == 3, "block size");
-  pdl_wait();
   if (DOT && flags[Flag::DONE]) return;
   if (DOT && p2p) {
     // fused peer-memory mode: the neighbours' update kernels stored the ghost entries of x straight
@@ -250,7 +249,6 @@ pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s,
                   double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
                   int64_t n, int parity, int first, int max_iter, double* partials, int pstride, double* scal,
                   int* flags) {
-  pdl_wait();
   if (flags[Flag::DONE]) return;
   const double delta = scal[Scal::PQ];
   const double gamma = scal[Scal::RZ0 + (parity ^ 1)];
@@ -319,7 +317,6 @@ pcg_update_kernel(const double* __restrict__ Dinv, const double* __restrict__ s,
       rz += rg * zg; rr += rg * rg;
     }
   }
-  pdl_trigger();
   double mine[2], tot[2];
   mine[0] = rz;
   mine[1] = rr;
@@ -454,10 +451,6 @@ int launch_spmv(femb_handle* h, const double* x, double* y, bool masked, double*
 // to scal_out[Scal::PQ]
 int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool masked, double* dot_partials,
                      double* scal_out, const uint8_t* skip_node, const int32_t* node_list, const void* p2p_dev) {
-  static int tma_variant = -1;
-  if (tma_variant < 0) { const char* e = getenv("FEMB_SPMV_TMA"); tma_variant = e ? atoi(e) : 0; }
-  if (tma_variant > 0 && h->bs == 6 && n == h->ndof && !skip_node && !node_list && !p2p_dev)
-    return launch_spmv_tma(h, tma_variant, x, y, masked, dot_partials, scal_out);
   // row-block distributed PCG on a frame: the matrix-free operator over the owned nodes (dist.cu passes
   // scal_out = red + DELTA, whose neighbours red[1], red[2] the peer-memory epilogue posts, and the
   // reduction's flags block)
@@ -480,7 +473,6 @@ int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool
     else if (masked) SPMV(3, true, false);
     else SPMV(3, false, false);
   }
-#undef SPMV
 #undef SPMV
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
@@ -650,7 +642,6 @@ static bool linked_enabled() {
 
 static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
   if (twolevel_applicable(h, o)) return pcg_twolevel(h, o, d_b, st);
-  if (fused_pcg_applicable(h, o)) return pcg_fused(h, o, d_b, st);
   if (h->bs == 6 && o.precond != FEMB_PRECOND_BLOCK_JACOBI && ebe_selected(h, o.op) && linked_enabled())
     return pcg_core_linked(h, o, d_b, st);
   const int64_t n = h->ndof;
@@ -698,7 +689,7 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
       if (timed) cudaEventRecord(e1, h->stream);
       if (rc) return rc;
       ++spmv_launches;
-#define UPD(BS, BJ) launch_pdl(pcg_update_kernel<BS, kRowThreads, BJ>, occ_grid(h, pcg_update_kernel<BS, kRowThreads, BJ>, BJ ? n : (n + 1) / 2, kRowThreads), kRowThreads, h->stream, h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, it == 0 ? 1 : 0, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
+#define UPD(BS, BJ) pcg_update_kernel<BS, kRowThreads, BJ><<<occ_grid(h, pcg_update_kernel<BS, kRowThreads, BJ>, BJ ? n : (n + 1) / 2, kRowThreads), kRowThreads, 0, h->stream>>>(h->Dinv.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, h->z.p, n, parity, it == 0 ? 1 : 0, o.max_iter, h->partials.p + pstride, pstride, h->scal.p, h->flags.p)
       if (h->bs == 6) { if (blockj) UPD(6, true); else UPD(6, false); }
       else { if (blockj) UPD(3, true); else UPD(3, false); }
 #undef UPD
@@ -863,7 +854,6 @@ mpcg_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  const double* __restrict__ vals, const uint8_t* __restrict__ free_mask,
                  const double* __restrict__ p, double* __restrict__ qv, int64_t n,
                  double* partials, int pstride, double* scal, int* flags) {
-  pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
   double dot[NB];
 #pragma unroll
@@ -913,7 +903,6 @@ __global__ void __launch_bounds__(THREADS)
 mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict__ p, const double* __restrict__ qv,
                       double* __restrict__ x, double* __restrict__ r, int64_t n, int max_iter,
                       double* partials, int pstride, double* scal, int* flags) {
-  pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
   double alpha[NB];
   bool bad = false;
@@ -938,7 +927,6 @@ mpcg_update_xr_kernel(const double* __restrict__ dinv, const double* __restrict_
 #pragma unroll
     for (int q = 0; q < NB; ++q) { mine[q] += rv[q] * d * rv[q]; mine[NB + q] += rv[q] * rv[q]; }
   }
-  pdl_trigger();
   double tot[2 * NB];
   if (grid_reduce<THREADS, 2 * NB>(mine, partials, pstride, flags + MFlag::TICKET1, tot)) {
     if (threadIdx.x == 0) {
@@ -966,7 +954,6 @@ template <int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 mpcg_update_p_kernel(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ p, int64_t n,
                      const double* scal, const int* flags) {
-  pdl_wait();
   if (flags[MFlag::ALLDONE]) return;
   double beta[NB];
 #pragma unroll
@@ -1260,9 +1247,9 @@ static int pcg_solve_multi_t(femb_handle* h, const femb_solve_opts& o, const dou
         mpcg_spmm_kernel<NB, kRowThreads><<<grid_mm, kRowThreads, 0, h->stream>>>(h->rowptr.p, h->colidx.p, h->Kvals.p, h->free_mask.p,
                                                                                    h->mp.p, h->mq.p, n, part0, pstride, h->mscal.p, h->mflags.p);
       }
-      launch_pdl(mpcg_update_xr_kernel<NB, kRowThreads>, grid_xr, kRowThreads, h->stream, h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n,
+      mpcg_update_xr_kernel<NB, kRowThreads><<<grid_xr, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->mp.p, h->mq.p, h->mx.p, h->mr.p, n,
                  max_iter, part1, pstride, h->mscal.p, h->mflags.p);
-      launch_pdl(mpcg_update_p_kernel<NB, kRowThreads>, gridv, kRowThreads, h->stream, h->Dinv.p, h->mr.p, h->mp.p, n, h->mscal.p, h->mflags.p);
+      mpcg_update_p_kernel<NB, kRowThreads><<<gridv, kRowThreads, 0, h->stream>>>(h->Dinv.p, h->mr.p, h->mp.p, n, h->mscal.p, h->mflags.p);
       h->launches += 3;
       ++spmm;
     }

@@ -46,7 +46,6 @@ struct TlDev {
   const double* xyz;
   const uint8_t* free_mask;
   const double* inv;        // (n_pad, n_pad)
-  const double* invp;       // packed lower 6x6 blocks of the inverse, block (I, J <= I) at (I (I + 1) / 2 + J) * 36
   double* rc;               // (n_pad)
   int n_agg, n_pad;
   double omega;             // weight of the Jacobi term: z = omega D^-1 r + P Kc^-1 P^T r
@@ -198,8 +197,6 @@ __device__ __forceinline__ void expand_pair(int part, double2 a, double* u) {
   for (int c = 0; c < 3; ++c) { u[2 * c] = (c == part) ? a.x : 0.0; u[2 * c + 1] = (c == part) ? a.y : 0.0; }
 }
 
-__device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // P^T r contribution of one node: translations take the force, rotations take rho x force + moment
 __device__ __forceinline__ void restrict_add(const double* r, double rx, double ry, double rz, double* acc) {
   acc[0] += r[0]; acc[1] += r[1]; acc[2] += r[2];
@@ -241,25 +238,11 @@ tl_init_kernel(const TlDev T, const double* __restrict__ b, double* __restrict__
 // update(it): consumes delta (operator) and gamma (coarse-z of the previous iteration / init) like
 // pcg_update_linked_kernel, then p = z + beta p, q = s + beta q, x += alpha p, r -= alpha q on the
 // aggregate's nodes, rc = P^T r, and publishes ||r||^2 into buffer (it + 1) & 1
-// PRE: all CTAs of these one-wave kernels run their phases together, so while every CTA adds up the
-// published partials (and, in tl_coarse_z, forms its coarse product) no vector traffic flows.  With PRE
-// every thread first issues prefetch.global.L2 for the lines of its items (no registers held — holding
-// the first item's operands in registers across the prologue spilled under the 56-register cap), so
-// HBM streams during the prologue and the loads after it hit the L2.
-template <bool PRE>
 __global__ void __launch_bounds__(kTlThreads, 3)
 tl_update_kernel(const TlDev T, const double* __restrict__ z, const double* __restrict__ s, double* __restrict__ p,
                  double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, const PcgLink L) {
   __shared__ double s_part[7 * kTlThreads / 32];
   if (L.flags[Flag::DONE]) return;
-  if (PRE) {
-    const int f0 = T.agg_ptr[blockIdx.x], c0 = T.agg_ptr[blockIdx.x + 1] - f0;
-    for (int w = threadIdx.x; w < 3 * c0; w += kTlThreads) {
-      const size_t off = (size_t)T.agg_nodes[f0 + w / 3] * 6 + 2 * (w % 3);
-      prefetch_l2(z + off); prefetch_l2(s + off); prefetch_l2(p + off);
-      prefetch_l2(q + off); prefetch_l2(x + off); prefetch_l2(r + off);
-    }
-  }
   const int rd = L.it & 1, wr = rd ^ 1;
   double tot[2] = {0.0, 0.0};
   {
@@ -312,55 +295,14 @@ tl_update_kernel(const TlDev T, const double* __restrict__ z, const double* __re
 
 // y_I = (Kc^-1 rc)[6I .. 6I+6), then z = D^-1 r + P y on the aggregate's nodes; publishes the (r, z)
 // partial into buffer wr.  The inverse is symmetric: rows are read, contiguously.
-// PACKED: the inverse is symmetric, so only its lower 6x6 blocks are stored (29 instead of 58 MB at 444
-// aggregates — the difference decides whether the iteration's working set fits the L2).  Thread
-// (jj, e = (a, b)) of the first 360 walks the blocks J = jj, jj + 10, ... of block row I: for J <= I it
-// reads entry (a, b) of block (I, J) and adds to y[a]; for J > I entry (a, b) of block (J, I) is
-// Kc^-1[6J + a][6I + b] and adds to y[b].  Two accumulators per thread, combined in a fixed order.
-template <bool PACKED, bool PRE>
 __global__ void __launch_bounds__(kTlThreads, 3)
 tl_coarse_z_kernel(const TlDev T, const double* __restrict__ dinv, const double* __restrict__ r,
                    double* __restrict__ z, int wr, const PcgLink L) {
   __shared__ double s_part[6 * kTlThreads / 32];
-  __shared__ double s_row[PACKED ? 360 : 1], s_col[PACKED ? 360 : 1], s_y[6];
   if (L.flags[Flag::DONE]) return;
   const int I = blockIdx.x;
-  if (PRE) {
-    const int f0 = T.agg_ptr[I], c0 = T.agg_ptr[I + 1] - f0;
-    for (int w = threadIdx.x; w < 3 * c0; w += kTlThreads) {
-      const size_t off = (size_t)T.agg_nodes[f0 + w / 3] * 6 + 2 * (w % 3);
-      prefetch_l2(r + off); prefetch_l2(dinv + off);
-    }
-  }
   double y[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if constexpr (PACKED) {
-    const int t = threadIdx.x;
-    if (t < 360) {
-      const int e = t % 36, a = e / 6, b = e % 6, jj = t / 36;
-      double acc_row = 0.0, acc_col = 0.0;
-      const double* rowI = T.invp + (size_t)(I * (I + 1) / 2) * 36 + e;
-#pragma unroll 4
-      for (int J = jj; J <= I; J += 10) acc_row += __ldg(rowI + (size_t)J * 36) * __ldcg(T.rc + 6 * J + b);
-      const int j0 = I + 1 + ((jj - (I + 1)) % 10 + 10) % 10;       // first J > I with J % 10 == jj
-#pragma unroll 4
-      for (int J = j0; J < T.n_agg; J += 10)
-        acc_col += __ldg(T.invp + ((size_t)(J * (J + 1) / 2) + I) * 36 + e) * __ldcg(T.rc + 6 * J + a);
-      s_row[t] = acc_row;
-      s_col[t] = acc_col;
-    }
-    __syncthreads();
-    if (t < 6) {
-      double sum = 0.0;
-      for (int g = 0; g < 10; ++g)
-        for (int c = 0; c < 6; ++c) sum += s_row[g * 36 + t * 6 + c];
-      for (int g = 0; g < 10; ++g)
-        for (int c = 0; c < 6; ++c) sum += s_col[g * 36 + c * 6 + t];
-      s_y[t] = sum;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < 6; ++m) y[m] = s_y[m];
-  } else {
+  {
     const double2* rc2 = reinterpret_cast<const double2*>(T.rc);
     const double* rows = T.inv + (size_t)6 * I * T.n_pad;
     const int n2 = T.n_pad >> 1;
@@ -408,32 +350,6 @@ tl_decide_kernel(const PcgLink L) {
   __shared__ double s_part[2 * 128 / 32];
   if (L.flags[Flag::DONE]) return;
   pcg_link_decide<128>(L, s_part);
-}
-
-// packed lower 6x6 blocks of the symmetric inverse (see tl_coarse_z_kernel<true>)
-__global__ void tl_pack_inverse_kernel(const double* __restrict__ inv, int64_t n_pad, int n_agg, double* __restrict__ invp) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)n_agg * (n_agg + 1) / 2 * 36;
-  if (idx >= total) return;
-  const int64_t blk = idx / 36;
-  const int e = (int)(idx % 36);
-  int I = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
-  while ((int64_t)(I + 1) * (I + 2) / 2 <= blk) ++I;
-  while ((int64_t)I * (I + 1) / 2 > blk) --I;
-  const int J = (int)(blk - (int64_t)I * (I + 1) / 2);
-  invp[idx] = inv[(size_t)(6 * I + e / 6) * n_pad + 6 * J + e % 6];
-}
-
-static bool tl_prefetch_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("FEMB_TL_PREFETCH"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on != 0;
-}
-
-static bool tl_packed_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("FEMB_TL_PACKED"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on != 0;
 }
 
 static int coarse_target_aggregates(const femb_handle* h) {
@@ -515,13 +431,6 @@ static int ensure_coarse_numeric(femb_handle* h) {
     fprintf(stderr, "[femb trace] two-level numeric setup: coarse dim %lld, Galerkin assembly %.3f ms, inversion %.3f ms\n",
             (long long)n, a, b);
   }
-  if (ok && tl_packed_enabled()) {
-    const int64_t total = (int64_t)n_agg * (n_agg + 1) / 2 * 36;
-    FEMB_CUDA(h, h->coarse_invp.ensure((size_t)total));
-    tl_pack_inverse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->coarse_inv.p, n_pad, n_agg, h->coarse_invp.p);
-    h->launches++;
-    FEMB_CUDA(h, cudaGetLastError());
-  }
   h->coarse_num_ok = ok;
   h->coarse_failed = !ok;
   return FEMB_OK;
@@ -531,8 +440,8 @@ constexpr int64_t kTlAutoNodes = 50000;   // FEMB_PRECOND_AUTO: below this the c
 
 bool twolevel_applicable(const femb_handle* h, const femb_solve_opts& o) {
   const bool want = o.precond == FEMB_PRECOND_TWO_LEVEL ||
-                    (o.precond == FEMB_PRECOND_AUTO && o.op != FEMB_OP_EBE_FUSED && h->n_nodes >= kTlAutoNodes);
-  return want && h->bs == 6 && ebe_selected(h, o.op == FEMB_OP_EBE_FUSED ? FEMB_OP_AUTO : o.op);
+                    (o.precond == FEMB_PRECOND_AUTO && h->n_nodes >= kTlAutoNodes);
+  return want && h->bs == 6 && ebe_selected(h, o.op);
 }
 
 int pcg_twolevel(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
@@ -562,13 +471,8 @@ int pcg_twolevel(femb_handle* h, const femb_solve_opts& o, const double* d_b, fe
   L.n_upd = n_agg; L.n_op = ebe_grid(h, 1, h->n_nodes); L.pstride = pstride;
   L.it = 0; L.max_iter = o.max_iter; L.rtol = o.rtol;
   tl_init_kernel<<<n_agg, kTlThreads, 0, h->stream>>>(T, d_b, h->x.p, h->r.p, h->p.p, h->q.p, L);
-  const bool packed = tl_packed_enabled() && h->coarse_invp.p != nullptr;
-  T.invp = h->coarse_invp.p;
-  const bool pre = tl_prefetch_enabled();
   auto coarse_z = [&](int wr_buf) {
-    if (packed) tl_coarse_z_kernel<true, false><<<n_agg, kTlThreads, 0, h->stream>>>(T, h->Dinv.p, h->r.p, h->z.p, wr_buf, L);
-    else if (pre) tl_coarse_z_kernel<false, true><<<n_agg, kTlThreads, 0, h->stream>>>(T, h->Dinv.p, h->r.p, h->z.p, wr_buf, L);
-    else tl_coarse_z_kernel<false, false><<<n_agg, kTlThreads, 0, h->stream>>>(T, h->Dinv.p, h->r.p, h->z.p, wr_buf, L);
+    tl_coarse_z_kernel<<<n_agg, kTlThreads, 0, h->stream>>>(T, h->Dinv.p, h->r.p, h->z.p, wr_buf, L);
   };
   coarse_z(0);
   h->launches += 2;
@@ -598,8 +502,7 @@ int pcg_twolevel(femb_handle* h, const femb_solve_opts& o, const double* d_b, fe
       if (timed) cudaEventRecord(e1, h->stream);
       if (rc) return rc;
       ++spmv_launches;
-      if (pre) tl_update_kernel<true><<<n_agg, kTlThreads, 0, h->stream>>>(T, h->z.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, L);
-      else tl_update_kernel<false><<<n_agg, kTlThreads, 0, h->stream>>>(T, h->z.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, L);
+      tl_update_kernel<<<n_agg, kTlThreads, 0, h->stream>>>(T, h->z.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, L);
       coarse_z((it & 1) ^ 1);
       if (timed) { cudaEventRecord(e2, h->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); }
       h->launches += 2;

@@ -71,10 +71,7 @@ enum { FEMB_PRECOND_NONE = 0, FEMB_PRECOND_JACOBI = 1, FEMB_PRECOND_BLOCK_JACOBI
  *        unique (no duplicate members, node degree <= 127), single GPU;
  *   AUTO EBE where it applies, else BSR.
  * K is assembled either way (Jacobi diagonal, reactions K u - f, CSR export).               */
-enum { FEMB_OP_AUTO = 0, FEMB_OP_BSR = 1, FEMB_OP_EBE = 2,
-       FEMB_OP_EBE_FUSED = 3 /* EBE with ONE kernel per CG iteration (csrc/fused_pcg.cu; scalar Jacobi,
-                                static solve only).  Correct and tested, but measured slower than the
-                                two-kernel iteration at 1M DOF (52 vs 45 us), hence opt-in.          */ };
+enum { FEMB_OP_AUTO = 0, FEMB_OP_BSR = 1, FEMB_OP_EBE = 2 };
 
 typedef struct {
   int32_t method;        /* FEMB_SOLVER_*                         default AUTO            */

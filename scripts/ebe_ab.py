@@ -17,7 +17,7 @@ for which, name in ((0, "bsr spmv"), (3, "ebe x1"), (4, "ebe x4")):
     ms, by = m.time_kernel(which, 5, 100)
     print(f"{name}: b2b {ms*1e3:.1f} us, {by/1e6:.1f} MB algorithmic -> {by/ms/1e6:.0f} GB/s")
 us = {}
-for op, name in ((L.OP_BSR, "bsr"), (L.OP_EBE_FUSED, "ebe-fused"), (L.OP_EBE, "ebe")):
+for op, name in ((L.OP_BSR, "bsr"), (L.OP_EBE, "ebe")):
     for rep in range(2):
         u, r, st = m.solve_static(method=L.SOLVER_PCG, rtol=1e-12, want_reactions=False, op=op)
     us[name] = u

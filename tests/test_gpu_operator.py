@@ -56,41 +56,39 @@ def test_pcg_with_either_operator_matches_oracle():
     _, free, _ = S.frame_bc(mesh, bc)
     uo, _ = S.solve_static(Ko, f, fixed, free, method="direct")
     its = {}
-    # OP_EBE: operator + update kernels; OP_EBE_FUSED: one kernel per iteration (fused_pcg.cu)
-    for op in (L.OP_BSR, L.OP_EBE, L.OP_EBE_FUSED):
+    for op in (L.OP_BSR, L.OP_EBE):
         u, r, st = m.solve_static(method=L.SOLVER_PCG, op=op)
-        assert st["op_used"] == min(op, L.OP_EBE) and st["converged"] == 1
+        assert st["op_used"] == op and st["converged"] == 1
         assert np.linalg.norm(u - uo) <= 1e-10 * np.linalg.norm(uo), (op, st)
         assert np.linalg.norm(r - (Ko @ uo - f)) <= 1e-9 * np.linalg.norm(f)
         u2, _, _ = m.solve_static(method=L.SOLVER_PCG, op=op)
         assert np.array_equal(u, u2)
         its[op] = st["iterations"]
-    for op in (L.OP_EBE, L.OP_EBE_FUSED):
-        assert abs(its[L.OP_BSR] - its[op]) <= max(5, its[L.OP_BSR] // 50)   # same Krylov trajectory up to rounding
+    assert abs(its[L.OP_BSR] - its[L.OP_EBE]) <= max(5, its[L.OP_BSR] // 50)   # same Krylov trajectory up to rounding
     # AUTO picks the matrix-free operator for a frame with unique members on one GPU
     _, _, st = m.solve_static(method=L.SOLVER_PCG)
     assert st["op_used"] == L.OP_EBE
     m.close()
 
 
-def test_fused_pcg_edge_cases():
+def test_linked_pcg_edge_cases():
     """Zero load (u = 0 without iterating), iteration cap, unpreconditioned run and a singular system
-    through the one-kernel-per-iteration PCG."""
+    through the linked-reduction PCG of the matrix-free operator."""
     mesh, bc, es, props, fixed, f, m = _setup(6, 5, 5, 0.05)
     m.set_bc(fixed, np.zeros_like(f))
-    u, r, st = m.solve_static(method=L.SOLVER_PCG, op=L.OP_EBE_FUSED)
+    u, r, st = m.solve_static(method=L.SOLVER_PCG, op=L.OP_EBE)
     assert st["converged"] == 1 and st["iterations"] == 0 and not u.any()
     m.set_bc(fixed, f)
     with pytest.raises(L.FembError) as ei:
-        m.solve_static(method=L.SOLVER_PCG, op=L.OP_EBE_FUSED, max_iter=7)
+        m.solve_static(method=L.SOLVER_PCG, op=L.OP_EBE, max_iter=7)
     assert ei.value.code == L.FEMB_ERR_NOT_CONVERGED and m.last_stats["iterations"] == 7
-    u0, _, st0 = m.solve_static(method=L.SOLVER_PCG, op=L.OP_EBE_FUSED, precond=L.PRECOND_NONE)
+    u0, _, st0 = m.solve_static(method=L.SOLVER_PCG, op=L.OP_EBE, precond=L.PRECOND_NONE)
     u1, _, st1 = m.solve_static(method=L.SOLVER_PCG, op=L.OP_BSR, precond=L.PRECOND_NONE)
     assert st0["converged"] == 1 and np.linalg.norm(u0 - u1) <= 1e-9 * np.linalg.norm(u1)
     assert abs(st0["iterations"] - st1["iterations"]) <= max(5, st1["iterations"] // 50)
     m.set_bc(np.zeros(0, dtype=np.int64), f)          # no supports: K_ff singular
     with pytest.raises(L.FembError):
-        m.solve_static(method=L.SOLVER_PCG, op=L.OP_EBE_FUSED, max_iter=3000)
+        m.solve_static(method=L.SOLVER_PCG, op=L.OP_EBE, max_iter=3000)
     m.close()
 
 
