@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("FEMB_LIB") or os.path.join(HERE, "libfemb200.so")   #
 FEMB_OK, FEMB_ERR_ARG, FEMB_ERR_CUDA, FEMB_ERR_NOT_CONVERGED, FEMB_ERR_SINGULAR, FEMB_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MAT_K, MAT_M = 0, 1
 SOLVER_AUTO, SOLVER_PCG, SOLVER_CHAIN, SOLVER_DENSE = 0, 1, 2, 3
-PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_TWO_LEVEL, PRECOND_AUTO = 0, 1, 2, 3, 4
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_TWO_LEVEL, PRECOND_AUTO, PRECOND_LINES = 0, 1, 2, 3, 4, 5
 OP_AUTO, OP_BSR, OP_EBE = 0, 1, 2
 
 
@@ -34,7 +34,7 @@ class EigOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("method_used", C.c_int32), ("iterations", C.c_int32), ("converged", C.c_int32),
                 ("spmv_launches", C.c_int32), ("kernel_launches", C.c_int32), ("spmv_timed", C.c_int32),
-                ("op_used", C.c_int32), ("coarse_dim", C.c_int32),
+                ("op_used", C.c_int32), ("coarse_dim", C.c_int32), ("precond_used", C.c_int32), ("reserved", C.c_int32),
                 ("rel_residual", C.c_double), ("device_ms", C.c_double), ("spmv_ms", C.c_double),
                 ("update_ms", C.c_double)]
 
@@ -92,6 +92,8 @@ SIGNATURES = {
     "femb_symbolic_lines": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_double, C.c_int32, C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int64), _P, _P, _P, _P]),
     "femb_symbolic_coarse": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, _P, C.POINTER(C.c_int64), _P, _P]),
+    "femb_symbolic_line_bundles": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, _P, _P, C.POINTER(C.c_int64),
+                                             C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
 }
 
 _lib = None

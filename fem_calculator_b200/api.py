@@ -322,3 +322,21 @@ def symbolic_lines(points, conn, cos_tol=0.94, min_nodes=3):
     if rc:
         raise L.FembError(rc, "femb_symbolic_lines")
     return line_ptr, line_nodes[:nn.value], line_dir[:nl.value], fam[:nl.value]
+
+
+def symbolic_line_bundles(points, conn, target_per_family=768):
+    """Host-only: symbolic phase of PRECOND_LINES (csrc/coarse.cpp build_line_symbolic) — needs no GPU.
+    Returns dict(node_bundle (3,N), node_pos (3,N), fam_off (4,), n_lines, n_entries, coverage)."""
+    lib = L.load()
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    cn = np.ascontiguousarray(conn, dtype=np.int64).reshape(-1, 2)
+    nb = np.full((3, len(pts)), -1, dtype=np.int32)
+    pos = np.full((3, len(pts)), -1, dtype=np.int32)
+    fam_off = np.zeros(4, dtype=np.int32)
+    nl, ne, cov = C.c_int64(), C.c_int64(), C.c_double()
+    rc = lib.femb_symbolic_line_bundles(len(pts), len(cn), L.ptr(cn), L.ptr(pts), int(target_per_family), L.ptr(nb),
+                                        L.ptr(pos), L.ptr(fam_off), C.byref(nl), C.byref(ne), C.byref(cov))
+    if rc:
+        raise L.FembError(rc, "femb_symbolic_line_bundles")
+    return {"node_bundle": nb, "node_pos": pos, "fam_off": fam_off, "n_lines": nl.value, "n_entries": ne.value,
+            "coverage": cov.value}

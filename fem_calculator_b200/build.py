@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfemb200.so")
-SOURCES = ["capi.cu", "assemble.cu", "solver.cu", "direct.cu", "post.cu", "modal.cu", "dist.cu", "ebe.cu", "twolevel.cu", "symbolic.cpp", "coarse.cpp"]
+SOURCES = ["capi.cu", "assemble.cu", "solver.cu", "direct.cu", "post.cu", "modal.cu", "dist.cu", "ebe.cu", "twolevel.cu", "lines.cu", "symbolic.cpp", "coarse.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-O3,-pthread", "--use_fast_math=false"]
 

@@ -194,6 +194,7 @@ static int ensure_symbolic(femb_handle* h) {
   FEMB_CUDA(h, upload(h->tile_ptr, S.tile_ptr, h->stream));
   h->pairs_dev_ok = false;
   h->coarse_sym_ok = h->coarse_num_ok = false;
+  h->line_sym_ok = h->line_num_ok = h->line_failed = false;
   if (S.pairs_ok && h->kind == Kind::Frame && h->n_sec < (1 << 24)) {
     // 16-byte pair records: everything the pair kernel would otherwise chase through
     // pair_code -> conn -> elem_sec is resolved here once
@@ -259,6 +260,7 @@ int femb_assemble(femb_handle* h) {
   h->have_solution = false;
   h->chain_factored = h->dense_factored = false;
   h->coarse_num_ok = h->coarse_failed = false;
+  h->line_num_ok = h->line_failed = false;
   return FEMB_OK;
 }
 
@@ -344,6 +346,7 @@ int femb_set_bc(femb_handle* h, int64_t n_fixed, const int64_t* fixed_dofs, cons
   h->have_solution = false;
   h->chain_factored = h->dense_factored = false;
   h->coarse_num_ok = h->coarse_failed = false;
+  h->line_num_ok = h->line_failed = false;
   return FEMB_OK;
 }
 

@@ -197,6 +197,117 @@ void build_member_lines(int64_t n_nodes, int64_t n_elem, const int32_t* conn, co
     if (!seen[e]) walk((int32_t)e, 0);       // closed ring
 }
 
+
+// Symbolic phase of the line preconditioner (lines.cu).  Why lines: after diagonal scaling the slow modes of a
+// frame are rows of collinear members moving along their own axis — such a motion costs only the bending
+// energy of the crossing members (12 EI / L^3) while the diagonal carries EA / L.  The preconditioner
+//     M^-1 = D^-1 + sum_lines Q_a (Q_a^T A Q_a)^-1 Q_a^T + sum_families P_f (P_f^T A P_f)^-1 P_f^T
+// solves the axial chain of every member line exactly (a tridiagonal system per line) and couples the lines
+// through one axial translation mode per BUNDLE of neighbouring lines (dense inverse per family, a few
+// hundred unknowns).  Here: member lines (build_member_lines) cut to kLnMaxLen nodes, families = classes of
+// node-disjoint lines (dominant direction component; a line that shares a node with an earlier line of its
+// class moves to another class or is dropped), bundles = recursive coordinate bisection of the line
+// midpoints into at most target_per_family groups per family.
+void build_line_symbolic(const Symbolic& S, const int32_t* conn, const double* xyz, int target_per_family, LineSym& L) {
+  L = LineSym();
+  const int64_t N = S.n_nodes;
+  std::vector<int32_t> lp, ln, lf;
+  std::vector<double> ld;
+  build_member_lines(N, S.n_elem, conn, xyz, 0.94, 3, lp, ln, ld, lf);
+  // cut long lines; a closed ring repeats its first node at the end: drop the repeat
+  struct Raw { int32_t lo, hi, fam; };
+  std::vector<Raw> raw;
+  for (size_t a = 0; a + 1 < lp.size(); ++a) {
+    int32_t lo = lp[a], hi = lp[a + 1];
+    if (hi - lo >= 2 && ln[lo] == ln[hi - 1]) --hi;
+    const int32_t len = hi - lo;
+    const int32_t pieces = (len + kLnMaxLen - 1) / kLnMaxLen;
+    for (int32_t q = 0; q < pieces; ++q) {
+      const int32_t a0 = lo + (int32_t)((int64_t)len * q / pieces), a1 = lo + (int32_t)((int64_t)len * (q + 1) / pieces);
+      if (a1 - a0 >= 2) raw.push_back({a0, a1, lf[a]});
+    }
+  }
+  // families: node-disjoint classes
+  std::vector<uint8_t> used((size_t)kLnMaxFam * N, 0);
+  std::vector<std::vector<int32_t>> fam_lines(kLnMaxFam);
+  for (size_t a = 0; a < raw.size(); ++a) {
+    int chosen = -1;
+    for (int t = 0; t < kLnMaxFam && chosen < 0; ++t) {
+      const int f = (raw[a].fam + t) % kLnMaxFam;
+      bool free_ = true;
+      for (int32_t k = raw[a].lo; k < raw[a].hi && free_; ++k) free_ = !used[(size_t)f * N + ln[k]];
+      if (free_) chosen = f;
+    }
+    if (chosen < 0) continue;
+    for (int32_t k = raw[a].lo; k < raw[a].hi; ++k) used[(size_t)chosen * N + ln[k]] = 1;
+    fam_lines[chosen].push_back((int32_t)a);
+  }
+  // bundles per family: RCB of the line midpoints
+  L.node_bundle.assign((size_t)kLnMaxFam * N, -1);
+  L.node_ent.assign((size_t)kLnMaxFam * N, -1);
+  L.line_ptr.assign(1, 0);
+  L.bundle_ptr.assign(1, 0);
+  int32_t coarse0 = 0;
+  for (int f = 0; f < kLnMaxFam; ++f) {
+    const std::vector<int32_t>& lines = fam_lines[f];
+    L.fam_off[f] = coarse0;
+    const int nl = (int)lines.size();
+    if (nl == 0) continue;
+    const int nb = std::max(1, std::min(nl, target_per_family));
+    std::vector<double> mid((size_t)nl * 3);
+    for (int q = 0; q < nl; ++q) {
+      const Raw& r = raw[lines[q]];
+      for (int c = 0; c < 3; ++c) mid[3 * (size_t)q + c] = 0.5 * (xyz[3 * (size_t)ln[r.lo] + c] + xyz[3 * (size_t)ln[r.hi - 1] + c]);
+    }
+    std::vector<int32_t> part;
+    build_aggregates(nl, mid.data(), nb, part);
+    std::vector<int32_t> order((size_t)nl);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return part[x] < part[y]; });
+    int32_t prev = -1;
+    for (int q = 0; q < nl; ++q) {
+      const int32_t pq = part[order[q]];
+      const Raw& r = raw[lines[order[q]]];
+      if (pq != prev) {                               // RCB parts are never empty for nb <= nl
+        if (prev >= 0) L.bundle_ptr.push_back((int32_t)L.line_bundle.size());
+        prev = pq;
+      }
+      const int32_t cidx = coarse0 + pq;
+      L.line_bundle.push_back(cidx);
+      for (int32_t k = r.lo; k < r.hi; ++k) {
+        const int32_t node = ln[k];
+        const int32_t e = (int32_t)L.ent_node.size();
+        L.ent_node.push_back(node);
+        L.ent_blk_diag.push_back(S.diag_blk[node]);
+        int32_t nxt = -1;
+        if (k + 1 < r.hi) {
+          const int32_t* b0 = S.colidx.data() + S.rowptr[node];
+          const int32_t* b1 = S.colidx.data() + S.rowptr[node + 1];
+          const int32_t* it = std::lower_bound(b0, b1, ln[k + 1]);
+          if (it != b1 && *it == ln[k + 1]) nxt = (int32_t)(it - S.colidx.data());
+        }
+        L.ent_blk_next.push_back(nxt);
+        L.node_bundle[(size_t)f * N + node] = cidx;
+        L.node_ent[(size_t)f * N + node] = e;
+      }
+      L.line_ptr.push_back((int32_t)L.ent_node.size());
+    }
+    L.bundle_ptr.push_back((int32_t)L.line_bundle.size());
+    coarse0 += nb;
+  }
+  L.fam_off[kLnMaxFam] = coarse0;
+  L.n_coarse = coarse0;
+  L.n_lines = (int32_t)L.line_bundle.size();
+  L.n_entries = (int64_t)L.ent_node.size();
+  int64_t covered = 0;
+  for (int64_t i = 0; i < N; ++i) {
+    bool any = false;
+    for (int f = 0; f < kLnMaxFam; ++f) any = any || L.node_ent[(size_t)f * N + i] >= 0;
+    covered += any;
+  }
+  L.coverage = N > 0 ? (double)covered / (double)N : 0.0;
+}
+
 }  // namespace femb
 
 extern "C" int femb_symbolic_aggregates(int64_t n_nodes, const double* xyz, int32_t n_parts,
@@ -258,5 +369,31 @@ extern "C" int femb_symbolic_lines(int64_t n_nodes, int64_t n_elem, const int64_
     if (!ld.empty()) std::memcpy(line_dir, ld.data(), ld.size() * sizeof(double));
     if (!lf.empty()) std::memcpy(line_family, lf.data(), lf.size() * sizeof(int32_t));
   }
+  return FEMB_OK;
+}
+
+// Host-only view of the symbolic phase of the line preconditioner (csrc/lines.cu) for the CPU test-suite.
+// node_bundle: (3, n_nodes) coarse index of the node's line in each family (-1: none); node_pos: (3, n_nodes)
+// position of the node inside the sorted entry list (entries of one line are consecutive, lines of one bundle
+// too); fam_off: (4) coarse index range per family.
+extern "C" int femb_symbolic_line_bundles(int64_t n_nodes, int64_t n_elem, const int64_t* conn, const double* xyz,
+                                          int32_t target_per_family, int32_t* node_bundle, int32_t* node_pos,
+                                          int32_t* fam_off, int64_t* n_lines, int64_t* n_entries, double* coverage) {
+  if (n_nodes < 0 || n_elem < 0 || (!conn && n_elem > 0) || (!xyz && n_nodes > 0) || target_per_family < 1) return FEMB_ERR_ARG;
+  std::vector<int32_t> c32((size_t)n_elem * 2);
+  for (size_t i = 0; i < c32.size(); ++i) {
+    if (conn[i] < 0 || conn[i] >= n_nodes) return FEMB_ERR_ARG;
+    c32[i] = (int32_t)conn[i];
+  }
+  femb::Symbolic S;
+  femb::build_symbolic(n_nodes, n_elem, 2, 6, c32.data(), 1 << 30, 1 << 30, S);
+  femb::LineSym L;
+  femb::build_line_symbolic(S, c32.data(), xyz, target_per_family, L);
+  if (node_bundle && !L.node_bundle.empty()) std::memcpy(node_bundle, L.node_bundle.data(), L.node_bundle.size() * sizeof(int32_t));
+  if (node_pos && !L.node_ent.empty()) std::memcpy(node_pos, L.node_ent.data(), L.node_ent.size() * sizeof(int32_t));
+  if (fam_off) std::memcpy(fam_off, L.fam_off, sizeof(L.fam_off));
+  if (n_lines) *n_lines = L.n_lines;
+  if (n_entries) *n_entries = L.n_entries;
+  if (coverage) *coverage = L.coverage;
   return FEMB_OK;
 }

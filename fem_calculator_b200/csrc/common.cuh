@@ -95,6 +95,27 @@ void build_member_lines(int64_t n_nodes, int64_t n_elem, const int32_t* conn, co
 void build_symbolic(int64_t n_nodes, int64_t n_elem, int nper, int bs, const int32_t* conn,
                     int tile_max_blocks, int tile_max_contrib, Symbolic& out);
 
+// Host-side symbolic part of the line preconditioner (coarse.cpp, lines.cu): member lines sorted by
+// (family, bundle), their node entries in order along the line, and the bundles (groups of
+// neighbouring lines of one family) whose axial translations span the coarse space.
+constexpr int kLnMaxFam = 3;       // families = classes of node-disjoint lines (dominant direction component)
+constexpr int kLnMaxLen = 128;     // entries per line (longer member lines are cut): 4 per lane of the line's warp
+struct LineSym {
+  int32_t n_lines = 0, n_coarse = 0;
+  int64_t n_entries = 0;
+  double coverage = 0.0;             // fraction of nodes that lie on at least one line
+  int32_t fam_off[kLnMaxFam + 1] = {0, 0, 0, 0};   // coarse index range of each family
+  std::vector<int32_t> line_ptr;     // (n_lines+1) entry ranges; lines sorted by (family, bundle)
+  std::vector<int32_t> line_bundle;  // (n_lines) coarse index (global over the families)
+  std::vector<int32_t> bundle_ptr;   // (n_coarse+1) line ranges of the bundles
+  std::vector<int32_t> ent_node;     // (n_entries)
+  std::vector<int32_t> ent_blk_diag; // (n_entries) block (i, i) of K
+  std::vector<int32_t> ent_blk_next; // (n_entries) block (i, next node of the line) or -1 at the line's end
+  std::vector<int32_t> node_bundle;  // (kLnMaxFam, n_nodes) coarse index of the node's line in family f, -1: none
+  std::vector<int32_t> node_ent;     // (kLnMaxFam, n_nodes) entry of the node in family f, -1: none
+};
+void build_line_symbolic(const Symbolic& S, const int32_t* conn, const double* xyz, int target_per_family, LineSym& out);
+
 enum class Kind { None, Frame, Tet10 };
 
 }  // namespace femb
@@ -173,6 +194,16 @@ struct femb_handle {
   femb::DevBuf<double> coarse_r;            // (4 * n_pad) restricted residual(s)
   femb::DevBuf<double> coarse_scratch;      // chunk partial sums of the Galerkin assembly
   int64_t coarse_scratch_per_agg = 0;
+
+  // line preconditioner (lines.cu): member lines, per-line tridiagonal factors, bundle coarse spaces
+  bool line_sym_ok = false;       // line tables on the device match the current topology
+  bool line_num_ok = false;       // factors and inverses match the current K and BC mask
+  bool line_failed = false;       // a bundle Galerkin matrix of the current K / BC could not be factored
+  femb::LineSym line_sym;         // host copy (the per-entry tables are dropped after the upload)
+  int32_t ln_fam_pad[femb::kLnMaxFam] = {0, 0, 0};
+  int64_t ln_inv_off[femb::kLnMaxFam] = {0, 0, 0};
+  femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle;
+  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_yb, ln_inv;
 
   // row-block distributed solve (dist.cu): this rank owns the first n_owned_nodes local nodes
   void* nccl_comm = nullptr;
@@ -276,6 +307,9 @@ int pcg_solve_rhs(femb_handle* h, const femb_solve_opts& o, const double* d_b, f
 bool twolevel_applicable(const femb_handle* h, const femb_solve_opts& o);
 int pcg_twolevel(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 int coarse_invert(femb_handle* h, double* aug, int64_t n_pad, double* inv, bool* ok);
+// line preconditioner (lines.cu)
+bool lines_applicable(femb_handle* h, const femb_solve_opts& o);
+int pcg_lines(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
                     int64_t ldx, femb_stats* st);
 int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda, double* phi, int32_t* n_found,

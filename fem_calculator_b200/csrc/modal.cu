@@ -239,7 +239,7 @@ static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const
   if (method == FEMB_SOLVER_DENSE) return dense_apply(h, B, X, nb, ws.n);
   // two-level preconditioner: one right-hand side at a time through the three-kernel iteration of
   // twolevel.cu (the coarse inverse is built once per K / BC and shared by every solve)
-  const bool two_level = twolevel_applicable(h, so);
+  const bool two_level = lines_applicable(h, so) || twolevel_applicable(h, so);
   if (h->bs == 6 && !two_level && !getenv("FEMB_MODAL_SINGLE_RHS")) {
     // all right-hand sides of the block advance in lockstep and share one matrix pass per iteration
     femb_stats s1;
@@ -262,6 +262,7 @@ static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const
     if (rc) return rc;
     st->op_used = s1.op_used;
     st->coarse_dim = s1.coarse_dim;
+    st->precond_used = s1.precond_used;
     st->iterations += s1.iterations;
     st->spmv_launches += s1.spmv_launches;
     FEMB_CUDA(h, cudaMemcpyAsync(X + (size_t)q * ws.n, h->x.p, ws.n * 8, cudaMemcpyDeviceToDevice, h->stream));
@@ -355,7 +356,7 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
   femb_solve_opts so;
   std::memset(&so, 0, sizeof(so));
   so.method = FEMB_SOLVER_PCG; so.max_iter = 200000; so.check_every = 50;
-  so.precond = (o.precond == FEMB_PRECOND_TWO_LEVEL || o.precond == FEMB_PRECOND_AUTO) ? o.precond : FEMB_PRECOND_JACOBI;
+  so.precond = (o.precond == FEMB_PRECOND_TWO_LEVEL || o.precond == FEMB_PRECOND_LINES || o.precond == FEMB_PRECOND_AUTO) ? o.precond : FEMB_PRECOND_JACOBI;
   // inner solves 1000x tighter than the wanted pencil residual: measured at 1M DOF, 20 modes, rtol 1e-8 —
   // inner 1e-10 stalls at a pencil residual of 7.7e-8, inner 1e-9 at 3.2e-6 (and both take longer)
   so.rtol = std::min(1e-11, o.rtol * 1e-3);

@@ -613,6 +613,7 @@ static int pcg_core_linked(femb_handle* h, const femb_solve_opts& o, const doubl
   if (st) {
     st->method_used = FEMB_SOLVER_PCG;
     st->op_used = FEMB_OP_EBE;
+    st->precond_used = (o.precond == FEMB_PRECOND_NONE) ? FEMB_PRECOND_NONE : FEMB_PRECOND_JACOBI;
     st->iterations = peek->flags[Flag::ITERS];
     st->converged = (done == 1);
     st->spmv_launches = spmv_launches;
@@ -641,6 +642,7 @@ static bool linked_enabled() {
 }
 
 static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
+  if (lines_applicable(h, o)) return pcg_lines(h, o, d_b, st);
   if (twolevel_applicable(h, o)) return pcg_twolevel(h, o, d_b, st);
   if (h->bs == 6 && o.precond != FEMB_PRECOND_BLOCK_JACOBI && ebe_selected(h, o.op) && linked_enabled())
     return pcg_core_linked(h, o, d_b, st);
@@ -709,6 +711,7 @@ static int pcg_core(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   if (st) {
     st->method_used = FEMB_SOLVER_PCG;
     st->op_used = ebe ? FEMB_OP_EBE : FEMB_OP_BSR;
+    st->precond_used = (o.precond == FEMB_PRECOND_NONE || o.precond == FEMB_PRECOND_BLOCK_JACOBI) ? o.precond : FEMB_PRECOND_JACOBI;
     st->iterations = peek->flags[Flag::ITERS];
     st->converged = (done == 1);
     st->spmv_launches = spmv_launches;
@@ -1272,6 +1275,7 @@ static int pcg_solve_multi_t(femb_handle* h, const femb_solve_opts& o, const dou
   if (st) {
     st->method_used = FEMB_SOLVER_PCG;
     st->op_used = ebe ? FEMB_OP_EBE : FEMB_OP_BSR;
+    st->precond_used = (o.precond == FEMB_PRECOND_NONE || o.precond == FEMB_PRECOND_BLOCK_JACOBI) ? o.precond : FEMB_PRECOND_JACOBI;
     st->iterations = peek->flags[MFlag::ITERS];
     st->spmv_launches = spmm;
     st->converged = conv ? 1 : 0;

@@ -520,6 +520,7 @@ int pcg_twolevel(femb_handle* h, const femb_solve_opts& o, const double* d_b, fe
     st->method_used = FEMB_SOLVER_PCG;
     st->op_used = FEMB_OP_EBE;
     st->coarse_dim = (int32_t)h->coarse_n;
+    st->precond_used = FEMB_PRECOND_TWO_LEVEL;
     st->iterations = peek->flags[Flag::ITERS];
     st->converged = (done == 1);
     st->spmv_launches = spmv_launches;

@@ -60,8 +60,17 @@ enum { FEMB_PRECOND_NONE = 0, FEMB_PRECOND_JACOBI = 1, FEMB_PRECOND_BLOCK_JACOBI
                                      than Jacobi at 1M DOF.  Where it does not apply (Tet10, BSR operator, the
                                      row-block distributed solve) the solve runs with JACOBI;
                                      femb_stats.coarse_dim tells which one ran.                              */,
-       FEMB_PRECOND_AUTO = 4      /* TWO_LEVEL where it applies and the mesh has >= 50,000 nodes (below that the
-                                     coarse setup costs more than it saves), else JACOBI                       */ };
+       FEMB_PRECOND_AUTO = 4      /* frames with >= 50,000 nodes and the matrix-free operator: LINES when at least half
+                                     of the nodes lie on member lines, else TWO_LEVEL; everything else JACOBI (below
+                                     50,000 nodes the coarse setup costs more than it saves)                     */,
+       FEMB_PRECOND_LINES = 5     /* Jacobi + exact solves along member lines + bundle coarse space (csrc/lines.cu): the
+                                     axial DOFs of every maximal chain of collinear members are solved exactly (one
+                                     tridiagonal system per line, factored per assembled K), and one axial translation
+                                     per bundle of neighbouring parallel lines spans a coarse space inverted explicitly
+                                     (DMMA Cholesky kernels):
+                                     M^-1 = D^-1 + sum_lines Q (Q^T K_ff Q)^-1 Q^T + sum_families P (P^T K_ff P)^-1 P^T.
+                                     Frames on one GPU with the matrix-free operator: 199 iterations instead of 1,324
+                                     (TWO_LEVEL) / 6,931 (JACOBI) at 1M DOF.  Falls back like TWO_LEVEL does.          */ };
 
 /* femb_solve_opts.op / femb_eig_opts.op: how the Krylov loops apply K_ff.
  *   BSR  the assembled block-CSR matrix (HBM-bound: 8 B per stored value and product);
@@ -94,7 +103,7 @@ typedef struct {
   double lambda_min;     /* keep eigenvalues > lambda_min (BeamSolver.py:448)  default 1e-6 */
   int32_t precond;       /* preconditioner of the inner PCG solves: FEMB_PRECOND_TWO_LEVEL (one right-hand side
                             at a time), FEMB_PRECOND_AUTO (as for the static solve), anything else = JACOBI
-                            (4-/2-vector lockstep PCG); ignored behind a factorisation                   */
+                            (4-/2-vector lockstep PCG); FEMB_PRECOND_LINES as TWO_LEVEL; ignored behind a factorisation                   */
   int32_t reserved;
 } femb_eig_opts;
 
@@ -106,7 +115,9 @@ typedef struct {
   int32_t kernel_launches;    /* all kernel launches of this library in this call          */
   int32_t spmv_timed;         /* SpMV launches bracketed by events (opts.profile); modal: restarts */
   int32_t op_used;            /* FEMB_OP_BSR or FEMB_OP_EBE for the Krylov loops of this call (0: none) */
-  int32_t coarse_dim;         /* dimension of the coarse space of FEMB_PRECOND_TWO_LEVEL (0: plain Jacobi ran) */
+  int32_t coarse_dim;         /* dimension of the coarse space of FEMB_PRECOND_TWO_LEVEL / LINES (0: plain Jacobi ran) */
+  int32_t precond_used;       /* FEMB_PRECOND_* the PCG of this call ran with (0 when no PCG ran)                 */
+  int32_t reserved;
   double rel_residual;        /* final ||r||/||b||                                         */
   double device_ms;           /* CUDA-event time of the whole call on the handle's stream  */
   double spmv_ms;             /* summed device time of the timed SpMV launches              */
@@ -295,6 +306,17 @@ int femb_symbolic_coarse(int64_t n_nodes, int64_t n_elem, const int64_t* conn, c
 int femb_symbolic_lines(int64_t n_nodes, int64_t n_elem, const int64_t* conn, const double* xyz,
                         double cos_tol, int32_t min_nodes, int64_t* n_lines, int64_t* n_line_nodes,
                         int32_t* line_ptr, int32_t* line_nodes, double* line_dir, int32_t* line_family);
+
+/* Host-only: symbolic phase of FEMB_PRECOND_LINES (csrc/lines.cu) — member lines (femb_symbolic_lines, cut to 128
+ * nodes) are split into three families of node-disjoint lines (dominant direction component) and the lines of
+ * a family are grouped into at most target_per_family bundles (recursive coordinate bisection of the line
+ * midpoints).  node_bundle: (3, n_nodes) coarse index of the node's line per family, -1 = none; node_pos:
+ * (3, n_nodes) index of the node in the sorted entry list (consecutive along a line, lines of a bundle
+ * consecutive); fam_off: (4) coarse index range per family; coverage: fraction of nodes on at least one line.
+ * Any output pointer may be NULL.                                                                          */
+int femb_symbolic_line_bundles(int64_t n_nodes, int64_t n_elem, const int64_t* conn, const double* xyz,
+                               int32_t target_per_family, int32_t* node_bundle, int32_t* node_pos,
+                               int32_t* fam_off, int64_t* n_lines, int64_t* n_entries, double* coverage);
 
 #ifdef __cplusplus
 }
