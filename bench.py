@@ -1,26 +1,27 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the FEM hot path on B200 (contract in the task prompt).
 
-Metric (BASELINE.json): DOF/s of the static solve at ~1M DOF.  One "step" = one pass of the
-hot path over the synthetic BASELINE config-3 frame (56x56x54 lattice, 169,344 nodes,
-1,016,064 DOF, 498,848 elements, box/C/L sections, 5 % seeded node jitter):
-    fused element+assembly  ->  BC mask / RHS  ->  Jacobi-PCG to ||r||/||b|| <= 1e-12 with the
-    matrix-free (element-by-element) frame operator  ->  reaction recovery K u - f (assembled K).
-`value`  : free DOFs / step, device-timed (CUDA events on the library's stream), mesh and
-           loads resident in HBM.  Every step re-assembles the 359 MB matrix (> 126 MB L2), which
-           evicts the solver's working set between steps (no extra flush needed).
-`e2e`    : the same metric through the reference-shaped entry point
-           (compat.BeamAnalysisB200.run_simulation: host numpy arrays in, u / reactions /
-           stresses out, symbolic analysis + all H2D/D2H inside the timed region).
-`roofline`: the dominant kernel (the operator kernel of the PCG), CUDA-event-timed inside the
-           timed steps (every 8th launch, events from a pre-created pool), against
-           MEASURED_PEAKS.json; `roofline_bsr_spmv`: the assembled-matrix SpMV the same solve would
-           use without the matrix-free operator (one extra solve after the timed region);
-           `modal` (N=1): device ms of the 20-mode modal solve of the same frame; `assembly`: the
-           fused element+assembly kernel (elements/s).
-N > 1 (torchrun): independent load cases of the same frame, one per GPU (weak scaling, no
-data-path collective; north_star: "independent load cases ... dealt out one batch per GPU").
-`--impl reference`: the CPU oracle port of the reference path on the host cores.
+Metric (BASELINE.json): DOF/s of the static solve at ~1M DOF; ms per 20-mode modal at 1M DOF; elements assembled/s.
+
+N = 1.  One "step" = one pass of the hot path over the synthetic BASELINE configs[2] frame (56x56x54 lattice,
+169,344 nodes, 1,016,064 DOF, 498,848 elements, box/C/L sections, 5 % seeded node jitter):
+    fused element+assembly -> BC mask / RHS -> line-preconditioned PCG to ||r||/||b|| <= 1e-12 with the matrix-free
+    frame operator (its numeric setup — line factors, bundle Galerkin matrices, inverses — rebuilt every step)
+    -> reaction recovery K u - f (assembled K).
+  value     free DOFs / step, device-timed (CUDA events on the library's stream), mesh and loads resident in HBM.
+  e2e       the same metric through the reference-shaped entry point (compat.BeamAnalysisB200.run_simulation: host
+            numpy arrays in, u / reactions / stresses out, all H2D/D2H inside the timed region).
+  roofline  the operator kernel of the PCG (largest single kernel of the step), CUDA-event-timed inside the timed
+            steps (every 8th launch), against MEASURED_PEAKS.json; `fp64` next to it: FP64 instructions issued
+            against the FMA issue ceiling measured in this run (the kernel is issue/latency bound, not byte bound).
+  parity    the 40x40x38 lattice (364,800 DOF, production preconditioner configuration) solved by the GPU path and by
+            the CPU oracle in this run: relative errors of u and of the reactions.
+  cpu_baseline  the oracle's complete solve of that 40x40x38 lattice on all host cores (measured, not extrapolated).
+  modal / assembly / c4_batch / tet10: the other configurations of BASELINE.json with their own CPU timings.
+N > 1 (torchrun).  BASELINE configs[4]: ONE 110^3 frame (7,986,000 DOF) split by node slabs across the N GPUs
+  (row-block PCG, NVLink halo + scalar exchange fused into the kernels), strong scaling; every line also carries the
+  single-GPU solve of the same frame (rank 0, same run) and the config-4 batch sharded across the N GPUs.
+`--impl reference`: the CPU oracle's complete solve of the FULL 1M-DOF workload on all host cores (one measured step).
 """
 from __future__ import annotations
 
@@ -39,11 +40,14 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 LATTICE = (56, 56, 54)
+LATTICE_C5 = (110, 110, 110)
+SLICE = (40, 40, 38)          # parity + bounded CPU baseline
+MODAL_SLICE = (16, 16, 14)    # CPU modal baseline (SuperLU shift-invert: 3-D lattices fill in fast)
 JITTER = 0.05
 RTOL = 1e-12
-SAMPLE_LATTICE = (40, 40, 38)
-SAMPLE_ITERS = 400
 FALLBACK_HBM_GBS = 6650.0
+C4_MODELS, C4_ELEMS = 8192, 2000
+TET10_BOX = (64, 16, 64)      # 393,216 Tet10
 
 
 def peaks():
@@ -71,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -119,87 +123,192 @@ def build_case(load_scale=1.0, lattice=LATTICE):
     return mesh, sec, bc, es, props, fixed, f
 
 
-def cpu_baseline_sample(full_n_elem, full_n_free, full_iterations):
-    """Oracle port on a bounded sample, scaled to the full workload (oracle/cpu_baseline.py)."""
-    from oracle import cpu_baseline as CB
-    mesh, sec, bc, es, props, fixed, f = build_case(lattice=SAMPLE_LATTICE)
-    from fem_calculator_b200 import meshgen
-    s = CB.lattice_static_sample(mesh, es, props, bc, meshgen.E_STEEL, meshgen.NU_STEEL, cg_iters=SAMPLE_ITERS)
-    dofs, t_full = CB.scaled_static_dof_per_s(s, full_n_elem, full_n_free, full_iterations)
-    return dofs, t_full, s
+def workload_text(lat=LATTICE):
+    n = lat[0] * lat[1] * lat[2]
+    ne = (lat[0] - 1) * lat[1] * lat[2] + lat[0] * (lat[1] - 1) * lat[2] + lat[0] * lat[1] * (lat[2] - 1)
+    which = "configs[2]" if lat == LATTICE else ("configs[4]" if lat == LATTICE_C5 else "slice")
+    return (f"BASELINE {which}: synthetic gmsh-like 3D space frame, {lat[0]}x{lat[1]}x{lat[2]} lattice, {n:,} nodes / "
+            f"{6 * n:,} DOF ({6 * (n - lat[0] * lat[1]):,} free), {ne:,} Timoshenko elements, box/C/L sections, 5 % node "
+            f"jitter, base fixed, loads on all top nodes; static solve K u = F (PCG rtol 1e-12) with reaction recovery")
 
 
-def sample_text(s, iters):
-    return (f"oracle/ref_sparse port: {SAMPLE_LATTICE[0]}x{SAMPLE_LATTICE[1]}x{SAMPLE_LATTICE[2]} lattice slice "
-            f"({s['n_elem']} elements, {s['n_free']} free DOF): numpy element formation + scipy COO->CSR "
-            f"({s['t_assemble']:.2f} s) + {SAMPLE_ITERS} Jacobi-PCG iterations ({s['t_per_iter']*1e3:.2f} ms each); "
-            f"scaled linearly in elements to 498,848 elements and to the {iters} iterations the same "
-            f"Jacobi-PCG needs at full size for rtol 1e-12; scipy's sparse mat-vec and the numpy vector updates that "
-            f"make up >97 % of this time are single-threaded (cores = 1)")
+def config_dict(parallel="1 GPU", lat=LATTICE, step=None):
+    return {"workload": workload_text(lat),
+            "step": step or ("fused element+assembly -> BC -> line-preconditioned PCG (matrix-free operator; Jacobi + exact "
+                             "tridiagonal solves along member lines + bundle coarse space, factors / Galerkin matrices / "
+                             "inverses rebuilt every step) -> reactions"),
+            "l2": "every step re-assembles the 359 MB K (> 126 MB L2), evicting the PCG working set between steps",
+            "parallelism": parallel}
 
 
-JACOBI_ITERS_FULL = 6931  # Jacobi-PCG iterations at full size, rtol 1e-12 (profiles/r01_*, measured on B200)
-
-
+# ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
+    """The CPU oracle's complete solve of the full workload, all host cores, ONE measured step (no warm-up: a step is
+    2-5 minutes of CPU work; `steps` in the JSON is what ran)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_nodes = LATTICE[0] * LATTICE[1] * LATTICE[2]
-    n_free = 6 * (n_nodes - LATTICE[0] * LATTICE[1])
-    n_elem = (LATTICE[0] - 1) * LATTICE[1] * LATTICE[2] + LATTICE[0] * (LATTICE[1] - 1) * LATTICE[2] + \
-        LATTICE[0] * LATTICE[1] * (LATTICE[2] - 1)
-    vals, s = [], None
-    for i in range(args.warmup + args.steps):
-        dofs, t_full, s = cpu_baseline_sample(n_elem, n_free, JACOBI_ITERS_FULL)
-        if i >= args.warmup:
-            vals.append((dofs, t_full))
-    v = statistics.mean(x[0] for x in vals)
-    t = statistics.mean(x[1] for x in vals)
+    from fem_calculator_b200 import meshgen
+    from oracle import cpu_baseline as CB
+    mesh, sec, bc, es, props, fixed, f = build_case()
+    s = CB.lattice_static_solve(mesh, es, props, bc, meshgen.E_STEEL, meshgen.NU_STEEL, rtol=RTOL)
+    v = s["n_free"] / s["t_total"]
+    sample = (f"FULL workload, one complete solve: numpy element formation + scipy COO->CSR {s['t_assemble']:.1f} s, BC partition "
+              f"{s['t_bc']:.1f} s, Jacobi-CG (oracle/cg_omp.c, OpenMP) {s['iterations']} iterations to rtol 1e-12 in {s['t_cg']:.1f} s, "
+              f"reactions {s['t_reactions']:.2f} s; {s['threads']} threads of {os.cpu_count()} host CPUs")
     out = {"impl": "reference", "metric": "static_solve_dof_per_s", "value": v, "unit": "DOF/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": config_dict(),
-           "cpu_baseline": {"value": v, "unit": "DOF/s", "cores": 1, "kind": "port", "sample": sample_text(s, JACOBI_ITERS_FULL)},
+           "n_gpus": args.gpus, "steps": 1, "warmup": 0, "requested_steps": args.steps, "requested_warmup": args.warmup,
+           "ms_per_step": s["t_total"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "extrapolated": False,
+           "config": config_dict("host CPU", step="numpy element formation -> scipy COO->CSR assembly -> BC partition -> "
+                                 "Jacobi-preconditioned CG to rtol 1e-12 (all host cores) -> reactions K u - f"),
+           "cpu_baseline": {"value": v, "unit": "DOF/s", "cores": s["threads"], "kind": "port", "sample": sample,
+                            "host_cpus": os.cpu_count(), "iterations": s["iterations"], "rel_residual": s["rel_residual"]},
            "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
-def config_dict(parallel="1 GPU"):
-    return {"workload": "BASELINE configs[2]: synthetic gmsh-like 3D space frame, 56x56x54 lattice, 169,344 nodes / "
-                        "1,016,064 DOF (997,248 free), 498,848 Timoshenko elements, box/C/L sections, base fixed, "
-                        "loads on all top nodes; static solve K u = F (PCG rtol 1e-12) with reaction recovery",
-            "step": "fused element+assembly -> BC -> two-level PCG (matrix-free operator; Jacobi + rigid-body coarse space, "
-                    "Galerkin matrix and its inverse rebuilt every step) -> reactions",
-            "l2": "every step re-assembles the 359 MB K (> 126 MB L2), evicting the CG working set (~80 MB) between steps",
-            "parallelism": parallel}
+# ------------------------------------------------------------------------------------------ GPU legs
+def leg_parity_and_cpu(local):
+    """40x40x38 lattice: GPU solve (AUTO = production preconditioner configuration) vs the oracle's CPU solve."""
+    from fem_calculator_b200 import _lib as L, meshgen
+    from fem_calculator_b200.api import FrameModel
+    from oracle import cpu_baseline as CB
+    E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+    mesh, sec, bc, es, props, fixed, f = build_case(lattice=SLICE)
+    m = FrameModel(local)
+    m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)))
+    m.assemble()
+    m.set_bc(fixed, f)
+    u, r, st = m.solve_static(method=L.SOLVER_PCG, rtol=1e-13)
+    m.assemble()
+    _, _, st2 = m.solve_static(method=L.SOLVER_PCG, rtol=RTOL, want_u=False, want_reactions=False)
+    m.close()
+    s = CB.lattice_static_solve(mesh, es, props, bc, E, nu, rtol=1e-13)
+    parity = {"lattice": list(SLICE), "n_dof": int(s["n_dof"]), "gpu_precond_used": int(st["precond_used"]),
+              "gpu_coarse_dim": int(st["coarse_dim"]), "gpu_iterations": int(st["iterations"]),
+              "rel_err_u": float(np.linalg.norm(u - s["u"]) / np.linalg.norm(s["u"])),
+              "rel_err_reactions": float(np.linalg.norm((r - s["reactions"])[s["fixed"]]) / np.linalg.norm(s["f"])),
+              "tolerance_u": 1e-10, "tolerance_reactions": 1e-9,
+              "oracle": "oracle/ref_sparse.py assembly + oracle/cg_omp.c Jacobi-CG to 1e-13 (CPU, this run)"}
+    v = s["n_free"] / s["t_total"]
+    cpu = {"value": v, "unit": "DOF/s", "cores": s["threads"], "kind": "port", "host_cpus": os.cpu_count(),
+           "sample": (f"complete solve of a {SLICE[0]}x{SLICE[1]}x{SLICE[2]} lattice of the same family ({s['n_elem']} elements, "
+                      f"{s['n_free']} free DOF): element formation + COO->CSR {s['t_assemble']:.2f} s, BC {s['t_bc']:.2f} s, Jacobi-CG "
+                      f"{s['iterations']} iterations to 1e-13 in {s['t_cg']:.1f} s on {s['threads']} threads (measured, not scaled; the "
+                      f"full 1M-DOF CPU solve is the --impl reference arm)"),
+           "seconds": s["t_total"], "elements_per_s_assembly": s["n_elem"] / s["t_assemble"],
+           "gpu_same_problem": {"ms_step": st2["device_ms"], "dof_per_s": s["n_free"] / (st2["device_ms"] * 1e-3)}}
+    return parity, cpu
 
 
-def run_gpu(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+def leg_modal_cpu():
+    from fem_calculator_b200 import meshgen
+    from oracle import cpu_baseline as CB
+    mesh, sec, bc, es, props, fixed, f = build_case(lattice=MODAL_SLICE)
+    s = CB.lattice_modal_solve(mesh, es, props, bc, meshgen.E_STEEL, meshgen.NU_STEEL, k=20)
+    return {"seconds": s["seconds"], "kind": "port", "cores": 1,
+            "sample": (f"{MODAL_SLICE[0]}x{MODAL_SLICE[1]}x{MODAL_SLICE[2]} lattice ({s['n_free']} free DOF), 20 modes: assembly "
+                       f"{s['t_assemble']:.2f} s + scipy eigsh(sigma=0) with SuperLU {s['t_eig']:.1f} s (measured at this size; SuperLU's "
+                       f"fill on 3-D lattices makes the 1M-DOF pencil infeasible on the host)")}
+
+
+def c4_inputs(n_models, n_el):
+    from fem_calculator_b200 import meshgen
+    from fem_calculator_b200.sections import calculate_section_properties as csp
+    p = meshgen.batch_cantilever_params(C4_MODELS)
+    mesh, _, _ = meshgen.cantilever_case(n_el, 4.0)
+    nn = n_el + 1
+    props = np.array([csp("rectangular section", {"d": d, "b": b}) for d, b in zip(p["d"], p["b"])])
+    fixed_mask = np.zeros(6 * nn, dtype=np.uint8)
+    fixed_mask[:6] = 1
+    f = np.zeros((C4_MODELS, 6 * nn))
+    f[:, 6 * (nn - 1) + 1] = p["tip_fy"]
+    f[:, 8::6] += p["nodal_fz"][:, None]          # uniform nodal F_z on the free nodes
+    return mesh.points, props[:n_models], fixed_mask, f[:n_models]
+
+
+def leg_c4(local, rank=0, world=1, cpu=True):
+    """BASELINE configs[3]: 8,192 independent 2,000-element cantilevers, dealt out 8192/N per GPU (no collective)."""
+    from fem_calculator_b200 import meshgen
+    from fem_calculator_b200.api import FrameModel
+    E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+    xyz, props, fixed_mask, f = c4_inputs(C4_MODELS, C4_ELEMS)
+    per = C4_MODELS // world
+    lo = rank * per
+    props_l, f_l = np.ascontiguousarray(props[lo:lo + per]), np.ascontiguousarray(f[lo:lo + per])
+    m = FrameModel(local)
+    u, st = m.batch_solve(xyz, props_l, E, E / (2 * (1 + nu)), fixed_mask, f_l)          # warm-up (allocations)
+    dev, wall = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        u, st = m.batch_solve(xyz, props_l, E, E / (2 * (1 + nu)), fixed_mask, f_l)
+        wall.append(time.perf_counter() - t0)
+        dev.append(st["device_ms"])
+    m.close()
+    out = {"models_this_gpu": per, "elements_per_model": C4_ELEMS, "free_dof_this_gpu": per * 6 * C4_ELEMS,
+           "device_ms": min(dev), "e2e_ms": min(wall) * 1e3,
+           "h2d_bytes": int(f_l.nbytes + props_l.nbytes), "d2h_bytes": int(u.nbytes)}
+    if cpu and rank == 0:
+        from oracle import cpu_baseline as CB
+        n_cpu = 16
+        uc, t = CB.chain_batch_solve(xyz, props_l, E, E / (2 * (1 + nu)), fixed_mask, f_l, n_cpu)
+        err = max(np.linalg.norm(u[k] - uc[k]) / np.linalg.norm(uc[k]) for k in range(n_cpu))
+        out["cpu_baseline"] = {"value": n_cpu * 6 * C4_ELEMS / t, "unit": "DOF/s", "cores": 1, "kind": "port",
+                               "sample": f"first {n_cpu} models: ref_sparse chain assembly + scipy solveh_banded, {t:.2f} s"}
+        out["parity_rel_err_u_max"] = float(err)
+    return out
+
+
+def leg_tet10(local, peak):
+    """ReactionSolver path (Tet10): fused element+assembly, 3x3-BSR SpMV, PCG solve on a 393k-tet box; CPU assembly beside it."""
+    from fem_calculator_b200 import _lib as L, meshgen
+    from fem_calculator_b200.api import Tet10Model
+    from oracle import cpu_baseline as CB
+    mesh, fd, xd = meshgen.tet10_box_case(*TET10_BOX)
+    conn = mesh.cells_dict["tetra10"]
+    m = Tet10Model(local)
+    m.set_mesh(mesh.points, conn, 2e11, 0.3)
+    m.assemble()
+    asm_ms, asm_bytes = m.time_kernel(1, 2, 10)
+    pts = mesh.points
+    ndof = 3 * len(pts)
+    fixed = np.flatnonzero(np.repeat(pts[:, 0] <= pts[:, 0].min() + 1e-12, 3)).astype(np.int64)
+    f = np.zeros(ndof)
+    f[3 * np.flatnonzero(pts[:, 0] >= pts[:, 0].max() - 1e-12) + 1] = -10.0
+    m.set_bc(fixed, f)
+    spmv_ms, spmv_bytes = m.time_kernel(0, 3, 20)
+    _, _, st = m.solve_static(method=L.SOLVER_PCG, rtol=1e-10, want_u=False, want_reactions=False)
+    m.close()
+    small, _, _ = meshgen.tet10_box_case(16, 4, 16)           # 6,144 tets for the CPU port
+    _, t_cpu = CB.tet10_assembly(small.points, small.cells_dict["tetra10"], 2e11, 0.3)
+    return {"tets": int(len(conn)), "n_dof": int(ndof),
+            "assembly": {"ms": asm_ms, "tets_per_s": len(conn) / (asm_ms * 1e-3), "achieved_gbs": asm_bytes / (asm_ms * 1e-3) / 1e9,
+                         "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": asm_bytes,
+                         "kernels": "tet10_point_records_kernel + tet10_block_gather_kernel"},
+            "spmv": {"kernel": "bsr_spmv_kernel<3,...> back to back", "ms": spmv_ms, "achieved_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
+                     "frac": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": spmv_bytes},
+            "pcg": {"iterations": st["iterations"], "ms": st["device_ms"], "rtol": 1e-10,
+                    "dof_per_s": (ndof - len(fixed)) / (st["device_ms"] * 1e-3)},
+            "cpu_baseline": {"value": len(small.cells_dict["tetra10"]) / t_cpu, "unit": "tets/s (assembly)", "cores": 1, "kind": "port",
+                             "sample": f"oracle/ref_sparse.tet10_assemble (vectorised port of ReactionSolver.py:115-152) on "
+                                       f"{len(small.cells_dict['tetra10'])} tets: {t_cpu:.2f} s"}}
+
+
+def run_single(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from fem_calculator_b200 import _lib as L
     from fem_calculator_b200 import compat, meshgen
     from fem_calculator_b200.api import FrameModel
-    from fem_calculator_b200.sections import calculate_section_properties as csp
 
     E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
-    mesh, sec, bc, es, props, fixed, f = build_case(load_scale=1.0 + 0.25 * rank)  # one load case per GPU
+    mesh, sec, bc, es, props, fixed, f = build_case()
     n_free = len(f) - len(fixed)
     n_elem = len(es)
     m = FrameModel(local)
     m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)))
     m.assemble()
     m.set_bc(fixed, f)
-    # FEMB_PRECOND_AUTO: at this size the two-level preconditioner (Jacobi + rigid-body coarse space, csrc/twolevel.cu);
-    # its numeric setup (Galerkin matrix + explicit inverse) is rebuilt inside every timed step, after the assembly
     solve_kw = dict(method=L.SOLVER_PCG, precond=L.PRECOND_AUTO, rtol=RTOL, want_u=False, want_reactions=False)
 
     def step(profile=0):
@@ -207,217 +316,258 @@ def run_gpu(args):
         _, _, st = m.solve_static(profile=profile, **solve_kw)
         return st
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step(profile=8)                       # same code path as the timed steps (fills the event pool)
-
-    def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
-
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
     m.timer_start()
     stats = [step(profile=8) for _ in range(args.steps)]
     total_ms = m.timer_stop()
     clocks = sampler.stop()
-    barrier()
-    if dist is not None:
-        import torch
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * n_free / (ms_per_step / 1e3)
+    value = n_free / (ms_per_step / 1e3)
     launches = sum(s["kernel_launches"] for s in stats) + args.steps  # + one assembly launch per step
-    iters = stats[-1]["iterations"]
+    last = stats[-1]
+    iters = last["iterations"]
     n_timed = max(1, sum(s["spmv_timed"] for s in stats))
-    spmv_ms = sum(s["spmv_ms"] for s in stats) / n_timed
-    update_ms = sum(s["update_ms"] for s in stats) / n_timed
-    spmv_share = spmv_ms * sum(s["spmv_launches"] for s in stats) / total_ms if world == 1 else None
+    op_ms = sum(s["spmv_ms"] for s in stats) / n_timed
+    rest_ms = sum(s["update_ms"] for s in stats) / n_timed
+    op_share = op_ms * sum(s["spmv_launches"] for s in stats) / total_ms
 
-    coarse_dim = int(stats[-1].get("coarse_dim", 0))
-    if coarse_dim:
-        n_pad = (coarse_dim + 63) // 64 * 64
-        upd_bytes = 13 * 8 * len(f) + 8 * n_pad * n_pad + 2 * (24 + 4) * len(mesh.points)
-    else:
-        upd_bytes = 12 * 8 * len(f)
-    # per-kernel roofline numbers (algorithmic bytes: DESIGN.md §kernels)
     peak, peak_src = peaks()
-    ebe = stats[-1].get("op_used") == L.OP_EBE
     _, spmv_bytes = m.time_kernel(0, 1, 1)
     asm_ms, asm_bytes = m.time_kernel(1, 3, 20)
     spmv_b2b_ms, _ = m.time_kernel(0, 3, 50)
-    op_bytes = spmv_bytes
-    op_b2b_ms = spmv_b2b_ms
-    if ebe:
-        op_b2b_ms, op_bytes = m.time_kernel(3, 3, 50)
+    op_b2b_ms, op_bytes = m.time_kernel(3, 3, 50)
+    dfma_ms, dfma_count = m.time_kernel(10, 2, 5)
+    dfma_peak = dfma_count / (dfma_ms * 1e-3)                 # FP64 FMA instructions (lane-level) per second, measured
+    n_pairs = 2 * n_elem
+    fp64_instr = 135.0 * n_pairs                               # ~135 FP64 instructions per (node, element end) pair
 
     def _traffic(name):
         tp = os.path.join(ROOT, "profiles", name)
-        if os.path.exists(tp):
-            try:
-                return json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                return None
-        return None
+        try:
+            return json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
 
-    achieved = op_bytes / (spmv_ms * 1e-3) / 1e9
-    if ebe:
-        roofline = {"kernel": "frame_ebe_node_kernel<1,1,2,masked,dot,128,4> — matrix-free frame operator y = K_ff x "
-                              "(inside PCG, every 8th launch timed)",
-                    "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "bytes_per_launch": op_bytes, "ms_per_launch": spmv_ms,
-                    "share_of_step": spmv_share, "traffic": _traffic("ncu_ebe_traffic.json"),
-                    "note": "algorithmic bytes are the kernel's own compulsory traffic (16 B/pair + node records + "
-                            "coordinates + x + y + mask = 40 MB), 9x fewer than the 359 MB the assembled SpMV streams for "
-                            "the same product; the kernel is FP64-issue / gather-latency bound, not HBM bound (ncu: FP64 "
-                            "pipe 34-41 %, DRAM 13 % of peak) — see roofline_bsr_spmv for the HBM-bound form of the product",
-                    "equivalent_bsr_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9}
-    else:
-        roofline = {"kernel": "bsr_spmv_kernel<6,masked,dot,192,2> (inside PCG, every 8th launch timed)", "bound": "hbm",
-                    "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                    "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "share_of_step": spmv_share,
-                    "traffic": _traffic("ncu_spmv_traffic.json")}
+    achieved = op_bytes / (op_ms * 1e-3) / 1e9
+    roofline = {"kernel": "frame_ebe_node_kernel<1,1,2,masked,dot,linked,128,4> — matrix-free frame operator y = K_ff x "
+                          "(inside the PCG, every 8th launch timed)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "bytes_per_launch": op_bytes, "ms_per_launch": op_ms, "share_of_step": op_share,
+                "traffic": _traffic("ncu_ebe_traffic.json"),
+                "fp64": {"what": "the bound that applies: FP64 instruction issue + gather latency, not bytes",
+                         "fp64_instructions_per_launch": fp64_instr, "achieved_ginstr_per_s": fp64_instr / (op_ms * 1e-3) / 1e9,
+                         "peak_gfma_per_s_measured": dfma_peak / 1e9, "frac": fp64_instr / (op_ms * 1e-3) / dfma_peak,
+                         "peak_source": "femb_time_kernel(10): 8 independent DFMA chains per thread, this run"},
+                "note": "algorithmic bytes = the kernel's own compulsory traffic (16 B/pair + node records + coordinates + x + y + mask), "
+                        "9x fewer than the 359 MB the assembled SpMV streams for the same product — see roofline_bsr_spmv for the "
+                        "HBM-bound form of the product",
+                "equivalent_bsr_gbs": spmv_bytes / (op_ms * 1e-3) / 1e9}
+    lines = last.get("precond_used") == L.PRECOND_LINES
     extra = {
-        "pcg": {"iterations": iters, "ms_per_iteration": stats[-1]["device_ms"] / max(1, iters),
-                "rel_residual": stats[-1]["rel_residual"],
-                "precond": "two-level (Jacobi + 6 rigid-body modes per aggregate)" if coarse_dim else "jacobi",
-                "coarse_dim": coarse_dim,
-                "form": "Chronopoulos-Gear, 3 kernels/iteration (operator, update + restriction, coarse solve + prolongation)"
-                        if coarse_dim else "Chronopoulos-Gear, 2 kernels/iteration",
-                "update_kernel_ms": update_ms, "update_kernel_gbs": upd_bytes / (update_ms * 1e-3) / 1e9 if update_ms else None},
+        "pcg": {"iterations": iters, "ms_per_iteration": last["device_ms"] / max(1, iters), "rel_residual": last["rel_residual"],
+                "precond": ("lines: Jacobi + tridiagonal solves along member lines + bundle coarse space" if lines else
+                            f"precond {last.get('precond_used')}"),
+                "coarse_dim": int(last.get("coarse_dim", 0)),
+                "form": "Chronopoulos-Gear, 5 kernels/iteration (operator, update, line solves, coarse products, prolongation), "
+                        "linked reductions, no float atomics",
+                "operator_ms": op_ms, "rest_of_iteration_ms": rest_ms, "operator": "matrix-free (EBE)"},
         "assembly": {"kernel": "frame_assemble_pairs_persistent_kernel (fused element+assembly)", "ms": asm_ms,
                      "elements_per_s": n_elem / (asm_ms * 1e-3), "achieved_gbs": asm_bytes / (asm_ms * 1e-3) / 1e9,
-                     "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": asm_bytes},
+                     "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": asm_bytes,
+                     "timing": "20 back-to-back launches (the 336 MB of K written per launch exceed the 126 MB L2)"},
         "spmv_back_to_back": {"ms": spmv_b2b_ms, "achieved_gbs": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9,
                               "frac": spmv_bytes / (spmv_b2b_ms * 1e-3) / 1e9 / peak},
         "operator_back_to_back_ms": op_b2b_ms,
     }
-    if coarse_dim:
-        extra["pcg"]["update_kernel_note"] = ("tl_update_kernel + tl_coarse_z_kernel together (two launches): 10 + 3 vector "
-                                              "passes, the n_pad^2 coarse inverse, coordinates and node lists")
-    extra["pcg"]["operator"] = "matrix-free (EBE)" if ebe else "assembled BSR"
-    extra["pcg"]["update_kernel_frac"] = (extra["pcg"]["update_kernel_gbs"] / peak) if extra["pcg"]["update_kernel_gbs"] else None
-    if coarse_dim and world == 1:
-        # the same step with the plain Jacobi preconditioner, outside the timed region (what the coarse space buys)
-        jkw = dict(solve_kw, precond=L.PRECOND_JACOBI)
-        m.solve_static(**jkw)
-        _, _, jst = m.solve_static(profile=8, **jkw)
-        extra["jacobi_pcg"] = {"iterations": jst["iterations"], "pcg_ms": jst["device_ms"],
-                               "ms_per_iteration": jst["device_ms"] / max(1, jst["iterations"]),
-                               "operator_ms": jst["spmv_ms"] / max(1, jst["spmv_timed"]),
-                               "update_ms": jst["update_ms"] / max(1, jst["spmv_timed"]),
-                               "dof_per_s_pcg_only": n_free / (jst["device_ms"] * 1e-3)}
-        _, _, tst = m.solve_static(**solve_kw)      # coarse inverse kept: the solve alone
-        extra["pcg"]["solve_only_ms"] = tst["device_ms"]
-        extra["pcg"]["coarse_setup_ms"] = stats[-1]["device_ms"] - tst["device_ms"]
-    if ebe and world == 1:
-        # the HBM-bound form of the same product: one solve with the assembled BSR operator, outside the timed region
-        _, _, bst = m.solve_static(profile=8, op=L.OP_BSR, **dict(solve_kw, precond=L.PRECOND_JACOBI))
-        nb_t = max(1, bst["spmv_timed"])
-        b_ms = bst["spmv_ms"] / nb_t
-        b_ach = spmv_bytes / (b_ms * 1e-3) / 1e9
-        extra["roofline_bsr_spmv"] = {"kernel": "bsr_spmv_kernel<6,masked,dot,192,2> (inside a PCG with op = BSR, every 8th launch timed)",
-                                      "bound": "hbm", "achieved": b_ach, "peak": peak, "unit": "GB/s", "frac": b_ach / peak,
-                                      "bytes_per_launch": spmv_bytes, "ms_per_launch": b_ms,
-                                      "traffic": _traffic("ncu_spmv_traffic.json"),
-                                      "pcg_ms": bst["device_ms"], "pcg_iterations": bst["iterations"],
-                                      "dof_per_s_pcg_only": n_free / (bst["device_ms"] * 1e-3)}
-    if world == 1 and not args.no_modal:
+    # what the preconditioner buys: the same solve with the solve alone (setup kept), rigid-body two-level, Jacobi
+    _, _, tst = m.solve_static(**solve_kw)
+    extra["pcg"]["solve_only_ms"] = tst["device_ms"]
+    extra["pcg"]["precond_setup_ms"] = last["device_ms"] - tst["device_ms"]
+    for nm, pc in (("rigid_body_two_level_pcg", L.PRECOND_TWO_LEVEL), ("jacobi_pcg", L.PRECOND_JACOBI)):
+        kw = dict(solve_kw, precond=pc)
+        m.solve_static(**kw)
+        _, _, jst = m.solve_static(profile=8, **kw)
+        extra[nm] = {"iterations": jst["iterations"], "pcg_ms": jst["device_ms"],
+                     "ms_per_iteration": jst["device_ms"] / max(1, jst["iterations"]),
+                     "dof_per_s_pcg_only": n_free / (jst["device_ms"] * 1e-3)}
+    # the HBM-bound form of the same product: one solve with the assembled BSR operator, outside the timed region
+    _, _, bst = m.solve_static(profile=8, op=L.OP_BSR, **dict(solve_kw, precond=L.PRECOND_JACOBI))
+    b_ms = bst["spmv_ms"] / max(1, bst["spmv_timed"])
+    b_ach = spmv_bytes / (b_ms * 1e-3) / 1e9
+    extra["roofline_bsr_spmv"] = {"kernel": "bsr_spmv_kernel<6,masked,dot,192,2> (inside a PCG with op = BSR, every 8th launch timed)",
+                                  "bound": "hbm", "achieved": b_ach, "peak": peak, "unit": "GB/s", "frac": b_ach / peak,
+                                  "bytes_per_launch": spmv_bytes, "ms_per_launch": b_ms, "traffic": _traffic("ncu_spmv_traffic.json"),
+                                  "pcg_ms": bst["device_ms"], "pcg_iterations": bst["iterations"]}
+    if not args.no_modal:
         # second headline metric: ms per 20-mode modal solve at 1M DOF (device time of femb_modal)
-        two_level_modal = os.environ.get("FEMB_BENCH_MODAL_PRECOND", "two_level") != "jacobi"
-        lam, _, mst = m.modal(k=20, rtol=1e-8, precond=L.PRECOND_TWO_LEVEL if two_level_modal else L.PRECOND_JACOBI)
+        lam, _, mst = m.modal(k=20, rtol=1e-8, precond=L.PRECOND_AUTO)
         extra["modal"] = {"metric": "ms_per_20_mode_modal", "ms": mst["device_ms"], "modes": int(len(lam)),
-                          "pcg_iterations": mst["iterations"], "matrix_passes": mst["spmv_launches"],
+                          "pcg_iterations": mst["iterations"], "operator_passes": mst["spmv_launches"],
+                          "us_per_pcg_iteration": mst["device_ms"] / max(1, mst["iterations"]) * 1e3,
                           "rel_residual": mst["rel_residual"], "omega_min_rad_s": float(np.sqrt(lam[0])),
-                          "omega_max_rad_s": float(np.sqrt(lam[-1])),
-                          "operator": "matrix-free (EBE)" if mst.get("op_used") == L.OP_EBE else "assembled BSR SpMM",
-                          "coarse_dim": int(mst.get("coarse_dim", 0)),
-                          "method": ("block shift-invert Krylov (block 2), two-level PCG as K^-1, one right-hand side at a time"
-                                     if mst.get("coarse_dim") else
-                                     "block shift-invert Krylov (block 2), 2-RHS lockstep Jacobi-PCG as K^-1")}
+                          "omega_max_rad_s": float(np.sqrt(lam[-1])), "coarse_dim": int(mst.get("coarse_dim", 0)),
+                          "method": "block shift-invert Krylov (block 2), line-preconditioned PCG as K^-1 (factors built once), "
+                                    "full re-orthogonalisation, thick restart"}
+        if not args.no_cpu_baseline:
+            extra["modal"]["cpu_baseline"] = leg_modal_cpu()
     m.close()
 
-    if world > 1 and not args.no_rowblock:
-        # strong-scaling companion (not the headline): the SAME frame split by node slabs across the N
-        # GPUs, distributed PCG with peer-memory (NVLink) halo + scalar exchange fused into its kernels
-        import torch
-        from fem_calculator_b200.api import DistFrameModel
-        mesh0, sec0, bc0, es0, props0, fixed0, f0 = build_case(load_scale=1.0)
-        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            t = torch.tensor(list(DistFrameModel.unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-
-        def _gather(obj):
-            out = [None] * world
-            dist.all_gather_object(out, obj)
-            return out
-
-        d = DistFrameModel(local)
-        d.setup(mesh0.points, mesh0.cells_dict["line"], es0, props0, E, E / (2 * (1 + nu)), fixed0, f0, rank, world,
-                bytes(t.cpu().numpy().tolist()), all_gather=_gather)
-        d.solve_static_dist(precond=L.PRECOND_JACOBI, rtol=RTOL, want_u=False, want_reactions=False)   # warm-up
-        barrier()
-        _, _, dst = d.solve_static_dist(precond=L.PRECOND_JACOBI, rtol=RTOL, want_u=False, want_reactions=False)
-        tt = torch.tensor([dst["device_ms"]], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        extra["rowblock"] = {"what": "one 1,016,064-DOF frame, node-slab partition over the N GPUs (strong scaling), PCG solve only",
-                             "iterations": dst["iterations"], "ms": float(tt.item()),
-                             "us_per_iteration": float(tt.item()) / max(1, dst["iterations"]) * 1e3,
-                             "dof_per_s": (len(f0) - len(fixed0)) / (float(tt.item()) * 1e-3),
-                             "exchange": "peer memory (CUDA IPC over NVLink), fused into SpMV/update" if d.p2p else "NCCL"}
-        d.close()
-
     # end-to-end through the reference-shaped entry point, host buffers in / out
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     w = compat.BeamAnalysisB200(mesh, sec, bc, E, nu, device=local)
     tc = time.perf_counter()
     w.run_simulation(k_modes=0, solver=L.SOLVER_PCG, rtol=RTOL)  # warm-up (context, allocator, symbolic analysis)
     e2e_first_call_s = time.perf_counter() - tc
     L.io_bytes(reset=True)
-    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         w.run_simulation(k_modes=0, solver=L.SOLVER_PCG, rtol=RTOL)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    barrier()
     h2d, d2h = L.io_bytes()
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": world * n_free / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": h2d // e2e_steps,
+    w.close()
+    e2e = {"value": n_free / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": h2d // e2e_steps,
            "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
            "first_call_ms": e2e_first_call_s * 1e3,
-           "api": "fem_calculator_b200.compat.BeamAnalysisB200.run_simulation (BeamSolver.py:345 signature), "
-                  "timed with the host clock around the call; every call takes coordinates, connectivity, sections, "
-                  "BCs and loads as host numpy arrays, copies coordinates / section data / loads / BCs to the device and "
-                  "returns u / reactions / stresses to the host; the connectivity is compared with the previous call's and "
-                  "the symbolic analysis (block pattern, pair records, 62 MB of device tables) is rebuilt and re-uploaded only "
-                  "when it changed — first_call_ms is a call that builds it"}
+           "api": "fem_calculator_b200.compat.BeamAnalysisB200.run_simulation (BeamSolver.py:345 signature), timed with the host "
+                  "clock around the call; every call takes coordinates, connectivity, sections, BCs and loads as host numpy "
+                  "arrays, copies them to the device and returns u / reactions / stresses to the host; the symbolic analysis "
+                  "(block pattern, pair records, line tables) is rebuilt only when the connectivity changed — first_call_ms is a "
+                  "call that builds it"}
 
-    out = {"metric": "static_solve_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps,
-           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": config_dict("1 GPU" if world == 1 else f"{world} independent load cases, one per GPU (no collective)"),
+    out = {"metric": "static_solve_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(),
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
     out.update(extra)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # Jacobi-PCG iteration count at full size comes from this very run (same algorithm, same rtol)
-        # the CPU port runs the Jacobi-PCG (oracle/cpu_baseline.py): scale with ITS iteration count at full size
-        cpu_iters = extra.get("jacobi_pcg", {}).get("iterations", iters if not coarse_dim else JACOBI_ITERS_FULL)
-        dofs, t_full, s = cpu_baseline_sample(n_elem, n_free, cpu_iters)
-        out["cpu_baseline"] = {"value": dofs, "unit": "DOF/s", "cores": 1, "kind": "port",
-                               "sample": sample_text(s, cpu_iters), "est_seconds_full": t_full}
+    if not args.no_extra:
+        out["c4_batch"] = leg_c4(local, cpu=not args.no_cpu_baseline)
+        c4 = out["c4_batch"]
+        c4["dof_per_s_device"] = c4["free_dof_this_gpu"] / (c4["device_ms"] * 1e-3)
+        c4["dof_per_s_e2e"] = c4["free_dof_this_gpu"] / (c4["e2e_ms"] * 1e-3)
+        out["tet10"] = leg_tet10(local, peak)
+    if not args.no_cpu_baseline:
+        out["parity"], out["cpu_baseline"] = leg_parity_and_cpu(local)
+    print(json.dumps(out), flush=True)
+
+
+def run_multi(args):
+    """N > 1: BASELINE configs[4] (110^3 frame) row-block over the N GPUs, strong scaling."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from fem_calculator_b200 import _lib as L
+    from fem_calculator_b200 import meshgen
+    from fem_calculator_b200.api import DistFrameModel, FrameModel
+
+    E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+    lat = tuple(int(v) for v in os.environ.get("FEMB_BENCH_MULTI_LATTICE", "x".join(map(str, LATTICE_C5))).split("x"))
+    mesh, sec, bc, es, props, fixed, f = build_case(lattice=lat)
+    n_free = len(f) - len(fixed)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # the same frame on ONE GPU (rank 0, this run): the denominator of the strong-scaling efficiency
+    single = None
+    if rank == 0 and not args.no_single:
+        m = FrameModel(local)
+        m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)))
+        m.assemble()
+        m.set_bc(fixed, f)
+        kw = dict(method=L.SOLVER_PCG, precond=L.PRECOND_AUTO, rtol=RTOL, want_u=False, want_reactions=False)
+        m.solve_static(**kw)
+        m.assemble()
+        m.timer_start()
+        m.assemble()
+        _, _, st = m.solve_static(**kw)
+        ms = m.timer_stop()
+        single = {"ms_per_step": ms, "value": n_free / (ms * 1e-3), "iterations": st["iterations"],
+                  "precond_used": st["precond_used"], "coarse_dim": st["coarse_dim"]}
+        m.close()
+    barrier()
+
+    t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        t = torch.tensor(list(DistFrameModel.unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+
+    def _gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    d = DistFrameModel(local)
+    d.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world,
+            bytes(t.cpu().numpy().tolist()), all_gather=_gather)
+    kwd = dict(precond=L.PRECOND_AUTO, rtol=RTOL, want_u=False, want_reactions=False)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        d.assemble()
+        d.solve_static_dist(**kwd)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    d.timer_start()
+    stats = []
+    for _ in range(args.steps):
+        d.assemble()                                   # local rows only ("owner computes")
+        _, _, st = d.solve_static_dist(**kwd)
+        stats.append(st)
+    total_ms = d.timer_stop()
+    clocks = sampler.stop()
+    barrier()
+    total_ms = maxr(total_ms)
+    ms_per_step = total_ms / args.steps
+    last = stats[-1]
+    launches = sum(s["kernel_launches"] for s in stats) + args.steps
+    # e2e: host arrays of the rank's partition in, owned u / reactions out
+    L.io_bytes(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    d.set_bc_local()                                   # re-upload loads / BC of the partition (H2D)
+    d.assemble()
+    u_own, r_own, _ = d.solve_static_dist(precond=L.PRECOND_AUTO, rtol=RTOL)
+    torch.cuda.synchronize()
+    e2e_s = maxr(time.perf_counter() - t0)
+    h2d, d2h = L.io_bytes()
+    exch = "peer memory (CUDA IPC over NVLink), fused into the kernels" if d.p2p else "NCCL"
+    d.close()
+    out = {"metric": "static_solve_dof_per_s", "value": n_free / (ms_per_step * 1e-3), "unit": "DOF/s", "n_gpus": world,
+           "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(f"one frame, contiguous node slabs over {world} GPUs (row-block PCG; halo of the search direction and "
+                                 f"the reduction scalars / coarse residuals exchanged through {exch})", lat=lat),
+           "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": n_free / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": e2e_s * 1e3, "api": "api.DistFrameModel: per-rank partition loads / BC from host numpy, assemble, "
+                   "distributed solve, owned u and reactions back to the host (bytes are this rank's)"},
+           "pcg": {"iterations": last["iterations"], "precond_used": last.get("precond_used"), "coarse_dim": last.get("coarse_dim"),
+                   "us_per_iteration": last["device_ms"] / max(1, last["iterations"]) * 1e3, "rel_residual": last["rel_residual"]},
+           "single_gpu_same_workload": single}
+    if not args.no_extra:
+        c4 = leg_c4(local, rank, world, cpu=False)
+        dev = maxr(c4["device_ms"])
+        wall = maxr(c4["e2e_ms"])
+        out["c4_batch"] = {"what": f"BASELINE configs[3]: 8,192 x 2,000-element cantilevers, {C4_MODELS // world} models per GPU, no collective",
+                           "device_ms_max_over_ranks": dev, "e2e_ms_max_over_ranks": wall,
+                           "dof_per_s_device": C4_MODELS * 6 * C4_ELEMS / (dev * 1e-3), "dof_per_s_e2e": C4_MODELS * 6 * C4_ELEMS / (wall * 1e-3)}
     if rank == 0:
         print(json.dumps(out), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    dist.destroy_process_group()
 
 
 def main():
@@ -426,14 +576,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-rowblock", action="store_true", help="N>1: skip the row-block (strong-scaling) companion solve")
-    ap.add_argument("--no-modal", action="store_true", help="skip the 20-mode modal measurement (N=1 only, ~45 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle legs (parity, cpu_baseline)")
+    ap.add_argument("--no-modal", action="store_true", help="skip the 20-mode modal measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-4 batch and Tet10 objects")
+    ap.add_argument("--no-single", action="store_true", help="N>1: skip the single-GPU solve of the same frame on rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_multi(args)
     else:
-        run_gpu(args)
+        run_single(args)
 
 
 if __name__ == "__main__":

@@ -521,6 +521,24 @@ __global__ void stream_read_kernel(const double2* __restrict__ a, size_t n2, dou
   if (acc == 1.2345e300) *sink = acc;   // never true: keeps the loads alive
 }
 
+// FP64 issue ceiling: 8 independent DFMA chains per thread, 4096 steps; the denominator for kernels that are bound
+// by FP64 instruction issue rather than bytes (the matrix-free operator, ebe.cu)
+__global__ void __launch_bounds__(256)
+dfma_peak_kernel(double* sink, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = a * (double)(threadIdx.x + k);
+#pragma unroll 1
+  for (int it = 0; it < 4096; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc += v[k];
+  if (acc == 1.2345e300) *sink = acc;   // never true: keeps the chains alive
+}
+
 static void launch_stream_read(femb_handle* h, const double* a, size_t n2, double* sink) {
   stream_read_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(a), n2, sink);
 }
@@ -602,6 +620,21 @@ int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, doubl
     float t9 = 0.f;
     FEMB_CUDA(h, cudaEventElapsedTime(&t9, h->ev0, h->ev1));
     *ms = (double)t9 / reps;
+    return FEMB_OK;
+  } else if (which == 10) {
+    // FP64 FMA issue peak; *bytes receives the number of FP64 FMA instructions (per thread-lane) of one launch
+    const int grid = h->num_sms * 8;
+    *bytes = (double)grid * 256.0 * 8.0 * 4096.0;
+    DevBuf<double> sink;
+    FEMB_CUDA(h, sink.alloc(1));
+    for (int i = 0; i < warm; ++i) dfma_peak_kernel<<<grid, 256, 0, h->stream>>>(sink.p, 0.999999, 1e-9);
+    FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps; ++i) dfma_peak_kernel<<<grid, 256, 0, h->stream>>>(sink.p, 0.999999, 1e-9);
+    FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    float t10 = 0.f;
+    FEMB_CUDA(h, cudaEventElapsedTime(&t10, h->ev0, h->ev1));
+    *ms = (double)t10 / reps;
     return FEMB_OK;
   } else {
     return fail(h, FEMB_ERR_ARG, "unknown kernel selector");

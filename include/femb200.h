@@ -268,7 +268,8 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
  * algorithmic bytes of one launch.  which: 0 = BSR SpMV (masked
  * K_ff operator), 1 = fused element+assembly, 3 = matrix-free (EBE) operator, 4 = its 4-vector
  * form, 5 = EBE with the fused (x, y) reduction, 7 = dense blocked Cholesky (fill + factor; *bytes
- * then receives the FLOP count n^3/3), 9 = plain 16-byte read of the K values (streaming ceiling). */
+ * then receives the FLOP count n^3/3), 9 = plain 16-byte read of the K values (streaming ceiling), 10 = FP64 FMA issue
+ * ceiling (8 independent chains per thread; *bytes receives the FMA count of one launch). */
 int femb_time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes);
 
 /* CUDA-event stopwatch on the handle's stream: stop = 0 records the start (after draining the

@@ -253,7 +253,8 @@ def test_full_size_c3_properties():
     u, r, st = m.solve_static(method=L.SOLVER_PCG, rtol=1e-12)
     m.close()
     assert st["converged"] == 1 and st["rel_residual"] <= 1e-12
-    assert st["coarse_dim"] == 6 * 3 * 148      # FEMB_PRECOND_AUTO: two-level at this size, three aggregates per SM
+    # FEMB_PRECOND_AUTO at this size: the line preconditioner, 768 bundles per member direction
+    assert st["precond_used"] == L.PRECOND_LINES and st["coarse_dim"] == 3 * 768, st
     free = np.ones(len(f), dtype=bool); free[fixed] = False
     assert np.linalg.norm(r[free]) <= 1e-10 * np.linalg.norm(f)          # K u = f on free DOFs
     R = r.reshape(-1, 6)[:, :3].sum(axis=0)
