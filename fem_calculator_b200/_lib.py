@@ -92,8 +92,9 @@ SIGNATURES = {
     "femb_symbolic_lines": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_double, C.c_int32, C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int64), _P, _P, _P, _P]),
     "femb_symbolic_coarse": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, _P, C.POINTER(C.c_int64), _P, _P]),
+    "femb_dist_set_lines": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
     "femb_symbolic_line_bundles": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, _P, _P, C.POINTER(C.c_int64),
-                                             C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+                                             C.POINTER(C.c_int64), C.POINTER(C.c_double), _P, _P]),
 }
 
 _lib = None

@@ -165,10 +165,11 @@ class DistFrameModel(FrameModel):
         return bytes(buf)
 
     def setup(self, points, conn, elem_sec, sec_props, E, G, fixed_dofs, f, rank, world, unique_id=None, rho=7850.0,
-              all_gather=None):
+              all_gather=None, lines=True, line_bundles=768):
         """``all_gather(obj) -> [obj of rank 0, ..., obj of rank world-1]`` (e.g. a wrapper of
         torch.distributed.all_gather_object) switches the iteration's exchanges from NCCL to the
-        peer-memory kernels (CUDA IPC over NVLink); without it NCCL is used."""
+        peer-memory kernels (CUDA IPC over NVLink); without it NCCL is used.  ``lines``: hand the rank's
+        member-line tables to the library (PRECOND_LINES / AUTO on the partition; needs the peer-memory path)."""
         from . import partition as P
         points = np.asarray(points, dtype=np.float64)
         conn = np.asarray(conn, dtype=np.int64)
@@ -190,6 +191,22 @@ class DistFrameModel(FrameModel):
         rcnt = np.ascontiguousarray(part.recv_count, dtype=np.int64)
         self._check(self.lib.femb_dist_set_halo(self._h, part.n_owned, len(nbr), L.ptr(nbr), L.ptr(sp), L.ptr(sn),
                                                 L.ptr(rs), L.ptr(rcnt)))
+        self._bc_local = (fixed_l, f_l)
+        self.lines = False
+        if lines and world > 1 and all_gather is not None and world <= 8:
+            # symbolic phase of the line preconditioner on the GLOBAL mesh (host; identical on every rank), then the
+            # rows of this rank's local nodes
+            lb = symbolic_line_bundles(points, conn, line_bundles)
+            if lb["n_lines"] > 0 and lb["coverage"] >= 0.5:
+                ln = part.local_nodes
+                fam_off = np.ascontiguousarray(lb["fam_off"], dtype=np.int32)
+                nbl = np.ascontiguousarray(lb["node_bundle"][:, ln], dtype=np.int32)
+                nll = np.ascontiguousarray(lb["node_line"][:, ln], dtype=np.int32)
+                npl = np.ascontiguousarray(lb["node_pos"][:, ln], dtype=np.int32)
+                ndl = np.ascontiguousarray(lb["node_dir"][:, ln, :], dtype=np.float64)
+                self._check(self.lib.femb_dist_set_lines(self._h, int(fam_off[3]), L.ptr(fam_off), L.ptr(nbl), L.ptr(nll),
+                                                         L.ptr(npl), L.ptr(ndl)))
+                self.lines = True
         self.p2p = False
         if world > 1 and all_gather is not None and world <= 8:
             buf = (C.c_uint8 * 128)()
@@ -203,6 +220,10 @@ class DistFrameModel(FrameModel):
             self._check(self.lib.femb_dist_p2p_import(self._h, hb, L.ptr(pgs)))
             self.p2p = True
         return part
+
+    def set_bc_local(self):
+        """Re-upload the partition's fixed-DOF list and load vector (the host -> device part of a step)."""
+        self.set_bc(*self._bc_local)
 
     def modal_dist(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6):
         """(lambda (k,), phi_owned (n_owned_dof, k), stats) — collective: every rank calls it."""
@@ -326,17 +347,20 @@ def symbolic_lines(points, conn, cos_tol=0.94, min_nodes=3):
 
 def symbolic_line_bundles(points, conn, target_per_family=768):
     """Host-only: symbolic phase of PRECOND_LINES (csrc/coarse.cpp build_line_symbolic) — needs no GPU.
-    Returns dict(node_bundle (3,N), node_pos (3,N), fam_off (4,), n_lines, n_entries, coverage)."""
+    Returns dict(node_bundle / node_pos / node_line (3,N), node_dir (3,N,3), fam_off (4,), n_lines, n_entries, coverage)."""
     lib = L.load()
     pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
     cn = np.ascontiguousarray(conn, dtype=np.int64).reshape(-1, 2)
     nb = np.full((3, len(pts)), -1, dtype=np.int32)
     pos = np.full((3, len(pts)), -1, dtype=np.int32)
     fam_off = np.zeros(4, dtype=np.int32)
+    line = np.full((3, len(pts)), -1, dtype=np.int32)
+    ndir = np.zeros((3, len(pts), 3))
     nl, ne, cov = C.c_int64(), C.c_int64(), C.c_double()
     rc = lib.femb_symbolic_line_bundles(len(pts), len(cn), L.ptr(cn), L.ptr(pts), int(target_per_family), L.ptr(nb),
-                                        L.ptr(pos), L.ptr(fam_off), C.byref(nl), C.byref(ne), C.byref(cov))
+                                        L.ptr(pos), L.ptr(fam_off), C.byref(nl), C.byref(ne), C.byref(cov), L.ptr(line),
+                                        L.ptr(ndir))
     if rc:
         raise L.FembError(rc, "femb_symbolic_line_bundles")
-    return {"node_bundle": nb, "node_pos": pos, "fam_off": fam_off, "n_lines": nl.value, "n_entries": ne.value,
-            "coverage": cov.value}
+    return {"node_bundle": nb, "node_pos": pos, "node_line": line, "node_dir": ndir, "fam_off": fam_off,
+            "n_lines": nl.value, "n_entries": ne.value, "coverage": cov.value}

@@ -245,6 +245,7 @@ void build_line_symbolic(const Symbolic& S, const int32_t* conn, const double* x
   // bundles per family: RCB of the line midpoints
   L.node_bundle.assign((size_t)kLnMaxFam * N, -1);
   L.node_ent.assign((size_t)kLnMaxFam * N, -1);
+  L.node_line.assign((size_t)kLnMaxFam * N, -1);
   L.line_ptr.assign(1, 0);
   L.bundle_ptr.assign(1, 0);
   int32_t coarse0 = 0;
@@ -289,6 +290,7 @@ void build_line_symbolic(const Symbolic& S, const int32_t* conn, const double* x
         L.ent_blk_next.push_back(nxt);
         L.node_bundle[(size_t)f * N + node] = cidx;
         L.node_ent[(size_t)f * N + node] = e;
+        L.node_line[(size_t)f * N + node] = (int32_t)L.line_bundle.size() - 1;
       }
       L.line_ptr.push_back((int32_t)L.ent_node.size());
     }
@@ -306,6 +308,63 @@ void build_line_symbolic(const Symbolic& S, const int32_t* conn, const double* x
     covered += any;
   }
   L.coverage = N > 0 ? (double)covered / (double)N : 0.0;
+}
+
+
+void build_line_symbolic_local(const Symbolic& S, int64_t n_owned, int32_t n_coarse, const int32_t* fam_off,
+                               const int32_t* node_bundle, const int32_t* node_line, const int32_t* node_pos,
+                               const double* node_dir, LineSym& L) {
+  L = LineSym();
+  const int64_t N = S.n_nodes;
+  L.n_coarse = n_coarse;
+  for (int f = 0; f <= kLnMaxFam; ++f) L.fam_off[f] = fam_off[f];
+  L.node_bundle.assign(node_bundle, node_bundle + (size_t)kLnMaxFam * N);
+  L.node_dir.assign(node_dir, node_dir + (size_t)kLnMaxFam * N * 3);
+  L.line_ptr.assign(1, 0);
+  L.bundle_ptr.assign(1, 0);
+  struct Item { int32_t bundle, line, pos, node; };
+  std::vector<Item> items;
+  for (int f = 0; f < kLnMaxFam; ++f) {
+    items.clear();
+    for (int64_t i = 0; i < n_owned; ++i) {
+      const size_t fn = (size_t)f * N + i;
+      if (node_bundle[fn] >= 0) items.push_back({node_bundle[fn], node_line[fn], node_pos[fn], (int32_t)i});
+    }
+    std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+      return a.bundle != b.bundle ? a.bundle < b.bundle : (a.line != b.line ? a.line < b.line : a.pos < b.pos);
+    });
+    for (size_t k = 0; k < items.size();) {
+      // one piece: consecutive positions of one global line, all owned
+      size_t k1 = k + 1;
+      while (k1 < items.size() && items[k1].line == items[k].line && items[k1].pos == items[k1 - 1].pos + 1 &&
+             (int)(k1 - k) < kLnMaxLen) ++k1;
+      const int32_t bundle = items[k].bundle;
+      if (L.bundle_ids.empty() || L.bundle_ids.back() != bundle) {
+        if (!L.bundle_ids.empty()) L.bundle_ptr.push_back((int32_t)L.line_bundle.size());
+        L.bundle_ids.push_back(bundle);
+      }
+      L.line_bundle.push_back(bundle);
+      for (size_t q = k; q < k1; ++q) {
+        const int32_t node = items[q].node;
+        L.ent_node.push_back(node);
+        L.ent_blk_diag.push_back(S.diag_blk[node]);
+        int32_t nxt = -1;
+        if (q + 1 < k1) {
+          const int32_t* b0 = S.colidx.data() + S.rowptr[node];
+          const int32_t* b1 = S.colidx.data() + S.rowptr[node + 1];
+          const int32_t* it = std::lower_bound(b0, b1, items[q + 1].node);
+          if (it != b1 && *it == items[q + 1].node) nxt = (int32_t)(it - S.colidx.data());
+        }
+        L.ent_blk_next.push_back(nxt);
+      }
+      L.line_ptr.push_back((int32_t)L.ent_node.size());
+      k = k1;
+    }
+  }
+  if (!L.bundle_ids.empty()) L.bundle_ptr.push_back((int32_t)L.line_bundle.size());
+  L.n_lines = (int32_t)L.line_bundle.size();
+  L.n_entries = (int64_t)L.ent_node.size();
+  L.coverage = 1.0;
 }
 
 }  // namespace femb
@@ -378,7 +437,8 @@ extern "C" int femb_symbolic_lines(int64_t n_nodes, int64_t n_elem, const int64_
 // too); fam_off: (4) coarse index range per family.
 extern "C" int femb_symbolic_line_bundles(int64_t n_nodes, int64_t n_elem, const int64_t* conn, const double* xyz,
                                           int32_t target_per_family, int32_t* node_bundle, int32_t* node_pos,
-                                          int32_t* fam_off, int64_t* n_lines, int64_t* n_entries, double* coverage) {
+                                          int32_t* fam_off, int64_t* n_lines, int64_t* n_entries, double* coverage,
+                                          int32_t* node_line, double* node_dir) {
   if (n_nodes < 0 || n_elem < 0 || (!conn && n_elem > 0) || (!xyz && n_nodes > 0) || target_per_family < 1) return FEMB_ERR_ARG;
   std::vector<int32_t> c32((size_t)n_elem * 2);
   for (size_t i = 0; i < c32.size(); ++i) {
@@ -392,6 +452,23 @@ extern "C" int femb_symbolic_line_bundles(int64_t n_nodes, int64_t n_elem, const
   if (node_bundle && !L.node_bundle.empty()) std::memcpy(node_bundle, L.node_bundle.data(), L.node_bundle.size() * sizeof(int32_t));
   if (node_pos && !L.node_ent.empty()) std::memcpy(node_pos, L.node_ent.data(), L.node_ent.size() * sizeof(int32_t));
   if (fam_off) std::memcpy(fam_off, L.fam_off, sizeof(L.fam_off));
+  if (node_line && !L.node_line.empty()) std::memcpy(node_line, L.node_line.data(), L.node_line.size() * sizeof(int32_t));
+  if (node_dir) {
+    // unit end-to-end direction of every line, copied to its nodes (zero where the node has no line in the family)
+    std::vector<double> ldir((size_t)L.n_lines * 3, 0.0);
+    for (int32_t a = 0; a < L.n_lines; ++a) {
+      const int32_t i0 = L.ent_node[L.line_ptr[a]], i1 = L.ent_node[L.line_ptr[a + 1] - 1];
+      double d[3], n2 = 0.0;
+      for (int c = 0; c < 3; ++c) { d[c] = xyz[3 * (size_t)i1 + c] - xyz[3 * (size_t)i0 + c]; n2 += d[c] * d[c]; }
+      const double inv = n2 > 0.0 ? 1.0 / std::sqrt(n2) : 0.0;
+      for (int c = 0; c < 3; ++c) ldir[3 * (size_t)a + c] = d[c] * inv;
+    }
+    for (int f = 0; f < femb::kLnMaxFam; ++f)
+      for (int64_t i = 0; i < n_nodes; ++i) {
+        const int32_t a = L.node_line[(size_t)f * n_nodes + i];
+        for (int c = 0; c < 3; ++c) node_dir[((size_t)f * n_nodes + i) * 3 + c] = a >= 0 ? ldir[3 * (size_t)a + c] : 0.0;
+      }
+  }
   if (n_lines) *n_lines = L.n_lines;
   if (n_entries) *n_entries = L.n_entries;
   if (coverage) *coverage = L.coverage;

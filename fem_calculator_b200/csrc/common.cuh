@@ -113,8 +113,19 @@ struct LineSym {
   std::vector<int32_t> ent_blk_next; // (n_entries) block (i, next node of the line) or -1 at the line's end
   std::vector<int32_t> node_bundle;  // (kLnMaxFam, n_nodes) coarse index of the node's line in family f, -1: none
   std::vector<int32_t> node_ent;     // (kLnMaxFam, n_nodes) entry of the node in family f, -1: none
+  std::vector<int32_t> node_line;    // (kLnMaxFam, n_nodes) line of the node in family f, -1: none
+  std::vector<int32_t> bundle_ids;   // (number of bundle_ptr ranges) coarse index of each range; empty = identity.  Filled on a
+                                     // row-block partition, where a rank only holds the bundles that cross its slab
+  std::vector<double> node_dir;      // (kLnMaxFam, n_nodes, 3) unit line direction per node when the caller provides it
+                                     // (row-block partition: the GLOBAL line's direction, identical on all ranks); empty = the
+                                     // device computes end-to-end directions from the current coordinates
 };
 void build_line_symbolic(const Symbolic& S, const int32_t* conn, const double* xyz, int target_per_family, LineSym& out);
+// Line tables of one rank of a row-block partition from the GLOBAL symbolic phase restricted to the rank's local
+// nodes (owned first, then ghosts): lines are cut where they leave the owned range; bundles keep their global index.
+void build_line_symbolic_local(const Symbolic& S, int64_t n_owned, int32_t n_coarse, const int32_t* fam_off,
+                               const int32_t* node_bundle, const int32_t* node_line, const int32_t* node_pos,
+                               const double* node_dir, LineSym& out);
 
 enum class Kind { None, Frame, Tet10 };
 
@@ -200,10 +211,14 @@ struct femb_handle {
   bool line_num_ok = false;       // factors and inverses match the current K and BC mask
   bool line_failed = false;       // a bundle Galerkin matrix of the current K / BC could not be factored
   femb::LineSym line_sym;         // host copy (the per-entry tables are dropped after the upload)
+  bool line_dist = false;         // tables of a row-block partition (femb_dist_set_lines): pieces inside the slab, global bundles
   int32_t ln_fam_pad[femb::kLnMaxFam] = {0, 0, 0};
   int64_t ln_inv_off[femb::kLnMaxFam] = {0, 0, 0};
-  femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle;
-  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_yb, ln_inv;
+  int32_t ln_range_off[femb::kLnMaxFam + 1] = {0, 0, 0, 0};
+  int32_t ln_n_ranges = 0;
+  femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle,
+      ln_bundle_ids;
+  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_yb, ln_inv, ln_gal, ln_node_dir;
 
   // row-block distributed solve (dist.cu): this rank owns the first n_owned_nodes local nodes
   void* nccl_comm = nullptr;
@@ -310,6 +325,13 @@ int coarse_invert(femb_handle* h, double* aug, int64_t n_pad, double* inv, bool*
 // line preconditioner (lines.cu)
 bool lines_applicable(femb_handle* h, const femb_solve_opts& o);
 int pcg_lines(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
+int dist_set_lines(femb_handle* h, int32_t n_coarse, const int32_t* fam_off, const int32_t* node_bundle,
+                   const int32_t* node_line, const int32_t* node_pos, const double* node_dir);
+bool dist_lines_applicable(femb_handle* h, const femb_solve_opts& o, bool fused_p2p);
+int dist_lines_setup(femb_handle* h);
+int dist_lines_precond(femb_handle* h, double* red);
+int dist_lines_update(femb_handle* h, int first, double rtol, double* red);
+int dist_lines_coarse_dim(const femb_handle* h);
 int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
                     int64_t ldx, femb_stats* st);
 int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda, double* phi, int32_t* n_found,

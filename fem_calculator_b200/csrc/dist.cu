@@ -72,11 +72,6 @@ const char* load_nccl() {
       return femb::fail((h), FEMB_ERR_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
   } while (0)
 
-// red[] slots of the distributed solver (doubles): the first three are all-reduced each iteration
-struct Red {
-  enum { DELTA = 0, GAMMA = 1, RR = 2, DELTA2 = 3, NRED = 4, GPREV = 5, ALPHA = 6, TOL2 = 7, BB = 8, RRFINAL = 9, COUNT = 12 };
-};
-
 __global__ void pack_nodes_kernel(const double* __restrict__ v, const int32_t* __restrict__ nodes, int64_t n_send,
                                   int bs, double* __restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,15 +374,27 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
     if (rc) return rc;
     d_rhs = h->b.p;
   }
-  rc = setup_precond_public(h, o.precond);
+  // peer-memory path (femb_dist_p2p_import done and the exported z vector still the live one); fused: the exchanges
+  // live inside the SpMV and update kernels; FEMB_DIST_P2P_KERNELS=1 keeps the two stand-alone exchange kernels
+  const bool overlap = h->dist_world > 1 && h->dist_n_bnd > 0 && h->nccl_comm_halo && getenv("FEMB_DIST_OVERLAP");
+  const bool p2p = h->dist_world > 1 && h->p2p_dev && h->p2p_z_exported == h->z.p && !overlap && !getenv("FEMB_DIST_NO_P2P");
+  const bool fused = p2p && h->p2p_dev_copy.p && !getenv("FEMB_DIST_P2P_KERNELS");
+  // line preconditioner on the partition (lines.cu): needs the fused peer-memory exchange; otherwise Jacobi
+  bool lines = dist_lines_applicable(h, o, fused);
+  rc = setup_precond_public(h, lines ? FEMB_PRECOND_JACOBI : o.precond);
   if (rc) return rc;
+  if (lines) {
+    rc = dist_lines_setup(h);
+    if (rc < 0) return rc;
+    if (rc > 0) lines = false;                  // a bundle matrix could not be factored: Jacobi
+  }
   FEMB_CUDA(h, h->dist_red.alloc(Red::COUNT));
   FEMB_CUDA(h, cudaMemsetAsync(h->dist_red.p, 0, sizeof(double) * Red::COUNT, h->stream));
   FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
   // ghost tails start from zero (z's is overwritten by the first halo exchange)
   for (double* v : {h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, h->s.p})
     FEMB_CUDA(h, cudaMemsetAsync(v, 0, sizeof(double) * n_all, h->stream));
-  const bool blockj = (o.precond == FEMB_PRECOND_BLOCK_JACOBI);
+  const bool blockj = !lines && (o.precond == FEMB_PRECOND_BLOCK_JACOBI);
   double* red = h->dist_red.p;
 #define INIT(BS, BJ) dist_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(d_rhs, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, n, h->partials.p + pstride, pstride, red, h->flags.p)
   if (h->bs == 6) { if (blockj) INIT(6, true); else INIT(6, false); }
@@ -401,17 +408,11 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
   Peek* peek = reinterpret_cast<Peek*>(h->pinned);
   const int check = o.check_every > 0 ? o.check_every : 50;
   int it = 0, done = 0, spmv_launches = 0;
-  // Overlapping the halo with the interior rows is opt-in: at 1M DOF over 2 GPUs it measured SLOWER
+  // Overlapping the halo with the interior rows (FEMB_DIST_OVERLAP) is opt-in: at 1M DOF over 2 GPUs it measured SLOWER
   // (87.8 vs 83.0 us/iteration — the extra launches and the NCCL kernel competing for SMs cost more
   // than the ~12 us exchange they hide), at 8M DOF 3 % faster (profiles/r01_dist_2gpu.log).
-  const bool overlap = h->dist_world > 1 && h->dist_n_bnd > 0 && h->nccl_comm_halo && getenv("FEMB_DIST_OVERLAP");
   // one CG iteration, enqueued on the handle's stream (and the halo stream when overlapping)
-  // peer-memory path (femb_dist_p2p_import done and the exported z vector still the live one)
-  const bool p2p = h->dist_world > 1 && h->p2p_dev && h->p2p_z_exported == h->z.p && !overlap && !getenv("FEMB_DIST_NO_P2P");
   const P2PDev* pd = reinterpret_cast<const P2PDev*>(h->p2p_dev);
-  // fused: the exchanges live inside the SpMV and update kernels (two launches per iteration);
-  // FEMB_DIST_P2P_KERNELS=1 keeps the two stand-alone exchange kernels instead
-  const bool fused = p2p && h->p2p_dev_copy.p && !getenv("FEMB_DIST_P2P_KERNELS");
   if (p2p) {
     // line the ranks up once per solve (they arrive from host-side setup of different length): the
     // bounded waits of the peer-memory kernels are sized for iteration-scale skew, NCCL's is unbounded
@@ -420,8 +421,23 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
     *hb = h->p2p_seq_base;
     FEMB_CUDA(h, cudaMemcpyAsync(h->p2p_base_dev, hb, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
   }
+  if (lines) {
+    // z_0 = M^-1 r_0 (replaces the Jacobi z of the init kernel), its boundary entries pushed to the neighbours
+    rc = dist_lines_precond(h, red);
+    if (rc) return rc;
+  }
   auto enqueue_iteration = [&](int first) -> int {
     int rc2;
+    if (lines) {
+      // operator (waits for the halo flags, posts {delta, gamma, ||r||^2}) -> update (collects them) -> line solves
+      // (posts the bundle residuals) -> coarse products (collect them) -> prolongation (pushes the halo of z)
+      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red + Red::DELTA, nullptr, nullptr, h->p2p_dev_copy.p);
+      if (rc2) return rc2;
+      ++spmv_launches;
+      rc2 = dist_lines_update(h, first, o.rtol, red);
+      if (rc2) return rc2;
+      return dist_lines_precond(h, red);
+    }
     if (overlap) {
       // halo of z on its own stream / communicator while the rows that read no ghost column run
       FEMB_CUDA(h, cudaEventRecord(h->ev_vec, h->stream));
@@ -502,7 +518,7 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
       FEMB_CUDA(h, cudaGraphLaunch(gexec, h->stream));
       it += check;
       spmv_launches += (overlap ? 2 : 1) * check;
-      h->launches += (overlap ? 4 : 3) * check;
+      h->launches += (lines ? 5 : (overlap ? 4 : 3)) * check;
     } else {
       const int batch = std::min(check, o.max_iter + 1 - it);
       for (int k = 0; k < batch; ++k, ++it) {
@@ -523,6 +539,9 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
     st->iterations = peek->flags[Flag::ITERS];
     st->converged = (done == 1);
     st->spmv_launches = spmv_launches;
+    st->precond_used = lines ? FEMB_PRECOND_LINES : (blockj ? FEMB_PRECOND_BLOCK_JACOBI : FEMB_PRECOND_JACOBI);
+    st->coarse_dim = lines ? dist_lines_coarse_dim(h) : 0;
+    st->op_used = ebe_available_dist(h) ? FEMB_OP_EBE : FEMB_OP_BSR;
     const double bb = peek->red[Red::BB];
     st->rel_residual = bb > 0.0 ? std::sqrt(peek->red[Red::RRFINAL] / bb) : 0.0;
   }
@@ -653,6 +672,13 @@ int femb_dist_set_halo(femb_handle* h, int64_t n_owned_nodes, int32_t n_nbr, con
   return FEMB_OK;
 }
 
+int femb_dist_set_lines(femb_handle* h, int32_t n_coarse, const int32_t* fam_off, const int32_t* node_bundle,
+                        const int32_t* node_line, const int32_t* node_pos, const double* node_dir) {
+  if (!h || !fam_off || !node_bundle || !node_line || !node_pos || !node_dir) return fail(h, FEMB_ERR_ARG, "bad femb_dist_set_lines arguments");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  return dist_set_lines(h, n_coarse, fam_off, node_bundle, node_line, node_pos, node_dir);
+}
+
 int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128) {
   if (!h || !handles128) return FEMB_ERR_ARG;
   if (!h->have_bc || !h->z.p) return fail(h, FEMB_ERR_ARG, "call femb_set_bc before femb_dist_p2p_export");
@@ -661,8 +687,9 @@ int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128) {
   // ONE dedicated allocation per rank — mailboxes, flags and the z vector itself — of at least
   // 2 MB, so that it is never a sub-allocation of a block shared with other buffers: the IPC
   // handle then maps exactly this memory at offset 0 in every peer.
-  const size_t zbytes = (size_t)h->ndof * sizeof(double);
-  const size_t bytes = std::max<size_t>(kP2PZOffset + zbytes, (size_t)4 << 20);
+  const size_t zbytes = ((size_t)h->ndof * sizeof(double) + 255) / 256 * 256;
+  const size_t rbbytes = (size_t)h->dist_world * 2 * kLnMaxCoarse * sizeof(double);   // coarse-residual mail of lines.cu
+  const size_t bytes = std::max<size_t>(kP2PZOffset + zbytes + rbbytes, (size_t)4 << 20);
   h->z.release();                       // z moves into the exported allocation
   FEMB_CUDA(h, h->p2p_comm.alloc(bytes));
   FEMB_CUDA(h, cudaMemset(h->p2p_comm.p, 0, bytes));
@@ -672,6 +699,8 @@ int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   std::memset(handles128, 0, 128);
   std::memcpy(handles128, &hc, 64);
+  const unsigned long long zb = zbytes;            // where this rank's coarse-residual mail starts behind its z vector
+  std::memcpy(handles128 + 64, &zb, sizeof(zb));
   h->p2p_z_exported = h->z.p;
   return FEMB_OK;
 }
@@ -691,6 +720,11 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
   pd->my_halo_flag = flag_of(cb);
   h->p2p_base_dev = flag_of(cb) + world;
   h->p2p_ticket = reinterpret_cast<int*>(flag_of(cb) + world + 1);
+  // header continues: [rb flags (world)] [ticket2]; the coarse-residual mail follows the z vector
+  const size_t zbytes = ((size_t)h->ndof * sizeof(double) + 255) / 256 * 256;
+  auto rbflag_of = [&](char* base) { return flag_of(base) + world + 2; };
+  pd->my_rbflag = rbflag_of(cb);
+  pd->ticket2 = reinterpret_cast<int*>(rbflag_of(cb) + world);
   pd->base = h->p2p_base_dev;
   pd->world = world; pd->rank = rank;
   std::vector<char*> peer_comm(world, nullptr);
@@ -704,6 +738,16 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
     h->p2p_mapped.push_back(ptr);
   }
   for (int p = 0; p < world; ++p) pd->peer_mail[p] = mail_of(peer_comm[p]);
+  // every rank's local vector has its own length, so a peer's mail area sits behind ITS z: the offsets travel with the
+  // handles (femb_dist_p2p_export writes the rank's z bytes into its 128-byte blob)
+  for (int p = 0; p < world; ++p) {
+    unsigned long long zb = 0;
+    std::memcpy(&zb, all_handles + (size_t)p * 128 + 64, sizeof(zb));
+    if (p == rank) zb = zbytes;
+    pd->peer_rbmail[p] = reinterpret_cast<double*>(peer_comm[p] + kP2PZOffset + zb);
+    pd->peer_rbflag[p] = rbflag_of(peer_comm[p]);
+  }
+  pd->my_rbmail = pd->peer_rbmail[rank];
   pd->n_nbr = (int)h->dist_nbr.size();
   if (pd->n_nbr > kMaxRanks) { delete pd; return fail(h, FEMB_ERR_ARG, "too many neighbour ranks"); }
   for (int k = 0; k < pd->n_nbr; ++k) {

@@ -195,7 +195,15 @@ struct P2PDev {
   const int32_t* send_slot;
   const int32_t* extra;      // (n_extra, 2)
   int n_extra;
+  // coarse residuals of the line preconditioner (lines.cu): every rank stores its partial bundle residuals into
+  // every rank's mail area [source rank][parity][kLnMaxCoarse] and releases the flag [source rank]
+  double* peer_rbmail[kMaxRanks];     // per RANK p
+  long long* peer_rbflag[kMaxRanks];  // per RANK p
+  double* my_rbmail;
+  long long* my_rbflag;
+  int* ticket2;
 };
+constexpr int kLnMaxCoarse = 3072;    // capacity of the coarse-residual mail slots (3 families x 1024 bundles)
 
 __device__ __forceinline__ void st_release_sys(long long* p, long long v) {
   asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -206,6 +214,12 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
   return v;
 }
 constexpr long long kSpinLimit = 1ll << 24;   // several seconds of polling, then DONE = 4
+
+// red[] slots of the distributed solver (doubles): the first three are all-reduced each iteration
+struct Red {
+  enum { DELTA = 0, GAMMA = 1, RR = 2, DELTA2 = 3, NRED = 4, GPREV = 5, ALPHA = 6, TOL2 = 7, BB = 8, RRFINAL = 9, COUNT = 12 };
+};
+
 
 
 inline int vec_grid(const femb_handle* h, int64_t n, int threads) {

@@ -260,6 +260,14 @@ int femb_dist_solve_static(femb_handle* h, const femb_solve_opts* opts, int minu
  * PCG then replaces ncclSend/ncclRecv + ncclAllReduce by two small kernels that store straight into
  * the peers' memory (see csrc/dist.cu); without the import it uses NCCL.  Up to 8 ranks.        */
 int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128);
+/* Line preconditioner on the partition (FEMB_PRECOND_LINES / AUTO in femb_dist_solve_static; needs the peer-memory
+ * exchange): every rank runs femb_symbolic_line_bundles on the GLOBAL mesh and passes the rows of its LOCAL nodes
+ * (owned, then ghosts): node_bundle / node_line / node_pos (3, n_local) and node_dir (3, n_local, 3), plus the global
+ * n_coarse and fam_off (4).  Lines are cut where they leave the rank's slab; a bundle's residual is the sum of the
+ * ranks' partial residuals (one all-gather of n_coarse doubles per iteration through the peers' mail areas) and the
+ * bundle Galerkin matrices are summed over the ranks once per assembled K.  Call after femb_dist_set_halo.        */
+int femb_dist_set_lines(femb_handle* h, int32_t n_coarse, const int32_t* fam_off, const int32_t* node_bundle,
+                        const int32_t* node_line, const int32_t* node_pos, const double* node_dir);
 int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64_t* peer_ghost_start);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------
@@ -313,11 +321,13 @@ int femb_symbolic_lines(int64_t n_nodes, int64_t n_elem, const int64_t* conn, co
  * a family are grouped into at most target_per_family bundles (recursive coordinate bisection of the line
  * midpoints).  node_bundle: (3, n_nodes) coarse index of the node's line per family, -1 = none; node_pos:
  * (3, n_nodes) index of the node in the sorted entry list (consecutive along a line, lines of a bundle
- * consecutive); fam_off: (4) coarse index range per family; coverage: fraction of nodes on at least one line.
+ * consecutive); fam_off: (4) coarse index range per family; coverage: fraction of nodes on at least one line;
+ * node_line: (3, n_nodes) line index per family; node_dir: (3, n_nodes, 3) unit end-to-end direction of that line.
  * Any output pointer may be NULL.                                                                          */
 int femb_symbolic_line_bundles(int64_t n_nodes, int64_t n_elem, const int64_t* conn, const double* xyz,
                                int32_t target_per_family, int32_t* node_bundle, int32_t* node_pos,
-                               int32_t* fam_off, int64_t* n_lines, int64_t* n_entries, double* coverage);
+                               int32_t* fam_off, int64_t* n_lines, int64_t* n_entries, double* coverage,
+                               int32_t* node_line, double* node_dir);
 
 #ifdef __cplusplus
 }

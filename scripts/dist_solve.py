@@ -14,6 +14,10 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 nx, ny, nz = [int(v) for v in args[:3]] if len(args) >= 3 else (56, 56, 54)
 check = "--check" in sys.argv
 precond = L.PRECOND_BLOCK_JACOBI if "--blockj" in sys.argv else L.PRECOND_JACOBI
+for a in sys.argv[1:]:
+    if a.startswith("--precond="):
+        precond = {"jacobi": L.PRECOND_JACOBI, "lines": L.PRECOND_LINES, "auto": L.PRECOND_AUTO, "blockj": L.PRECOND_BLOCK_JACOBI}[a.split("=")[1]]
+reps = 3 if "--reps" in sys.argv else 1
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -43,7 +47,12 @@ t_setup = time.time() - t0
 u, r, st = m.solve_static_dist(precond=precond)            # warm-up (NCCL connections, allocator)
 if world > 1:
     dist.barrier(); torch.cuda.synchronize()
-u, r, st = m.solve_static_dist(precond=precond)
+best = None
+for _ in range(reps):
+    m.assemble()                                            # numeric setup of the preconditioner inside the timed solve
+    u, r, st = m.solve_static_dist(precond=precond)
+    best = st if best is None or st["device_ms"] < best["device_ms"] else best
+st = best
 ms = torch.tensor([st["device_ms"]], device="cuda", dtype=torch.float64)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -54,7 +63,7 @@ if rank == 0:
                       "us_per_iteration": float(ms.item()) / max(1, st["iterations"]) * 1e3,
                       "dof_per_s": n_free / (float(ms.item()) * 1e-3), "owned_nodes_rank0": int(part.n_owned),
                       "ghost_nodes_rank0": int(len(part.local_nodes) - part.n_owned), "setup_s": t_setup,
-                      "precond": "block-jacobi" if precond == L.PRECOND_BLOCK_JACOBI else "jacobi", "exchange": "p2p" if getattr(m, "p2p", False) else "nccl"}), flush=True)
+                      "precond_requested": precond, "precond_used": st["precond_used"], "coarse_dim": st["coarse_dim"], "exchange": "p2p" if getattr(m, "p2p", False) else "nccl"}), flush=True)
 if check:
     from oracle import ref_sparse as S
     if world > 1:

@@ -1,0 +1,40 @@
+"""Multi-rank test of the row-block distributed solve (csrc/dist.cu + csrc/lines.cu): needs >= 2 GPUs on the box
+(skipped otherwise).  Launches scripts/dist_solve.py under torchrun with 2 ranks — peer-memory halo / scalar /
+coarse-residual exchange, line preconditioner on the partition — and lets it compare the gathered u with the CPU
+oracle's direct solve (||u - u_ref|| <= 1e-10 ||u_ref||)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    from fem_calculator_b200 import _lib
+    return int(_lib.load().femb_device_count())
+
+
+def _run(world, lattice, precond, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "scripts", "dist_solve.py"), *map(str, lattice), "--check",
+           f"--precond={precond}"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    assert "check: ||u - u_oracle||" in r.stdout
+    return json.loads(line)
+
+
+@pytest.mark.parametrize("precond", ["lines", "jacobi"])
+def test_two_rank_solve_matches_oracle(precond):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _run(2, (14, 10, 9), precond, 29611 if precond == "lines" else 29612)
+    assert out["world"] == 2 and out["exchange"] == "p2p"
+    if precond == "lines":
+        assert out["precond_used"] == 5 and out["coarse_dim"] > 0, out
+        assert out["iterations"] < 300, out
