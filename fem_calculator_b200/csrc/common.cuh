@@ -244,7 +244,7 @@ struct femb_handle {
   long long p2p_seq_base = 0;
   std::vector<void*> p2p_mapped;
   femb::DevBuf<char> p2p_dev_copy;         // device-resident P2PDev for the fused kernels
-  femb::DevBuf<int32_t> p2p_send_slot, p2p_extra;
+  femb::DevBuf<int32_t> p2p_send_slot, p2p_extra, p2p_bnd_nodes;
 
   void* pinned = nullptr;           // small pinned staging area
   size_t pinned_bytes = 0;

@@ -725,6 +725,7 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
   auto rbflag_of = [&](char* base) { return flag_of(base) + world + 2; };
   pd->my_rbflag = rbflag_of(cb);
   pd->ticket2 = reinterpret_cast<int*>(rbflag_of(cb) + world);
+  pd->ticket3 = reinterpret_cast<int*>(rbflag_of(cb) + world + 1);
   pd->base = h->p2p_base_dev;
   pd->world = world; pd->rank = rank;
   std::vector<char*> peer_comm(world, nullptr);
@@ -775,6 +776,13 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
         else { extra.push_back(node); extra.push_back(sl); }
       }
     if (ok) {
+      std::vector<int32_t> bnd;
+      for (int64_t i = 0; i < h->n_owned_nodes; ++i)
+        if (slot[i] >= 0) bnd.push_back((int32_t)i);
+      pd->n_bnd = (int)bnd.size();
+      if (bnd.empty()) bnd.push_back(0);
+      FEMB_CUDA(h, upload(h->p2p_bnd_nodes, bnd, h->stream));
+      pd->bnd_nodes = h->p2p_bnd_nodes.p;
       FEMB_CUDA(h, upload(h->p2p_send_slot, slot, h->stream));
       if (extra.empty()) { extra.push_back(0); extra.push_back(0); pd->n_extra = 0; }
       else pd->n_extra = (int)(extra.size() / 2);

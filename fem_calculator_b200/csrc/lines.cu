@@ -568,53 +568,67 @@ dist_ln_update_kernel(const double* __restrict__ z, const double* __restrict__ s
   }
 }
 
-// prolongation over the owned nodes: z = omega D^-1 r + sum_f w_f (yl_f + yb[bundle_f]); the boundary entries of z
-// go straight into the neighbours' ghost tails (remote stores), the local (r, z) to red[GAMMA]; the last CTA handles
-// the nodes with several destinations and releases the halo flag of the next operator launch at every neighbour.
+// prolongation over the owned nodes: z = omega D^-1 r + sum_f w_f (yl_f + yb[bundle_f]); the local (r, z) goes to
+// red[GAMMA].  Phase 1 handles the nodes a neighbour needs: their z goes straight into the neighbours' ghost tails
+// (remote stores) and the last CTA to finish the phase (ticket) stores the few nodes with several destinations and
+// releases the halo flag of the next operator launch at every neighbour — while phase 2, the interior, is still
+// running, so the flag has landed long before the neighbour's operator kernel looks for it.
+__device__ __forceinline__ double ln_prolong_node(const LnDev& T, const double* __restrict__ dinv, const double* __restrict__ r,
+                                                  double* __restrict__ z, int node, double* zt) {
+  const double2* r2 = reinterpret_cast<const double2*>(r + 6 * (size_t)node);
+  const double2* d2 = reinterpret_cast<const double2*>(dinv + 6 * (size_t)node);
+  const double2 ra = r2[0], rb2 = r2[1], rc = r2[2];
+  const double2 da = __ldg(d2), db = __ldg(d2 + 1), dc = __ldg(d2 + 2);
+  zt[0] = T.omega * da.x * ra.x; zt[1] = T.omega * da.y * ra.y; zt[2] = T.omega * db.x * rb2.x;
+  zt[3] = T.omega * db.y * rb2.y; zt[4] = T.omega * dc.x * rc.x; zt[5] = T.omega * dc.y * rc.y;
+#pragma unroll
+  for (int f = 0; f < kLnMaxFam; ++f) {
+    const size_t fn = (size_t)f * T.n_nodes + node;
+    const int cb = __ldg(T.node_bundle + fn);
+    if (cb >= 0) {
+      const double amp = T.yl[fn] + __ldcg(T.yb + cb);
+      const double* w = T.node_w + 3 * fn;
+      zt[0] = fma(__ldg(w), amp, zt[0]); zt[1] = fma(__ldg(w + 1), amp, zt[1]); zt[2] = fma(__ldg(w + 2), amp, zt[2]);
+    }
+  }
+  double2* zo = reinterpret_cast<double2*>(z + 6 * (size_t)node);
+  zo[0] = make_double2(zt[0], zt[1]); zo[1] = make_double2(zt[2], zt[3]); zo[2] = make_double2(zt[4], zt[5]);
+  return ra.x * zt[0] + ra.y * zt[1] + rb2.x * zt[2] + rb2.y * zt[3] + rc.x * zt[4] + rc.y * zt[5];
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 dist_ln_prolong_kernel(const LnDev T, const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ z,
                        int n_owned, double* partials, int pstride, double* red, int* flags, const P2PDev* __restrict__ p2p) {
+  __shared__ int s_last;
   if (flags[Flag::DONE]) return;
   double g = 0.0;
+  // phase 1: boundary nodes
   bool pushed = false;
-  for (int node = blockIdx.x * THREADS + threadIdx.x; node < n_owned; node += gridDim.x * THREADS) {
-    const double2* r2 = reinterpret_cast<const double2*>(r + 6 * (size_t)node);
-    const double2* d2 = reinterpret_cast<const double2*>(dinv + 6 * (size_t)node);
-    const double2 ra = r2[0], rb2 = r2[1], rc = r2[2];
-    const double2 da = __ldg(d2), db = __ldg(d2 + 1), dc = __ldg(d2 + 2);
-    double zt[6] = {T.omega * da.x * ra.x, T.omega * da.y * ra.y, T.omega * db.x * rb2.x,
-                    T.omega * db.y * rb2.y, T.omega * dc.x * rc.x, T.omega * dc.y * rc.y};
-#pragma unroll
-    for (int f = 0; f < kLnMaxFam; ++f) {
-      const size_t fn = (size_t)f * T.n_nodes + node;
-      const int cb = __ldg(T.node_bundle + fn);
-      if (cb >= 0) {
-        const double amp = T.yl[fn] + __ldcg(T.yb + cb);
-        const double* w = T.node_w + 3 * fn;
-        zt[0] = fma(__ldg(w), amp, zt[0]); zt[1] = fma(__ldg(w + 1), amp, zt[1]); zt[2] = fma(__ldg(w + 2), amp, zt[2]);
-      }
-    }
-    double2* zo = reinterpret_cast<double2*>(z + 6 * (size_t)node);
-    zo[0] = make_double2(zt[0], zt[1]); zo[1] = make_double2(zt[2], zt[3]); zo[2] = make_double2(zt[4], zt[5]);
+  for (int k = blockIdx.x * THREADS + threadIdx.x; k < p2p->n_bnd; k += gridDim.x * THREADS) {
+    const int node = __ldg(p2p->bnd_nodes + k);
+    double zt[6];
+    g += ln_prolong_node(T, dinv, r, z, node, zt);
     const int sl = __ldg(p2p->send_slot + node);
-    if (sl >= 0) {
-      double* dst = p2p->peer_z[sl >> 28] + (size_t)(sl & 0xFFFFFFF) * 6;
+    double* dst = p2p->peer_z[sl >> 28] + (size_t)(sl & 0xFFFFFFF) * 6;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) dst[c] = zt[c];
-      pushed = true;
-    }
-    g += ra.x * zt[0] + ra.y * zt[1] + rb2.x * zt[2] + rb2.y * zt[3] + rc.x * zt[4] + rc.y * zt[5];
+    for (int c = 0; c < 6; ++c) dst[c] = zt[c];
+    pushed = true;
   }
   if (pushed) __threadfence_system();
-  double mine[1], tot[1];
-  mine[0] = g;
-  if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET2, tot)) {
-    if (threadIdx.x == 0) red[Red::GAMMA] = tot[0];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int tk = atomicAdd(p2p->ticket3, 1);
+    s_last = (tk == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
     for (int e = threadIdx.x; e < p2p->n_extra * 6; e += THREADS) {
       const int i = e / 6, c = e - i * 6;
       const int node = p2p->extra[2 * i], sl = p2p->extra[2 * i + 1];
-      p2p->peer_z[sl >> 28][(size_t)(sl & 0xFFFFFFF) * 6 + c] = z[(size_t)node * 6 + c];
+      p2p->peer_z[sl >> 28][(size_t)(sl & 0xFFFFFFF) * 6 + c] = __ldcg(z + (size_t)node * 6 + c);
     }
     __threadfence_system();
     __syncthreads();
@@ -622,6 +636,18 @@ dist_ln_prolong_kernel(const LnDev T, const double* __restrict__ dinv, const dou
       const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;
       st_release_sys(p2p->peer_halo_flag[threadIdx.x] + p2p->rank, seq);
     }
+    if (threadIdx.x == 0) *p2p->ticket3 = 0;
+  }
+  // phase 2: interior nodes
+  for (int node = blockIdx.x * THREADS + threadIdx.x; node < n_owned; node += gridDim.x * THREADS) {
+    if (__ldg(p2p->send_slot + node) >= 0) continue;
+    double zt[6];
+    g += ln_prolong_node(T, dinv, r, z, node, zt);
+  }
+  double mine[1], tot[1];
+  mine[0] = g;
+  if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET2, tot)) {
+    if (threadIdx.x == 0) red[Red::GAMMA] = tot[0];
   }
 }
 

@@ -202,6 +202,11 @@ struct P2PDev {
   double* my_rbmail;
   long long* my_rbflag;
   int* ticket2;
+  // owned nodes with at least one remote destination, ascending (the prolongation handles them first and releases
+  // the halo flags before it touches the interior)
+  const int32_t* bnd_nodes;
+  int n_bnd;
+  int* ticket3;
 };
 constexpr int kLnMaxCoarse = 3072;    // capacity of the coarse-residual mail slots (3 families x 1024 bundles)
 
