@@ -215,10 +215,11 @@ struct femb_handle {
   int32_t ln_fam_pad[femb::kLnMaxFam] = {0, 0, 0};
   int64_t ln_inv_off[femb::kLnMaxFam] = {0, 0, 0};
   int32_t ln_range_off[femb::kLnMaxFam + 1] = {0, 0, 0, 0};
-  int32_t ln_n_ranges = 0;
+  int32_t ln_n_ranges = 0, ln_max_len = 0;
   femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle,
-      ln_bundle_ids;
-  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_yb, ln_inv, ln_gal, ln_node_dir;
+      ln_bundle_ids, ln_bundle_cnt, ln_line_range;
+  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_yb, ln_inv, ln_gal, ln_node_dir, ln_line_sum;
+  femb::DevBuf<unsigned long long> mega_state;   // persistent PCG kernel: grid barrier words + per-phase clocks
 
   // row-block distributed solve (dist.cu): this rank owns the first n_owned_nodes local nodes
   void* nccl_comm = nullptr;
@@ -329,9 +330,7 @@ int dist_set_lines(femb_handle* h, int32_t n_coarse, const int32_t* fam_off, con
                    const int32_t* node_line, const int32_t* node_pos, const double* node_dir);
 bool dist_lines_applicable(femb_handle* h, const femb_solve_opts& o, bool fused_p2p);
 int dist_lines_setup(femb_handle* h);
-int dist_lines_precond(femb_handle* h, double* red);
-int dist_lines_update(femb_handle* h, int first, double rtol, double* red);
-int dist_lines_coarse_dim(const femb_handle* h);
+int dist_lines_solve(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
                     int64_t ldx, femb_stats* st);
 int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda, double* phi, int32_t* n_found,

@@ -397,7 +397,8 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
   const bool blockj = !lines && (o.precond == FEMB_PRECOND_BLOCK_JACOBI);
   double* red = h->dist_red.p;
 #define INIT(BS, BJ) dist_init_kernel<BS, kRowThreads, BJ><<<gridv, kRowThreads, 0, h->stream>>>(d_rhs, h->Dinv.p, h->x.p, h->r.p, h->z.p, h->p.p, h->q.p, n, h->partials.p + pstride, pstride, red, h->flags.p)
-  if (h->bs == 6) { if (blockj) INIT(6, true); else INIT(6, false); }
+  if (lines) { /* the persistent kernel initialises its own vectors */ }
+  else if (h->bs == 6) { if (blockj) INIT(6, true); else INIT(6, false); }
   else { if (blockj) INIT(3, true); else INIT(3, false); }
 #undef INIT
   h->launches++;
@@ -422,22 +423,15 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
     FEMB_CUDA(h, cudaMemcpyAsync(h->p2p_base_dev, hb, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
   }
   if (lines) {
-    // z_0 = M^-1 r_0 (replaces the Jacobi z of the init kernel), its boundary entries pushed to the neighbours
-    rc = dist_lines_precond(h, red);
-    if (rc) return rc;
+    // line-preconditioned PCG: the whole iteration, exchanges included, runs inside one persistent kernel (lines.cu)
+    rc = dist_lines_solve(h, o, d_rhs, st);
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->p2p_seq_base += (long long)peek->flags[Flag::ITERS] + 4;   // identical on every rank
+    return rc;
   }
   auto enqueue_iteration = [&](int first) -> int {
     int rc2;
-    if (lines) {
-      // operator (waits for the halo flags, posts {delta, gamma, ||r||^2}) -> update (collects them) -> line solves
-      // (posts the bundle residuals) -> coarse products (collect them) -> prolongation (pushes the halo of z)
-      rc2 = launch_spmv_rows(h, h->z.p, h->s.p, n, true, h->partials.p, red + Red::DELTA, nullptr, nullptr, h->p2p_dev_copy.p);
-      if (rc2) return rc2;
-      ++spmv_launches;
-      rc2 = dist_lines_update(h, first, o.rtol, red);
-      if (rc2) return rc2;
-      return dist_lines_precond(h, red);
-    }
     if (overlap) {
       // halo of z on its own stream / communicator while the rows that read no ghost column run
       FEMB_CUDA(h, cudaEventRecord(h->ev_vec, h->stream));
@@ -518,7 +512,7 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
       FEMB_CUDA(h, cudaGraphLaunch(gexec, h->stream));
       it += check;
       spmv_launches += (overlap ? 2 : 1) * check;
-      h->launches += (lines ? 5 : (overlap ? 4 : 3)) * check;
+      h->launches += (overlap ? 4 : 3) * check;
     } else {
       const int batch = std::min(check, o.max_iter + 1 - it);
       for (int k = 0; k < batch; ++k, ++it) {
@@ -539,8 +533,7 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
     st->iterations = peek->flags[Flag::ITERS];
     st->converged = (done == 1);
     st->spmv_launches = spmv_launches;
-    st->precond_used = lines ? FEMB_PRECOND_LINES : (blockj ? FEMB_PRECOND_BLOCK_JACOBI : FEMB_PRECOND_JACOBI);
-    st->coarse_dim = lines ? dist_lines_coarse_dim(h) : 0;
+    st->precond_used = blockj ? FEMB_PRECOND_BLOCK_JACOBI : FEMB_PRECOND_JACOBI;
     st->op_used = ebe_available_dist(h) ? FEMB_OP_EBE : FEMB_OP_BSR;
     const double bb = peek->red[Red::BB];
     st->rel_residual = bb > 0.0 ? std::sqrt(peek->red[Red::RRFINAL] / bb) : 0.0;
@@ -796,7 +789,7 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
   }
   if (h->p2p_dev) delete reinterpret_cast<P2PDev*>(h->p2p_dev);
   h->p2p_dev = pd;
-  h->p2p_seq_base = 0;
+  h->p2p_seq_base = 2;          // never 0: the flags start at 0 and the first coarse-residual exchange of a solve is numbered `base`
   return FEMB_OK;
 }
 

@@ -101,4 +101,74 @@ __device__ __forceinline__ void load6(const double* __restrict__ x, int node, do
   u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
 }
 
+// y = K_ff x over all nodes by the CTAs [cta, cta + ncta, ..) of a PERSISTENT kernel (lines.cu): the node-gather
+// mapping of frame_ebe_node_kernel<1, 1, 2> (two lanes per node, interleaved steps of THREADS / 2 nodes) as a device
+// function.  x was written by other CTAs of the same launch: it is read with plain coherent loads (the grid barrier
+// before the phase carries acquire semantics), never through the non-coherent read-only path.  Returns the thread's
+// share of (x, y).
+template <int THREADS>
+__device__ __forceinline__ double ebe_nodes_phase(const FrameParams& P, const int4* __restrict__ pair_rec,
+                                                  const int4* __restrict__ node_rec, int n_nodes,
+                                                  const uint8_t* __restrict__ free_mask, const double* x, double* y,
+                                                  int cta, int ncta) {
+  constexpr int NPC = THREADS / 2;
+  const int part = threadIdx.x & 1;
+  double dot = 0.0;
+  for (int base = cta * NPC; base < n_nodes; base += ncta * NPC) {
+    const int node = base + (threadIdx.x >> 1);
+    const bool active = node < n_nodes;
+    int first = 0, count = 0;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    double ua[6], acc[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { ua[c] = 0.0; acc[c] = 0.0; }
+    if (active) {
+      const int4 nr = __ldg(node_rec + node);
+      first = nr.x; count = nr.y;
+      const double* pp = P.xyz + 3 * (size_t)node;
+      px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+      const double2* xp = reinterpret_cast<const double2*>(x + (size_t)node * 6);
+      const double2 a = xp[0], b = xp[1], c2 = xp[2];
+      ua[0] = a.x; ua[1] = a.y; ua[2] = b.x; ua[3] = b.y; ua[4] = c2.x; ua[5] = c2.y;
+    }
+#pragma unroll 2
+    for (int j = part; j < count; j += 2) {
+      const int4 rec = __ldg(pair_rec + first + j);
+      const int a = (rec.w >> 24) & 1;
+      const double* po = P.xyz + 3 * (size_t)rec.y;
+      const double ox = __ldg(po), oy = __ldg(po + 1), oz = __ldg(po + 2);
+      const double* sp = P.sec_props + 8 * (size_t)(rec.w & 0xFFFFFF);
+      FrameIn in;   // element direction: end 0 -> end 1, as in the assembly kernel
+      in.dx = a ? px - ox : ox - px; in.dy = a ? py - oy : oy - py; in.dz = a ? pz - oz : oz - pz;
+      in.A = __ldg(sp); in.Ix = __ldg(sp + 1); in.Iy = __ldg(sp + 2); in.J = __ldg(sp + 3);
+      in.ky = __ldg(sp + 4); in.kz = __ldg(sp + 5);
+      double uo[6];
+      {
+        const double2* xo = reinterpret_cast<const double2*>(x + (size_t)rec.y * 6);
+        const double2 u0 = xo[0], u1 = xo[1], u2 = xo[2];
+        uo[0] = u0.x; uo[1] = u0.y; uo[2] = u1.x; uo[3] = u1.y; uo[4] = u2.x; uo[5] = u2.y;
+      }
+      KRec k;
+      krec_from(P, in, a, k);
+      double o6[6];
+      ebe_apply(k, ua, uo, o6);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[c] += o6[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+    if (active && part == 0) {
+      const uint8_t* fm = free_mask + (size_t)node * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        if (!fm[c]) acc[c] = ua[c];      // identity rows on the fixed DOFs
+      double2* yp = reinterpret_cast<double2*>(y + (size_t)node * 6);
+      yp[0] = make_double2(acc[0], acc[1]); yp[1] = make_double2(acc[2], acc[3]); yp[2] = make_double2(acc[4], acc[5]);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) dot += ua[c] * acc[c];
+    }
+  }
+  return dot;
+}
+
 }  // namespace femb

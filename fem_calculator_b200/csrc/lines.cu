@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "ebe.cuh"
 #include "pcg_common.cuh"
 
 namespace femb {
@@ -51,6 +52,10 @@ struct LnDev {
   double* fac;                  // (n_entries, 3) {1/delta, forward coefficient, backward coefficient}
   double* yl;                   // (F, N) line-solve amplitude of the node's line entry
   double* rb;                   // (n_coarse) bundle residuals
+  double* line_sum;             // (n_lines) axial residual sum of every line (persistent kernel: bundles are summed from these)
+  int32_t max_len;              // longest line (entries)
+  int32_t* bundle_cnt;          // (bundle_ptr ranges) lines of each bundle finished in the current pass (persistent kernel)
+  const int32_t* line_range;    // (n_lines) bundle_ptr range of every line
   double* yb;                   // (n_coarse) coarse solution
   const double* inv;            // per-family inverses, family f at inv_off[f], leading dimension fam_pad[f]
   int64_t inv_off[kLnMaxFam];
@@ -234,111 +239,45 @@ __global__ void ln_aug_fill_kernel(const double* __restrict__ G, double* __restr
 }
 
 // ---- iteration kernels --------------------------------------------------------------------------------
-// init: x = 0, r = b, p = q = 0; publishes ||b||^2 into buffer 0 (gamma_0 follows from ln_prolong with wr = 0)
-__global__ void __launch_bounds__(kLnVecThreads)
-ln_init_kernel(const double* __restrict__ b, double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
-               double* __restrict__ q, int64_t n, const PcgLink L) {
-  __shared__ double s_part[kLnVecThreads / 32];
-  double v[1] = {0.0};
-  for (int64_t g = (int64_t)blockIdx.x * kLnVecThreads + threadIdx.x; g < n; g += (int64_t)gridDim.x * kLnVecThreads) {
-    const double bg = b[g];
-    x[g] = 0.0; r[g] = bg; p[g] = 0.0; q[g] = 0.0;
-    v[0] += bg * bg;
-  }
-  block_sum_all<kLnVecThreads, 1>(v, s_part);
-  if (threadIdx.x == 0) L.upd_partials[L.pstride + blockIdx.x] = v[0];
-  if (blockIdx.x == 0 && threadIdx.x == 0) { L.flags[Flag::DONE] = 0; L.flags[Flag::ITERS] = 0; }
-}
-
-// update(it): consumes delta (operator) and gamma (ln_prolong of the previous iteration / init) like
-// pcg_update_linked_kernel; p = z + beta p, q = s + beta q, x += alpha p, r -= alpha q; publishes ||r||^2 into
-// buffer (it + 1) & 1
-__global__ void __launch_bounds__(kLnVecThreads)
-ln_update_kernel(const double* __restrict__ z, const double* __restrict__ s, double* __restrict__ p, double* __restrict__ q,
-                 double* __restrict__ x, double* __restrict__ r, int64_t n, const PcgLink L) {
-  __shared__ double s_part[2 * kLnVecThreads / 32];
-  if (L.flags[Flag::DONE]) return;
-  const int rd = L.it & 1, wr = rd ^ 1;
-  double tot[2] = {0.0, 0.0};
-  {
-    const double* pu = L.upd_partials + (size_t)rd * 2 * L.pstride;
-    for (int i = threadIdx.x; i < L.n_op; i += kLnVecThreads) tot[0] += __ldcg(L.op_partials + i);
-    for (int i = threadIdx.x; i < L.n_upd; i += kLnVecThreads) tot[1] += __ldcg(pu + i);
-  }
-  block_sum_all<kLnVecThreads, 2>(tot, s_part);
-  const double delta = tot[0], gamma = tot[1];
-  const bool first = (L.it == 0);
-  const double beta = first ? 0.0 : gamma / L.scal[Scal::RZ0 + rd];
-  const double den = first ? delta : delta - beta * gamma / L.scal[Scal::ALPHA + rd];
-  const bool bad = !(den > 0.0);           // K_ff (or the preconditioner) not positive definite along p
-  const double alpha = bad ? 0.0 : gamma / den;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    L.scal[Scal::RZ0 + wr] = gamma;
-    L.scal[Scal::ALPHA + wr] = alpha;
-    L.scal[Scal::PQ] = delta;
-    if (bad) L.flags[Flag::DONE] = 2;
-  }
-  if (bad) return;
-  double v[1] = {0.0};
-  const int64_t n2 = n >> 1;                // ndof = 6 n_nodes is even
-  const double2* z2 = reinterpret_cast<const double2*>(z);
-  const double2* s2 = reinterpret_cast<const double2*>(s);
-  double2* p2 = reinterpret_cast<double2*>(p);
-  double2* q2 = reinterpret_cast<double2*>(q);
-  double2* x2 = reinterpret_cast<double2*>(x);
-  double2* r2 = reinterpret_cast<double2*>(r);
-#pragma unroll 2
-  for (int64_t i = (int64_t)blockIdx.x * kLnVecThreads + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kLnVecThreads) {
-    const double2 zv = z2[i], sv = s2[i];
-    double2 pv = p2[i], qv = q2[i], xv = x2[i], rv = r2[i];
-    pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
-    qv.x = sv.x + beta * qv.x; qv.y = sv.y + beta * qv.y;
-    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
-    rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
-    p2[i] = pv; q2[i] = qv; x2[i] = xv; r2[i] = rv;
-    v[0] += rv.x * rv.x; v[0] += rv.y * rv.y;
-  }
-  block_sum_all<kLnVecThreads, 1>(v, s_part);
-  if (threadIdx.x == 0) L.upd_partials[(size_t)wr * 2 * L.pstride + L.pstride + blockIdx.x] = v[0];
-}
-
 // One CTA per bundle, one warp per line (lines w, w + 4, .. of the bundle): axial residuals a_k = w_k . r_k,
 // the line solve (two scans), the line's amplitude per node -> yl, and the bundle residual rb = sum of the
 // axial residuals of its lines (per-warp sums in line order, then warp order: fixed).
 // A lane holds CH = 4 consecutive entries of the line; affine maps y -> F y + G compose across lanes with a
 // Hillis-Steele scan.
+template <int LW>
 __device__ __forceinline__ void ln_scan_affine_up(double& F, double& G, int lane) {
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const double Fp = __shfl_up_sync(0xffffffffu, F, d), Gp = __shfl_up_sync(0xffffffffu, G, d);
+  for (int d = 1; d < LW; d <<= 1) {
+    const double Fp = __shfl_up_sync(0xffffffffu, F, d, LW), Gp = __shfl_up_sync(0xffffffffu, G, d, LW);
     if (lane >= d) { G = fma(F, Gp, G); F *= Fp; }
   }
 }
+template <int LW>
 __device__ __forceinline__ void ln_scan_affine_down(double& F, double& G, int lane) {
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const double Fp = __shfl_down_sync(0xffffffffu, F, d), Gp = __shfl_down_sync(0xffffffffu, G, d);
-    if (lane + d < 32) { G = fma(F, Gp, G); F *= Fp; }
+  for (int d = 1; d < LW; d <<= 1) {
+    const double Fp = __shfl_down_sync(0xffffffffu, F, d, LW), Gp = __shfl_down_sync(0xffffffffu, G, d, LW);
+    if (lane + d < LW) { G = fma(F, Gp, G); F *= Fp; }
   }
 }
 
-// DIST (row-block partition): the lines are the pieces inside the rank's slab and rb holds the rank's PARTIAL bundle
-// residuals; the last CTA (ticket) stores them into every rank's mail area and releases the sequence flag there.
-template <bool DIST>
-__global__ void __launch_bounds__(kLnThreads)
-ln_solve_kernel(const LnDev T, const double* __restrict__ r, const int* __restrict__ flags, const P2PDev* __restrict__ p2p) {
+// the line solves of one bundle_ptr range by the CTA's warps; leaves the bundle residual in rb[c].  LW lanes share a
+// line (4 consecutive entries each): lines of up to 64 nodes take a half warp, so a warp works on two lines at once.
+// r is read through the L2 (it may have been written by other CTAs of the same launch).
+template <int THREADS, int LW>
+__device__ __forceinline__ double ln_solve_lines(const LnDev& T, const double* r, int f, int l0, int l1) {
   constexpr int CH = kLnMaxLen / 32;
-  __shared__ double s_sum[kLnThreads / 32];
-  if (flags[Flag::DONE]) return;
-  const int rg = blockIdx.x;
-  const int c = T.bundle_ids ? T.bundle_ids[rg] : rg;
-  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = ln_family_of(T, c);
-  const int l0 = T.bundle_ptr[rg], l1 = T.bundle_ptr[rg + 1];
-  double wsum = 0.0;
-  for (int line = l0 + wl; line < l1; line += kLnThreads / 32) {
-    const int lo = T.line_ptr[line], len = T.line_ptr[line + 1] - lo;
-    const int per = (len + 31) >> 5;               // entries per lane (<= CH), consecutive
+  constexpr int GPW = 32 / LW;                       // line groups per warp
+  constexpr int NG = (THREADS / 32) * GPW;           // line groups per CTA
+  const int lane = threadIdx.x & (LW - 1);
+  const int grp = threadIdx.x / LW;
+  double gsum = 0.0;
+  const int nl = l1 - l0;
+  for (int li0 = 0; li0 < nl; li0 += NG) {           // uniform trip count: the shuffles below need the whole warp
+    const int line = l0 + li0 + grp;
+    const bool on = li0 + grp < nl;
+    const int lo = on ? T.line_ptr[line] : 0, len = on ? T.line_ptr[line + 1] - lo : 0;
+    const int per = (len + LW - 1) / LW;             // entries per lane (<= CH), consecutive
     const int k0 = lane * per;
     double a[CH], id[CH], ff[CH], cc[CH];
     int node[CH];
@@ -349,12 +288,12 @@ ln_solve_kernel(const LnDev T, const double* __restrict__ r, const int* __restri
       a[j] = 0.0; id[j] = 0.0; ff[j] = 0.0; cc[j] = 0.0; node[j] = -1;
       if (j < per && k < len) {
         const size_t e = (size_t)(lo + k);
-        node[j] = T.ent_node[e];
+        node[j] = __ldg(T.ent_node + e);
         const double* w = T.ent_w + 3 * e;
         const double* rn = r + 6 * (size_t)node[j];
-        a[j] = w[0] * rn[0] + w[1] * rn[1] + w[2] * rn[2];
+        a[j] = __ldg(w) * __ldcg(rn) + __ldg(w + 1) * __ldcg(rn + 1) + __ldg(w + 2) * __ldcg(rn + 2);
         const double* fc = T.fac + 3 * e;
-        id[j] = fc[0]; ff[j] = fc[1]; cc[j] = fc[2];
+        id[j] = __ldg(fc); ff[j] = __ldg(fc + 1); cc[j] = __ldg(fc + 2);
         lsum += a[j];
       }
     }
@@ -363,8 +302,8 @@ ln_solve_kernel(const LnDev T, const double* __restrict__ r, const int* __restri
 #pragma unroll
     for (int j = 0; j < CH; ++j)
       if (j < per) { G = fma(ff[j], G, a[j] * id[j]); F *= ff[j]; }
-    ln_scan_affine_up(F, G, lane);
-    double yin = __shfl_up_sync(0xffffffffu, G, 1);
+    ln_scan_affine_up<LW>(F, G, lane);
+    double yin = __shfl_up_sync(0xffffffffu, G, 1, LW);
     if (lane == 0) yin = 0.0;
     double y[CH];
 #pragma unroll
@@ -377,286 +316,515 @@ ln_solve_kernel(const LnDev T, const double* __restrict__ r, const int* __restri
 #pragma unroll
     for (int j = CH - 1; j >= 0; --j)
       if (j < per) { G = fma(cc[j], G, y[j]); F *= cc[j]; }
-    ln_scan_affine_down(F, G, lane);
-    double xin = __shfl_down_sync(0xffffffffu, G, 1);
-    if (lane == 31) xin = 0.0;
+    ln_scan_affine_down<LW>(F, G, lane);
+    double xin = __shfl_down_sync(0xffffffffu, G, 1, LW);
+    if (lane == LW - 1) xin = 0.0;
 #pragma unroll
     for (int j = CH - 1; j >= 0; --j)
       if (j < per) {
         xin = fma(cc[j], xin, y[j]);
         if (node[j] >= 0) T.yl[(size_t)f * T.n_nodes + node[j]] = xin;
       }
-    lsum = warp_sum(lsum);
-    wsum += lsum;                                   // valid in lane 0
+#pragma unroll
+    for (int o = LW / 2; o > 0; o >>= 1) lsum += __shfl_down_sync(0xffffffffu, lsum, o, LW);
+    gsum += lsum;                                    // valid in lane 0 of the group; lines in ascending order
   }
-  if (lane == 0) s_sum[wl] = wsum;
+  return gsum;
+}
+
+// persistent kernel: ALL lines dealt round-robin to the line groups (LW lanes) of the whole grid — every group gets
+// n_lines / (groups in the grid) lines instead of a CTA walking its bundles one after the other; the per-line
+// residual sums go to line_sum and the bundles are summed from them (bundle order, line order) where they are used.
+// Lane l of a group holds entries l, l + LW, l + 2 LW, .. (coalesced table reads — with consecutive entries per lane
+// the 40 narrow loads of a lane each touched their own sector and the phase was bound by L1 wavefronts); the two
+// recurrences run as CH rounds of LW-wide affine scans with the carry handed from round to round.
+template <int THREADS, int LW>
+__device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double* r, int cta, int ncta) {
+  constexpr int CH = kLnMaxLen / LW;                  // rounds (LW = 16: 8 rounds cover 128 entries)
+  constexpr int NG = THREADS / LW;
+  const int lane = threadIdx.x & (LW - 1);
+  const int gg = cta * NG + threadIdx.x / LW, tg = ncta * NG;
+  for (int li0 = 0; li0 < T.n_lines; li0 += tg) {     // uniform trip count (shuffles)
+    const int line = li0 + gg;
+    const bool on = line < T.n_lines;
+    const int lo = on ? __ldg(T.line_ptr + line) : 0, len = on ? __ldg(T.line_ptr + line + 1) - lo : 0;
+    const int f = on ? ln_family_of(T, __ldg(T.line_bundle + line)) : 0;
+    int nround = (len + LW - 1) / LW;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, o));   // warp-uniform
+    double g[CH], ff[CH], cc[CH];
+    int node[CH];
+    double lsum = 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      g[j] = 0.0; ff[j] = 0.0; cc[j] = 0.0; node[j] = -1;
+      const int k = j * LW + lane;
+      if (j < nround && k < len) {
+        const size_t e = (size_t)(lo + k);
+        node[j] = __ldg(T.ent_node + e);
+        const double* w = T.ent_w + 3 * e;
+        const double* rn = r + 6 * (size_t)node[j];
+        const double a = __ldg(w) * __ldcg(rn) + __ldg(w + 1) * __ldcg(rn + 1) + __ldg(w + 2) * __ldcg(rn + 2);
+        const double* fc = T.fac + 3 * e;
+        g[j] = a * __ldg(fc); ff[j] = __ldg(fc + 1); cc[j] = __ldg(fc + 2);
+        lsum += a;
+      }
+    }
+    // forward: y_k = g_k + f_k y_{k-1}
+    double carry = 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (j < nround) {
+        double F = ff[j], G = g[j];
+        ln_scan_affine_up<LW>(F, G, lane);
+        g[j] = fma(F, carry, G);                      // y of this entry
+        carry = __shfl_sync(0xffffffffu, g[j], LW - 1, LW);
+      }
+    // backward: x_k = y_k + c_k x_{k+1}
+    carry = 0.0;
+#pragma unroll
+    for (int j = CH - 1; j >= 0; --j)
+      if (j < nround) {
+        double F = cc[j], G = g[j];
+        ln_scan_affine_down<LW>(F, G, lane);
+        const double xk = fma(F, carry, G);
+        carry = __shfl_sync(0xffffffffu, xk, 0, LW);
+        if (node[j] >= 0) T.yl[(size_t)f * T.n_nodes + node[j]] = xk;
+      }
+    // line sum in a fixed order: per lane round by round, then the shuffle tree
+#pragma unroll
+    for (int o = LW / 2; o > 0; o >>= 1) lsum += __shfl_down_sync(0xffffffffu, lsum, o, LW);
+    if (on && lane == 0) {
+      // the group that completes a bundle (integer ticket) adds the bundle's line sums in line order: the value does
+      // not depend on which group that is
+      T.line_sum[line] = lsum;
+      __threadfence();
+      const int c = __ldg(T.line_bundle + line);
+      const int rg = __ldg(T.line_range + line);
+      const int b0 = __ldg(T.bundle_ptr + rg), b1 = __ldg(T.bundle_ptr + rg + 1);
+      if (atomicAdd(T.bundle_cnt + rg, 1) == b1 - b0 - 1) {
+        __threadfence();
+        double t = 0.0;
+        for (int l = b0; l < b1; ++l) t += __ldcg(T.line_sum + l);
+        T.rb[c] = t;
+        T.bundle_cnt[rg] = 0;
+      }
+    }
+  }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void ln_solve_bundle(const LnDev& T, const double* r, int rg, double* s_sum /* THREADS / 16 */) {
+  const int c = T.bundle_ids ? T.bundle_ids[rg] : rg;
+  const int f = ln_family_of(T, c);
+  const int l0 = T.bundle_ptr[rg], l1 = T.bundle_ptr[rg + 1];
+  bool small = true;                                 // every line of the bundle fits a half warp
+  for (int line = l0; line < l1; ++line) small = small && (T.line_ptr[line + 1] - T.line_ptr[line] <= 16 * (kLnMaxLen / 32));
+  int ng;
+  if (small) {
+    const double g = ln_solve_lines<THREADS, 16>(T, r, f, l0, l1);
+    if ((threadIdx.x & 15) == 0) s_sum[threadIdx.x >> 4] = g;
+    ng = THREADS / 16;
+  } else {
+    const double g = ln_solve_lines<THREADS, 32>(T, r, f, l0, l1);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = g;
+    ng = THREADS / 32;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLnThreads / 32; ++w) t += s_sum[w];
+    for (int w = 0; w < ng; ++w) t += s_sum[w];
     T.rb[c] = t;
   }
-  if constexpr (DIST) {
-    __shared__ int s_last;
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const int tk = atomicAdd(p2p->ticket2, 1);
-      s_last = (tk == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;
-    const int par = (int)(seq & 1);
-    for (int pr = 0; pr < p2p->world; ++pr) {
-      double* dst = p2p->peer_rbmail[pr] + (size_t)(p2p->rank * 2 + par) * kLnMaxCoarse;
-      for (int k = threadIdx.x; k < T.n_coarse; k += kLnThreads) dst[k] = __ldcg(T.rb + k);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < p2p->world) st_release_sys(p2p->peer_rbflag[threadIdx.x] + p2p->rank, seq);
-    if (threadIdx.x == 0) *p2p->ticket2 = 0;
-  }
+  __syncthreads();                                   // s_sum is reused by the caller's next bundle
 }
 
-// yb = blockdiag(K_f^-1) rb: one warp per coarse row, the CTA's rows belong to one family (coarse_blk_off).
-// DIST: the family's bundle residuals are first summed over the ranks' mail slots in rank order (identical on every
-// rank) into shared memory, after waiting for every rank's sequence flag.
-template <bool DIST>
-__global__ void __launch_bounds__(kLnCoarseWarps * 32)
-ln_coarse_kernel(const LnDev T, const int* __restrict__ flags, const P2PDev* __restrict__ p2p) {
-  __shared__ double s_rb[DIST ? 1024 : 1];
-  if (flags[Flag::DONE]) return;
-  int f = 0;
-#pragma unroll
-  for (int k = 1; k < kLnMaxFam; ++k) f += ((int)blockIdx.x >= T.coarse_blk_off[k]) ? 1 : 0;
-  const int off = T.fam_off[f], nf = T.fam_off[f + 1] - off;
-  const int lane = threadIdx.x & 31;
-  const int row = ((int)blockIdx.x - T.coarse_blk_off[f]) * kLnCoarseWarps + (threadIdx.x >> 5);
-  if constexpr (DIST) {
-    const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;
-    const int par = (int)(seq & 1);
-    if ((int)threadIdx.x < p2p->world) {
-      long long spins = 0;
-      while (ld_acquire_sys(p2p->my_rbflag + threadIdx.x) != seq) {
-        if (++spins > kSpinLimit) { const_cast<int*>(flags)[Flag::DONE] = 4; break; }
-      }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < nf; k += kLnCoarseWarps * 32) {
-      double t = 0.0;
-      for (int pr = 0; pr < p2p->world; ++pr)
-        t += *reinterpret_cast<const volatile double*>(p2p->my_rbmail + (size_t)(pr * 2 + par) * kLnMaxCoarse + off + k);
-      s_rb[k] = t;
-    }
-    __syncthreads();
-  }
-  if (row >= nf) return;
-  const double* inv_row = T.inv + T.inv_off[f] + (size_t)row * T.fam_pad[f];
-  const double* rb = T.rb + off;
-  double acc = 0.0;
-#pragma unroll 4
-  for (int k = lane; k < nf; k += 32) acc = fma(__ldg(inv_row + k), DIST ? s_rb[k] : __ldcg(rb + k), acc);
-  acc = warp_sum(acc);
-  if (lane == 0) T.yb[off + row] = acc;
-}
+// ---- the whole iteration as ONE persistent kernel (single GPU) --------------------------------------------------
+// Five dependent kernels per iteration (operator, update, line solves, coarse products, prolongation) of 10-30 us
+// each leave a fifth of the iteration in launch gaps and reduction tails (ncu launch list: 75 us of kernels in a
+// 95 us iteration at 1M DOF).  ln_pcg_mega_kernel runs `n_iters` iterations in one cooperative launch: every SM
+// keeps its CTAs resident, the five phases are separated by grid-wide barriers (one atomic arrive + a generation
+// flag, acquire/release at device scope), and every reduction is a "publish partials, barrier, everybody adds them
+// in the same fixed order" — no last-CTA tail, still no float atomics, bit-reproducible.  The host launches again
+// every `check_every` iterations and reads the flags in between.
+constexpr int kMegaThreads = 128;      // the operator phase needs 128 registers: 4 CTAs of 128 threads per SM
 
-// z = omega D^-1 r + sum_f w_f (yl_f + yb[bundle_f]) on the translations of every node; publishes (r, z)
-__global__ void __launch_bounds__(kLnVecThreads)
-ln_prolong_kernel(const LnDev T, const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ z,
-                  int wr, const PcgLink L) {
-  __shared__ double s_part[kLnVecThreads / 32];
-  if (L.flags[Flag::DONE]) return;
-  double g[1] = {0.0};
-  for (int node = blockIdx.x * kLnVecThreads + threadIdx.x; node < T.n_nodes; node += gridDim.x * kLnVecThreads) {
-    const double2* r2 = reinterpret_cast<const double2*>(r + 6 * (size_t)node);
-    const double2* d2 = reinterpret_cast<const double2*>(dinv + 6 * (size_t)node);
-    const double2 ra = r2[0], rb2 = r2[1], rc = r2[2];
-    const double2 da = __ldg(d2), db = __ldg(d2 + 1), dc = __ldg(d2 + 2);
-    double zt[3] = {T.omega * da.x * ra.x, T.omega * da.y * ra.y, T.omega * db.x * rb2.x};
-#pragma unroll
-    for (int f = 0; f < kLnMaxFam; ++f) {
-      const size_t fn = (size_t)f * T.n_nodes + node;
-      const int cb = __ldg(T.node_bundle + fn);
-      if (cb >= 0) {
-        const double amp = T.yl[fn] + __ldcg(T.yb + cb);
-        const double* w = T.node_w + 3 * fn;
-        zt[0] = fma(__ldg(w), amp, zt[0]); zt[1] = fma(__ldg(w + 1), amp, zt[1]); zt[2] = fma(__ldg(w + 2), amp, zt[2]);
-      }
-    }
-    const double z3 = T.omega * db.y * rb2.y, z4 = T.omega * dc.x * rc.x, z5 = T.omega * dc.y * rc.y;
-    double2* zo = reinterpret_cast<double2*>(z + 6 * (size_t)node);
-    zo[0] = make_double2(zt[0], zt[1]); zo[1] = make_double2(zt[2], z3); zo[2] = make_double2(z4, z5);
-    g[0] += ra.x * zt[0] + ra.y * zt[1] + rb2.x * zt[2] + rb2.y * z3 + rc.x * z4 + rc.y * z5;
-  }
-  block_sum_all<kLnVecThreads, 1>(g, s_part);
-  if (threadIdx.x == 0) L.upd_partials[(size_t)wr * 2 * L.pstride + blockIdx.x] = g[0];
-}
+struct MegaArgs {
+  LnDev T;
+  FrameParams P;
+  const int4* pair_rec;
+  const int4* node_rec;
+  const uint8_t* free_mask;
+  const double* dinv;
+  const double* b;
+  double *x, *r, *z, *p, *q, *s;
+  double* part;          // [3][pstride] published partial sums: delta, ||r||^2, gamma
+  double* scal;          // Scal:: slots (carried across launches and mirrored for the host)
+  int* flags;
+  unsigned int* bar;     // [0] arrive counter, [1] generation
+  unsigned long long* phase_ns;   // [8] time spent per phase (CTA 0), accumulated
+  int64_t n;             // ndof
+  int n_nodes, n_ranges, pstride;
+  int it0, n_iters, max_iter, init;
+  double rtol;
+  const P2PDev* p2p;     // row-block partition (DIST): n / n_nodes count the OWNED rows, T.n_nodes all local nodes
+};
 
-// ---- row-block partition (dist.cu): the same iteration with the scalars travelling through the peers' mailboxes ----
-// update(it) over the owned rows: waits for every rank's {delta, gamma, ||r||^2} (posted by the operator kernels,
-// added in rank order: identical on every rank), convergence decision, p, q, x, r; the local ||r||^2 goes to
-// red[RR], the iteration counter advances (last CTA of the ordered reduction).
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-dist_ln_update_kernel(const double* __restrict__ z, const double* __restrict__ s, double* __restrict__ p, double* __restrict__ q,
-                      double* __restrict__ x, double* __restrict__ r, int64_t n, int first, double rtol, double* partials,
-                      int pstride, double* red, int* flags, const P2PDev* __restrict__ p2p) {
-  __shared__ double s_glob[3];
-  if (flags[Flag::DONE]) return;
-  if (threadIdx.x < 32) {
-    const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;
-    const int lane = threadIdx.x;
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-    bool lost = false;
-    if (lane < p2p->world) {
-      const MailSlot* src = p2p->my_mail + (lane * 2 + (int)(seq & 1));
-      long long spins = 0;
-      while (ld_acquire_sys(&src->seq) != seq) {
-        if (++spins > kSpinLimit) { lost = true; break; }
-      }
-      v0 = *reinterpret_cast<const volatile double*>(&src->v[0]);
-      v1 = *reinterpret_cast<const volatile double*>(&src->v[1]);
-      v2 = *reinterpret_cast<const volatile double*>(&src->v[2]);
-    }
-    lost = __any_sync(0xffffffffu, lost);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int pr = 0; pr < p2p->world; ++pr) {
-      a0 += __shfl_sync(0xffffffffu, v0, pr); a1 += __shfl_sync(0xffffffffu, v1, pr); a2 += __shfl_sync(0xffffffffu, v2, pr);
-    }
-    if (lane == 0) { s_glob[0] = a0; s_glob[1] = a1; s_glob[2] = lost ? -1.0 : a2; if (lost) flags[Flag::DONE] = 4; }
-  }
-  __syncthreads();
-  const double delta = s_glob[0], gamma = s_glob[1], rr = s_glob[2];
-  if (rr < 0.0) return;
-  const double tol2 = first ? rtol * rtol * rr : red[Red::TOL2];
-  if (first ? (rr == 0.0) : (rr <= tol2)) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      red[Red::RRFINAL] = rr;
-      if (first) red[Red::BB] = rr;
-      flags[Flag::DONE] = 1;
-    }
-    return;
-  }
-  const double beta = first ? 0.0 : gamma / red[Red::GPREV];
-  const double den = first ? delta : delta - beta * gamma / red[Red::ALPHA];
-  const bool bad = !(den > 0.0);
-  const double alpha = bad ? 0.0 : gamma / den;
-  double rr_new = 0.0;
-  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < n; g += (int64_t)gridDim.x * THREADS) {
-    const double pg = z[g] + beta * p[g];
-    const double qg = s[g] + beta * q[g];
-    const double rg = r[g] - alpha * qg;
-    p[g] = pg; q[g] = qg;
-    x[g] += alpha * pg;
-    r[g] = rg;
-    rr_new += rg * rg;
-  }
-  double mine[1], tot[1];
-  mine[0] = rr_new;
-  if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET1, tot)) {
-    if (threadIdx.x == 0) {
-      red[Red::GPREV] = gamma;
-      red[Red::ALPHA] = alpha;
-      if (first) { red[Red::TOL2] = tol2; red[Red::BB] = rr; }
-      red[Red::RRFINAL] = rr;
-      red[Red::RR] = tot[0];
-      flags[Flag::ITERS] = flags[Flag::ITERS] + 1;
-      if (bad) flags[Flag::DONE] = 2;
-    }
-  }
-}
-
-// prolongation over the owned nodes: z = omega D^-1 r + sum_f w_f (yl_f + yb[bundle_f]); the local (r, z) goes to
-// red[GAMMA].  Phase 1 handles the nodes a neighbour needs: their z goes straight into the neighbours' ghost tails
-// (remote stores) and the last CTA to finish the phase (ticket) stores the few nodes with several destinations and
-// releases the halo flag of the next operator launch at every neighbour — while phase 2, the interior, is still
-// running, so the flag has landed long before the neighbour's operator kernel looks for it.
-__device__ __forceinline__ double ln_prolong_node(const LnDev& T, const double* __restrict__ dinv, const double* __restrict__ r,
-                                                  double* __restrict__ z, int node, double* zt) {
-  const double2* r2 = reinterpret_cast<const double2*>(r + 6 * (size_t)node);
-  const double2* d2 = reinterpret_cast<const double2*>(dinv + 6 * (size_t)node);
-  const double2 ra = r2[0], rb2 = r2[1], rc = r2[2];
-  const double2 da = __ldg(d2), db = __ldg(d2 + 1), dc = __ldg(d2 + 2);
-  zt[0] = T.omega * da.x * ra.x; zt[1] = T.omega * da.y * ra.y; zt[2] = T.omega * db.x * rb2.x;
-  zt[3] = T.omega * db.y * rb2.y; zt[4] = T.omega * dc.x * rc.x; zt[5] = T.omega * dc.y * rc.y;
-#pragma unroll
-  for (int f = 0; f < kLnMaxFam; ++f) {
-    const size_t fn = (size_t)f * T.n_nodes + node;
-    const int cb = __ldg(T.node_bundle + fn);
-    if (cb >= 0) {
-      const double amp = T.yl[fn] + __ldcg(T.yb + cb);
-      const double* w = T.node_w + 3 * fn;
-      zt[0] = fma(__ldg(w), amp, zt[0]); zt[1] = fma(__ldg(w + 1), amp, zt[1]); zt[2] = fma(__ldg(w + 2), amp, zt[2]);
-    }
-  }
-  double2* zo = reinterpret_cast<double2*>(z + 6 * (size_t)node);
-  zo[0] = make_double2(zt[0], zt[1]); zo[1] = make_double2(zt[2], zt[3]); zo[2] = make_double2(zt[4], zt[5]);
-  return ra.x * zt[0] + ra.y * zt[1] + rb2.x * zt[2] + rb2.y * zt[3] + rc.x * zt[4] + rc.y * zt[5];
-}
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-dist_ln_prolong_kernel(const LnDev T, const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ z,
-                       int n_owned, double* partials, int pstride, double* red, int* flags, const P2PDev* __restrict__ p2p) {
-  __shared__ int s_last;
-  if (flags[Flag::DONE]) return;
-  double g = 0.0;
-  // phase 1: boundary nodes
-  bool pushed = false;
-  for (int k = blockIdx.x * THREADS + threadIdx.x; k < p2p->n_bnd; k += gridDim.x * THREADS) {
-    const int node = __ldg(p2p->bnd_nodes + k);
-    double zt[6];
-    g += ln_prolong_node(T, dinv, r, z, node, zt);
-    const int sl = __ldg(p2p->send_slot + node);
-    double* dst = p2p->peer_z[sl >> 28] + (size_t)(sl & 0xFFFFFFF) * 6;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) dst[c] = zt[c];
-    pushed = true;
-  }
-  if (pushed) __threadfence_system();
+__device__ __forceinline__ void mega_barrier(unsigned int* bar, unsigned int nb) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    volatile unsigned int* vgen = bar + 1;
+    const unsigned int gen = *vgen;            // read before arriving
     __threadfence();
-    const int tk = atomicAdd(p2p->ticket3, 1);
-    s_last = (tk == (int)gridDim.x - 1);
+    if (atomicAdd(bar, 1u) == nb - 1) {
+      bar[0] = 0;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*vgen == gen) { }
+    }
+    __threadfence();
   }
   __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int e = threadIdx.x; e < p2p->n_extra * 6; e += THREADS) {
-      const int i = e / 6, c = e - i * 6;
-      const int node = p2p->extra[2 * i], sl = p2p->extra[2 * i + 1];
-      p2p->peer_z[sl >> 28][(size_t)(sl & 0xFFFFFFF) * 6 + c] = __ldcg(z + (size_t)node * 6 + c);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < p2p->n_nbr) {
-      const long long seq = p2p->base[0] + flags[Flag::ITERS] + 1;
-      st_release_sys(p2p->peer_halo_flag[threadIdx.x] + p2p->rank, seq);
-    }
-    if (threadIdx.x == 0) *p2p->ticket3 = 0;
-  }
-  // phase 2: interior nodes
-  for (int node = blockIdx.x * THREADS + threadIdx.x; node < n_owned; node += gridDim.x * THREADS) {
-    if (__ldg(p2p->send_slot + node) >= 0) continue;
-    double zt[6];
-    g += ln_prolong_node(T, dinv, r, z, node, zt);
-  }
-  double mine[1], tot[1];
-  mine[0] = g;
-  if (grid_reduce<THREADS, 1>(mine, partials, pstride, flags + Flag::TICKET2, tot)) {
-    if (threadIdx.x == 0) red[Red::GAMMA] = tot[0];
-  }
 }
 
-// one CTA: the operator-side decision alone (host poll), as pcg_decide_linked_kernel
-__global__ void __launch_bounds__(128)
-ln_decide_kernel(const PcgLink L) {
-  __shared__ double s_part[2 * 128 / 32];
-  if (L.flags[Flag::DONE]) return;
-  pcg_link_decide<128>(L, s_part);
+__device__ __forceinline__ unsigned long long mega_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// fixed-order sum of `cnt` published partials, identical in every thread of every CTA
+template <int THREADS>
+__device__ __forceinline__ double mega_total(const double* part, int cnt, double* s_part) {
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < cnt; i += THREADS) v[0] += __ldcg(part + i);
+  block_sum_all<THREADS, 1>(v, s_part);
+  return v[0];
+}
+
+// DIST (one rank of a row-block partition, dist.cu): the same kernel on the owned rows; the three exchanges with the
+// other GPUs happen INSIDE the launch, through peer memory:
+//   halo        the prolongation handles the nodes a neighbour needs first and releases the neighbours' halo flags
+//               while the interior is still running; the operator phase polls its own flags before it starts;
+//   scalars     after the operator's barrier CTA 0 stores the rank's {delta, gamma, ||r||^2} into every rank's
+//               mailbox; every CTA adds the world's entries in rank order (identical on every rank);
+//   coarse      after the line phase CTA p stores the rank's partial bundle residuals into rank p's mail area; the
+//               coarse phase adds the world's partials in rank order.
+// Sequence numbers = per-solve base + iteration; waits are bounded (a lost peer sets DONE = 4).
+template <bool DIST>
+__global__ void __launch_bounds__(kMegaThreads, 4)
+ln_pcg_mega_kernel(const MegaArgs A) {
+  __shared__ double s_part[2 * kMegaThreads / 32];
+  __shared__ double s_rb[DIST ? 1024 : 1];
+  __shared__ double s_glob[3];
+  __shared__ int s_flag;
+  const LnDev& T = A.T;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const unsigned int nb = gridDim.x;
+  double* part_delta = A.part;
+  double* part_rr = A.part + A.pstride;
+  double* part_gamma = A.part + 2 * (size_t)A.pstride;
+  const bool clock = (cta == 0 && threadIdx.x == 0);
+  unsigned long long t_last = clock ? mega_now() : 0ull;
+  auto lap = [&](int ph) {
+    if (clock) { const unsigned long long t = mega_now(); A.phase_ns[ph] += t - t_last; t_last = t; }
+  };
+  // one application of the preconditioner: z = M^-1 r, publishes the (r, z) partials.  DIST: `seq` numbers the
+  // coarse-residual exchange of this application, seq + 1 the halo the next operator phase waits for.
+  auto precond = [&](long long seq) {
+    ln_solve_lines_flat<kMegaThreads, 16>(T, A.r, cta, ncta);
+    mega_barrier(A.bar, nb);
+    lap(2);
+    if constexpr (DIST) {
+      const P2PDev* pd = A.p2p;
+      const int par = (int)(seq & 1);
+      if (cta < pd->world) {                      // CTA p -> rank p
+        double* dst = pd->peer_rbmail[cta] + (size_t)(pd->rank * 2 + par) * kLnMaxCoarse;
+        for (int k = threadIdx.x; k < T.n_coarse; k += kMegaThreads) dst[k] = __ldcg(T.rb + k);
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence_system(); st_release_sys(pd->peer_rbflag[cta] + pd->rank, seq); }
+      }
+      // only CTA 0 polls the flags the peers write (hundreds of CTAs polling one line cost ~20 us per exchange); the
+      // grid barrier hands the visibility on to everybody else
+      if (cta == 0 && (int)threadIdx.x < pd->world) {
+        long long spins = 0;
+        while (ld_acquire_sys(pd->my_rbflag + threadIdx.x) != seq) {
+          if (++spins > kSpinLimit) { A.flags[Flag::DONE] = 4; break; }
+        }
+      }
+      mega_barrier(A.bar, nb);
+    }
+    if constexpr (DIST) {
+      // coarse products; the family's bundle residuals = sum over the ranks' partials (rank order) in shared memory
+      constexpr int NW = kMegaThreads / 32;
+      const P2PDev* pd = A.p2p;
+      const int par = (int)(seq & 1);
+      const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+      for (int c0 = cta * NW; c0 < T.n_coarse; c0 += ncta * NW) {
+        const int c = c0 + wl;
+        const int f_lo = ln_family_of(T, c0), f_hi = ln_family_of(T, min(c0 + NW - 1, T.n_coarse - 1));
+        for (int f = f_lo; f <= f_hi; ++f) {
+          const int off = T.fam_off[f], nf = T.fam_off[f + 1] - off;
+          for (int k = threadIdx.x; k < nf; k += kMegaThreads) {
+            double t = 0.0;
+            for (int pr = 0; pr < pd->world; ++pr)
+              t += *reinterpret_cast<const volatile double*>(pd->my_rbmail + (size_t)(pr * 2 + par) * kLnMaxCoarse + off + k);
+            s_rb[k] = t;
+          }
+          __syncthreads();
+          if (c < T.n_coarse && ln_family_of(T, c) == f) {
+            const double* inv_row = T.inv + T.inv_off[f] + (size_t)(c - off) * T.fam_pad[f];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = lane;
+#pragma unroll 2
+            for (; k + 96 < nf; k += 128) {
+              const double m0 = __ldg(inv_row + k), m1 = __ldg(inv_row + k + 32), m2 = __ldg(inv_row + k + 64), m3 = __ldg(inv_row + k + 96);
+              a0 = fma(m0, s_rb[k], a0); a1 = fma(m1, s_rb[k + 32], a1);
+              a2 = fma(m2, s_rb[k + 64], a2); a3 = fma(m3, s_rb[k + 96], a3);
+            }
+            for (; k < nf; k += 32) a0 = fma(__ldg(inv_row + k), s_rb[k], a0);
+            const double acc = warp_sum((a0 + a1) + (a2 + a3));
+            if (lane == 0) T.yb[c] = acc;
+          }
+          __syncthreads();
+        }
+      }
+    } else {   // coarse products: one warp per row, rows dealt to the grid's warps
+      const int lane = threadIdx.x & 31;
+      const int nwarp = ncta * (kMegaThreads / 32);
+      for (int c = cta * (kMegaThreads / 32) + (threadIdx.x >> 5); c < T.n_coarse; c += nwarp) {
+        const int f = ln_family_of(T, c);
+        const int off = T.fam_off[f], nf = T.fam_off[f + 1] - off;
+        const double* inv_row = T.inv + T.inv_off[f] + (size_t)(c - off) * T.fam_pad[f];
+        const double* rb = T.rb + off;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = lane;
+#pragma unroll 2
+        for (; k + 96 < nf; k += 128) {
+          const double m0 = __ldg(inv_row + k), m1 = __ldg(inv_row + k + 32), m2 = __ldg(inv_row + k + 64), m3 = __ldg(inv_row + k + 96);
+          a0 = fma(m0, __ldcg(rb + k), a0); a1 = fma(m1, __ldcg(rb + k + 32), a1);
+          a2 = fma(m2, __ldcg(rb + k + 64), a2); a3 = fma(m3, __ldcg(rb + k + 96), a3);
+        }
+        for (; k < nf; k += 32) a0 = fma(__ldg(inv_row + k), __ldcg(rb + k), a0);
+        const double acc = warp_sum((a0 + a1) + (a2 + a3));
+        if (lane == 0) T.yb[c] = acc;
+      }
+    }
+    mega_barrier(A.bar, nb);
+    lap(3);
+    double g = 0.0;
+    auto prolong_node = [&](int node, double* zt) {
+      // every load of the node issued before the first dependent one (the yb gather): two latencies per node
+      const double2* r2 = reinterpret_cast<const double2*>(A.r + 6 * (size_t)node);
+      const double2* d2 = reinterpret_cast<const double2*>(A.dinv + 6 * (size_t)node);
+      const double2 ra = r2[0], rb2 = r2[1], rc = r2[2];
+      const double2 da = __ldg(d2), db = __ldg(d2 + 1), dc = __ldg(d2 + 2);
+      int cb[kLnMaxFam];
+      double yl[kLnMaxFam], w[kLnMaxFam][3];
+#pragma unroll
+      for (int f = 0; f < kLnMaxFam; ++f) {
+        const size_t fn = (size_t)f * T.n_nodes + node;
+        cb[f] = __ldg(T.node_bundle + fn);
+        yl[f] = __ldcg(T.yl + fn);                    // zero where the node has no line in the family
+        w[f][0] = __ldg(T.node_w + 3 * fn); w[f][1] = __ldg(T.node_w + 3 * fn + 1); w[f][2] = __ldg(T.node_w + 3 * fn + 2);
+      }
+      zt[0] = T.omega * da.x * ra.x; zt[1] = T.omega * da.y * ra.y; zt[2] = T.omega * db.x * rb2.x;
+#pragma unroll
+      for (int f = 0; f < kLnMaxFam; ++f) {
+        const double amp = yl[f] + __ldcg(T.yb + max(cb[f], 0));      // w is zero where cb < 0
+        zt[0] = fma(w[f][0], amp, zt[0]); zt[1] = fma(w[f][1], amp, zt[1]); zt[2] = fma(w[f][2], amp, zt[2]);
+      }
+      zt[3] = T.omega * db.y * rb2.y; zt[4] = T.omega * dc.x * rc.x; zt[5] = T.omega * dc.y * rc.y;
+      double2* zo = reinterpret_cast<double2*>(A.z + 6 * (size_t)node);
+      zo[0] = make_double2(zt[0], zt[1]); zo[1] = make_double2(zt[2], zt[3]); zo[2] = make_double2(zt[4], zt[5]);
+      g += ra.x * zt[0] + ra.y * zt[1] + rb2.x * zt[2] + rb2.y * zt[3] + rc.x * zt[4] + rc.y * zt[5];
+    };
+    if constexpr (DIST) {
+      // the nodes a neighbour needs first: z straight into the neighbours' ghost tails, halo flags released by the
+      // last CTA to finish them (ticket) while everybody moves on to the interior
+      const P2PDev* pd = A.p2p;
+      bool pushed = false;
+      for (int k = cta * kMegaThreads + threadIdx.x; k < pd->n_bnd; k += ncta * kMegaThreads) {
+        const int node = __ldg(pd->bnd_nodes + k);
+        double zt[6];
+        prolong_node(node, zt);
+        const int sl = __ldg(pd->send_slot + node);
+        double* dst = pd->peer_z[sl >> 28] + (size_t)(sl & 0xFFFFFFF) * 6;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dst[c] = zt[c];
+        pushed = true;
+      }
+      const int any_pushed = __syncthreads_or(pushed ? 1 : 0);
+      if (threadIdx.x == 0) {
+        if (any_pushed) __threadfence_system();     // the CTA's remote stores (ordered before by the barrier) are out
+        else __threadfence();
+        s_flag = (atomicAdd(pd->ticket3, 1) == (int)nb - 1);
+      }
+      __syncthreads();
+      if (s_flag) {
+        __threadfence();
+        for (int e = threadIdx.x; e < pd->n_extra * 6; e += kMegaThreads) {
+          const int i = e / 6, c = e - i * 6;
+          const int node = pd->extra[2 * i], sl = pd->extra[2 * i + 1];
+          pd->peer_z[sl >> 28][(size_t)(sl & 0xFFFFFFF) * 6 + c] = __ldcg(A.z + (size_t)node * 6 + c);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < pd->n_nbr) { __threadfence_system(); st_release_sys(pd->peer_halo_flag[threadIdx.x] + pd->rank, seq + 1); }
+        if (threadIdx.x == 0) *pd->ticket3 = 0;
+      }
+      for (int node = cta * kMegaThreads + threadIdx.x; node < A.n_nodes; node += ncta * kMegaThreads) {
+        if (__ldg(pd->send_slot + node) >= 0) continue;
+        double zt[6];
+        prolong_node(node, zt);
+      }
+    } else {
+      for (int node = cta * kMegaThreads + threadIdx.x; node < A.n_nodes; node += ncta * kMegaThreads) {
+        double zt[6];
+        prolong_node(node, zt);
+      }
+    }
+    double v[1] = {g};
+    block_sum_all<kMegaThreads, 1>(v, s_part);
+    if (threadIdx.x == 0) part_gamma[cta] = v[0];
+    if constexpr (DIST) {
+      // the neighbours' halo for the next operator phase: CTA 0 waits, the barrier below passes it on
+      const P2PDev* pd = A.p2p;
+      if (cta == 0 && (int)threadIdx.x < pd->n_nbr) {
+        long long spins = 0;
+        while (ld_acquire_sys(pd->my_halo_flag + pd->nbr[threadIdx.x]) < seq + 1) {
+          if (++spins > kSpinLimit) { A.flags[Flag::DONE] = 4; break; }
+        }
+      }
+    }
+    mega_barrier(A.bar, nb);
+    lap(4);
+  };
+
+  double gamma_prev = A.scal[Scal::RZ0], alpha_prev = A.scal[Scal::ALPHA], tol2 = A.scal[Scal::TOL2];
+  if (A.init) {
+    // x = 0, r = b, p = q = 0; ||b||^2; z_0 = M^-1 r_0
+    double v[1] = {0.0};
+    for (int64_t g = (int64_t)cta * kMegaThreads + threadIdx.x; g < A.n; g += (int64_t)ncta * kMegaThreads) {
+      const double bg = A.b[g];
+      A.x[g] = 0.0; A.r[g] = bg; A.p[g] = 0.0; A.q[g] = 0.0;
+      v[0] += bg * bg;
+    }
+    block_sum_all<kMegaThreads, 1>(v, s_part);
+    if (threadIdx.x == 0) part_rr[cta] = v[0];
+    mega_barrier(A.bar, nb);
+    precond(DIST ? A.p2p->base[0] : 0);
+  }
+  int it = A.it0, done = 0;
+  double rr = 0.0;
+  for (int k = 0; k < A.n_iters; ++k, ++it) {
+    // scalars of the state after `it` updates: (r, z) and ||r||^2, same value in every thread of every CTA
+    double gamma = mega_total<kMegaThreads>(part_gamma, ncta, s_part);
+    rr = mega_total<kMegaThreads>(part_rr, ncta, s_part);
+    double delta;
+    if constexpr (!DIST) {
+      if (it == 0) {
+        tol2 = A.rtol * A.rtol * rr;
+        if (clock) { A.scal[Scal::BB] = rr; A.scal[Scal::TOL2] = tol2; }
+        if (rr == 0.0) done = 1;               // zero load: u = 0 is the answer
+      } else if (rr <= tol2) done = 1;
+      else if (it >= A.max_iter) done = 3;
+      if (done) break;
+    } else {
+      // (the halo of z has landed: CTA 0 waited for the neighbours' flags before the barrier that closed the prolongation)
+    }
+    // operator: s = A z, publishes (z, s)
+    {
+      double v[1];
+      v[0] = ebe_nodes_phase<kMegaThreads>(A.P, A.pair_rec, A.node_rec, A.n_nodes, A.free_mask, A.z, A.s, cta, ncta);
+      block_sum_all<kMegaThreads, 1>(v, s_part);
+      if (threadIdx.x == 0) part_delta[cta] = v[0];
+    }
+    mega_barrier(A.bar, nb);
+    lap(0);
+    delta = mega_total<kMegaThreads>(part_delta, ncta, s_part);
+    if constexpr (DIST) {
+      // {delta, gamma, ||r||^2} of the world: CTA 0 posts this rank's, every CTA adds all ranks' in rank order
+      const P2PDev* pd = A.p2p;
+      const long long seq = pd->base[0] + it + 1;
+      if (cta == 0 && (int)threadIdx.x < pd->world) {
+        MailSlot* dst = pd->peer_mail[threadIdx.x] + (pd->rank * 2 + (int)(seq & 1));
+        dst->v[0] = delta; dst->v[1] = gamma; dst->v[2] = rr; dst->v[3] = 0.0;
+        __threadfence_system();
+        st_release_sys(&dst->seq, seq);
+        const MailSlot* src = pd->my_mail + (threadIdx.x * 2 + (int)(seq & 1));
+        long long spins = 0;
+        while (ld_acquire_sys(&src->seq) != seq) {
+          if (++spins > kSpinLimit) { A.flags[Flag::DONE] = 4; break; }
+        }
+      }
+      mega_barrier(A.bar, nb);                      // CTA 0 arrives once every rank's entry has landed
+      if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (lane < pd->world) {
+          const MailSlot* src = pd->my_mail + (lane * 2 + (int)(seq & 1));
+          v0 = *reinterpret_cast<const volatile double*>(&src->v[0]);
+          v1 = *reinterpret_cast<const volatile double*>(&src->v[1]);
+          v2 = *reinterpret_cast<const volatile double*>(&src->v[2]);
+        }
+        const bool lost = (*reinterpret_cast<volatile int*>(A.flags + Flag::DONE) == 4);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int pr = 0; pr < pd->world; ++pr) {
+          a0 += __shfl_sync(0xffffffffu, v0, pr); a1 += __shfl_sync(0xffffffffu, v1, pr); a2 += __shfl_sync(0xffffffffu, v2, pr);
+        }
+        if (lane == 0) { s_glob[0] = a0; s_glob[1] = a1; s_glob[2] = lost ? -1.0 : a2; }
+      }
+      __syncthreads();
+      delta = s_glob[0]; gamma = s_glob[1]; rr = s_glob[2];
+      __syncthreads();
+      if (rr < 0.0) { done = 4; break; }          // a peer never answered
+      if (it == 0) {
+        tol2 = A.rtol * A.rtol * rr;
+        if (clock) { A.scal[Scal::BB] = rr; A.scal[Scal::TOL2] = tol2; }
+        if (rr == 0.0) done = 1;
+      } else if (rr <= tol2) done = 1;
+      else if (it >= A.max_iter) done = 3;
+      if (done) break;
+    }
+    const double beta = (it == 0) ? 0.0 : gamma / gamma_prev;
+    const double den = (it == 0) ? delta : delta - beta * gamma / alpha_prev;
+    if (!(den > 0.0)) { done = 2; break; }     // K_ff (or the preconditioner) not positive definite along p
+    const double alpha = gamma / den;
+    gamma_prev = gamma; alpha_prev = alpha;
+    {
+      double v[1] = {0.0};
+      const int64_t n2 = A.n >> 1;                // ndof = 6 n_nodes is even
+      const double2* z2 = reinterpret_cast<const double2*>(A.z);
+      const double2* s2 = reinterpret_cast<const double2*>(A.s);
+      double2* p2 = reinterpret_cast<double2*>(A.p);
+      double2* q2 = reinterpret_cast<double2*>(A.q);
+      double2* x2 = reinterpret_cast<double2*>(A.x);
+      double2* r2 = reinterpret_cast<double2*>(A.r);
+#pragma unroll 2
+      for (int64_t i = (int64_t)cta * kMegaThreads + threadIdx.x; i < n2; i += (int64_t)ncta * kMegaThreads) {
+        const double2 zv = z2[i], sv = s2[i];
+        double2 pv = p2[i], qv = q2[i], xv = x2[i], rv = r2[i];
+        pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
+        qv.x = sv.x + beta * qv.x; qv.y = sv.y + beta * qv.y;
+        xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+        rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
+        p2[i] = pv; q2[i] = qv; x2[i] = xv; r2[i] = rv;
+        v[0] += rv.x * rv.x; v[0] += rv.y * rv.y;
+      }
+      block_sum_all<kMegaThreads, 1>(v, s_part);
+      if (threadIdx.x == 0) part_rr[cta] = v[0];
+    }
+    mega_barrier(A.bar, nb);
+    lap(1);
+    precond(DIST ? A.p2p->base[0] + it + 1 : 0);
+  }
+  if (clock) {
+    A.scal[Scal::RZ0] = gamma_prev; A.scal[Scal::ALPHA] = alpha_prev;
+    if (done) A.scal[Scal::RR] = rr;
+    A.flags[Flag::ITERS] = it;
+    if (done) A.flags[Flag::DONE] = done;
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -693,6 +861,18 @@ static int upload_line_tables(femb_handle* h) {
     FEMB_CUDA(h, h->ln_yl.alloc((size_t)kLnMaxFam * h->n_nodes));
     FEMB_CUDA(h, h->ln_rb.alloc((size_t)S.n_coarse));
     FEMB_CUDA(h, h->ln_yb.alloc((size_t)S.n_coarse));
+    FEMB_CUDA(h, h->ln_line_sum.alloc((size_t)S.n_lines));
+    FEMB_CUDA(h, h->ln_bundle_cnt.alloc((size_t)std::max<size_t>(1, S.bundle_ptr.size())));
+    {
+      std::vector<int32_t> lr((size_t)S.n_lines, 0);
+      for (size_t rg = 0; rg + 1 < S.bundle_ptr.size(); ++rg)
+        for (int32_t l = S.bundle_ptr[rg]; l < S.bundle_ptr[rg + 1]; ++l) lr[l] = (int32_t)rg;
+      FEMB_CUDA(h, upload(h->ln_line_range, lr, h->stream));
+      FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    FEMB_CUDA(h, cudaMemsetAsync(h->ln_bundle_cnt.p, 0, h->ln_bundle_cnt.bytes(), h->stream));
+    h->ln_max_len = 0;
+    for (int32_t a = 0; a < S.n_lines; ++a) h->ln_max_len = std::max(h->ln_max_len, S.line_ptr[a + 1] - S.line_ptr[a]);
     int64_t off = 0, gmax = 1;
     for (int f = 0; f < kLnMaxFam; ++f) {
       const int nf = S.fam_off[f + 1] - S.fam_off[f];
@@ -749,6 +929,7 @@ static LnDev ln_dev(const femb_handle* h) {
   T.node_bundle = h->ln_node_bundle.p; T.bundle_ids = h->ln_bundle_ids.p; T.node_dir = h->ln_node_dir.p;
   T.ent_w = h->ln_ent_w.p; T.node_w = h->ln_node_w.p; T.fac = h->ln_fac.p;
   T.yl = h->ln_yl.p; T.rb = h->ln_rb.p; T.yb = h->ln_yb.p; T.inv = h->ln_inv.p;
+  T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p; T.line_range = h->ln_line_range.p;
   for (int f = 0; f < kLnMaxFam; ++f) { T.inv_off[f] = h->ln_inv_off[f]; T.fam_pad[f] = h->ln_fam_pad[f]; }
   T.coarse_blk_off[0] = 0;
   for (int f = 0; f <= kLnMaxFam; ++f) {
@@ -844,8 +1025,86 @@ bool lines_applicable(femb_handle* h, const femb_solve_opts& o) {
   return o.precond == FEMB_PRECOND_LINES || h->line_sym.coverage >= kLnAutoCoverage;
 }
 
-int pcg_lines(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
+// launches of the persistent kernel until the solve is over; `dist`: this rank's part of a row-block partition
+static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st, bool dist) {
   const int pstride = h->num_sms * 8;
+  FEMB_CUDA(h, h->fpartials.ensure((size_t)pstride * 6));
+  FEMB_CUDA(h, h->mega_state.ensure(16));          // [0] barrier words, [2..] phase clocks (8 x u64)
+  FEMB_CUDA(h, cudaMemsetAsync(h->mega_state.p, 0, h->mega_state.bytes(), h->stream));
+  FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
+  FEMB_CUDA(h, cudaMemsetAsync(h->scal.p, 0, sizeof(double) * Scal::COUNT, h->stream));
+  static int per_sm[2] = {0, 0};
+  if (!per_sm[dist]) {
+    if (dist) FEMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], ln_pcg_mega_kernel<true>, kMegaThreads, 0));
+    else FEMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], ln_pcg_mega_kernel<false>, kMegaThreads, 0));
+    per_sm[dist] = std::max(1, std::min(per_sm[dist], 8));      // the partial arrays hold num_sms * 8 entries
+  }
+  MegaArgs A;
+  A.T = ln_dev(h);
+  A.P.xyz = h->xyz.p; A.P.conn = h->conn.p; A.P.elem_sec = h->elem_sec.p; A.P.sec_props = h->sec_props.p;
+  A.P.E = h->E; A.P.G = h->G; A.P.rho = h->rho;
+  A.pair_rec = reinterpret_cast<const int4*>(h->pair_rec.p);
+  A.node_rec = reinterpret_cast<const int4*>(h->pair_node_rec.p);
+  A.free_mask = h->free_mask.p; A.dinv = h->Dinv.p; A.b = d_b;
+  A.x = h->x.p; A.r = h->r.p; A.z = h->z.p; A.p = h->p.p; A.q = h->q.p; A.s = h->s.p;
+  A.part = h->fpartials.p; A.scal = h->scal.p; A.flags = h->flags.p;
+  A.bar = reinterpret_cast<unsigned int*>(h->mega_state.p);
+  A.phase_ns = h->mega_state.p + 2;
+  A.n_nodes = (int)(dist ? h->n_owned_nodes : h->n_nodes);
+  A.n = (int64_t)A.n_nodes * 6;
+  A.n_ranges = h->ln_n_ranges; A.pstride = pstride;
+  A.max_iter = o.max_iter; A.rtol = o.rtol;
+  A.p2p = dist ? reinterpret_cast<const P2PDev*>(h->p2p_dev_copy.p) : nullptr;
+  const int grid = h->num_sms * per_sm[dist];
+  struct Peek { int32_t flags[Flag::COUNT]; double scal[Scal::COUNT]; unsigned long long ns[8]; };
+  Peek* peek = reinterpret_cast<Peek*>(h->pinned);
+  const int check = o.check_every > 0 ? o.check_every : 50;
+  int it = 0, done = 0, launches = 0;
+  while (!done && it <= o.max_iter) {
+    // one more pass than updates: the pass that finds ||r|| <= tol (or the cap) leaves through the decision
+    A.it0 = it; A.n_iters = std::min(check, o.max_iter + 1 - it); A.init = (it == 0) ? 1 : 0;
+    void* args[] = {(void*)&A};
+    const void* fn = dist ? (const void*)ln_pcg_mega_kernel<true> : (const void*)ln_pcg_mega_kernel<false>;
+    FEMB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kMegaThreads), args, 0, h->stream));
+    h->launches++;
+    ++launches;
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaMemcpyAsync(peek->scal, h->scal.p, sizeof(peek->scal), cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    done = peek->flags[Flag::DONE];
+    it = peek->flags[Flag::ITERS];
+    if (!done && A.n_iters <= 0) break;
+  }
+  FEMB_CUDA(h, cudaMemcpyAsync(peek->ns, h->mega_state.p + 2, sizeof(peek->ns), cudaMemcpyDeviceToHost, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (st) {
+    st->method_used = FEMB_SOLVER_PCG;
+    st->op_used = FEMB_OP_EBE;
+    st->coarse_dim = A.T.n_coarse;
+    st->precond_used = FEMB_PRECOND_LINES;
+    st->iterations = peek->flags[Flag::ITERS];
+    st->converged = (done == 1);
+    st->spmv_launches = peek->flags[Flag::ITERS];      // operator passes (phases of the persistent kernel)
+    const double bb = peek->scal[Scal::BB];
+    st->rel_residual = bb > 0.0 ? sqrt(peek->scal[Scal::RR] / bb) : 0.0;
+    // phase clocks of CTA 0 (globaltimer): operator | update + line solves + coarse products + prolongation
+    st->spmv_ms = (double)peek->ns[0] * 1e-6;
+    st->update_ms = (double)(peek->ns[1] + peek->ns[2] + peek->ns[3] + peek->ns[4]) * 1e-6;
+    st->spmv_timed = peek->flags[Flag::ITERS];
+    if (getenv("FEMB_TRACE"))
+      fprintf(stderr, "[femb trace] persistent PCG: %d iterations in %d launches; per-iteration phase times (CTA 0): operator %.2f us, "
+              "update %.2f, line solves %.2f, coarse %.2f, prolongation %.2f\n", st->iterations, launches,
+              peek->ns[0] * 1e-3 / std::max(1, st->iterations), peek->ns[1] * 1e-3 / std::max(1, st->iterations),
+              peek->ns[2] * 1e-3 / std::max(1, st->iterations), peek->ns[3] * 1e-3 / std::max(1, st->iterations),
+              peek->ns[4] * 1e-3 / std::max(1, st->iterations));
+  }
+  if (done == 4) return fail(h, FEMB_ERR_CUDA, "peer-memory exchange timed out waiting for another rank");
+  if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");
+  if (done != 1) return fail(h, FEMB_ERR_NOT_CONVERGED, "PCG did not reach rtol within max_iter");
+  return FEMB_OK;
+}
+
+int pcg_lines(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
   int rc = setup_precond_public(h, FEMB_PRECOND_JACOBI);
   if (rc) return rc;
   rc = ensure_line_numeric(h);
@@ -856,98 +1115,11 @@ int pcg_lines(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_
     oj.precond = FEMB_PRECOND_JACOBI;
     return pcg_solve_rhs(h, oj, d_b, st);
   }
-  const int64_t n = h->ndof;
-  FEMB_CUDA(h, h->fpartials.ensure((size_t)pstride * 6));
-  FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
-  FEMB_CUDA(h, cudaMemsetAsync(h->scal.p, 0, sizeof(double) * Scal::COUNT, h->stream));
-  const LnDev T = ln_dev(h);
-  // update and prolong publish into the same partial arrays: one grid size for both
-  const int grid_v = std::max(1, std::min((int)((h->n_nodes + kLnVecThreads - 1) / kLnVecThreads), h->num_sms * 4));
-  const int grid_c = T.coarse_blk_off[kLnMaxFam];
-  const int grid_s = h->ln_n_ranges;
-  PcgLink L;
-  L.upd_partials = h->fpartials.p; L.op_partials = h->fpartials.p + (size_t)4 * pstride;
-  L.scal = h->scal.p; L.flags = h->flags.p;
-  L.n_upd = grid_v; L.n_op = ebe_grid(h, 1, h->n_nodes); L.pstride = pstride;
-  L.it = 0; L.max_iter = o.max_iter; L.rtol = o.rtol;
-  auto precond = [&](int wr_buf) {
-    ln_solve_kernel<false><<<grid_s, kLnThreads, 0, h->stream>>>(T, h->r.p, h->flags.p, nullptr);
-    ln_coarse_kernel<false><<<grid_c, kLnCoarseWarps * 32, 0, h->stream>>>(T, h->flags.p, nullptr);
-    ln_prolong_kernel<<<grid_v, kLnVecThreads, 0, h->stream>>>(T, h->Dinv.p, h->r.p, h->z.p, wr_buf, L);
-    h->launches += 3;
-  };
-  ln_init_kernel<<<grid_v, kLnVecThreads, 0, h->stream>>>(d_b, h->x.p, h->r.p, h->p.p, h->q.p, n, L);
-  h->launches++;
-  precond(0);
-  FEMB_CUDA(h, cudaGetLastError());
-  struct Peek { int32_t flags[Flag::COUNT]; double scal[Scal::COUNT]; };
-  Peek* peek = reinterpret_cast<Peek*>(h->pinned);
-  const int check = o.check_every > 0 ? o.check_every : 50;
-  const bool prof = o.profile != 0;
-  std::vector<cudaEvent_t> evs;
-  int spmv_launches = 0, it = 0, done = 0;
-  while (!done && it < o.max_iter) {
-    const int batch = std::min(check, o.max_iter - it);
-    for (int k = 0; k < batch; ++k, ++it) {
-      const bool timed = prof && (it % o.profile) == 0;
-      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-      if (timed) {
-        if (h->ev_pool.size() < evs.size() + 3) {
-          const size_t old = h->ev_pool.size();
-          h->ev_pool.resize(old + 768);
-          for (size_t e = old; e < h->ev_pool.size(); ++e) cudaEventCreate(&h->ev_pool[e]);
-        }
-        e0 = h->ev_pool[evs.size()]; e1 = h->ev_pool[evs.size() + 1]; e2 = h->ev_pool[evs.size() + 2];
-        cudaEventRecord(e0, h->stream);
-      }
-      L.it = it;
-      rc = launch_ebe(h, h->z.p, h->s.p, 1, true, nullptr, nullptr, nullptr, nullptr, &L);
-      if (timed) cudaEventRecord(e1, h->stream);
-      if (rc) return rc;
-      ++spmv_launches;
-      ln_update_kernel<<<grid_v, kLnVecThreads, 0, h->stream>>>(h->z.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, n, L);
-      h->launches++;
-      precond((it & 1) ^ 1);
-      if (timed) { cudaEventRecord(e2, h->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); }
-    }
-    L.it = it;
-    ln_decide_kernel<<<1, 128, 0, h->stream>>>(L);
-    h->launches++;
-    FEMB_CUDA(h, cudaGetLastError());
-    FEMB_CUDA(h, cudaMemcpyAsync(peek->flags, h->flags.p, sizeof(peek->flags), cudaMemcpyDeviceToHost, h->stream));
-    FEMB_CUDA(h, cudaMemcpyAsync(peek->scal, h->scal.p, sizeof(peek->scal), cudaMemcpyDeviceToHost, h->stream));
-    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
-    done = peek->flags[Flag::DONE];
-  }
-  if (st) {
-    st->method_used = FEMB_SOLVER_PCG;
-    st->op_used = FEMB_OP_EBE;
-    st->coarse_dim = T.n_coarse;
-    st->precond_used = FEMB_PRECOND_LINES;
-    st->iterations = peek->flags[Flag::ITERS];
-    st->converged = (done == 1);
-    st->spmv_launches = spmv_launches;
-    const double bb = peek->scal[Scal::BB];
-    st->rel_residual = bb > 0.0 ? sqrt(peek->scal[Scal::RR] / bb) : 0.0;
-    st->spmv_ms = 0.0;
-    st->update_ms = 0.0;
-    for (size_t i = 0; i + 2 < evs.size(); i += 3) {
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
-      st->spmv_ms += ms;
-      cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]);
-      st->update_ms += ms;
-    }
-    st->spmv_timed = (int32_t)(evs.size() / 3);
-  }
-  if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");
-  if (done != 1) return fail(h, FEMB_ERR_NOT_CONVERGED, "PCG did not reach rtol within max_iter");
-  return FEMB_OK;
+  return run_mega(h, o, d_b, st, false);
 }
 
-// ---- row-block partition: the pieces dist.cu's solver loop launches --------------------------------------
-// usable when the rank's line tables are set, the exchange runs through peer memory with the exchanges fused into
-// the kernels, and the matrix-free operator applies
+// ---- row-block partition (dist.cu) -------------------------------------------------------------------------
+// usable when the rank's line tables are set, the exchange runs through peer memory and the matrix-free operator applies
 bool dist_lines_applicable(femb_handle* h, const femb_solve_opts& o, bool fused_p2p) {
   if (!(o.precond == FEMB_PRECOND_LINES || o.precond == FEMB_PRECOND_AUTO)) return false;
   return fused_p2p && h->bs == 6 && h->line_sym_ok && h->line_dist && !h->line_failed && ebe_available_dist(h);
@@ -959,35 +1131,11 @@ int dist_lines_setup(femb_handle* h) {
   return h->line_num_ok ? FEMB_OK : 1;          // 1: fall back to Jacobi
 }
 
-// z = M^-1 r on the owned rows (+ halo push, (r, z) -> red[GAMMA]); three launches on the handle's stream
-int dist_lines_precond(femb_handle* h, double* red) {
-  const LnDev T = ln_dev(h);
-  const int pstride = h->num_sms * 8;
-  const P2PDev* pd = reinterpret_cast<const P2PDev*>(h->p2p_dev_copy.p);
-  const int n_owned = (int)h->n_owned_nodes;
-  const int grid_v = std::max(1, std::min((n_owned + kLnVecThreads - 1) / kLnVecThreads, h->num_sms * 4));
-  if (h->ln_n_ranges > 0) ln_solve_kernel<true><<<h->ln_n_ranges, kLnThreads, 0, h->stream>>>(T, h->r.p, h->flags.p, pd);
-  else return fail(h, FEMB_ERR_ARG, "line preconditioner: this rank owns no line piece");
-  ln_coarse_kernel<true><<<T.coarse_blk_off[kLnMaxFam], kLnCoarseWarps * 32, 0, h->stream>>>(T, h->flags.p, pd);
-  dist_ln_prolong_kernel<kLnVecThreads><<<grid_v, kLnVecThreads, 0, h->stream>>>(T, h->Dinv.p, h->r.p, h->z.p, n_owned,
-                                                                                   h->partials.p + 2 * pstride, pstride, red, h->flags.p, pd);
-  h->launches += 3;
-  FEMB_CUDA(h, cudaGetLastError());
-  return FEMB_OK;
+// the whole distributed solve of one right-hand side (owned rows of d_b); the caller has zeroed the ghost tails of the
+// Krylov vectors, uploaded the sequence base and lined the ranks up
+int dist_lines_solve(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
+  if (h->ln_n_ranges <= 0) return fail(h, FEMB_ERR_ARG, "line preconditioner: this rank owns no line piece");
+  return run_mega(h, o, d_b, st, true);
 }
-
-int dist_lines_update(femb_handle* h, int first, double rtol, double* red) {
-  const int pstride = h->num_sms * 8;
-  const int64_t n = h->n_owned_nodes * 6;
-  const P2PDev* pd = reinterpret_cast<const P2PDev*>(h->p2p_dev_copy.p);
-  const int grid = vec_grid(h, n, kLnVecThreads);
-  dist_ln_update_kernel<kLnVecThreads><<<grid, kLnVecThreads, 0, h->stream>>>(h->z.p, h->s.p, h->p.p, h->q.p, h->x.p, h->r.p, n, first, rtol,
-                                                                               h->partials.p + pstride, pstride, red, h->flags.p, pd);
-  h->launches++;
-  FEMB_CUDA(h, cudaGetLastError());
-  return FEMB_OK;
-}
-
-int dist_lines_coarse_dim(const femb_handle* h) { return h->line_sym.n_coarse; }
 
 }  // namespace femb
