@@ -28,7 +28,8 @@ class SolveOpts(C.Structure):
 
 class EigOpts(C.Structure):
     _fields_ = [("k", C.c_int32), ("block", C.c_int32), ("max_iter", C.c_int32), ("op", C.c_int32),
-                ("rtol", C.c_double), ("lambda_min", C.c_double), ("precond", C.c_int32), ("reserved", C.c_int32)]
+                ("rtol", C.c_double), ("lambda_min", C.c_double), ("precond", C.c_int32), ("reserved", C.c_int32),
+                ("accept_rtol", C.c_double)]
 
 
 class Stats(C.Structure):

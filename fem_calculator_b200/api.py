@@ -82,8 +82,11 @@ class Handle:
         self._check(self.lib.femb_apply_k(self._h, int(op), int(masked), x, y, C.byref(used)))
         return y, used.value
 
-    def modal(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6, op=L.OP_AUTO, precond=L.PRECOND_AUTO):
-        o = L.EigOpts(k, block, max_iter, int(op), rtol, lambda_min, int(precond), 0)
+    def modal(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6, op=L.OP_AUTO, precond=L.PRECOND_AUTO,
+              accept_rtol=0.0):
+        """``accept_rtol`` > rtol: also return a solve that stagnated above rtol when its worst pencil residual is below
+        accept_rtol (stats['converged'] == 0, stats['rel_residual'] = what was reached); 0 = strict."""
+        o = L.EigOpts(k, block, max_iter, int(op), rtol, lambda_min, int(precond), 0, float(accept_rtol))
         st = L.Stats()
         lam = np.zeros(k)
         phi = np.zeros((k, self.ndof))  # column-major (ndof,k) == row-major (k,ndof)
@@ -227,7 +230,7 @@ class DistFrameModel(FrameModel):
 
     def modal_dist(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6):
         """(lambda (k,), phi_owned (n_owned_dof, k), stats) — collective: every rank calls it."""
-        o = L.EigOpts(k, block, max_iter, 0, rtol, lambda_min, 0, 0)
+        o = L.EigOpts(k, block, max_iter, 0, rtol, lambda_min, 0, 0, 0.0)
         st = L.Stats()
         lam = np.zeros(k)
         phi = np.zeros((k, self.n_owned_dof))

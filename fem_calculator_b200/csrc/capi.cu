@@ -621,6 +621,11 @@ int time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, doubl
     FEMB_CUDA(h, cudaEventElapsedTime(&t9, h->ev0, h->ev1));
     *ms = (double)t9 / reps;
     return FEMB_OK;
+  } else if (which == 11) {
+    // no launch: algorithmic bytes of ONE iteration of the persistent line-preconditioned PCG kernel (lines.cu)
+    *ms = 0.0;
+    *bytes = lines_iteration_bytes(h);
+    return *bytes > 0.0 ? FEMB_OK : fail(h, FEMB_ERR_ARG, "line preconditioner not set up (solve once with it first)");
   } else if (which == 10) {
     // FP64 FMA issue peak; *bytes receives the number of FP64 FMA instructions (per thread-lane) of one launch
     const int grid = h->num_sms * 8;

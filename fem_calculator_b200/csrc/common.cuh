@@ -331,6 +331,7 @@ int dist_set_lines(femb_handle* h, int32_t n_coarse, const int32_t* fam_off, con
 bool dist_lines_applicable(femb_handle* h, const femb_solve_opts& o, bool fused_p2p);
 int dist_lines_setup(femb_handle* h);
 int dist_lines_solve(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
+double lines_iteration_bytes(const femb_handle* h);
 int pcg_solve_multi(femb_handle* h, const femb_solve_opts& o, const double* d_B, int64_t ldb, int nb, double* d_X,
                     int64_t ldx, femb_stats* st);
 int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda, double* phi, int32_t* n_found,

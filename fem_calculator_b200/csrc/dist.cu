@@ -15,7 +15,6 @@
 // `check_every` iterations.  NCCL is loaded with dlopen at femb_dist_init, so single-GPU users
 // need no NCCL at all.
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -32,19 +31,28 @@ int setup_precond_public(femb_handle* h, int mode);
 
 namespace {
 
+// The few NCCL declarations this file needs, spelled out here so that the library builds without the NCCL
+// development header (NCCL is only dlopen'ed, and only by multi-GPU callers); values follow nccl.h's stable ABI.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclSum = 0 } ncclRedOp_t;
+typedef enum { ncclDouble = 8 } ncclDataType_t;
+struct ncclConfig_t;
+
 struct NcclApi {
   void* lib = nullptr;
-  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
-  decltype(&ncclCommInitRank) CommInitRank = nullptr;
-  decltype(&ncclCommDestroy) CommDestroy = nullptr;
-  decltype(&ncclCommSplit) CommSplit = nullptr;
-  decltype(&ncclAllReduce) AllReduce = nullptr;
-  decltype(&ncclSend) Send = nullptr;
-  decltype(&ncclRecv) Recv = nullptr;
-  decltype(&ncclGroupStart) GroupStart = nullptr;
-  decltype(&ncclGroupEnd) GroupEnd = nullptr;
-  decltype(&ncclGetErrorString) GetErrorString = nullptr;
-  decltype(&ncclGetVersion) GetVersion = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;   // optional (NCCL >= 2.18)
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
 };
 
 NcclApi g_nccl;
@@ -58,9 +66,11 @@ const char* load_nccl() {
 #define SYM(name)                                                           \
   g_nccl.name = reinterpret_cast<decltype(g_nccl.name)>(dlsym(lib, "nccl" #name)); \
   if (!g_nccl.name) return "libnccl.so.2 lacks nccl" #name
-  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(CommSplit); SYM(AllReduce); SYM(Send); SYM(Recv);
+  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Send); SYM(Recv);
   SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString); SYM(GetVersion);
 #undef SYM
+  // only the opt-in overlapped halo stream needs a second communicator: older NCCLs do without it
+  g_nccl.CommSplit = reinterpret_cast<decltype(g_nccl.CommSplit)>(dlsym(lib, "ncclCommSplit"));
   g_nccl.lib = lib;
   return nullptr;
 }
@@ -494,7 +504,8 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
   // ... the rest as a CUDA graph of `check` iterations — NCCL calls included — launched once per
   // poll: with 6-8 enqueues per iteration (two of them NCCL) the host, not the GPU, would
   // otherwise set the pace of a 1M-DOF/GPU iteration.
-  const bool use_graph = h->dist_world > 1 && !getenv("FEMB_DIST_NO_GRAPH");
+  // (a graph always runs `check` iterations: with a smaller iteration cap the eager path keeps the cap exact)
+  const bool use_graph = h->dist_world > 1 && o.max_iter >= check && !getenv("FEMB_DIST_NO_GRAPH");
   (void)comm;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -502,30 +513,29 @@ int run_dist_pcg(femb_handle* h, const femb_solve_opts& o, const double* d_rhs, 
     FEMB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
     for (int k = 0; k < check && !rc; ++k) rc = enqueue_iteration(0);
     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    FEMB_CUDA(h, ce);
-    FEMB_CUDA(h, cudaGraphInstantiate(&gexec, graph, 0));
+    if (!rc && ce != cudaSuccess) rc = fail(h, FEMB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    if (!rc && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) rc = fail(h, FEMB_ERR_CUDA, "cudaGraphInstantiate failed");
     spmv_launches = overlap ? 2 : 1;
   }
-  while (!done && it <= o.max_iter) {
+  while (!rc && !done && it <= o.max_iter) {
     if (use_graph) {
-      FEMB_CUDA(h, cudaGraphLaunch(gexec, h->stream));
+      if (cudaGraphLaunch(gexec, h->stream) != cudaSuccess) { rc = fail(h, FEMB_ERR_CUDA, "cudaGraphLaunch failed"); break; }
       it += check;
       spmv_launches += (overlap ? 2 : 1) * check;
       h->launches += (overlap ? 4 : 3) * check;
     } else {
       const int batch = std::min(check, o.max_iter + 1 - it);
-      for (int k = 0; k < batch; ++k, ++it) {
-        rc = enqueue_iteration(0);
-        if (rc) return rc;
-      }
+      for (int k = 0; k < batch && !rc; ++k, ++it) rc = enqueue_iteration(0);
+      if (rc) break;
     }
     rc = poll();
     if (rc) break;
   }
+  // every exit goes through here: graph objects released, and the sequence base advanced by an amount that does not
+  // depend on where this rank stopped (its peers' mailbox / halo numbering must stay in step)
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
-  if (p2p) h->p2p_seq_base += (long long)peek->flags[Flag::ITERS] + 2;   // identical on every rank
+  if (p2p) h->p2p_seq_base += (long long)std::max(it, (int)peek->flags[Flag::ITERS]) + check + 4;
   if (rc) return rc;
   if (done == 4) return fail(h, FEMB_ERR_CUDA, "peer-memory exchange timed out waiting for another rank");
   if (st) {
@@ -594,7 +604,7 @@ int femb_dist_init(femb_handle* h, int rank, int world, const uint8_t* id128) {
   h->nccl_comm = comm;
   h->dist_rank = rank;
   h->dist_world = world;
-  if (world > 1) {
+  if (world > 1 && g_nccl.CommSplit) {
     ncclComm_t comm2 = nullptr;
     FEMB_NCCL(h, g_nccl.CommSplit(comm, 0, rank, &comm2, nullptr));
     h->nccl_comm_halo = comm2;

@@ -1104,6 +1104,21 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   return FEMB_OK;
 }
 
+// compulsory bytes of one iteration of the persistent kernel (every array once per phase that must touch it):
+//   operator   pair + node records, coordinates, z read, s written, mask            (ebe_bytes)
+//   update     z, s, p, q, x, r read; p, q, x, r written                            10 x 8 B / DOF
+//   lines      per line entry: node id 4 + direction 24 + factors 24 + r 24 read, amplitude 8 written
+//   coarse     the per-family inverses                                              8 B x sum nf^2
+//   prolong    r, 1/diag read, z written (48 B each) + per family bundle id 4, amplitude 8, direction 24
+double lines_iteration_bytes(const femb_handle* h) {
+  if (!h->line_sym_ok || h->line_sym.n_coarse == 0) return 0.0;
+  const LineSym& S = h->line_sym;
+  const double nodes = (double)(h->line_dist ? h->n_owned_nodes : h->n_nodes);
+  double inv = 0.0;
+  for (int f = 0; f < kLnMaxFam; ++f) { const double nf = S.fam_off[f + 1] - S.fam_off[f]; inv += 8.0 * nf * nf; }
+  return ebe_bytes(h, 1) + 80.0 * 6.0 * nodes + 84.0 * (double)S.n_entries + inv + (144.0 + 36.0 * kLnMaxFam) * nodes;
+}
+
 int pcg_lines(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
   int rc = setup_precond_public(h, FEMB_PRECOND_JACOBI);
   if (rc) return rc;

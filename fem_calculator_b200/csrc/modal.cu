@@ -545,8 +545,9 @@ int run_modal(femb_handle* h, const femb_eig_opts& o, double* lambda_out, double
     }
     ncand = nb;
   }
-  // stagnation at the accuracy of the inner solver (ill-conditioned chains): accept if small
-  if (!ok && best_res <= 1e-4) ok = true;
+  // stagnation at the accuracy of the inner solver (ill-conditioned chains): accepted only up to the tolerance the
+  // caller allows explicitly (femb_eig_opts.accept_rtol); strict by default
+  if (!ok && o.accept_rtol > o.rtol && best_res <= o.accept_rtol) ok = true;
   const int kk = std::min(k, m);
   st->converged = (st->rel_residual <= o.rtol) ? 1 : 0;
   st->method_used = method;

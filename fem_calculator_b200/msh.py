@@ -66,8 +66,9 @@ def read_msh(path: str) -> Mesh:
     with open(path, "r") as fh:
         sec = _sections(fh.read())
     ver = sec["MeshFormat"][0].split()
-    if not ver[0].startswith("4.") or int(ver[1]) != 0:
-        raise ValueError(f"only MSH 4.x ASCII is supported, got header {ver}")
+    if ver[0] != "4.1" or int(ver[1]) != 0:
+        # 4.0 lays out $Entities / $Nodes / $Elements differently: refuse it instead of misreading tags and coordinates
+        raise ValueError(f"only MSH 4.1 ASCII is supported, got header {ver}")
 
     field_data = {}
     for ln in sec.get("PhysicalNames", [])[1:]:

@@ -19,6 +19,7 @@ reference (BeamSolver.py:55-57,80-82).
 from __future__ import annotations
 
 import math
+import warnings
 
 
 def _rect_J(long_side: float, short_side: float) -> float:
@@ -82,9 +83,18 @@ def _props(section_type: str, p: dict):
     return None
 
 
+_FILLET_KEYS = ("r", "r_out", "r_r", "r_t")      # fillet radii of the I / C / box / L dialogs (BeamSolver.py:104-137)
+
+
 def calculate_section_properties(section_type: str, params: dict, rotate: bool = False):
-    """Same signature and return record as BeamSolver.py:32."""
+    """Same signature and return record as BeamSolver.py:32.  The closed forms are for sharp corners: a non-zero
+    fillet radius is reported (warning) and left out, it is not silently dropped."""
     try:
+        rounded = [k for k in _FILLET_KEYS if params.get(k)]
+        if rounded:
+            warnings.warn(f"closed-form section properties ignore the fillet radii {rounded} of '{section_type}' "
+                          f"(sharp-corner formulas; use the reference's sectionproperties front end for rounded corners)",
+                          RuntimeWarning, stacklevel=2)
         r = _props(section_type, params)
         if r is None:
             print(f"Warning: Unknown section type '{section_type}'.")

@@ -105,6 +105,9 @@ typedef struct {
                             at a time), FEMB_PRECOND_AUTO (as for the static solve), anything else = JACOBI
                             (4-/2-vector lockstep PCG); FEMB_PRECOND_LINES as TWO_LEVEL; ignored behind a factorisation                   */
   int32_t reserved;
+  double accept_rtol;    /* a solve that stagnates above rtol (ill-conditioned chains: cond(K) eps > rtol) is still returned
+                            with FEMB_OK when its worst residual is <= accept_rtol (femb_stats.converged stays 0 and
+                            rel_residual tells what was reached); 0 = strict: FEMB_ERR_NOT_CONVERGED above rtol   */
 } femb_eig_opts;
 
 typedef struct {
@@ -277,7 +280,8 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
  * K_ff operator), 1 = fused element+assembly, 3 = matrix-free (EBE) operator, 4 = its 4-vector
  * form, 5 = EBE with the fused (x, y) reduction, 7 = dense blocked Cholesky (fill + factor; *bytes
  * then receives the FLOP count n^3/3), 9 = plain 16-byte read of the K values (streaming ceiling), 10 = FP64 FMA issue
- * ceiling (8 independent chains per thread; *bytes receives the FMA count of one launch). */
+ * ceiling (8 independent chains per thread; *bytes receives the FMA count of one launch), 11 = no launch: *bytes receives
+ * the algorithmic bytes of one iteration of the persistent line-preconditioned PCG kernel. */
 int femb_time_kernel(femb_handle* h, int which, int warm, int reps, double* ms, double* bytes);
 
 /* CUDA-event stopwatch on the handle's stream: stop = 0 records the start (after draining the

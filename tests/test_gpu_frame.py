@@ -291,3 +291,22 @@ def test_same_topology_reuses_symbolic_analysis_correctly():
         uo, _ = S.solve_static(Ko, f, fixed, free, method="direct")
         assert np.linalg.norm(u - uo) <= 1e-10 * np.linalg.norm(uo)
     m.close()
+
+
+def test_qr_algorithm_helper_reproduces_the_reference_iteration():
+    """compat.BeamAnalysisB200.qr_algorithm (BeamSolver.py:467-481 signature) on inv(M_ff) K_ff of the shipped
+    cantilever: same eigenvalues as the unmodified reference's own loop (tests/golden, omega = sqrt(lambda)) and
+    orthonormal accumulated vectors."""
+    c = G.load_beam("c1_cantilever_beam")
+    raw = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_cantilever_beam.npz"), allow_pickle=True)
+    K, M = raw["ref_K_dense"], raw["ref_M_dense"]
+    _, free, _ = S.frame_bc(c["mesh"], c["bc"])
+    A = np.linalg.inv(M[np.ix_(free, free)]) @ K[np.ix_(free, free)]
+    w = compat.BeamAnalysisB200.__new__(compat.BeamAnalysisB200)
+    w.device = 0
+    lam, V = w.qr_algorithm(A)
+    assert lam.shape == (len(free),) and V.shape == (len(free), len(free)) and np.all(np.diff(lam) >= 0)
+    om = np.sqrt(lam[lam > 1e-6])
+    ref = np.sort(np.asarray(raw["ref_natural_frequencies"]))
+    assert np.abs(om[:len(ref)] - ref).max() <= 1e-6 * ref.max(), (om[:4], ref[:4])
+    assert np.abs(V.T @ V - np.eye(len(free))).max() <= 1e-10

@@ -102,7 +102,8 @@ def _simply_supported(n_el, length=10.0):
     m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)))
     m.assemble()
     m.set_bc(fixed, f)
-    lam, phi, st = m.modal(k=20)
+    # cond(K) ~ (L/h)^4 of a long chain puts the pencil residual out of reach of FP64: the caller says how far it may stagnate
+    lam, phi, st = m.modal(k=20, accept_rtol=1e-4)
     m.close()
     return mesh, bc, es, props, lam, phi, st
 

@@ -360,10 +360,15 @@ def test_line_precond_spec_matches_matrix_form():
     assert np.abs(z - zref).max() <= 1e-10 * np.abs(zref).max()
 
 
-def test_qr_algorithm_helper_points_at_the_modal_solve():
-    """BeamSolver.py:467 is deliberately not restated on the CPU: the mirror class says so."""
+def test_qr_algorithm_helper_has_no_cpu_fallback():
+    """BeamSolver.py:467 keeps its signature on the mirror class and runs on the GPU (tests/test_gpu_frame.py compares
+    it with the unmodified reference's output); without a device it raises instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the GPU test")
     w = compat.BeamAnalysisB200.__new__(compat.BeamAnalysisB200)
-    with pytest.raises(NotImplementedError, match="modal"):
+    w.device = 0
+    with pytest.raises(RuntimeError, match="no CUDA device"):
         w.qr_algorithm(np.eye(3))
 
 
@@ -386,3 +391,144 @@ def test_result_tables_follow_the_reference_report(tmp_path):
     assert len(modes) == 11 and modes[1] == "1,10.0000,1.5915"
     w.natural_frequencies = None
     assert w.modal_result_table().shape == (0, 3) and len(w.write_result_tables(str(tmp_path / "static"))) == 1
+
+
+# ---- closed-form section front end: value tests for all seven dialog types ------------------------
+def _polygon_props(poly):
+    """Area, centroid and centroidal second moments of a simple polygon (exact: Green's theorem)."""
+    x, y = np.asarray(poly, dtype=float).T
+    x1, y1 = np.roll(x, -1), np.roll(y, -1)
+    c = x * y1 - x1 * y
+    A = c.sum() / 2
+    cx = ((x + x1) * c).sum() / (6 * A)
+    cy = ((y + y1) * c).sum() / (6 * A)
+    ixx = ((y ** 2 + y * y1 + y1 ** 2) * c).sum() / 12 - A * cy ** 2
+    iyy = ((x ** 2 + x * x1 + x1 ** 2) * c).sum() / 12 - A * cx ** 2
+    s = 1.0 if A > 0 else -1.0
+    return s * A, cx, cy, s * ixx, s * iyy
+
+
+def _shape_polygons(kind, p):
+    """(outer polygon, hole polygon or None) of the sharp-cornered dialog shapes, picture axes (x horizontal)."""
+    if kind == "rectangular section":
+        d, b = p["d"], p["b"]
+        return [(0, 0), (b, 0), (b, d), (0, d)], None
+    if kind == "I section":
+        d, b, tf, tw = p["d"], p["b"], p["t_f"], p["t_w"]
+        x0, x1 = (b - tw) / 2, (b + tw) / 2
+        return [(0, 0), (b, 0), (b, tf), (x1, tf), (x1, d - tf), (b, d - tf), (b, d), (0, d), (0, d - tf), (x0, d - tf), (x0, tf), (0, tf)], None
+    if kind == "C section":
+        d, b, tf, tw = p["d"], p["b"], p["t_f"], p["t_w"]
+        return [(0, 0), (b, 0), (b, tf), (tw, tf), (tw, d - tf), (b, d - tf), (b, d), (0, d)], None
+    if kind == "L section":
+        d, b, t = p["d"], p["b"], p["t"]
+        return [(0, 0), (b, 0), (b, t), (t, t), (t, d), (0, d)], None
+    if kind == "hollow box section":
+        d, b, t = p["d"], p["b"], p["t"]
+        return [(0, 0), (b, 0), (b, d), (0, d)], [(t, t), (b - t, t), (b - t, d - t), (t, d - t)]
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind,params", [
+    ("rectangular section", {"d": 0.1, "b": 0.05}),
+    ("I section", {"d": 0.2, "b": 0.1, "t_f": 0.0085, "t_w": 0.0056, "r": 0.0}),
+    ("C section", {"d": 0.1, "b": 0.05, "t_f": 0.005, "t_w": 0.005, "r": 0.0}),
+    ("L section", {"d": 0.075, "b": 0.075, "t": 0.006, "r_r": 0.0, "r_t": 0.0}),
+    ("L section", {"d": 0.12, "b": 0.07, "t": 0.008, "r_r": 0.0, "r_t": 0.0}),
+    ("hollow box section", {"d": 0.1, "b": 0.1, "t": 0.005, "r_out": 0.0}),
+    ("hollow box section", {"d": 0.15, "b": 0.08, "t": 0.006, "r_out": 0.0}),
+])
+def test_polygonal_sections_match_exact_polygon_integrals(kind, params):
+    """A, I_x, I_y and the extreme fibre distances of the five polygonal dialog shapes against exact polygon integrals;
+    `rotate` swaps the (I, kappa, c) pairs (BeamSolver.py:73-79)."""
+    from fem_calculator_b200.sections import calculate_section_properties as csp
+    outer, hole = _shape_polygons(kind, params)
+    A, cx, cy, ixx, iyy = _polygon_props(outer)
+    if hole:
+        Ah, hx, hy, hxx, hyy = _polygon_props(hole)
+        ixx = ixx + A * cy ** 2 - (hxx + Ah * hy ** 2)
+        iyy = iyy + A * cx ** 2 - (hyy + Ah * hx ** 2)
+        cx, cy = (A * cx - Ah * hx) / (A - Ah), (A * cy - Ah * hy) / (A - Ah)
+        A -= Ah
+        ixx -= A * cy ** 2
+        iyy -= A * cx ** 2
+    xs, ys = np.asarray(outer, dtype=float).T
+    got = csp(kind, params, False)
+    assert abs(got[0] - A) <= 1e-12 * A
+    assert abs(got[1] - ixx) <= 1e-11 * ixx and abs(got[2] - iyy) <= 1e-11 * iyy, (got, ixx, iyy)
+    assert abs(got[6] - max(cx - xs.min(), xs.max() - cx)) <= 1e-12 and abs(got[7] - max(cy - ys.min(), ys.max() - cy)) <= 1e-12
+    assert 0.0 < got[4] < 1.0 and 0.0 < got[5] < 1.0 and got[3] > 0.0
+    rot = csp(kind, params, True)
+    assert rot[1] == got[2] and rot[2] == got[1] and rot[4] == got[5] and rot[5] == got[4] and rot[6] == got[7] and rot[7] == got[6]
+
+
+def test_section_torsion_constants_and_round_sections_match_published_values():
+    """J: exact for the circle (pi d^4 / 32) and the tube; Roark's table for the solid rectangle (beta = 0.229 at
+    a/b = 2, 0.141 for the square); Bredt's formula for the closed box; sum(b t^3 / 3) for the open thin-walled shapes."""
+    from fem_calculator_b200.sections import calculate_section_properties as csp
+    d = 0.08
+    c = csp("circular section", {"d": d})
+    assert abs(c[0] - np.pi * d * d / 4) <= 1e-15 and abs(c[1] - np.pi * d ** 4 / 64) <= 1e-18 and c[1] == c[2]
+    assert abs(c[3] - np.pi * d ** 4 / 32) <= 1e-18 and abs(c[4] - 6 / 7) <= 1e-12 and c[6] == d / 2
+    t = 0.004
+    h = csp("hollow circular section", {"d": d, "t": t})
+    di = d - 2 * t
+    assert abs(h[0] - np.pi * (d * d - di * di) / 4) <= 1e-15 and abs(h[3] - np.pi * (d ** 4 - di ** 4) / 32) <= 1e-18
+    assert 0.5 < h[4] < 6 / 7                       # thin tube -> 1/2, solid -> 6/7 (Cowper, nu = 0)
+    r = csp("rectangular section", {"d": 0.1, "b": 0.05})
+    assert abs(r[3] / (0.1 * 0.05 ** 3) - 0.229) <= 1e-3 and abs(r[4] - 5 / 6) <= 1e-12
+    sq = csp("rectangular section", {"d": 0.06, "b": 0.06})
+    assert abs(sq[3] / 0.06 ** 4 - 0.1406) <= 1e-3
+    bx = csp("hollow box section", {"d": 0.15, "b": 0.08, "t": 0.006, "r_out": 0.0})
+    Am = (0.15 - 0.006) * (0.08 - 0.006)
+    assert abs(bx[3] - 4 * Am ** 2 / (2 * ((0.15 - 0.006) + (0.08 - 0.006)) / 0.006)) <= 1e-12 * bx[3]
+    i = csp("I section", {"d": 0.2, "b": 0.1, "t_f": 0.0085, "t_w": 0.0056, "r": 0.0})
+    assert abs(i[3] - (2 * 0.1 * 0.0085 ** 3 + (0.2 - 0.0085) * 0.0056 ** 3) / 3) <= 1e-18
+    ell = csp("L section", {"d": 0.075, "b": 0.075, "t": 0.006, "r_r": 0.0, "r_t": 0.0})
+    assert abs(ell[3] - (0.075 + 0.075 - 0.006) * 0.006 ** 3 / 3) <= 1e-18
+
+
+def test_fillet_radii_are_reported_not_silently_dropped():
+    from fem_calculator_b200.sections import calculate_section_properties as csp
+    with pytest.warns(RuntimeWarning, match="fillet"):
+        a = csp("I section", {"d": 0.2, "b": 0.1, "t_f": 0.0085, "t_w": 0.0056, "r": 0.012})
+    b = csp("I section", {"d": 0.2, "b": 0.1, "t_f": 0.0085, "t_w": 0.0056, "r": 0.0})
+    assert a == b
+
+
+def test_msh_reader_rejects_other_format_versions(tmp_path):
+    from fem_calculator_b200 import msh
+    p = tmp_path / "old.msh"
+    p.write_text("$MeshFormat\n4.0 0 8\n$EndMeshFormat\n")
+    with pytest.raises(ValueError, match="4.1"):
+        msh.read_msh(str(p))
+
+
+def test_accelerated_force_analysis_keeps_the_reference_bookkeeping():
+    """compat.accelerate_force_analysis: the subclass inherits the reference's apply_boundary_conditions /
+    print_reactions and only adds the device hand-over (here with a stand-in model: no GPU)."""
+    from fem_calculator_b200 import compat
+
+    class Ref:                                       # the shape of ReactionSolver.ForceAnalysis
+        def __init__(self):
+            self.calls = []
+
+        def apply_boundary_conditions(self):
+            self.calls.append("ref-bc")
+            self.fixed_dofs = np.array([0, 1, 2])
+            self.f = np.arange(9.0)
+
+        def print_reactions(self):
+            self.calls.append("ref-print")
+
+    class Model:
+        def set_bc(self, fixed, f):
+            self.got = (fixed, f)
+
+    G = compat.accelerate_force_analysis(Ref)
+    g = G()
+    g._model = Model()
+    g.apply_boundary_conditions()
+    g.print_reactions()
+    assert g.calls == ["ref-bc", "ref-print"] and g._model.got[0].dtype == np.int64 and np.array_equal(g._model.got[1], np.arange(9.0))
+    assert G.__name__ == "RefGPU" and G.solve is compat.ForceAnalysisB200.solve
