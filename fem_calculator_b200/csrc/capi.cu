@@ -70,6 +70,7 @@ void femb_destroy(femb_handle* h) {
   cudaSetDevice(h->device);
   femb_dist_finalize(h);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& e : h->batch_pinned) cudaHostUnregister(e.first);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);

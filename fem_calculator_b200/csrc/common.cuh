@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/femb200.h"
@@ -246,6 +247,10 @@ struct femb_handle {
   std::vector<void*> p2p_mapped;
   femb::DevBuf<char> p2p_dev_copy;         // device-resident P2PDev for the fused kernels
   femb::DevBuf<int32_t> p2p_send_slot, p2p_extra, p2p_bnd_nodes;
+
+  // batched chain solve (direct.cu): persistent device buffers and the host ranges page-locked in place
+  femb::DevBuf<double> batch_f, batch_u, batch_W, batch_z;
+  std::vector<std::pair<void*, size_t>> batch_pinned;
 
   void* pinned = nullptr;           // small pinned staging area
   size_t pinned_bytes = 0;

@@ -213,144 +213,228 @@ int run_chain_solve(femb_handle* h, femb_stats* st) {
 }
 
 // ---- batched chain models: fused element generation + block-tridiagonal solve ------------
-// Scratch layout is model-interleaved: W[(k*36+q)*nm + m], z[(k*6+c)*nm + m], so the 32
-// threads of a warp (32 consecutive models) touch 32 consecutive doubles.
+// BASELINE config 4: thousands of independent chain models.  SIX lanes share a model — lane r owns ROW r of every
+// 6x6 block of the recurrence (S_k, G_k = S_k^-1, O_k, W_k = O_k G_k) and entry r of the 6-vectors — and five models
+// share a warp.  The first version gave each model ONE thread: 8,192 threads on 148 SMs walking a 2,000-step
+// dependent recurrence of ~700 FP64 operations per step, 10.2 ms whether 1,024 or 8,192 models were solved.  With
+// the rows spread over lanes a step is ~130 FP64 operations per lane plus ~120 shuffles, six times the threads hide
+// the latency, and the time follows the model count.  Scratch (W_k, z_k for the back substitution) is model-major:
+// a lane writes / reads its 48-byte row, a model's 336 bytes per step are contiguous.
 struct BatchParams {
   const double* xyz;        // (n_nodes,3) shared
   const double* sec_props;  // (n_models,8)
   const uint8_t* fixed;     // (ndof) 1 = fixed
   const double* f;          // (n_models, ndof)
   double* u;                // (n_models, ndof)
-  double* W;                // scratch
-  double* z;                // scratch
+  double* W;                // scratch (n_models, n_nodes, 36)
+  double* z;                // scratch (n_models, n_nodes, 6)
   int* status;              // count of models with a non-positive pivot
   int64_t n_models, n_elem;
   double E, G;
 };
 
-__global__ void __launch_bounds__(64)
-batch_chain_kernel(BatchParams B) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= B.n_models) return;
-  const int64_t nm = B.n_models, nn = B.n_elem + 1, ndof = nn * 6;
-  // per-model element generator: same record code as the assembly path
+// row `row` of block [a][b] of R^T k R (the expressions of frame_kblock, one row, no dynamic indexing)
+__device__ __forceinline__ void frame_krow(const FrameRec& R, int a, int b, int row, double* out) {
+  const bool same = (a == b);
+  const double suu = same ? 1.0 : -1.0;
+  const double sa = (a == 0) ? 1.0 : -1.0, sb = (b == 0) ? 1.0 : -1.0;
+  const int rr = row < 3 ? row : row - 3;
+  const double tr = rr == 0 ? R.t[0] : (rr == 1 ? R.t[1] : R.t[2]);
+  const double n1r = rr == 0 ? R.n1[0] : (rr == 1 ? R.n1[1] : R.n1[2]);
+  const double n2r = rr == 0 ? R.n2[0] : (rr == 1 ? R.n2[1] : R.n2[2]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double tt = tr * R.t[c], n11 = n1r * R.n1[c], n22 = n2r * R.n2[c], n12 = n1r * R.n2[c], n21 = n2r * R.n1[c];
+    if (row < 3) {
+      out[c] = suu * (R.ax * tt + R.k11z * n11 + R.k11y * n22);
+      out[3 + c] = sa * (R.k12z * n12 - R.k12y * n21);
+    } else {
+      out[c] = sb * (R.k12z * n21 - R.k12y * n12);
+      out[3 + c] = (same ? R.tor : -R.tor) * tt + (same ? R.k22y : R.k23y) * n11 + (same ? R.k22z : R.k23z) * n22;
+    }
+  }
+}
+
+constexpr int kBcThreads = 192;       // 6 warps x 5 models
+
+__global__ void __launch_bounds__(kBcThreads)
+batch_chain_rows_kernel(BatchParams B) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / 6, r = lane - grp * 6;
+  const int64_t m_raw = ((int64_t)blockIdx.x * (kBcThreads / 32) + warp) * 5 + grp;
+  const bool active = grp < 5 && m_raw < B.n_models;
+  const int64_t m = active ? m_raw : 0;               // idle lanes shadow model 0 (they store nothing)
+  const int base = (grp < 5 ? grp : 4) * 6;           // first lane of the group the shuffles read from
+  const int64_t nn = B.n_elem + 1, ndof = nn * 6;
   int32_t conn2[2] = {0, 1};
   int32_t sec0 = 0;
   FrameParams P;
   P.conn = conn2; P.elem_sec = &sec0; P.sec_props = B.sec_props + 8 * m;
   P.E = B.E; P.G = B.G; P.rho = 0.0;
   const double* f = B.f + m * ndof;
-  double S[36], G[36], O[36], Wk[36], y[6];
-  FrameRec R;
-  auto fixmask = [&](int64_t node) {
+  double* Wm = B.W + (size_t)m * nn * 36;
+  double* zm = B.z + (size_t)m * nn * 6;
+  auto freemask = [&](int64_t node) {
     unsigned mk = 0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) mk |= (B.fixed[node * 6 + c] ? 0u : 1u) << c;
     return mk;
   };
   bool ok = true;
-  // node 0: D_0 = K_e0[0][0]
+  FrameRec R;
   P.xyz = B.xyz;
   frame_record(P, 0, R);
-  frame_kblock<true>(R, 0, 0, S);
-  unsigned mi = fixmask(0);
-  mask_block(S, mi, mi, true);
+  double a[6], y;
+  unsigned mi = freemask(0);
+  frame_krow(R, 0, 0, r, a);                           // D_0 = K_e0[0][0]
 #pragma unroll
-  for (int c = 0; c < 6; ++c) y[c] = ((mi >> c) & 1u) ? f[c] : 0.0;
-  for (int64_t k = 0; k < nn; ++k) {
-    ok = inv6_spd(S, G) && ok;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s += G[r * 6 + c] * y[c];
-      B.z[(k * 6 + r) * nm + m] = s;
-    }
-    if (k + 1 == nn) break;
-    // element k joins nodes k, k+1: record R currently holds element k
-    const unsigned mj = fixmask(k + 1);
-    frame_kblock<true>(R, 1, 0, O);          // K[k+1][k]
-    mask_block(O, mj, mi, false);
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double s = 0.0;
-#pragma unroll
-        for (int t = 0; t < 6; ++t) s += O[r * 6 + t] * G[t * 6 + c];
-        Wk[r * 6 + c] = s;
-      }
-#pragma unroll
-    for (int q = 0; q < 36; ++q) B.W[(k * 36 + q) * nm + m] = Wk[q];
-    frame_kblock<true>(R, 1, 1, S);          // element k's share of D_{k+1}
-    if (k + 1 < B.n_elem) {                  // plus element k+1's [0][0]
-      P.xyz = B.xyz + 3 * (k + 1);
-      frame_record(P, 0, R);
-      frame_kblock<false>(R, 0, 0, S);
-    }
-    mask_block(S, mj, mj, true);
-    double yn[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      double s = ((mj >> r) & 1u) ? f[(k + 1) * 6 + r] : 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        s -= Wk[r * 6 + c] * y[c];
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) t += Wk[r * 6 + q] * O[c * 6 + q];
-        S[r * 6 + c] -= t;
-      }
-      yn[r] = s;
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) y[c] = yn[c];
-    mi = mj;
+  for (int c = 0; c < 6; ++c) {
+    const bool fr = ((mi >> r) & 1u) && ((mi >> c) & 1u);
+    if (!fr) a[c] = (c == r) ? 1.0 : 0.0;
   }
-  double xn[6];
-  double* u = B.u + m * ndof;
+  y = ((mi >> r) & 1u) ? f[r] : 0.0;
+  for (int64_t k = 0; k < nn; ++k) {
+    // G = S^-1: Gauss-Jordan, rows spread over the six lanes
+    double g[6];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) { xn[c] = B.z[((nn - 1) * 6 + c) * nm + m]; u[(nn - 1) * 6 + c] = xn[c]; }
-  for (int64_t k = nn - 2; k >= 0; --k) {
-    double xk[6];
+    for (int c = 0; c < 6; ++c) g[c] = (c == r) ? 1.0 : 0.0;
 #pragma unroll
-    for (int r = 0; r < 6; ++r) xk[r] = B.z[(k * 6 + r) * nm + m];
+    for (int p = 0; p < 6; ++p) {
+      double ap[6], gp[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        ap[c] = (c >= p) ? __shfl_sync(FULL, a[c], base + p) : 0.0;
+        gp[c] = (c <= p) ? __shfl_sync(FULL, g[c], base + p) : 0.0;
+      }
+      const double piv = ap[p];
+      if (!(piv > 0.0)) ok = false;
+      const double ip = 1.0 / piv;
+      const double fct = (r == p) ? 0.0 : a[p] * ip;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        if (c >= p) a[c] = (r == p) ? ap[c] * ip : a[c] - fct * ap[c];
+        if (c <= p) g[c] = (r == p) ? gp[c] * ip : g[c] - fct * gp[c];
+      }
+    }
+    double yc[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) yc[c] = __shfl_sync(FULL, y, base + c);
+    double zk = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) zk = fma(g[c], yc[c], zk);
+    if (active) zm[k * 6 + r] = zk;
+    if (k + 1 == nn) break;
+    // element k joins nodes k, k + 1 (R holds it): O = K[k+1][k], W = O G
+    const unsigned mj = freemask(k + 1);
+    double o[6];
+    frame_krow(R, 1, 0, r, o);
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+      if (!(((mj >> r) & 1u) && ((mi >> c) & 1u))) o[c] = 0.0;
+    double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) w[c] = fma(o[t], __shfl_sync(FULL, g[c], base + t), w[c]);
+    }
+    if (active) {
+      double2* wp = reinterpret_cast<double2*>(Wm + k * 36 + r * 6);
+      wp[0] = make_double2(w[0], w[1]); wp[1] = make_double2(w[2], w[3]); wp[2] = make_double2(w[4], w[5]);
+    }
+    // S_{k+1} = D_{k+1} - W O^T,  D_{k+1} = K_e(k)[1][1] + K_e(k+1)[0][0]
+    frame_krow(R, 1, 1, r, a);
+    double s_sub[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) xk[r] -= B.W[(k * 36 + c * 6 + r) * nm + m] * xn[c];
+      for (int q = 0; q < 6; ++q) s_sub[c] = fma(w[q], __shfl_sync(FULL, o[q], base + c), s_sub[c]);
+    }
+    if (k + 1 < B.n_elem) {
+      P.xyz = B.xyz + 3 * (k + 1);
+      frame_record(P, 0, R);
+      double d2[6];
+      frame_krow(R, 0, 0, r, d2);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a[c] += d2[c];
     }
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { xn[c] = xk[c]; u[k * 6 + c] = xk[c]; }
+    for (int c = 0; c < 6; ++c) {
+      const bool fr = ((mj >> r) & 1u) && ((mj >> c) & 1u);
+      a[c] = fr ? a[c] - s_sub[c] : ((c == r) ? 1.0 : 0.0);
+    }
+    double yn = ((mj >> r) & 1u) ? f[(k + 1) * 6 + r] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) yn = fma(-w[c], yc[c], yn);
+    y = yn;
+    mi = mj;
   }
-  if (!ok) atomicAdd(B.status, 1);
+  // back substitution: x_k = z_k - W_k^T x_{k+1}; lane r reads column r of W_k
+  double* u = B.u + m * ndof;
+  double xn = active ? zm[(nn - 1) * 6 + r] : 0.0;
+  if (active) u[(nn - 1) * 6 + r] = xn;
+#pragma unroll 4
+  for (int64_t k = nn - 2; k >= 0; --k) {
+    double wc[6], xk = 0.0;
+    if (active) {
+      xk = zm[k * 6 + r];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) wc[c] = Wm[k * 36 + c * 6 + r];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) wc[c] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) xk = fma(-wc[c], __shfl_sync(FULL, xn, base + c), xk);
+    xn = xk;
+    if (active) u[k * 6 + r] = xk;
+  }
+  if (!ok && active && r == 0) atomicAdd(B.status, 1);
+}
+
+// Host buffers of a batch are hundreds of MB: page-locking them in place (cudaHostRegister, kept while the same
+// pointer / size comes back) lets the copies run at PCIe speed instead of through the driver's pageable staging
+static void batch_register_host(femb_handle* h, const void* p, size_t bytes) {
+  if (!p || bytes < ((size_t)8 << 20)) return;
+  for (auto& e : h->batch_pinned)
+    if (e.first == p && e.second >= bytes) return;
+  for (auto it = h->batch_pinned.begin(); it != h->batch_pinned.end();)      // a stale registration of the same address
+    if (it->first == p) { cudaHostUnregister(it->first); it = h->batch_pinned.erase(it); } else ++it;
+  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) h->batch_pinned.emplace_back(const_cast<void*>(p), bytes);
+  else cudaGetLastError();                                                   // not registrable: plain pageable copy
 }
 
 int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const double* xyz,
                     const double* sec_props, double E, double G, const uint8_t* fixed_mask,
                     const double* f, double* u, femb_stats* st) {
   const int64_t nn = n_elem + 1, ndof = nn * 6;
-  DevBuf<double> dxyz, dsec, df, du, W, z;
+  batch_register_host(h, f, (size_t)n_models * ndof * 8);
+  batch_register_host(h, u, u ? (size_t)n_models * ndof * 8 : 0);
+  DevBuf<double> dxyz, dsec;
   DevBuf<uint8_t> dfix;
   DevBuf<int> status;
   FEMB_CUDA(h, upload(dxyz, xyz, (size_t)nn * 3, h->stream));
   FEMB_CUDA(h, upload(dsec, sec_props, (size_t)n_models * 8, h->stream));
   FEMB_CUDA(h, upload(dfix, fixed_mask, (size_t)ndof, h->stream));
-  FEMB_CUDA(h, upload(df, f, (size_t)n_models * ndof, h->stream));
-  FEMB_CUDA(h, du.alloc((size_t)n_models * ndof));
-  FEMB_CUDA(h, W.alloc((size_t)n_models * nn * 36));
-  FEMB_CUDA(h, z.alloc((size_t)n_models * nn * 6));
+  // the big device buffers persist in the handle (loads, solutions, 336 B of scratch per node and model)
+  FEMB_CUDA(h, h->batch_f.ensure((size_t)n_models * ndof));
+  FEMB_CUDA(h, h->batch_u.ensure((size_t)n_models * ndof));
+  FEMB_CUDA(h, h->batch_W.ensure((size_t)n_models * nn * 36));
+  FEMB_CUDA(h, h->batch_z.ensure((size_t)n_models * nn * 6));
+  g_h2d_bytes += (long long)n_models * ndof * 8;
+  FEMB_CUDA(h, cudaMemcpyAsync(h->batch_f.p, f, (size_t)n_models * ndof * 8, cudaMemcpyHostToDevice, h->stream));
   FEMB_CUDA(h, status.alloc(1));
   FEMB_CUDA(h, cudaMemsetAsync(status.p, 0, sizeof(int), h->stream));
-  BatchParams B{dxyz.p, dsec.p, dfix.p, df.p, du.p, W.p, z.p, status.p, n_models, n_elem, E, G};
+  BatchParams B{dxyz.p, dsec.p, dfix.p, h->batch_f.p, h->batch_u.p, h->batch_W.p, h->batch_z.p, status.p, n_models, n_elem, E, G};
   FEMB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  batch_chain_kernel<<<(unsigned)((n_models + 63) / 64), 64, 0, h->stream>>>(B);
+  const int64_t per_cta = (kBcThreads / 32) * 5;
+  batch_chain_rows_kernel<<<(unsigned)((n_models + per_cta - 1) / per_cta), kBcThreads, 0, h->stream>>>(B);
   h->launches++;
   FEMB_CUDA(h, cudaGetLastError());
   FEMB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   int* hs = reinterpret_cast<int*>(h->pinned);
   FEMB_CUDA(h, cudaMemcpyAsync(hs, status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  if (u) FEMB_CUDA(h, download(u, du.p, (size_t)n_models * ndof * 8, h->stream));
+  if (u) FEMB_CUDA(h, download(u, h->batch_u.p, (size_t)n_models * ndof * 8, h->stream));
   FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);

@@ -219,7 +219,8 @@ int femb_frame_stress(femb_handle* h, const double* u, double* sigma_node);
 /* ---- batched independent chain models (BASELINE config 4) ----------------------------
  * n_models cantilever/chain models of n_elem elements each (nodes 0..n_elem in chain
  * order along xyz), one section record per model, solved by a batched block-tridiagonal
- * Cholesky (one warp per model).  Equivalent to n_models calls of run_simulation's
+ * factorisation (six lanes per model, one row of every 6x6 block each; five models per warp).  Host buffers of
+ * 8 MB or more are page-locked in place on first use and stay registered while the same pointer comes back.  Equivalent to n_models calls of run_simulation's
  * static part (BeamSolver.py:360-418).
  *   xyz        (n_nodes,3) shared node coordinates, n_nodes = n_elem+1
  *   sec_props  (n_models,8)

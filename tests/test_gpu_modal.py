@@ -174,3 +174,44 @@ def test_batch_chain_solve_matches_oracle_and_single_model_path():
     u2, _ = m.batch_solve(xyz, props, E, E / (2 * (1 + nu)), fixed_mask, 2.0 * f)
     m.close()
     assert np.abs(u2 - 2.0 * u).max() <= 1e-12 * np.abs(u).max()
+
+
+def test_batch_chain_solve_at_config4_length_matches_banded_cholesky():
+    """BASELINE config 4 element count (2,000 elements per model), a ragged model count (not a multiple of the 30
+    models a CTA holds), inclined / non-uniform chain: a few models against scipy's banded Cholesky on the oracle's
+    matrix.  cond(K) ~ (L/h)^4 ~ 1e13 here, so two direct solvers agree to ~1e-6 on u (1e-10 is a statement about
+    well-conditioned lattices); the closed-form tip deflection of a uniform cantilever pins the absolute value."""
+    from oracle import cpu_baseline as CB
+    n_models, n_el = 67, 2000
+    p = meshgen.batch_cantilever_params(n_models)
+    t = np.linspace(0.0, 1.0, n_el + 1) ** 1.1 * 4.0          # graded spacing
+    xyz = np.stack([t, 0.05 * t, 0.02 * t], axis=1)           # inclined: generic rotation matrices
+    nn = n_el + 1
+    props = np.array([csp("rectangular section", {"d": d, "b": b}) for d, b in zip(p["d"], p["b"])])
+    fixed_mask = np.zeros(6 * nn, dtype=np.uint8)
+    fixed_mask[:6] = 1
+    f = np.zeros((n_models, 6 * nn))
+    f[:, 6 * (nn - 1) + 1] = p["tip_fy"]
+    f[:, 8::6] += p["nodal_fz"][:, None]
+    E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+    m = FrameModel(0)
+    u, st = m.batch_solve(xyz, props, E, E / (2 * (1 + nu)), fixed_mask, f)
+    u_again, _ = m.batch_solve(xyz, props, E, E / (2 * (1 + nu)), fixed_mask, f)
+    m.close()
+    assert st["converged"] == 1 and np.array_equal(u, u_again)
+    sel = [0, 29, 30, n_models - 1]
+    uo, _ = CB.chain_batch_solve(xyz, props[sel], E, E / (2 * (1 + nu)), fixed_mask, f[sel], len(sel))
+    for j, i in enumerate(sel):
+        assert np.linalg.norm(u[i] - uo[j]) <= 2e-5 * np.linalg.norm(uo[j]), (i, np.linalg.norm(u[i] - uo[j]) / np.linalg.norm(uo[j]))
+    # straight uniform cantilever, tip load only: u_y(tip) = P L^3 / (3 E I) + P L / (kappa G A)
+    xs = np.stack([np.linspace(0.0, 4.0, nn), np.zeros(nn), np.zeros(nn)], axis=1)
+    f1 = np.zeros((n_models, 6 * nn))
+    f1[:, 6 * (nn - 1) + 1] = p["tip_fy"]
+    m = FrameModel(0)
+    u1, _ = m.batch_solve(xs, props, E, E / (2 * (1 + nu)), fixed_mask, f1)
+    m.close()
+    G_ = E / (2 * (1 + nu))
+    A, Iy, ky = props[:, 0], props[:, 2], props[:, 4]
+    tip = p["tip_fy"] * 4.0 ** 3 / (3 * E * Iy) + p["tip_fy"] * 4.0 / (ky * G_ * A)
+    err = np.abs(u1[:, 6 * (nn - 1) + 1] - tip) / np.abs(tip)
+    assert err.max() <= 1e-4, err.max()          # eps * cond(K) ~ 1e-16 * (L/h)^4 = 1.6e-3 is the worst case
