@@ -219,7 +219,7 @@ struct femb_handle {
   int32_t ln_n_ranges = 0, ln_max_len = 0;
   femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle,
       ln_bundle_ids, ln_bundle_cnt, ln_line_range;
-  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_yb, ln_inv, ln_gal, ln_node_dir, ln_line_sum;
+  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_rbt, ln_yb, ln_inv, ln_gal, ln_node_dir, ln_line_sum;
   femb::DevBuf<unsigned long long> mega_state;   // persistent PCG kernel: grid barrier words + per-phase clocks
 
   // row-block distributed solve (dist.cu): this rank owns the first n_owned_nodes local nodes
@@ -246,7 +246,7 @@ struct femb_handle {
   long long p2p_seq_base = 0;
   std::vector<void*> p2p_mapped;
   femb::DevBuf<char> p2p_dev_copy;         // device-resident P2PDev for the fused kernels
-  femb::DevBuf<int32_t> p2p_send_slot, p2p_extra, p2p_bnd_nodes;
+  femb::DevBuf<int32_t> p2p_send_slot, p2p_extra, p2p_bnd_nodes, p2p_bnd_dst_ptr, p2p_bnd_dst;
 
   // batched chain solve (direct.cu): persistent device buffers and the host ranges page-locked in place
   femb::DevBuf<double> batch_f, batch_u, batch_W, batch_z;

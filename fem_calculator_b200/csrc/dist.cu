@@ -691,8 +691,11 @@ int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128) {
   // 2 MB, so that it is never a sub-allocation of a block shared with other buffers: the IPC
   // handle then maps exactly this memory at offset 0 in every peer.
   const size_t zbytes = ((size_t)h->ndof * sizeof(double) + 255) / 256 * 256;
-  const size_t rbbytes = (size_t)h->dist_world * 2 * kLnMaxCoarse * sizeof(double);   // coarse-residual mail of lines.cu
-  const size_t bytes = std::max<size_t>(kP2PZOffset + zbytes + rbbytes, (size_t)4 << 20);
+  // behind z: the flag-in-data slots of the persistent line-preconditioned PCG (lines.cu; 16 bytes per value):
+  // scalars [world][2][4] | coarse residuals [world][2][kLnMaxCoarse] | halo [ghost nodes][6]
+  const size_t n_ghost = (size_t)(h->n_nodes - h->n_owned_nodes);
+  const size_t llbytes = kLLScalBytes + ((size_t)h->dist_world * 2 * kLnMaxCoarse + n_ghost * 6) * sizeof(uint4);
+  const size_t bytes = std::max<size_t>(kP2PZOffset + zbytes + llbytes, (size_t)4 << 20);
   h->z.release();                       // z moves into the exported allocation
   FEMB_CUDA(h, h->p2p_comm.alloc(bytes));
   FEMB_CUDA(h, cudaMemset(h->p2p_comm.p, 0, bytes));
@@ -702,8 +705,10 @@ int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   std::memset(handles128, 0, 128);
   std::memcpy(handles128, &hc, 64);
-  const unsigned long long zb = zbytes;            // where this rank's coarse-residual mail starts behind its z vector
+  const unsigned long long zb = zbytes;            // where this rank's flag-in-data slots start behind its z vector
   std::memcpy(handles128 + 64, &zb, sizeof(zb));
+  const long long no = h->n_owned_nodes;           // ... and where its ghost tail starts (halo slots are indexed from there)
+  std::memcpy(handles128 + 72, &no, sizeof(no));
   h->p2p_z_exported = h->z.p;
   return FEMB_OK;
 }
@@ -723,12 +728,7 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
   pd->my_halo_flag = flag_of(cb);
   h->p2p_base_dev = flag_of(cb) + world;
   h->p2p_ticket = reinterpret_cast<int*>(flag_of(cb) + world + 1);
-  // header continues: [rb flags (world)] [ticket2]; the coarse-residual mail follows the z vector
   const size_t zbytes = ((size_t)h->ndof * sizeof(double) + 255) / 256 * 256;
-  auto rbflag_of = [&](char* base) { return flag_of(base) + world + 2; };
-  pd->my_rbflag = rbflag_of(cb);
-  pd->ticket2 = reinterpret_cast<int*>(rbflag_of(cb) + world);
-  pd->ticket3 = reinterpret_cast<int*>(rbflag_of(cb) + world + 1);
   pd->base = h->p2p_base_dev;
   pd->world = world; pd->rank = rank;
   std::vector<char*> peer_comm(world, nullptr);
@@ -744,14 +744,22 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
   for (int p = 0; p < world; ++p) pd->peer_mail[p] = mail_of(peer_comm[p]);
   // every rank's local vector has its own length, so a peer's mail area sits behind ITS z: the offsets travel with the
   // handles (femb_dist_p2p_export writes the rank's z bytes into its 128-byte blob)
+  std::vector<uint4*> peer_halo(world, nullptr);
+  std::vector<long long> peer_owned(world, 0);
   for (int p = 0; p < world; ++p) {
     unsigned long long zb = 0;
     std::memcpy(&zb, all_handles + (size_t)p * 128 + 64, sizeof(zb));
-    if (p == rank) zb = zbytes;
-    pd->peer_rbmail[p] = reinterpret_cast<double*>(peer_comm[p] + kP2PZOffset + zb);
-    pd->peer_rbflag[p] = rbflag_of(peer_comm[p]);
+    std::memcpy(&peer_owned[p], all_handles + (size_t)p * 128 + 72, sizeof(long long));
+    if (p == rank) { zb = zbytes; peer_owned[p] = h->n_owned_nodes; }
+    char* ll = peer_comm[p] + kP2PZOffset + zb;
+    pd->peer_ll_scal[p] = reinterpret_cast<uint4*>(ll);
+    pd->peer_ll_rb[p] = reinterpret_cast<uint4*>(ll + kLLScalBytes);
+    peer_halo[p] = pd->peer_ll_rb[p] + (size_t)world * 2 * kLnMaxCoarse;
   }
-  pd->my_rbmail = pd->peer_rbmail[rank];
+  pd->my_ll_scal = pd->peer_ll_scal[rank];
+  pd->my_ll_rb = pd->peer_ll_rb[rank];
+  pd->my_ll_halo = peer_halo[rank];
+  pd->n_owned = h->n_owned_nodes;
   pd->n_nbr = (int)h->dist_nbr.size();
   if (pd->n_nbr > kMaxRanks) { delete pd; return fail(h, FEMB_ERR_ARG, "too many neighbour ranks"); }
   for (int k = 0; k < pd->n_nbr; ++k) {
@@ -761,6 +769,9 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
     pd->peer_halo_flag[k] = flag_of(peer_comm[p]);
     pd->nbr[k] = p;
     pd->send_ptr[k] = h->dist_send_ptr[k];
+    pd->peer_ll_halo[k] = peer_halo[p] + (size_t)(peer_ghost_start[k] - peer_owned[p]) * 6;
+    pd->recv_start[k] = h->dist_recv_start[k];
+    pd->recv_count[k] = h->dist_recv_count[k];
   }
   pd->send_ptr[pd->n_nbr] = h->dist_send_ptr.back();
   // fused mode tables: destination of every owned node's entries
@@ -779,13 +790,27 @@ int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64
         else { extra.push_back(node); extra.push_back(sl); }
       }
     if (ok) {
-      std::vector<int32_t> bnd;
+      // boundary nodes (ascending) and, per boundary node, all its destinations (k << 28 | offset among MY nodes at k)
+      std::vector<std::vector<int32_t>> dst_of((size_t)h->n_owned_nodes);
+      for (int k = 0; k < pd->n_nbr; ++k)
+        for (int64_t i = h->dist_send_ptr[k]; i < h->dist_send_ptr[k + 1]; ++i)
+          dst_of[snodes[i]].push_back((int32_t)((k << 28) | (int32_t)(i - h->dist_send_ptr[k])));
+      std::vector<int32_t> bnd, dptr(1, 0), dst;
       for (int64_t i = 0; i < h->n_owned_nodes; ++i)
-        if (slot[i] >= 0) bnd.push_back((int32_t)i);
+        if (slot[i] >= 0) {
+          bnd.push_back((int32_t)i);
+          dst.insert(dst.end(), dst_of[i].begin(), dst_of[i].end());
+          dptr.push_back((int32_t)dst.size());
+        }
       pd->n_bnd = (int)bnd.size();
       if (bnd.empty()) bnd.push_back(0);
+      if (dst.empty()) dst.push_back(0);
       FEMB_CUDA(h, upload(h->p2p_bnd_nodes, bnd, h->stream));
+      FEMB_CUDA(h, upload(h->p2p_bnd_dst_ptr, dptr, h->stream));
+      FEMB_CUDA(h, upload(h->p2p_bnd_dst, dst, h->stream));
       pd->bnd_nodes = h->p2p_bnd_nodes.p;
+      pd->bnd_dst_ptr = h->p2p_bnd_dst_ptr.p;
+      pd->bnd_dst = h->p2p_bnd_dst.p;
       FEMB_CUDA(h, upload(h->p2p_send_slot, slot, h->stream));
       if (extra.empty()) { extra.push_back(0); extra.push_back(0); pd->n_extra = 0; }
       else pd->n_extra = (int)(extra.size() / 2);

@@ -21,6 +21,7 @@
 // sums, bit-reproducible):  operator (ebe.cu) -> ln_update (p, q, x, r; ||r||^2) -> ln_solve (line solves,
 // bundle residuals) -> ln_coarse (dense products) -> ln_prolong (z = M^-1 r; (r, z)).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -51,7 +52,8 @@ struct LnDev {
   double* node_w;               // (F, N, 3)      the same, indexed by (family, node); zero where the node has no line
   double* fac;                  // (n_entries, 3) {1/delta, forward coefficient, backward coefficient}
   double* yl;                   // (F, N) line-solve amplitude of the node's line entry
-  double* rb;                   // (n_coarse) bundle residuals
+  double* rb;                   // (n_coarse) bundle residuals (row-block partition: this rank's partial sums)
+  double* rbt;                  // (n_coarse) bundle residuals the coarse products read (= rb; partition: the sum over ranks)
   double* line_sum;             // (n_lines) axial residual sum of every line (persistent kernel: bundles are summed from these)
   int32_t max_len;              // longest line (entries)
   int32_t* bundle_cnt;          // (bundle_ptr ranges) lines of each bundle finished in the current pass (persistent kernel)
@@ -463,6 +465,7 @@ struct MegaArgs {
   int* flags;
   unsigned int* bar;     // [0] arrive counter, [1] generation
   unsigned long long* phase_ns;   // [8] time spent per phase (CTA 0), accumulated
+  double* glob;          // [4] DIST: {delta, gamma, ||r||^2} of the world, written by CTA 0 before the barrier
   int64_t n;             // ndof
   int n_nodes, n_ranges, pstride;
   int it0, n_iters, max_iter, init;
@@ -504,21 +507,22 @@ __device__ __forceinline__ double mega_total(const double* part, int cnt, double
 }
 
 // DIST (one rank of a row-block partition, dist.cu): the same kernel on the owned rows; the three exchanges with the
-// other GPUs happen INSIDE the launch, through peer memory:
-//   halo        the prolongation handles the nodes a neighbour needs first and releases the neighbours' halo flags
-//               while the interior is still running; the operator phase polls its own flags before it starts;
+// other GPUs happen INSIDE the launch, through peer memory, as flag-in-data stores (P2PDev in pcg_common.cuh: every
+// value is one 16-byte store that carries its own sequence flag, the receiver polls the value's slot — no system
+// fence, no separate flag, no extra grid barrier to hand a "it has landed" on):
+//   halo        the prolongation handles the nodes a neighbour needs first and stores their z into the neighbour's
+//               halo slots; after its interior nodes every CTA unpacks a share of the rank's own halo slots into the
+//               ghost tail of z (by then the values have usually landed);
 //   scalars     after the operator's barrier CTA 0 stores the rank's {delta, gamma, ||r||^2} into every rank's
-//               mailbox; every CTA adds the world's entries in rank order (identical on every rank);
-//   coarse      after the line phase CTA p stores the rank's partial bundle residuals into rank p's mail area; the
-//               coarse phase adds the world's partials in rank order.
+//               slots, adds the world's entries in rank order (identical on every rank) and leaves the totals
+//               behind the next barrier;
+//   coarse      after the line phase CTA p stores the rank's partial bundle residuals into rank p's slots; the next
+//               CTAs add the world's partials in rank order as they land.
 // Sequence numbers = per-solve base + iteration; waits are bounded (a lost peer sets DONE = 4).
 template <bool DIST>
 __global__ void __launch_bounds__(kMegaThreads, 4)
 ln_pcg_mega_kernel(const MegaArgs A) {
   __shared__ double s_part[2 * kMegaThreads / 32];
-  __shared__ double s_rb[DIST ? 1024 : 1];
-  __shared__ double s_glob[3];
-  __shared__ int s_flag;
   const LnDev& T = A.T;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const unsigned int nb = gridDim.x;
@@ -537,67 +541,35 @@ ln_pcg_mega_kernel(const MegaArgs A) {
     mega_barrier(A.bar, nb);
     lap(2);
     if constexpr (DIST) {
+      // bundle residuals of the world: CTA p copies this rank's partial sums into rank p's slots (flag-in-data, no
+      // fence); the next CTAs add the world's slots in rank order as they land -> rbt
       const P2PDev* pd = A.p2p;
       const int par = (int)(seq & 1);
-      if (cta < pd->world) {                      // CTA p -> rank p
-        double* dst = pd->peer_rbmail[cta] + (size_t)(pd->rank * 2 + par) * kLnMaxCoarse;
-        for (int k = threadIdx.x; k < T.n_coarse; k += kMegaThreads) dst[k] = __ldcg(T.rb + k);
-        __syncthreads();
-        if (threadIdx.x == 0) { __threadfence_system(); st_release_sys(pd->peer_rbflag[cta] + pd->rank, seq); }
-      }
-      // only CTA 0 polls the flags the peers write (hundreds of CTAs polling one line cost ~20 us per exchange); the
-      // grid barrier hands the visibility on to everybody else
-      if (cta == 0 && (int)threadIdx.x < pd->world) {
-        long long spins = 0;
-        while (ld_acquire_sys(pd->my_rbflag + threadIdx.x) != seq) {
-          if (++spins > kSpinLimit) { A.flags[Flag::DONE] = 4; break; }
+      const unsigned flag = (unsigned)seq;
+      if (cta < pd->world) {
+        uint4* dst = pd->peer_ll_rb[cta] + (size_t)(pd->rank * 2 + par) * kLnMaxCoarse;
+        for (int k = threadIdx.x; k < T.n_coarse; k += kMegaThreads) ll_store(dst + k, __ldcg(T.rb + k), flag);
+      } else {
+        for (int k = (cta - pd->world) * kMegaThreads + threadIdx.x; k < T.n_coarse; k += (ncta - pd->world) * kMegaThreads) {
+          double t = 0.0;
+          for (int pr = 0; pr < pd->world; ++pr) {
+            double v;
+            if (!ll_wait(pd->my_ll_rb + (size_t)(pr * 2 + par) * kLnMaxCoarse + k, flag, v)) A.flags[Flag::DONE] = 4;
+            t += v;
+          }
+          T.rbt[k] = t;
         }
       }
       mega_barrier(A.bar, nb);
     }
-    if constexpr (DIST) {
-      // coarse products; the family's bundle residuals = sum over the ranks' partials (rank order) in shared memory
-      constexpr int NW = kMegaThreads / 32;
-      const P2PDev* pd = A.p2p;
-      const int par = (int)(seq & 1);
-      const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-      for (int c0 = cta * NW; c0 < T.n_coarse; c0 += ncta * NW) {
-        const int c = c0 + wl;
-        const int f_lo = ln_family_of(T, c0), f_hi = ln_family_of(T, min(c0 + NW - 1, T.n_coarse - 1));
-        for (int f = f_lo; f <= f_hi; ++f) {
-          const int off = T.fam_off[f], nf = T.fam_off[f + 1] - off;
-          for (int k = threadIdx.x; k < nf; k += kMegaThreads) {
-            double t = 0.0;
-            for (int pr = 0; pr < pd->world; ++pr)
-              t += *reinterpret_cast<const volatile double*>(pd->my_rbmail + (size_t)(pr * 2 + par) * kLnMaxCoarse + off + k);
-            s_rb[k] = t;
-          }
-          __syncthreads();
-          if (c < T.n_coarse && ln_family_of(T, c) == f) {
-            const double* inv_row = T.inv + T.inv_off[f] + (size_t)(c - off) * T.fam_pad[f];
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int k = lane;
-#pragma unroll 2
-            for (; k + 96 < nf; k += 128) {
-              const double m0 = __ldg(inv_row + k), m1 = __ldg(inv_row + k + 32), m2 = __ldg(inv_row + k + 64), m3 = __ldg(inv_row + k + 96);
-              a0 = fma(m0, s_rb[k], a0); a1 = fma(m1, s_rb[k + 32], a1);
-              a2 = fma(m2, s_rb[k + 64], a2); a3 = fma(m3, s_rb[k + 96], a3);
-            }
-            for (; k < nf; k += 32) a0 = fma(__ldg(inv_row + k), s_rb[k], a0);
-            const double acc = warp_sum((a0 + a1) + (a2 + a3));
-            if (lane == 0) T.yb[c] = acc;
-          }
-          __syncthreads();
-        }
-      }
-    } else {   // coarse products: one warp per row, rows dealt to the grid's warps
+    {   // coarse products: one warp per row, rows dealt to the grid's warps
       const int lane = threadIdx.x & 31;
       const int nwarp = ncta * (kMegaThreads / 32);
       for (int c = cta * (kMegaThreads / 32) + (threadIdx.x >> 5); c < T.n_coarse; c += nwarp) {
         const int f = ln_family_of(T, c);
         const int off = T.fam_off[f], nf = T.fam_off[f + 1] - off;
         const double* inv_row = T.inv + T.inv_off[f] + (size_t)(c - off) * T.fam_pad[f];
-        const double* rb = T.rb + off;
+        const double* rb = T.rbt + off;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int k = lane;
 #pragma unroll 2
@@ -641,37 +613,20 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       g += ra.x * zt[0] + ra.y * zt[1] + rb2.x * zt[2] + rb2.y * zt[3] + rc.x * zt[4] + rc.y * zt[5];
     };
     if constexpr (DIST) {
-      // the nodes a neighbour needs first: z straight into the neighbours' ghost tails, halo flags released by the
-      // last CTA to finish them (ticket) while everybody moves on to the interior
+      // the nodes a neighbour needs first: their z goes out as flag-in-data stores into the neighbours' halo slots and
+      // is on the wire while the interior runs
       const P2PDev* pd = A.p2p;
-      bool pushed = false;
+      const unsigned hflag = (unsigned)(seq + 1);
       for (int k = cta * kMegaThreads + threadIdx.x; k < pd->n_bnd; k += ncta * kMegaThreads) {
         const int node = __ldg(pd->bnd_nodes + k);
         double zt[6];
         prolong_node(node, zt);
-        const int sl = __ldg(pd->send_slot + node);
-        double* dst = pd->peer_z[sl >> 28] + (size_t)(sl & 0xFFFFFFF) * 6;
+        for (int d = __ldg(pd->bnd_dst_ptr + k); d < __ldg(pd->bnd_dst_ptr + k + 1); ++d) {
+          const int sl = __ldg(pd->bnd_dst + d);
+          uint4* dst = pd->peer_ll_halo[sl >> 28] + (size_t)(sl & 0xFFFFFFF) * 6;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) dst[c] = zt[c];
-        pushed = true;
-      }
-      const int any_pushed = __syncthreads_or(pushed ? 1 : 0);
-      if (threadIdx.x == 0) {
-        if (any_pushed) __threadfence_system();     // the CTA's remote stores (ordered before by the barrier) are out
-        else __threadfence();
-        s_flag = (atomicAdd(pd->ticket3, 1) == (int)nb - 1);
-      }
-      __syncthreads();
-      if (s_flag) {
-        __threadfence();
-        for (int e = threadIdx.x; e < pd->n_extra * 6; e += kMegaThreads) {
-          const int i = e / 6, c = e - i * 6;
-          const int node = pd->extra[2 * i], sl = pd->extra[2 * i + 1];
-          pd->peer_z[sl >> 28][(size_t)(sl & 0xFFFFFFF) * 6 + c] = __ldcg(A.z + (size_t)node * 6 + c);
+          for (int c = 0; c < 6; ++c) ll_store(dst + c, zt[c], hflag);
         }
-        __syncthreads();
-        if ((int)threadIdx.x < pd->n_nbr) { __threadfence_system(); st_release_sys(pd->peer_halo_flag[threadIdx.x] + pd->rank, seq + 1); }
-        if (threadIdx.x == 0) *pd->ticket3 = 0;
       }
       for (int node = cta * kMegaThreads + threadIdx.x; node < A.n_nodes; node += ncta * kMegaThreads) {
         if (__ldg(pd->send_slot + node) >= 0) continue;
@@ -688,12 +643,17 @@ ln_pcg_mega_kernel(const MegaArgs A) {
     block_sum_all<kMegaThreads, 1>(v, s_part);
     if (threadIdx.x == 0) part_gamma[cta] = v[0];
     if constexpr (DIST) {
-      // the neighbours' halo for the next operator phase: CTA 0 waits, the barrier below passes it on
+      // the neighbours' halo for the next operator phase: unpack the slots into the ghost tail of z as they land (the
+      // grid starts from its last CTA: the first ones carry the boundary nodes above)
       const P2PDev* pd = A.p2p;
-      if (cta == 0 && (int)threadIdx.x < pd->n_nbr) {
-        long long spins = 0;
-        while (ld_acquire_sys(pd->my_halo_flag + pd->nbr[threadIdx.x]) < seq + 1) {
-          if (++spins > kSpinLimit) { A.flags[Flag::DONE] = 4; break; }
+      const unsigned hflag = (unsigned)(seq + 1);
+      for (int kn = 0; kn < pd->n_nbr; ++kn) {
+        const long long first = pd->recv_start[kn] * 6, cnt = pd->recv_count[kn] * 6;
+        const uint4* src = pd->my_ll_halo + (first - pd->n_owned * 6);
+        for (long long e = (long long)(ncta - 1 - cta) * kMegaThreads + threadIdx.x; e < cnt; e += (long long)ncta * kMegaThreads) {
+          double v;
+          if (!ll_wait(src + e, hflag, v)) A.flags[Flag::DONE] = 4;
+          A.z[first + e] = v;
         }
       }
     }
@@ -744,40 +704,32 @@ ln_pcg_mega_kernel(const MegaArgs A) {
     lap(0);
     delta = mega_total<kMegaThreads>(part_delta, ncta, s_part);
     if constexpr (DIST) {
-      // {delta, gamma, ||r||^2} of the world: CTA 0 posts this rank's, every CTA adds all ranks' in rank order
+      // {delta, gamma, ||r||^2} of the world: CTA 0 stores this rank's three into every rank's slots (flag-in-data),
+      // adds the world's in rank order as they land (identical on every rank) and leaves the totals for everybody
+      // behind the barrier
       const P2PDev* pd = A.p2p;
       const long long seq = pd->base[0] + it + 1;
-      if (cta == 0 && (int)threadIdx.x < pd->world) {
-        MailSlot* dst = pd->peer_mail[threadIdx.x] + (pd->rank * 2 + (int)(seq & 1));
-        dst->v[0] = delta; dst->v[1] = gamma; dst->v[2] = rr; dst->v[3] = 0.0;
-        __threadfence_system();
-        st_release_sys(&dst->seq, seq);
-        const MailSlot* src = pd->my_mail + (threadIdx.x * 2 + (int)(seq & 1));
-        long long spins = 0;
-        while (ld_acquire_sys(&src->seq) != seq) {
-          if (++spins > kSpinLimit) { A.flags[Flag::DONE] = 4; break; }
-        }
-      }
-      mega_barrier(A.bar, nb);                      // CTA 0 arrives once every rank's entry has landed
-      if (threadIdx.x < 32) {
+      const int par = (int)(seq & 1);
+      const unsigned flag = (unsigned)seq;
+      if (cta == 0 && threadIdx.x < 32) {
         const int lane = threadIdx.x;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        bool ok = true;
         if (lane < pd->world) {
-          const MailSlot* src = pd->my_mail + (lane * 2 + (int)(seq & 1));
-          v0 = *reinterpret_cast<const volatile double*>(&src->v[0]);
-          v1 = *reinterpret_cast<const volatile double*>(&src->v[1]);
-          v2 = *reinterpret_cast<const volatile double*>(&src->v[2]);
+          uint4* dst = pd->peer_ll_scal[lane] + (pd->rank * 2 + par) * 4;
+          ll_store(dst, delta, flag); ll_store(dst + 1, gamma, flag); ll_store(dst + 2, rr, flag);
+          const uint4* src = pd->my_ll_scal + (lane * 2 + par) * 4;
+          ok = ll_wait(src, flag, v0) & ll_wait(src + 1, flag, v1) & ll_wait(src + 2, flag, v2);
         }
-        const bool lost = (*reinterpret_cast<volatile int*>(A.flags + Flag::DONE) == 4);
+        const bool lost = __any_sync(0xffffffffu, !ok) || (*reinterpret_cast<volatile int*>(A.flags + Flag::DONE) == 4);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         for (int pr = 0; pr < pd->world; ++pr) {
           a0 += __shfl_sync(0xffffffffu, v0, pr); a1 += __shfl_sync(0xffffffffu, v1, pr); a2 += __shfl_sync(0xffffffffu, v2, pr);
         }
-        if (lane == 0) { s_glob[0] = a0; s_glob[1] = a1; s_glob[2] = lost ? -1.0 : a2; }
+        if (lane == 0) { A.glob[0] = a0; A.glob[1] = a1; A.glob[2] = lost ? -1.0 : a2; }
       }
-      __syncthreads();
-      delta = s_glob[0]; gamma = s_glob[1]; rr = s_glob[2];
-      __syncthreads();
+      mega_barrier(A.bar, nb);                      // CTA 0 arrives once every rank's entry has landed
+      delta = __ldcg(A.glob); gamma = __ldcg(A.glob + 1); rr = __ldcg(A.glob + 2);
       if (rr < 0.0) { done = 4; break; }          // a peer never answered
       if (it == 0) {
         tol2 = A.rtol * A.rtol * rr;
@@ -860,6 +812,7 @@ static int upload_line_tables(femb_handle* h) {
     FEMB_CUDA(h, h->ln_node_w.alloc((size_t)kLnMaxFam * h->n_nodes * 3));
     FEMB_CUDA(h, h->ln_yl.alloc((size_t)kLnMaxFam * h->n_nodes));
     FEMB_CUDA(h, h->ln_rb.alloc((size_t)S.n_coarse));
+    FEMB_CUDA(h, h->ln_rbt.alloc((size_t)S.n_coarse));
     FEMB_CUDA(h, h->ln_yb.alloc((size_t)S.n_coarse));
     FEMB_CUDA(h, h->ln_line_sum.alloc((size_t)S.n_lines));
     FEMB_CUDA(h, h->ln_bundle_cnt.alloc((size_t)std::max<size_t>(1, S.bundle_ptr.size())));
@@ -928,7 +881,7 @@ static LnDev ln_dev(const femb_handle* h) {
   T.ent_node = h->ln_ent_node.p; T.ent_blk_diag = h->ln_ent_blk_diag.p; T.ent_blk_next = h->ln_ent_blk_next.p;
   T.node_bundle = h->ln_node_bundle.p; T.bundle_ids = h->ln_bundle_ids.p; T.node_dir = h->ln_node_dir.p;
   T.ent_w = h->ln_ent_w.p; T.node_w = h->ln_node_w.p; T.fac = h->ln_fac.p;
-  T.yl = h->ln_yl.p; T.rb = h->ln_rb.p; T.yb = h->ln_yb.p; T.inv = h->ln_inv.p;
+  T.yl = h->ln_yl.p; T.rb = h->ln_rb.p; T.rbt = h->line_dist ? h->ln_rbt.p : h->ln_rb.p; T.yb = h->ln_yb.p; T.inv = h->ln_inv.p;
   T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p; T.line_range = h->ln_line_range.p;
   for (int f = 0; f < kLnMaxFam; ++f) { T.inv_off[f] = h->ln_inv_off[f]; T.fam_pad[f] = h->ln_fam_pad[f]; }
   T.coarse_blk_off[0] = 0;
@@ -1027,9 +980,10 @@ bool lines_applicable(femb_handle* h, const femb_solve_opts& o) {
 
 // launches of the persistent kernel until the solve is over; `dist`: this rank's part of a row-block partition
 static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st, bool dist) {
+  const auto t_host0 = std::chrono::steady_clock::now();
   const int pstride = h->num_sms * 8;
   FEMB_CUDA(h, h->fpartials.ensure((size_t)pstride * 6));
-  FEMB_CUDA(h, h->mega_state.ensure(16));          // [0] barrier words, [2..] phase clocks (8 x u64)
+  FEMB_CUDA(h, h->mega_state.ensure(32));          // [0] barrier words, [2..10) phase clocks (8 x u64), [16..20) world scalars
   FEMB_CUDA(h, cudaMemsetAsync(h->mega_state.p, 0, h->mega_state.bytes(), h->stream));
   FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
   FEMB_CUDA(h, cudaMemsetAsync(h->scal.p, 0, sizeof(double) * Scal::COUNT, h->stream));
@@ -1050,6 +1004,7 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   A.part = h->fpartials.p; A.scal = h->scal.p; A.flags = h->flags.p;
   A.bar = reinterpret_cast<unsigned int*>(h->mega_state.p);
   A.phase_ns = h->mega_state.p + 2;
+  A.glob = reinterpret_cast<double*>(h->mega_state.p + 16);
   A.n_nodes = (int)(dist ? h->n_owned_nodes : h->n_nodes);
   A.n = (int64_t)A.n_nodes * 6;
   A.n_ranges = h->ln_n_ranges; A.pstride = pstride;
@@ -1093,10 +1048,11 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
     st->spmv_timed = peek->flags[Flag::ITERS];
     if (getenv("FEMB_TRACE"))
       fprintf(stderr, "[femb trace] persistent PCG: %d iterations in %d launches; per-iteration phase times (CTA 0): operator %.2f us, "
-              "update %.2f, line solves %.2f, coarse %.2f, prolongation %.2f\n", st->iterations, launches,
+              "update %.2f, line solves %.2f, coarse %.2f, prolongation %.2f; host wall of the call %.3f ms\n", st->iterations, launches,
               peek->ns[0] * 1e-3 / std::max(1, st->iterations), peek->ns[1] * 1e-3 / std::max(1, st->iterations),
               peek->ns[2] * 1e-3 / std::max(1, st->iterations), peek->ns[3] * 1e-3 / std::max(1, st->iterations),
-              peek->ns[4] * 1e-3 / std::max(1, st->iterations));
+              peek->ns[4] * 1e-3 / std::max(1, st->iterations),
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
   }
   if (done == 4) return fail(h, FEMB_ERR_CUDA, "peer-memory exchange timed out waiting for another rank");
   if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");

@@ -195,19 +195,28 @@ struct P2PDev {
   const int32_t* send_slot;
   const int32_t* extra;      // (n_extra, 2)
   int n_extra;
-  // coarse residuals of the line preconditioner (lines.cu): every rank stores its partial bundle residuals into
-  // every rank's mail area [source rank][parity][kLnMaxCoarse] and releases the flag [source rank]
-  double* peer_rbmail[kMaxRanks];     // per RANK p
-  long long* peer_rbflag[kMaxRanks];  // per RANK p
-  double* my_rbmail;
-  long long* my_rbflag;
-  int* ticket2;
-  // owned nodes with at least one remote destination, ascending (the prolongation handles them first and releases
-  // the halo flags before it touches the interior)
+  // ---- persistent line-preconditioned PCG (lines.cu): flag-in-data exchanges -------------------------------------
+  // Every value travels as ONE 16-byte store {low word, flag, high word, flag} (flag = low 32 bits of the exchange's
+  // sequence number): the receiver polls the slot itself until both flags match, so no system-scope fence, no separate
+  // flag store and no second round trip sit between "value produced" and "value usable" (the fence + release-flag form
+  // of the other kernels costs 10-20 us per exchange inside a 90 us iteration; this form 2-3).
+  uint4* peer_ll_scal[kMaxRanks];     // per RANK p: its scalar slots   [source rank][parity][4]
+  uint4* my_ll_scal;
+  uint4* peer_ll_rb[kMaxRanks];       // per RANK p: its coarse-residual slots [source rank][parity][kLnMaxCoarse]
+  uint4* my_ll_rb;
+  uint4* peer_ll_halo[kMaxRanks];     // per neighbour k: the slots of MY nodes in its ghost tail (6 per node)
+  uint4* my_ll_halo;                  // [ghost node - n_owned][6]
+  long long recv_start[kMaxRanks];    // per neighbour k: first local (ghost) node it fills, and how many
+  long long recv_count[kMaxRanks];
+  long long n_owned;
+  // owned nodes with at least one remote destination, ascending (the prolongation handles them first so that their
+  // values are on the wire while the interior runs), and their destinations (k << 28 | node offset in peer_ll_halo[k])
   const int32_t* bnd_nodes;
+  const int32_t* bnd_dst_ptr;         // (n_bnd + 1)
+  const int32_t* bnd_dst;
   int n_bnd;
-  int* ticket3;
 };
+constexpr size_t kLLScalBytes = (size_t)kMaxRanks * 2 * 4 * sizeof(uint4);   // scalar slots of the flag-in-data exchange
 constexpr int kLnMaxCoarse = 3072;    // capacity of the coarse-residual mail slots (3 families x 1024 bundles)
 
 __device__ __forceinline__ void st_release_sys(long long* p, long long v) {
@@ -219,6 +228,26 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
   return v;
 }
 constexpr long long kSpinLimit = 1ll << 24;   // several seconds of polling, then DONE = 4
+
+// flag-in-data slot (see P2PDev): 8-byte halves {data word, flag} are written / read atomically
+__device__ __forceinline__ void ll_store(uint4* slot, double v, unsigned flag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"((unsigned)b), "r"(flag),
+               "r"((unsigned)(b >> 32)), "r"(flag) : "memory");
+}
+// polls until the slot carries `flag`; false after kSpinLimit polls (a lost peer)
+__device__ __forceinline__ bool ll_wait(const uint4* slot, unsigned flag, double& v) {
+  for (long long spins = 0; spins < kSpinLimit; ++spins) {
+    unsigned a, f1, c, f2;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(f1), "=r"(c), "=r"(f2) : "l"(slot) : "memory");
+    if (f1 == flag && f2 == flag) {
+      v = __longlong_as_double((long long)(((unsigned long long)c << 32) | a));
+      return true;
+    }
+  }
+  v = 0.0;
+  return false;
+}
 
 // red[] slots of the distributed solver (doubles): the first three are all-reduced each iteration
 struct Red {
