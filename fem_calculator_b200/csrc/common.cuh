@@ -209,6 +209,7 @@ struct femb_handle {
 
   // line preconditioner (lines.cu): member lines, per-line tridiagonal factors, bundle coarse spaces
   bool line_sym_ok = false;       // line tables on the device match the current topology
+  bool ln_mask_ok = false;        // row-block partition: the bundles' owner masks are known
   bool line_num_ok = false;       // factors and inverses match the current K and BC mask
   bool line_failed = false;       // a bundle Galerkin matrix of the current K / BC could not be factored
   femb::LineSym line_sym;         // host copy (the per-entry tables are dropped after the upload)
@@ -218,7 +219,7 @@ struct femb_handle {
   int32_t ln_range_off[femb::kLnMaxFam + 1] = {0, 0, 0, 0};
   int32_t ln_n_ranges = 0, ln_max_len = 0;
   femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle,
-      ln_bundle_ids, ln_bundle_cnt, ln_line_range;
+      ln_bundle_ids, ln_bundle_cnt, ln_line_range, ln_rank_mask;
   femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_rbt, ln_yb, ln_inv, ln_gal, ln_node_dir, ln_line_sum;
   femb::DevBuf<unsigned long long> mega_state;   // persistent PCG kernel: grid barrier words + per-phase clocks
 

@@ -54,6 +54,7 @@ struct LnDev {
   double* yl;                   // (F, N) line-solve amplitude of the node's line entry
   double* rb;                   // (n_coarse) bundle residuals (row-block partition: this rank's partial sums)
   double* rbt;                  // (n_coarse) bundle residuals the coarse products read (= rb; partition: the sum over ranks)
+  const int32_t* rank_mask;     // (n_coarse) partition: bit p set = rank p owns a piece of the bundle (contributes to its residual)
   double* line_sum;             // (n_lines) axial residual sum of every line (persistent kernel: bundles are summed from these)
   int32_t max_len;              // longest line (entries)
   int32_t* bundle_cnt;          // (bundle_ptr ranges) lines of each bundle finished in the current pass (persistent kernel)
@@ -340,8 +341,11 @@ __device__ __forceinline__ double ln_solve_lines(const LnDev& T, const double* r
 // Lane l of a group holds entries l, l + LW, l + 2 LW, .. (coalesced table reads — with consecutive entries per lane
 // the 40 narrow loads of a lane each touched their own sector and the phase was bound by L1 wavefronts); the two
 // recurrences run as CH rounds of LW-wide affine scans with the carry handed from round to round.
-template <int THREADS, int LW>
-__device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double* r, int cta, int ncta) {
+// POST (row-block partition): the group that completes a bundle stores the rank's partial residual straight into every
+// rank's flag-in-data slot [this rank][parity][bundle] (lane p -> rank p) instead of into rb.
+template <int THREADS, int LW, bool POST>
+__device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double* r, int cta, int ncta,
+                                                    const P2PDev* pd = nullptr, long long seq = 0) {
   constexpr int CH = kLnMaxLen / LW;                  // rounds (LW = 16: 8 rounds cover 128 entries)
   constexpr int NG = THREADS / LW;
   const int lane = threadIdx.x & (LW - 1);
@@ -396,6 +400,8 @@ __device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double
     // line sum in a fixed order: per lane round by round, then the shuffle tree
 #pragma unroll
     for (int o = LW / 2; o > 0; o >>= 1) lsum += __shfl_down_sync(0xffffffffu, lsum, o, LW);
+    double t_post = 0.0;
+    int c_post = -1;
     if (on && lane == 0) {
       // the group that completes a bundle (integer ticket) adds the bundle's line sums in line order: the value does
       // not depend on which group that is
@@ -408,37 +414,18 @@ __device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double
         __threadfence();
         double t = 0.0;
         for (int l = b0; l < b1; ++l) t += __ldcg(T.line_sum + l);
-        T.rb[c] = t;
+        if constexpr (POST) { t_post = t; c_post = c; }
+        else T.rb[c] = t;
         T.bundle_cnt[rg] = 0;
       }
     }
+    if constexpr (POST) {
+      c_post = __shfl_sync(0xffffffffu, c_post, 0, LW);
+      t_post = __shfl_sync(0xffffffffu, t_post, 0, LW);
+      if (c_post >= 0 && lane < pd->world)
+        ll_store(pd->peer_ll_rb[lane] + (size_t)(pd->rank * 2 + (int)(seq & 1)) * kLnMaxCoarse + c_post, t_post, (unsigned)seq);
+    }
   }
-}
-
-template <int THREADS>
-__device__ __forceinline__ void ln_solve_bundle(const LnDev& T, const double* r, int rg, double* s_sum /* THREADS / 16 */) {
-  const int c = T.bundle_ids ? T.bundle_ids[rg] : rg;
-  const int f = ln_family_of(T, c);
-  const int l0 = T.bundle_ptr[rg], l1 = T.bundle_ptr[rg + 1];
-  bool small = true;                                 // every line of the bundle fits a half warp
-  for (int line = l0; line < l1; ++line) small = small && (T.line_ptr[line + 1] - T.line_ptr[line] <= 16 * (kLnMaxLen / 32));
-  int ng;
-  if (small) {
-    const double g = ln_solve_lines<THREADS, 16>(T, r, f, l0, l1);
-    if ((threadIdx.x & 15) == 0) s_sum[threadIdx.x >> 4] = g;
-    ng = THREADS / 16;
-  } else {
-    const double g = ln_solve_lines<THREADS, 32>(T, r, f, l0, l1);
-    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = g;
-    ng = THREADS / 32;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < ng; ++w) t += s_sum[w];
-    T.rb[c] = t;
-  }
-  __syncthreads();                                   // s_sum is reused by the caller's next bundle
 }
 
 // ---- the whole iteration as ONE persistent kernel (single GPU) --------------------------------------------------
@@ -491,6 +478,35 @@ __device__ __forceinline__ void mega_barrier(unsigned int* bar, unsigned int nb)
   __syncthreads();
 }
 
+// the same barrier; the LAST CTA to arrive runs `hook` (all its threads) before it releases the others: everything the
+// other CTAs published before arriving is visible to the hook, everything the hook writes is visible behind the barrier
+template <class F>
+__device__ __forceinline__ void mega_barrier_hook(unsigned int* bar, unsigned int nb, int* s_last, F hook) {
+  __syncthreads();
+  unsigned int gen = 0;
+  volatile unsigned int* vgen = bar + 1;
+  if (threadIdx.x == 0) {
+    gen = *vgen;
+    __threadfence();
+    *s_last = (atomicAdd(bar, 1u) == nb - 1) ? 1 : 0;
+    if (*s_last) __threadfence();
+  }
+  __syncthreads();
+  if (*s_last) {
+    hook();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bar[0] = 0;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    }
+  } else if (threadIdx.x == 0) {
+    while (*vgen == gen) { }
+  }
+  if (threadIdx.x == 0) __threadfence();
+  __syncthreads();
+}
+
 __device__ __forceinline__ unsigned long long mega_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -523,6 +539,7 @@ template <bool DIST>
 __global__ void __launch_bounds__(kMegaThreads, 4)
 ln_pcg_mega_kernel(const MegaArgs A) {
   __shared__ double s_part[2 * kMegaThreads / 32];
+  __shared__ int s_last;
   const LnDev& T = A.T;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const unsigned int nb = gridDim.x;
@@ -537,35 +554,37 @@ ln_pcg_mega_kernel(const MegaArgs A) {
   // one application of the preconditioner: z = M^-1 r, publishes the (r, z) partials.  DIST: `seq` numbers the
   // coarse-residual exchange of this application, seq + 1 the halo the next operator phase waits for.
   auto precond = [&](long long seq) {
-    ln_solve_lines_flat<kMegaThreads, 16>(T, A.r, cta, ncta);
-    mega_barrier(A.bar, nb);
-    lap(2);
     if constexpr (DIST) {
-      // bundle residuals of the world: CTA p copies this rank's partial sums into rank p's slots (flag-in-data, no
-      // fence); the next CTAs add the world's slots in rank order as they land -> rbt
+      // bundle residuals of the world: the line groups store this rank's partial sums straight into every rank's
+      // flag-in-data slots; right behind its own lines every CTA adds the contributing ranks' slots of a share of the
+      // bundles in rank order as they land -> rbt.  No barrier in between: the slots synchronise themselves.
       const P2PDev* pd = A.p2p;
+      ln_solve_lines_flat<kMegaThreads, 16, true>(T, A.r, cta, ncta, pd, seq);
       const int par = (int)(seq & 1);
       const unsigned flag = (unsigned)seq;
-      if (cta < pd->world) {
-        uint4* dst = pd->peer_ll_rb[cta] + (size_t)(pd->rank * 2 + par) * kLnMaxCoarse;
-        for (int k = threadIdx.x; k < T.n_coarse; k += kMegaThreads) ll_store(dst + k, __ldcg(T.rb + k), flag);
-      } else {
-        for (int k = (cta - pd->world) * kMegaThreads + threadIdx.x; k < T.n_coarse; k += (ncta - pd->world) * kMegaThreads) {
-          double t = 0.0;
-          for (int pr = 0; pr < pd->world; ++pr) {
+      for (int k = cta * kMegaThreads + threadIdx.x; k < T.n_coarse; k += ncta * kMegaThreads) {
+        const int mask = __ldg(T.rank_mask + k);
+        double t = 0.0;
+        for (int pr = 0; pr < pd->world; ++pr)
+          if ((mask >> pr) & 1) {
             double v;
             if (!ll_wait(pd->my_ll_rb + (size_t)(pr * 2 + par) * kLnMaxCoarse + k, flag, v)) A.flags[Flag::DONE] = 4;
             t += v;
           }
-          T.rbt[k] = t;
-        }
+        T.rbt[k] = t;
       }
-      mega_barrier(A.bar, nb);
+    } else {
+      ln_solve_lines_flat<kMegaThreads, 16, false>(T, A.r, cta, ncta);
     }
-    {   // coarse products: one warp per row, rows dealt to the grid's warps
+    mega_barrier(A.bar, nb);
+    lap(2);
+    {   // coarse products: one warp per row, rows dealt to the grid's warps (partition: only the rows of bundles this
+        // rank owns a piece of — the prolongation reads no others)
       const int lane = threadIdx.x & 31;
       const int nwarp = ncta * (kMegaThreads / 32);
-      for (int c = cta * (kMegaThreads / 32) + (threadIdx.x >> 5); c < T.n_coarse; c += nwarp) {
+      const int n_rows = DIST ? A.n_ranges : T.n_coarse;
+      for (int row = cta * (kMegaThreads / 32) + (threadIdx.x >> 5); row < n_rows; row += nwarp) {
+        const int c = DIST ? __ldg(T.bundle_ids + row) : row;
         const int f = ln_family_of(T, c);
         const int off = T.fam_off[f], nf = T.fam_off[f + 1] - off;
         const double* inv_row = T.inv + T.inv_off[f] + (size_t)(c - off) * T.fam_pad[f];
@@ -700,35 +719,39 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       block_sum_all<kMegaThreads, 1>(v, s_part);
       if (threadIdx.x == 0) part_delta[cta] = v[0];
     }
-    mega_barrier(A.bar, nb);
-    lap(0);
-    delta = mega_total<kMegaThreads>(part_delta, ncta, s_part);
-    if constexpr (DIST) {
-      // {delta, gamma, ||r||^2} of the world: CTA 0 stores this rank's three into every rank's slots (flag-in-data),
-      // adds the world's in rank order as they land (identical on every rank) and leaves the totals for everybody
-      // behind the barrier
+    if constexpr (!DIST) {
+      mega_barrier(A.bar, nb);
+      lap(0);
+      delta = mega_total<kMegaThreads>(part_delta, ncta, s_part);
+    } else {
+      // {delta, gamma, ||r||^2} of the world inside the operator's barrier: the last CTA to arrive adds the rank's
+      // delta partials, stores the rank's three scalars into every rank's slots (flag-in-data), adds the world's in
+      // rank order as they land (identical on every rank) and leaves the totals for everybody behind the barrier
       const P2PDev* pd = A.p2p;
       const long long seq = pd->base[0] + it + 1;
-      const int par = (int)(seq & 1);
-      const unsigned flag = (unsigned)seq;
-      if (cta == 0 && threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-        bool ok = true;
-        if (lane < pd->world) {
-          uint4* dst = pd->peer_ll_scal[lane] + (pd->rank * 2 + par) * 4;
-          ll_store(dst, delta, flag); ll_store(dst + 1, gamma, flag); ll_store(dst + 2, rr, flag);
-          const uint4* src = pd->my_ll_scal + (lane * 2 + par) * 4;
-          ok = ll_wait(src, flag, v0) & ll_wait(src + 1, flag, v1) & ll_wait(src + 2, flag, v2);
+      mega_barrier_hook(A.bar, nb, &s_last, [&]() {
+        const double dl = mega_total<kMegaThreads>(part_delta, ncta, s_part);
+        if (threadIdx.x < 32) {
+          const int lane = threadIdx.x;
+          const int par = (int)(seq & 1);
+          const unsigned flag = (unsigned)seq;
+          double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+          bool ok = true;
+          if (lane < pd->world) {
+            uint4* dst = pd->peer_ll_scal[lane] + (pd->rank * 2 + par) * 4;
+            ll_store(dst, dl, flag); ll_store(dst + 1, gamma, flag); ll_store(dst + 2, rr, flag);
+            const uint4* src = pd->my_ll_scal + (lane * 2 + par) * 4;
+            ok = ll_wait(src, flag, v0) & ll_wait(src + 1, flag, v1) & ll_wait(src + 2, flag, v2);
+          }
+          const bool lost = __any_sync(0xffffffffu, !ok) || (*reinterpret_cast<volatile int*>(A.flags + Flag::DONE) == 4);
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+          for (int pr = 0; pr < pd->world; ++pr) {
+            a0 += __shfl_sync(0xffffffffu, v0, pr); a1 += __shfl_sync(0xffffffffu, v1, pr); a2 += __shfl_sync(0xffffffffu, v2, pr);
+          }
+          if (lane == 0) { A.glob[0] = a0; A.glob[1] = a1; A.glob[2] = lost ? -1.0 : a2; }
         }
-        const bool lost = __any_sync(0xffffffffu, !ok) || (*reinterpret_cast<volatile int*>(A.flags + Flag::DONE) == 4);
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int pr = 0; pr < pd->world; ++pr) {
-          a0 += __shfl_sync(0xffffffffu, v0, pr); a1 += __shfl_sync(0xffffffffu, v1, pr); a2 += __shfl_sync(0xffffffffu, v2, pr);
-        }
-        if (lane == 0) { A.glob[0] = a0; A.glob[1] = a1; A.glob[2] = lost ? -1.0 : a2; }
-      }
-      mega_barrier(A.bar, nb);                      // CTA 0 arrives once every rank's entry has landed
+      });
+      lap(0);
       delta = __ldcg(A.glob); gamma = __ldcg(A.glob + 1); rr = __ldcg(A.glob + 2);
       if (rr < 0.0) { done = 4; break; }          // a peer never answered
       if (it == 0) {
@@ -848,6 +871,7 @@ static int upload_line_tables(femb_handle* h) {
   std::vector<double>().swap(S.node_dir);
   h->line_sym_ok = true;
   h->line_num_ok = false;
+  h->ln_mask_ok = false;
   return FEMB_OK;
 }
 
@@ -882,7 +906,7 @@ static LnDev ln_dev(const femb_handle* h) {
   T.node_bundle = h->ln_node_bundle.p; T.bundle_ids = h->ln_bundle_ids.p; T.node_dir = h->ln_node_dir.p;
   T.ent_w = h->ln_ent_w.p; T.node_w = h->ln_node_w.p; T.fac = h->ln_fac.p;
   T.yl = h->ln_yl.p; T.rb = h->ln_rb.p; T.rbt = h->line_dist ? h->ln_rbt.p : h->ln_rb.p; T.yb = h->ln_yb.p; T.inv = h->ln_inv.p;
-  T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p; T.line_range = h->ln_line_range.p;
+  T.rank_mask = h->ln_rank_mask.p; T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p; T.line_range = h->ln_line_range.p;
   for (int f = 0; f < kLnMaxFam; ++f) { T.inv_off[f] = h->ln_inv_off[f]; T.fam_pad[f] = h->ln_fam_pad[f]; }
   T.coarse_blk_off[0] = 0;
   for (int f = 0; f <= kLnMaxFam; ++f) {
@@ -911,6 +935,22 @@ static int ensure_line_numeric(femb_handle* h) {
   const bool trace = getenv("FEMB_TRACE") != nullptr;
   cudaEvent_t te[3] = {nullptr, nullptr, nullptr};
   if (trace) { for (auto& e : te) cudaEventCreate(&e); cudaEventRecord(te[0], h->stream); }
+  if (dist && !h->ln_mask_ok) {
+    // which ranks own a piece of which bundle (bit p = rank p): 2^rank per local bundle, summed over the ranks
+    std::vector<double> md((size_t)S.n_coarse, 0.0);
+    for (int32_t id : S.bundle_ids) md[id] = (double)(1 << h->dist_rank);
+    DevBuf<double> tmp;
+    FEMB_CUDA(h, upload(tmp, md, h->stream));
+    rc = dist_allreduce(h, tmp.p, S.n_coarse);
+    if (rc) return rc;
+    FEMB_CUDA(h, download(md.data(), tmp.p, md.size() * sizeof(double), h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::vector<int32_t> mi(md.size());
+    for (size_t k = 0; k < md.size(); ++k) mi[k] = (int32_t)md[k];
+    FEMB_CUDA(h, upload(h->ln_rank_mask, mi, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->ln_mask_ok = true;
+  }
   if (dist) {
     const int64_t tot = (int64_t)kLnMaxFam * h->n_nodes;
     ln_node_w_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(T, h->free_mask.p);
