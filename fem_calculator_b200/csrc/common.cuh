@@ -161,6 +161,7 @@ struct femb_handle {
   femb::DevBuf<int32_t> rowptr, colidx, blk_row, diag_blk, contrib_ptr, contrib_blk, tile_ptr;
   femb::DevBuf<uint32_t> contrib;
   femb::DevBuf<int32_t> pair_rec;   // (n_pairs,4) {node, other node, block, sec | end<<24 | pos<<25}
+  femb::DevBuf<double> pair_aux;    // (n_pairs,4) {1/L, 1/sqrt(cx^2+cy^2), w_z, w_y}: persistent PCG kernel (ebe.cuh), per assembled K
   femb::DevBuf<int32_t> pair_node_rec;  // (n_nodes,4) {first pair, pair count, diagonal block, 0}
   femb::DevBuf<int32_t> pair_tiles;     // (n_tiles,4) {first node, node count, first pair, pair count}
   bool pairs_dev_ok = false;        // pair records uploaded (frame fast path usable)
@@ -219,8 +220,8 @@ struct femb_handle {
   int32_t ln_range_off[femb::kLnMaxFam + 1] = {0, 0, 0, 0};
   int32_t ln_n_ranges = 0, ln_max_len = 0;
   femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle,
-      ln_bundle_ids, ln_bundle_cnt, ln_line_range, ln_rank_mask;
-  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_yl, ln_rb, ln_rbt, ln_yb, ln_inv, ln_gal, ln_node_dir, ln_line_sum;
+      ln_bundle_ids, ln_bundle_cnt, ln_line_range, ln_rank_mask, ln_ent_of;
+  femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_ae, ln_yle, ln_rb, ln_rbt, ln_yb, ln_inv, ln_gal, ln_node_dir, ln_line_sum;
   femb::DevBuf<unsigned long long> mega_state;   // persistent PCG kernel: grid barrier words + per-phase clocks
 
   // row-block distributed solve (dist.cu): this rank owns the first n_owned_nodes local nodes
@@ -335,6 +336,7 @@ int pcg_lines(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_
 int dist_set_lines(femb_handle* h, int32_t n_coarse, const int32_t* fam_off, const int32_t* node_bundle,
                    const int32_t* node_line, const int32_t* node_pos, const double* node_dir);
 bool dist_lines_applicable(femb_handle* h, const femb_solve_opts& o, bool fused_p2p);
+int ebe_pair_aux(femb_handle* h);
 int dist_lines_setup(femb_handle* h);
 int dist_lines_solve(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 double lines_iteration_bytes(const femb_handle* h);

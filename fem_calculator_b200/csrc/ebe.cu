@@ -290,6 +290,35 @@ constexpr int kEbeThreads = 128;
 constexpr int kEbe1CtasPerSm = 4;   // 128 registers: 4 x 128 threads resident per SM
 constexpr int kEbe4CtasPerSm = 3;   // 168 registers
 
+// one thread per (node, element end) pair: the four expensive constants of its element record (ebe.cuh: PairAux)
+__global__ void ebe_pair_aux_kernel(const FrameParams P, const int4* __restrict__ pair_rec, int64_t n_pairs,
+                                    double4* __restrict__ aux) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const int4 rec = __ldg(pair_rec + p);
+  const int a = (rec.w >> 24) & 1;
+  const double* pn = P.xyz + 3 * (size_t)rec.x;
+  const double* po = P.xyz + 3 * (size_t)rec.y;
+  const double px = pn[0], py = pn[1], pz = pn[2], ox = po[0], oy = po[1], oz = po[2];
+  const double* sp = P.sec_props + 8 * (size_t)(rec.w & 0xFFFFFF);
+  FrameIn in;   // element direction: end 0 -> end 1, as in the operator
+  in.dx = a ? px - ox : ox - px; in.dy = a ? py - oy : oy - py; in.dz = a ? pz - oz : oz - pz;
+  in.A = sp[0]; in.Ix = sp[1]; in.Iy = sp[2]; in.J = sp[3]; in.ky = sp[4]; in.kz = sp[5];
+  const PairAux x = pair_aux_from(P, in);
+  aux[p] = make_double4(x.iL, x.iD, x.wz, x.wy);
+}
+
+int ebe_pair_aux(femb_handle* h) {
+  const int64_t n_pairs = (int64_t)h->sym.pair_code.size();
+  if (n_pairs == 0 || !h->pair_rec.p) return FEMB_OK;
+  FEMB_CUDA(h, h->pair_aux.ensure((size_t)n_pairs * 4));
+  ebe_pair_aux_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, h->stream>>>(
+      ebe_params(h), reinterpret_cast<const int4*>(h->pair_rec.p), n_pairs, reinterpret_cast<double4*>(h->pair_aux.p));
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
 double ebe_bytes(const femb_handle* h, int nb) {
   const Symbolic& S = h->sym;
   // pair + node records, coordinates, x read once, y written, BC mask

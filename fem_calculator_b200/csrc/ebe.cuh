@@ -62,6 +62,79 @@ __device__ __forceinline__ void krec_from(const FrameParams& P, const FrameIn& i
   }
 }
 
+// The four numbers of the element record that cost a square root or a division — 1/L, 1/sqrt(cx^2 + cy^2) and the
+// two Timoshenko factors w = psi EI / L — depend on the geometry and the section only: ebe_pair_aux_kernel (ebe.cu)
+// stores them per (node, element end) pair once per assembled K, computed by exactly the expressions above, and the
+// persistent PCG kernel rebuilds the record from them with ~35 multiply-adds instead of ~75 FP64 instructions in four
+// long dependent chains (ncu, profiles/r02_ncu_full_persistent_pcg.txt: the two divisions and the two rsqrt were
+// 77 of the ~235 instructions of a pair and most of its fixed-latency stalls).  Same values, bit for bit.
+struct PairAux { double iL, iD, wz, wy; };
+
+__device__ __forceinline__ PairAux pair_aux_from(const FrameParams& P, const FrameIn& in) {
+  PairAux x;
+  const double L2 = in.dx * in.dx + in.dy * in.dy + in.dz * in.dz;
+  const double iL = rsqrt(L2);
+  const double cx = in.dx * iL, cy = in.dy * iL;
+  const double h2 = cx * cx + cy * cy;
+  x.iL = iL;
+  x.iD = (h2 < 1e-12) ? 0.0 : rsqrt(h2);
+  const double iL1 = (L2 > 0.0) ? iL : 0.0;
+  const double E = P.E, G = P.G;
+  {
+    const double EI = E * in.Iy;
+    const double den = G * in.ky * in.A * L2;
+    const double e = EI * iL1;
+    double w = e;
+    if (den > 0.0) w = e * (den / (den + 12.0 * EI));
+    x.wz = w;
+  }
+  {
+    const double EI = E * in.Ix;
+    const double den = G * in.kz * in.A * L2;
+    const double e = EI * iL1;
+    double w = e;
+    if (den > 0.0) w = e * (den / (den + 12.0 * EI));
+    x.wy = w;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void krec_from_aux(const FrameParams& P, const FrameIn& in, int a, const PairAux& x, KRec& k) {
+  const double dx = in.dx, dy = in.dy, dz = in.dz;
+  const double L2 = dx * dx + dy * dy + dz * dz;
+  const double iL = x.iL;
+  const double cx = dx * iL, cy = dy * iL, cz = dz * iL;
+  const double h2 = cx * cx + cy * cy;
+  if (h2 < 1e-12) {                                  // vertical member (eps = 1e-6)
+    const double s = cz > 0.0 ? 1.0 : -1.0;
+    k.t[0] = 0.0; k.t[1] = 0.0; k.t[2] = s;
+    k.n1[0] = 0.0; k.n1[1] = 1.0; k.n1[2] = 0.0;
+    k.n2[0] = -s; k.n2[1] = 0.0; k.n2[2] = 0.0;
+  } else {
+    const double iD = x.iD;
+    k.t[0] = cx; k.t[1] = cy; k.t[2] = cz;
+    k.n1[0] = -cy * iD; k.n1[1] = cx * iD; k.n1[2] = 0.0;
+    k.n2[0] = -cz * k.n1[1]; k.n2[1] = cz * k.n1[0]; k.n2[2] = cx * k.n1[1] - cy * k.n1[0];
+  }
+  const double iL1 = (L2 > 0.0) ? iL : 0.0;
+  const double sa = a ? -1.0 : 1.0;
+  const double E = P.E, G = P.G;
+  k.ax = in.A * E * iL1;
+  k.tor = G * in.J * iL1;
+  {
+    const double e = E * in.Iy * iL1;
+    const double w = x.wz;
+    const double k12 = 6.0 * w * iL1;
+    k.k23z = 3.0 * w - e; k.d22z = 2.0 * e; k.c12z = sa * k12; k.k11z = 2.0 * k12 * iL1;
+  }
+  {
+    const double e = E * in.Ix * iL1;
+    const double w = x.wy;
+    const double k12 = 6.0 * w * iL1;
+    k.k23y = 3.0 * w - e; k.d22y = 2.0 * e; k.c12y = sa * k12; k.k11y = 2.0 * k12 * iL1;
+  }
+}
+
 __device__ __forceinline__ double dot3(const double* a, double x, double y, double z) {
   return a[0] * x + a[1] * y + a[2] * z;
 }
@@ -110,7 +183,7 @@ template <int THREADS>
 __device__ __forceinline__ double ebe_nodes_phase(const FrameParams& P, const int4* __restrict__ pair_rec,
                                                   const int4* __restrict__ node_rec, int n_nodes,
                                                   const uint8_t* __restrict__ free_mask, const double* x, double* y,
-                                                  int cta, int ncta) {
+                                                  int cta, int ncta, const double4* __restrict__ pair_aux) {
   constexpr int NPC = THREADS / 2;
   const int part = threadIdx.x & 1;
   double dot = 0.0;
@@ -134,6 +207,8 @@ __device__ __forceinline__ double ebe_nodes_phase(const FrameParams& P, const in
 #pragma unroll 2
     for (int j = part; j < count; j += 2) {
       const int4 rec = __ldg(pair_rec + first + j);
+      double4 av;      // one 32-byte read-only load
+      asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(av.x), "=d"(av.y), "=d"(av.z), "=d"(av.w) : "l"(pair_aux + first + j));
       const int a = (rec.w >> 24) & 1;
       const double* po = P.xyz + 3 * (size_t)rec.y;
       const double ox = __ldg(po), oy = __ldg(po + 1), oz = __ldg(po + 2);
@@ -141,7 +216,7 @@ __device__ __forceinline__ double ebe_nodes_phase(const FrameParams& P, const in
       FrameIn in;   // element direction: end 0 -> end 1, as in the assembly kernel
       in.dx = a ? px - ox : ox - px; in.dy = a ? py - oy : oy - py; in.dz = a ? pz - oz : oz - pz;
       in.A = __ldg(sp); in.Ix = __ldg(sp + 1); in.Iy = __ldg(sp + 2); in.J = __ldg(sp + 3);
-      in.ky = __ldg(sp + 4); in.kz = __ldg(sp + 5);
+      in.ky = 0.0; in.kz = 0.0;
       double uo[6];
       {
         const double2* xo = reinterpret_cast<const double2*>(x + (size_t)rec.y * 6);
@@ -149,7 +224,8 @@ __device__ __forceinline__ double ebe_nodes_phase(const FrameParams& P, const in
         uo[0] = u0.x; uo[1] = u0.y; uo[2] = u1.x; uo[3] = u1.y; uo[4] = u2.x; uo[5] = u2.y;
       }
       KRec k;
-      krec_from(P, in, a, k);
+      const PairAux pa = {av.x, av.y, av.z, av.w};
+      krec_from_aux(P, in, a, pa, k);
       double o6[6];
       ebe_apply(k, ua, uo, o6);
 #pragma unroll

@@ -51,7 +51,9 @@ struct LnDev {
   double* ent_w;                // (n_entries, 3) masked line direction at the entry's node
   double* node_w;               // (F, N, 3)      the same, indexed by (family, node); zero where the node has no line
   double* fac;                  // (n_entries, 3) {1/delta, forward coefficient, backward coefficient}
-  double* yl;                   // (F, N) line-solve amplitude of the node's line entry
+  double* ae;                   // (n_entries) axial residual w . r of every line entry (written by the vector update)
+  double* yle;                  // (n_entries) line-solve amplitude of every line entry
+  const int32_t* ent_of;        // (F, N) line entry of the node in family f, -1: none
   double* rb;                   // (n_coarse) bundle residuals (row-block partition: this rank's partial sums)
   double* rbt;                  // (n_coarse) bundle residuals the coarse products read (= rb; partition: the sum over ranks)
   const int32_t* rank_mask;     // (n_coarse) partition: bit p set = rank p owns a piece of the bundle (contributes to its residual)
@@ -242,11 +244,8 @@ __global__ void ln_aug_fill_kernel(const double* __restrict__ G, double* __restr
 }
 
 // ---- iteration kernels --------------------------------------------------------------------------------
-// One CTA per bundle, one warp per line (lines w, w + 4, .. of the bundle): axial residuals a_k = w_k . r_k,
-// the line solve (two scans), the line's amplitude per node -> yl, and the bundle residual rb = sum of the
-// axial residuals of its lines (per-warp sums in line order, then warp order: fixed).
-// A lane holds CH = 4 consecutive entries of the line; affine maps y -> F y + G compose across lanes with a
-// Hillis-Steele scan.
+// Line solves: the two first-order recurrences of a line run as scans of affine maps y -> F y + G, composed across
+// the lanes of a line group with a Hillis-Steele scan.
 template <int LW>
 __device__ __forceinline__ void ln_scan_affine_up(double& F, double& G, int lane) {
 #pragma unroll
@@ -264,83 +263,15 @@ __device__ __forceinline__ void ln_scan_affine_down(double& F, double& G, int la
   }
 }
 
-// the line solves of one bundle_ptr range by the CTA's warps; leaves the bundle residual in rb[c].  LW lanes share a
-// line (4 consecutive entries each): lines of up to 64 nodes take a half warp, so a warp works on two lines at once.
-// r is read through the L2 (it may have been written by other CTAs of the same launch).
-template <int THREADS, int LW>
-__device__ __forceinline__ double ln_solve_lines(const LnDev& T, const double* r, int f, int l0, int l1) {
-  constexpr int CH = kLnMaxLen / 32;
-  constexpr int GPW = 32 / LW;                       // line groups per warp
-  constexpr int NG = (THREADS / 32) * GPW;           // line groups per CTA
-  const int lane = threadIdx.x & (LW - 1);
-  const int grp = threadIdx.x / LW;
-  double gsum = 0.0;
-  const int nl = l1 - l0;
-  for (int li0 = 0; li0 < nl; li0 += NG) {           // uniform trip count: the shuffles below need the whole warp
-    const int line = l0 + li0 + grp;
-    const bool on = li0 + grp < nl;
-    const int lo = on ? T.line_ptr[line] : 0, len = on ? T.line_ptr[line + 1] - lo : 0;
-    const int per = (len + LW - 1) / LW;             // entries per lane (<= CH), consecutive
-    const int k0 = lane * per;
-    double a[CH], id[CH], ff[CH], cc[CH];
-    int node[CH];
-    double lsum = 0.0;
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int k = k0 + j;
-      a[j] = 0.0; id[j] = 0.0; ff[j] = 0.0; cc[j] = 0.0; node[j] = -1;
-      if (j < per && k < len) {
-        const size_t e = (size_t)(lo + k);
-        node[j] = __ldg(T.ent_node + e);
-        const double* w = T.ent_w + 3 * e;
-        const double* rn = r + 6 * (size_t)node[j];
-        a[j] = __ldg(w) * __ldcg(rn) + __ldg(w + 1) * __ldcg(rn + 1) + __ldg(w + 2) * __ldcg(rn + 2);
-        const double* fc = T.fac + 3 * e;
-        id[j] = __ldg(fc); ff[j] = __ldg(fc + 1); cc[j] = __ldg(fc + 2);
-        lsum += a[j];
-      }
-    }
-    // forward: y_k = a_k / delta_k + f_k y_{k-1}
-    double F = 1.0, G = 0.0;
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (j < per) { G = fma(ff[j], G, a[j] * id[j]); F *= ff[j]; }
-    ln_scan_affine_up<LW>(F, G, lane);
-    double yin = __shfl_up_sync(0xffffffffu, G, 1, LW);
-    if (lane == 0) yin = 0.0;
-    double y[CH];
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      y[j] = 0.0;
-      if (j < per) { yin = fma(ff[j], yin, a[j] * id[j]); y[j] = yin; }
-    }
-    // backward: x_k = y_k + c_k x_{k+1}
-    F = 1.0; G = 0.0;
-#pragma unroll
-    for (int j = CH - 1; j >= 0; --j)
-      if (j < per) { G = fma(cc[j], G, y[j]); F *= cc[j]; }
-    ln_scan_affine_down<LW>(F, G, lane);
-    double xin = __shfl_down_sync(0xffffffffu, G, 1, LW);
-    if (lane == LW - 1) xin = 0.0;
-#pragma unroll
-    for (int j = CH - 1; j >= 0; --j)
-      if (j < per) {
-        xin = fma(cc[j], xin, y[j]);
-        if (node[j] >= 0) T.yl[(size_t)f * T.n_nodes + node[j]] = xin;
-      }
-#pragma unroll
-    for (int o = LW / 2; o > 0; o >>= 1) lsum += __shfl_down_sync(0xffffffffu, lsum, o, LW);
-    gsum += lsum;                                    // valid in lane 0 of the group; lines in ascending order
-  }
-  return gsum;
-}
-
 // persistent kernel: ALL lines dealt round-robin to the line groups (LW lanes) of the whole grid — every group gets
 // n_lines / (groups in the grid) lines instead of a CTA walking its bundles one after the other; the per-line
 // residual sums go to line_sum and the bundles are summed from them (bundle order, line order) where they are used.
 // Lane l of a group holds entries l, l + LW, l + 2 LW, .. (coalesced table reads — with consecutive entries per lane
 // the 40 narrow loads of a lane each touched their own sector and the phase was bound by L1 wavefronts); the two
 // recurrences run as CH rounds of LW-wide affine scans with the carry handed from round to round.
+// Everything the phase touches is indexed by line ENTRY (contiguous per line): the axial residuals ae = w . r were
+// scattered there by the vector update (which has r in registers and a thread per node), the amplitudes go to yle and
+// are gathered per node by the prolongation — no dependent node-id -> r gather sits on the scans' critical path.
 // POST (row-block partition): the group that completes a bundle stores the rank's partial residual straight into every
 // rank's flag-in-data slot [this rank][parity][bundle] (lane p -> rank p) instead of into rb.
 template <int THREADS, int LW, bool POST>
@@ -354,23 +285,18 @@ __device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double
     const int line = li0 + gg;
     const bool on = line < T.n_lines;
     const int lo = on ? __ldg(T.line_ptr + line) : 0, len = on ? __ldg(T.line_ptr + line + 1) - lo : 0;
-    const int f = on ? ln_family_of(T, __ldg(T.line_bundle + line)) : 0;
     int nround = (len + LW - 1) / LW;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, o));   // warp-uniform
     double g[CH], ff[CH], cc[CH];
-    int node[CH];
     double lsum = 0.0;
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-      g[j] = 0.0; ff[j] = 0.0; cc[j] = 0.0; node[j] = -1;
+      g[j] = 0.0; ff[j] = 0.0; cc[j] = 0.0;
       const int k = j * LW + lane;
       if (j < nround && k < len) {
         const size_t e = (size_t)(lo + k);
-        node[j] = __ldg(T.ent_node + e);
-        const double* w = T.ent_w + 3 * e;
-        const double* rn = r + 6 * (size_t)node[j];
-        const double a = __ldg(w) * __ldcg(rn) + __ldg(w + 1) * __ldcg(rn + 1) + __ldg(w + 2) * __ldcg(rn + 2);
+        const double a = __ldcg(T.ae + e);            // written by the vector update of this launch
         const double* fc = T.fac + 3 * e;
         g[j] = a * __ldg(fc); ff[j] = __ldg(fc + 1); cc[j] = __ldg(fc + 2);
         lsum += a;
@@ -395,7 +321,7 @@ __device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double
         ln_scan_affine_down<LW>(F, G, lane);
         const double xk = fma(F, carry, G);
         carry = __shfl_sync(0xffffffffu, xk, 0, LW);
-        if (node[j] >= 0) T.yl[(size_t)f * T.n_nodes + node[j]] = xk;
+        if (j * LW + lane < len) T.yle[(size_t)lo + j * LW + lane] = xk;
       }
     // line sum in a fixed order: per lane round by round, then the shuffle tree
 #pragma unroll
@@ -443,6 +369,7 @@ struct MegaArgs {
   FrameParams P;
   const int4* pair_rec;
   const int4* node_rec;
+  const double4* pair_aux;   // (n_pairs) {1/L, 1/sqrt(cx^2+cy^2), w_z, w_y} of every pair's element (ebe.cuh)
   const uint8_t* free_mask;
   const double* dinv;
   const double* b;
@@ -450,8 +377,9 @@ struct MegaArgs {
   double* part;          // [3][pstride] published partial sums: delta, ||r||^2, gamma
   double* scal;          // Scal:: slots (carried across launches and mirrored for the host)
   int* flags;
-  unsigned int* bar;     // [0] arrive counter, [1] generation
+  unsigned int* bar;     // grid barrier words (mega_barrier)
   unsigned long long* phase_ns;   // [8] time spent per phase (CTA 0), accumulated
+  unsigned long long* cta_ns;     // FEMB_TRACE: [grid][8] working time per phase of every CTA (null otherwise)
   double* glob;          // [4] DIST: {delta, gamma, ||r||^2} of the world, written by CTA 0 before the barrier
   int64_t n;             // ndof
   int n_nodes, n_ranges, pstride;
@@ -460,19 +388,28 @@ struct MegaArgs {
   const P2PDev* p2p;     // row-block partition (DIST): n / n_nodes count the OWNED rows, T.n_nodes all local nodes
 };
 
+// Grid barrier words (uint32): [0] arrive counter; generation flag replicated kBarCopies times, copy k at word
+// 32 (1 + k) — each on its own 128-byte line.  A CTA polls copy (cta mod kBarCopies): with one shared word the ~600
+// spinning CTAs kept one L2 slice busy and the arrive atomics of the stragglers queued behind their reads (measured:
+// phase wall minus mean working time per CTA ~5 us per barrier, profiles/r02_persistent_pcg_barrier.log).
+constexpr int kBarCopies = 16;
+constexpr int kBarWords = 32 * (1 + kBarCopies);
+
+__device__ __forceinline__ void mega_barrier_release(unsigned int* bar) {
+  bar[0] = 0;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < kBarCopies; ++k) atomicAdd(bar + 32 * (1 + k), 1u);
+}
+
 __device__ __forceinline__ void mega_barrier(unsigned int* bar, unsigned int nb) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    volatile unsigned int* vgen = bar + 1;
+    volatile unsigned int* vgen = bar + 32 * (1 + (blockIdx.x % kBarCopies));
     const unsigned int gen = *vgen;            // read before arriving
     __threadfence();
-    if (atomicAdd(bar, 1u) == nb - 1) {
-      bar[0] = 0;
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      while (*vgen == gen) { }
-    }
+    if (atomicAdd(bar, 1u) == nb - 1) mega_barrier_release(bar);
+    else while (*vgen == gen) { }
     __threadfence();
   }
   __syncthreads();
@@ -484,7 +421,7 @@ template <class F>
 __device__ __forceinline__ void mega_barrier_hook(unsigned int* bar, unsigned int nb, int* s_last, F hook) {
   __syncthreads();
   unsigned int gen = 0;
-  volatile unsigned int* vgen = bar + 1;
+  volatile unsigned int* vgen = bar + 32 * (1 + (blockIdx.x % kBarCopies));
   if (threadIdx.x == 0) {
     gen = *vgen;
     __threadfence();
@@ -495,11 +432,7 @@ __device__ __forceinline__ void mega_barrier_hook(unsigned int* bar, unsigned in
   if (*s_last) {
     hook();
     __syncthreads();
-    if (threadIdx.x == 0) {
-      bar[0] = 0;
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    }
+    if (threadIdx.x == 0) mega_barrier_release(bar);
   } else if (threadIdx.x == 0) {
     while (*vgen == gen) { }
   }
@@ -540,6 +473,7 @@ __global__ void __launch_bounds__(kMegaThreads, 4)
 ln_pcg_mega_kernel(const MegaArgs A) {
   __shared__ double s_part[2 * kMegaThreads / 32];
   __shared__ int s_last;
+  __shared__ double2 s_rt[kMegaThreads / 32][96];
   const LnDev& T = A.T;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const unsigned int nb = gridDim.x;
@@ -548,8 +482,75 @@ ln_pcg_mega_kernel(const MegaArgs A) {
   double* part_gamma = A.part + 2 * (size_t)A.pstride;
   const bool clock = (cta == 0 && threadIdx.x == 0);
   unsigned long long t_last = clock ? mega_now() : 0ull;
+  // FEMB_TRACE: every CTA's own working time per phase (barrier waits excluded) -> cta_ns[cta][8]
+  unsigned long long t_work = (A.cta_ns && threadIdx.x == 0) ? mega_now() : 0ull;
+  auto work_mark = [&](int ph) { if (A.cta_ns && threadIdx.x == 0) A.cta_ns[(size_t)cta * 8 + ph] += mega_now() - t_work; };
+  auto work_start = [&]() { if (A.cta_ns && threadIdx.x == 0) t_work = mega_now(); };
   auto lap = [&](int ph) {
     if (clock) { const unsigned long long t = mega_now(); A.phase_ns[ph] += t - t_last; t_last = t; }
+  };
+  // Vector update p = z + beta p, q = s + beta q, x += alpha p, r -= alpha q (init: x = 0, r = b, p = q = 0), the
+  // ||r||^2 partial, and the axial residuals of the new r for the line phase.  A warp takes 32 consecutive nodes = 96
+  // double2 per vector (three coalesced loads per lane); the new r is parked in shared memory so that lane n can pick
+  // up the three translations of node n and scatter w_f . r to the node's line entries (ae).
+  auto update_vectors = [&](bool init, double alpha, double beta) {
+    constexpr int NW = kMegaThreads / 32;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const double2* z2 = reinterpret_cast<const double2*>(A.z);
+    const double2* s2 = reinterpret_cast<const double2*>(A.s);
+    const double2* b2 = reinterpret_cast<const double2*>(A.b);
+    double2* p2 = reinterpret_cast<double2*>(A.p);
+    double2* q2 = reinterpret_cast<double2*>(A.q);
+    double2* x2 = reinterpret_cast<double2*>(A.x);
+    double2* r2 = reinterpret_cast<double2*>(A.r);
+    double v[1] = {0.0};
+    // equal contiguous node ranges per warp (the phase is bandwidth bound: equal bytes = equal time; chunks of 32 nodes
+    // dealt round-robin left 2 or 3 chunks per warp — measured max 15.2 against mean 12.2 us of working time per CTA)
+    const int64_t gw = (int64_t)cta * NW + wl, nw_tot = (int64_t)ncta * NW;
+    const int64_t n_lo = A.n_nodes * gw / nw_tot, n_hi = A.n_nodes * (gw + 1) / nw_tot;
+    for (int64_t n0 = n_lo; n0 < n_hi; n0 += 32) {
+      const int64_t i0 = n0 * 3, i_hi = n_hi * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int64_t i = i0 + c * 32 + lane;
+        if (i < i_hi) {
+          double2 rv;
+          if (init) {
+            rv = b2[i];
+            const double2 zero = make_double2(0.0, 0.0);
+            x2[i] = zero; p2[i] = zero; q2[i] = zero; r2[i] = rv;
+          } else {
+            const double2 zv = z2[i], sv = s2[i];
+            double2 pv = p2[i], qv = q2[i], xv = x2[i];
+            rv = r2[i];
+            pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
+            qv.x = sv.x + beta * qv.x; qv.y = sv.y + beta * qv.y;
+            xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+            rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
+            p2[i] = pv; q2[i] = qv; x2[i] = xv; r2[i] = rv;
+          }
+          v[0] += rv.x * rv.x; v[0] += rv.y * rv.y;
+          s_rt[wl][c * 32 + lane] = rv;
+        }
+      }
+      __syncwarp();
+      const int64_t node = n0 + lane;
+      if (node < n_hi) {
+        const double2 ra = s_rt[wl][3 * lane], rb2 = s_rt[wl][3 * lane + 1];
+#pragma unroll
+        for (int f = 0; f < kLnMaxFam; ++f) {
+          const size_t fn = (size_t)f * T.n_nodes + node;
+          const int e = __ldg(T.ent_of + fn);
+          if (e >= 0) {
+            const double* w = T.node_w + 3 * fn;
+            T.ae[e] = __ldg(w) * ra.x + __ldg(w + 1) * ra.y + __ldg(w + 2) * rb2.x;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    block_sum_all<kMegaThreads, 1>(v, s_part);
+    if (threadIdx.x == 0) part_rr[cta] = v[0];
   };
   // one application of the preconditioner: z = M^-1 r, publishes the (r, z) partials.  DIST: `seq` numbers the
   // coarse-residual exchange of this application, seq + 1 the halo the next operator phase waits for.
@@ -576,7 +577,7 @@ ln_pcg_mega_kernel(const MegaArgs A) {
     } else {
       ln_solve_lines_flat<kMegaThreads, 16, false>(T, A.r, cta, ncta);
     }
-    mega_barrier(A.bar, nb);
+    work_mark(2); mega_barrier(A.bar, nb); work_start();
     lap(2);
     {   // coarse products: one warp per row, rows dealt to the grid's warps (partition: only the rows of bundles this
         // rank owns a piece of — the prolongation reads no others)
@@ -602,9 +603,11 @@ ln_pcg_mega_kernel(const MegaArgs A) {
         if (lane == 0) T.yb[c] = acc;
       }
     }
-    mega_barrier(A.bar, nb);
+    work_mark(3); mega_barrier(A.bar, nb); work_start();
     lap(3);
     double g = 0.0;
+    // equal contiguous node ranges per CTA (same reasoning as in the vector update)
+    const int p_lo = (int)((int64_t)A.n_nodes * cta / ncta), p_hi = (int)((int64_t)A.n_nodes * (cta + 1) / ncta);
     auto prolong_node = [&](int node, double* zt) {
       // every load of the node issued before the first dependent one (the yb gather): two latencies per node
       const double2* r2 = reinterpret_cast<const double2*>(A.r + 6 * (size_t)node);
@@ -617,7 +620,8 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       for (int f = 0; f < kLnMaxFam; ++f) {
         const size_t fn = (size_t)f * T.n_nodes + node;
         cb[f] = __ldg(T.node_bundle + fn);
-        yl[f] = __ldcg(T.yl + fn);                    // zero where the node has no line in the family
+        const int e = __ldg(T.ent_of + fn);
+        yl[f] = e >= 0 ? __ldcg(T.yle + e) : 0.0;     // the node's line amplitude in the family
         w[f][0] = __ldg(T.node_w + 3 * fn); w[f][1] = __ldg(T.node_w + 3 * fn + 1); w[f][2] = __ldg(T.node_w + 3 * fn + 2);
       }
       zt[0] = T.omega * da.x * ra.x; zt[1] = T.omega * da.y * ra.y; zt[2] = T.omega * db.x * rb2.x;
@@ -647,13 +651,13 @@ ln_pcg_mega_kernel(const MegaArgs A) {
           for (int c = 0; c < 6; ++c) ll_store(dst + c, zt[c], hflag);
         }
       }
-      for (int node = cta * kMegaThreads + threadIdx.x; node < A.n_nodes; node += ncta * kMegaThreads) {
+      for (int node = p_lo + threadIdx.x; node < p_hi; node += kMegaThreads) {
         if (__ldg(pd->send_slot + node) >= 0) continue;
         double zt[6];
         prolong_node(node, zt);
       }
     } else {
-      for (int node = cta * kMegaThreads + threadIdx.x; node < A.n_nodes; node += ncta * kMegaThreads) {
+      for (int node = p_lo + threadIdx.x; node < p_hi; node += kMegaThreads) {
         double zt[6];
         prolong_node(node, zt);
       }
@@ -676,21 +680,14 @@ ln_pcg_mega_kernel(const MegaArgs A) {
         }
       }
     }
-    mega_barrier(A.bar, nb);
+    work_mark(4); mega_barrier(A.bar, nb); work_start();
     lap(4);
   };
 
   double gamma_prev = A.scal[Scal::RZ0], alpha_prev = A.scal[Scal::ALPHA], tol2 = A.scal[Scal::TOL2];
   if (A.init) {
     // x = 0, r = b, p = q = 0; ||b||^2; z_0 = M^-1 r_0
-    double v[1] = {0.0};
-    for (int64_t g = (int64_t)cta * kMegaThreads + threadIdx.x; g < A.n; g += (int64_t)ncta * kMegaThreads) {
-      const double bg = A.b[g];
-      A.x[g] = 0.0; A.r[g] = bg; A.p[g] = 0.0; A.q[g] = 0.0;
-      v[0] += bg * bg;
-    }
-    block_sum_all<kMegaThreads, 1>(v, s_part);
-    if (threadIdx.x == 0) part_rr[cta] = v[0];
+    update_vectors(true, 0.0, 0.0);
     mega_barrier(A.bar, nb);
     precond(DIST ? A.p2p->base[0] : 0);
   }
@@ -715,12 +712,12 @@ ln_pcg_mega_kernel(const MegaArgs A) {
     // operator: s = A z, publishes (z, s)
     {
       double v[1];
-      v[0] = ebe_nodes_phase<kMegaThreads>(A.P, A.pair_rec, A.node_rec, A.n_nodes, A.free_mask, A.z, A.s, cta, ncta);
+      v[0] = ebe_nodes_phase<kMegaThreads>(A.P, A.pair_rec, A.node_rec, A.n_nodes, A.free_mask, A.z, A.s, cta, ncta, A.pair_aux);
       block_sum_all<kMegaThreads, 1>(v, s_part);
       if (threadIdx.x == 0) part_delta[cta] = v[0];
     }
     if constexpr (!DIST) {
-      mega_barrier(A.bar, nb);
+      work_mark(0); mega_barrier(A.bar, nb); work_start();
       lap(0);
       delta = mega_total<kMegaThreads>(part_delta, ncta, s_part);
     } else {
@@ -729,7 +726,7 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       // rank order as they land (identical on every rank) and leaves the totals for everybody behind the barrier
       const P2PDev* pd = A.p2p;
       const long long seq = pd->base[0] + it + 1;
-      mega_barrier_hook(A.bar, nb, &s_last, [&]() {
+      work_mark(0); mega_barrier_hook(A.bar, nb, &s_last, [&]() {
         const double dl = mega_total<kMegaThreads>(part_delta, ncta, s_part);
         if (threadIdx.x < 32) {
           const int lane = threadIdx.x;
@@ -751,6 +748,7 @@ ln_pcg_mega_kernel(const MegaArgs A) {
           if (lane == 0) { A.glob[0] = a0; A.glob[1] = a1; A.glob[2] = lost ? -1.0 : a2; }
         }
       });
+      work_start();
       lap(0);
       delta = __ldcg(A.glob); gamma = __ldcg(A.glob + 1); rr = __ldcg(A.glob + 2);
       if (rr < 0.0) { done = 4; break; }          // a peer never answered
@@ -767,30 +765,8 @@ ln_pcg_mega_kernel(const MegaArgs A) {
     if (!(den > 0.0)) { done = 2; break; }     // K_ff (or the preconditioner) not positive definite along p
     const double alpha = gamma / den;
     gamma_prev = gamma; alpha_prev = alpha;
-    {
-      double v[1] = {0.0};
-      const int64_t n2 = A.n >> 1;                // ndof = 6 n_nodes is even
-      const double2* z2 = reinterpret_cast<const double2*>(A.z);
-      const double2* s2 = reinterpret_cast<const double2*>(A.s);
-      double2* p2 = reinterpret_cast<double2*>(A.p);
-      double2* q2 = reinterpret_cast<double2*>(A.q);
-      double2* x2 = reinterpret_cast<double2*>(A.x);
-      double2* r2 = reinterpret_cast<double2*>(A.r);
-#pragma unroll 2
-      for (int64_t i = (int64_t)cta * kMegaThreads + threadIdx.x; i < n2; i += (int64_t)ncta * kMegaThreads) {
-        const double2 zv = z2[i], sv = s2[i];
-        double2 pv = p2[i], qv = q2[i], xv = x2[i], rv = r2[i];
-        pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
-        qv.x = sv.x + beta * qv.x; qv.y = sv.y + beta * qv.y;
-        xv.x += alpha * pv.x; xv.y += alpha * pv.y;
-        rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
-        p2[i] = pv; q2[i] = qv; x2[i] = xv; r2[i] = rv;
-        v[0] += rv.x * rv.x; v[0] += rv.y * rv.y;
-      }
-      block_sum_all<kMegaThreads, 1>(v, s_part);
-      if (threadIdx.x == 0) part_rr[cta] = v[0];
-    }
-    mega_barrier(A.bar, nb);
+    update_vectors(false, alpha, beta);
+    work_mark(1); mega_barrier(A.bar, nb); work_start();
     lap(1);
     precond(DIST ? A.p2p->base[0] + it + 1 : 0);
   }
@@ -833,7 +809,19 @@ static int upload_line_tables(femb_handle* h) {
     FEMB_CUDA(h, h->ln_ent_w.alloc((size_t)S.n_entries * 3));
     FEMB_CUDA(h, h->ln_fac.alloc((size_t)S.n_entries * 3));
     FEMB_CUDA(h, h->ln_node_w.alloc((size_t)kLnMaxFam * h->n_nodes * 3));
-    FEMB_CUDA(h, h->ln_yl.alloc((size_t)kLnMaxFam * h->n_nodes));
+    FEMB_CUDA(h, h->ln_ae.alloc((size_t)S.n_entries));
+    FEMB_CUDA(h, h->ln_yle.alloc((size_t)S.n_entries));
+    {
+      // entry of every (family, node): families are contiguous coarse-index ranges, lines carry their bundle
+      std::vector<int32_t> eo((size_t)kLnMaxFam * h->n_nodes, -1);
+      for (int32_t l = 0; l < S.n_lines; ++l) {
+        int f = 0;
+        for (int k = 1; k < kLnMaxFam; ++k) f += (S.line_bundle[l] >= S.fam_off[k]) ? 1 : 0;
+        for (int32_t e = S.line_ptr[l]; e < S.line_ptr[l + 1]; ++e) eo[(size_t)f * h->n_nodes + S.ent_node[e]] = e;
+      }
+      FEMB_CUDA(h, upload(h->ln_ent_of, eo, h->stream));
+      FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     FEMB_CUDA(h, h->ln_rb.alloc((size_t)S.n_coarse));
     FEMB_CUDA(h, h->ln_rbt.alloc((size_t)S.n_coarse));
     FEMB_CUDA(h, h->ln_yb.alloc((size_t)S.n_coarse));
@@ -860,7 +848,8 @@ static int upload_line_tables(femb_handle* h) {
     FEMB_CUDA(h, h->ln_inv.alloc((size_t)std::max<int64_t>(off, 1)));
     FEMB_CUDA(h, h->ln_gal.alloc((size_t)gmax));
     FEMB_CUDA(h, cudaMemsetAsync(h->ln_node_w.p, 0, h->ln_node_w.bytes(), h->stream));
-    FEMB_CUDA(h, cudaMemsetAsync(h->ln_yl.p, 0, h->ln_yl.bytes(), h->stream));
+    FEMB_CUDA(h, cudaMemsetAsync(h->ln_ae.p, 0, h->ln_ae.bytes(), h->stream));
+    FEMB_CUDA(h, cudaMemsetAsync(h->ln_yle.p, 0, h->ln_yle.bytes(), h->stream));
     FEMB_CUDA(h, cudaMemsetAsync(h->ln_rb.p, 0, h->ln_rb.bytes(), h->stream));
     FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
@@ -905,7 +894,7 @@ static LnDev ln_dev(const femb_handle* h) {
   T.ent_node = h->ln_ent_node.p; T.ent_blk_diag = h->ln_ent_blk_diag.p; T.ent_blk_next = h->ln_ent_blk_next.p;
   T.node_bundle = h->ln_node_bundle.p; T.bundle_ids = h->ln_bundle_ids.p; T.node_dir = h->ln_node_dir.p;
   T.ent_w = h->ln_ent_w.p; T.node_w = h->ln_node_w.p; T.fac = h->ln_fac.p;
-  T.yl = h->ln_yl.p; T.rb = h->ln_rb.p; T.rbt = h->line_dist ? h->ln_rbt.p : h->ln_rb.p; T.yb = h->ln_yb.p; T.inv = h->ln_inv.p;
+  T.ae = h->ln_ae.p; T.yle = h->ln_yle.p; T.ent_of = h->ln_ent_of.p; T.rb = h->ln_rb.p; T.rbt = h->line_dist ? h->ln_rbt.p : h->ln_rb.p; T.yb = h->ln_yb.p; T.inv = h->ln_inv.p;
   T.rank_mask = h->ln_rank_mask.p; T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p; T.line_range = h->ln_line_range.p;
   for (int f = 0; f < kLnMaxFam; ++f) { T.inv_off[f] = h->ln_inv_off[f]; T.fam_pad[f] = h->ln_fam_pad[f]; }
   T.coarse_blk_off[0] = 0;
@@ -956,6 +945,8 @@ static int ensure_line_numeric(femb_handle* h) {
     ln_node_w_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(T, h->free_mask.p);
     h->launches++;
   }
+  rc = ebe_pair_aux(h);                              // per-pair constants of the operator phase (current coordinates)
+  if (rc) return rc;
   if (S.n_lines > 0) {
     ln_direction_kernel<<<grid_lines, kLnThreads, 0, h->stream>>>(T, h->xyz.p, h->free_mask.p);
     ln_tridiag_kernel<<<grid_lines, kLnThreads, 0, h->stream>>>(T, h->Kvals.p);
@@ -1023,14 +1014,17 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   const auto t_host0 = std::chrono::steady_clock::now();
   const int pstride = h->num_sms * 8;
   FEMB_CUDA(h, h->fpartials.ensure((size_t)pstride * 6));
-  FEMB_CUDA(h, h->mega_state.ensure(32));          // [0] barrier words, [2..10) phase clocks (8 x u64), [16..20) world scalars
+  // u64 words: [2..10) phase clocks, [16..20) world scalars, [64..) the grid barrier's words (kBarWords x u32)
+  FEMB_CUDA(h, h->mega_state.ensure(64 + kBarWords / 2));
   FEMB_CUDA(h, cudaMemsetAsync(h->mega_state.p, 0, h->mega_state.bytes(), h->stream));
   FEMB_CUDA(h, cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t) * Flag::COUNT, h->stream));
   FEMB_CUDA(h, cudaMemsetAsync(h->scal.p, 0, sizeof(double) * Scal::COUNT, h->stream));
+  // (5 or 6 CTAs of 96 / 80 registers per SM measured slower: 82.2 / 96.6 against 80.7 us per iteration,
+  // profiles/r02_persistent_pcg_experiments.log)
+  const void* fn = dist ? (const void*)ln_pcg_mega_kernel<true> : (const void*)ln_pcg_mega_kernel<false>;
   static int per_sm[2] = {0, 0};
   if (!per_sm[dist]) {
-    if (dist) FEMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], ln_pcg_mega_kernel<true>, kMegaThreads, 0));
-    else FEMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], ln_pcg_mega_kernel<false>, kMegaThreads, 0));
+    FEMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dist], fn, kMegaThreads, 0));
     per_sm[dist] = std::max(1, std::min(per_sm[dist], 8));      // the partial arrays hold num_sms * 8 entries
   }
   MegaArgs A;
@@ -1039,18 +1033,26 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   A.P.E = h->E; A.P.G = h->G; A.P.rho = h->rho;
   A.pair_rec = reinterpret_cast<const int4*>(h->pair_rec.p);
   A.node_rec = reinterpret_cast<const int4*>(h->pair_node_rec.p);
+  A.pair_aux = reinterpret_cast<const double4*>(h->pair_aux.p);
   A.free_mask = h->free_mask.p; A.dinv = h->Dinv.p; A.b = d_b;
   A.x = h->x.p; A.r = h->r.p; A.z = h->z.p; A.p = h->p.p; A.q = h->q.p; A.s = h->s.p;
   A.part = h->fpartials.p; A.scal = h->scal.p; A.flags = h->flags.p;
-  A.bar = reinterpret_cast<unsigned int*>(h->mega_state.p);
+  A.bar = reinterpret_cast<unsigned int*>(h->mega_state.p + 64);
   A.phase_ns = h->mega_state.p + 2;
   A.glob = reinterpret_cast<double*>(h->mega_state.p + 16);
+  A.cta_ns = nullptr;
   A.n_nodes = (int)(dist ? h->n_owned_nodes : h->n_nodes);
   A.n = (int64_t)A.n_nodes * 6;
   A.n_ranges = h->ln_n_ranges; A.pstride = pstride;
   A.max_iter = o.max_iter; A.rtol = o.rtol;
   A.p2p = dist ? reinterpret_cast<const P2PDev*>(h->p2p_dev_copy.p) : nullptr;
   const int grid = h->num_sms * per_sm[dist];
+  DevBuf<unsigned long long> cta_ns;
+  if (getenv("FEMB_TRACE")) {
+    FEMB_CUDA(h, cta_ns.alloc((size_t)grid * 8));
+    FEMB_CUDA(h, cudaMemsetAsync(cta_ns.p, 0, cta_ns.bytes(), h->stream));
+    A.cta_ns = cta_ns.p;
+  }
   struct Peek { int32_t flags[Flag::COUNT]; double scal[Scal::COUNT]; unsigned long long ns[8]; };
   Peek* peek = reinterpret_cast<Peek*>(h->pinned);
   const int check = o.check_every > 0 ? o.check_every : 50;
@@ -1059,7 +1061,6 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
     // one more pass than updates: the pass that finds ||r|| <= tol (or the cap) leaves through the decision
     A.it0 = it; A.n_iters = std::min(check, o.max_iter + 1 - it); A.init = (it == 0) ? 1 : 0;
     void* args[] = {(void*)&A};
-    const void* fn = dist ? (const void*)ln_pcg_mega_kernel<true> : (const void*)ln_pcg_mega_kernel<false>;
     FEMB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kMegaThreads), args, 0, h->stream));
     h->launches++;
     ++launches;
@@ -1093,6 +1094,17 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
               peek->ns[2] * 1e-3 / std::max(1, st->iterations), peek->ns[3] * 1e-3 / std::max(1, st->iterations),
               peek->ns[4] * 1e-3 / std::max(1, st->iterations),
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
+    if (A.cta_ns && st->iterations > 0) {
+      std::vector<unsigned long long> w((size_t)grid * 8);
+      cudaMemcpy(w.data(), cta_ns.p, w.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      const char* nm[5] = {"operator", "update", "line solves", "coarse", "prolongation"};
+      for (int ph = 0; ph < 5; ++ph) {
+        double sum = 0.0, mx = 0.0, mn = 1e300;
+        for (int c = 0; c < grid; ++c) { const double v = (double)w[(size_t)c * 8 + ph]; sum += v; mx = std::max(mx, v); mn = std::min(mn, v); }
+        fprintf(stderr, "[femb trace]   %-12s working time per CTA and iteration (barrier waits excluded): min %.2f us, mean %.2f, max %.2f\n",
+                nm[ph], mn * 1e-3 / st->iterations, sum / grid * 1e-3 / st->iterations, mx * 1e-3 / st->iterations);
+      }
+    }
   }
   if (done == 4) return fail(h, FEMB_ERR_CUDA, "peer-memory exchange timed out waiting for another rank");
   if (done == 2) return fail(h, FEMB_ERR_SINGULAR, "PCG breakdown: p^T K p <= 0 (K_ff is not positive definite — unconstrained rigid-body motion or zero section properties?)");
@@ -1101,18 +1113,19 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
 }
 
 // compulsory bytes of one iteration of the persistent kernel (every array once per phase that must touch it):
-//   operator   pair + node records, coordinates, z read, s written, mask            (ebe_bytes)
-//   update     z, s, p, q, x, r read; p, q, x, r written                            10 x 8 B / DOF
-//   lines      per line entry: node id 4 + direction 24 + factors 24 + r 24 read, amplitude 8 written
+//   operator   pair + node records, coordinates, z read, s written, mask (ebe_bytes) + 32 B per pair of constants
+//   update     z, s, p, q, x, r read; p, q, x, r written (10 x 8 B / DOF) + per family and node: entry id 4,
+//              direction 24 read, axial residual 8 written
+//   lines      per line entry: axial residual 8 + factors 24 read, amplitude 8 written
 //   coarse     the per-family inverses                                              8 B x sum nf^2
-//   prolong    r, 1/diag read, z written (48 B each) + per family bundle id 4, amplitude 8, direction 24
+//   prolong    r, 1/diag read, z written (48 B each) + per family bundle id 4, entry id 4, amplitude 8, direction 24
 double lines_iteration_bytes(const femb_handle* h) {
   if (!h->line_sym_ok || h->line_sym.n_coarse == 0) return 0.0;
   const LineSym& S = h->line_sym;
   const double nodes = (double)(h->line_dist ? h->n_owned_nodes : h->n_nodes);
   double inv = 0.0;
   for (int f = 0; f < kLnMaxFam; ++f) { const double nf = S.fam_off[f + 1] - S.fam_off[f]; inv += 8.0 * nf * nf; }
-  return ebe_bytes(h, 1) + 80.0 * 6.0 * nodes + 84.0 * (double)S.n_entries + inv + (144.0 + 36.0 * kLnMaxFam) * nodes;
+  return ebe_bytes(h, 1) + 32.0 * (double)h->sym.pair_code.size() + (480.0 + 36.0 * kLnMaxFam) * nodes + 40.0 * (double)S.n_entries + inv + (144.0 + 40.0 * kLnMaxFam) * nodes;
 }
 
 int pcg_lines(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st) {
