@@ -165,7 +165,7 @@ def run_reference(args):
            "cpu_baseline": {"value": v, "unit": "DOF/s", "cores": s["threads"], "kind": "port", "sample": sample,
                             "host_cpus": os.cpu_count(), "iterations": s["iterations"], "rel_residual": s["rel_residual"]},
            "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 # ------------------------------------------------------------------------------------------ GPU legs
@@ -295,6 +295,33 @@ def leg_tet10(local, peak):
                                        f"{len(small.cells_dict['tetra10'])} tets: {t_cpu:.2f} s"}}
 
 
+def leg_c5_single(local):
+    """BASELINE configs[4] (110^3 frame, 7,986,000 DOF) on ONE GPU: the denominator of the strong-scaling line that
+    `--gpus N` (N > 1) reports for the same frame split over N GPUs."""
+    from fem_calculator_b200 import _lib as L, meshgen
+    from fem_calculator_b200.api import FrameModel
+    E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+    mesh, sec, bc, es, props, fixed, f = build_case(lattice=LATTICE_C5)
+    n_free = len(f) - len(fixed)
+    m = FrameModel(local)
+    m.set_mesh(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)))
+    m.assemble()
+    m.set_bc(fixed, f)
+    kw = dict(method=L.SOLVER_PCG, precond=L.PRECOND_AUTO, rtol=RTOL, want_u=False, want_reactions=False)
+    m.solve_static(**kw)
+    best = None
+    for _ in range(3):
+        m.timer_start()
+        m.assemble()
+        _, _, st = m.solve_static(**kw)
+        ms = m.timer_stop()
+        best = ms if best is None else min(best, ms)
+    m.close()
+    return {"workload": workload_text(LATTICE_C5), "ms_per_step": best, "dof_per_s": n_free / (best * 1e-3),
+            "iterations": st["iterations"], "precond_used": st["precond_used"], "coarse_dim": st["coarse_dim"],
+            "rel_residual": st["rel_residual"], "us_per_iteration": st["device_ms"] / max(1, st["iterations"]) * 1e3}
+
+
 def run_single(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     from fem_calculator_b200 import _lib as L
@@ -342,12 +369,12 @@ def run_single(args):
     dfma_ms, dfma_count = m.time_kernel(10, 2, 5)
     dfma_peak = dfma_count / (dfma_ms * 1e-3)                 # FP64 FMA instructions (lane-level) per second, measured
     n_pairs = 2 * n_elem
-    fp64_instr = 135.0 * n_pairs                               # ~135 FP64 instructions per (node, element end) pair
+    fp64_instr = 96.0 * n_pairs                                # ~96 FP64 instructions per (node, element end) pair (36 record + 60 apply)
 
-    def _traffic(name):
+    def _traffic(name, key="dram_bytes_per_launch"):
         tp = os.path.join(ROOT, "profiles", name)
         try:
-            return json.load(open(tp)).get("dram_bytes_per_launch")
+            return json.load(open(tp)).get(key)
         except Exception:
             return None
 
@@ -366,17 +393,19 @@ def run_single(args):
                 "frac": achieved / peak, "bytes_per_launch": it_bytes * tst["iterations"] / n_launch,
                 "ms_per_launch": tst["device_ms"] / n_launch, "launches_per_solve": n_launch,
                 "bytes_per_iteration": it_bytes, "us_per_iteration": it_ms * 1e3,
-                "share_of_step": tst["device_ms"] / ms_per_step, "traffic": _traffic("ncu_mega_traffic.json"),
+                "share_of_step": tst["device_ms"] / ms_per_step, "traffic": (lambda t: None if t is None else t * tst["iterations"] / n_launch)(_traffic("ncu_mega_traffic.json", "dram_bytes_per_iteration")),
+                "traffic_source": "ncu --set full of one 50-iteration launch (profiles/ncu_mega_traffic.json): dram__bytes_read + dram__bytes_write per iteration x this run's iterations per launch",
                 "phases_us_per_iteration": {"operator": op_ms * 1e3, "update_lines_coarse_prolong": rest_ms * 1e3,
                                             "clock": "globaltimer of CTA 0 at the grid barriers, accumulated over the timed steps"},
                 "operator_phase": {"bytes": op_bytes, "gbs": op_bytes / (op_ms * 1e-3) / 1e9, "frac_hbm": op_bytes / (op_ms * 1e-3) / 1e9 / peak,
                                    "fp64_instructions": fp64_instr, "achieved_ginstr_per_s": fp64_instr / (op_ms * 1e-3) / 1e9,
                                    "peak_gfma_per_s_measured": dfma_peak / 1e9, "frac_fp64_issue": fp64_instr / (op_ms * 1e-3) / dfma_peak,
-                                   "note": "the operator phase (35 % of the iteration) is FP64-issue / gather-latency bound, not byte bound; "
-                                           "the FMA issue ceiling is femb_time_kernel(10) of this run"},
-                "note": "the iteration's working set (eight 8 MB vectors + 60 MB of tables) sits mostly in the 126 MB L2, so the kernel is "
-                        "bound by the latency of its dependent gathers and the five grid barriers, not by HBM: the same product through "
-                        "the assembled matrix is roofline_bsr_spmv",
+                                   "note": "the operator phase (a third of the iteration) is bound by the latency of its dependent gathers, not by "
+                                           "bytes or FP64 issue; the FMA issue ceiling is femb_time_kernel(10) of this run"},
+                "note": "ncu: 159 MB of DRAM traffic per iteration against these algorithmic bytes (part of the 250 MB working set — six "
+                        "8 MB vectors + ~150 MB of tables — is served by the 126 MB L2); a third of the iteration is grid-barrier wait "
+                        "(five barriers, slowest-CTA tails: profiles/r02_persistent_pcg_experiments.log). The HBM-bound form of the "
+                        "same operator product through the assembled matrix is roofline_bsr_spmv",
                 "equivalent_bsr_gbs": spmv_bytes / (op_ms * 1e-3) / 1e9}
     lines = last.get("precond_used") == L.PRECOND_LINES
     extra = {
@@ -460,9 +489,10 @@ def run_single(args):
         c4["dof_per_s_device"] = c4["free_dof_this_gpu"] / (c4["device_ms"] * 1e-3)
         c4["dof_per_s_e2e"] = c4["free_dof_this_gpu"] / (c4["e2e_ms"] * 1e-3)
         out["tet10"] = leg_tet10(local, peak)
+        out["c5_single_gpu"] = leg_c5_single(local)
     if not args.no_cpu_baseline:
         out["parity"], out["cpu_baseline"] = leg_parity_and_cpu(local)
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 def run_multi(args):
@@ -577,11 +607,25 @@ def run_multi(args):
                            "device_ms_max_over_ranks": dev, "e2e_ms_max_over_ranks": wall,
                            "dof_per_s_device": C4_MODELS * 6 * C4_ELEMS / (dev * 1e-3), "dof_per_s_e2e": C4_MODELS * 6 * C4_ELEMS / (wall * 1e-3)}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        _emit(out)
     dist.destroy_process_group()
 
 
+def _emit(obj):
+    """The ONE JSON line, on the process's real stdout (everything else — NCCL's version banner, library traces —
+    went to stderr: main() points fd 1 at fd 2 while the benchmark runs)."""
+    line = json.dumps(obj) + "\n"
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line.encode())
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -391,7 +391,7 @@ struct MegaArgs {
 // Grid barrier words (uint32): [0] arrive counter; generation flag replicated kBarCopies times, copy k at word
 // 32 (1 + k) — each on its own 128-byte line.  A CTA polls copy (cta mod kBarCopies): with one shared word the ~600
 // spinning CTAs kept one L2 slice busy and the arrive atomics of the stragglers queued behind their reads (measured:
-// phase wall minus mean working time per CTA ~5 us per barrier, profiles/r02_persistent_pcg_barrier.log).
+// phase wall minus mean working time per CTA ~5 us per barrier, profiles/r02_persistent_pcg_experiments.log).
 constexpr int kBarCopies = 16;
 constexpr int kBarWords = 32 * (1 + kBarCopies);
 
