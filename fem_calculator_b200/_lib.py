@@ -76,6 +76,8 @@ SIGNATURES = {
     "femb_apply_k": (C.c_int, [_P, C.c_int, C.c_int, _F64, _F64, C.POINTER(C.c_int32)]),
     "femb_modal": (C.c_int, [_P, C.POINTER(EigOpts), _P, _P, C.POINTER(C.c_int32), C.POINTER(Stats)]),
     "femb_frame_stress": (C.c_int, [_P, _P, _P]),
+    "femb_host_register": (C.c_int, [_P, C.c_void_p, C.c_int64]),
+    "femb_host_unregister": (C.c_int, [_P, C.c_void_p]),
     "femb_frame_batch_solve": (C.c_int, [_P, C.c_int64, C.c_int64, _F64, _F64, C.c_double, C.c_double,
                                          _U8, _F64, _P, C.POINTER(Stats)]),
     "femb_dist_unique_id": (C.c_int, [_P]),

@@ -22,8 +22,9 @@ class Handle:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
-            self.lib.femb_destroy(self._h)
+            self.lib.femb_destroy(self._h)        # also drops every femb_host_register registration of the handle
             self._h = None
+            self.__dict__.pop("_pins", None)
 
     def __del__(self):
         try:
@@ -136,13 +137,40 @@ class FrameModel(Handle):
         self._check(self.lib.femb_frame_stress(self._h, L.ptr(uu), L.ptr(s)))
         return s
 
-    def batch_solve(self, xyz, sec_props, E, G, fixed_mask, f, want_u=True):
+    _PIN_MIN_BYTES = 8 << 20
+
+    def _pin(self, role, arr):
+        """Page-lock ``arr`` in place for this handle and keep a reference to it: while the model holds the array its
+        address cannot be freed and handed out again, so the registration can never alias other memory.  One array per
+        role ('f', 'u'); a different array replaces (and unregisters) the previous one."""
+        pins = self.__dict__.setdefault("_pins", {})
+        cur = pins.get(role)
+        if cur is not None and cur is arr:
+            return
+        if cur is not None:
+            self.lib.femb_host_unregister(self._h, C.c_void_p(cur.ctypes.data))
+            pins.pop(role)
+        if arr is not None and arr.nbytes >= self._PIN_MIN_BYTES:
+            if self.lib.femb_host_register(self._h, C.c_void_p(arr.ctypes.data), arr.nbytes) == 0:
+                pins[role] = arr
+
+    def batch_solve(self, xyz, sec_props, E, G, fixed_mask, f, want_u=True, out=None, pin=True):
+        """BASELINE config 4: (u (n_models, ndof), stats).  ``out``: a C-contiguous float64 (n_models, ndof) array to
+        receive u (pass the same one again to reuse its page-locked registration); ``pin``: page-lock f and u in place
+        (buffers of 8 MB or more) — the model keeps them referenced until other arrays come or it is closed."""
         xyz = np.ascontiguousarray(xyz, dtype=np.float64)
         sp = np.ascontiguousarray(sec_props, dtype=np.float64).reshape(-1, 8)
         fm = np.ascontiguousarray(fixed_mask, dtype=np.uint8)
         f = np.ascontiguousarray(f, dtype=np.float64)
         nm, ne = len(sp), len(xyz) - 1
-        u = np.zeros((nm, 6 * len(xyz))) if want_u else None
+        u = None
+        if want_u:
+            u = out if out is not None else np.zeros((nm, 6 * len(xyz)))
+            if u.shape != (nm, 6 * len(xyz)) or u.dtype != np.float64 or not u.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float64 array of shape (n_models, ndof)")
+        if pin:
+            self._pin("f", f)
+            self._pin("u", u)
         st = L.Stats()
         rc = self.lib.femb_frame_batch_solve(self._h, nm, ne, xyz.reshape(-1), sp.reshape(-1), float(E), float(G),
                                              fm, f.reshape(-1), L.ptr(u), C.byref(st))

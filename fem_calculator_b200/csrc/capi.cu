@@ -484,6 +484,29 @@ int femb_frame_batch_solve(femb_handle* h, int64_t n_models, int64_t n_elem, con
   return rc;
 }
 
+int femb_host_register(femb_handle* h, void* ptr, int64_t bytes) {
+  if (!h || !ptr || bytes <= 0) return fail(h, FEMB_ERR_ARG, "bad femb_host_register arguments");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  for (auto& e : h->batch_pinned)
+    if (e.first == ptr) return fail(h, FEMB_ERR_ARG, "femb_host_register: this address is already registered (unregister it first)");
+  FEMB_CUDA(h, cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  h->batch_pinned.emplace_back(ptr, (size_t)bytes);
+  return FEMB_OK;
+}
+
+int femb_host_unregister(femb_handle* h, void* ptr) {
+  if (!h || !ptr) return fail(h, FEMB_ERR_ARG, "bad femb_host_unregister arguments");
+  FEMB_CUDA(h, cudaSetDevice(h->device));
+  for (auto it = h->batch_pinned.begin(); it != h->batch_pinned.end(); ++it)
+    if (it->first == ptr) {
+      if (h->stream) cudaStreamSynchronize(h->stream);
+      cudaHostUnregister(ptr);
+      h->batch_pinned.erase(it);
+      return FEMB_OK;
+    }
+  return fail(h, FEMB_ERR_ARG, "femb_host_unregister: address was not registered through this handle");
+}
+
 int femb_timer(femb_handle* h, int stop, double* ms) {
   if (!h) return FEMB_ERR_ARG;
   FEMB_CUDA(h, cudaSetDevice(h->device));

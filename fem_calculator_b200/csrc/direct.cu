@@ -392,24 +392,12 @@ batch_chain_rows_kernel(BatchParams B) {
   if (!ok && active && r == 0) atomicAdd(B.status, 1);
 }
 
-// Host buffers of a batch are hundreds of MB: page-locking them in place (cudaHostRegister, kept while the same
-// pointer / size comes back) lets the copies run at PCIe speed instead of through the driver's pageable staging
-static void batch_register_host(femb_handle* h, const void* p, size_t bytes) {
-  if (!p || bytes < ((size_t)8 << 20)) return;
-  for (auto& e : h->batch_pinned)
-    if (e.first == p && e.second >= bytes) return;
-  for (auto it = h->batch_pinned.begin(); it != h->batch_pinned.end();)      // a stale registration of the same address
-    if (it->first == p) { cudaHostUnregister(it->first); it = h->batch_pinned.erase(it); } else ++it;
-  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) h->batch_pinned.emplace_back(const_cast<void*>(p), bytes);
-  else cudaGetLastError();                                                   // not registrable: plain pageable copy
-}
-
 int run_batch_chain(femb_handle* h, int64_t n_models, int64_t n_elem, const double* xyz,
                     const double* sec_props, double E, double G, const uint8_t* fixed_mask,
                     const double* f, double* u, femb_stats* st) {
   const int64_t nn = n_elem + 1, ndof = nn * 6;
-  batch_register_host(h, f, (size_t)n_models * ndof * 8);
-  batch_register_host(h, u, u ? (size_t)n_models * ndof * 8 : 0);
+  // (f and u are hundreds of MB: a caller that page-locked them with femb_host_register gets PCIe-speed async copies,
+  // any other buffer goes through the driver's pageable staging — same result)
   DevBuf<double> dxyz, dsec;
   DevBuf<uint8_t> dfix;
   DevBuf<int> status;

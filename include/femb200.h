@@ -219,9 +219,9 @@ int femb_frame_stress(femb_handle* h, const double* u, double* sigma_node);
 /* ---- batched independent chain models (BASELINE config 4) ----------------------------
  * n_models cantilever/chain models of n_elem elements each (nodes 0..n_elem in chain
  * order along xyz), one section record per model, solved by a batched block-tridiagonal
- * factorisation (six lanes per model, one row of every 6x6 block each; five models per warp).  Host buffers of
- * 8 MB or more are page-locked in place on first use and stay registered while the same pointer comes back.  Equivalent to n_models calls of run_simulation's
- * static part (BeamSolver.py:360-418).
+ * factorisation (six lanes per model, one row of every 6x6 block each; five models per warp).  Equivalent to
+ * n_models calls of run_simulation's static part (BeamSolver.py:360-418).  f and u are hundreds of MB at BASELINE
+ * config 4: page-lock them with femb_host_register for PCIe-speed copies (optional; same results without).
  *   xyz        (n_nodes,3) shared node coordinates, n_nodes = n_elem+1
  *   sec_props  (n_models,8)
  *   fixed_mask (ndof) uint8, 1 = fixed DOF, shared by all models
@@ -230,6 +230,13 @@ int femb_frame_batch_solve(femb_handle* h, int64_t n_models, int64_t n_elem, con
                            const double* sec_props, double E, double G,
                            const uint8_t* fixed_mask, const double* f, double* u,
                            femb_stats* stats);
+
+/* Page-lock a caller-owned host buffer in place (cudaHostRegister) so that the library's copies to / from it run
+ * asynchronously at PCIe speed.  The registration belongs to the CALLER: the buffer must stay allocated until
+ * femb_host_unregister (or femb_destroy) — the library never keeps a registration of memory it was not told to keep,
+ * because a freed and re-allocated address would silently alias the old pages.                                  */
+int femb_host_register(femb_handle* h, void* ptr, int64_t bytes);
+int femb_host_unregister(femb_handle* h, void* ptr);
 
 /* ---- one large mesh across GPUs: row-block (node-slab) partition ----------------------------
  * One process (and one handle) per GPU.  Each rank passes femb_*_set_mesh its LOCAL mesh: the

@@ -215,3 +215,39 @@ def test_batch_chain_solve_at_config4_length_matches_banded_cholesky():
     tip = p["tip_fy"] * 4.0 ** 3 / (3 * E * Iy) + p["tip_fy"] * 4.0 / (ky * G_ * A)
     err = np.abs(u1[:, 6 * (nn - 1) + 1] - tip) / np.abs(tip)
     assert err.max() <= 1e-4, err.max()          # eps * cond(K) ~ 1e-16 * (L/h)^4 = 1.6e-3 is the worst case
+
+
+def test_batch_chain_page_locked_buffers_never_alias():
+    """femb_host_register path of the batched solve (api.FrameModel.batch_solve pin=True): buffers above 8 MB are
+    page-locked in place and the model keeps them referenced.  A result buffer that is dropped and re-allocated between
+    calls (numpy hands the same address out again) must still receive the new solution — the round-2 bench caught a
+    stale registration returning zeros — and pinned / unpinned calls agree bit for bit."""
+    n_models, n_el = 220, 1000                       # 220 x 6006 doubles = 10.6 MB per buffer
+    p = meshgen.batch_cantilever_params(n_models)
+    nn = n_el + 1
+    xyz = np.stack([np.linspace(0.0, 2.0, nn), np.zeros(nn), np.zeros(nn)], axis=1)
+    props = np.array([csp("rectangular section", {"d": d, "b": b}) for d, b in zip(p["d"], p["b"])])
+    fixed_mask = np.zeros(6 * nn, dtype=np.uint8)
+    fixed_mask[:6] = 1
+    E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
+    G = E / (2 * (1 + nu))
+
+    def loads(scale):
+        f = np.zeros((n_models, 6 * nn))
+        f[:, 6 * (nn - 1) + 1] = scale * p["tip_fy"]
+        return f
+
+    m = FrameModel(0)
+    ref1, _ = m.batch_solve(xyz, props, E, G, fixed_mask, loads(1.0), pin=False)
+    ref3, _ = m.batch_solve(xyz, props, E, G, fixed_mask, loads(3.0), pin=False)
+    for scale, ref in ((1.0, ref1), (3.0, ref3), (1.0, ref1)):
+        u, st = m.batch_solve(xyz, props, E, G, fixed_mask, loads(scale))      # fresh f and u every call
+        assert st["converged"] == 1
+        assert np.array_equal(u, ref)
+        del u
+    out = np.zeros((n_models, 6 * nn))
+    for scale, ref in ((3.0, ref3), (1.0, ref1)):
+        u, _ = m.batch_solve(xyz, props, E, G, fixed_mask, loads(scale), out=out)
+        assert u is out and np.array_equal(out, ref)
+    m.close()
+    assert np.abs(ref1).max() > 0.0 and np.allclose(ref3, 3.0 * ref1, rtol=1e-12, atol=0.0)
