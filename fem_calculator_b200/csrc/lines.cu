@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <limits>
 
 #include "common.cuh"
 #include "ebe.cuh"
@@ -61,6 +62,8 @@ struct LnDev {
   int32_t max_len;              // longest line (entries)
   int32_t* bundle_cnt;          // (bundle_ptr ranges) lines of each bundle finished in the current pass (persistent kernel)
   const int32_t* line_range;    // (n_lines) bundle_ptr range of every line
+  const int32_t* grp_ptr;       // (line groups of the grid + 1) persistent kernel: the lines of every line group ...
+  const int4* grp_lines;        // (n_lines) ... {line, first entry, entries, bundle range}, balanced by length on the host (ln_assign_lines)
   double* yb;                   // (n_coarse) coarse solution
   const double* inv;            // per-family inverses, family f at inv_off[f], leading dimension fam_pad[f]
   int64_t inv_off[kLnMaxFam];
@@ -280,11 +283,18 @@ __device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double
   constexpr int CH = kLnMaxLen / LW;                  // rounds (LW = 16: 8 rounds cover 128 entries)
   constexpr int NG = THREADS / LW;
   const int lane = threadIdx.x & (LW - 1);
-  const int gg = cta * NG + threadIdx.x / LW, tg = ncta * NG;
-  for (int li0 = 0; li0 < T.n_lines; li0 += tg) {     // uniform trip count (shuffles)
-    const int line = li0 + gg;
-    const bool on = line < T.n_lines;
-    const int lo = on ? __ldg(T.line_ptr + line) : 0, len = on ? __ldg(T.line_ptr + line + 1) - lo : 0;
+  const int gg = cta * NG + threadIdx.x / LW;
+  // the group's lines: host-side longest-processing-time assignment (ln_assign_lines): lines differ in length — on a
+  // row-block partition the pieces of cut lines are a fraction of the uncut ones — and dealt round-robin the groups
+  // that drew the long lines kept everybody else at the barrier
+  const int g0 = __ldg(T.grp_ptr + gg), g1 = __ldg(T.grp_ptr + gg + 1);
+  int trips = g1 - g0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));   // warp-uniform (shuffles)
+  for (int it = 0; it < trips; ++it) {
+    const bool on = g0 + it < g1;
+    const int4 lrec = on ? __ldg(T.grp_lines + g0 + it) : make_int4(0, 0, 0, 0);     // {line, first entry, entries, bundle range}
+    const int line = lrec.x, lo = lrec.y, len = lrec.z;
     int nround = (len + LW - 1) / LW;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nround = max(nround, __shfl_xor_sync(0xffffffffu, nround, o));   // warp-uniform
@@ -334,7 +344,7 @@ __device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double
       T.line_sum[line] = lsum;
       __threadfence();
       const int c = __ldg(T.line_bundle + line);
-      const int rg = __ldg(T.line_range + line);
+      const int rg = lrec.w;
       const int b0 = __ldg(T.bundle_ptr + rg), b1 = __ldg(T.bundle_ptr + rg + 1);
       if (atomicAdd(T.bundle_cnt + rg, 1) == b1 - b0 - 1) {
         __threadfence();
@@ -563,6 +573,8 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       ln_solve_lines_flat<kMegaThreads, 16, true>(T, A.r, cta, ncta, pd, seq);
       const int par = (int)(seq & 1);
       const unsigned flag = (unsigned)seq;
+      const bool clk1 = (A.cta_ns && cta == 1 && threadIdx.x == 0);       // FEMB_TRACE: time the polls of one thread
+      const unsigned long long tp0 = clk1 ? mega_now() : 0ull;
       for (int k = cta * kMegaThreads + threadIdx.x; k < T.n_coarse; k += ncta * kMegaThreads) {
         const int mask = __ldg(T.rank_mask + k);
         double t = 0.0;
@@ -574,6 +586,7 @@ ln_pcg_mega_kernel(const MegaArgs A) {
           }
         T.rbt[k] = t;
       }
+      if (clk1) A.phase_ns[5] += mega_now() - tp0;
     } else {
       ln_solve_lines_flat<kMegaThreads, 16, false>(T, A.r, cta, ncta);
     }
@@ -640,15 +653,46 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       // is on the wire while the interior runs
       const P2PDev* pd = A.p2p;
       const unsigned hflag = (unsigned)(seq + 1);
-      for (int k = cta * kMegaThreads + threadIdx.x; k < pd->n_bnd; k += ncta * kMegaThreads) {
-        const int node = __ldg(pd->bnd_nodes + k);
-        double zt[6];
-        prolong_node(node, zt);
-        for (int d = __ldg(pd->bnd_dst_ptr + k); d < __ldg(pd->bnd_dst_ptr + k + 1); ++d) {
-          const int sl = __ldg(pd->bnd_dst + d);
-          uint4* dst = pd->peer_ll_halo[sl >> 28] + (size_t)(sl & 0xFFFFFFF) * 6;
+      // A warp takes 32 consecutive boundary nodes; their z is parked in shared memory so that every store instruction
+      // writes 32 CONSECUTIVE 16-byte slots (full 128-byte NVLink writes): with one node per lane (6 slots each, 96 bytes
+      // apart) every slot travelled as its own packet and the 145k packets of an interior rank's 24,200 boundary nodes
+      // cost ~10 us per iteration on 8 GPUs (profiles/r02_dist_8gpu_phases.log).  Runs of nodes whose destination
+      // offsets are consecutive at one neighbour go out this way, anything else (a node with several destinations,
+      // a run that changes neighbour) falls back to per-node stores.
+      {
+        constexpr int NW = kMegaThreads / 32;
+        const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+        double* sz = reinterpret_cast<double*>(&s_rt[wl][0]);          // 192 doubles per warp
+        for (int k0 = (cta * NW + wl) * 32; k0 < pd->n_bnd; k0 += ncta * NW * 32) {
+          const int k = k0 + lane;
+          const bool on = k < pd->n_bnd;
+          int d0 = 0, d1 = 0, sl0 = -1;
+          double zt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+          if (on) {
+            const int node = __ldg(pd->bnd_nodes + k);
+            prolong_node(node, zt);
+            d0 = __ldg(pd->bnd_dst_ptr + k); d1 = __ldg(pd->bnd_dst_ptr + k + 1);
+            sl0 = __ldg(pd->bnd_dst + d0);
+          }
+          // uniform run: every lane has exactly one destination, same neighbour, consecutive offsets
+          const int base = __shfl_sync(0xffffffffu, sl0, 0);
+          const bool fits = on ? (d1 - d0 == 1 && sl0 == base + lane) : true;
+          const int n_on = min(32, pd->n_bnd - k0);
+          if (__all_sync(0xffffffffu, fits) && base >= 0) {
 #pragma unroll
-          for (int c = 0; c < 6; ++c) ll_store(dst + c, zt[c], hflag);
+            for (int c = 0; c < 6; ++c) sz[lane * 6 + c] = zt[c];
+            __syncwarp();
+            uint4* dst = pd->peer_ll_halo[base >> 28] + (size_t)(base & 0xFFFFFFF) * 6;
+            for (int e = lane; e < n_on * 6; e += 32) ll_store(dst + e, sz[e], hflag);
+            __syncwarp();
+          } else if (on) {
+            for (int d = d0; d < d1; ++d) {
+              const int sl = __ldg(pd->bnd_dst + d);
+              uint4* dst = pd->peer_ll_halo[sl >> 28] + (size_t)(sl & 0xFFFFFFF) * 6;
+#pragma unroll
+              for (int c = 0; c < 6; ++c) ll_store(dst + c, zt[c], hflag);
+            }
+          }
         }
       }
       for (int node = p_lo + threadIdx.x; node < p_hi; node += kMegaThreads) {
@@ -670,6 +714,8 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       // grid starts from its last CTA: the first ones carry the boundary nodes above)
       const P2PDev* pd = A.p2p;
       const unsigned hflag = (unsigned)(seq + 1);
+      const bool clk1 = (A.cta_ns && cta == ncta - 1 && threadIdx.x == 0);
+      const unsigned long long tp0 = clk1 ? mega_now() : 0ull;
       for (int kn = 0; kn < pd->n_nbr; ++kn) {
         const long long first = pd->recv_start[kn] * 6, cnt = pd->recv_count[kn] * 6;
         const uint4* src = pd->my_ll_halo + (first - pd->n_owned * 6);
@@ -679,6 +725,7 @@ ln_pcg_mega_kernel(const MegaArgs A) {
           A.z[first + e] = v;
         }
       }
+      if (clk1) A.phase_ns[6] += mega_now() - tp0;
     }
     work_mark(4); mega_barrier(A.bar, nb); work_start();
     lap(4);
@@ -861,6 +908,7 @@ static int upload_line_tables(femb_handle* h) {
   h->line_sym_ok = true;
   h->line_num_ok = false;
   h->ln_mask_ok = false;
+  h->ln_grp_count = 0;
   return FEMB_OK;
 }
 
@@ -895,7 +943,7 @@ static LnDev ln_dev(const femb_handle* h) {
   T.node_bundle = h->ln_node_bundle.p; T.bundle_ids = h->ln_bundle_ids.p; T.node_dir = h->ln_node_dir.p;
   T.ent_w = h->ln_ent_w.p; T.node_w = h->ln_node_w.p; T.fac = h->ln_fac.p;
   T.ae = h->ln_ae.p; T.yle = h->ln_yle.p; T.ent_of = h->ln_ent_of.p; T.rb = h->ln_rb.p; T.rbt = h->line_dist ? h->ln_rbt.p : h->ln_rb.p; T.yb = h->ln_yb.p; T.inv = h->ln_inv.p;
-  T.rank_mask = h->ln_rank_mask.p; T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p; T.line_range = h->ln_line_range.p;
+  T.grp_ptr = h->ln_grp_ptr.p; T.grp_lines = reinterpret_cast<const int4*>(h->ln_grp_lines.p); T.rank_mask = h->ln_rank_mask.p; T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p; T.line_range = h->ln_line_range.p;
   for (int f = 0; f < kLnMaxFam; ++f) { T.inv_off[f] = h->ln_inv_off[f]; T.fam_pad[f] = h->ln_fam_pad[f]; }
   T.coarse_blk_off[0] = 0;
   for (int f = 0; f <= kLnMaxFam; ++f) {
@@ -955,7 +1003,7 @@ static int ensure_line_numeric(femb_handle* h) {
   FEMB_CUDA(h, cudaGetLastError());
   if (trace) cudaEventRecord(te[1], h->stream);
   bool all_ok = true;
-  for (int f = 0; f < kLnMaxFam && all_ok; ++f) {
+  for (int f = 0; f < kLnMaxFam && (all_ok || dist); ++f) {
     const int nf = S.fam_off[f + 1] - S.fam_off[f];
     if (nf == 0) continue;
     const int64_t n_pad = h->ln_fam_pad[f], m = 2 * n_pad;
@@ -975,10 +1023,39 @@ static int ensure_line_numeric(femb_handle* h) {
     ln_aug_fill_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)n_pad), 256, 0, h->stream>>>(h->ln_gal.p, h->coarse_aug.p, nf, n_pad);
     h->launches++;
     FEMB_CUDA(h, cudaGetLastError());
+    // row-block partition: every rank holds the same summed Galerkin matrix, so the inversions are dealt out (family
+    // f to rank f mod world) instead of repeated on every rank; the inverses travel with one sum over the ranks below
+    // (the others contribute zeros), a failed factorisation as a NaN in the first entry
+    double* inv_f = h->ln_inv.p + h->ln_inv_off[f];
+    if (dist && (f % h->dist_world) != h->dist_rank) {
+      FEMB_CUDA(h, cudaMemsetAsync(inv_f, 0, (size_t)n_pad * n_pad * sizeof(double), h->stream));
+      continue;
+    }
     bool ok = false;
-    rc = coarse_invert(h, h->coarse_aug.p, n_pad, h->ln_inv.p + h->ln_inv_off[f], &ok);
+    rc = coarse_invert(h, h->coarse_aug.p, n_pad, inv_f, &ok);
     if (rc) return rc;
-    all_ok = all_ok && ok;
+    if (dist && !ok) {
+      const double nan = std::numeric_limits<double>::quiet_NaN();
+      FEMB_CUDA(h, cudaMemcpyAsync(inv_f, &nan, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    } else {
+      all_ok = all_ok && ok;
+    }
+  }
+  if (dist) {
+    int64_t tot = 0;
+    for (int f = 0; f < kLnMaxFam; ++f) tot = std::max<int64_t>(tot, h->ln_inv_off[f] + (int64_t)h->ln_fam_pad[f] * h->ln_fam_pad[f]);
+    rc = dist_allreduce(h, h->ln_inv.p, (int)tot);
+    if (rc) return rc;
+    double* first = reinterpret_cast<double*>(reinterpret_cast<char*>(h->pinned) + 1024);
+    for (int f = 0; f < kLnMaxFam; ++f) {
+      first[f] = 0.0;
+      if (S.fam_off[f + 1] > S.fam_off[f])
+        FEMB_CUDA(h, cudaMemcpyAsync(first + f, h->ln_inv.p + h->ln_inv_off[f], sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < kLnMaxFam; ++f)
+      if (!(first[f] == first[f])) all_ok = false;
   }
   if (trace) {
     cudaEventRecord(te[2], h->stream);
@@ -1009,6 +1086,47 @@ bool lines_applicable(femb_handle* h, const femb_solve_opts& o) {
   return o.precond == FEMB_PRECOND_LINES || h->line_sym.coverage >= kLnAutoCoverage;
 }
 
+// Lines -> line groups of the persistent kernel's grid (`n_groups` = CTAs x groups per CTA): longest processing time
+// first onto the least loaded group.  Cost model: a fixed part per line (pointer loads, ticket, fence) + one unit per
+// scan round of 16 entries.  Deterministic; any assignment gives the same numbers (the bundle sums are taken in line
+// order by whichever group completes a bundle).
+static int ln_assign_lines(femb_handle* h, int n_groups) {
+  if (h->ln_grp_count == n_groups && h->ln_grp_ptr.p) return FEMB_OK;
+  const LineSym& S = h->line_sym;
+  std::vector<int32_t> order((size_t)S.n_lines);
+  for (int32_t l = 0; l < S.n_lines; ++l) order[l] = l;
+  auto cost = [&](int32_t l) { return 2 + (S.line_ptr[l + 1] - S.line_ptr[l] + 15) / 16; };
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cost(a) > cost(b); });
+  // least-loaded group: a binary heap of (load, group)
+  std::vector<std::pair<int64_t, int32_t>> heap((size_t)n_groups);
+  for (int g = 0; g < n_groups; ++g) heap[g] = {0, g};
+  auto cmp = [](const std::pair<int64_t, int32_t>& a, const std::pair<int64_t, int32_t>& b) { return a > b; };   // min-heap
+  std::make_heap(heap.begin(), heap.end(), cmp);
+  std::vector<int32_t> of((size_t)S.n_lines), cnt((size_t)n_groups + 1, 0);
+  for (int32_t l : order) {
+    std::pop_heap(heap.begin(), heap.end(), cmp);
+    auto& top = heap.back();
+    of[l] = top.second;
+    cnt[top.second + 1]++;
+    top.first += cost(l);
+    std::push_heap(heap.begin(), heap.end(), cmp);
+  }
+  for (int g = 0; g < n_groups; ++g) cnt[g + 1] += cnt[g];
+  std::vector<int32_t> range_of((size_t)S.n_lines, 0);
+  for (size_t rg = 0; rg + 1 < S.bundle_ptr.size(); ++rg)
+    for (int32_t l = S.bundle_ptr[rg]; l < S.bundle_ptr[rg + 1]; ++l) range_of[l] = (int32_t)rg;
+  std::vector<int32_t> lines((size_t)std::max(1, S.n_lines) * 4, 0), fill(cnt.begin(), cnt.end() - 1);
+  for (int32_t l = 0; l < S.n_lines; ++l) {                              // ascending line index inside a group
+    int32_t* r = lines.data() + 4 * (size_t)fill[of[l]]++;
+    r[0] = l; r[1] = S.line_ptr[l]; r[2] = S.line_ptr[l + 1] - S.line_ptr[l]; r[3] = range_of[l];
+  }
+  FEMB_CUDA(h, upload(h->ln_grp_ptr, cnt, h->stream));
+  FEMB_CUDA(h, upload(h->ln_grp_lines, lines, h->stream));
+  FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->ln_grp_count = n_groups;
+  return FEMB_OK;
+}
+
 // launches of the persistent kernel until the solve is over; `dist`: this rank's part of a row-block partition
 static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st, bool dist) {
   const auto t_host0 = std::chrono::steady_clock::now();
@@ -1026,6 +1144,10 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
   if (!per_sm[dist]) {
     FEMB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dist], fn, kMegaThreads, 0));
     per_sm[dist] = std::max(1, std::min(per_sm[dist], 8));      // the partial arrays hold num_sms * 8 entries
+  }
+  {
+    const int rc = ln_assign_lines(h, h->num_sms * per_sm[dist] * (kMegaThreads / 16));
+    if (rc) return rc;
   }
   MegaArgs A;
   A.T = ln_dev(h);
@@ -1094,15 +1216,22 @@ static int run_mega(femb_handle* h, const femb_solve_opts& o, const double* d_b,
               peek->ns[2] * 1e-3 / std::max(1, st->iterations), peek->ns[3] * 1e-3 / std::max(1, st->iterations),
               peek->ns[4] * 1e-3 / std::max(1, st->iterations),
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
+    if (dist && A.cta_ns)
+      fprintf(stderr, "[femb trace]   one thread's polls per iteration: bundle residuals of the world %.2f us, halo unpack %.2f us\n",
+              peek->ns[5] * 1e-3 / std::max(1, st->iterations), peek->ns[6] * 1e-3 / std::max(1, st->iterations));
     if (A.cta_ns && st->iterations > 0) {
       std::vector<unsigned long long> w((size_t)grid * 8);
       cudaMemcpy(w.data(), cta_ns.p, w.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
       const char* nm[5] = {"operator", "update", "line solves", "coarse", "prolongation"};
       for (int ph = 0; ph < 5; ++ph) {
-        double sum = 0.0, mx = 0.0, mn = 1e300;
-        for (int c = 0; c < grid; ++c) { const double v = (double)w[(size_t)c * 8 + ph]; sum += v; mx = std::max(mx, v); mn = std::min(mn, v); }
-        fprintf(stderr, "[femb trace]   %-12s working time per CTA and iteration (barrier waits excluded): min %.2f us, mean %.2f, max %.2f\n",
-                nm[ph], mn * 1e-3 / st->iterations, sum / grid * 1e-3 / st->iterations, mx * 1e-3 / st->iterations);
+        double sum = 0.0, mx = 0.0, mn = 1e300, mx_hi = 0.0;
+        for (int c = 0; c < grid; ++c) {
+          const double v = (double)w[(size_t)c * 8 + ph];
+          sum += v; mx = std::max(mx, v); mn = std::min(mn, v);
+          if (c >= 64) mx_hi = std::max(mx_hi, v);      // the first CTAs also poll the other ranks' slots (partition)
+        }
+        fprintf(stderr, "[femb trace]   %-12s working time per CTA and iteration (barrier waits excluded): min %.2f us, mean %.2f, max %.2f (CTAs >= 64: %.2f)\n",
+                nm[ph], mn * 1e-3 / st->iterations, sum / grid * 1e-3 / st->iterations, mx * 1e-3 / st->iterations, mx_hi * 1e-3 / st->iterations);
       }
     }
   }

@@ -244,6 +244,9 @@ __device__ __forceinline__ bool ll_wait(const uint4* slot, unsigned flag, double
       v = __longlong_as_double((long long)(((unsigned long long)c << 32) | a));
       return true;
     }
+    // tens of thousands of threads poll at once: back off so that the polls do not keep the L2 busy while the peers'
+    // stores are trying to get in
+    __nanosleep(spins < 64 ? 40 : 200);
   }
   v = 0.0;
   return false;
