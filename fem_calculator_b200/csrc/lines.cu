@@ -573,9 +573,10 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       ln_solve_lines_flat<kMegaThreads, 16, true>(T, A.r, cta, ncta, pd, seq);
       const int par = (int)(seq & 1);
       const unsigned flag = (unsigned)seq;
-      const bool clk1 = (A.cta_ns && cta == 1 && threadIdx.x == 0);       // FEMB_TRACE: time the polls of one thread
+      // (the grid's LAST CTAs take the polls: the first ones hold the longest lines of the length-balanced assignment)
+      const bool clk1 = (A.cta_ns && cta == ncta - 2 && threadIdx.x == 0);       // FEMB_TRACE: time the polls of one thread
       const unsigned long long tp0 = clk1 ? mega_now() : 0ull;
-      for (int k = cta * kMegaThreads + threadIdx.x; k < T.n_coarse; k += ncta * kMegaThreads) {
+      for (int k = (ncta - 1 - cta) * kMegaThreads + threadIdx.x; k < T.n_coarse; k += ncta * kMegaThreads) {
         const int mask = __ldg(T.rank_mask + k);
         double t = 0.0;
         for (int pr = 0; pr < pd->world; ++pr)
