@@ -196,16 +196,24 @@ class DistFrameModel(FrameModel):
         return bytes(buf)
 
     def setup(self, points, conn, elem_sec, sec_props, E, G, fixed_dofs, f, rank, world, unique_id=None, rho=7850.0,
-              all_gather=None, lines=True, line_bundles=768):
+              all_gather=None, lines=True, line_bundles=768, partition="boxes"):
         """``all_gather(obj) -> [obj of rank 0, ..., obj of rank world-1]`` (e.g. a wrapper of
         torch.distributed.all_gather_object) switches the iteration's exchanges from NCCL to the
         peer-memory kernels (CUDA IPC over NVLink); without it NCCL is used.  ``lines``: hand the rank's
-        member-line tables to the library (PRECOND_LINES / AUTO on the partition; needs the peer-memory path)."""
+        member-line tables to the library (PRECOND_LINES / AUTO on the partition; needs the peer-memory path).
+        ``partition``: "boxes" (coordinate-bisection boxes of equal node count, ``partition.box_owner`` — member lines are
+        cut into few long pieces), "slabs" (contiguous ranges of the node order) or an explicit node -> rank array."""
         from . import partition as P
         points = np.asarray(points, dtype=np.float64)
         conn = np.asarray(conn, dtype=np.int64)
         n_nodes = len(points)
-        self.part = part = P.partition_mesh(conn, n_nodes, world, rank)
+        if isinstance(partition, str):
+            if partition not in ("boxes", "slabs"):
+                raise ValueError("partition must be 'boxes', 'slabs' or a node -> rank array")
+            owner = P.box_owner(points, world) if (partition == "boxes" and world > 1) else None
+        else:
+            owner = np.asarray(partition, dtype=np.int64)
+        self.part = part = P.partition_mesh(conn, n_nodes, world, rank, owner=owner)
         if world > 1:
             idbuf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
             self._check(self.lib.femb_dist_init(self._h, int(rank), int(world), idbuf))

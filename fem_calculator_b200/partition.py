@@ -1,13 +1,15 @@
-"""Row-block (node-slab) partition of one large mesh across GPUs (BASELINE configs 3/5).
+"""Row-block partition of one large mesh across GPUs (BASELINE configs 3/5): contiguous node slabs
+(``bounds``) or any node -> rank map (``owner``, e.g. the coordinate-bisection boxes of ``box_owner``).
 
 Pure host logic (numpy): every rank derives its own local mesh and halo lists from the GLOBAL
 arrays the reference already holds (mesh.points, connectivity — BeamSolver.py:364-372,
 ReactionSolver.py:62-66), deterministically and without communication:
 
 * rank r owns the contiguous global node range [bounds[r], bounds[r+1]) in the mesh's own node
-  order (DOF numbering is never changed: BeamSolver.py:354,360);
-* local nodes = owned nodes (global order) followed by ghost nodes (ascending global id, hence
-  grouped by owner rank);
+  order, or the nodes a node -> rank map gives it (DOF numbering is never changed: BeamSolver.py:354,360;
+  the rank's owned rows are its nodes in ascending global order);
+* local nodes = owned nodes (global order) followed by ghost nodes grouped by owner rank, ascending
+  global id inside a group;
 * local elements = every element touching an owned node, in ascending global element order, so
   the owned rows of the locally assembled K receive exactly the contributions, in exactly the
   order, of the single-GPU assembly ("owner computes", cut elements duplicated);
@@ -32,8 +34,8 @@ def node_bounds(n_nodes: int, world: int) -> np.ndarray:
 class Partition:
     rank: int
     world: int
-    bounds: np.ndarray            # (world+1) global node range boundaries
-    local_nodes: np.ndarray       # (n_local) global ids: owned first, then ghosts (ascending)
+    bounds: np.ndarray            # (world+1) global node range boundaries (empty for a node -> rank map)
+    local_nodes: np.ndarray       # (n_local) global ids: owned first (ascending), then ghosts (by owner, ascending)
     n_owned: int
     elem_ids: np.ndarray          # (n_local_elem) global element ids, ascending
     conn_local: np.ndarray        # (n_local_elem, nper) int64 in local node ids
@@ -44,12 +46,9 @@ class Partition:
     recv_count: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))
 
     @property
-    def node_lo(self) -> int:
-        return int(self.bounds[self.rank])
-
-    @property
-    def node_hi(self) -> int:
-        return int(self.bounds[self.rank + 1])
+    def owned_nodes(self) -> np.ndarray:
+        """Global ids of the rank's owned nodes, ascending (= the order of its owned rows)."""
+        return self.local_nodes[:self.n_owned]
 
     def local_dofs(self, bs: int) -> np.ndarray:
         """Global DOF index of every local DOF (owned + ghost), local order."""
@@ -61,22 +60,43 @@ class Partition:
         return g2l
 
 
-def partition_mesh(conn: np.ndarray, n_nodes: int, world: int, rank: int, bounds: np.ndarray | None = None) -> Partition:
+def box_owner(points: np.ndarray, world: int) -> np.ndarray:
+    """Node -> rank map by proportional recursive coordinate bisection (the library's host-side aggregate builder,
+    csrc/coarse.cpp): `world` boxes of equal node count (+-1).  Against slabs of the node order, boxes cut every member
+    line of a lattice-like frame into FEWER, LONGER pieces (2 x 2 x 2 boxes: two pieces per line in every direction
+    instead of eight in one) — the line preconditioner loses less — and have less surface (halo)."""
+    from .api import symbolic_aggregates
+    return np.asarray(symbolic_aggregates(points, int(world)), dtype=np.int64)
+
+
+def partition_mesh(conn: np.ndarray, n_nodes: int, world: int, rank: int, bounds: np.ndarray | None = None,
+                   owner: np.ndarray | None = None) -> Partition:
     conn = np.asarray(conn, dtype=np.int64)
-    bounds = node_bounds(n_nodes, world) if bounds is None else np.asarray(bounds, dtype=np.int64)
-    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    owner_of = lambda nodes: np.searchsorted(bounds[1:], nodes, side="right")  # noqa: E731
+    if owner is not None:
+        owner = np.asarray(owner, dtype=np.int64)
+        if owner.shape != (n_nodes,) or owner.min() < 0 or owner.max() >= world:
+            raise ValueError("owner must map every node to a rank in [0, world)")
+        bounds = np.zeros(0, dtype=np.int64)
+        owner_of = lambda nodes: owner[nodes]  # noqa: E731
+        owned = np.flatnonzero(owner == rank)
+    else:
+        bounds = node_bounds(n_nodes, world) if bounds is None else np.asarray(bounds, dtype=np.int64)
+        owner_of = lambda nodes: np.searchsorted(bounds[1:], nodes, side="right")  # noqa: E731
+        owned = np.arange(int(bounds[rank]), int(bounds[rank + 1]), dtype=np.int64)
     elem_owner = owner_of(conn)                                   # (E, nper)
     mine = (elem_owner == rank).any(axis=1)
     elem_ids = np.nonzero(mine)[0]
     le, lo_owner = conn[mine], elem_owner[mine]
     touched = np.unique(le) if len(le) else np.zeros(0, np.int64)
-    ghosts = touched[(touched < lo) | (touched >= hi)]
-    local_nodes = np.concatenate([np.arange(lo, hi, dtype=np.int64), ghosts])
+    ghosts = touched[owner_of(touched) != rank] if len(touched) else touched
+    if len(ghosts):
+        # grouped by owner rank, ascending global id inside a group (slabs: this IS the ascending order)
+        ghosts = ghosts[np.lexsort((ghosts, owner_of(ghosts)))]
+    local_nodes = np.concatenate([owned, ghosts])
     g2l = np.full(n_nodes, -1, dtype=np.int64)
     g2l[local_nodes] = np.arange(len(local_nodes))
     conn_local = g2l[le] if len(le) else np.zeros((0, conn.shape[1]), np.int64)
-    part = Partition(rank, world, bounds, local_nodes, hi - lo, elem_ids, conn_local)
+    part = Partition(rank, world, bounds, local_nodes, len(owned), elem_ids, conn_local)
     if world == 1 or len(ghosts) == 0:
         return part
     ghost_owner = owner_of(ghosts)
@@ -91,7 +111,7 @@ def partition_mesh(conn: np.ndarray, n_nodes: int, world: int, rank: int, bounds
         with_s = (lo_owner == s).any(axis=1)
         sub, subo = le[with_s], lo_owner[with_s]
         mine_nodes = np.unique(sub[subo == rank])
-        send_nodes.append(mine_nodes - lo)
+        send_nodes.append(g2l[mine_nodes])
         send_ptr.append(send_ptr[-1] + len(mine_nodes))
     part.nbr = nbrs.astype(np.int32)
     part.send_ptr = np.asarray(send_ptr, dtype=np.int64)

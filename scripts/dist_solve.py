@@ -18,6 +18,7 @@ for a in sys.argv[1:]:
     if a.startswith("--precond="):
         precond = {"jacobi": L.PRECOND_JACOBI, "lines": L.PRECOND_LINES, "auto": L.PRECOND_AUTO, "blockj": L.PRECOND_BLOCK_JACOBI}[a.split("=")[1]]
 reps = 3 if "--reps" in sys.argv else 1
+partition = "slabs" if "--slabs" in sys.argv else "boxes"
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -42,7 +43,7 @@ def _gather(obj):
 use_p2p = world > 1 and not os.environ.get("FEMB_DIST_NO_P2P")
 m = DistFrameModel(local)
 t0 = time.time()
-part = m.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world, uid, all_gather=_gather if use_p2p else None)
+part = m.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world, uid, all_gather=_gather if use_p2p else None, partition=partition)
 t_setup = time.time() - t0
 u, r, st = m.solve_static_dist(precond=precond)            # warm-up (NCCL connections, allocator)
 if world > 1:
@@ -63,13 +64,16 @@ if rank == 0:
                       "us_per_iteration": float(ms.item()) / max(1, st["iterations"]) * 1e3,
                       "dof_per_s": n_free / (float(ms.item()) * 1e-3), "owned_nodes_rank0": int(part.n_owned),
                       "ghost_nodes_rank0": int(len(part.local_nodes) - part.n_owned), "setup_s": t_setup,
-                      "precond_requested": precond, "precond_used": st["precond_used"], "coarse_dim": st["coarse_dim"], "exchange": "p2p" if getattr(m, "p2p", False) else "nccl"}), flush=True)
+                      "precond_requested": precond, "precond_used": st["precond_used"], "coarse_dim": st["coarse_dim"], "exchange": "p2p" if getattr(m, "p2p", False) else "nccl", "partition": partition,
+                      "neighbours_rank0": [int(x) for x in part.nbr]}), flush=True)
 if check:
     from oracle import ref_sparse as S
     if world > 1:
         parts = [None] * world
-        dist.all_gather_object(parts, u)
-        ug = np.concatenate(parts)
+        dist.all_gather_object(parts, (part.owned_nodes, u))
+        ug = np.zeros(len(f))
+        for nodes, uu in parts:                       # owned rows of every rank, in its ascending global node order
+            ug.reshape(-1, 6)[nodes] = uu.reshape(-1, 6)
     else:
         ug = u
     if rank == 0:

@@ -18,10 +18,10 @@ def _n_gpus():
     return int(_lib.load().femb_device_count())
 
 
-def _run(world, lattice, precond, port):
+def _run(world, lattice, precond, port, partition="boxes"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "scripts", "dist_solve.py"), *map(str, lattice), "--check",
-           f"--precond={precond}"]
+           f"--precond={precond}"] + (["--slabs"] if partition == "slabs" else [])
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
@@ -29,12 +29,20 @@ def _run(world, lattice, precond, port):
     return json.loads(line)
 
 
-@pytest.mark.parametrize("precond", ["lines", "jacobi"])
-def test_two_rank_solve_matches_oracle(precond):
+@pytest.mark.parametrize("precond,partition", [("lines", "boxes"), ("lines", "slabs"), ("jacobi", "boxes")])
+def test_two_rank_solve_matches_oracle(precond, partition):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    out = _run(2, (14, 10, 9), precond, 29611 if precond == "lines" else 29612)
-    assert out["world"] == 2 and out["exchange"] == "p2p"
+    out = _run(2, (14, 10, 9), precond, {"lines": 29611, "jacobi": 29612}[precond] + (10 if partition == "slabs" else 0), partition)
+    assert out["world"] == 2 and out["exchange"] == "p2p" and out["partition"] == partition
     if precond == "lines":
         assert out["precond_used"] == 5 and out["coarse_dim"] > 0, out
         assert out["iterations"] < 300, out
+
+
+def test_four_rank_box_partition_matches_oracle():
+    """2 x 2 boxes: every rank has two neighbours that are not adjacent in rank order, ghosts grouped by owner."""
+    if _n_gpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    out = _run(4, (14, 12, 9), "lines", 29631)
+    assert out["world"] == 4 and out["precond_used"] == 5, out

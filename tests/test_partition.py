@@ -25,20 +25,29 @@ def _case(nx=6, ny=4, nz=5):
     return mesh, es, props, fixed, f
 
 
-@pytest.mark.parametrize("world", [1, 2, 3, 5])
-def test_partition_invariants(world):
+@pytest.mark.parametrize("kind", ["slabs", "boxes"])
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+def test_partition_invariants(world, kind):
     mesh, es, props, fixed, f = _case()
     conn = mesh.cells_dict["line"]
     n = len(mesh.points)
-    parts = [P.partition_mesh(conn, n, world, r) for r in range(world)]
+    owner = P.box_owner(mesh.points, world) if kind == "boxes" else None
+    if owner is not None:
+        cnt = np.bincount(owner, minlength=world)
+        assert cnt.max() - cnt.min() <= 1                             # equal node counts
+    parts = [P.partition_mesh(conn, n, world, r, owner=owner) for r in range(world)]
     owned = np.concatenate([p.local_nodes[:p.n_owned] for p in parts])
-    assert np.array_equal(owned, np.arange(n))
+    assert np.array_equal(np.sort(owned), np.arange(n))
+    for p in parts:
+        assert np.all(np.diff(p.owned_nodes) > 0)                     # owned rows in ascending global order
     covered = np.zeros(len(conn), dtype=int)
     for p in parts:
         assert np.all(np.diff(p.elem_ids) > 0)                       # ascending global element order
         assert np.array_equal(p.local_nodes[p.conn_local], conn[p.elem_ids])
         ghosts = p.local_nodes[p.n_owned:]
-        assert np.all(np.diff(ghosts) > 0)
+        for k in range(len(p.nbr)):                                   # grouped by owner, ascending inside a group
+            run = ghosts[p.recv_start[k] - p.n_owned:p.recv_start[k] - p.n_owned + p.recv_count[k]]
+            assert np.all(np.diff(run) > 0)
         covered[p.elem_ids] += 1
         # what I receive from s is exactly what s sends me, in the same order
         for k, s in enumerate(p.nbr):
@@ -57,8 +66,9 @@ def test_owned_rows_of_local_assembly_equal_global_rows():
     n = len(mesh.points)
     E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
     K, _ = S.frame_assemble(mesh.points, conn, es, props, E, nu)
-    for r in range(3):
-        p = P.partition_mesh(conn, n, 3, r)
+    owner = P.box_owner(mesh.points, 3)
+    for r in range(6):
+        p = P.partition_mesh(conn, n, 3, r % 3, owner=owner if r >= 3 else None)
         Kl, _ = S.frame_assemble(mesh.points[p.local_nodes], p.conn_local, es[p.elem_ids], props, E, nu)
         ld = p.local_dofs(6)
         rows = slice(0, 6 * p.n_owned)
