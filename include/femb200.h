@@ -238,10 +238,11 @@ int femb_frame_batch_solve(femb_handle* h, int64_t n_models, int64_t n_elem, con
 int femb_host_register(femb_handle* h, void* ptr, int64_t bytes);
 int femb_host_unregister(femb_handle* h, void* ptr);
 
-/* ---- one large mesh across GPUs: row-block (node-slab) partition ----------------------------
+/* ---- one large mesh across GPUs: row-block partition ------------------------------------------
  * One process (and one handle) per GPU.  Each rank passes femb_*_set_mesh its LOCAL mesh: the
- * owned nodes first (a contiguous range of the global node order), then the ghost nodes its
- * elements touch (sorted by global id, hence grouped by owner rank), and every element that
+ * owned nodes first (ascending global id: a coordinate-bisection box, a contiguous slab of the
+ * node order, or any other set), then the ghost nodes its elements touch (grouped by owner rank,
+ * ascending global id inside a group), and every element that
  * touches an owned node; femb_assemble / femb_set_bc work on that local mesh unchanged ("owner
  * computes": no assembly communication; owned rows equal the single-GPU rows bit for bit).
  * fem_calculator_b200/partition.py builds these inputs from the global arrays the reference
@@ -265,18 +266,21 @@ int femb_dist_set_halo(femb_handle* h, int64_t n_owned_nodes, int32_t n_nbr, con
 int femb_dist_solve_static(femb_handle* h, const femb_solve_opts* opts, int minus_f, double* u_owned,
                            double* reactions_owned, femb_stats* stats);
 /* Optional peer-memory (NVLink) exchange for the iteration: after femb_set_bc + femb_dist_set_halo
- * every rank exports two CUDA-IPC handles (128 bytes: its CG direction vector and its mailbox), the
+ * every rank exports one CUDA-IPC handle (128-byte blob: the handle of ONE allocation holding its mailboxes, its CG
+ * direction vector and its flag-in-data slots, plus two sizes the peers need to address it), the
  * host gathers the world*128 bytes and every rank imports them together with, per neighbour k, the
  * first local node index of THIS rank's nodes in neighbour k's ghost numbering.  The distributed
- * PCG then replaces ncclSend/ncclRecv + ncclAllReduce by two small kernels that store straight into
- * the peers' memory (see csrc/dist.cu); without the import it uses NCCL.  Up to 8 ranks.        */
+ * PCG then stores halo entries, reduction scalars and coarse residuals straight into the peers' memory from inside
+ * its kernels (csrc/dist.cu, csrc/lines.cu) instead of calling ncclSend/ncclRecv + ncclAllReduce; without the import
+ * it uses NCCL (Jacobi only).  Up to 8 ranks.                                                                    */
 int femb_dist_p2p_export(femb_handle* h, uint8_t* handles128);
 /* Line preconditioner on the partition (FEMB_PRECOND_LINES / AUTO in femb_dist_solve_static; needs the peer-memory
  * exchange): every rank runs femb_symbolic_line_bundles on the GLOBAL mesh and passes the rows of its LOCAL nodes
  * (owned, then ghosts): node_bundle / node_line / node_pos (3, n_local) and node_dir (3, n_local, 3), plus the global
- * n_coarse and fam_off (4).  Lines are cut where they leave the rank's slab; a bundle's residual is the sum of the
- * ranks' partial residuals (one all-gather of n_coarse doubles per iteration through the peers' mail areas) and the
- * bundle Galerkin matrices are summed over the ranks once per assembled K.  Call after femb_dist_set_halo.        */
+ * n_coarse and fam_off (4).  Lines are cut where they leave the rank's owned set; a bundle's residual is the sum of the
+ * partial residuals of the ranks that own a piece of it (stored by their line groups into every rank's flag-in-data
+ * slots, added in rank order) and the bundle Galerkin matrices are summed over the ranks once per assembled K.
+ * Call after femb_dist_set_halo.                                                                                  */
 int femb_dist_set_lines(femb_handle* h, int32_t n_coarse, const int32_t* fam_off, const int32_t* node_bundle,
                         const int32_t* node_line, const int32_t* node_pos, const double* node_dir);
 int femb_dist_p2p_import(femb_handle* h, const uint8_t* all_handles, const int64_t* peer_ghost_start);
