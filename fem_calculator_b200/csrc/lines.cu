@@ -1004,6 +1004,8 @@ static int ensure_line_numeric(femb_handle* h) {
   FEMB_CUDA(h, cudaGetLastError());
   if (trace) cudaEventRecord(te[1], h->stream);
   bool all_ok = true;
+  std::vector<cudaEvent_t> tev;                     // FEMB_TRACE: Galerkin kernel | sum over ranks | inversion, per family
+  auto mark = [&]() { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); tev.push_back(e); } };
   for (int f = 0; f < kLnMaxFam && (all_ok || dist); ++f) {
     const int nf = S.fam_off[f + 1] - S.fam_off[f];
     if (nf == 0) continue;
@@ -1012,15 +1014,18 @@ static int ensure_line_numeric(femb_handle* h) {
     FEMB_CUDA(h, cudaMemsetAsync(h->coarse_aug.p, 0, (size_t)m * m * sizeof(double), h->stream));
     FEMB_CUDA(h, cudaMemsetAsync(h->ln_gal.p, 0, (size_t)n_pad * n_pad * sizeof(double), h->stream));
     const int n_rg = T.range_off[f + 1] - T.range_off[f];
+    mark();
     if (n_rg > 0) {
       const size_t smem = (size_t)nf * sizeof(double);
       ln_galerkin_kernel<<<n_rg, kLnThreads, smem, h->stream>>>(T, f, h->rowptr.p, h->colidx.p, h->Kvals.p, h->ln_gal.p, n_pad);
       h->launches++;
     }
+    mark();
     if (dist) {                                     // rows of the other ranks' bundles: sum over the ranks
       rc = dist_allreduce(h, h->ln_gal.p, (int)(n_pad * n_pad));
       if (rc) return rc;
     }
+    mark();
     ln_aug_fill_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)n_pad), 256, 0, h->stream>>>(h->ln_gal.p, h->coarse_aug.p, nf, n_pad);
     h->launches++;
     FEMB_CUDA(h, cudaGetLastError());
@@ -1030,6 +1035,7 @@ static int ensure_line_numeric(femb_handle* h) {
     double* inv_f = h->ln_inv.p + h->ln_inv_off[f];
     if (dist && (f % h->dist_world) != h->dist_rank) {
       FEMB_CUDA(h, cudaMemsetAsync(inv_f, 0, (size_t)n_pad * n_pad * sizeof(double), h->stream));
+      mark();
       continue;
     }
     bool ok = false;
@@ -1042,6 +1048,7 @@ static int ensure_line_numeric(femb_handle* h) {
     } else {
       all_ok = all_ok && ok;
     }
+    mark();
   }
   if (dist) {
     int64_t tot = 0;
@@ -1068,6 +1075,11 @@ static int ensure_line_numeric(femb_handle* h) {
     fprintf(stderr, "[femb trace] line preconditioner setup: %d lines, %lld entries, coarse dim %d (%d/%d/%d), coverage %.3f; "
             "line factors %.3f ms, Galerkin + inversion %.3f ms\n", S.n_lines, (long long)S.n_entries, S.n_coarse,
             S.fam_off[1] - S.fam_off[0], S.fam_off[2] - S.fam_off[1], S.fam_off[3] - S.fam_off[2], S.coverage, a, b);
+    double part[3] = {0.0, 0.0, 0.0};
+    for (size_t k = 0; k + 3 < tev.size(); k += 4)
+      for (int j = 0; j < 3; ++j) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[k + j], tev[k + j + 1]); part[j] += ms; }
+    fprintf(stderr, "[femb trace]   Galerkin kernels %.3f ms, their sums over the ranks %.3f ms, inversions on this rank %.3f ms\n", part[0], part[1], part[2]);
+    for (auto e : tev) cudaEventDestroy(e);
   }
   h->line_num_ok = all_ok;
   h->line_failed = !all_ok;
