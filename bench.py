@@ -453,6 +453,13 @@ def run_single(args):
                           "omega_max_rad_s": float(np.sqrt(lam[-1])), "coarse_dim": int(mst.get("coarse_dim", 0)),
                           "method": "block shift-invert Krylov (block 2), line-preconditioned PCG as K^-1 (factors built once), "
                                     "full re-orthogonalisation, thick restart"}
+        m_ach = it_bytes * mst["iterations"] / (mst["device_ms"] * 1e-3) / 1e9
+        extra["modal"]["roofline"] = {"kernel": "ln_pcg_mega_kernel<false> as K^-1 of the shift-invert iteration", "bound": "hbm",
+                                      "achieved": m_ach, "peak": peak, "unit": "GB/s", "frac": m_ach / peak,
+                                      "bytes_per_iteration": it_bytes,
+                                      "note": "algorithmic bytes of the PCG iterations over the WHOLE modal device time (Krylov "
+                                              "bookkeeping, orthogonalisation, Ritz step and launch gaps included): a lower bound "
+                                              "on what the kernel achieves"}
         if not args.no_cpu_baseline:
             extra["modal"]["cpu_baseline"] = leg_modal_cpu()
     m.close()
