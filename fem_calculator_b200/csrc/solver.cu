@@ -482,12 +482,23 @@ int launch_spmv_rows(femb_handle* h, const double* x, double* y, int64_t n, bool
 int setup_bc_vectors(femb_handle* h) {
   const int64_t n = h->ndof;
   FEMB_CUDA(h, h->b.alloc(n));
-  FEMB_CUDA(h, h->x.alloc(n));
-  FEMB_CUDA(h, h->r.alloc(n));
-  FEMB_CUDA(h, h->z.alloc(n));
-  FEMB_CUDA(h, h->p.alloc(n));
-  FEMB_CUDA(h, h->q.alloc(n));
-  FEMB_CUDA(h, h->s.alloc(n));
+  // the six Krylov vectors share ONE allocation: the persistent PCG kernel pins that range in the L2 (access policy
+  // window, lines.cu) so that the vectors survive the table streams of the other phases
+  const size_t stride = ((size_t)n + 31) / 32 * 32;
+  if (h->vec_pool.n != 6 * stride || !h->vec_pool.p) {
+    for (DevBuf<double>* v : {&h->x, &h->r, &h->z, &h->p, &h->q, &h->s})
+      if (!(v == &h->z && h->p2p_z_exported && h->z.p == h->p2p_z_exported && h->z.n == (size_t)n)) v->release();
+    FEMB_CUDA(h, h->vec_pool.alloc(6 * stride));
+  }
+  {
+    int k = 0;
+    for (DevBuf<double>* v : {&h->x, &h->r, &h->z, &h->p, &h->q, &h->s}) {
+      double* slot = h->vec_pool.p + stride * (size_t)(k++);
+      // (a row-block rank's z lives in its exported peer-memory allocation, dist.cu: it stays there)
+      if (v == &h->z && h->p2p_z_exported && h->z.p == h->p2p_z_exported && h->z.n == (size_t)n) continue;
+      v->adopt(slot, (size_t)n);
+    }
+  }
   FEMB_CUDA(h, h->partials.alloc((size_t)h->num_sms * 8 * 4));
   FEMB_CUDA(h, h->scal.alloc(Scal::COUNT));
   FEMB_CUDA(h, h->flags.alloc(Flag::COUNT));
