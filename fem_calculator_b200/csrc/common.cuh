@@ -221,7 +221,7 @@ struct femb_handle {
   int32_t ln_n_ranges = 0, ln_max_len = 0;
   int32_t ln_grp_count = 0;       // line groups the current ln_grp_ptr / ln_grp_lines were built for
   femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle,
-      ln_bundle_ids, ln_bundle_cnt, ln_line_range, ln_rank_mask, ln_ent_of, ln_grp_ptr, ln_grp_lines;
+      ln_bundle_ids, ln_bundle_cnt, ln_rank_mask, ln_ent_of, ln_grp_ptr, ln_grp_lines;
   femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_ae, ln_yle, ln_rb, ln_rbt, ln_yb, ln_inv, ln_gal, ln_node_dir, ln_line_sum;
   femb::DevBuf<double> vec_pool;                 // x | r | z | p | q | s (setup_bc_vectors)
   femb::DevBuf<unsigned long long> mega_state;   // persistent PCG kernel: grid barrier words + per-phase clocks

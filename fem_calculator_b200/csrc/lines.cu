@@ -17,9 +17,11 @@
 // CPU study behind the choice (scipy, tests/prototypes/line_precond_study.py): 56x56x54 lattice, rtol 1e-12:
 // Jacobi 6,931 iterations, rigid-body two-level 1,324, this form 199 with 2,296 coarse unknowns.
 //
-// Iteration (Chronopoulos-Gear, linked reductions as in pcg_common.cuh — no float atomics, fixed-order
-// sums, bit-reproducible):  operator (ebe.cu) -> ln_update (p, q, x, r; ||r||^2) -> ln_solve (line solves,
-// bundle residuals) -> ln_coarse (dense products) -> ln_prolong (z = M^-1 r; (r, z)).
+// Iteration (Chronopoulos-Gear; no float atomics, fixed-order sums, bit-reproducible): ONE persistent cooperative
+// kernel, ln_pcg_mega_kernel, with five phases per iteration separated by grid barriers — operator (ebe.cuh) ->
+// vector update (p, q, x, r; ||r||^2; axial residuals of the line entries) -> line solves + bundle residuals ->
+// coarse products -> prolongation (z = M^-1 r; (r, z)).  On a row-block partition the same kernel exchanges halo,
+// reduction scalars and bundle residuals with the other GPUs from inside the launch (flag-in-data stores).
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -33,8 +35,6 @@
 namespace femb {
 
 constexpr int kLnThreads = 128;        // ln_solve / setup CTAs: 4 warps = 4 lines at a time
-constexpr int kLnVecThreads = 256;     // update / prolong kernels
-constexpr int kLnCoarseWarps = 8;
 constexpr double kLnRidge = 1e-10;     // relative ridge on the diagonal of the bundle Galerkin matrices
 constexpr int kLnTargetPerFamily = 768;
 
@@ -49,7 +49,6 @@ struct LnDev {
   const int32_t* bundle_ids;    // coarse index of every bundle_ptr range (null: identity; row-block partition: the local subset)
   const double* node_dir;       // (F, N, 3) caller-provided unit line directions (null: end-to-end from the coordinates)
   int32_t range_off[kLnMaxFam + 1];   // bundle_ptr ranges of each family
-  int32_t coarse_blk_off[kLnMaxFam + 1];   // CTAs of ln_coarse_kernel per family (kLnCoarseWarps rows each)
   double* ent_w;                // (n_entries, 3) masked line direction at the entry's node
   double* node_w;               // (F, N, 3)      the same, indexed by (family, node); zero where the node has no line
   double* fac;                  // (n_entries, 3) {1/delta, forward coefficient, backward coefficient}
@@ -62,7 +61,6 @@ struct LnDev {
   double* line_sum;             // (n_lines) axial residual sum of every line (persistent kernel: bundles are summed from these)
   int32_t max_len;              // longest line (entries)
   int32_t* bundle_cnt;          // (bundle_ptr ranges) lines of each bundle finished in the current pass (persistent kernel)
-  const int32_t* line_range;    // (n_lines) bundle_ptr range of every line
   const int32_t* grp_ptr;       // (line groups of the grid + 1) persistent kernel: the lines of every line group ...
   const int4* grp_lines;        // (n_lines) ... {line, first entry, entries, bundle range}, balanced by length on the host (ln_assign_lines)
   double* yb;                   // (n_coarse) coarse solution
@@ -279,7 +277,7 @@ __device__ __forceinline__ void ln_scan_affine_down(double& F, double& G, int la
 // POST (row-block partition): the group that completes a bundle stores the rank's partial residual straight into every
 // rank's flag-in-data slot [this rank][parity][bundle] (lane p -> rank p) instead of into rb.
 template <int THREADS, int LW, bool POST>
-__device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, const double* r, int cta, int ncta,
+__device__ __forceinline__ void ln_solve_lines_flat(const LnDev& T, int cta, int ncta,
                                                     const P2PDev* pd = nullptr, long long seq = 0) {
   constexpr int CH = kLnMaxLen / LW;                  // rounds (LW = 16: 8 rounds cover 128 entries)
   constexpr int NG = THREADS / LW;
@@ -571,7 +569,7 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       // flag-in-data slots; right behind its own lines every CTA adds the contributing ranks' slots of a share of the
       // bundles in rank order as they land -> rbt.  No barrier in between: the slots synchronise themselves.
       const P2PDev* pd = A.p2p;
-      ln_solve_lines_flat<kMegaThreads, 16, true>(T, A.r, cta, ncta, pd, seq);
+      ln_solve_lines_flat<kMegaThreads, 16, true>(T, cta, ncta, pd, seq);
       const int par = (int)(seq & 1);
       const unsigned flag = (unsigned)seq;
       // (the grid's LAST CTAs take the polls: the first ones hold the longest lines of the length-balanced assignment)
@@ -590,7 +588,7 @@ ln_pcg_mega_kernel(const MegaArgs A) {
       }
       if (clk1) A.phase_ns[5] += mega_now() - tp0;
     } else {
-      ln_solve_lines_flat<kMegaThreads, 16, false>(T, A.r, cta, ncta);
+      ln_solve_lines_flat<kMegaThreads, 16, false>(T, cta, ncta);
     }
     work_mark(2); mega_barrier(A.bar, nb); work_start();
     lap(2);
@@ -876,13 +874,6 @@ static int upload_line_tables(femb_handle* h) {
     FEMB_CUDA(h, h->ln_yb.alloc((size_t)S.n_coarse));
     FEMB_CUDA(h, h->ln_line_sum.alloc((size_t)S.n_lines));
     FEMB_CUDA(h, h->ln_bundle_cnt.alloc((size_t)std::max<size_t>(1, S.bundle_ptr.size())));
-    {
-      std::vector<int32_t> lr((size_t)S.n_lines, 0);
-      for (size_t rg = 0; rg + 1 < S.bundle_ptr.size(); ++rg)
-        for (int32_t l = S.bundle_ptr[rg]; l < S.bundle_ptr[rg + 1]; ++l) lr[l] = (int32_t)rg;
-      FEMB_CUDA(h, upload(h->ln_line_range, lr, h->stream));
-      FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
-    }
     FEMB_CUDA(h, cudaMemsetAsync(h->ln_bundle_cnt.p, 0, h->ln_bundle_cnt.bytes(), h->stream));
     h->ln_max_len = 0;
     for (int32_t a = 0; a < S.n_lines; ++a) h->ln_max_len = std::max(h->ln_max_len, S.line_ptr[a + 1] - S.line_ptr[a]);
@@ -945,13 +936,11 @@ static LnDev ln_dev(const femb_handle* h) {
   T.node_bundle = h->ln_node_bundle.p; T.bundle_ids = h->ln_bundle_ids.p; T.node_dir = h->ln_node_dir.p;
   T.ent_w = h->ln_ent_w.p; T.node_w = h->ln_node_w.p; T.fac = h->ln_fac.p;
   T.ae = h->ln_ae.p; T.yle = h->ln_yle.p; T.ent_of = h->ln_ent_of.p; T.rb = h->ln_rb.p; T.rbt = h->line_dist ? h->ln_rbt.p : h->ln_rb.p; T.yb = h->ln_yb.p; T.inv = h->ln_inv.p;
-  T.grp_ptr = h->ln_grp_ptr.p; T.grp_lines = reinterpret_cast<const int4*>(h->ln_grp_lines.p); T.rank_mask = h->ln_rank_mask.p; T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p; T.line_range = h->ln_line_range.p;
+  T.grp_ptr = h->ln_grp_ptr.p; T.grp_lines = reinterpret_cast<const int4*>(h->ln_grp_lines.p); T.rank_mask = h->ln_rank_mask.p; T.line_sum = h->ln_line_sum.p; T.max_len = h->ln_max_len; T.bundle_cnt = h->ln_bundle_cnt.p;
   for (int f = 0; f < kLnMaxFam; ++f) { T.inv_off[f] = h->ln_inv_off[f]; T.fam_pad[f] = h->ln_fam_pad[f]; }
-  T.coarse_blk_off[0] = 0;
   for (int f = 0; f <= kLnMaxFam; ++f) {
     T.fam_off[f] = S.fam_off[f];
     T.range_off[f] = h->ln_range_off[f];
-    if (f > 0) T.coarse_blk_off[f] = T.coarse_blk_off[f - 1] + (S.fam_off[f] - S.fam_off[f - 1] + kLnCoarseWarps - 1) / kLnCoarseWarps;
   }
   T.n_lines = S.n_lines; T.n_coarse = S.n_coarse; T.n_nodes = (int32_t)h->n_nodes;
   T.omega = 1.0;
