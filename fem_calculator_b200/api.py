@@ -264,9 +264,11 @@ class DistFrameModel(FrameModel):
         """Re-upload the partition's fixed-DOF list and load vector (the host -> device part of a step)."""
         self.set_bc(*self._bc_local)
 
-    def modal_dist(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6):
-        """(lambda (k,), phi_owned (n_owned_dof, k), stats) — collective: every rank calls it."""
-        o = L.EigOpts(k, block, max_iter, 0, rtol, lambda_min, 0, 0, 0.0)
+    def modal_dist(self, k=20, rtol=1e-8, max_iter=5000, block=0, lambda_min=1e-6, precond=L.PRECOND_AUTO):
+        """(lambda (k,), phi_owned (n_owned_dof, k), stats) — collective: every rank calls it.  ``precond``: the
+        preconditioner of the inner distributed PCG solves (AUTO / LINES: the line preconditioner on the partition
+        when ``setup`` handed the line tables over and the peer-memory exchange is on; else Jacobi)."""
+        o = L.EigOpts(k, block, max_iter, 0, rtol, lambda_min, int(precond), 0, 0.0)
         st = L.Stats()
         lam = np.zeros(k)
         phi = np.zeros((k, self.n_owned_dof))

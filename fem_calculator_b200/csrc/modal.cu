@@ -230,6 +230,8 @@ static int solve_block(ModalWs& ws, int method, const femb_solve_opts& so, const
       if (rc) return rc;
       st->iterations += s1.iterations;
       st->spmv_launches += s1.spmv_launches;
+      st->precond_used = s1.precond_used;
+      st->coarse_dim = s1.coarse_dim;
       FEMB_CUDA(h, cudaMemsetAsync(X + (size_t)q * ws.n, 0, ws.n * 8, h->stream));
       FEMB_CUDA(h, cudaMemcpyAsync(X + (size_t)q * ws.n, h->x.p, ws.n_own * 8, cudaMemcpyDeviceToDevice, h->stream));
     }

@@ -12,6 +12,7 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 nx, ny, nz = [int(v) for v in args[:3]]
 k = int(args[3]) if len(args) > 3 else 20
 check = "--check" in sys.argv
+precond = L.PRECOND_JACOBI if "--jacobi" in sys.argv else L.PRECOND_AUTO
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -37,18 +38,20 @@ use_p2p = world > 1 and not os.environ.get("FEMB_DIST_NO_P2P")
 m = DistFrameModel(local)
 part = m.setup(mesh.points, mesh.cells_dict["line"], es, props, E, E / (2 * (1 + nu)), fixed, f, rank, world, uid, all_gather=_gather if use_p2p else None)
 t0 = time.time()
-lam, phi, st = m.modal_dist(k=k) if world > 1 else m.modal(k=k)
+lam, phi, st = m.modal_dist(k=k, precond=precond) if world > 1 else m.modal(k=k)
 wall = time.time() - t0
 if rank == 0:
     print(json.dumps({"lattice": [nx, ny, nz], "ndof": len(f), "world": world, "k": k, "modes": len(lam), "device_ms": st["device_ms"], "wall_s": wall,
-                      "pcg_iterations": st["iterations"], "rel_residual": st["rel_residual"],
+                      "pcg_iterations": st["iterations"], "rel_residual": st["rel_residual"], "precond_used": st.get("precond_used"),
                       "omega": [float(x) for x in np.sqrt(lam[:4])]}), flush=True)
 if check:
     from oracle import ref_sparse as S
     if world > 1:
         parts = [None] * world
-        dist.all_gather_object(parts, phi)
-        phig = np.concatenate(parts, axis=0)
+        dist.all_gather_object(parts, (part.owned_nodes, phi))
+        phig = np.zeros((len(f), phi.shape[1]))
+        for nodes, ph in parts:                        # owned rows of every rank, in its ascending global node order
+            phig.reshape(-1, 6, phi.shape[1])[nodes] = ph.reshape(-1, 6, phi.shape[1])
     else:
         phig = phi
     if rank == 0:

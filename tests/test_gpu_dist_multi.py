@@ -46,3 +46,18 @@ def test_four_rank_box_partition_matches_oracle():
         pytest.skip("needs 4 GPUs")
     out = _run(4, (14, 12, 9), "lines", 29631)
     assert out["world"] == 4 and out["precond_used"] == 5, out
+
+
+def test_two_rank_modal_on_the_line_preconditioner_matches_oracle():
+    """femb_modal on a 2-rank box partition with the line-preconditioned persistent PCG behind K^-1: eigenvalues
+    against the oracle's generalized pencil (1e-8), M-orthonormal shapes (scripts/dist_modal.py --check)."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(ROOT, "scripts", "dist_modal.py"), "12", "9", "8", "6", "--check"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    assert "check: max rel eigenvalue error" in r.stdout
+    assert out["modes"] == 6 and out["precond_used"] == 5, out
