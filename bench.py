@@ -594,13 +594,28 @@ def run_multi(args):
     e2e_s = maxr(time.perf_counter() - t0)
     h2d, d2h = L.io_bytes()
     exch = "peer memory (CUDA IPC over NVLink), fused into the kernels" if d.p2p else "NCCL"
+    roofline = None
+    try:        # the dominant kernel of every rank: the persistent PCG kernel on its part of the frame
+        peak, peak_src = peaks()
+        _, itb = d.time_kernel(11, 0, 1)
+        ach = itb * last["iterations"] / (last["device_ms"] * 1e-3) / 1e9
+        roofline = {"kernel": "ln_pcg_mega_kernel<true> — the persistent line-preconditioned PCG kernel on this rank's part of the "
+                              "frame, halo / scalar / coarse-residual exchanges inside the launch",
+                    "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "bytes_per_iteration_per_gpu": itb, "iterations": last["iterations"],
+                    "note": "per GPU (rank 0): algorithmic bytes of one iteration on the rank's local mesh x iterations over the "
+                            "device time of its whole distributed solve (numeric setup of the preconditioner included); the "
+                            "difference to the N = 1 figure is exchange wait and the fixed barrier cost of a smaller local problem"}
+    except Exception as e:      # a measurement convenience must never take the benchmark line down
+        roofline = {"error": str(e)}
     d.close()
     out = {"metric": "static_solve_dof_per_s", "value": n_free / (ms_per_step * 1e-3), "unit": "DOF/s", "n_gpus": world,
            "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(f"one frame, contiguous node slabs over {world} GPUs (row-block PCG; halo of the search direction and "
                                  f"the reduction scalars / coarse residuals exchanged through {exch})", lat=lat),
-           "clocks": clocks, "gpu_launches": int(launches),
+           "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+           "cpu_baseline": None,      # the CPU legs run at N = 1 only (see that line and --impl reference)
            "e2e": {"value": n_free / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": e2e_s * 1e3, "api": "api.DistFrameModel: per-rank partition loads / BC from host numpy, assemble, "
                    "distributed solve, owned u and reactions back to the host (bytes are this rank's)"},
