@@ -38,7 +38,14 @@ def _group_nodes(mesh, element_type, name):
         if phys is None:
             return np.array([], dtype=int)
         target = mesh.field_data[name][0]
-        return np.unique(np.asarray(cells)[np.asarray(phys) == target].flatten())
+        sel = np.asarray(cells)[np.asarray(phys) == target].reshape(-1)
+        if sel.size == 0 or sel.min() < 0:
+            return np.unique(sel)
+        # sorted unique node ids without a sort: mark and collect (the groups of a 1M-DOF frame hold 1e4-1e5 vertices
+        # and this runs inside every run_simulation call)
+        mark = np.zeros(int(sel.max()) + 1, dtype=bool)
+        mark[sel] = True
+        return np.flatnonzero(mark).astype(sel.dtype, copy=False)
     except (KeyError, IndexError):
         return np.array([], dtype=int)
 
@@ -69,7 +76,11 @@ def frame_section_table(mesh, section_data, props_fn):
     tags = np.asarray(mesh.cell_data_dict["gmsh:physical"]["line"])
     names = list(props_map.keys())
     lut = {}
-    for t in np.unique(tags):
+    if tags.size and tags.dtype.kind in "iu" and tags.min() >= 0 and tags.max() < (1 << 22):
+        present = np.flatnonzero(np.bincount(tags))            # distinct tags without sorting half a million entries
+    else:
+        present = np.unique(tags)
+    for t in present:
         name = gid2name.get(int(t))
         if not name or name not in props_map:
             return None, None, name
