@@ -235,10 +235,11 @@ class BeamAnalysisB200:
 
     def close(self):
         """Release the GPU handle kept between runs."""
-        m = getattr(self, "_femb_model", None)
-        if m is not None:
-            m.close()
-            self._femb_model = None
+        for name in ("_femb_model", "_elem_model"):
+            m = getattr(self, name, None)
+            if m is not None:
+                m.close()
+                setattr(self, name, None)
 
     def bc_nodes_indexing(self, element_type, bc_name):
         return _group_nodes(self.mesh, element_type, bc_name)
@@ -308,14 +309,13 @@ class BeamAnalysisB200:
         return eigenvalues[idx].cpu().numpy(), V[:, idx].cpu().numpy()
 
     def _one_element(self, L_, E, G, props, rho, want_k, want_m):
-        m = FrameModel(self.device)
-        try:
-            pts = np.array([[0.0, 0.0, 0.0], [float(L_), 0.0, 0.0]])
-            m.set_mesh(pts, np.array([[0, 1]]), np.zeros(1, dtype=np.int32), np.asarray(props, dtype=np.float64), E, G, rho)
-            ke, me = m.elements(want_k, want_m)
-        finally:
-            m.close()
-        return ke, me
+        # one small handle kept for the helper calls (creating a CUDA handle per 12x12 matrix cost ~100 ms a call)
+        m = getattr(self, "_elem_model", None)
+        if m is None or getattr(m, "_h", None) is None:
+            m = self._elem_model = FrameModel(self.device)
+        pts = np.array([[0.0, 0.0, 0.0], [float(L_), 0.0, 0.0]])
+        m.set_mesh(pts, np.array([[0, 1]]), np.zeros(1, dtype=np.int32), np.asarray(props, dtype=np.float64), E, G, rho)
+        return m.elements(want_k, want_m)
 
     def get_timoshenko_stiffness_matrix(self, L, E, G, A, I_x, I_y, J, kappa_y, kappa_z):
         """BeamSolver.py:646 — local 12x12 stiffness, evaluated by the CUDA element kernel on
