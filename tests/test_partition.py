@@ -88,7 +88,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _dist_pcg_worker(rank, world, port, out_dir):
+def _dist_pcg_worker(rank, world, port, out_dir, kind="slabs"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -98,7 +98,7 @@ def _dist_pcg_worker(rank, world, port, out_dir):
     conn = mesh.cells_dict["line"]
     n = len(mesh.points)
     E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
-    p = P.partition_mesh(conn, n, world, rank)
+    p = P.partition_mesh(conn, n, world, rank, owner=P.box_owner(mesh.points, world) if kind == "boxes" else None)
     Kl, _ = S.frame_assemble(mesh.points[p.local_nodes], p.conn_local, es[p.elem_ids], props, E, nu)
     fixed_l, f_l = P.localize_bc(p, 6, fixed, f, n)
     nloc, no = Kl.shape[0], 6 * p.n_owned
@@ -149,19 +149,23 @@ def _dist_pcg_worker(rank, world, port, out_dir):
         red[1] = r[:no] @ z[:no]; red[2] = r[:no] @ r[:no]
         its += 1
     np.save(os.path.join(out_dir, f"u_{rank}.npy"), x[:no])
+    np.save(os.path.join(out_dir, f"nodes_{rank}.npy"), p.owned_nodes)
     np.save(os.path.join(out_dir, f"its_{rank}.npy"), np.array([its]))
     dist.destroy_process_group()
 
 
-def test_distributed_pcg_gloo_world2(tmp_path):
+@pytest.mark.parametrize("kind", ["slabs", "boxes"])
+def test_distributed_pcg_gloo_world2(tmp_path, kind):
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(_dist_pcg_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_dist_pcg_worker, args=(world, _free_port(), str(tmp_path), kind), nprocs=world, join=True)
     mesh, es, props, fixed, f = _case()
     E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
     K, _ = S.frame_assemble(mesh.points, mesh.cells_dict["line"], es, props, E, nu)
     free = np.setdiff1d(np.arange(len(f)), fixed)
     uo, _ = S.solve_static(K, f, fixed, free, method="direct")
-    u = np.concatenate([np.load(tmp_path / f"u_{r}.npy") for r in range(world)])
+    u = np.zeros(len(f))
+    for r in range(world):                                             # owned rows of rank r, ascending global node order
+        u.reshape(-1, 6)[np.load(tmp_path / f"nodes_{r}.npy")] = np.load(tmp_path / f"u_{r}.npy").reshape(-1, 6)
     assert np.linalg.norm(u - uo) <= 1e-10 * np.linalg.norm(uo)
     assert int(np.load(tmp_path / "its_0.npy")[0]) == int(np.load(tmp_path / "its_1.npy")[0]) > 10
