@@ -149,7 +149,8 @@ def run_reference(args):
     if rank != 0:
         return
     from fem_calculator_b200 import meshgen
-    from oracle import cpu_baseline as CB
+    from oracle import cpu_baseline as CB, native
+    native.use_all_cores()                  # torchrun exports OMP_NUM_THREADS=1 to its workers
     mesh, sec, bc, es, props, fixed, f = build_case()
     s = CB.lattice_static_solve(mesh, es, props, bc, meshgen.E_STEEL, meshgen.NU_STEEL, rtol=RTOL)
     v = s["n_free"] / s["t_total"]
@@ -173,7 +174,8 @@ def leg_parity_and_cpu(local):
     """40x40x38 lattice: GPU solve (AUTO = production preconditioner configuration) vs the oracle's CPU solve."""
     from fem_calculator_b200 import _lib as L, meshgen
     from fem_calculator_b200.api import FrameModel
-    from oracle import cpu_baseline as CB
+    from oracle import cpu_baseline as CB, native
+    native.use_all_cores()
     E, nu = meshgen.E_STEEL, meshgen.NU_STEEL
     mesh, sec, bc, es, props, fixed, f = build_case(lattice=SLICE)
     m = FrameModel(local)

@@ -25,6 +25,16 @@ int femb_oracle_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm of bench.py (rank 0 under torchrun at N > 1)
+ * asks for the host's cores explicitly */
+void femb_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* y = A x, CSR, rows split across threads */
 static void spmv(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data, const double* x, double* y) {
 #pragma omp parallel for schedule(static)

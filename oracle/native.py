@@ -41,6 +41,21 @@ def threads() -> int:
     return int(load().femb_oracle_threads())
 
 
+def use_all_cores() -> int:
+    """Let the OpenMP CG use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to
+    1 for its workers).  Returns the thread count."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib = load()
+    lib.femb_oracle_set_threads.argtypes = [C.c_int]
+    lib.femb_oracle_set_threads.restype = None
+    lib.femb_oracle_set_threads(int(n))
+    return threads()
+
+
 def pcg_jacobi(A, b, rtol=1e-13, max_iter=200_000):
     """Jacobi-PCG on a scipy CSR matrix with all host cores.  Returns (x, dict(iterations, rel_residual, flag))."""
     lib = load()
