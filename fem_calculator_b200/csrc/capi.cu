@@ -77,6 +77,11 @@ void femb_destroy(femb_handle* h) {
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
+  for (int f = 0; f < femb::kLnMaxFam; ++f) {
+    if (h->ln_stream[f]) cudaStreamDestroy(h->ln_stream[f]);
+    if (h->ln_ev_done[f]) cudaEventDestroy(h->ln_ev_done[f]);
+  }
+  if (h->ln_ev_start) cudaEventDestroy(h->ln_ev_start);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

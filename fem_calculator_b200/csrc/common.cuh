@@ -223,6 +223,11 @@ struct femb_handle {
   femb::DevBuf<int32_t> ln_line_ptr, ln_line_bundle, ln_bundle_ptr, ln_ent_node, ln_ent_blk_diag, ln_ent_blk_next, ln_node_bundle,
       ln_bundle_ids, ln_bundle_cnt, ln_rank_mask, ln_ent_of, ln_grp_ptr, ln_grp_lines;
   femb::DevBuf<double> ln_ent_w, ln_node_w, ln_fac, ln_ae, ln_yle, ln_rb, ln_rbt, ln_yb, ln_inv, ln_gal, ln_node_dir, ln_line_sum;
+  // line preconditioner setup: one stream, work matrix and Galerkin buffer per family (the three inversions overlap)
+  cudaStream_t ln_stream[femb::kLnMaxFam] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ln_ev_start = nullptr, ln_ev_done[femb::kLnMaxFam] = {nullptr, nullptr, nullptr};
+  femb::DevBuf<double> ln_aug_f[femb::kLnMaxFam], ln_gal_f[femb::kLnMaxFam];
+  femb::DevBuf<int> ln_status;
   femb::DevBuf<double> vec_pool;                 // x | r | z | p | q | s (setup_bc_vectors)
   femb::DevBuf<unsigned long long> mega_state;   // persistent PCG kernel: grid barrier words + per-phase clocks
 
@@ -339,6 +344,7 @@ int dist_set_lines(femb_handle* h, int32_t n_coarse, const int32_t* fam_off, con
                    const int32_t* node_line, const int32_t* node_pos, const double* node_dir);
 bool dist_lines_applicable(femb_handle* h, const femb_solve_opts& o, bool fused_p2p);
 int ebe_pair_aux(femb_handle* h);
+int coarse_invert_async(femb_handle* h, cudaStream_t stream, double* aug, int64_t n_pad, double* inv, int* status_dev);
 int dist_lines_setup(femb_handle* h);
 int dist_lines_solve(femb_handle* h, const femb_solve_opts& o, const double* d_b, femb_stats* st);
 double lines_iteration_bytes(const femb_handle* h);

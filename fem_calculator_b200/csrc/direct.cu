@@ -712,6 +712,26 @@ __global__ void coarse_extract_kernel(const double* __restrict__ aug, int64_t ld
   inv[i * n_pad + j] = -aug[(n_pad + r) * ld + n_pad + c];
 }
 
+// the same elimination enqueued on `stream` without a host round trip: *status_dev (zeroed by the caller) counts
+// non-positive pivots; used by the line preconditioner's setup to run its three inversions on three streams
+int coarse_invert_async(femb_handle* h, cudaStream_t stream, double* aug, int64_t n_pad, double* inv, int* status_dev) {
+  const int64_t m = 2 * n_pad;
+  const size_t smem = (size_t)2 * kCB * kCBLd * sizeof(double);
+  FEMB_CUDA(h, cudaFuncSetAttribute(chol_syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned nt = (unsigned)(n_pad / kCB);
+  for (int64_t k0 = 0; k0 < n_pad; k0 += kCB) {
+    chol_potrf_block_lean_kernel<<<1, kCB, 0, stream>>>(aug, m, (int)k0, status_dev);
+    const int64_t row_end = n_pad + k0 + kCB;
+    chol_trsm_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, stream>>>(aug, m, (int)k0, (int)row_end);
+    chol_syrk_dmma_kernel<<<dim3(nt, nt), 128, smem, stream>>>(aug, m, (int)k0);
+    h->launches += 3;
+  }
+  coarse_extract_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)n_pad), 256, 0, stream>>>(aug, m, n_pad, inv);
+  h->launches++;
+  FEMB_CUDA(h, cudaGetLastError());
+  return FEMB_OK;
+}
+
 int coarse_invert(femb_handle* h, double* aug, int64_t n_pad, double* inv, bool* ok) {
   const int64_t m = 2 * n_pad;
   DevBuf<int> status;

@@ -994,6 +994,54 @@ static int ensure_line_numeric(femb_handle* h) {
   FEMB_CUDA(h, cudaGetLastError());
   if (trace) cudaEventRecord(te[1], h->stream);
   bool all_ok = true;
+  // One GPU: the three families' chains (Galerkin matrix -> augmented matrix -> 12 panel steps of three small kernels
+  // -> extraction) are independent and latency bound (~0.6 ms each, launch after launch): they run on three streams
+  // forked from the handle's and joined back into it; one host round trip reads the three pivot counters.
+  // FEMB_LN_SETUP_STREAMS=0, FEMB_TRACE and the row-block partition (NCCL sums in between) keep the sequential path.
+  static const bool concurrent_ok = !(getenv("FEMB_LN_SETUP_STREAMS") && atoi(getenv("FEMB_LN_SETUP_STREAMS")) == 0);
+  if (!dist && !trace && concurrent_ok) {
+    for (int f = 0; f < kLnMaxFam; ++f) {
+      if (!h->ln_stream[f]) FEMB_CUDA(h, cudaStreamCreateWithFlags(&h->ln_stream[f], cudaStreamNonBlocking));
+      if (!h->ln_ev_done[f]) FEMB_CUDA(h, cudaEventCreateWithFlags(&h->ln_ev_done[f], cudaEventDisableTiming));
+    }
+    if (!h->ln_ev_start) FEMB_CUDA(h, cudaEventCreateWithFlags(&h->ln_ev_start, cudaEventDisableTiming));
+    FEMB_CUDA(h, h->ln_status.ensure(kLnMaxFam));
+    FEMB_CUDA(h, cudaMemsetAsync(h->ln_status.p, 0, sizeof(int) * kLnMaxFam, h->stream));
+    for (int f = 0; f < kLnMaxFam; ++f) {                      // allocations before the fork (cudaMalloc synchronises)
+      const int64_t n_pad = h->ln_fam_pad[f], m = 2 * n_pad;
+      if (S.fam_off[f + 1] == S.fam_off[f]) continue;
+      FEMB_CUDA(h, h->ln_aug_f[f].ensure((size_t)m * m));
+      FEMB_CUDA(h, h->ln_gal_f[f].ensure((size_t)n_pad * n_pad));
+    }
+    FEMB_CUDA(h, cudaEventRecord(h->ln_ev_start, h->stream));
+    for (int f = 0; f < kLnMaxFam; ++f) {
+      const int nf = S.fam_off[f + 1] - S.fam_off[f];
+      if (nf == 0) continue;
+      cudaStream_t st = h->ln_stream[f];
+      const int64_t n_pad = h->ln_fam_pad[f], m = 2 * n_pad;
+      FEMB_CUDA(h, cudaStreamWaitEvent(st, h->ln_ev_start, 0));
+      FEMB_CUDA(h, cudaMemsetAsync(h->ln_aug_f[f].p, 0, (size_t)m * m * sizeof(double), st));
+      FEMB_CUDA(h, cudaMemsetAsync(h->ln_gal_f[f].p, 0, (size_t)n_pad * n_pad * sizeof(double), st));
+      const int n_rg = T.range_off[f + 1] - T.range_off[f];
+      if (n_rg > 0) {
+        ln_galerkin_kernel<<<n_rg, kLnThreads, (size_t)nf * sizeof(double), st>>>(T, f, h->rowptr.p, h->colidx.p, h->Kvals.p, h->ln_gal_f[f].p, n_pad);
+        h->launches++;
+      }
+      ln_aug_fill_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)n_pad), 256, 0, st>>>(h->ln_gal_f[f].p, h->ln_aug_f[f].p, nf, n_pad);
+      h->launches++;
+      rc = coarse_invert_async(h, st, h->ln_aug_f[f].p, n_pad, h->ln_inv.p + h->ln_inv_off[f], h->ln_status.p + f);
+      if (rc) return rc;
+      FEMB_CUDA(h, cudaEventRecord(h->ln_ev_done[f], st));
+      FEMB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ln_ev_done[f], 0));
+    }
+    int* hs = reinterpret_cast<int*>(reinterpret_cast<char*>(h->pinned) + 1024);
+    FEMB_CUDA(h, cudaMemcpyAsync(hs, h->ln_status.p, sizeof(int) * kLnMaxFam, cudaMemcpyDeviceToHost, h->stream));
+    FEMB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < kLnMaxFam; ++f) all_ok = all_ok && (hs[f] == 0);
+    h->line_num_ok = all_ok;
+    h->line_failed = !all_ok;
+    return FEMB_OK;
+  }
   std::vector<cudaEvent_t> tev;                     // FEMB_TRACE: Galerkin kernel | sum over ranks | inversion, per family
   auto mark = [&]() { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); tev.push_back(e); } };
   for (int f = 0; f < kLnMaxFam && (all_ok || dist); ++f) {
